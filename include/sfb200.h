@@ -1,0 +1,214 @@
+/*
+ * sfb200.h -- C ABI of the B200-native diffusion-UNet hot path (libsfb200.so).
+ *
+ * Drop-in boundary.  The reference binds its native code as a pybind11/TORCH_LIBRARY module
+ * (`sfast._C`, /root/reference/src/sfast/csrc/main.cpp:13-24) whose operators take at::Tensor,
+ * allocate their outputs and launch on at::cuda::getCurrentCUDAStream().  This library is the
+ * replacement for the operators on the UNet hot path, re-cut as a plain C ABI:
+ *
+ *   - plain pointers and sizes only (no torch / ATen types);
+ *   - the CALLER owns every buffer (activations, packed weights, workspaces, tensor maps);
+ *   - the library never allocates device memory, never synchronises and only launches on the
+ *     stream it is given, so every entry point is CUDA-graph capturable;
+ *   - every entry point returns 0 on success or a negative sfb_status; sfb_last_error() gives a
+ *     thread-local message.  There is NO CPU / library fallback: a missing GPU path is an error.
+ *
+ * Reference operator each entry point replaces (file:line under /root/reference/src/sfast):
+ *   sfb_gemm            csrc/operators/cudnn/cudnn_convolution_impl.cc:890-987,1413-1433
+ *                       (cudnn_convolution_bias / _bias_add), csrc/operators/cublas/
+ *                       cublas_gemm.cpp:798-853,900-948 (cublas_lowp_linear / _linear_add),
+ *                       csrc/operators/cutlass/cutlass_dual_linear_kernel.cu:442-539
+ *                       (cutlass_linear_geglu_unified)
+ *   sfb_attention       libs/xformers/xformers_attention.py:26-63 (memory_efficient_attention)
+ *   sfb_group_norm_*    triton/ops/group_norm.py:126-165,272-320 (group_norm / group_norm_silu)
+ *   sfb_layer_norm      triton/ops/layer_norm.py:51-133
+ *   sfb_small_linear    csrc/operators/cublas/cublas_gemm.cpp:798-853 at M = batch rows
+ *   sfb_timestep_embed, sfb_conv_in, sfb_conv_out, sfb_upsample2x: aten ops the reference
+ *                       leaves untouched in the traced graph
+ */
+#ifndef SFB200_H_
+#define SFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_ABI_VERSION 1
+
+typedef void* sfb_stream_t; /* cudaStream_t */
+
+enum sfb_status {
+    SFB_OK = 0,
+    SFB_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+    SFB_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+    SFB_ERR_NO_DRIVER = -3, /* driver entry point unavailable */
+};
+
+enum sfb_dtype { SFB_F16 = 0, SFB_BF16 = 1 };
+
+int sfb_abi_version(void);
+const char* sfb_last_error(void);
+/* Number of kernel launches issued through this library since load (host-side counter). */
+uint64_t sfb_launch_count(void);
+
+/* ---- TMA tensor maps (host side; `out128` receives a 128-byte, 64-byte-aligned CUtensorMap) */
+
+/* Row-major 2-D matrix [rows, cols] of 16-bit elements, row pitch `pitch_elems`;
+ * box = [box_rows, 64 cols], 128-byte swizzle. */
+int sfb_tmap_2d(void* out128, const void* base, uint64_t rows, uint64_t cols,
+                uint64_t pitch_elems, uint32_t box_rows);
+
+/* NHWC activation [n, h, w, c] of 16-bit elements with channel pitch `pitch_elems`
+ * (>= c; lets a tensor live inside a wider concat buffer).  box = [box_n, box_h, box_w, 64 ch];
+ * `stride` (1 or 2) is the traversal stride along h and w (stride-2 convolution). */
+int sfb_tmap_nhwc(void* out128, const void* base, uint32_t n, uint32_t h, uint32_t w, uint32_t c,
+                  uint64_t pitch_elems, uint32_t box_n, uint32_t box_h, uint32_t box_w,
+                  uint32_t stride);
+
+/* ---- tcgen05 GEMM / implicit-GEMM convolution -------------------------------------------- */
+
+enum sfb_gemm_a_mode {
+    SFB_A_MATRIX = 0,  /* A is [M, K] row-major (linear layers, 1x1 convolutions) */
+    SFB_A_CONV3X3 = 1, /* A is an NHWC image; K = 9 * cin, padding 1, stride 1 or 2 */
+};
+
+enum sfb_epilogue {
+    SFB_EPI_STORE = 0, /* out[m, n] = acc + bias[n] + rowbias[img(m), n] + residual[m, n] */
+    SFB_EPI_GEGLU = 1, /* out[m, j] = (acc_v + b_v) * gelu(acc_g + b_g); weights tile-interleaved */
+    SFB_EPI_QKV = 2,   /* scatter columns into per-head Q / K ([bh, s, dp]) and V^T ([bh, d, sp]) */
+};
+
+typedef struct sfb_gemm_params {
+    const void* tmap_a; /* host pointer to a 128-byte tensor map */
+    const void* tmap_b; /* weights [N, K] row-major (K contiguous), box rows = 160 */
+    int32_t a_mode;
+    int32_t M, N, K;
+    int32_t dtype;
+    /* SFB_A_CONV3X3 geometry: OUTPUT image dims and the M-tile box */
+    int32_t img_n, img_h, img_w, cin, conv_stride, box_h, box_n;
+    /* split-K: >1 writes fp32 partials to `ws` ([splits, M, N]) and a second kernel reduces */
+    int32_t splits;
+    float* ws;
+    /* epilogue */
+    int32_t epi;
+    void* out;
+    int32_t ldo;
+    const float* bias;    /* [N] fp32 or NULL */
+    const float* rowbias; /* [M / rows_per_img, ld_rowbias] fp32 or NULL (time-embedding add) */
+    int32_t rows_per_img;
+    int32_t ld_rowbias;
+    const void* residual; /* [M, ldr] 16-bit or NULL */
+    int32_t ldr;
+    /* SFB_EPI_GEGLU: logical output width; weight rows are tile-interleaved: physical columns
+     * [160 j, 160 j + 80) are the value half and [160 j + 80, 160 j + 160) the gate half of
+     * output columns [80 j, 80 j + 80); N is the padded physical width (multiple of 160). */
+    int32_t geglu_n_out;
+    /* SFB_EPI_QKV */
+    void* q;
+    void* k;
+    void* vt;
+    int32_t heads, head_dim; /* column n -> which = n / (heads*head_dim) + which_base */
+    int32_t which_base;      /* 0: q,k,v   1: k,v (cross-attention K/V projection) */
+    int32_t seq;             /* tokens per batch item: row m -> (b, s) = (m / seq, m % seq) */
+    int32_t q_pitch;         /* element pitch of a Q/K row (64 / 128 / 192) */
+    int32_t q_rows;          /* rows allocated per (b, head) in the Q buffer */
+    int32_t k_rows;          /* rows allocated per (b, head) in the K buffer */
+    int32_t vt_rows;         /* rows per (b, head) in V^T (head_dim rounded up to 16) */
+    int32_t vt_pitch;        /* element pitch of a V^T row */
+} sfb_gemm_params;
+
+int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream);
+
+/* ---- tcgen05 flash attention: O = softmax(Q K^T * scale) V ------------------------------- */
+
+typedef struct sfb_attn_params {
+    const void* tmap_q;  /* 2-D map over Q  [bh * q_rows,  q_pitch], box 128 rows */
+    const void* tmap_k;  /* 2-D map over K  [bh * k_rows,  q_pitch], box 128 rows */
+    const void* tmap_vt; /* 2-D map over V^T [bh * vt_rows, vt_pitch], box vt_rows rows */
+    void* out;           /* [batch, seq_q, heads * head_dim] 16-bit */
+    int32_t batch, heads, head_dim;
+    int32_t seq_q, seq_kv;
+    int32_t q_rows, k_rows, vt_rows;
+    int32_t dtype;
+    float scale; /* 1 / sqrt(head_dim) */
+} sfb_attn_params;
+
+int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream);
+
+/* ---- normalisation ----------------------------------------------------------------------- */
+
+typedef struct sfb_gn_params {
+    const void* x;   /* NHWC [n, hw, c] 16-bit, channel pitch ldx */
+    void* y;         /* [n, hw, c] 16-bit, channel pitch ldy */
+    const float* gamma;
+    const float* beta;
+    float* stats;    /* [n, groups, 2] fp32 (sum, sum of squares); zeroed by sfb_group_norm_stats */
+    int32_t n, hw, c, ldx, ldy, groups;
+    float eps;
+    int32_t silu;    /* 1: y = silu(gn(x)) */
+    int32_t dtype;
+} sfb_gn_params;
+
+int sfb_group_norm_stats(const sfb_gn_params* p, sfb_stream_t stream);
+int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream);
+
+typedef struct sfb_ln_params {
+    const void* x; /* [rows, c] 16-bit, pitch ldx */
+    void* y;       /* [rows, c] 16-bit, pitch ldy */
+    const float* gamma;
+    const float* beta;
+    int32_t rows, c, ldx, ldy;
+    float eps;
+    int32_t dtype;
+} sfb_ln_params;
+
+int sfb_layer_norm(const sfb_ln_params* p, sfb_stream_t stream);
+
+/* ---- small / glue kernels ---------------------------------------------------------------- */
+
+/* out[b, :] = [cos(t_b f_i) | sin(t_b f_i)] (flip_sin_to_cos) or [sin | cos], 16-bit output */
+int sfb_timestep_embed(const float* t, int32_t batch, int32_t dim, int32_t flip_sin_to_cos,
+                       float freq_shift, void* out, int32_t ldo, int32_t dtype,
+                       sfb_stream_t stream);
+
+/* y[b, n] = act_out(sum_k act_in(x[b, k]) W[n, k] + bias[n] (+ add[b, n]));
+ * act: 0 none, 1 SiLU.  x 16-bit [batch, k]; W 16-bit [n, k]; y 16-bit (y16) or fp32 (y32). */
+typedef struct sfb_small_linear_params {
+    const void* x;
+    const void* w;
+    const float* bias;
+    const void* add16; /* optional 16-bit [batch, n] added before act_out */
+    void* y16;
+    float* y32;
+    int32_t batch, n, k, ldx, ldy;
+    int32_t act_in, act_out;
+    int32_t dtype;
+} sfb_small_linear_params;
+
+int sfb_small_linear(const sfb_small_linear_params* p, sfb_stream_t stream);
+
+/* 3x3 pad-1 convolution with tiny channel counts at the two ends of the UNet.
+ * conv_in:  x NCHW [n, cin<=8, h, w] 16-bit  -> y NHWC [n, h, w, cout] (channel pitch ldy)
+ * conv_out: x NHWC [n, h, w, cin] (pitch ldx) -> y NCHW [n, cout<=8, h, w] 16-bit
+ * w: 16-bit [cout, 3, 3, cin] (K-major, same packing as sfb_gemm); bias fp32. */
+int sfb_conv_in(const void* x, const void* w, const float* bias, void* y, int32_t n, int32_t h,
+                int32_t wd, int32_t cin, int32_t cout, int32_t ldy, int32_t dtype,
+                sfb_stream_t stream);
+int sfb_conv_out(const void* x, const void* w, const float* bias, void* y, int32_t n, int32_t h,
+                 int32_t wd, int32_t cin, int32_t cout, int32_t ldx, int32_t dtype,
+                 sfb_stream_t stream);
+
+/* nearest-neighbour 2x upsample, NHWC, 16-bit */
+int sfb_upsample2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                   int32_t ldx, int32_t ldy, sfb_stream_t stream);
+
+/* cudaMemsetAsync wrapper (graph capturable) */
+int sfb_memset(void* p, int32_t value, size_t bytes, sfb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H_ */

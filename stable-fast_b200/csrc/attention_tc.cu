@@ -1,0 +1,358 @@
+// tcgen05 flash attention for sm_100a:  O = softmax(Q K^T * scale) V, one (batch, head, 128-query
+// tile) per CTA, online softmax over 128-wide KV tiles.
+//
+// Warp roles (192 threads):
+//   warp 0      TMA producer: Q once, then a ring of K tiles and a ring of V^T tiles;
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:
+//                 S = Q K^T  (128 x 128, fp32, TMEM columns [0,128))
+//                 O += P V   (128 x DV,  fp32, TMEM columns [128,128+DV))
+//               QK^T of tile j+1 is issued as soon as the softmax warps have pulled S_j into
+//               registers, so it overlaps the exponentials of tile j;
+//   warps 2..5  softmax: thread = query row; tcgen05.ld S, running max / sum in fp32 (exp2 with
+//               scale*log2e folded), P written to shared memory in the 128-byte-swizzled K-major
+//               layout tcgen05.mma reads as its A operand, O rescaled in TMEM only when the
+//               running max moved; final O / l stored token-major for the out-projection GEMM.
+// All three operands are K-major: Q/K as [rows, head_dim] and V pre-transposed as V^T
+// [head_dim, seq] -- the QKV projection's epilogue (gemm_tc.cu, SFB_EPI_QKV) writes those
+// layouts directly, so no permute/copy kernels exist between projection and attention.
+//
+// Replaces xformers.ops.memory_efficient_attention as wrapped at
+// /root/reference/src/sfast/libs/xformers/xformers_attention.py:26-63.
+#include "common.cuh"
+#include "host.h"
+
+#include <string.h>
+
+namespace sfb {
+
+constexpr int kAttnThreads = 192;
+constexpr int kTileQ = 128;
+constexpr int kTileKV = 128;
+
+struct AttnArgs {
+    void* out;
+    int batch, heads, head_dim;
+    int seq_q, seq_kv;
+    int q_rows, k_rows, vt_rows;
+    int dtype;
+    float scale_log2;  // scale * log2(e)
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int DC, int DV, int KVS>
+struct AttnSmem {
+    static constexpr int kQBytes = DC * kTileQ * 128;
+    static constexpr int kKStage = DC * kTileKV * 128;
+    static constexpr int kVChunk = DV * 128;  // [DV rows x 64 kv columns]
+    static constexpr int kVStage = 2 * kVChunk;
+    static constexpr int kPBytes = 2 * kTileQ * 128;
+    static constexpr int kOffK = kQBytes;
+    static constexpr int kOffV = kOffK + KVS * kKStage;
+    static constexpr int kOffP = kOffV + KVS * kVStage;
+    static constexpr int kOffBar = kOffP + kPBytes;
+    static constexpr int kTotal = kOffBar + 256 + 1024;
+    static_assert(kVChunk % 1024 == 0, "V^T chunk must keep 1024-byte swizzle-atom alignment");
+};
+
+template <int DC, int DV, int KVS>
+__global__ void __launch_bounds__(kAttnThreads, (DC == 1) ? 2 : 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
+                    const __grid_constant__ CUtensorMap tma_k,
+                    const __grid_constant__ CUtensorMap tma_vt, const AttnArgs a) {
+    using L = AttnSmem<DC, DV, KVS>;
+    constexpr uint32_t kTmemCols = (128 + DV <= 256) ? 256 : 512;
+    constexpr uint32_t kColS = 0, kColO = 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + L::kOffK;
+    uint8_t* sV = smem + L::kOffV;
+    uint8_t* sP = smem + L::kOffP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + KVS;
+    uint64_t* v_full = k_empty + KVS;
+    uint64_t* v_empty = v_full + KVS;
+    uint64_t* s_full = v_empty + KVS;
+    uint64_t* s_free = s_full + 1;
+    uint64_t* p_full = s_free + 1;
+    uint64_t* pv_done = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q_tile = blockIdx.x;
+    const int bh = blockIdx.y;
+    const int n_kv = (a.seq_kv + kTileKV - 1) / kTileKV;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_k);
+        tma_prefetch_desc(&tma_vt);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < KVS; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 128);
+        mbar_init(p_full, 128);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, L::kQBytes);
+#pragma unroll
+            for (int c = 0; c < DC; ++c)
+                tma_load_2d(sQ + c * (kTileQ * 128), &tma_q, q_full, c * 64,
+                            bh * a.q_rows + q_tile * kTileQ);
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j % KVS;
+                const uint32_t ph = (j / KVS) & 1;
+                mbar_wait(&k_empty[st], ph ^ 1);
+                mbar_expect_tx(&k_full[st], L::kKStage);
+#pragma unroll
+                for (int c = 0; c < DC; ++c)
+                    tma_load_2d(sK + st * L::kKStage + c * (kTileKV * 128), &tma_k, &k_full[st],
+                                c * 64, bh * a.k_rows + j * kTileKV);
+                mbar_wait(&v_empty[st], ph ^ 1);
+                mbar_expect_tx(&v_full[st], L::kVStage);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    tma_load_2d(sV + st * L::kVStage + c * L::kVChunk, &tma_vt, &v_full[st],
+                                j * kTileKV + c * 64, bh * a.vt_rows);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const bool bf16 = a.dtype == SFB_BF16;
+            const uint32_t idesc_s = umma_idesc_f16(kTileQ, kTileKV, bf16);
+            const uint32_t idesc_o = umma_idesc_f16(kTileQ, DV, bf16);
+            const uint32_t tS = tmem_base + kColS;
+            const uint32_t tO = tmem_base + kColO;
+            auto issue_qk = [&](int j) {
+                const int st = j % KVS;
+#pragma unroll
+                for (int kk = 0; kk < DV / 16; ++kk) {
+                    const int c = kk / 4, k4 = kk % 4;
+                    const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ + c * (kTileQ * 128)));
+                    const uint64_t dk = umma_desc_k_sw128(
+                        smem_u32(sK + st * L::kKStage + c * (kTileKV * 128)));
+                    umma_f16_ss(tS, dq + (uint64_t)(k4 * 2), dk + (uint64_t)(k4 * 2), idesc_s,
+                                kk != 0);
+                }
+                umma_commit(&k_empty[st]);
+                umma_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_qk(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) {
+                    const int st1 = (j + 1) % KVS;
+                    mbar_wait(&k_full[st1], ((j + 1) / KVS) & 1);
+                    mbar_wait(s_free, j & 1);  // S_j is in the softmax warps' registers
+                    tc_fence_after();
+                    issue_qk(j + 1);
+                }
+                const int st = j % KVS;
+                mbar_wait(&v_full[st], (j / KVS) & 1);
+                mbar_wait(p_full, j & 1);  // P_j in smem, O rescaled
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < kTileKV / 16; ++kk) {
+                    const int c = kk / 4, k4 = kk % 4;
+                    const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + c * (kTileQ * 128)));
+                    const uint64_t dv =
+                        umma_desc_k_sw128(smem_u32(sV + st * L::kVStage + c * L::kVChunk));
+                    umma_f16_ss(tO, dp + (uint64_t)(k4 * 2), dv + (uint64_t)(k4 * 2), idesc_o,
+                                (j > 0) || (kk != 0));
+                }
+                umma_commit(&v_empty[st]);
+                umma_commit(pv_done);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + kColS;
+        const uint32_t tO = tmem_base + lane_base + kColO;
+        float m_run = -INFINITY;
+        float l_run = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t sraw[128];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t tmp[32];
+                tmem_ld32(tS + c * 32, tmp);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sraw[c * 32 + i] = tmp[i];
+            }
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(s_free);
+
+            // scaled scores in the log2 domain; mask the ragged tail of the last KV tile
+            const int kv0 = j * kTileKV;
+            const int n_valid = a.seq_kv - kv0;  // >= 1
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 128; ++i) {
+                float s = __uint_as_float(sraw[i]) * a.scale_log2;
+                if (i >= n_valid) s = -INFINITY;
+                sraw[i] = __float_as_uint(s);
+                mx = fmaxf(mx, s);
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
+            m_run = m_new;
+
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O stable
+                tc_fence_after();
+            }
+            float lsum = 0.f;
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {  // 16 groups of 8 kv columns -> one 16-byte store
+                float p[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    p[i] = fast_exp2(__uint_as_float(sraw[g * 8 + i]) - m_new);
+                    lsum += p[i];
+                }
+                uint4 pk;
+                pk.x = pack2(p[0], p[1], a.dtype);
+                pk.y = pack2(p[2], p[3], a.dtype);
+                pk.z = pack2(p[4], p[5], a.dtype);
+                pk.w = pack2(p[6], p[7], a.dtype);
+                const int chunk = g >> 3;  // which 64-column half
+                const int g8 = g & 7;
+                uint8_t* dst = sP + chunk * (kTileQ * 128) + r * 128 + ((g8 ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = pk;
+            }
+            l_run = l_run * alpha + lsum;
+
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+                for (int c = 0; c < DV / 16; ++c) {
+                    uint32_t o[16];
+                    tmem_ld16(tO + c * 16, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st16(tO + c * 16, o);
+                }
+                tmem_wait_st();
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // final: O / l
+        mbar_wait(pv_done, (n_kv - 1) & 1);
+        tc_fence_after();
+        const int srow = q_tile * kTileQ + r;
+        const bool valid = srow < a.seq_q;
+        const int b = bh / a.heads, h = bh % a.heads;
+        const float inv_l = 1.0f / l_run;
+        uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) +
+                         ((size_t)b * a.seq_q + (valid ? srow : 0)) * (a.heads * a.head_dim) +
+                         h * a.head_dim;
+#pragma unroll 1
+        for (int c = 0; c < DV / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tO + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int jv = 0; jv < 2; ++jv) {
+                const int d = c * 16 + jv * 8;
+                if (valid && d < a.head_dim) {
+                    uint4 pk;
+                    pk.x = pack2(__uint_as_float(o[jv * 8 + 0]) * inv_l, __uint_as_float(o[jv * 8 + 1]) * inv_l, a.dtype);
+                    pk.y = pack2(__uint_as_float(o[jv * 8 + 2]) * inv_l, __uint_as_float(o[jv * 8 + 3]) * inv_l, a.dtype);
+                    pk.z = pack2(__uint_as_float(o[jv * 8 + 4]) * inv_l, __uint_as_float(o[jv * 8 + 5]) * inv_l, a.dtype);
+                    pk.w = pack2(__uint_as_float(o[jv * 8 + 6]) * inv_l, __uint_as_float(o[jv * 8 + 7]) * inv_l, a.dtype);
+                    *reinterpret_cast<uint4*>(orow + d) = pk;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+template <int DC, int DV, int KVS>
+static int launch_attention(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
+    using L = AttnSmem<DC, DV, KVS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(attention_tc_kernel<DC, DV, KVS>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (err != cudaSuccess)
+            return fail(SFB_ERR_CUDA, "sfb_attention: smem attribute: %s", cudaGetErrorString(err));
+        attr_set = true;
+    }
+    CUtensorMap tq, tk, tv;
+    memcpy(&tq, p->tmap_q, sizeof(CUtensorMap));
+    memcpy(&tk, p->tmap_k, sizeof(CUtensorMap));
+    memcpy(&tv, p->tmap_vt, sizeof(CUtensorMap));
+    dim3 grid((p->seq_q + kTileQ - 1) / kTileQ, p->batch * p->heads);
+    attention_tc_kernel<DC, DV, KVS><<<grid, kAttnThreads, L::kTotal, stream>>>(tq, tk, tv, a);
+    return check_launch("sfb_attention");
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!p || !p->tmap_q || !p->tmap_k || !p->tmap_vt || !p->out)
+        return fail(SFB_ERR_INVALID, "sfb_attention: null argument");
+    if (p->head_dim % 8 || p->head_dim <= 0 || p->seq_q <= 0 || p->seq_kv <= 0)
+        return fail(SFB_ERR_INVALID, "sfb_attention: bad geometry");
+    const int dv = (p->head_dim + 15) / 16 * 16;
+    if (p->vt_rows != dv)
+        return fail(SFB_ERR_INVALID, "sfb_attention: vt_rows=%d must be head_dim rounded to 16 (%d)", p->vt_rows, dv);
+    AttnArgs a{};
+    a.out = p->out; a.batch = p->batch; a.heads = p->heads; a.head_dim = p->head_dim;
+    a.seq_q = p->seq_q; a.seq_kv = p->seq_kv; a.q_rows = p->q_rows; a.k_rows = p->k_rows;
+    a.vt_rows = p->vt_rows; a.dtype = p->dtype;
+    a.scale_log2 = p->scale * 1.4426950408889634f;
+    switch (dv) {
+        case 32: return launch_attention<1, 32, 2>(p, a, stream);
+        case 48: return launch_attention<1, 48, 2>(p, a, stream);
+        case 64: return launch_attention<1, 64, 2>(p, a, stream);
+        case 80: return launch_attention<2, 80, 2>(p, a, stream);
+        case 128: return launch_attention<2, 128, 2>(p, a, stream);
+        case 160: return launch_attention<3, 160, 1>(p, a, stream);
+        default:
+            return fail(SFB_ERR_INVALID, "sfb_attention: unsupported head_dim %d", p->head_dim);
+    }
+}

@@ -1,0 +1,461 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M, N] = A[M, K] * W[N, K]^T   (fp16/bf16 operands, fp32 accumulation in TMEM)
+//
+// One 128 x 160 output tile per CTA.  Warp roles (192 threads):
+//   warp 0      TMA producer: A tile (128 rows x 64 K) + W tile (160 rows x 64 K) per stage,
+//               both landing in 128-byte-swizzled K-major shared memory;
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per stage);
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (thread = row), fuse bias / time-embedding
+//               row bias / residual / GEGLU / QKV head scatter, store 16-byte vectors.
+// For the convolution the A tile of filter tap (kh, kw) is a *shifted NHWC box*: the tile's
+// 128 output pixels are a [box_n, box_h, W] block, so one 4-D TMA box load at
+// (c, kw-1, h0*stride+kh-1, n0) is exactly the im2col slice, and TMA's out-of-bounds zero fill
+// is the convolution's zero padding.  No im2col buffer, no index tables.
+//
+// Replaces: cudnn_convolution_bias(_add) (/root/reference/src/sfast/csrc/operators/cudnn/
+// cudnn_convolution_impl.cc:890-987), cublas_lowp_linear(_add) (csrc/operators/cublas/
+// cublas_gemm.cpp:798-853,900-948) and cutlass_linear_geglu (csrc/operators/cutlass/
+// cutlass_dual_linear_kernel.cu:442-525).
+#include "common.cuh"
+#include "host.h"
+
+#include <string.h>
+
+namespace sfb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 192;
+
+struct EpiArgs {
+    int epi;
+    int dtype;
+    int M, N;
+    void* out;
+    int ldo;
+    const float* bias;
+    const float* rowbias;
+    int rows_per_img;
+    int ld_rowbias;
+    const void* residual;
+    int ldr;
+    int geglu_n_out;
+    void* q;
+    void* k;
+    void* vt;
+    int heads, head_dim, which_base, seq, q_pitch, q_rows, k_rows, vt_rows, vt_pitch;
+};
+
+struct GemmArgs {
+    int a_mode;
+    int nkb_total;  // K / 64
+    int splits;
+    float* ws;
+    // conv geometry
+    int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
+    EpiArgs e;
+};
+
+// ---------------------------------------------------------------------------------------
+// epilogue building blocks (shared by the GEMM kernel and the split-K reduction kernel)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void add_bias8(const float* __restrict__ b, int n, float (&acc)[8]) {
+    const float4 b0 = *reinterpret_cast<const float4*>(b + n);
+    const float4 b1 = *reinterpret_cast<const float4*>(b + n + 4);
+    acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
+    acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&acc)[8], int bf16) {
+    uint4 o;
+    o.x = pack2(acc[0], acc[1], bf16);
+    o.y = pack2(acc[2], acc[3], bf16);
+    o.z = pack2(acc[4], acc[5], bf16);
+    o.w = pack2(acc[6], acc[7], bf16);
+    return o;
+}
+
+// 8 consecutive output columns [n, n+8) of row m.
+__device__ __forceinline__ void epi_store8(const EpiArgs& e, int m, int n, float (&acc)[8]) {
+    if (e.bias) add_bias8(e.bias, n, acc);
+    if (e.epi == SFB_EPI_STORE) {
+        if (e.rowbias) add_bias8(e.rowbias + (size_t)(m / e.rows_per_img) * e.ld_rowbias, n, acc);
+        if (e.residual) {
+            const uint4 r = *reinterpret_cast<const uint4*>(
+                reinterpret_cast<const uint16_t*>(e.residual) + (size_t)m * e.ldr + n);
+            float2 f;
+            f = unpack2(r.x, e.dtype); acc[0] += f.x; acc[1] += f.y;
+            f = unpack2(r.y, e.dtype); acc[2] += f.x; acc[3] += f.y;
+            f = unpack2(r.z, e.dtype); acc[4] += f.x; acc[5] += f.y;
+            f = unpack2(r.w, e.dtype); acc[6] += f.x; acc[7] += f.y;
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)m * e.ldo + n) =
+            pack8(acc, e.dtype);
+    } else {  // SFB_EPI_QKV
+        const int C = e.heads * e.head_dim;
+        const int which = n / C + e.which_base;
+        const int nn = n % C;
+        const int h = nn / e.head_dim;
+        const int d = nn % e.head_dim;
+        const int b = m / e.seq;
+        const int s = m % e.seq;
+        const size_t bh = (size_t)b * e.heads + h;
+        if (which == 0) {
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.q) +
+                                      (bh * e.q_rows + s) * e.q_pitch + d) = pack8(acc, e.dtype);
+        } else if (which == 1) {
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.k) +
+                                      (bh * e.k_rows + s) * e.q_pitch + d) = pack8(acc, e.dtype);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                store1(e.vt, (bh * e.vt_rows + d + i) * e.vt_pitch + s, acc[i], e.dtype);
+        }
+    }
+}
+
+// GEGLU: value / gate accumulators of 8 output columns [nout, nout+8); nv / ng are the
+// physical (tile-interleaved) column indices of the value / gate halves, used for the bias.
+__device__ __forceinline__ void epi_geglu8(const EpiArgs& e, int m, int nout, int nv, int ng,
+                                           float (&v)[8], float (&g)[8]) {
+    if (e.bias) {
+        add_bias8(e.bias, nv, v);
+        add_bias8(e.bias, ng, g);
+    }
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = v[i] * gelu_erf_f(g[i]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)m * e.ldo + nout) =
+        pack8(o, e.dtype);
+}
+
+// tile-local row r (0..127) of M-tile `tile` -> global row m; false if the row is padding
+__device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r, int& m) {
+    if (a.a_mode == SFB_A_MATRIX) {
+        m = tile * BM + r;
+        return m < a.e.M;
+    }
+    int n0, h0;
+    if (a.box_n == 1) {
+        n0 = tile / a.tiles_per_img;
+        h0 = (tile - n0 * a.tiles_per_img) * a.box_h;
+    } else {
+        n0 = tile * a.box_n;
+        h0 = 0;
+    }
+    const int w = r % a.img_w;
+    const int t = r / a.img_w;
+    const int dh = t % a.box_h;
+    const int dn = t / a.box_h;
+    const int n = n0 + dn, h = h0 + dh;
+    m = (n * a.img_h + h) * a.img_w + w;
+    return (n < a.img_n) && (h < a.img_h);
+}
+
+// ---------------------------------------------------------------------------------------
+// the GEMM kernel
+// ---------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const GemmArgs args) {
+    using L = GemmSmem<BN, STAGES>;
+    constexpr uint32_t kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * L::kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x;
+    const int m_tile = blockIdx.y;
+    const int split = blockIdx.z;
+    const int kb_begin = (int)(((long long)args.nkb_total * split) / args.splits);
+    const int kb_end = (int)(((long long)args.nkb_total * (split + 1)) / args.splits);
+    const int nkb = kb_end - kb_begin;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int n0 = 0, h0 = 0;
+            if (args.a_mode == SFB_A_CONV3X3) {
+                if (args.box_n == 1) {
+                    n0 = m_tile / args.tiles_per_img;
+                    h0 = (m_tile - n0 * args.tiles_per_img) * args.box_h;
+                } else {
+                    n0 = m_tile * args.box_n;
+                }
+            }
+            for (int i = 0; i < nkb; ++i) {
+                const int stage = i % STAGES;
+                const uint32_t phase = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                const int kb = kb_begin + i;
+                if (args.a_mode == SFB_A_MATRIX) {
+                    tma_load_2d(sA + stage * L::kABytes, &tma_a, &full_bar[stage], kb * BK,
+                                m_tile * BM);
+                } else {
+                    const int tap = kb / args.cpb;
+                    const int cc = kb - tap * args.cpb;
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    tma_load_4d(sA + stage * L::kABytes, &tma_a, &full_bar[stage], cc * BK,
+                                kw - 1, h0 * args.conv_stride + kh - 1, n0);
+                }
+                tma_load_2d(sB + stage * L::kBBytes, &tma_b, &full_bar[stage], kb * BK,
+                            n_tile * BN);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(BM, BN, args.e.dtype == SFB_BF16);
+            for (int i = 0; i < nkb; ++i) {
+                const int stage = i % STAGES;
+                const uint32_t phase = (i / STAGES) & 1;
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * L::kABytes));
+                const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::kBBytes));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // +32 bytes along K inside the 128-byte swizzle atom = +2 in the >>4 field
+                    umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                (i | k) != 0);
+                }
+                umma_commit(&empty_bar[stage]);
+            }
+            umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+    } else {
+        // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        int m;
+        const bool valid = tile_row_to_m(args, m_tile, r, m);
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const EpiArgs& e = args.e;
+        const int ncol0 = n_tile * BN;
+        if (args.splits > 1) {
+            float* wsrow = args.ws + ((size_t)split * e.M + (valid ? m : 0)) * e.N;
+#pragma unroll 1
+            for (int c = 0; c < BN / 16; ++c) {
+                uint32_t v[16];
+                tmem_ld16(trow + c * 16, v);
+                tmem_wait_ld();
+                const int n = ncol0 + c * 16;
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (n + j * 4 < e.N)
+                            *reinterpret_cast<uint4*>(wsrow + n + j * 4) =
+                                make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                    }
+                }
+            }
+        } else if (e.epi == SFB_EPI_GEGLU) {
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[16], g[16];
+                tmem_ld16(trow + c * 16, v);
+                tmem_ld16(trow + BN / 2 + c * 16, g);
+                tmem_wait_ld();
+                const int nout = n_tile * (BN / 2) + c * 16;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (valid && nout + j * 8 < e.geglu_n_out) {
+                        float fv[8], fg[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            fv[i] = __uint_as_float(v[j * 8 + i]);
+                            fg[i] = __uint_as_float(g[j * 8 + i]);
+                        }
+                        epi_geglu8(e, m, nout + j * 8, ncol0 + c * 16 + j * 8,
+                                   ncol0 + BN / 2 + c * 16 + j * 8, fv, fg);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < BN / 16; ++c) {
+                uint32_t v[16];
+                tmem_ld16(trow + c * 16, v);
+                tmem_wait_ld();
+                const int n = ncol0 + c * 16;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (valid && n + j * 8 < e.N) {
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
+                        epi_store8(e, m, n + j * 8, f);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// split-K reduction + epilogue: one thread per (row, 8 output columns)
+// ---------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) {
+    const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
+    const int groups = ncols / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)e.M * groups) return;
+    const int m = (int)(idx / groups);
+    const int n = (int)(idx % groups) * 8;
+    auto sum8 = [&](int col, float (&acc)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int s = 0; s < splits; ++s) {
+            const float* p = ws + ((size_t)s * e.M + m) * e.N + col;
+            const float4 a = *reinterpret_cast<const float4*>(p);
+            const float4 b = *reinterpret_cast<const float4*>(p + 4);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+    };
+    if (e.epi == SFB_EPI_GEGLU) {
+        const int tile = n / (BN / 2);
+        const int nv = tile * BN + (n - tile * (BN / 2));
+        const int ng = nv + BN / 2;
+        float v[8], g[8];
+        sum8(nv, v);
+        sum8(ng, g);
+        epi_geglu8(e, m, n, nv, ng, v, g);
+    } else {
+        float acc[8];
+        sum8(n, acc);
+        epi_store8(e, m, n, acc);
+    }
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
+    constexpr int BN = 160;
+    constexpr int STAGES = 3;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!p || !p->tmap_a || !p->tmap_b) return fail(SFB_ERR_INVALID, "sfb_gemm: null argument");
+    if (p->K <= 0 || p->K % BK) return fail(SFB_ERR_INVALID, "sfb_gemm: K=%d must be a multiple of 64", p->K);
+    if (p->N <= 0 || p->N % 8 || p->M <= 0) return fail(SFB_ERR_INVALID, "sfb_gemm: bad M=%d N=%d", p->M, p->N);
+    if (p->dtype != SFB_F16 && p->dtype != SFB_BF16) return fail(SFB_ERR_INVALID, "sfb_gemm: dtype");
+    GemmArgs a{};
+    a.a_mode = p->a_mode;
+    a.nkb_total = p->K / BK;
+    a.splits = p->splits < 1 ? 1 : p->splits;
+    if (a.splits > a.nkb_total) return fail(SFB_ERR_INVALID, "sfb_gemm: splits > K blocks");
+    if (a.splits > 1 && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
+    a.ws = p->ws;
+    int m_tiles;
+    if (p->a_mode == SFB_A_CONV3X3) {
+        if (p->cin <= 0 || p->cin % BK || p->K != 9 * p->cin)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: conv cin=%d K=%d", p->cin, p->K);
+        if (p->box_n * p->box_h * p->img_w != BM)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: conv M-tile box %dx%dx%d != 128", p->box_n, p->box_h, p->img_w);
+        if (p->box_n > 1 && p->box_h != p->img_h)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: multi-image box needs box_h == img_h");
+        if (p->M != p->img_n * p->img_h * p->img_w) return fail(SFB_ERR_INVALID, "sfb_gemm: conv M mismatch");
+        a.img_n = p->img_n; a.img_h = p->img_h; a.img_w = p->img_w;
+        a.cpb = p->cin / BK;
+        a.conv_stride = p->conv_stride;
+        a.box_h = p->box_h; a.box_n = p->box_n;
+        a.tiles_per_img = (p->img_h + p->box_h - 1) / p->box_h;
+        m_tiles = (p->box_n == 1) ? p->img_n * a.tiles_per_img : (p->img_n + p->box_n - 1) / p->box_n;
+    } else if (p->a_mode == SFB_A_MATRIX) {
+        m_tiles = (p->M + BM - 1) / BM;
+    } else {
+        return fail(SFB_ERR_INVALID, "sfb_gemm: a_mode");
+    }
+    EpiArgs& e = a.e;
+    e.epi = p->epi; e.dtype = p->dtype; e.M = p->M; e.N = p->N;
+    e.out = p->out; e.ldo = p->ldo; e.bias = p->bias; e.rowbias = p->rowbias;
+    e.rows_per_img = p->rows_per_img > 0 ? p->rows_per_img : 1;
+    e.ld_rowbias = p->ld_rowbias; e.residual = p->residual; e.ldr = p->ldr;
+    e.q = p->q; e.k = p->k; e.vt = p->vt; e.heads = p->heads; e.head_dim = p->head_dim;
+    e.which_base = p->which_base; e.seq = p->seq; e.q_pitch = p->q_pitch; e.q_rows = p->q_rows;
+    e.k_rows = p->k_rows; e.vt_rows = p->vt_rows; e.vt_pitch = p->vt_pitch;
+    if (p->epi == SFB_EPI_STORE) {
+        if (!p->out || p->ldo % 8) return fail(SFB_ERR_INVALID, "sfb_gemm: out/ldo");
+        if (p->residual && p->ldr % 8) return fail(SFB_ERR_INVALID, "sfb_gemm: ldr");
+    } else if (p->epi == SFB_EPI_GEGLU) {
+        if (!p->out || p->ldo % 8 || p->N % BN) return fail(SFB_ERR_INVALID, "sfb_gemm: geglu needs N %% 160 == 0");
+        if (p->geglu_n_out <= 0 || p->geglu_n_out % 8 || p->geglu_n_out > p->N / 2)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: geglu_n_out");
+        e.geglu_n_out = p->geglu_n_out;
+    } else if (p->epi == SFB_EPI_QKV) {
+        if (p->head_dim % 8 || p->heads <= 0 || p->seq <= 0 || p->N % (p->heads * p->head_dim))
+            return fail(SFB_ERR_INVALID, "sfb_gemm: qkv geometry");
+    } else {
+        return fail(SFB_ERR_INVALID, "sfb_gemm: epilogue mode");
+    }
+    using L = GemmSmem<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
+        attr_set = true;
+    }
+    dim3 grid((p->N + BN - 1) / BN, m_tiles, a.splits);
+    CUtensorMap ta, tb;
+    memcpy(&ta, p->tmap_a, sizeof(CUtensorMap));
+    memcpy(&tb, p->tmap_b, sizeof(CUtensorMap));
+    gemm_tc_kernel<BN, STAGES><<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, a);
+    int rc = check_launch("sfb_gemm");
+    if (rc) return rc;
+    if (a.splits > 1) {
+        const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
+        const long long items = (long long)e.M * (ncols / 8);
+        const int blocks = (int)((items + 255) / 256);
+        splitk_finish_kernel<BN><<<blocks, 256, 0, stream>>>(a.ws, a.splits, e);
+        rc = check_launch("sfb_gemm(split-K finish)");
+    }
+    return rc;
+}

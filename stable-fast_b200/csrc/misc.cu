@@ -1,0 +1,308 @@
+// Small kernels at the edges of the UNet: sinusoidal timestep embedding, batch-row linears
+// (time-embedding MLP and all per-resnet time projections: weight-bandwidth-bound GEMV-like work,
+// one warp per output column), the 4-channel conv_in / conv_out, nearest-neighbour upsampling.
+// These are the ops the reference leaves as plain aten kernels in its traced graph
+// (SURVEY.md section 8a, rows a6 (M = batch linears) and a11).
+#include "common.cuh"
+#include "host.h"
+
+namespace sfb {
+
+// ---------------------------------------------------------------------------------------
+// timestep embedding (diffusers get_timestep_embedding; fp32 math, 16-bit output)
+// ---------------------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int batch, int half, int flip,
+                                      float freq_shift, void* out, int ldo, int dtype) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * half) return;
+    const int b = idx / half, i = idx - b * half;
+    const float freq = expf(-9.210340371976184f * (float)i / ((float)half - freq_shift));
+    const float arg = t[b] * freq;
+    const float s = sinf(arg), c = cosf(arg);
+    const size_t row = (size_t)b * ldo;
+    if (flip) {
+        store1(out, row + i, c, dtype);
+        store1(out, row + half + i, s, dtype);
+    } else {
+        store1(out, row + i, s, dtype);
+        store1(out, row + half + i, c, dtype);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// batch-row linear: one warp per output column, up to 8 batch rows per pass
+// ---------------------------------------------------------------------------------------
+struct SmallLinearArgs {
+    const uint16_t* x;
+    const uint16_t* w;
+    const float* bias;
+    const uint16_t* add16;
+    uint16_t* y16;
+    float* y32;
+    int batch, n, k, ldx, ldy, act_in, act_out, dtype;
+};
+
+__global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearArgs a) {
+    const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int b0 = blockIdx.y * 8;
+    if (col >= a.n) return;
+    const int nb = min(8, a.batch - b0);
+    float acc[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+    const uint16_t* wr = a.w + (size_t)col * a.k;
+    for (int kv = lane; kv < a.k / 8; kv += 32) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(wr + kv * 8);
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        float wf[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack2(ww[i], a.dtype);
+            wf[2 * i] = f.x; wf[2 * i + 1] = f.y;
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b < nb) {
+                const uint4 xv = *reinterpret_cast<const uint4*>(a.x + (size_t)(b0 + b) * a.ldx + kv * 8);
+                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 f = unpack2(xw[i], a.dtype);
+                    if (a.act_in) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
+                    acc[b] += f.x * wf[2 * i] + f.y * wf[2 * i + 1];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+    }
+    if (lane == 0) {
+        for (int b = 0; b < nb; ++b) {
+            float v = acc[b] + (a.bias ? a.bias[col] : 0.f);
+            const size_t o = (size_t)(b0 + b) * a.ldy + col;
+            if (a.add16) v += load1(a.add16, o, a.dtype);
+            if (a.act_out) v = silu_f(v);
+            if (a.y32) a.y32[o] = v;
+            if (a.y16) store1(a.y16, o, v, a.dtype);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// conv_in: NCHW (cin <= 8) -> NHWC, 3x3 pad 1.  Weights staged as [9*cin][cout] in smem.
+// thread = (pixel slot, group of 8 output channels)
+// ---------------------------------------------------------------------------------------
+struct ConvEdgeArgs {
+    const uint16_t* x;
+    const uint16_t* w;
+    const float* bias;
+    uint16_t* y;
+    int n, h, wd, cin, cout, ld, dtype;
+};
+
+constexpr int kConvInPixelsPerBlock = 64;
+
+__global__ void __launch_bounds__(256) conv_in_kernel(const ConvEdgeArgs a) {
+    extern __shared__ uint16_t wsm[];  // [9*cin][cout]
+    const int kk = 9 * a.cin;
+    for (int i = threadIdx.x; i < kk * a.cout; i += blockDim.x) {
+        const int co = i / kk, j = i - co * kk;  // packed weight is [cout][kh][kw][cin]
+        wsm[j * a.cout + co] = a.w[i];
+    }
+    __syncthreads();
+    const int ngroups = a.cout / 8;
+    const int slots = blockDim.x / ngroups;
+    const int g = threadIdx.x % ngroups;
+    const int slot = threadIdx.x / ngroups;
+    if (slot >= slots) return;
+    const int total = a.n * a.h * a.wd;
+    const int p0 = blockIdx.x * kConvInPixelsPerBlock;
+    for (int p = p0 + slot; p < min(p0 + kConvInPixelsPerBlock, total); p += slots) {
+        const int xw = p % a.wd;
+        const int yh = (p / a.wd) % a.h;
+        const int img = p / (a.wd * a.h);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = a.bias ? a.bias[g * 8 + i] : 0.f;
+        for (int kh = 0; kh < 3; ++kh) {
+            const int iy = yh + kh - 1;
+            if (iy < 0 || iy >= a.h) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ix = xw + kw - 1;
+                if (ix < 0 || ix >= a.wd) continue;
+                for (int ci = 0; ci < a.cin; ++ci) {
+                    const float xv = load1(a.x, (((size_t)img * a.cin + ci) * a.h + iy) * a.wd + ix, a.dtype);
+                    const int j = (kh * 3 + kw) * a.cin + ci;
+                    const uint4 wv = *reinterpret_cast<const uint4*>(&wsm[j * a.cout + g * 8]);
+                    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = unpack2(ww[i], a.dtype);
+                        acc[2 * i] += xv * f.x;
+                        acc[2 * i + 1] += xv * f.y;
+                    }
+                }
+            }
+        }
+        uint4 o;
+        o.x = pack2(acc[0], acc[1], a.dtype); o.y = pack2(acc[2], acc[3], a.dtype);
+        o.z = pack2(acc[4], acc[5], a.dtype); o.w = pack2(acc[6], acc[7], a.dtype);
+        *reinterpret_cast<uint4*>(a.y + (size_t)p * a.ld + g * 8) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// conv_out: NHWC (pitch ld) -> NCHW (cout <= 8), 3x3 pad 1.  One warp per output pixel; lanes
+// split the 9 * cin/8 (tap, 8-channel vector) items; weights [cout][9][cin] staged in smem.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_out_kernel(const ConvEdgeArgs a) {
+    extern __shared__ uint16_t wsm[];  // [cout][9*cin]
+    const int kk = 9 * a.cin;
+    for (int i = threadIdx.x; i < (kk * a.cout) / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(wsm)[i] = reinterpret_cast<const uint4*>(a.w)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int total = a.n * a.h * a.wd;
+    const int nvec = a.cin / 8;
+    for (int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < total; p += gridDim.x * 8) {
+        const int xw = p % a.wd;
+        const int yh = (p / a.wd) % a.h;
+        const int img = p / (a.wd * a.h);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int it = lane; it < 9 * nvec; it += 32) {
+            const int tap = it / nvec, vec = it - tap * nvec;
+            const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
+            if (iy < 0 || iy >= a.h || ix < 0 || ix >= a.wd) continue;
+            const uint4 xv = *reinterpret_cast<const uint4*>(
+                a.x + (((size_t)img * a.h + iy) * a.wd + ix) * a.ld + vec * 8);
+            const uint32_t xw4[4] = {xv.x, xv.y, xv.z, xv.w};
+            float xf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2(xw4[i], a.dtype);
+                xf[2 * i] = f.x; xf[2 * i + 1] = f.y;
+            }
+#pragma unroll
+            for (int co = 0; co < 8; ++co) {
+                if (co < a.cout) {
+                    const uint4 wv = *reinterpret_cast<const uint4*>(&wsm[co * kk + tap * a.cin + vec * 8]);
+                    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = unpack2(ww[i], a.dtype);
+                        acc[co] += xf[2 * i] * f.x + xf[2 * i + 1] * f.y;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < 8; ++co) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+        }
+        if (lane < a.cout) {
+            float v = 0.f;
+#pragma unroll
+            for (int co = 0; co < 8; ++co) if (lane == co) v = acc[co];
+            v += a.bias ? a.bias[lane] : 0.f;
+            store1(a.y, (((size_t)img * a.cout + lane) * a.h + yh) * a.wd + xw, v, a.dtype);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// nearest-neighbour 2x upsample, NHWC, 16-byte vectors
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
+                                                         int n, int h, int w, int nvec, int ldx, int ldy) {
+    const long long total = (long long)n * 2 * h * 2 * w * nvec;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int vec = (int)(idx % nvec);
+        long long p = idx / nvec;
+        const int ox = (int)(p % (2 * w)); p /= (2 * w);
+        const int oy = (int)(p % (2 * h));
+        const int img = (int)(p / (2 * h));
+        const uint4 v = *reinterpret_cast<const uint4*>(
+            x + (((size_t)img * h + oy / 2) * w + ox / 2) * ldx + vec * 8);
+        *reinterpret_cast<uint4*>(y + (((size_t)img * 2 * h + oy) * 2 * w + ox) * ldy + vec * 8) = v;
+    }
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" int sfb_timestep_embed(const float* t, int32_t batch, int32_t dim, int32_t flip,
+                                  float freq_shift, void* out, int32_t ldo, int32_t dtype,
+                                  sfb_stream_t stream) {
+    if (!t || !out || dim % 2 || batch <= 0) return fail(SFB_ERR_INVALID, "timestep_embed: bad argument");
+    const int half = dim / 2;
+    const int total = batch * half;
+    timestep_embed_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        t, batch, half, flip, freq_shift, out, ldo, dtype);
+    return check_launch("sfb_timestep_embed");
+}
+
+extern "C" int sfb_small_linear(const sfb_small_linear_params* p, sfb_stream_t stream) {
+    if (!p || !p->x || !p->w || (!p->y16 && !p->y32)) return fail(SFB_ERR_INVALID, "small_linear: null argument");
+    if (p->k % 8 || p->ldx % 8 || p->batch <= 0 || p->n <= 0) return fail(SFB_ERR_INVALID, "small_linear: k/ldx must be multiples of 8");
+    SmallLinearArgs a{};
+    a.x = reinterpret_cast<const uint16_t*>(p->x);
+    a.w = reinterpret_cast<const uint16_t*>(p->w);
+    a.bias = p->bias; a.add16 = reinterpret_cast<const uint16_t*>(p->add16);
+    a.y16 = reinterpret_cast<uint16_t*>(p->y16); a.y32 = p->y32;
+    a.batch = p->batch; a.n = p->n; a.k = p->k; a.ldx = p->ldx; a.ldy = p->ldy;
+    a.act_in = p->act_in; a.act_out = p->act_out; a.dtype = p->dtype;
+    dim3 grid((p->n + 7) / 8, (p->batch + 7) / 8);
+    small_linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("sfb_small_linear");
+}
+
+extern "C" int sfb_conv_in(const void* x, const void* w, const float* bias, void* y, int32_t n,
+                           int32_t h, int32_t wd, int32_t cin, int32_t cout, int32_t ldy,
+                           int32_t dtype, sfb_stream_t stream) {
+    if (!x || !w || !y || cin <= 0 || cin > 8 || cout % 8 || cout / 8 > 256 || ldy % 8)
+        return fail(SFB_ERR_INVALID, "conv_in: unsupported geometry cin=%d cout=%d", cin, cout);
+    const size_t smem = (size_t)9 * cin * cout * 2;
+    if (smem > 48 * 1024) return fail(SFB_ERR_INVALID, "conv_in: weights exceed 48 KB of shared memory");
+    ConvEdgeArgs a{reinterpret_cast<const uint16_t*>(x), reinterpret_cast<const uint16_t*>(w), bias,
+                   reinterpret_cast<uint16_t*>(y), n, h, wd, cin, cout, ldy, dtype};
+    const int total = n * h * wd;
+    conv_in_kernel<<<(total + kConvInPixelsPerBlock - 1) / kConvInPixelsPerBlock, 256, smem,
+                     static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("sfb_conv_in");
+}
+
+extern "C" int sfb_conv_out(const void* x, const void* w, const float* bias, void* y, int32_t n,
+                            int32_t h, int32_t wd, int32_t cin, int32_t cout, int32_t ldx,
+                            int32_t dtype, sfb_stream_t stream) {
+    if (!x || !w || !y || cout <= 0 || cout > 8 || cin % 8 || ldx % 8)
+        return fail(SFB_ERR_INVALID, "conv_out: unsupported geometry cin=%d cout=%d", cin, cout);
+    const size_t smem = (size_t)9 * cin * cout * 2;
+    if (smem > 48 * 1024) return fail(SFB_ERR_INVALID, "conv_out: weights exceed 48 KB of shared memory");
+    ConvEdgeArgs a{reinterpret_cast<const uint16_t*>(x), reinterpret_cast<const uint16_t*>(w), bias,
+                   reinterpret_cast<uint16_t*>(y), n, h, wd, cin, cout, ldx, dtype};
+    const int total = n * h * wd;
+    int blocks = (total + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    conv_out_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("sfb_conv_out");
+}
+
+extern "C" int sfb_upsample2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                              int32_t ldx, int32_t ldy, sfb_stream_t stream) {
+    if (!x || !y || c % 8 || ldx % 8 || ldy % 8) return fail(SFB_ERR_INVALID, "upsample2x: bad argument");
+    const long long total = (long long)n * 4 * h * w * (c / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    upsample2x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(y), n, h, w, c / 8, ldx, ldy);
+    return check_launch("sfb_upsample2x");
+}

@@ -1,0 +1,244 @@
+// GroupNorm (+SiLU) and LayerNorm for NHWC / token-major 16-bit activations (HBM-bound kernels).
+//
+// GroupNorm is two passes, like the reference's NHWC path (/root/reference/src/sfast/triton/ops/
+// group_norm.py:126-165 stats, :272-320 apply) but with the statistics kept in fp32 end to end
+// (the reference round-trips mean/rstd through the input dtype, group_norm.py:405-416) and with
+// the stats grid sized to fill 148 SMs instead of groups*batch CTAs.
+// LayerNorm is one warp per row, row held in registers, two-pass mean/variance in fp32
+// (reference: triton/ops/layer_norm.py:51-133).
+#include "common.cuh"
+#include "host.h"
+
+namespace sfb {
+
+constexpr int kGnThreads = 512;
+
+struct GnArgs {
+    const uint16_t* x;
+    uint16_t* y;
+    const float* gamma;
+    const float* beta;
+    float* stats;
+    int n, hw, c, ldx, ldy, groups, cpg, nvec, rows_per_block;
+    float eps;
+    int silu, dtype;
+};
+
+// grid (blocks_per_img, n).  Thread (tx = vector column, ty = row slot) keeps per-channel
+// partial sums for its 8 channels over rows ty, ty+BY, ...; one shared-memory atomic per
+// (thread, group run) at the end, then one global atomic per (block, group, moment).
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
+    __shared__ float acc[2 * 64];
+    const int img = blockIdx.y;
+    const int by = kGnThreads / a.nvec;
+    const int tx = threadIdx.x % a.nvec;
+    const int ty = threadIdx.x / a.nvec;
+    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads) acc[i] = 0.f;
+    __syncthreads();
+    if (ty < by) {
+        float s[8], ss[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+        const int row0 = blockIdx.x * a.rows_per_block;
+        const int row1 = min(row0 + a.rows_per_block, a.hw);
+        const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
+        for (int row = row0 + ty; row < row1; row += by) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2(w[i], a.dtype);
+                s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
+                s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
+            }
+        }
+        // merge runs of equal group id among the 8 channels
+        int g_run = (tx * 8) / a.cpg;
+        float rs = 0.f, rss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (tx * 8 + i) / a.cpg;
+            if (g != g_run) {
+                atomicAdd(&acc[2 * g_run], rs);
+                atomicAdd(&acc[2 * g_run + 1], rss);
+                g_run = g; rs = 0.f; rss = 0.f;
+            }
+            rs += s[i]; rss += ss[i];
+        }
+        atomicAdd(&acc[2 * g_run], rs);
+        atomicAdd(&acc[2 * g_run + 1], rss);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads)
+        atomicAdd(&a.stats[(size_t)img * a.groups * 2 + i], acc[i]);
+}
+
+// grid (blocks_per_img, n): per-channel scale/shift for this image staged in shared memory, then
+// a streaming y = act(x * scale + shift) over the block's rows with 16-byte accesses.
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
+    extern __shared__ float sm[];
+    float* scale = sm;
+    float* shift = sm + a.c;
+    const int img = blockIdx.y;
+    const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
+    for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
+        const int g = ch / a.cpg;
+        const float sum = a.stats[((size_t)img * a.groups + g) * 2];
+        const float sq = a.stats[((size_t)img * a.groups + g) * 2 + 1];
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + a.eps);
+        const float sc = rstd * a.gamma[ch];
+        scale[ch] = sc;
+        shift[ch] = a.beta[ch] - mean * sc;
+    }
+    __syncthreads();
+    const int row0 = blockIdx.x * a.rows_per_block;
+    const int row1 = min(row0 + a.rows_per_block, a.hw);
+    const int items = (row1 - row0) * a.nvec;
+    const uint16_t* xb = a.x + ((size_t)img * a.hw + row0) * a.ldx;
+    uint16_t* yb = a.y + ((size_t)img * a.hw + row0) * a.ldy;
+    for (int it = threadIdx.x; it < items; it += kGnThreads) {
+        const int row = it / a.nvec;
+        const int vec = it - row * a.nvec;
+        const uint4 v = *reinterpret_cast<const uint4*>(xb + (size_t)row * a.ldx + vec * 8);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack2(w[i], a.dtype);
+            const int ch = vec * 8 + 2 * i;
+            float y0 = f.x * scale[ch] + shift[ch];
+            float y1 = f.y * scale[ch + 1] + shift[ch + 1];
+            if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+            o[i] = pack2(y0, y1, a.dtype);
+        }
+        *reinterpret_cast<uint4*>(yb + (size_t)row * a.ldy + vec * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+struct LnArgs {
+    const uint16_t* x;
+    uint16_t* y;
+    const float* gamma;
+    const float* beta;
+    int rows, c, ldx, ldy, nvec;
+    float eps;
+    int dtype;
+};
+
+constexpr int kLnMaxVec = 8;  // c <= 8 * 32 * 8 = 2048
+
+__global__ void __launch_bounds__(256) layer_norm_kernel(const LnArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.rows) return;
+    const uint16_t* xr = a.x + (size_t)warp * a.ldx;
+    float v[kLnMaxVec][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+        const int vec = lane + j * 32;
+        if (vec < a.nvec) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + vec * 8);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2(w[i], a.dtype);
+                v[j][2 * i] = f.x; v[j][2 * i + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)a.c;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+        if (lane + j * 32 < a.nvec) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; sq += d * d; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)a.c + a.eps);
+    uint16_t* yr = a.y + (size_t)warp * a.ldy;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+        const int vec = lane + j * 32;
+        if (vec < a.nvec) {
+            const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + vec * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + vec * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(a.beta + vec * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(a.beta + vec * 8 + 4);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                o[i] = pack2((v[j][2 * i] - mean) * rstd * g[2 * i] + b[2 * i],
+                             (v[j][2 * i + 1] - mean) * rstd * g[2 * i + 1] + b[2 * i + 1], a.dtype);
+            *reinterpret_cast<uint4*>(yr + vec * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+static int make_gn_args(const sfb_gn_params* p, GnArgs& a, int& blocks_per_img) {
+    if (!p || !p->x || !p->stats) return fail(SFB_ERR_INVALID, "group_norm: null argument");
+    if (p->c % 8 || p->ldx % 8 || p->groups <= 0 || p->groups > 64 || p->c % p->groups ||
+        p->c / 8 > kGnThreads || p->c > 4096)
+        return fail(SFB_ERR_INVALID, "group_norm: unsupported geometry c=%d groups=%d ldx=%d", p->c, p->groups, p->ldx);
+    a.x = reinterpret_cast<const uint16_t*>(p->x);
+    a.y = reinterpret_cast<uint16_t*>(p->y);
+    a.gamma = p->gamma; a.beta = p->beta; a.stats = p->stats;
+    a.n = p->n; a.hw = p->hw; a.c = p->c; a.ldx = p->ldx; a.ldy = p->ldy; a.groups = p->groups;
+    a.cpg = p->c / p->groups; a.nvec = p->c / 8; a.eps = p->eps; a.silu = p->silu; a.dtype = p->dtype;
+    const int by = kGnThreads / a.nvec;
+    // aim for >= 2 waves of 148 SMs while giving each thread a few rows
+    int want = (2 * 148 + p->n - 1) / p->n;
+    int max_blocks = (p->hw + by - 1) / by;
+    blocks_per_img = want < max_blocks ? want : max_blocks;
+    if (blocks_per_img < 1) blocks_per_img = 1;
+    a.rows_per_block = (p->hw + blocks_per_img - 1) / blocks_per_img;
+    blocks_per_img = (p->hw + a.rows_per_block - 1) / a.rows_per_block;
+    return SFB_OK;
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" int sfb_group_norm_stats(const sfb_gn_params* p, sfb_stream_t stream) {
+    GnArgs a{};
+    int bpi = 1;
+    int rc = make_gn_args(p, a, bpi);
+    if (rc) return rc;
+    gn_stats_kernel<<<dim3(bpi, p->n), kGnThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("sfb_group_norm_stats");
+}
+
+extern "C" int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream) {
+    GnArgs a{};
+    int bpi = 1;
+    int rc = make_gn_args(p, a, bpi);
+    if (rc) return rc;
+    if (!p->y || !p->gamma || !p->beta || p->ldy % 8) return fail(SFB_ERR_INVALID, "group_norm_apply: null/ldy");
+    gn_apply_kernel<<<dim3(bpi, p->n), kGnThreads, 2 * p->c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("sfb_group_norm_apply");
+}
+
+extern "C" int sfb_layer_norm(const sfb_ln_params* p, sfb_stream_t stream) {
+    if (!p || !p->x || !p->y || !p->gamma || !p->beta) return fail(SFB_ERR_INVALID, "layer_norm: null argument");
+    if (p->c % 8 || p->c > kLnMaxVec * 256 || p->ldx % 8 || p->ldy % 8 || p->rows <= 0)
+        return fail(SFB_ERR_INVALID, "layer_norm: unsupported geometry c=%d", p->c);
+    LnArgs a{};
+    a.x = reinterpret_cast<const uint16_t*>(p->x);
+    a.y = reinterpret_cast<uint16_t*>(p->y);
+    a.gamma = p->gamma; a.beta = p->beta; a.rows = p->rows; a.c = p->c; a.ldx = p->ldx; a.ldy = p->ldy;
+    a.nvec = p->c / 8; a.eps = p->eps; a.dtype = p->dtype;
+    const int blocks = (p->rows + 7) / 8;
+    layer_norm_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("sfb_layer_norm");
+}

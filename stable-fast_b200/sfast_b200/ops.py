@@ -1,0 +1,240 @@
+"""Launch descriptors for the C-ABI kernels.
+
+Each builder returns an :class:`Op`: a bound C entry point plus its argument block, created ONCE
+at plan-build time (pointers, tensor maps, geometry are all static), so that running or
+CUDA-graph-capturing a UNet step is a flat loop of ``op.launch(stream)`` calls.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (A_CONV3X3, A_MATRIX, EPI_GEGLU, EPI_QKV, EPI_STORE, AttnParams, GemmParams,
+                   GnParams, LnParams, SmallLinearParams, TensorMap, check)
+
+BM, BN, BK = 128, 160, 64
+NUM_SMS = 148
+
+
+def dtype_code(dt):
+    if dt == torch.float16:
+        return _lib.SFB_F16
+    if dt == torch.bfloat16:
+        return _lib.SFB_BF16
+    raise NotImplementedError(f"sfast_b200 computes in fp16/bf16 storage; got {dt}")
+
+
+class Act:
+    """A [n, h, w, c] (or [rows, c] with h = w = 1) activation view with channel pitch ``ld``
+    inside a (possibly wider) buffer, e.g. one half of a skip-concat buffer."""
+    __slots__ = ("buf", "off", "n", "h", "w", "c", "ld")
+
+    def __init__(self, buf, n, h, w, c, ld=None, off=0):
+        self.buf, self.n, self.h, self.w, self.c = buf, n, h, w, c
+        self.ld = c if ld is None else ld
+        self.off = off
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + self.off * self.buf.element_size()
+
+    @property
+    def rows(self):
+        return self.n * self.h * self.w
+
+    def tensor(self):
+        """torch view [n, h, w, c] (for tests / debugging)."""
+        flat = self.buf.view(-1)[self.off:]
+        return flat.as_strided((self.n, self.h, self.w, self.c),
+                               (self.h * self.w * self.ld, self.w * self.ld, self.ld, 1))
+
+
+class Op:
+    __slots__ = ("name", "fn", "args", "keep", "flops", "bytes")
+
+    def __init__(self, name, fn, args, keep, flops=0, nbytes=0):
+        self.name, self.fn, self.args, self.keep = name, fn, args, keep
+        self.flops, self.bytes = flops, nbytes
+
+    def launch(self, stream):
+        rc = self.fn(*self.args, stream)
+        if rc != 0:
+            check(rc, self.name)
+
+
+class DryMap:
+    """Stand-in for a TMA tensor map when a plan is built without a GPU (host-logic tests)."""
+    ptr = 0
+
+    def __init__(self, *geom):
+        self.geom = geom
+
+
+def matrix_map(ptr, rows, cols, pitch, box_rows, dry=False):
+    if dry:
+        return DryMap("2d", rows, cols, pitch, box_rows)
+    return TensorMap.matrix(ptr, rows, cols, pitch, box_rows)
+
+
+def nhwc_map(ptr, n, h, w, c, pitch, box_n, box_h, box_w, stride=1, dry=False):
+    if dry:
+        return DryMap("nhwc", n, h, w, c, pitch, box_n, box_h, box_w, stride)
+    return TensorMap.nhwc(ptr, n, h, w, c, pitch, box_n, box_h, box_w, stride)
+
+
+def conv_tile_box(ho, wo):
+    """[box_n, box_h] of the 128-pixel M tile for an output image of ho x wo (full-width rows)."""
+    if wo > BM or BM % wo:
+        raise NotImplementedError(f"conv output width {wo} must divide 128")
+    rows = BM // wo
+    if rows <= ho:
+        return 1, rows
+    if rows % ho:
+        raise NotImplementedError(f"conv output {ho}x{wo}: 128 is not a multiple of h*w")
+    return rows // ho, ho
+
+
+def choose_splits(m_tiles, n_tiles, nkb):
+    """Split-K factor: fill ~148 SMs when the output has few tiles (weight-bandwidth-bound
+    low-resolution layers), but keep >= 4 K-blocks per split."""
+    tiles = m_tiles * n_tiles
+    s = (NUM_SMS + tiles // 2) // tiles
+    return max(1, min(s, nkb // 4))
+
+
+def gemm_op(name, lib, *, a_map, b_map, M, N, K, dt, out=None, ldo=0, bias=None, rowbias=None,
+            rows_per_img=1, ld_rowbias=0, residual=None, ldr=0, epi=EPI_STORE, geglu_n_out=0,
+            conv=None, qkv=None, ws=None, splits=None, keep=()):
+    p = GemmParams()
+    p.tmap_a, p.tmap_b = a_map.ptr, b_map.ptr
+    p.a_mode = A_CONV3X3 if conv else A_MATRIX
+    p.M, p.N, p.K, p.dtype = M, N, K, dtype_code(dt)
+    if conv:
+        p.img_n, p.img_h, p.img_w = conv["n"], conv["h"], conv["w"]
+        p.cin, p.conv_stride = conv["cin"], conv["stride"]
+        p.box_n, p.box_h = conv["box_n"], conv["box_h"]
+        if p.box_n == 1:
+            m_tiles = p.img_n * ((p.img_h + p.box_h - 1) // p.box_h)
+        else:
+            m_tiles = (p.img_n + p.box_n - 1) // p.box_n
+    else:
+        m_tiles = (M + BM - 1) // BM
+    n_tiles = (N + BN - 1) // BN
+    nkb = K // BK
+    if splits is None:
+        splits = choose_splits(m_tiles, n_tiles, nkb)
+    if ws is None:
+        splits = 1
+    p.splits = splits
+    if splits > 1:
+        need = splits * M * N
+        if ws.numel() < need:
+            raise ValueError(f"{name}: split-K workspace too small ({ws.numel()} < {need})")
+        p.ws = ws.data_ptr()
+    p.epi = epi
+    p.out = out if isinstance(out, int) else (out.data_ptr() if out is not None else None)
+    p.ldo = ldo
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.rowbias = rowbias if isinstance(rowbias, int) else (
+        rowbias.data_ptr() if rowbias is not None else None)
+    p.rows_per_img, p.ld_rowbias = rows_per_img, ld_rowbias
+    p.residual = residual if isinstance(residual, int) else (
+        residual.data_ptr() if residual is not None else None)
+    p.ldr = ldr
+    p.geglu_n_out = geglu_n_out
+    if qkv:
+        p.q = qkv["q"].data_ptr() if qkv.get("q") is not None else None
+        p.k = qkv["k"].data_ptr() if qkv.get("k") is not None else None
+        p.vt = qkv["vt"].data_ptr() if qkv.get("vt") is not None else None
+        for f in ("heads", "head_dim", "which_base", "seq", "q_pitch", "q_rows", "k_rows",
+                  "vt_rows", "vt_pitch"):
+            setattr(p, f, qkv[f])
+    esz = 2
+    flops = 2 * M * N * K
+    nbytes = (M * K + N * K) * esz + M * (geglu_n_out if epi == EPI_GEGLU else N) * esz
+    op = Op(name, lib.sfb_gemm, (C.byref(p),), (p, a_map, b_map, out, bias, rowbias, residual, ws,
+                                               qkv, keep), flops, nbytes)
+    return op
+
+
+def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq_kv, q_rows, k_rows,
+                 vt_rows, q_pitch, vt_pitch, dt, dry=False):
+    bh = batch * heads
+    tq = matrix_map(q.data_ptr(), bh * q_rows, q_pitch, q_pitch, 128, dry)
+    tk = matrix_map(k.data_ptr(), bh * k_rows, q_pitch, q_pitch, 128, dry)
+    tv = matrix_map(vt.data_ptr(), bh * vt_rows, vt_pitch, vt_pitch, vt_rows, dry)
+    p = AttnParams()
+    p.tmap_q, p.tmap_k, p.tmap_vt = tq.ptr, tk.ptr, tv.ptr
+    p.out = out if isinstance(out, int) else out.data_ptr()
+    p.batch, p.heads, p.head_dim = batch, heads, head_dim
+    p.seq_q, p.seq_kv = seq_q, seq_kv
+    p.q_rows, p.k_rows, p.vt_rows = q_rows, k_rows, vt_rows
+    p.dtype = dtype_code(dt)
+    p.scale = 1.0 / math.sqrt(head_dim)
+    flops = 4 * batch * heads * seq_q * seq_kv * head_dim
+    nbytes = 2 * bh * (2 * seq_q + 2 * seq_kv) * head_dim
+    return Op(name, lib.sfb_attention, (C.byref(p),), (p, tq, tk, tv, q, k, vt, out), flops, nbytes)
+
+
+def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, dt):
+    p = GnParams()
+    p.x, p.y = x.ptr, y.ptr
+    p.gamma, p.beta, p.stats = gamma.data_ptr(), beta.data_ptr(), stats.data_ptr()
+    p.n, p.hw, p.c, p.ldx, p.ldy, p.groups = x.n, x.h * x.w, x.c, x.ld, y.ld, groups
+    p.eps, p.silu, p.dtype = eps, int(silu), dtype_code(dt)
+    keep = (p, x.buf, y.buf, gamma, beta, stats)
+    nb = x.rows * x.c * 2
+    return [Op(name + ".stats", lib.sfb_group_norm_stats, (C.byref(p),), keep, 0, nb),
+            Op(name + ".apply", lib.sfb_group_norm_apply, (C.byref(p),), keep, 0, 2 * nb)]
+
+
+def ln_op(name, lib, *, x, y, rows, c, gamma, beta, eps, dt, ldx=None, ldy=None):
+    p = LnParams()
+    p.x, p.y = x.data_ptr(), y.data_ptr()
+    p.gamma, p.beta = gamma.data_ptr(), beta.data_ptr()
+    p.rows, p.c, p.ldx, p.ldy = rows, c, ldx or c, ldy or c
+    p.eps, p.dtype = eps, dtype_code(dt)
+    return Op(name, lib.sfb_layer_norm, (C.byref(p),), (p, x, y, gamma, beta), 0, 4 * rows * c)
+
+
+def small_linear_op(name, lib, *, x, w, bias, batch, n, k, dt, y16=None, y32=None, add16=None,
+                    act_in=0, act_out=0, ldx=None, ldy=None):
+    p = SmallLinearParams()
+    p.x, p.w = x.data_ptr(), w.data_ptr()
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.add16 = add16.data_ptr() if add16 is not None else None
+    p.y16 = y16.data_ptr() if y16 is not None else None
+    p.y32 = y32.data_ptr() if y32 is not None else None
+    p.batch, p.n, p.k, p.ldx, p.ldy = batch, n, k, ldx or k, ldy or n
+    p.act_in, p.act_out, p.dtype = act_in, act_out, dtype_code(dt)
+    return Op(name, lib.sfb_small_linear, (C.byref(p),), (p, x, w, bias, add16, y16, y32),
+              2 * batch * n * k, 2 * n * k)
+
+
+# ---------------------------------------------------------------------------------------------
+# weight packing (done once at plan-build time)
+# ---------------------------------------------------------------------------------------------
+def pack_conv3x3(w, dt):
+    """[cout, cin, 3, 3] -> K-major [cout, (kh, kw, cin)]"""
+    return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dt).contiguous()
+
+
+def pack_geglu(w, b, dt):
+    """GEGLU projection [2*inner, k] (value rows first, gate rows second; reference chunk order
+    /root/reference/src/sfast/jit/passes/__init__.py:643-648) -> tile-interleaved
+    [ceil(inner/80)*160, k]: per 160-row tile, 80 value rows then the matching 80 gate rows."""
+    inner = w.shape[0] // 2
+    half = BN // 2
+    tiles = (inner + half - 1) // half
+    wp = torch.zeros(tiles * BN, w.shape[1], dtype=dt, device=w.device)
+    bp = torch.zeros(tiles * BN, dtype=torch.float32, device=w.device)
+    wv, wg = w.detach()[:inner], w.detach()[inner:]
+    for t in range(tiles):
+        lo, hi = t * half, min((t + 1) * half, inner)
+        wp[t * BN:t * BN + hi - lo] = wv[lo:hi].to(dt)
+        wp[t * BN + half:t * BN + half + hi - lo] = wg[lo:hi].to(dt)
+        if b is not None:
+            bp[t * BN:t * BN + hi - lo] = b.detach()[lo:hi].float()
+            bp[t * BN + half:t * BN + half + hi - lo] = b.detach()[inner + lo:inner + hi].float()
+    return wp, bp, inner

@@ -1,0 +1,405 @@
+"""Per-kernel parity checks of the CUDA path (through the C ABI) against plain PyTorch fp32
+references of the same op on the same seeded inputs.  Imported by ``tests/test_kernels_gpu.py``
+(pytest, ``-m gpu``) and runnable as a script so each check can be isolated in its own process:
+
+    python tests/kernel_checks.py [name ...]      # prints one JSON line per check
+
+Tolerances mirror the reference's own operator tests: conv 1e-3-class
+(/root/reference/tests/operators/test_cudnn_convolution.py:65), GEGLU 2e-2
+(tests/operators/test_cutlass_dual_linear.py:56), GroupNorm / LayerNorm 1e-2
+(src/sfast/triton/ops/group_norm.py:485-523, layer_norm.py:435-438).
+"""
+import json
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(_ROOT, "stable-fast_b200"))
+
+from sfast_b200 import _lib, ops  # noqa: E402
+from sfast_b200.ops import Act  # noqa: E402
+
+DEV = "cuda"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel_err(got, ref):
+    got, ref = got.float(), ref.float()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+
+
+def _rand(*shape, dt=torch.float16, scale=1.0, seed=None):
+    if seed is not None:
+        torch.manual_seed(seed)
+    return (torch.randn(*shape, device=DEV) * scale).to(dt)
+
+
+# ------------------------------------------------------------------------------------------
+def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, residual=True, seed=0):
+    lib = _lib.lib()
+    a = _rand(M, K, dt=dt, seed=seed)
+    w = _rand(N, K, dt=dt, scale=1 / math.sqrt(K))
+    b = torch.randn(N, device=DEV) if bias else None
+    r = _rand(M, N, dt=dt) if residual else None
+    out = torch.zeros(M, N, device=DEV, dtype=dt)
+    ws = torch.empty(max(splits, 1) * M * N, device=DEV, dtype=torch.float32)
+    op = ops.gemm_op("gemm", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
+                     b_map=ops.matrix_map(w.data_ptr(), N, K, K, ops.BN), M=M, N=N, K=K, dt=dt,
+                     out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits)
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    if residual:
+        ref = ref + r.float()
+    return rel_err(out, ref)
+
+
+def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1):
+    lib = _lib.lib()
+    x = _rand(M, K, dt=dt, seed=seed)
+    w = _rand(2 * inner, K, dt=dt, scale=1 / math.sqrt(K))
+    b = torch.randn(2 * inner, device=DEV) * 0.1
+    wp, bp, _ = ops.pack_geglu(w, b, dt)
+    Np = wp.shape[0]
+    out = torch.zeros(M, inner, device=DEV, dtype=dt)
+    ws = torch.empty(max(splits, 1) * M * Np, device=DEV, dtype=torch.float32)
+    op = ops.gemm_op("geglu", lib, a_map=ops.matrix_map(x.data_ptr(), M, K, K, 128),
+                     b_map=ops.matrix_map(wp.data_ptr(), Np, K, K, ops.BN), M=M, N=Np, K=K, dt=dt,
+                     out=out, ldo=inner, bias=bp, epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws,
+                     splits=splits)
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    # reference semantics: h * gelu(gate), hidden first (sfast passes/__init__.py:643-648)
+    y = x.float() @ w.float().t() + b
+    h, g = y.chunk(2, dim=-1)
+    return rel_err(out, h * F.gelu(g))
+
+
+def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, splits=None,
+               rowbias=True, residual=True, pitch_extra=0, seed=2):
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    ld = cin + pitch_extra
+    xbuf = _rand(n, h, w, ld, dt=dt)
+    x = Act(xbuf, n, h, w, cin, ld=ld)
+    wt = _rand(cout, cin, 3, 3, dt=dt, scale=1 / math.sqrt(9 * cin))
+    b = torch.randn(cout, device=DEV)
+    ho, wo = h // stride, w // stride
+    M = n * ho * wo
+    rb = torch.randn(n, cout, device=DEV) if rowbias else None
+    r = _rand(M, cout, dt=dt) if residual else None
+    out = torch.zeros(M, cout, device=DEV, dtype=dt)
+    wp = ops.pack_conv3x3(wt, dt)
+    box_n, box_h = ops.conv_tile_box(ho, wo)
+    amap = ops.nhwc_map(x.ptr, n, h, w, cin, ld, box_n, box_h, wo, stride)
+    ws = torch.empty(64 * M * cout, device=DEV, dtype=torch.float32) if splits != 1 else None
+    op = ops.gemm_op("conv", lib, a_map=amap, b_map=ops.matrix_map(wp.data_ptr(), cout, 9 * cin,
+                                                                 9 * cin, ops.BN),
+                     M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb,
+                     rows_per_img=ho * wo, ld_rowbias=cout, residual=r, ldr=cout, ws=ws,
+                     splits=splits,
+                     conv=dict(n=n, h=ho, w=wo, cin=cin, stride=stride, box_n=box_n, box_h=box_h))
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    xin = x.tensor().permute(0, 3, 1, 2).float()
+    ref = F.conv2d(xin, wt.float(), b, stride=stride, padding=1)
+    if rowbias:
+        ref = ref + rb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(M, cout)
+    if residual:
+        ref = ref + r.float()
+    return rel_err(out, ref)
+
+
+def _attn_buffers(B, H, S, Skv, D, dt):
+    dv = (D + 15) // 16 * 16
+    q_pitch = (dv + 63) // 64 * 64
+    vt_pitch = (Skv + 63) // 64 * 64
+    q = torch.zeros(B * H * S, q_pitch, device=DEV, dtype=dt)
+    k = torch.zeros(B * H * Skv, q_pitch, device=DEV, dtype=dt)
+    vt = torch.zeros(B * H * dv, vt_pitch, device=DEV, dtype=dt)
+    return q, k, vt, dv, q_pitch, vt_pitch
+
+
+def check_attention(B=2, H=8, S=1024, Skv=None, D=40, dt=torch.float16, seed=3):
+    lib = _lib.lib()
+    Skv = Skv or S
+    torch.manual_seed(seed)
+    qr = _rand(B, H, S, D, dt=dt)
+    kr = _rand(B, H, Skv, D, dt=dt)
+    vr = _rand(B, H, Skv, D, dt=dt)
+    q, k, vt, dv, q_pitch, vt_pitch = _attn_buffers(B, H, S, Skv, D, dt)
+    q.view(B * H, S, q_pitch)[:, :, :D] = qr.reshape(B * H, S, D)
+    k.view(B * H, Skv, q_pitch)[:, :, :D] = kr.reshape(B * H, Skv, D)
+    vt.view(B * H, dv, vt_pitch)[:, :D, :Skv] = vr.reshape(B * H, Skv, D).transpose(1, 2)
+    out = torch.zeros(B, S, H * D, device=DEV, dtype=dt)
+    op = ops.attention_op("attn", lib, q=q, k=k, vt=vt, out=out, batch=B, heads=H, head_dim=D,
+                          seq_q=S, seq_kv=Skv, q_rows=S, k_rows=Skv, vt_rows=dv, q_pitch=q_pitch,
+                          vt_pitch=vt_pitch, dt=dt)
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(qr.float(), kr.float(), vr.float())
+    ref = ref.transpose(1, 2).reshape(B, S, H * D)
+    return rel_err(out, ref)
+
+
+def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=4):
+    """QKV projection GEMM whose epilogue writes the attention layouts directly."""
+    lib = _lib.lib()
+    C = H * D
+    torch.manual_seed(seed)
+    if cross_kv:
+        Kdim, seq, which_base, ncols = 768, cross_kv, 1, 2 * C
+    else:
+        Kdim, seq, which_base, ncols = C, S, 0, 3 * C
+    x = _rand(B * seq, Kdim, dt=dt)
+    w = _rand(ncols, Kdim, dt=dt, scale=1 / math.sqrt(Kdim))
+    q, k, vt, dv, q_pitch, vt_pitch = _attn_buffers(B, H, S, seq, D, dt)
+    M = B * seq
+    op = ops.gemm_op("qkv", lib, a_map=ops.matrix_map(x.data_ptr(), M, Kdim, Kdim, 128),
+                     b_map=ops.matrix_map(w.data_ptr(), ncols, Kdim, Kdim, ops.BN), M=M, N=ncols,
+                     K=Kdim, dt=dt, epi=ops.EPI_QKV,
+                     qkv=dict(q=q, k=k, vt=vt, heads=H, head_dim=D, which_base=which_base,
+                              seq=seq, q_pitch=q_pitch, q_rows=S, k_rows=seq, vt_rows=dv,
+                              vt_pitch=vt_pitch))
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    y = (x.float() @ w.float().t()).view(B, seq, -1, H, D)  # [B, seq, which, H, D]
+    errs = []
+    idx = 0
+    if not cross_kv:
+        qref = y[:, :, 0].permute(0, 2, 1, 3).reshape(B * H, S, D)
+        errs.append(rel_err(q.view(B * H, S, q_pitch)[:, :, :D], qref))
+        idx = 1
+    kref = y[:, :, idx].permute(0, 2, 1, 3).reshape(B * H, seq, D)
+    vref = y[:, :, idx + 1].permute(0, 2, 3, 1).reshape(B * H, D, seq)
+    errs.append(rel_err(k.view(B * H, seq, q_pitch)[:, :, :D], kref))
+    errs.append(rel_err(vt.view(B * H, dv, vt_pitch)[:, :D, :seq], vref))
+    # padding must stay zero
+    pad = float(q.view(B * H, S, q_pitch)[:, :, D:].abs().max()) if not cross_kv else 0.0
+    pad += float(vt.view(B * H, dv, vt_pitch)[:, :, seq:].abs().max()) if vt_pitch > seq else 0.0
+    return max(errs) + pad
+
+
+def check_group_norm(n=2, c=320, h=32, w=32, silu=True, dt=torch.float16, pitch_extra=0, eps=1e-5,
+                     seed=5):
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    ld = c + pitch_extra
+    xb = _rand(n, h, w, ld, dt=dt)
+    x = Act(xb, n, h, w, c, ld=ld)
+    yb = torch.zeros(n, h, w, c, device=DEV, dtype=dt)
+    y = Act(yb, n, h, w, c)
+    gamma = torch.randn(c, device=DEV)
+    beta = torch.randn(c, device=DEV)
+    stats = torch.zeros(n, 32, 2, device=DEV)
+    for op in ops.gn_ops("gn", lib, x=x, y=y, gamma=gamma, beta=beta, stats=stats, groups=32,
+                         eps=eps, silu=silu, dt=dt):
+        op.launch(_stream())
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.tensor().permute(0, 3, 1, 2).float(), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    return rel_err(yb, ref.permute(0, 2, 3, 1))
+
+
+def check_layer_norm(rows=1151, c=1280, dt=torch.float16, seed=6):
+    lib = _lib.lib()
+    x = _rand(rows, c, dt=dt, seed=seed)
+    y = torch.zeros_like(x)
+    gamma = torch.randn(c, device=DEV)
+    beta = torch.randn(c, device=DEV)
+    ops.ln_op("ln", lib, x=x, y=y, rows=rows, c=c, gamma=gamma, beta=beta, eps=1e-5,
+              dt=dt).launch(_stream())
+    torch.cuda.synchronize()
+    return rel_err(y, F.layer_norm(x.float(), (c,), gamma, beta, 1e-5))
+
+
+def check_timestep_embed(batch=3, dim=320, dt=torch.float16):
+    lib = _lib.lib()
+    t = torch.tensor([999.0, 500.0, 1.0], device=DEV)[:batch]
+    out = torch.zeros(batch, dim, device=DEV, dtype=dt)
+    _lib.check(lib.sfb_timestep_embed(t.data_ptr(), batch, dim, 1, 0.0, out.data_ptr(), dim,
+                                      ops.dtype_code(dt), _stream()))
+    torch.cuda.synchronize()
+    half = dim // 2
+    ex = -math.log(10000) * torch.arange(half, device=DEV, dtype=torch.float32) / half
+    emb = t[:, None] * torch.exp(ex)[None]
+    ref = torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+    return (out.float() - ref).abs().max().item()
+
+
+def check_small_linear(batch=11, n=1280, k=320, act_out=1, dt=torch.float16, seed=7):
+    lib = _lib.lib()
+    x = _rand(batch, k, dt=dt, seed=seed)
+    w = _rand(n, k, dt=dt, scale=1 / math.sqrt(k))
+    b = torch.randn(n, device=DEV)
+    add = _rand(batch, n, dt=dt)
+    y16 = torch.zeros(batch, n, device=DEV, dtype=dt)
+    y32 = torch.zeros(batch, n, device=DEV)
+    ops.small_linear_op("sl", lib, x=x, w=w, bias=b, batch=batch, n=n, k=k, dt=dt, y16=y16,
+                        y32=y32, add16=add, act_out=act_out).launch(_stream())
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + b + add.float()
+    if act_out:
+        ref = F.silu(ref)
+    return max(rel_err(y16, ref), rel_err(y32, ref))
+
+
+def check_conv_in(n=2, h=64, w=64, cin=4, cout=320, dt=torch.float16, seed=8):
+    lib = _lib.lib()
+    x = _rand(n, cin, h, w, dt=dt, seed=seed)
+    wt = _rand(cout, cin, 3, 3, dt=dt, scale=0.2)
+    b = torch.randn(cout, device=DEV)
+    wp = ops.pack_conv3x3(wt, dt)
+    y = torch.zeros(n, h, w, cout, device=DEV, dtype=dt)
+    _lib.check(lib.sfb_conv_in(x.data_ptr(), wp.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, w,
+                               cin, cout, cout, ops.dtype_code(dt), _stream()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), wt.float(), b, padding=1).permute(0, 2, 3, 1)
+    return rel_err(y, ref)
+
+
+def check_conv_out(n=2, h=64, w=64, cin=320, cout=4, dt=torch.float16, seed=9):
+    lib = _lib.lib()
+    x = _rand(n, h, w, cin, dt=dt, seed=seed)
+    wt = _rand(cout, cin, 3, 3, dt=dt, scale=1 / math.sqrt(9 * cin))
+    b = torch.randn(cout, device=DEV)
+    wp = ops.pack_conv3x3(wt, dt)
+    y = torch.zeros(n, cout, h, w, device=DEV, dtype=dt)
+    _lib.check(lib.sfb_conv_out(x.data_ptr(), wp.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, w,
+                                cin, cout, cin, ops.dtype_code(dt), _stream()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), b, padding=1)
+    return rel_err(y, ref)
+
+
+def check_upsample(n=2, h=16, w=16, c=1280, dt=torch.float16):
+    lib = _lib.lib()
+    x = _rand(n, h, w, c, dt=dt, seed=10)
+    y = torch.zeros(n, 2 * h, 2 * w, c, device=DEV, dtype=dt)
+    _lib.check(lib.sfb_upsample2x(x.data_ptr(), y.data_ptr(), n, h, w, c, c, c, _stream()))
+    torch.cuda.synchronize()
+    ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
+    return rel_err(y, ref.permute(0, 2, 3, 1))
+
+
+
+def diag_gemm(dt=torch.float16):
+    """Informational: one-hot probes that reveal row / K permutations if a descriptor or swizzle
+    is wrong.  Prints the observed k -> k' and m -> m' maps for a single 128 x 160 x 64 tile."""
+    lib = _lib.lib()
+    M, N, K = 128, 160, 64
+    torch.manual_seed(11)
+    w = _rand(N, K, dt=dt)
+    info = {}
+    kmap = {}
+    for k0 in (0, 1, 7, 8, 15, 16, 31, 32, 48, 63):
+        a = torch.zeros(M, K, device=DEV, dtype=dt)
+        a[:, k0] = 1
+        out = torch.zeros(M, N, device=DEV, dtype=dt)
+        ops.gemm_op("diag", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
+                    b_map=ops.matrix_map(w.data_ptr(), N, K, K, ops.BN), M=M, N=N, K=K, dt=dt,
+                    out=out, ldo=N).launch(_stream())
+        torch.cuda.synchronize()
+        d = (out[0].float()[:, None] - w.float()).abs().sum(0)  # [K]
+        kmap[k0] = (int(d.argmin()), round(float(d.min()), 3))
+    info["k_map(row0)"] = kmap
+    # row map: A[m, :] = onehot(m % 64) * (1 + m // 64) -> out[m, n] = W[n, m % 64] * (1 + m//64)
+    a = torch.zeros(M, K, device=DEV, dtype=dt)
+    for m in range(M):
+        a[m, m % 64] = 1 + m // 64
+    out = torch.zeros(M, N, device=DEV, dtype=dt)
+    ops.gemm_op("diag", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
+                b_map=ops.matrix_map(w.data_ptr(), N, K, K, ops.BN), M=M, N=N, K=K, dt=dt,
+                out=out, ldo=N).launch(_stream())
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t())
+    bad_rows = ((out.float() - ref).abs().max(1).values > 1e-2).nonzero().flatten().tolist()
+    bad_cols = ((out.float() - ref).abs().max(0).values > 1e-2).nonzero().flatten().tolist()
+    info["bad_rows"] = bad_rows[:40]
+    info["n_bad_rows"] = len(bad_rows)
+    info["bad_cols"] = bad_cols[:40]
+    info["n_bad_cols"] = len(bad_cols)
+    info["out00"] = [round(float(v), 3) for v in out[0, :6]]
+    info["ref00"] = [round(float(v), 3) for v in ref[0, :6]]
+    print(json.dumps({"diag_gemm": info}), flush=True)
+    return 0.0
+
+
+# name -> (callable, tolerance)
+CHECKS = {
+    "diag_gemm": (diag_gemm, 1.0),
+    "gemm_small": (lambda: check_gemm(300, 320, 320), 2e-3),
+    "gemm_k64": (lambda: check_gemm(128, 160, 64, bias=False, residual=False), 2e-3),
+    "gemm_big": (lambda: check_gemm(8192, 1280, 1280), 2e-3),
+    "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
+    "gemm_bf16": (lambda: check_gemm(300, 320, 320, dt=torch.bfloat16), 1e-2),
+    "geglu": (lambda: check_geglu(256, 320, 1280), 2e-2),
+    "geglu_ragged": (lambda: check_geglu(100, 64, 256), 2e-2),
+    "geglu_splitk": (lambda: check_geglu(128, 1280, 5120, splits=4), 2e-2),
+    "conv_64": (lambda: check_conv(2, 64, 64, 320, 320, splits=1), 2e-3),
+    "conv_32": (lambda: check_conv(2, 32, 32, 640, 640, splits=1), 2e-3),
+    "conv_16_splitk": (lambda: check_conv(2, 16, 16, 1280, 1280), 2e-3),
+    "conv_8_multi_image": (lambda: check_conv(3, 8, 8, 1280, 1280), 2e-3),
+    "conv_4_tiny": (lambda: check_conv(5, 4, 4, 256, 256), 2e-3),
+    "conv_concat_pitch": (lambda: check_conv(2, 32, 32, 640, 320, pitch_extra=320, splits=1), 2e-3),
+    "conv_stride2": (lambda: check_conv(2, 64, 64, 320, 320, stride=2, residual=False,
+                                        rowbias=False), 2e-3),
+    "conv_stride2_16": (lambda: check_conv(2, 16, 16, 1280, 1280, stride=2, residual=False,
+                                           rowbias=False), 2e-3),
+    "attn_d40": (lambda: check_attention(2, 8, 1024, None, 40), 5e-3),
+    "attn_d40_4096": (lambda: check_attention(1, 8, 4096, None, 40), 5e-3),
+    "attn_d80": (lambda: check_attention(2, 8, 256, None, 80), 5e-3),
+    "attn_d160": (lambda: check_attention(2, 8, 64, None, 160), 5e-3),
+    "attn_d64": (lambda: check_attention(1, 10, 384, None, 64), 5e-3),
+    "attn_d32": (lambda: check_attention(1, 2, 1024, None, 32), 5e-3),
+    "attn_cross77": (lambda: check_attention(2, 8, 1024, 77, 40), 5e-3),
+    "attn_cross77_d160": (lambda: check_attention(2, 8, 64, 77, 160), 5e-3),
+    "attn_ragged_q": (lambda: check_attention(1, 8, 200, 300, 80), 5e-3),
+    "qkv_scatter": (lambda: check_qkv_scatter(2, 8, 256, 40), 2e-3),
+    "qkv_scatter_d160": (lambda: check_qkv_scatter(2, 8, 64, 160), 2e-3),
+    "kv_scatter_cross": (lambda: check_qkv_scatter(2, 8, 256, 40, cross_kv=77), 2e-3),
+    "group_norm_silu": (lambda: check_group_norm(2, 320, 32, 32, True), 1e-2),
+    "group_norm": (lambda: check_group_norm(2, 320, 32, 32, False, eps=1e-6), 1e-2),
+    "group_norm_1920_pitch": (lambda: check_group_norm(2, 1920, 16, 16, True, pitch_extra=640), 1e-2),
+    "group_norm_2560": (lambda: check_group_norm(3, 2560, 8, 8, True), 1e-2),
+    "group_norm_64": (lambda: check_group_norm(1, 64, 32, 32, True), 1e-2),
+    "layer_norm": (lambda: check_layer_norm(1151, 1280), 1e-2),
+    "layer_norm_320": (lambda: check_layer_norm(8192, 320), 1e-2),
+    "timestep_embed": (lambda: check_timestep_embed(), 2e-3),
+    "small_linear": (lambda: check_small_linear(), 2e-3),
+    "small_linear_noact": (lambda: check_small_linear(2, 960, 1280, act_out=0), 2e-3),
+    "conv_in": (lambda: check_conv_in(), 2e-3),
+    "conv_out": (lambda: check_conv_out(), 2e-3),
+    "upsample": (lambda: check_upsample(), 0.0),
+}
+
+
+def main(argv):
+    names = argv or list(CHECKS)
+    ok = True
+    for name in names:
+        fn, tol = CHECKS[name]
+        try:
+            err = fn()
+            passed = bool(err <= tol) and err == err
+            print(json.dumps({"check": name, "err": err, "tol": tol, "pass": passed}), flush=True)
+        except Exception as e:  # noqa: BLE001
+            passed = False
+            print(json.dumps({"check": name, "error": repr(e)[:300], "pass": False}), flush=True)
+        ok = ok and passed
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))
