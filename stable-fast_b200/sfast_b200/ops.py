@@ -25,6 +25,17 @@ def dtype_code(dt):
     raise NotImplementedError(f"sfast_b200 computes in fp16/bf16 storage; got {dt}")
 
 
+def _ptr(t):
+    """Device address of a tensor / raw address; 0 for None-like dry-run (meta) tensors."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    if t.device.type == "meta":
+        return 0
+    return t.data_ptr()
+
+
 class Act:
     """A [n, h, w, c] (or [rows, c] with h = w = 1) activation view with channel pitch ``ld``
     inside a (possibly wider) buffer, e.g. one half of a skip-concat buffer."""
@@ -37,7 +48,7 @@ class Act:
 
     @property
     def ptr(self):
-        return self.buf.data_ptr() + self.off * self.buf.element_size()
+        return _ptr(self.buf) + self.off * self.buf.element_size()
 
     @property
     def rows(self):
@@ -131,22 +142,18 @@ def gemm_op(name, lib, *, a_map, b_map, M, N, K, dt, out=None, ldo=0, bias=None,
         need = splits * M * N
         if ws.numel() < need:
             raise ValueError(f"{name}: split-K workspace too small ({ws.numel()} < {need})")
-        p.ws = ws.data_ptr()
+        p.ws = _ptr(ws) if not hasattr(ws, "finalize") else 0
     p.epi = epi
-    p.out = out if isinstance(out, int) else (out.data_ptr() if out is not None else None)
+    p.out = _ptr(out)
     p.ldo = ldo
-    p.bias = bias.data_ptr() if bias is not None else None
-    p.rowbias = rowbias if isinstance(rowbias, int) else (
-        rowbias.data_ptr() if rowbias is not None else None)
+    p.bias = _ptr(bias)
+    p.rowbias = _ptr(rowbias)
     p.rows_per_img, p.ld_rowbias = rows_per_img, ld_rowbias
-    p.residual = residual if isinstance(residual, int) else (
-        residual.data_ptr() if residual is not None else None)
+    p.residual = _ptr(residual)
     p.ldr = ldr
     p.geglu_n_out = geglu_n_out
     if qkv:
-        p.q = qkv["q"].data_ptr() if qkv.get("q") is not None else None
-        p.k = qkv["k"].data_ptr() if qkv.get("k") is not None else None
-        p.vt = qkv["vt"].data_ptr() if qkv.get("vt") is not None else None
+        p.q, p.k, p.vt = _ptr(qkv.get("q")), _ptr(qkv.get("k")), _ptr(qkv.get("vt"))
         for f in ("heads", "head_dim", "which_base", "seq", "q_pitch", "q_rows", "k_rows",
                   "vt_rows", "vt_pitch"):
             setattr(p, f, qkv[f])
@@ -161,12 +168,12 @@ def gemm_op(name, lib, *, a_map, b_map, M, N, K, dt, out=None, ldo=0, bias=None,
 def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq_kv, q_rows, k_rows,
                  vt_rows, q_pitch, vt_pitch, dt, dry=False):
     bh = batch * heads
-    tq = matrix_map(q.data_ptr(), bh * q_rows, q_pitch, q_pitch, 128, dry)
-    tk = matrix_map(k.data_ptr(), bh * k_rows, q_pitch, q_pitch, 128, dry)
-    tv = matrix_map(vt.data_ptr(), bh * vt_rows, vt_pitch, vt_pitch, vt_rows, dry)
+    tq = matrix_map(_ptr(q), bh * q_rows, q_pitch, q_pitch, 128, dry)
+    tk = matrix_map(_ptr(k), bh * k_rows, q_pitch, q_pitch, 128, dry)
+    tv = matrix_map(_ptr(vt), bh * vt_rows, vt_pitch, vt_pitch, vt_rows, dry)
     p = AttnParams()
     p.tmap_q, p.tmap_k, p.tmap_vt = tq.ptr, tk.ptr, tv.ptr
-    p.out = out if isinstance(out, int) else out.data_ptr()
+    p.out = _ptr(out)
     p.batch, p.heads, p.head_dim = batch, heads, head_dim
     p.seq_q, p.seq_kv = seq_q, seq_kv
     p.q_rows, p.k_rows, p.vt_rows = q_rows, k_rows, vt_rows
@@ -180,7 +187,7 @@ def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq
 def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, dt):
     p = GnParams()
     p.x, p.y = x.ptr, y.ptr
-    p.gamma, p.beta, p.stats = gamma.data_ptr(), beta.data_ptr(), stats.data_ptr()
+    p.gamma, p.beta, p.stats = _ptr(gamma), _ptr(beta), _ptr(stats)
     p.n, p.hw, p.c, p.ldx, p.ldy, p.groups = x.n, x.h * x.w, x.c, x.ld, y.ld, groups
     p.eps, p.silu, p.dtype = eps, int(silu), dtype_code(dt)
     keep = (p, x.buf, y.buf, gamma, beta, stats)
@@ -191,8 +198,8 @@ def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, 
 
 def ln_op(name, lib, *, x, y, rows, c, gamma, beta, eps, dt, ldx=None, ldy=None):
     p = LnParams()
-    p.x, p.y = x.data_ptr(), y.data_ptr()
-    p.gamma, p.beta = gamma.data_ptr(), beta.data_ptr()
+    p.x, p.y = _ptr(x), _ptr(y)
+    p.gamma, p.beta = _ptr(gamma), _ptr(beta)
     p.rows, p.c, p.ldx, p.ldy = rows, c, ldx or c, ldy or c
     p.eps, p.dtype = eps, dtype_code(dt)
     return Op(name, lib.sfb_layer_norm, (C.byref(p),), (p, x, y, gamma, beta), 0, 4 * rows * c)
@@ -201,11 +208,8 @@ def ln_op(name, lib, *, x, y, rows, c, gamma, beta, eps, dt, ldx=None, ldy=None)
 def small_linear_op(name, lib, *, x, w, bias, batch, n, k, dt, y16=None, y32=None, add16=None,
                     act_in=0, act_out=0, ldx=None, ldy=None):
     p = SmallLinearParams()
-    p.x, p.w = x.data_ptr(), w.data_ptr()
-    p.bias = bias.data_ptr() if bias is not None else None
-    p.add16 = add16.data_ptr() if add16 is not None else None
-    p.y16 = y16.data_ptr() if y16 is not None else None
-    p.y32 = y32.data_ptr() if y32 is not None else None
+    p.x, p.w = _ptr(x), _ptr(w)
+    p.bias, p.add16, p.y16, p.y32 = _ptr(bias), _ptr(add16), _ptr(y16), _ptr(y32)
     p.batch, p.n, p.k, p.ldx, p.ldy = batch, n, k, ldx or k, ldy or n
     p.act_in, p.act_out, p.dtype = act_in, act_out, dtype_code(dt)
     return Op(name, lib.sfb_small_linear, (C.byref(p),), (p, x, w, bias, add16, y16, y32),

@@ -1,0 +1,528 @@
+"""Schedule builder: turns (UNet config, state dict, batch, height, width) into a flat, static
+list of C-ABI kernel launches over pre-allocated buffers -- the replacement for the reference's
+TorchScript trace + graph passes (/root/reference/src/sfast/jit/trace_helper.py:33-72,
+/root/reference/src/sfast/jit/passes/__init__.py) on the UNet hot path.
+
+Design points:
+  * NHWC / token-major activations end to end: [B, H, W, C] is also [B*H*W, C], so the
+    resnet -> transformer hand-off needs no layout kernels.
+  * zero-copy skip concatenation: every skip tensor is produced directly into the channel slice
+    of the buffer its up-block consumer reads (`torch.cat` never runs).
+  * every residual / bias / time-embedding add / GEGLU / head split lives in a GEMM epilogue.
+  * weights are repacked once (conv OIHW -> K-major [cout, 9*cin], fused QKV, tile-interleaved
+    GEGLU, one concatenated matrix for all 22 time-embedding projections).
+"""
+import math
+
+import torch
+
+from . import _lib, ops
+from .ops import Act, EPI_GEGLU, EPI_QKV, Op, _ptr
+from .unet_spec import UNetSpec, spec_from_config
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class PackedWeights:
+    """Device-resident, kernel-ready copy of a UNet state dict (shape independent).
+
+    The packed tensors are COPIES: an in-place update of the original parameters (LoRA switch,
+    /root/reference/README.md:228-265) needs `CompiledUNet.rebind()`.
+    """
+
+    def __init__(self, spec: UNetSpec, state_dict, dtype, device, dry=False):
+        self.spec, self.dtype, self.device, self.dry = spec, dtype, torch.device(device), dry
+        self.sd = state_dict
+        self._cache = {}
+        # all per-resnet time projections as ONE [sum(cout), temb_dim] matrix
+        ws, bs, self.tproj_off = [], [], {}
+        off = 0
+        for r in spec.all_resnets():
+            ws.append(self._raw(r.prefix + ".time_emb_proj.weight"))
+            bs.append(self._raw(r.prefix + ".time_emb_proj.bias"))
+            self.tproj_off[r.prefix] = off
+            off += r.cout
+        self.tproj_total = off
+        self.tproj_w = torch.cat(ws, 0).to(device=self.device, dtype=dtype).contiguous()
+        self.tproj_b = torch.cat(bs, 0).to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _raw(self, name):
+        if name not in self.sd:
+            raise KeyError(f"UNet state dict has no parameter {name!r}")
+        return self.sd[name].detach()
+
+    def f32(self, name):
+        key = ("f32", name)
+        if key not in self._cache:
+            self._cache[key] = self._raw(name).to(device=self.device, dtype=torch.float32).contiguous()
+        return self._cache[key]
+
+    def _bmap(self, w):
+        return ops.matrix_map(w.data_ptr(), w.shape[0], w.shape[1], w.shape[1], ops.BN, self.dry)
+
+    def matrix(self, name):
+        """[n, k] weight (linear or 1x1 conv) + its TMA map."""
+        key = ("mat", name)
+        if key not in self._cache:
+            w = self._raw(name)
+            w = w.reshape(w.shape[0], -1).to(device=self.device, dtype=self.dtype).contiguous()
+            self._cache[key] = (w, self._bmap(w))
+        return self._cache[key]
+
+    def conv3x3(self, name):
+        key = ("c3", name)
+        if key not in self._cache:
+            w = ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)
+            self._cache[key] = (w, self._bmap(w))
+        return self._cache[key]
+
+    def conv3x3_plain(self, name):
+        key = ("c3p", name)
+        if key not in self._cache:
+            self._cache[key] = ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)
+        return self._cache[key]
+
+    def cat_matrix(self, names):
+        key = ("cat",) + tuple(names)
+        if key not in self._cache:
+            w = torch.cat([self._raw(n) for n in names], 0)
+            w = w.to(device=self.device, dtype=self.dtype).contiguous()
+            self._cache[key] = (w, self._bmap(w))
+        return self._cache[key]
+
+    def geglu(self, prefix):
+        key = ("geglu", prefix)
+        if key not in self._cache:
+            wp, bp, inner = ops.pack_geglu(self._raw(prefix + ".weight").to(self.device),
+                                           self._raw(prefix + ".bias").to(self.device), self.dtype)
+            self._cache[key] = (wp, bp, inner, self._bmap(wp))
+        return self._cache[key]
+
+    def small(self, name):
+        key = ("small", name)
+        if key not in self._cache:
+            self._cache[key] = self._raw(name).to(device=self.device, dtype=self.dtype).contiguous()
+        return self._cache[key]
+
+
+class UNetPlan:
+    """One static launch schedule for a fixed (batch, height, width)."""
+
+    def __init__(self, weights: PackedWeights, batch, height, width, ctx_len=77):
+        self.w = weights
+        self.spec = weights.spec
+        self.dt, self.dev, self.dry = weights.dtype, weights.device, weights.dry
+        self.lib = None if self.dry else _lib.lib()
+        self.B, self.H, self.W, self.ctx_len = batch, height, width, ctx_len
+        self.ops = []
+        self._bufs = {}
+        self._gn_count = 0
+        spec = self.spec
+        nres = len(spec.down)
+        if height % (1 << (nres - 1)) or width % (1 << (nres - 1)):
+            raise NotImplementedError(f"latent {height}x{width} must be divisible by {1 << (nres - 1)}")
+        # ---- static inputs / output
+        self.sample_in = self._alloc((batch, spec.in_channels, height, width), self.dt)
+        self.t_in = self._alloc((batch,), torch.float32)
+        self.ehs_in = self._alloc((batch, ctx_len, spec.cross_attention_dim), self.dt)
+        self.out = self._alloc((batch, spec.out_channels, height, width), self.dt)
+        if spec.addition_embed_type == "text_time":
+            self.add_in = self._alloc((batch, spec.add_in_dim), self.dt)
+            self.time_ids_in = self._alloc((batch * 6,), torch.float32)
+        # group-norm statistics arena: one [B, groups, 2] slot per GroupNorm, zeroed once per step
+        n_gn = sum(2 for _ in spec.all_resnets()) + 1
+        for blk in spec.down + [spec.mid] + spec.up:
+            n_gn += sum(1 for t in blk.attentions if t is not None)
+        self.gn_stats = self._alloc((n_gn, batch, spec.groups, 2), torch.float32)
+        self.ws = None
+        self._ws_need = 0
+        self._build()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self, shape, dtype, zero=True):
+        if self.dry:
+            return torch.empty(shape, dtype=dtype, device="meta")
+        return torch.zeros(shape, dtype=dtype, device=self.dev)
+
+    def buf(self, name, shape, dtype=None):
+        key = (name, tuple(shape), dtype or self.dt)
+        if key not in self._bufs:
+            self._bufs[key] = self._alloc(shape, dtype or self.dt)
+        return self._bufs[key]
+
+    def act(self, name, n, h, w, c):
+        return Act(self.buf(name, (n, h, w, c)), n, h, w, c)
+
+    def activation_bytes(self):
+        tot = sum(b.numel() * b.element_size() for b in self._bufs.values())
+        return tot + self.gn_stats.numel() * 4
+
+    # ------------------------------------------------------------------ op emitters
+    def _emit(self, op):
+        if isinstance(op, (list, tuple)):
+            self.ops.extend(op)
+        else:
+            self.ops.append(op)
+
+    def _gemm(self, name, **kw):
+        # split-K workspace: one shared fp32 buffer, sized after all ops are known
+        kw.setdefault("ws", self._ws_token)
+        op = ops.gemm_op(name, self.lib_or_dry(), **kw)
+        return op
+
+    def lib_or_dry(self):
+        return self.lib if self.lib is not None else _DryLib
+
+    def _a_matrix(self, x: Act):
+        return ops.matrix_map(x.ptr, x.rows, x.c, x.ld, 128, self.dry)
+
+    def group_norm(self, name, x: Act, prefix, silu, eps):
+        y = self.act("gn_out", x.n, x.h, x.w, x.c)
+        stats = self.gn_stats[self._gn_count]
+        self._gn_count += 1
+        self._emit(ops.gn_ops(name, self.lib_or_dry(), x=x, y=y, gamma=self.w.f32(prefix + ".weight"),
+                              beta=self.w.f32(prefix + ".bias"), stats=stats,
+                              groups=self.spec.groups, eps=eps, silu=silu, dt=self.dt))
+        return y
+
+    def conv3x3(self, name, x: Act, wname, dst: Act, stride=1, rowbias=None, residual: Act = None):
+        w, bmap = self.w.conv3x3(wname + ".weight")
+        cout = w.shape[0]
+        ho, wo = x.h // stride, x.w // stride
+        box_n, box_h = ops.conv_tile_box(ho, wo)
+        amap = ops.nhwc_map(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, wo,
+                            stride, self.dry)
+        M = x.n * ho * wo
+        kw = dict(a_map=amap, b_map=bmap, M=M, N=cout, K=9 * x.c, dt=self.dt,
+                  out=dst.ptr, ldo=dst.ld, bias=self.w.f32(wname + ".bias"),
+                  conv=dict(n=x.n, h=ho, w=wo, cin=x.c, stride=stride, box_n=box_n, box_h=box_h),
+                  keep=(x.buf, dst.buf, w))
+        if rowbias is not None:
+            kw.update(rowbias=rowbias[0], rows_per_img=ho * wo, ld_rowbias=rowbias[1])
+        if residual is not None:
+            kw.update(residual=residual.ptr, ldr=residual.ld)
+        self._emit(self._gemm(name, **kw))
+
+    def linear(self, name, x: Act, w_and_map, bias, dst: Act, residual: Act = None):
+        w, bmap = w_and_map
+        kw = dict(a_map=self._a_matrix(x), b_map=bmap, M=x.rows, N=w.shape[0], K=x.c, dt=self.dt,
+                  out=dst.ptr, ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, w))
+        if residual is not None:
+            kw.update(residual=residual.ptr, ldr=residual.ld)
+        self._emit(self._gemm(name, **kw))
+
+    # ------------------------------------------------------------------ sub-graphs
+    def resnet(self, r, x: Act, dst: Act):
+        p = r.prefix
+        a1 = self.group_norm(p + ".norm1", x, p + ".norm1", True, self.spec.eps)
+        h1 = self.act("res_h1", x.n, x.h, x.w, r.cout)
+        rb_ptr = _ptr(self.temb_proj) + 4 * self.w.tproj_off[p]
+        self.conv3x3(p + ".conv1", a1, p + ".conv1", h1, rowbias=(rb_ptr, self.w.tproj_total))
+        a2 = self.group_norm(p + ".norm2", h1, p + ".norm2", True, self.spec.eps)
+        if r.has_shortcut:
+            sc = self.act("res_sc", x.n, x.h, x.w, r.cout)
+            self.linear(p + ".conv_shortcut", x, self.w.matrix(p + ".conv_shortcut.weight"),
+                        self.w.f32(p + ".conv_shortcut.bias"), sc)
+            res = sc
+        else:
+            res = x
+        self.conv3x3(p + ".conv2", a2, p + ".conv2", dst, residual=res)
+
+    def attention(self, name, hs: Act, ln: Act, blk, t, cross):
+        """attn(ln) + hs -> hs (in place).  Self-attention: fused QKV projection; cross: Q from
+        the tokens, K/V from the text embedding."""
+        B, S, C, H, D = hs.n, hs.h * hs.w, t.dim, t.heads, t.head_dim
+        dv = _round_up(D, 16)
+        q_pitch = _round_up(dv, 64)
+        a = f"{blk}.attn2" if cross else f"{blk}.attn1"
+        skv = self.ctx_len if cross else S
+        vt_pitch = _round_up(skv, 64)
+        tag = f"{B}x{H}x{S}x{skv}x{D}"
+        q = self.buf("attn_q_" + tag, (B * H * S, q_pitch))
+        k = self.buf("attn_k_" + tag, (B * H * skv, q_pitch))
+        vt = self.buf("attn_vt_" + tag, (B * H * dv, vt_pitch))
+        qkv = dict(q=q, k=k, vt=vt, heads=H, head_dim=D, q_pitch=q_pitch, q_rows=S, k_rows=skv,
+                   vt_rows=dv, vt_pitch=vt_pitch)
+        if not cross:
+            w = self.w.cat_matrix([f"{a}.to_q.weight", f"{a}.to_k.weight", f"{a}.to_v.weight"])
+            self._emit(self._gemm(a + ".qkv", a_map=self._a_matrix(ln), b_map=w[1], M=ln.rows,
+                                  N=3 * C, K=C, dt=self.dt, epi=EPI_QKV,
+                                  qkv=dict(qkv, which_base=0, seq=S), keep=(ln.buf, w[0])))
+        else:
+            wq = self.w.matrix(f"{a}.to_q.weight")
+            self._emit(self._gemm(a + ".q", a_map=self._a_matrix(ln), b_map=wq[1], M=ln.rows, N=C,
+                                  K=C, dt=self.dt, epi=EPI_QKV,
+                                  qkv=dict(qkv, which_base=0, seq=S), keep=(ln.buf, wq[0])))
+            wkv = self.w.cat_matrix([f"{a}.to_k.weight", f"{a}.to_v.weight"])
+            ehs = Act(self.ehs_in, B, 1, self.ctx_len, self.spec.cross_attention_dim)
+            self._emit(self._gemm(a + ".kv", a_map=self._a_matrix(ehs), b_map=wkv[1], M=ehs.rows,
+                                  N=2 * C, K=ehs.c, dt=self.dt, epi=EPI_QKV,
+                                  qkv=dict(qkv, which_base=1, seq=self.ctx_len),
+                                  keep=(self.ehs_in, wkv[0])))
+        ao = self.act("attn_out", hs.n, hs.h, hs.w, C)
+        self._emit(ops.attention_op(a + ".core", self.lib_or_dry(), q=q, k=k, vt=vt, out=ao.buf,
+                                    batch=B, heads=H, head_dim=D, seq_q=S, seq_kv=skv, q_rows=S,
+                                    k_rows=skv, vt_rows=dv, q_pitch=q_pitch, vt_pitch=vt_pitch,
+                                    dt=self.dt, dry=self.dry))
+        self.linear(a + ".to_out", ao, self.w.matrix(f"{a}.to_out.0.weight"),
+                    self.w.f32(f"{a}.to_out.0.bias"), hs, residual=hs)
+
+    def layer_norm(self, name, x: Act, prefix):
+        y = self.act("ln_out", x.n, x.h, x.w, x.c)
+        self._emit(ops.ln_op(name, self.lib_or_dry(), x=x.buf, y=y.buf, rows=x.rows, c=x.c,
+                             gamma=self.w.f32(prefix + ".weight"), beta=self.w.f32(prefix + ".bias"),
+                             eps=1e-5, dt=self.dt))
+        return y
+
+    def transformer(self, t, x: Act, dst: Act):
+        p = t.prefix
+        a1 = self.group_norm(p + ".norm", x, p + ".norm", False, 1e-6)
+        hs = self.act("tf_hidden", x.n, x.h, x.w, t.dim)
+        self.linear(p + ".proj_in", a1, self.w.matrix(p + ".proj_in.weight"),
+                    self.w.f32(p + ".proj_in.bias"), hs)
+        for d in range(t.depth):
+            b = f"{p}.transformer_blocks.{d}"
+            ln = self.layer_norm(b + ".norm1", hs, b + ".norm1")
+            self.attention(b + ".attn1", hs, ln, b, t, cross=False)
+            ln = self.layer_norm(b + ".norm2", hs, b + ".norm2")
+            self.attention(b + ".attn2", hs, ln, b, t, cross=True)
+            ln = self.layer_norm(b + ".norm3", hs, b + ".norm3")
+            wp, bp, inner, gmap = self.w.geglu(b + ".ff.net.0.proj")
+            ff = self.act("ff_act", x.n, x.h, x.w, inner)
+            self._emit(self._gemm(b + ".ff.geglu", a_map=self._a_matrix(ln), b_map=gmap, M=ln.rows,
+                                  N=wp.shape[0], K=t.dim, dt=self.dt, out=ff.ptr, ldo=inner,
+                                  bias=bp, epi=EPI_GEGLU, geglu_n_out=inner,
+                                  keep=(ln.buf, ff.buf, wp)))
+            self.linear(b + ".ff.out", ff, self.w.matrix(b + ".ff.net.2.weight"),
+                        self.w.f32(b + ".ff.net.2.bias"), hs, residual=hs)
+        self.linear(p + ".proj_out", hs, self.w.matrix(p + ".proj_out.weight"),
+                    self.w.f32(p + ".proj_out.bias"), dst, residual=x)
+
+    def time_embedding(self):
+        spec, B, lib = self.spec, self.B, self.lib_or_dry()
+        c0 = spec.block_out_channels[0]
+        t_emb = self.buf("t_emb", (B, c0))
+        self._emit(Op("time_proj", lib.sfb_timestep_embed,
+                      (_ptr(self.t_in), B, c0,
+                       int(spec.flip_sin_to_cos), float(spec.freq_shift),
+                       _ptr(t_emb), c0, ops.dtype_code(self.dt)),
+                      (self.t_in, t_emb)))
+        h = self.buf("temb_h", (B, spec.temb_dim))
+        self._emit(ops.small_linear_op("time_embedding.linear_1", lib, x=t_emb,
+                                       w=self.w.small("time_embedding.linear_1.weight"),
+                                       bias=self.w.f32("time_embedding.linear_1.bias"), batch=B,
+                                       n=spec.temb_dim, k=c0, dt=self.dt, y16=h, act_out=1))
+        temb_act = self.buf("temb_act", (B, spec.temb_dim))  # silu(emb): all consumers apply SiLU
+        if spec.addition_embed_type == "text_time":
+            emb_t = self.buf("temb_t", (B, spec.temb_dim))
+            self._emit(ops.small_linear_op("time_embedding.linear_2", lib, x=h,
+                                           w=self.w.small("time_embedding.linear_2.weight"),
+                                           bias=self.w.f32("time_embedding.linear_2.bias"), batch=B,
+                                           n=spec.temb_dim, k=spec.temb_dim, dt=self.dt, y16=emb_t))
+            ad = spec.addition_time_embed_dim
+            # time_ids -> sinusoid written straight into the tail of the [text_embeds | time] row
+            n_text = spec.add_in_dim - 6 * ad
+            tid = self.buf("add_tid", (B * 6, ad))
+            self._emit(Op("add_time_proj", lib.sfb_timestep_embed,
+                          (_ptr(self.time_ids_in), B * 6, ad,
+                           int(spec.flip_sin_to_cos), float(spec.freq_shift),
+                           _ptr(tid), ad, ops.dtype_code(self.dt)),
+                          (self.time_ids_in, tid)))
+            self._add_concat = (n_text, tid)
+            h2 = self.buf("add_h", (B, spec.temb_dim))
+            self._emit(_CopyOp(self, n_text, tid))
+            self._emit(ops.small_linear_op("add_embedding.linear_1", lib, x=self.add_in,
+                                           w=self.w.small("add_embedding.linear_1.weight"),
+                                           bias=self.w.f32("add_embedding.linear_1.bias"), batch=B,
+                                           n=spec.temb_dim, k=spec.add_in_dim, dt=self.dt, y16=h2,
+                                           act_out=1))
+            self._emit(ops.small_linear_op("add_embedding.linear_2", lib, x=h2,
+                                           w=self.w.small("add_embedding.linear_2.weight"),
+                                           bias=self.w.f32("add_embedding.linear_2.bias"), batch=B,
+                                           n=spec.temb_dim, k=spec.temb_dim, dt=self.dt,
+                                           y16=temb_act, add16=emb_t, act_out=1))
+        else:
+            self._emit(ops.small_linear_op("time_embedding.linear_2", lib, x=h,
+                                           w=self.w.small("time_embedding.linear_2.weight"),
+                                           bias=self.w.f32("time_embedding.linear_2.bias"), batch=B,
+                                           n=spec.temb_dim, k=spec.temb_dim, dt=self.dt,
+                                           y16=temb_act, act_out=1))
+        # all resnets' time projections in one launch: [B, sum(cout)] fp32 row biases
+        self.temb_proj = self.buf("temb_proj", (B, self.w.tproj_total), torch.float32)
+        self._emit(ops.small_linear_op("time_emb_proj(all)", lib, x=temb_act, w=self.w.tproj_w,
+                                       bias=self.w.tproj_b, batch=B, n=self.w.tproj_total,
+                                       k=spec.temb_dim, dt=self.dt, y32=self.temb_proj))
+
+    # ------------------------------------------------------------------ whole UNet
+    def _build(self):
+        spec, B, H, W, lib = self.spec, self.B, self.H, self.W, self.lib_or_dry()
+        self._ws_token = _WsToken()
+        self._emit(Op("gn_stats.zero", lib.sfb_memset,
+                      (_ptr(self.gn_stats), 0,
+                       self.gn_stats.numel() * 4), (self.gn_stats,)))
+        self.time_embedding()
+
+        # ---- shape pass: where does every skip tensor live (inside its consumer's concat buffer)
+        skip_shapes = [(spec.block_out_channels[0], H, W)]
+        h, w = H, W
+        for blk in spec.down:
+            for _ in blk.resnets:
+                skip_shapes.append((blk.cout, h, w))
+            if blk.sampler:
+                h, w = h // 2, w // 2
+                skip_shapes.append((blk.cout, h, w))
+        pending = list(range(len(skip_shapes)))
+        skip_dst = {}
+        up_in = {}
+        cprev = spec.block_out_channels[-1]
+        for i, blk in enumerate(spec.up):
+            for j, r in enumerate(blk.resnets):
+                idx = pending.pop()
+                sc, sh, sw = skip_shapes[idx]
+                xc = r.cin - sc
+                cat = self.buf(f"cat_{i}_{j}", (B, sh, sw, r.cin))
+                skip_dst[idx] = Act(cat, B, sh, sw, sc, ld=r.cin, off=xc)
+                up_in[(i, j)] = (Act(cat, B, sh, sw, r.cin), Act(cat, B, sh, sw, xc, ld=r.cin))
+        assert not pending
+
+        # ---- conv_in
+        c0 = spec.block_out_channels[0]
+        x = skip_dst[0]
+        w_in = self.w.conv3x3_plain("conv_in.weight")
+        self._emit(Op("conv_in", lib.sfb_conv_in,
+                      (_ptr(self.sample_in),
+                       _ptr(w_in),
+                       _ptr(self.w.f32("conv_in.bias")),
+                       x.ptr, B, H, W, spec.in_channels, c0, x.ld,
+                       ops.dtype_code(self.dt)), (self.sample_in, w_in, x.buf),
+                      2 * B * H * W * c0 * 9 * spec.in_channels))
+        # ---- down path
+        k = 1
+        for blk in spec.down:
+            for r, t in zip(blk.resnets, blk.attentions):
+                dst = skip_dst[k]
+                k += 1
+                if t is None:
+                    self.resnet(r, x, dst)
+                else:
+                    mid = self.act("res_out", x.n, x.h, x.w, r.cout)
+                    self.resnet(r, x, mid)
+                    self.transformer(t, mid, dst)
+                x = dst
+            if blk.sampler:
+                dst = skip_dst[k]
+                k += 1
+                self.conv3x3(blk.sampler, x, blk.sampler, dst, stride=2)
+                x = dst
+        # ---- mid
+        m = spec.mid
+        a = self.act("res_out", x.n, x.h, x.w, m.cout)
+        self.resnet(m.resnets[0], x, a)
+        b = self.act("mid_tf_out", x.n, x.h, x.w, m.cout)
+        self.transformer(m.attentions[0], a, b)
+        self.resnet(m.resnets[1], b, up_in[(0, 0)][1])
+        # ---- up path
+        for i, blk in enumerate(spec.up):
+            n_res = len(blk.resnets)
+            for j, (r, t) in enumerate(zip(blk.resnets, blk.attentions)):
+                xin = up_in[(i, j)][0]
+                last = j == n_res - 1
+                if not last:
+                    dst = up_in[(i, j + 1)][1]
+                elif blk.sampler:
+                    dst = self.act("up_block_out", xin.n, xin.h, xin.w, r.cout)
+                else:
+                    dst = self.act("final_hidden", xin.n, xin.h, xin.w, r.cout)
+                if t is None:
+                    self.resnet(r, xin, dst)
+                else:
+                    mid = self.act("res_out", xin.n, xin.h, xin.w, r.cout)
+                    self.resnet(r, xin, mid)
+                    self.transformer(t, mid, dst)
+                x = dst
+            if blk.sampler:
+                up = self.act("upsampled", x.n, 2 * x.h, 2 * x.w, x.c)
+                self._emit(Op(blk.sampler + ".nearest2x", lib.sfb_upsample2x,
+                              (x.ptr, up.ptr, x.n,
+                               x.h, x.w, x.c, x.ld, up.ld), (x.buf, up.buf), 0,
+                              5 * x.rows * x.c * 2))
+                self.conv3x3(blk.sampler, up, blk.sampler, up_in[(i + 1, 0)][1])
+        # ---- head
+        y = self.group_norm("conv_norm_out", x, "conv_norm_out", True, spec.eps)
+        w_out = self.w.conv3x3_plain("conv_out.weight")
+        self._emit(Op("conv_out", lib.sfb_conv_out,
+                      (y.ptr, _ptr(w_out),
+                       _ptr(self.w.f32("conv_out.bias")),
+                       _ptr(self.out), B, H, W, c0, spec.out_channels,
+                       y.ld, ops.dtype_code(self.dt)), (y.buf, w_out, self.out),
+                      2 * B * H * W * c0 * 9 * spec.out_channels))
+        assert self._gn_count == self.gn_stats.shape[0], (self._gn_count, self.gn_stats.shape)
+        # ---- split-K workspace: allocate once at the largest requirement and patch the ops
+        self._ws_token.finalize(self)
+
+    # ------------------------------------------------------------------ execution
+    def run(self, stream):
+        for op in self.ops:
+            op.launch(stream)
+
+    def flops(self):
+        return sum(op.flops for op in self.ops)
+
+
+class _WsToken:
+    """Deferred split-K workspace: ops are created before the shared buffer size is known."""
+
+    def __init__(self):
+        self.users = []
+
+    def numel(self):
+        return 1 << 62
+
+    def data_ptr(self):
+        return 0
+
+    def finalize(self, plan):
+        need = 0
+        for op in plan.ops:
+            if op.fn is plan.lib_or_dry().sfb_gemm:
+                p = op.keep[0]
+                if p.splits > 1:
+                    need = max(need, p.splits * p.M * p.N)
+        plan.ws = plan._alloc((max(need, 1),), torch.float32)
+        for op in plan.ops:
+            if op.fn is plan.lib_or_dry().sfb_gemm:
+                p = op.keep[0]
+                if p.splits > 1:
+                    p.ws = _ptr(plan.ws)
+
+
+class _CopyOp(Op):
+    """SDXL: place the time-id sinusoids after text_embeds in the add-embedding input row."""
+
+    def __init__(self, plan, n_text, tid):
+        super().__init__("add_embedding.concat", None, (), (plan.add_in, tid))
+        self.plan, self.n_text, self.tid = plan, n_text, tid
+
+    def launch(self, stream):
+        B = self.plan.B
+        self.plan.add_in[:, self.n_text:].copy_(self.tid.view(B, -1))
+
+
+class _DryFn:
+    def __init__(self, name):
+        self.name = name
+
+    def __call__(self, *a):
+        raise RuntimeError("dry plan cannot be launched")
+
+
+class _DryLibT:
+    def __getattr__(self, name):
+        fn = _DryFn(name)
+        setattr(self, name, fn)
+        return fn
+
+
+_DryLib = _DryLibT()

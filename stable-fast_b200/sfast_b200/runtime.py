@@ -1,0 +1,170 @@
+"""Runtime that replaces ``unet.forward``: per-(batch, H, W, dtype) plan cache + CUDA-graph replay.
+
+Reference counterparts: the lazy-trace wrapper (/root/reference/src/sfast/jit/trace_helper.py:
+33-72) and the dynamic CUDA-graph cache (/root/reference/src/sfast/cuda/graphs.py:16-51,
+147-157).  Same contract: inputs are copied into static buffers, the graph is replayed, the
+output is returned as a fresh clone, all under a per-object lock; unlike the reference the
+timestep is always read from device memory inside the graph (never keyed by value,
+graphs.py:229-231).
+"""
+import logging
+import threading
+
+import torch
+
+from .plan import PackedWeights, UNetPlan
+from .unet_spec import spec_from_config
+
+logger = logging.getLogger(__name__)
+
+try:  # diffusers is not a dependency; use its output type when present
+    from diffusers.models.unets.unet_2d_condition import UNet2DConditionOutput  # type: ignore
+except Exception:  # noqa: BLE001
+    class UNet2DConditionOutput(dict):
+        """Minimal stand-in for diffusers' BaseOutput: attribute, key and index access."""
+
+        def __init__(self, sample):
+            super().__init__(sample=sample)
+            self.sample = sample
+
+        def __getitem__(self, k):
+            if isinstance(k, int):
+                return tuple(self.values())[k]
+            return super().__getitem__(k)
+
+        def to_tuple(self):
+            return tuple(self.values())
+
+
+_UNSUPPORTED_KWARGS = ("class_labels", "timestep_cond", "attention_mask",
+                       "down_block_additional_residuals", "mid_block_additional_residual",
+                       "down_intrablock_additional_residuals", "encoder_attention_mask")
+
+
+def require_b200(device):
+    if device.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError("sfast (B200 build): the UNet hot path needs a CUDA sm_100 device; "
+                           "there is no CPU / eager fallback")
+    major, minor = torch.cuda.get_device_capability(device)
+    if major != 10:
+        raise RuntimeError(f"sfast (B200 build): kernels are sm_100a only, device is sm_{major}{minor}")
+
+
+class _GraphedPlan:
+    def __init__(self, plan: UNetPlan, use_graph: bool):
+        self.plan = plan
+        self.graph = None
+        stream = torch.cuda.current_stream()
+        # warm-up (also sets kernel attributes, which must not happen during capture)
+        side = torch.cuda.Stream()
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            plan.run(side.cuda_stream)
+        stream.wait_stream(side)
+        torch.cuda.synchronize()
+        if use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                plan.run(torch.cuda.current_stream().cuda_stream)
+            self.graph = g
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.plan.run(torch.cuda.current_stream().cuda_stream)
+
+
+class CompiledUNet:
+    """Callable with the signature of diffusers ``UNet2DConditionModel.forward``."""
+
+    def __init__(self, config, state_dict_fn, enable_cuda_graph=True):
+        self._config = config
+        self._state_dict_fn = state_dict_fn
+        self.enable_cuda_graph = enable_cuda_graph
+        self._weights = None
+        self._cached = {}
+        self._lock = threading.Lock()
+        self.spec = spec_from_config(config)
+
+    # -- weights -------------------------------------------------------------------------
+    def _ensure_weights(self, dtype, device):
+        if self._weights is None or self._weights.dtype != dtype or self._weights.device != device:
+            logger.info("Packing UNet weights for the B200 path (%s, %s)", dtype, device)
+            self._weights = PackedWeights(self.spec, self._state_dict_fn(), dtype, device)
+            self._cached.clear()
+        return self._weights
+
+    def rebind(self):
+        """Re-pack weights after the module's parameters were changed in place (LoRA switch)."""
+        with self._lock:
+            self._weights = None
+            self._cached.clear()
+
+    # -- forward -------------------------------------------------------------------------
+    def __call__(self, sample, timestep, encoder_hidden_states, class_labels=None,
+                 timestep_cond=None, attention_mask=None, cross_attention_kwargs=None,
+                 added_cond_kwargs=None, down_block_additional_residuals=None,
+                 mid_block_additional_residual=None, down_intrablock_additional_residuals=None,
+                 encoder_attention_mask=None, return_dict=True):
+        given = dict(class_labels=class_labels, timestep_cond=timestep_cond,
+                     attention_mask=attention_mask,
+                     down_block_additional_residuals=down_block_additional_residuals,
+                     mid_block_additional_residual=mid_block_additional_residual,
+                     down_intrablock_additional_residuals=down_intrablock_additional_residuals,
+                     encoder_attention_mask=encoder_attention_mask)
+        for k in _UNSUPPORTED_KWARGS:
+            if given[k] is not None:
+                raise NotImplementedError(f"sfast (B200 build): UNet argument `{k}` is not supported")
+        if cross_attention_kwargs:
+            scale = cross_attention_kwargs.get("scale", 1.0)
+            if set(cross_attention_kwargs) - {"scale"} or scale != 1.0:
+                raise NotImplementedError("sfast (B200 build): cross_attention_kwargs (LoRA scale) "
+                                          "is not supported; fuse LoRA weights and call rebind()")
+        require_b200(sample.device)
+        dtype = sample.dtype
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise NotImplementedError(f"sfast (B200 build): UNet dtype {dtype}; use fp16 or bf16")
+        B, _, H, W = sample.shape
+        ctx_len = encoder_hidden_states.shape[1]
+        with self._lock:
+            weights = self._ensure_weights(dtype, sample.device)
+            key = (B, H, W, dtype, ctx_len, sample.device.index)
+            gp = self._cached.get(key)
+            if gp is None:
+                logger.info("Building UNet launch plan for %s", key)
+                plan = UNetPlan(weights, B, H, W, ctx_len)
+                gp = _GraphedPlan(plan, self.enable_cuda_graph)
+                self._cached[key] = gp
+            plan = gp.plan
+            plan.sample_in.copy_(sample, non_blocking=True)
+            plan.ehs_in.copy_(encoder_hidden_states, non_blocking=True)
+            t = timestep if torch.is_tensor(timestep) else torch.tensor(float(timestep))
+            t = t.reshape(-1).to(device=sample.device, dtype=torch.float32, non_blocking=True)
+            plan.t_in.copy_(t.expand(B) if t.numel() == 1 else t)
+            if self.spec.addition_embed_type == "text_time":
+                if not added_cond_kwargs or "text_embeds" not in added_cond_kwargs:
+                    raise ValueError("added_cond_kwargs with text_embeds / time_ids is required")
+                te = added_cond_kwargs["text_embeds"]
+                plan.add_in[:, :te.shape[1]].copy_(te)
+                plan.time_ids_in.copy_(added_cond_kwargs["time_ids"].reshape(-1).float())
+            gp.step()
+            out = plan.out.clone()
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(sample=out)
+
+
+def compile_unet_module(m, enable_cuda_graph=True):
+    """Replace ``m.forward`` (same module object, as the reference does at
+    /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:146-149)."""
+    compiled = CompiledUNet(m.config, m.state_dict, enable_cuda_graph)
+
+    def forward(*args, **kwargs):
+        return compiled(*args, **kwargs)
+
+    forward.__self__ = m
+    forward._cached = compiled._cached
+    forward._compiled = compiled
+    m.forward = forward
+    return m

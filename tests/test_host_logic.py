@@ -1,0 +1,168 @@
+"""CPU tests of the host side: drop-in surface, architecture walk, schedule builder (dry run),
+weight packing, C-ABI symbol table.  No compute kernels are called (no GPU here)."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import unet_oracle as uo
+from sfast_b200 import _lib, ops
+from sfast_b200.plan import PackedWeights, UNetPlan
+from sfast_b200.unet_spec import param_shapes, random_state_dict, spec_from_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_compilation_config_has_reference_fields():
+    from sfast.compilers.diffusion_pipeline_compiler import CompilationConfig, compile, compile_unet, compile_vae  # noqa: F401
+    names = [f.name for f in dataclasses.fields(CompilationConfig.Default)]
+    # /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:65-78
+    assert names == ["memory_format", "enable_jit", "enable_jit_freeze", "preserve_parameters",
+                     "enable_cnn_optimization", "enable_fused_linear_geglu", "prefer_lowp_gemm",
+                     "enable_xformers", "enable_cuda_graph", "enable_triton", "trace_scheduler"]
+    c = CompilationConfig.Default()
+    assert c.enable_jit and c.enable_jit_freeze and c.preserve_parameters and c.prefer_lowp_gemm
+    assert not c.enable_xformers and not c.enable_cuda_graph and not c.enable_triton
+    from sfast.compilers import stable_diffusion_pipeline_compiler as alias
+    assert alias.compile is compile
+
+
+def test_compile_unet_refuses_cpu_modules_loudly():
+    from sfast.compilers.diffusion_pipeline_compiler import CompilationConfig, compile_unet
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    m = uo.build_unet(uo.tiny_config())
+    with pytest.raises(RuntimeError, match="no CPU"):
+        compile_unet(m, CompilationConfig.Default())
+
+
+@pytest.mark.parametrize("cfgf", [uo.sd15_config, uo.sdxl_config, uo.tiny_config])
+def test_spec_parameter_names_match_oracle_state_dict(cfgf):
+    cfg = cfgf()
+    shapes = param_shapes(spec_from_config(cfg))
+    with torch.device("meta"):
+        sd = {k: tuple(v.shape) for k, v in uo.UNet2DConditionModel(cfg).state_dict().items()}
+    assert set(sd) == set(shapes)
+    assert all(tuple(shapes[k]) == sd[k] for k in sd)
+
+
+def test_unsupported_architecture_is_rejected():
+    cfg = uo.sd15_config()
+    cfg.down_block_types = ("AttnDownBlock2D",) + cfg.down_block_types[1:]
+    with pytest.raises(NotImplementedError):
+        spec_from_config(cfg)
+
+
+def _dry_plan(cfg, batch, h, w):
+    spec = spec_from_config(cfg)
+    sd = {k: torch.empty(s, dtype=torch.float16, device="meta") for k, s in param_shapes(spec).items()}
+    pw = PackedWeights(spec, sd, torch.float16, "meta", dry=True)
+    return UNetPlan(pw, batch, h, w)
+
+
+def test_sd15_plan_matches_survey_kernel_counts_and_flops():
+    plan = _dry_plan(uo.sd15_config(), 2, 64, 64)
+    names = [op.fn.name for op in plan.ops if op.fn is not None]
+    # 61 GroupNorms, 48 LayerNorms, 32 attention calls, 3 upsamples
+    assert names.count("sfb_group_norm_apply") == 61
+    assert names.count("sfb_layer_norm") == 48
+    assert names.count("sfb_attention") == 32
+    assert names.count("sfb_upsample2x") == 3
+    # 98 convs + 184 GEMMs of the reference collapse to 208 GEMM launches (fused QKV / KV, 22
+    # time projections in one small_linear, conv_in / conv_out as edge kernels)
+    assert names.count("sfb_gemm") == 208
+    # algorithmic FLOPs (conv/linear/attention MACs * 2), SURVEY.md section 8d: 1.607 TFLOP at B = 2
+    assert abs(plan.flops() / 1e12 - 1.607) < 0.003
+    # every skip concat is zero-copy: 12 concat buffers, no copy op exists
+    assert sum(1 for k in plan._bufs if k[0].startswith("cat_")) == 12
+
+
+def test_plan_scales_linearly_in_batch_and_handles_128_latents():
+    f1 = _dry_plan(uo.sd15_config(), 1, 64, 64).flops()
+    f8 = _dry_plan(uo.sd15_config(), 8, 64, 64).flops()
+    assert abs(f8 / f1 - 8) < 1e-6
+    big = _dry_plan(uo.sd15_config(), 1, 128, 128).flops()
+    assert abs(big / 1e12 - 4.674) < 0.01
+
+
+def test_sdxl_plan_builds():
+    plan = _dry_plan(uo.sdxl_config(), 2, 128, 128)
+    assert abs(plan.flops() / 2 / 1e12 - 6.761) < 0.02
+
+
+def test_split_k_policy():
+    assert ops.choose_splits(64, 2, 45) == 1       # 64^2 resnet conv: 128 tiles, no split
+    assert ops.choose_splits(16, 4, 90) == 2       # 32^2: 64 tiles -> 2 splits
+    assert ops.choose_splits(1, 8, 180) == 19      # 8^2: weight-bandwidth-bound, fill the SMs
+    assert ops.choose_splits(1, 1, 5) == 1         # never fewer than 4 K-blocks per split
+
+
+def test_conv_tile_box():
+    assert ops.conv_tile_box(64, 64) == (1, 2)
+    assert ops.conv_tile_box(8, 8) == (2, 8)
+    assert ops.conv_tile_box(4, 4) == (8, 4)
+    assert ops.conv_tile_box(72, 128) == (1, 1)
+    with pytest.raises(NotImplementedError):
+        ops.conv_tile_box(24, 24)
+
+
+def test_geglu_packing_round_trip():
+    torch.manual_seed(0)
+    inner, k = 200, 64
+    w, b = torch.randn(2 * inner, k), torch.randn(2 * inner)
+    wp, bp, n = ops.pack_geglu(w, b, torch.float32)
+    assert n == inner and wp.shape == (3 * 160, k)
+    x = torch.randn(5, k)
+    y = x @ wp.t() + bp
+    out = torch.zeros(5, inner)
+    for t in range(3):
+        lo, hi = t * 80, min((t + 1) * 80, inner)
+        v, g = y[:, t * 160:t * 160 + hi - lo], y[:, t * 160 + 80:t * 160 + 80 + hi - lo]
+        out[:, lo:hi] = v * torch.nn.functional.gelu(g)
+    h, g = (x @ w.t() + b).chunk(2, -1)
+    torch.testing.assert_close(out, h * torch.nn.functional.gelu(g), rtol=1e-4, atol=1e-4)
+    assert float(wp[inner % 80 + 160 * 2:160 * 2 + 80].abs().max()) == 0  # padding rows are zero
+
+
+def test_conv_weight_packing_order():
+    w = torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = ops.pack_conv3x3(w, torch.float32)
+    assert p.shape == (2, 27)
+    # K index = (kh * 3 + kw) * cin + c
+    assert p[1, (1 * 3 + 2) * 3 + 1] == w[1, 1, 1, 2]
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sfb200.h")).read()
+    declared = set(re.findall(r"\b(sfb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(h, name), name
+    lib = _lib.lib()
+    assert lib.sfb_abi_version() == 1
+    # argument validation works without a GPU and never falls back silently
+    p = _lib.GemmParams()
+    assert lib.sfb_gemm(ctypes.byref(p), None) < 0
+    assert b"sfb_gemm" in lib.sfb_last_error()
+
+
+def test_struct_layouts_match_the_header():
+    # sizes computed by hand from include/sfb200.h with natural alignment
+    assert ctypes.sizeof(_lib.AttnParams) == 4 * 8 + 10 * 4
+    assert ctypes.sizeof(_lib.LnParams) == 4 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.GnParams) == 5 * 8 + 9 * 4 + 4
+    assert ctypes.sizeof(_lib.SmallLinearParams) == 6 * 8 + 8 * 4
+
+
+def test_random_state_dict_is_seeded_and_complete():
+    spec = spec_from_config(uo.tiny_config())
+    a = random_state_dict(spec, seed=3)
+    b = random_state_dict(spec, seed=3)
+    assert set(a) == set(param_shapes(spec))
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    m = uo.build_unet(uo.tiny_config())
+    m.load_state_dict({k: v.float() for k, v in a.items()})
