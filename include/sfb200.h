@@ -53,6 +53,10 @@ int sfb_abi_version(void);
 const char* sfb_last_error(void);
 /* Number of kernel launches issued through this library since load (host-side counter). */
 uint64_t sfb_launch_count(void);
+/* Programmatic dependent launch (default on): kernels are launched with the programmatic stream
+ * serialization attribute and gate their first dependent global access on griddepcontrol.wait, so
+ * a kernel's prologue overlaps its predecessor's tail (also inside captured CUDA graphs). */
+void sfb_set_pdl(int enable);
 
 /* ---- TMA tensor maps (host side; `out128` receives a 128-byte, 64-byte-aligned CUtensorMap) */
 
@@ -83,7 +87,8 @@ enum sfb_epilogue {
 
 typedef struct sfb_gemm_params {
     const void* tmap_a; /* host pointer to a 128-byte tensor map */
-    const void* tmap_b; /* weights [N, K] row-major (K contiguous), box rows = 160 */
+    const void* tmap_b; /* weights, TILED: block (n_tile, k_block) = contiguous [160, 64]; 2-D map
+                         * over [n_tiles * K/64 * 160, 64], box rows = 160 */
     int32_t a_mode;
     int32_t M, N, K;
     int32_t dtype;
@@ -116,7 +121,8 @@ typedef struct sfb_gemm_params {
     int32_t q_pitch;         /* element pitch of a Q/K row (64 / 128 / 192) */
     int32_t q_rows;          /* rows allocated per (b, head) in the Q buffer */
     int32_t k_rows;          /* rows allocated per (b, head) in the K buffer */
-    int32_t vt_rows;         /* rows per (b, head) in V^T (head_dim rounded up to 16) */
+    int32_t vt_rows;         /* rows per (b, head) in V^T: (head_dim + 1) rounded up to 16; row
+                              * `head_dim` must be pre-filled with ones (softmax denominator) */
     int32_t vt_pitch;        /* element pitch of a V^T row */
 } sfb_gemm_params;
 

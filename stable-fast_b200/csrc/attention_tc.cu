@@ -8,10 +8,12 @@
 //                 O += P V   (128 x DV,  fp32, TMEM columns [128,128+DV))
 //               QK^T of tile j+1 is issued as soon as the softmax warps have pulled S_j into
 //               registers, so it overlaps the exponentials of tile j;
-//   warps 2..5  softmax: thread = query row; tcgen05.ld S, running max / sum in fp32 (exp2 with
-//               scale*log2e folded), P written to shared memory in the 128-byte-swizzled K-major
-//               layout tcgen05.mma reads as its A operand, O rescaled in TMEM only when the
-//               running max moved; final O / l stored token-major for the out-projection GEMM.
+//   warps 2..5  softmax: thread = query row; tcgen05.ld S, running max in fp32, one FFMA
+//               (s*scale*log2e - max) + packed 16-bit ex2 per element, P written to shared memory
+//               in the 128-byte-swizzled K-major layout tcgen05.mma reads as its A operand, O
+//               rescaled in TMEM only when the running max moved.  The softmax denominator costs
+//               nothing: row `head_dim` of V^T is all ones, so column `head_dim` of O accumulates
+//               sum(P) on the tensor core, consistently with the rounded P and the O rescales.
 // All three operands are K-major: Q/K as [rows, head_dim] and V pre-transposed as V^T
 // [head_dim, seq] -- the QKV projection's epilogue (gemm_tc.cu, SFB_EPI_QKV) writes those
 // layouts directly, so no permute/copy kernels exist between projection and attention.
@@ -44,7 +46,27 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-template <int DC, int DV, int KVS>
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// {2^x0, 2^x1} computed and returned in the 16-bit storage type (x <= 0): the probabilities are
+// needed as fp16/bf16 MMA operands anyway, so the convert happens before the MUFU, not after.
+__device__ __forceinline__ uint32_t exp2_pack(float x0, float x1, int bf16) {
+    uint32_t r;
+    if (bf16) {
+        asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tex2.approx.ftz.bf16x2 %0, t;\n\t}"
+            : "=r"(r) : "f"(x0), "f"(x1));
+    } else {
+        asm("{\n\t.reg .b32 t;\n\tcvt.rn.f16x2.f32 t, %2, %1;\n\tex2.approx.f16x2 %0, t;\n\t}"
+            : "=r"(r) : "f"(x0), "f"(x1));
+    }
+    return r;
+}
+
+template <int DC, int DK, int DV, int KVS>
 struct AttnSmem {
     static constexpr int kQBytes = DC * kTileQ * 128;
     static constexpr int kKStage = DC * kTileKV * 128;
@@ -59,12 +81,12 @@ struct AttnSmem {
     static_assert(kVChunk % 1024 == 0, "V^T chunk must keep 1024-byte swizzle-atom alignment");
 };
 
-template <int DC, int DV, int KVS>
+template <int DC, int DK, int DV, int KVS>
 __global__ void __launch_bounds__(kAttnThreads, (DC == 1) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
                     const __grid_constant__ CUtensorMap tma_k,
                     const __grid_constant__ CUtensorMap tma_vt, const AttnArgs a) {
-    using L = AttnSmem<DC, DV, KVS>;
+    using L = AttnSmem<DC, DK, DV, KVS>;
     constexpr uint32_t kTmemCols = (128 + DV <= 256) ? 256 : 512;
     constexpr uint32_t kColS = 0, kColO = 128;
     extern __shared__ uint8_t smem_raw[];
@@ -109,6 +131,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    pdl_launch_dependents();
+    pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -149,7 +173,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
             auto issue_qk = [&](int j) {
                 const int st = j % KVS;
 #pragma unroll
-                for (int kk = 0; kk < DV / 16; ++kk) {
+                for (int kk = 0; kk < DK / 16; ++kk) {
                     const int c = kk / 4, k4 = kk % 4;
                     const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ + c * (kTileQ * 128)));
                     const uint64_t dk = umma_desc_k_sw128(
@@ -197,7 +221,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
         const uint32_t tS = tmem_base + lane_base + kColS;
         const uint32_t tO = tmem_base + lane_base + kColO;
         float m_run = -INFINITY;
-        float l_run = 0.f;
+        const float sl2 = a.scale_log2;
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
@@ -213,45 +237,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
             tc_fence_before();
             mbar_arrive(s_free);
 
-            // scaled scores in the log2 domain; mask the ragged tail of the last KV tile
-            const int kv0 = j * kTileKV;
-            const int n_valid = a.seq_kv - kv0;  // >= 1
+            // ragged tail: only the last KV tile can hold columns >= seq_kv
+            const int n_valid = a.seq_kv - j * kTileKV;  // >= 1
+            if (n_valid < kTileKV) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= n_valid) sraw[i] = 0xff800000u;  // -inf
+            }
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 128; ++i) {
-                float s = __uint_as_float(sraw[i]) * a.scale_log2;
-                if (i >= n_valid) s = -INFINITY;
-                sraw[i] = __float_as_uint(s);
-                mx = fmaxf(mx, s);
-            }
-            const float m_new = fmaxf(m_run, mx);
+            for (int i = 0; i < 128; i += 2)
+                mx = fmax3(mx, __uint_as_float(sraw[i]), __uint_as_float(sraw[i + 1]));
+            const float m_new = fmaxf(m_run, mx * sl2);  // scale > 0
             const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
             m_run = m_new;
+            const float neg_m = -m_new;
 
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O stable
                 tc_fence_after();
             }
-            float lsum = 0.f;
 #pragma unroll
             for (int g = 0; g < 16; ++g) {  // 16 groups of 8 kv columns -> one 16-byte store
-                float p[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    p[i] = fast_exp2(__uint_as_float(sraw[g * 8 + i]) - m_new);
-                    lsum += p[i];
-                }
                 uint4 pk;
-                pk.x = pack2(p[0], p[1], a.dtype);
-                pk.y = pack2(p[2], p[3], a.dtype);
-                pk.z = pack2(p[4], p[5], a.dtype);
-                pk.w = pack2(p[6], p[7], a.dtype);
+                pk.x = exp2_pack(fmaf(__uint_as_float(sraw[g * 8 + 0]), sl2, neg_m),
+                                 fmaf(__uint_as_float(sraw[g * 8 + 1]), sl2, neg_m), a.dtype);
+                pk.y = exp2_pack(fmaf(__uint_as_float(sraw[g * 8 + 2]), sl2, neg_m),
+                                 fmaf(__uint_as_float(sraw[g * 8 + 3]), sl2, neg_m), a.dtype);
+                pk.z = exp2_pack(fmaf(__uint_as_float(sraw[g * 8 + 4]), sl2, neg_m),
+                                 fmaf(__uint_as_float(sraw[g * 8 + 5]), sl2, neg_m), a.dtype);
+                pk.w = exp2_pack(fmaf(__uint_as_float(sraw[g * 8 + 6]), sl2, neg_m),
+                                 fmaf(__uint_as_float(sraw[g * 8 + 7]), sl2, neg_m), a.dtype);
                 const int chunk = g >> 3;  // which 64-column half
                 const int g8 = g & 7;
                 uint8_t* dst = sP + chunk * (kTileQ * 128) + r * 128 + ((g8 ^ (r & 7)) << 4);
                 *reinterpret_cast<uint4*>(dst) = pk;
             }
-            l_run = l_run * alpha + lsum;
 
             if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
@@ -269,13 +290,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
             tc_fence_before();
             mbar_arrive(p_full);
         }
-        // final: O / l
+        // final: O / l, with l = O[:, head_dim] (the ones row of V^T)
         mbar_wait(pv_done, (n_kv - 1) & 1);
         tc_fence_after();
         const int srow = q_tile * kTileQ + r;
         const bool valid = srow < a.seq_q;
         const int b = bh / a.heads, h = bh % a.heads;
-        const float inv_l = 1.0f / l_run;
+        float inv_l;
+        {
+            uint32_t o[16];
+            tmem_ld16(tO + (a.head_dim & ~15), o);
+            tmem_wait_ld();
+            float l = 1.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i == (a.head_dim & 15)) l = __uint_as_float(o[i]);
+            inv_l = 1.0f / l;
+        }
         uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) +
                          ((size_t)b * a.seq_q + (valid ? srow : 0)) * (a.heads * a.head_dim) +
                          h * a.head_dim;
@@ -307,12 +338,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
     }
 }
 
-template <int DC, int DV, int KVS>
+template <int DC, int DK, int DV, int KVS>
 static int launch_attention(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
-    using L = AttnSmem<DC, DV, KVS>;
+    using L = AttnSmem<DC, DK, DV, KVS>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(attention_tc_kernel<DC, DV, KVS>,
+        cudaError_t err = cudaFuncSetAttribute(attention_tc_kernel<DC, DK, DV, KVS>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (err != cudaSuccess)
             return fail(SFB_ERR_CUDA, "sfb_attention: smem attribute: %s", cudaGetErrorString(err));
@@ -323,7 +354,9 @@ static int launch_attention(const sfb_attn_params* p, const AttnArgs& a, cudaStr
     memcpy(&tk, p->tmap_k, sizeof(CUtensorMap));
     memcpy(&tv, p->tmap_vt, sizeof(CUtensorMap));
     dim3 grid((p->seq_q + kTileQ - 1) / kTileQ, p->batch * p->heads);
-    attention_tc_kernel<DC, DV, KVS><<<grid, kAttnThreads, L::kTotal, stream>>>(tq, tk, tv, a);
+    cudaError_t err = launch_pdl(attention_tc_kernel<DC, DK, DV, KVS>, grid, dim3(kAttnThreads),
+                                 L::kTotal, stream, tq, tk, tv, a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_attention: launch: %s", cudaGetErrorString(err));
     return check_launch("sfb_attention");
 }
 
@@ -337,21 +370,23 @@ extern "C" int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream_) {
         return fail(SFB_ERR_INVALID, "sfb_attention: null argument");
     if (p->head_dim % 8 || p->head_dim <= 0 || p->seq_q <= 0 || p->seq_kv <= 0)
         return fail(SFB_ERR_INVALID, "sfb_attention: bad geometry");
-    const int dv = (p->head_dim + 15) / 16 * 16;
+    // V^T carries one extra all-ones row at index head_dim (softmax denominator on the tensor
+    // core), so its row count is (head_dim + 1) rounded up to 16
+    const int dv = (p->head_dim + 1 + 15) / 16 * 16;
     if (p->vt_rows != dv)
-        return fail(SFB_ERR_INVALID, "sfb_attention: vt_rows=%d must be head_dim rounded to 16 (%d)", p->vt_rows, dv);
+        return fail(SFB_ERR_INVALID, "sfb_attention: vt_rows=%d must be (head_dim+1) rounded to 16 (%d)", p->vt_rows, dv);
     AttnArgs a{};
     a.out = p->out; a.batch = p->batch; a.heads = p->heads; a.head_dim = p->head_dim;
     a.seq_q = p->seq_q; a.seq_kv = p->seq_kv; a.q_rows = p->q_rows; a.k_rows = p->k_rows;
     a.vt_rows = p->vt_rows; a.dtype = p->dtype;
     a.scale_log2 = p->scale * 1.4426950408889634f;
-    switch (dv) {
-        case 32: return launch_attention<1, 32, 2>(p, a, stream);
-        case 48: return launch_attention<1, 48, 2>(p, a, stream);
-        case 64: return launch_attention<1, 64, 2>(p, a, stream);
-        case 80: return launch_attention<2, 80, 2>(p, a, stream);
-        case 128: return launch_attention<2, 128, 2>(p, a, stream);
-        case 160: return launch_attention<3, 160, 1>(p, a, stream);
+    switch (p->head_dim) {
+        case 32: return launch_attention<1, 32, 48, 2>(p, a, stream);
+        case 40: return launch_attention<1, 48, 48, 2>(p, a, stream);
+        case 64: return launch_attention<1, 64, 80, 2>(p, a, stream);
+        case 80: return launch_attention<2, 80, 96, 2>(p, a, stream);
+        case 128: return launch_attention<2, 128, 144, 1>(p, a, stream);
+        case 160: return launch_attention<3, 160, 176, 1>(p, a, stream);
         default:
             return fail(SFB_ERR_INVALID, "sfb_attention: unsupported head_dim %d", p->head_dim);
     }

@@ -79,6 +79,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor drains; it must not touch the predecessor's output
+// before pdl_wait() (which returns once the predecessor grid has completed and flushed).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05.mma reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -51,6 +51,7 @@ struct GemmArgs {
     int a_mode;
     int nkb_total;  // K / 64
     int splits;
+    int pdl;        // launched with programmatic stream serialization
     float* ws;
     // conv geometry
     int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
@@ -76,20 +77,17 @@ __device__ __forceinline__ uint4 pack8(const float (&acc)[8], int bf16) {
     return o;
 }
 
-// 8 consecutive output columns [n, n+8) of row m.
-__device__ __forceinline__ void epi_store8(const EpiArgs& e, int m, int n, float (&acc)[8]) {
-    if (e.bias) add_bias8(e.bias, n, acc);
+__device__ __forceinline__ void add_res8(uint4 r, int dtype, float (&acc)[8]) {
+    float2 f;
+    f = unpack2(r.x, dtype); acc[0] += f.x; acc[1] += f.y;
+    f = unpack2(r.y, dtype); acc[2] += f.x; acc[3] += f.y;
+    f = unpack2(r.z, dtype); acc[4] += f.x; acc[5] += f.y;
+    f = unpack2(r.w, dtype); acc[6] += f.x; acc[7] += f.y;
+}
+
+// 8 consecutive output columns [n, n+8) of row m; `acc` already holds bias / row bias / residual.
+__device__ __forceinline__ void epi_store8(const EpiArgs& e, int m, int n, const float (&acc)[8]) {
     if (e.epi == SFB_EPI_STORE) {
-        if (e.rowbias) add_bias8(e.rowbias + (size_t)(m / e.rows_per_img) * e.ld_rowbias, n, acc);
-        if (e.residual) {
-            const uint4 r = *reinterpret_cast<const uint4*>(
-                reinterpret_cast<const uint16_t*>(e.residual) + (size_t)m * e.ldr + n);
-            float2 f;
-            f = unpack2(r.x, e.dtype); acc[0] += f.x; acc[1] += f.y;
-            f = unpack2(r.y, e.dtype); acc[2] += f.x; acc[3] += f.y;
-            f = unpack2(r.z, e.dtype); acc[4] += f.x; acc[5] += f.y;
-            f = unpack2(r.w, e.dtype); acc[6] += f.x; acc[7] += f.y;
-        }
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)m * e.ldo + n) =
             pack8(acc, e.dtype);
     } else {  // SFB_EPI_QKV
@@ -115,14 +113,9 @@ __device__ __forceinline__ void epi_store8(const EpiArgs& e, int m, int n, float
     }
 }
 
-// GEGLU: value / gate accumulators of 8 output columns [nout, nout+8); nv / ng are the
-// physical (tile-interleaved) column indices of the value / gate halves, used for the bias.
-__device__ __forceinline__ void epi_geglu8(const EpiArgs& e, int m, int nout, int nv, int ng,
-                                           float (&v)[8], float (&g)[8]) {
-    if (e.bias) {
-        add_bias8(e.bias, nv, v);
-        add_bias8(e.bias, ng, g);
-    }
+// GEGLU: value / gate (bias already added) of 8 output columns [nout, nout+8)
+__device__ __forceinline__ void epi_geglu8(const EpiArgs& e, int m, int nout, const float (&v)[8],
+                                           const float (&g)[8]) {
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = v[i] * gelu_erf_f(g[i]);
@@ -162,11 +155,13 @@ struct GemmSmem {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
-    static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int kBiasOffset = kBarOffset + 256;              // fp32 [kBiasSlots][BN]
+    static constexpr int kBiasSlots = 8;                              // images per conv M-tile
+    static constexpr int kTotal = kBiasOffset + kBiasSlots * BN * 4 + 1024;  // + alignment slack
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+__global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmArgs args) {
     using L = GemmSmem<BN, STAGES>;
@@ -179,6 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* sBias = reinterpret_cast<float*>(smem + L::kBiasOffset);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -200,6 +196,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    // Everything above overlaps the previous kernel's tail (programmatic dependent launch);
+    // global memory produced by it may only be touched after this point.
+    pdl_launch_dependents();
+    pdl_wait();
+    if (warp >= 2 && args.splits == 1) {
+        // stage bias (+ per-image time-embedding row bias) for this tile's columns in smem
+        const EpiArgs& e = args.e;
+        const int t = threadIdx.x - 64;
+        int img0 = 0, nslots = 1;
+        if (e.rowbias) {
+            nslots = args.box_n;
+            img0 = (args.box_n == 1) ? (m_tile / args.tiles_per_img) : m_tile * args.box_n;
+        }
+        for (int i = t; i < nslots * BN; i += 128) {
+            const int slot = i / BN, c = i - slot * BN;
+            const int n = n_tile * BN + c;
+            float v = 0.f;
+            if (n < e.N) {
+                if (e.bias) v = e.bias[n];
+                if (e.rowbias && img0 + slot < args.img_n)
+                    v += e.rowbias[(size_t)(img0 + slot) * e.ld_rowbias + n];
+            }
+            sBias[i] = v;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -232,8 +253,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     tma_load_4d(sA + stage * L::kABytes, &tma_a, &full_bar[stage], cc * BK,
                                 kw - 1, h0 * args.conv_stride + kh - 1, n0);
                 }
-                tma_load_2d(sB + stage * L::kBBytes, &tma_b, &full_bar[stage], kb * BK,
-                            n_tile * BN);
+                // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous BN x 64 block
+                tma_load_2d(sB + stage * L::kBBytes, &tma_b, &full_bar[stage], 0,
+                            (n_tile * args.nkb_total + kb) * BN);
             }
         }
         __syncwarp();
@@ -300,28 +322,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         float fv[8], fg[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            fv[i] = __uint_as_float(v[j * 8 + i]);
-                            fg[i] = __uint_as_float(g[j * 8 + i]);
+                            fv[i] = __uint_as_float(v[j * 8 + i]) + sBias[c * 16 + j * 8 + i];
+                            fg[i] = __uint_as_float(g[j * 8 + i]) + sBias[BN / 2 + c * 16 + j * 8 + i];
                         }
-                        epi_geglu8(e, m, nout + j * 8, ncol0 + c * 16 + j * 8,
-                                   ncol0 + BN / 2 + c * 16 + j * 8, fv, fg);
+                        epi_geglu8(e, m, nout + j * 8, fv, fg);
                     }
                 }
             }
         } else {
+            // bias slot of this row (image index inside the tile for the time-embedding row bias)
+            const float* brow = sBias;
+            if (e.rowbias) brow += (r / (args.box_h * args.img_w)) * BN;
+            const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE);
+            const uint16_t* rrow = reinterpret_cast<const uint16_t*>(e.residual) +
+                                   (size_t)(valid ? m : 0) * e.ldr + ncol0;
+            constexpr int kHalf = BN / 32;  // 16-column chunks per half tile
 #pragma unroll 1
-            for (int c = 0; c < BN / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld16(trow + c * 16, v);
-                tmem_wait_ld();
-                const int n = ncol0 + c * 16;
+            for (int hb = 0; hb < 2; ++hb) {
+                // issue all residual loads of this half first: one memory latency, not ten
+                uint4 res[2 * kHalf];
+                if (has_res && valid) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (valid && n + j * 8 < e.N) {
-                        float f[8];
+                    for (int i = 0; i < 2 * kHalf; ++i) {
+                        const int n = ncol0 + hb * (BN / 2) + i * 8;
+                        res[i] = (n < e.N)
+                                     ? *reinterpret_cast<const uint4*>(rrow + hb * (BN / 2) + i * 8)
+                                     : make_uint4(0, 0, 0, 0);
+                    }
+                }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
-                        epi_store8(e, m, n + j * 8, f);
+                for (int cc = 0; cc < kHalf; ++cc) {
+                    const int c = hb * kHalf + cc;
+                    uint32_t v[16];
+                    tmem_ld16(trow + c * 16, v);
+                    tmem_wait_ld();
+                    const int n = ncol0 + c * 16;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (valid && n + j * 8 < e.N) {
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                f[i] = __uint_as_float(v[j * 8 + i]) + brow[c * 16 + j * 8 + i];
+                            if (has_res) add_res8(res[cc * 2 + j], e.dtype, f);
+                            epi_store8(e, m, n + j * 8, f);
+                        }
                     }
                 }
             }
@@ -342,6 +387,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 template <int BN>
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
     const int groups = ncols / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -366,10 +413,22 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
         float v[8], g[8];
         sum8(nv, v);
         sum8(ng, g);
-        epi_geglu8(e, m, n, nv, ng, v, g);
+        if (e.bias) {
+            add_bias8(e.bias, nv, v);
+            add_bias8(e.bias, ng, g);
+        }
+        epi_geglu8(e, m, n, v, g);
     } else {
         float acc[8];
         sum8(n, acc);
+        if (e.bias) add_bias8(e.bias, n, acc);
+        if (e.epi == SFB_EPI_STORE) {
+            if (e.rowbias) add_bias8(e.rowbias + (size_t)(m / e.rows_per_img) * e.ld_rowbias, n, acc);
+            if (e.residual)
+                add_res8(*reinterpret_cast<const uint4*>(
+                             reinterpret_cast<const uint16_t*>(e.residual) + (size_t)m * e.ldr + n),
+                         e.dtype, acc);
+        }
         epi_store8(e, m, n, acc);
     }
 }
@@ -378,9 +437,25 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
 
 using namespace sfb;
 
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
+                       cudaStream_t stream) {
+    using L = GemmSmem<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
+        attr_set = true;
+    }
+    cudaError_t err = launch_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(kGemmThreads), L::kTotal, stream,
+                                 ta, tb, a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s", cudaGetErrorString(err));
+    return check_launch("sfb_gemm");
+}
+
 extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     constexpr int BN = 160;
-    constexpr int STAGES = 3;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!p || !p->tmap_a || !p->tmap_b) return fail(SFB_ERR_INVALID, "sfb_gemm: null argument");
     if (p->K <= 0 || p->K % BK) return fail(SFB_ERR_INVALID, "sfb_gemm: K=%d must be a multiple of 64", p->K);
@@ -390,6 +465,7 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     a.a_mode = p->a_mode;
     a.nkb_total = p->K / BK;
     a.splits = p->splits < 1 ? 1 : p->splits;
+    a.pdl = g_pdl;
     if (a.splits > a.nkb_total) return fail(SFB_ERR_INVALID, "sfb_gemm: splits > K blocks");
     if (a.splits > 1 && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
     a.ws = p->ws;
@@ -413,6 +489,8 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     } else {
         return fail(SFB_ERR_INVALID, "sfb_gemm: a_mode");
     }
+    if (p->rowbias && (p->a_mode != SFB_A_CONV3X3 || p->box_n > GemmSmem<BN, 3>::kBiasSlots))
+        return fail(SFB_ERR_INVALID, "sfb_gemm: rowbias needs conv mode with <= 8 images per tile");
     EpiArgs& e = a.e;
     e.epi = p->epi; e.dtype = p->dtype; e.M = p->M; e.N = p->N;
     e.out = p->out; e.ldo = p->ldo; e.bias = p->bias; e.rowbias = p->rowbias;
@@ -435,26 +513,22 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     } else {
         return fail(SFB_ERR_INVALID, "sfb_gemm: epilogue mode");
     }
-    using L = GemmSmem<BN, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-        if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
-        attr_set = true;
-    }
     dim3 grid((p->N + BN - 1) / BN, m_tiles, a.splits);
     CUtensorMap ta, tb;
     memcpy(&ta, p->tmap_a, sizeof(CUtensorMap));
     memcpy(&tb, p->tmap_b, sizeof(CUtensorMap));
-    gemm_tc_kernel<BN, STAGES><<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, a);
-    int rc = check_launch("sfb_gemm");
+    // <= one CTA per SM anyway: take the deep 6-stage pipeline; otherwise 3 stages x 2 CTAs/SM
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    int rc = (ctas <= 148) ? launch_gemm<BN, 6>(ta, tb, a, grid, stream)
+                           : launch_gemm<BN, 3>(ta, tb, a, grid, stream);
     if (rc) return rc;
     if (a.splits > 1) {
         const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
         const long long items = (long long)e.M * (ncols / 8);
         const int blocks = (int)((items + 255) / 256);
-        splitk_finish_kernel<BN><<<blocks, 256, 0, stream>>>(a.ws, a.splits, e);
+        cudaError_t err = launch_pdl(splitk_finish_kernel<BN>, dim3(blocks), dim3(256), 0, stream,
+                                     (const float*)a.ws, a.splits, e);
+        if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: finish launch: %s", cudaGetErrorString(err));
         rc = check_launch("sfb_gemm(split-K finish)");
     }
     return rc;

@@ -12,6 +12,7 @@ namespace sfb {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+int g_pdl = 1;
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -49,6 +50,7 @@ using namespace sfb;
 extern "C" int sfb_abi_version(void) { return SFB_ABI_VERSION; }
 extern "C" const char* sfb_last_error(void) { return g_err; }
 extern "C" uint64_t sfb_launch_count(void) { return g_launches.load(); }
+extern "C" void sfb_set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
 
 extern "C" int sfb_tmap_2d(void* out128, const void* base, uint64_t rows, uint64_t cols,
                            uint64_t pitch_elems, uint32_t box_rows) {

@@ -13,6 +13,8 @@ namespace sfb {
 // ---------------------------------------------------------------------------------------
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int batch, int half, int flip,
                                       float freq_shift, void* out, int ldo, int dtype) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch * half) return;
     const int b = idx / half, i = idx - b * half;
@@ -43,6 +45,8 @@ struct SmallLinearArgs {
 };
 
 __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int b0 = blockIdx.y * 8;
@@ -104,10 +108,12 @@ struct ConvEdgeArgs {
     int n, h, wd, cin, cout, ld, dtype;
 };
 
-constexpr int kConvInPixelsPerBlock = 64;
+constexpr int kConvInPixelsPerBlock = 12;
 
 __global__ void __launch_bounds__(256) conv_in_kernel(const ConvEdgeArgs a) {
     extern __shared__ uint16_t wsm[];  // [9*cin][cout]
+    pdl_launch_dependents();
+    pdl_wait();
     const int kk = 9 * a.cin;
     for (int i = threadIdx.x; i < kk * a.cout; i += blockDim.x) {
         const int co = i / kk, j = i - co * kk;  // packed weight is [cout][kh][kw][cin]
@@ -128,17 +134,26 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const ConvEdgeArgs a) {
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = a.bias ? a.bias[g * 8 + i] : 0.f;
-        for (int kh = 0; kh < 3; ++kh) {
-            const int iy = yh + kh - 1;
-            if (iy < 0 || iy >= a.h) continue;
-            for (int kw = 0; kw < 3; ++kw) {
-                const int ix = xw + kw - 1;
-                if (ix < 0 || ix >= a.wd) continue;
-                for (int ci = 0; ci < a.cin; ++ci) {
-                    const float xv = load1(a.x, (((size_t)img * a.cin + ci) * a.h + iy) * a.wd + ix, a.dtype);
-                    const int j = (kh * 3 + kw) * a.cin + ci;
+        // gather the 9 * cin inputs first (independent loads), then do the FMAs
+        float xin[9 * 8];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
+            const bool ok = iy >= 0 && iy < a.h && ix >= 0 && ix < a.wd;
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci)
+                xin[tap * 8 + ci] = (ok && ci < a.cin)
+                    ? load1(a.x, (((size_t)img * a.cin + ci) * a.h + iy) * a.wd + ix, a.dtype) : 0.f;
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                if (ci < a.cin) {
+                    const int j = tap * a.cin + ci;
                     const uint4 wv = *reinterpret_cast<const uint4*>(&wsm[j * a.cout + g * 8]);
                     const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+                    const float xv = xin[tap * 8 + ci];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float2 f = unpack2(ww[i], a.dtype);
@@ -161,6 +176,8 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const ConvEdgeArgs a) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_out_kernel(const ConvEdgeArgs a) {
     extern __shared__ uint16_t wsm[];  // [cout][9*cin]
+    pdl_launch_dependents();
+    pdl_wait();
     const int kk = 9 * a.cin;
     for (int i = threadIdx.x; i < (kk * a.cout) / 8; i += blockDim.x)
         reinterpret_cast<uint4*>(wsm)[i] = reinterpret_cast<const uint4*>(a.w)[i];
@@ -221,6 +238,8 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvEdgeArgs a) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
                                                          int n, int h, int w, int nvec, int ldx, int ldy) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)n * 2 * h * 2 * w * nvec;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -245,8 +264,10 @@ extern "C" int sfb_timestep_embed(const float* t, int32_t batch, int32_t dim, in
     if (!t || !out || dim % 2 || batch <= 0) return fail(SFB_ERR_INVALID, "timestep_embed: bad argument");
     const int half = dim / 2;
     const int total = batch * half;
-    timestep_embed_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        t, batch, half, flip, freq_shift, out, ldo, dtype);
+    cudaError_t err = launch_pdl(timestep_embed_kernel, dim3((total + 127) / 128), dim3(128), 0,
+                                 static_cast<cudaStream_t>(stream), t, batch, half, flip, freq_shift,
+                                 out, ldo, dtype);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "timestep_embed: %s", cudaGetErrorString(err));
     return check_launch("sfb_timestep_embed");
 }
 
@@ -261,7 +282,9 @@ extern "C" int sfb_small_linear(const sfb_small_linear_params* p, sfb_stream_t s
     a.batch = p->batch; a.n = p->n; a.k = p->k; a.ldx = p->ldx; a.ldy = p->ldy;
     a.act_in = p->act_in; a.act_out = p->act_out; a.dtype = p->dtype;
     dim3 grid((p->n + 7) / 8, (p->batch + 7) / 8);
-    small_linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    cudaError_t err = launch_pdl(small_linear_kernel, grid, dim3(256), 0,
+                                 static_cast<cudaStream_t>(stream), a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "small_linear: %s", cudaGetErrorString(err));
     return check_launch("sfb_small_linear");
 }
 
@@ -275,8 +298,10 @@ extern "C" int sfb_conv_in(const void* x, const void* w, const float* bias, void
     ConvEdgeArgs a{reinterpret_cast<const uint16_t*>(x), reinterpret_cast<const uint16_t*>(w), bias,
                    reinterpret_cast<uint16_t*>(y), n, h, wd, cin, cout, ldy, dtype};
     const int total = n * h * wd;
-    conv_in_kernel<<<(total + kConvInPixelsPerBlock - 1) / kConvInPixelsPerBlock, 256, smem,
-                     static_cast<cudaStream_t>(stream)>>>(a);
+    cudaError_t err = launch_pdl(conv_in_kernel,
+                                 dim3((total + kConvInPixelsPerBlock - 1) / kConvInPixelsPerBlock),
+                                 dim3(256), smem, static_cast<cudaStream_t>(stream), a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "conv_in: %s", cudaGetErrorString(err));
     return check_launch("sfb_conv_in");
 }
 
@@ -292,7 +317,9 @@ extern "C" int sfb_conv_out(const void* x, const void* w, const float* bias, voi
     const int total = n * h * wd;
     int blocks = (total + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    conv_out_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    cudaError_t err = launch_pdl(conv_out_kernel, dim3(blocks), dim3(256), smem,
+                                 static_cast<cudaStream_t>(stream), a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "conv_out: %s", cudaGetErrorString(err));
     return check_launch("sfb_conv_out");
 }
 
@@ -302,7 +329,9 @@ extern "C" int sfb_upsample2x(const void* x, void* y, int32_t n, int32_t h, int3
     const long long total = (long long)n * 4 * h * w * (c / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    upsample2x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(y), n, h, w, c / 8, ldx, ldy);
+    cudaError_t err = launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0,
+                                 static_cast<cudaStream_t>(stream), reinterpret_cast<const uint16_t*>(x),
+                                 reinterpret_cast<uint16_t*>(y), n, h, w, c / 8, ldx, ldy);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "upsample2x: %s", cudaGetErrorString(err));
     return check_launch("sfb_upsample2x");
 }

@@ -29,6 +29,8 @@ struct GnArgs {
 // (thread, group run) at the end, then one global atomic per (block, group, moment).
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
     __shared__ float acc[2 * 64];
+    pdl_launch_dependents();
+    pdl_wait();
     const int img = blockIdx.y;
     const int by = kGnThreads / a.nvec;
     const int tx = threadIdx.x % a.nvec;
@@ -77,6 +79,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
 // a streaming y = act(x * scale + shift) over the block's rows with 16-byte accesses.
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     extern __shared__ float sm[];
+    pdl_launch_dependents();
+    pdl_wait();
     float* scale = sm;
     float* shift = sm + a.c;
     const int img = blockIdx.y;
@@ -130,6 +134,8 @@ struct LnArgs {
 constexpr int kLnMaxVec = 8;  // c <= 8 * 32 * 8 = 2048
 
 __global__ void __launch_bounds__(256) layer_norm_kernel(const LnArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.rows) return;
@@ -215,7 +221,9 @@ extern "C" int sfb_group_norm_stats(const sfb_gn_params* p, sfb_stream_t stream)
     int bpi = 1;
     int rc = make_gn_args(p, a, bpi);
     if (rc) return rc;
-    gn_stats_kernel<<<dim3(bpi, p->n), kGnThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    cudaError_t err = launch_pdl(gn_stats_kernel, dim3(bpi, p->n), dim3(kGnThreads), 0,
+                                 static_cast<cudaStream_t>(stream), a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_stats: %s", cudaGetErrorString(err));
     return check_launch("sfb_group_norm_stats");
 }
 
@@ -225,7 +233,9 @@ extern "C" int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream)
     int rc = make_gn_args(p, a, bpi);
     if (rc) return rc;
     if (!p->y || !p->gamma || !p->beta || p->ldy % 8) return fail(SFB_ERR_INVALID, "group_norm_apply: null/ldy");
-    gn_apply_kernel<<<dim3(bpi, p->n), kGnThreads, 2 * p->c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+    cudaError_t err = launch_pdl(gn_apply_kernel, dim3(bpi, p->n), dim3(kGnThreads),
+                                 2 * p->c * sizeof(float), static_cast<cudaStream_t>(stream), a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_apply: %s", cudaGetErrorString(err));
     return check_launch("sfb_group_norm_apply");
 }
 
@@ -239,6 +249,8 @@ extern "C" int sfb_layer_norm(const sfb_ln_params* p, sfb_stream_t stream) {
     a.gamma = p->gamma; a.beta = p->beta; a.rows = p->rows; a.c = p->c; a.ldx = p->ldx; a.ldy = p->ldy;
     a.nvec = p->c / 8; a.eps = p->eps; a.dtype = p->dtype;
     const int blocks = (p->rows + 7) / 8;
-    layer_norm_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    cudaError_t err = launch_pdl(layer_norm_kernel, dim3(blocks), dim3(256), 0,
+                                 static_cast<cudaStream_t>(stream), a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "layer_norm: %s", cudaGetErrorString(err));
     return check_launch("sfb_layer_norm");
 }

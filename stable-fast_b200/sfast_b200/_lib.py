@@ -77,6 +77,7 @@ SYMBOLS = {
     "sfb_abi_version": (C.c_int, []),
     "sfb_last_error": (C.c_char_p, []),
     "sfb_launch_count": (C.c_uint64, []),
+    "sfb_set_pdl": (None, [C.c_int]),
     "sfb_tmap_2d": (C.c_int, [_VP, _VP, _U64, _U64, _U64, _U32]),
     "sfb_tmap_nhwc": (C.c_int, [_VP, _VP, _U32, _U32, _U32, _U32, _U64, _U32, _U32, _U32, _U32]),
     "sfb_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),

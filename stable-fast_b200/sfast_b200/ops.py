@@ -107,11 +107,14 @@ def conv_tile_box(ho, wo):
 
 
 def choose_splits(m_tiles, n_tiles, nkb):
-    """Split-K factor: fill ~148 SMs when the output has few tiles (weight-bandwidth-bound
-    low-resolution layers), but keep >= 4 K-blocks per split."""
+    """Split-K factor.  Only the weight-bandwidth-bound low-resolution layers (few output tiles,
+    long K) are split, to put ~148 CTAs on the machine; every split keeps >= 8 K-blocks so the
+    fp32 partial round trip + reduction kernel stays small next to the main loop (measured on
+    B200: splitting K = 1280 five ways cost more in the reduction kernel than it saved)."""
     tiles = m_tiles * n_tiles
-    s = (NUM_SMS + tiles // 2) // tiles
-    return max(1, min(s, nkb // 4))
+    if tiles * 2 > NUM_SMS:
+        return 1
+    return max(1, min(NUM_SMS // tiles, nkb // 8))
 
 
 def gemm_op(name, lib, *, a_map, b_map, M, N, K, dt, out=None, ldo=0, bias=None, rowbias=None,
@@ -219,6 +222,28 @@ def small_linear_op(name, lib, *, x, w, bias, batch, n, k, dt, y16=None, y32=Non
 # ---------------------------------------------------------------------------------------------
 # weight packing (done once at plan-build time)
 # ---------------------------------------------------------------------------------------------
+class Mat:
+    """A GEMM B operand: logical [n, k] weight stored TILED in HBM -- tile (n_tile, k_block) is one
+    contiguous 160 x 64 block (20 KB), so each TMA box is a single contiguous DRAM stream instead
+    of 160 rows strided by k -- plus its TMA map (2-D view [tiles*160, 64], box 160 rows)."""
+    __slots__ = ("data", "map", "n", "k")
+
+    def __init__(self, w, dry=False):
+        n, k = w.shape
+        assert k % BK == 0, f"weight K={k} must be a multiple of {BK}"
+        nt, nkb = (n + BN - 1) // BN, k // BK
+        self.n, self.k = n, k
+        if w.device.type == "meta":
+            self.data = torch.empty(nt * nkb * BN, BK, dtype=w.dtype, device="meta")
+        else:
+            wp = torch.zeros(nt * BN, k, dtype=w.dtype, device=w.device)
+            wp[:n] = w
+            self.data = wp.view(nt, BN, nkb, BK).permute(0, 2, 1, 3).contiguous().view(-1, BK)
+        self.map = matrix_map(_ptr(self.data), nt * nkb * BN, BK, BK, BN, dry)
+        self.map.keep = self.data  # the map alone keeps the tiled copy alive
+
+
+
 def pack_conv3x3(w, dt):
     """[cout, cin, 3, 3] -> K-major [cout, (kh, kw, cin)]"""
     return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dt).contiguous()

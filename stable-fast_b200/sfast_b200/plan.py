@@ -59,23 +59,22 @@ class PackedWeights:
             self._cache[key] = self._raw(name).to(device=self.device, dtype=torch.float32).contiguous()
         return self._cache[key]
 
-    def _bmap(self, w):
-        return ops.matrix_map(w.data_ptr(), w.shape[0], w.shape[1], w.shape[1], ops.BN, self.dry)
+    def _mat(self, w):
+        return ops.Mat(w, self.dry)
 
     def matrix(self, name):
-        """[n, k] weight (linear or 1x1 conv) + its TMA map."""
+        """[n, k] weight (linear or 1x1 conv) as a tiled GEMM operand."""
         key = ("mat", name)
         if key not in self._cache:
             w = self._raw(name)
             w = w.reshape(w.shape[0], -1).to(device=self.device, dtype=self.dtype).contiguous()
-            self._cache[key] = (w, self._bmap(w))
+            self._cache[key] = self._mat(w)
         return self._cache[key]
 
     def conv3x3(self, name):
         key = ("c3", name)
         if key not in self._cache:
-            w = ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)
-            self._cache[key] = (w, self._bmap(w))
+            self._cache[key] = self._mat(ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype))
         return self._cache[key]
 
     def conv3x3_plain(self, name):
@@ -89,7 +88,7 @@ class PackedWeights:
         if key not in self._cache:
             w = torch.cat([self._raw(n) for n in names], 0)
             w = w.to(device=self.device, dtype=self.dtype).contiguous()
-            self._cache[key] = (w, self._bmap(w))
+            self._cache[key] = self._mat(w)
         return self._cache[key]
 
     def geglu(self, prefix):
@@ -97,7 +96,7 @@ class PackedWeights:
         if key not in self._cache:
             wp, bp, inner = ops.pack_geglu(self._raw(prefix + ".weight").to(self.device),
                                            self._raw(prefix + ".bias").to(self.device), self.dtype)
-            self._cache[key] = (wp, bp, inner, self._bmap(wp))
+            self._cache[key] = (self._mat(wp), bp, inner)
         return self._cache[key]
 
     def small(self, name):
@@ -188,27 +187,26 @@ class UNetPlan:
         return y
 
     def conv3x3(self, name, x: Act, wname, dst: Act, stride=1, rowbias=None, residual: Act = None):
-        w, bmap = self.w.conv3x3(wname + ".weight")
-        cout = w.shape[0]
+        wm = self.w.conv3x3(wname + ".weight")
+        cout = wm.n
         ho, wo = x.h // stride, x.w // stride
         box_n, box_h = ops.conv_tile_box(ho, wo)
         amap = ops.nhwc_map(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, wo,
                             stride, self.dry)
         M = x.n * ho * wo
-        kw = dict(a_map=amap, b_map=bmap, M=M, N=cout, K=9 * x.c, dt=self.dt,
+        kw = dict(a_map=amap, b_map=wm.map, M=M, N=cout, K=9 * x.c, dt=self.dt,
                   out=dst.ptr, ldo=dst.ld, bias=self.w.f32(wname + ".bias"),
                   conv=dict(n=x.n, h=ho, w=wo, cin=x.c, stride=stride, box_n=box_n, box_h=box_h),
-                  keep=(x.buf, dst.buf, w))
+                  keep=(x.buf, dst.buf, wm))
         if rowbias is not None:
             kw.update(rowbias=rowbias[0], rows_per_img=ho * wo, ld_rowbias=rowbias[1])
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
         self._emit(self._gemm(name, **kw))
 
-    def linear(self, name, x: Act, w_and_map, bias, dst: Act, residual: Act = None):
-        w, bmap = w_and_map
-        kw = dict(a_map=self._a_matrix(x), b_map=bmap, M=x.rows, N=w.shape[0], K=x.c, dt=self.dt,
-                  out=dst.ptr, ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, w))
+    def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None):
+        kw = dict(a_map=self._a_matrix(x), b_map=wm.map, M=x.rows, N=wm.n, K=x.c, dt=self.dt,
+                  out=dst.ptr, ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, wm))
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
         self._emit(self._gemm(name, **kw))
@@ -234,33 +232,36 @@ class UNetPlan:
         """attn(ln) + hs -> hs (in place).  Self-attention: fused QKV projection; cross: Q from
         the tokens, K/V from the text embedding."""
         B, S, C, H, D = hs.n, hs.h * hs.w, t.dim, t.heads, t.head_dim
-        dv = _round_up(D, 16)
-        q_pitch = _round_up(dv, 64)
+        dv = _round_up(D + 1, 16)  # + the all-ones row that yields the softmax denominator
+        q_pitch = _round_up(D, 64)
         a = f"{blk}.attn2" if cross else f"{blk}.attn1"
         skv = self.ctx_len if cross else S
         vt_pitch = _round_up(skv, 64)
         tag = f"{B}x{H}x{S}x{skv}x{D}"
         q = self.buf("attn_q_" + tag, (B * H * S, q_pitch))
         k = self.buf("attn_k_" + tag, (B * H * skv, q_pitch))
+        new_vt = ("attn_vt_" + tag, (B * H * dv, vt_pitch), self.dt) not in self._bufs
         vt = self.buf("attn_vt_" + tag, (B * H * dv, vt_pitch))
+        if new_vt and not self.dry:
+            vt.view(B * H, dv, vt_pitch)[:, D, :] = 1.0
         qkv = dict(q=q, k=k, vt=vt, heads=H, head_dim=D, q_pitch=q_pitch, q_rows=S, k_rows=skv,
                    vt_rows=dv, vt_pitch=vt_pitch)
         if not cross:
             w = self.w.cat_matrix([f"{a}.to_q.weight", f"{a}.to_k.weight", f"{a}.to_v.weight"])
-            self._emit(self._gemm(a + ".qkv", a_map=self._a_matrix(ln), b_map=w[1], M=ln.rows,
+            self._emit(self._gemm(a + ".qkv", a_map=self._a_matrix(ln), b_map=w.map, M=ln.rows,
                                   N=3 * C, K=C, dt=self.dt, epi=EPI_QKV,
-                                  qkv=dict(qkv, which_base=0, seq=S), keep=(ln.buf, w[0])))
+                                  qkv=dict(qkv, which_base=0, seq=S), keep=(ln.buf, w)))
         else:
             wq = self.w.matrix(f"{a}.to_q.weight")
-            self._emit(self._gemm(a + ".q", a_map=self._a_matrix(ln), b_map=wq[1], M=ln.rows, N=C,
+            self._emit(self._gemm(a + ".q", a_map=self._a_matrix(ln), b_map=wq.map, M=ln.rows, N=C,
                                   K=C, dt=self.dt, epi=EPI_QKV,
-                                  qkv=dict(qkv, which_base=0, seq=S), keep=(ln.buf, wq[0])))
+                                  qkv=dict(qkv, which_base=0, seq=S), keep=(ln.buf, wq)))
             wkv = self.w.cat_matrix([f"{a}.to_k.weight", f"{a}.to_v.weight"])
             ehs = Act(self.ehs_in, B, 1, self.ctx_len, self.spec.cross_attention_dim)
-            self._emit(self._gemm(a + ".kv", a_map=self._a_matrix(ehs), b_map=wkv[1], M=ehs.rows,
+            self._emit(self._gemm(a + ".kv", a_map=self._a_matrix(ehs), b_map=wkv.map, M=ehs.rows,
                                   N=2 * C, K=ehs.c, dt=self.dt, epi=EPI_QKV,
                                   qkv=dict(qkv, which_base=1, seq=self.ctx_len),
-                                  keep=(self.ehs_in, wkv[0])))
+                                  keep=(self.ehs_in, wkv)))
         ao = self.act("attn_out", hs.n, hs.h, hs.w, C)
         self._emit(ops.attention_op(a + ".core", self.lib_or_dry(), q=q, k=k, vt=vt, out=ao.buf,
                                     batch=B, heads=H, head_dim=D, seq_q=S, seq_kv=skv, q_rows=S,
@@ -289,12 +290,12 @@ class UNetPlan:
             ln = self.layer_norm(b + ".norm2", hs, b + ".norm2")
             self.attention(b + ".attn2", hs, ln, b, t, cross=True)
             ln = self.layer_norm(b + ".norm3", hs, b + ".norm3")
-            wp, bp, inner, gmap = self.w.geglu(b + ".ff.net.0.proj")
+            gm, bp, inner = self.w.geglu(b + ".ff.net.0.proj")
             ff = self.act("ff_act", x.n, x.h, x.w, inner)
-            self._emit(self._gemm(b + ".ff.geglu", a_map=self._a_matrix(ln), b_map=gmap, M=ln.rows,
-                                  N=wp.shape[0], K=t.dim, dt=self.dt, out=ff.ptr, ldo=inner,
+            self._emit(self._gemm(b + ".ff.geglu", a_map=self._a_matrix(ln), b_map=gm.map, M=ln.rows,
+                                  N=gm.n, K=t.dim, dt=self.dt, out=ff.ptr, ldo=inner,
                                   bias=bp, epi=EPI_GEGLU, geglu_n_out=inner,
-                                  keep=(ln.buf, ff.buf, wp)))
+                                  keep=(ln.buf, ff.buf, gm)))
             self.linear(b + ".ff.out", ff, self.w.matrix(b + ".ff.net.2.weight"),
                         self.w.f32(b + ".ff.net.2.bias"), hs, residual=hs)
         self.linear(p + ".proj_out", hs, self.w.matrix(p + ".proj_out.weight"),

@@ -51,7 +51,7 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     out = torch.zeros(M, N, device=DEV, dtype=dt)
     ws = torch.empty(max(splits, 1) * M * N, device=DEV, dtype=torch.float32)
     op = ops.gemm_op("gemm", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
-                     b_map=ops.matrix_map(w.data_ptr(), N, K, K, ops.BN), M=M, N=N, K=K, dt=dt,
+                     b_map=ops.Mat(w).map, M=M, N=N, K=K, dt=dt,
                      out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits)
     op.launch(_stream())
     torch.cuda.synchronize()
@@ -73,7 +73,7 @@ def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1):
     out = torch.zeros(M, inner, device=DEV, dtype=dt)
     ws = torch.empty(max(splits, 1) * M * Np, device=DEV, dtype=torch.float32)
     op = ops.gemm_op("geglu", lib, a_map=ops.matrix_map(x.data_ptr(), M, K, K, 128),
-                     b_map=ops.matrix_map(wp.data_ptr(), Np, K, K, ops.BN), M=M, N=Np, K=K, dt=dt,
+                     b_map=ops.Mat(wp).map, M=M, N=Np, K=K, dt=dt,
                      out=out, ldo=inner, bias=bp, epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws,
                      splits=splits)
     op.launch(_stream())
@@ -102,8 +102,7 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
     box_n, box_h = ops.conv_tile_box(ho, wo)
     amap = ops.nhwc_map(x.ptr, n, h, w, cin, ld, box_n, box_h, wo, stride)
     ws = torch.empty(64 * M * cout, device=DEV, dtype=torch.float32) if splits != 1 else None
-    op = ops.gemm_op("conv", lib, a_map=amap, b_map=ops.matrix_map(wp.data_ptr(), cout, 9 * cin,
-                                                                 9 * cin, ops.BN),
+    op = ops.gemm_op("conv", lib, a_map=amap, b_map=ops.Mat(wp).map,
                      M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb,
                      rows_per_img=ho * wo, ld_rowbias=cout, residual=r, ldr=cout, ws=ws,
                      splits=splits,
@@ -121,12 +120,13 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
 
 
 def _attn_buffers(B, H, S, Skv, D, dt):
-    dv = (D + 15) // 16 * 16
-    q_pitch = (dv + 63) // 64 * 64
+    dv = (D + 1 + 15) // 16 * 16  # + the all-ones row (softmax denominator on the tensor core)
+    q_pitch = (D + 63) // 64 * 64
     vt_pitch = (Skv + 63) // 64 * 64
     q = torch.zeros(B * H * S, q_pitch, device=DEV, dtype=dt)
     k = torch.zeros(B * H * Skv, q_pitch, device=DEV, dtype=dt)
     vt = torch.zeros(B * H * dv, vt_pitch, device=DEV, dtype=dt)
+    vt.view(B * H, dv, vt_pitch)[:, D, :] = 1.0
     return q, k, vt, dv, q_pitch, vt_pitch
 
 
@@ -166,7 +166,7 @@ def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=
     q, k, vt, dv, q_pitch, vt_pitch = _attn_buffers(B, H, S, seq, D, dt)
     M = B * seq
     op = ops.gemm_op("qkv", lib, a_map=ops.matrix_map(x.data_ptr(), M, Kdim, Kdim, 128),
-                     b_map=ops.matrix_map(w.data_ptr(), ncols, Kdim, Kdim, ops.BN), M=M, N=ncols,
+                     b_map=ops.Mat(w).map, M=M, N=ncols,
                      K=Kdim, dt=dt, epi=ops.EPI_QKV,
                      qkv=dict(q=q, k=k, vt=vt, heads=H, head_dim=D, which_base=which_base,
                               seq=seq, q_pitch=q_pitch, q_rows=S, k_rows=seq, vt_rows=dv,
@@ -186,7 +186,7 @@ def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=
     errs.append(rel_err(vt.view(B * H, dv, vt_pitch)[:, :D, :seq], vref))
     # padding must stay zero
     pad = float(q.view(B * H, S, q_pitch)[:, :, D:].abs().max()) if not cross_kv else 0.0
-    pad += float(vt.view(B * H, dv, vt_pitch)[:, :, seq:].abs().max()) if vt_pitch > seq else 0.0
+    pad += float(vt.view(B * H, dv, vt_pitch)[:, :D, seq:].abs().max()) if vt_pitch > seq else 0.0
     return max(errs) + pad
 
 
@@ -308,7 +308,7 @@ def diag_gemm(dt=torch.float16):
         a[:, k0] = 1
         out = torch.zeros(M, N, device=DEV, dtype=dt)
         ops.gemm_op("diag", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
-                    b_map=ops.matrix_map(w.data_ptr(), N, K, K, ops.BN), M=M, N=N, K=K, dt=dt,
+                    b_map=ops.Mat(w).map, M=M, N=N, K=K, dt=dt,
                     out=out, ldo=N).launch(_stream())
         torch.cuda.synchronize()
         d = (out[0].float()[:, None] - w.float()).abs().sum(0)  # [K]
@@ -320,7 +320,7 @@ def diag_gemm(dt=torch.float16):
         a[m, m % 64] = 1 + m // 64
     out = torch.zeros(M, N, device=DEV, dtype=dt)
     ops.gemm_op("diag", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
-                b_map=ops.matrix_map(w.data_ptr(), N, K, K, ops.BN), M=M, N=N, K=K, dt=dt,
+                b_map=ops.Mat(w).map, M=M, N=N, K=K, dt=dt,
                 out=out, ldo=N).launch(_stream())
     torch.cuda.synchronize()
     ref = (a.float() @ w.float().t())

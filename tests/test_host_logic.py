@@ -95,9 +95,11 @@ def test_sdxl_plan_builds():
 
 def test_split_k_policy():
     assert ops.choose_splits(64, 2, 45) == 1       # 64^2 resnet conv: 128 tiles, no split
-    assert ops.choose_splits(16, 4, 90) == 2       # 32^2: 64 tiles -> 2 splits
-    assert ops.choose_splits(1, 8, 180) == 19      # 8^2: weight-bandwidth-bound, fill the SMs
-    assert ops.choose_splits(1, 1, 5) == 1         # never fewer than 4 K-blocks per split
+    assert ops.choose_splits(16, 4, 10) == 1       # 32^2 linear, K = 640: too short to split
+    assert ops.choose_splits(16, 4, 90) == 2       # 32^2 conv: 64 tiles -> 2 splits
+    assert ops.choose_splits(4, 8, 20) == 2        # 16^2 linear K = 1280
+    assert ops.choose_splits(1, 8, 180) == 18      # 8^2 conv: weight-bandwidth-bound, fill the SMs
+    assert ops.choose_splits(1, 1, 5) == 1         # never fewer than 8 K-blocks per split
 
 
 def test_conv_tile_box():
