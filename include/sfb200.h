@@ -124,6 +124,17 @@ typedef struct sfb_gemm_params {
     int32_t vt_rows;         /* rows per (b, head) in V^T: (head_dim + 1) rounded up to 16; row
                               * `head_dim` must be pre-filled with ones (softmax denominator) */
     int32_t vt_pitch;        /* element pitch of a V^T row */
+    /* LayerNorm folded around the GEMM (replaces sfast_triton::layer_norm,
+     * /root/reference/src/sfast/triton/ops/layer_norm.py:51-133, as a separate pass):
+     *   producer (SFB_EPI_STORE): rowstats_out[m] += (sum, sum of squares) of the stored row;
+     *   consumer: A is the RAW activation, the weight is pre-scaled by gamma (W' = W * gamma),
+     *     out = rstd_m * (acc - mean_m * ln_colsum[n]) + bias[n],  bias = beta W^T + b,
+     *     (mean_m, rstd_m) from ln_rowstats[m] over ln_dim columns.  Buffers are caller-zeroed. */
+    float* rowstats_out;       /* [M, 2] fp32 or NULL */
+    const float* ln_rowstats;  /* [M, 2] fp32 or NULL */
+    const float* ln_colsum;    /* [N] fp32: sum_k W'[n, k] */
+    float ln_eps;
+    int32_t ln_dim;
 } sfb_gemm_params;
 
 int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream);
@@ -151,15 +162,22 @@ typedef struct sfb_gn_params {
     void* y;         /* [n, hw, c] 16-bit, channel pitch ldy */
     const float* gamma;
     const float* beta;
-    float* stats;    /* [n, groups, 2] fp32 (sum, sum of squares); zeroed by sfb_group_norm_stats */
+    float* stats;    /* [n, groups, 2] fp32 (sum, sum of squares); the CALLER zeroes it per use */
     int32_t n, hw, c, ldx, ldy, groups;
     float eps;
     int32_t silu;    /* 1: y = silu(gn(x)) */
     int32_t dtype;
+    uint32_t* sync_counter; /* sfb_group_norm_fused only: grid-barrier counter, zeroed by caller */
 } sfb_gn_params;
 
+/* two-pass path (any size): `stats` must be zero before sfb_group_norm_stats */
 int sfb_group_norm_stats(const sfb_gn_params* p, sfb_stream_t stream);
 int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream);
+/* single-launch path for tensors that fit in the GPU's shared memory (grid <= 148 CTAs with a
+ * grid-wide barrier): x is read once.  `stats` and `sync_counter` must be zero on entry.
+ * sfb_group_norm_fused_fits() returns 1 when the geometry qualifies. */
+int sfb_group_norm_fused_fits(const sfb_gn_params* p);
+int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream);
 
 typedef struct sfb_ln_params {
     const void* x; /* [rows, c] 16-bit, pitch ldx */
@@ -199,7 +217,8 @@ int sfb_small_linear(const sfb_small_linear_params* p, sfb_stream_t stream);
 /* 3x3 pad-1 convolution with tiny channel counts at the two ends of the UNet.
  * conv_in:  x NCHW [n, cin<=8, h, w] 16-bit  -> y NHWC [n, h, w, cout] (channel pitch ldy)
  * conv_out: x NHWC [n, h, w, cin] (pitch ldx) -> y NCHW [n, cout<=8, h, w] 16-bit
- * w: 16-bit [cout, 3, 3, cin] (K-major, same packing as sfb_gemm); bias fp32. */
+ * conv_in  w: 16-bit [3, 3, cin, cout] (tap-major, cout contiguous);
+ * conv_out w: 16-bit [cout, 3, 3, cin]; bias fp32. */
 int sfb_conv_in(const void* x, const void* w, const float* bias, void* y, int32_t n, int32_t h,
                 int32_t wd, int32_t cin, int32_t cout, int32_t ldy, int32_t dtype,
                 sfb_stream_t stream);

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "host.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace sfb {
@@ -37,6 +38,7 @@ struct AttnArgs {
     int seq_q, seq_kv;
     int q_rows, k_rows, vt_rows;
     int dtype;
+    int exp16;         // 1: exponentials computed directly in the 16-bit type (MUFU.EX2.F16/BF16)
     float scale_log2;  // scale * log2(e)
 };
 
@@ -244,10 +246,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
                 for (int i = 0; i < 128; ++i)
                     if (i >= n_valid) sraw[i] = 0xff800000u;  // -inf
             }
-            float mx = -INFINITY;
+            // four independent FMNMX3 chains: a single 128-long max chain is pure latency
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 128; i += 2)
-                mx = fmax3(mx, __uint_as_float(sraw[i]), __uint_as_float(sraw[i + 1]));
+            for (int i = 0; i < 128; i += 8) {
+                mx0 = fmax3(mx0, __uint_as_float(sraw[i]), __uint_as_float(sraw[i + 1]));
+                mx1 = fmax3(mx1, __uint_as_float(sraw[i + 2]), __uint_as_float(sraw[i + 3]));
+                mx2 = fmax3(mx2, __uint_as_float(sraw[i + 4]), __uint_as_float(sraw[i + 5]));
+                mx3 = fmax3(mx3, __uint_as_float(sraw[i + 6]), __uint_as_float(sraw[i + 7]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             const float m_new = fmaxf(m_run, mx * sl2);  // scale > 0
             const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
             m_run = m_new;
@@ -259,15 +267,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
             }
 #pragma unroll
             for (int g = 0; g < 16; ++g) {  // 16 groups of 8 kv columns -> one 16-byte store
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
                 uint4 pk;
-                pk.x = exp2_pack(fmaf(__uint_as_float(sraw[g * 8 + 0]), sl2, neg_m),
-                                 fmaf(__uint_as_float(sraw[g * 8 + 1]), sl2, neg_m), a.dtype);
-                pk.y = exp2_pack(fmaf(__uint_as_float(sraw[g * 8 + 2]), sl2, neg_m),
-                                 fmaf(__uint_as_float(sraw[g * 8 + 3]), sl2, neg_m), a.dtype);
-                pk.z = exp2_pack(fmaf(__uint_as_float(sraw[g * 8 + 4]), sl2, neg_m),
-                                 fmaf(__uint_as_float(sraw[g * 8 + 5]), sl2, neg_m), a.dtype);
-                pk.w = exp2_pack(fmaf(__uint_as_float(sraw[g * 8 + 6]), sl2, neg_m),
-                                 fmaf(__uint_as_float(sraw[g * 8 + 7]), sl2, neg_m), a.dtype);
+                if (a.exp16) {
+                    pk.x = exp2_pack(x[0], x[1], a.dtype);
+                    pk.y = exp2_pack(x[2], x[3], a.dtype);
+                    pk.z = exp2_pack(x[4], x[5], a.dtype);
+                    pk.w = exp2_pack(x[6], x[7], a.dtype);
+                } else {
+                    pk.x = pack2(fast_exp2(x[0]), fast_exp2(x[1]), a.dtype);
+                    pk.y = pack2(fast_exp2(x[2]), fast_exp2(x[3]), a.dtype);
+                    pk.z = pack2(fast_exp2(x[4]), fast_exp2(x[5]), a.dtype);
+                    pk.w = pack2(fast_exp2(x[6]), fast_exp2(x[7]), a.dtype);
+                }
                 const int chunk = g >> 3;  // which 64-column half
                 const int g8 = g & 7;
                 uint8_t* dst = sP + chunk * (kTileQ * 128) + r * 128 + ((g8 ^ (r & 7)) << 4);
@@ -380,6 +394,8 @@ extern "C" int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream_) {
     a.seq_q = p->seq_q; a.seq_kv = p->seq_kv; a.q_rows = p->q_rows; a.k_rows = p->k_rows;
     a.vt_rows = p->vt_rows; a.dtype = p->dtype;
     a.scale_log2 = p->scale * 1.4426950408889634f;
+    static const int exp16 = [] { const char* v = getenv("SFB_ATTN_EXP16"); return v ? atoi(v) : 0; }();
+    a.exp16 = exp16;
     switch (p->head_dim) {
         case 32: return launch_attention<1, 32, 48, 2>(p, a, stream);
         case 40: return launch_attention<1, 48, 48, 2>(p, a, stream);

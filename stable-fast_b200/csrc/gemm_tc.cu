@@ -45,7 +45,23 @@ struct EpiArgs {
     void* k;
     void* vt;
     int heads, head_dim, which_base, seq, q_pitch, q_rows, k_rows, vt_rows, vt_pitch;
+    // LayerNorm folded around the GEMM (see sfb200.h): producer side / consumer side
+    float* rowstats_out;
+    const float* ln_rowstats;
+    const float* ln_colsum;
+    float ln_eps;
+    int ln_dim;
 };
+
+// LayerNorm(x) W^T == rstd * (x W'^T - mean * colsum(W')) + (beta W^T + b), W' = W * gamma.
+// (mean, rstd) of row m from the (sum, sum of squares) its producer GEMMs accumulated.
+__device__ __forceinline__ float2 ln_row_params(const EpiArgs& e, int m) {
+    const float2 st = __ldcg(reinterpret_cast<const float2*>(e.ln_rowstats) + m);
+    const float inv = 1.0f / (float)e.ln_dim;
+    const float mean = st.x * inv;
+    const float var = fmaxf(st.y * inv - mean * mean, 0.f);
+    return make_float2(mean, rsqrtf(var + e.ln_eps));
+}
 
 struct GemmArgs {
     int a_mode;
@@ -83,6 +99,18 @@ __device__ __forceinline__ void add_res8(uint4 r, int dtype, float (&acc)[8]) {
     f = unpack2(r.y, dtype); acc[2] += f.x; acc[3] += f.y;
     f = unpack2(r.z, dtype); acc[4] += f.x; acc[5] += f.y;
     f = unpack2(r.w, dtype); acc[6] += f.x; acc[7] += f.y;
+}
+
+// (sum, sum of squares) of 8 values as they will be stored (rounded to the 16-bit type)
+__device__ __forceinline__ void row_stats8(const float (&acc)[8], int dtype, float& s, float& ss) {
+    const uint4 p = pack8(acc, dtype);
+    const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack2(w[i], dtype);
+        s += f.x + f.y;
+        ss += f.x * f.x + f.y * f.y;
+    }
 }
 
 // 8 consecutive output columns [n, n+8) of row m; `acc` already holds bias / row bias / residual.
@@ -156,8 +184,10 @@ struct GemmSmem {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
     static constexpr int kBiasOffset = kBarOffset + 256;              // fp32 [kBiasSlots][BN]
-    static constexpr int kBiasSlots = 8;                              // images per conv M-tile
+    // images per conv M-tile whose row bias is staged; 3 stages + 4 slots keeps 2 CTAs per SM
+    static constexpr int kBiasSlots = 4;
     static constexpr int kTotal = kBiasOffset + kBiasSlots * BN * 4 + 1024;  // + alignment slack
+    static_assert(STAGES > 3 || 2 * (kTotal + 1024) <= 228 * 1024, "3-stage config must fit twice per SM");
 };
 
 template <int BN, int STAGES>
@@ -205,7 +235,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const EpiArgs& e = args.e;
         const int t = threadIdx.x - 64;
         int img0 = 0, nslots = 1;
-        if (e.rowbias) {
+        const bool rb_staged = e.rowbias && args.box_n <= L::kBiasSlots;
+        if (rb_staged) {
             nslots = args.box_n;
             img0 = (args.box_n == 1) ? (m_tile / args.tiles_per_img) : m_tile * args.box_n;
         }
@@ -215,10 +246,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             float v = 0.f;
             if (n < e.N) {
                 if (e.bias) v = e.bias[n];
-                if (e.rowbias && img0 + slot < args.img_n)
+                if (rb_staged && img0 + slot < args.img_n)
                     v += e.rowbias[(size_t)(img0 + slot) * e.ld_rowbias + n];
             }
             sBias[i] = v;
+        }
+        if (e.ln_rowstats) {  // slot 1: column sums of the gamma-scaled weight
+            for (int c = t; c < BN; c += 128) {
+                const int n = n_tile * BN + c;
+                sBias[BN + c] = (n < e.N) ? e.ln_colsum[n] : 0.f;
+            }
         }
     }
     tc_fence_before();
@@ -291,6 +328,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const EpiArgs& e = args.e;
         const int ncol0 = n_tile * BN;
+        float2 ln = make_float2(0.f, 1.f);
+        if (e.ln_rowstats && valid && args.splits == 1) ln = ln_row_params(e, m);
         if (args.splits > 1) {
             float* wsrow = args.ws + ((size_t)split * e.M + (valid ? m : 0)) * e.N;
 #pragma unroll 1
@@ -322,8 +361,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         float fv[8], fg[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            fv[i] = __uint_as_float(v[j * 8 + i]) + sBias[c * 16 + j * 8 + i];
-                            fg[i] = __uint_as_float(g[j * 8 + i]) + sBias[BN / 2 + c * 16 + j * 8 + i];
+                            const int cv = c * 16 + j * 8 + i, cg = BN / 2 + cv;
+                            float av = __uint_as_float(v[j * 8 + i]), ag = __uint_as_float(g[j * 8 + i]);
+                            if (e.ln_rowstats) {
+                                av = ln.y * (av - ln.x * sBias[BN + cv]);
+                                ag = ln.y * (ag - ln.x * sBias[BN + cg]);
+                            }
+                            fv[i] = av + sBias[cv];
+                            fg[i] = ag + sBias[cg];
                         }
                         epi_geglu8(e, m, nout + j * 8, fv, fg);
                     }
@@ -332,11 +377,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         } else {
             // bias slot of this row (image index inside the tile for the time-embedding row bias)
             const float* brow = sBias;
-            if (e.rowbias) brow += (r / (args.box_h * args.img_w)) * BN;
+            const bool rb_staged = e.rowbias && args.box_n <= L::kBiasSlots;
+            if (rb_staged) brow += (r / (args.box_h * args.img_w)) * BN;
+            // many tiny images per tile (4x4 feature maps): row bias straight from global memory
+            const float* rb_global = nullptr;
+            if (e.rowbias && !rb_staged)
+                rb_global = e.rowbias + (size_t)(m_tile * args.box_n + r / (args.box_h * args.img_w)) * e.ld_rowbias;
             const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE);
             const uint16_t* rrow = reinterpret_cast<const uint16_t*>(e.residual) +
                                    (size_t)(valid ? m : 0) * e.ldr + ncol0;
             constexpr int kHalf = BN / 32;  // 16-column chunks per half tile
+            float rs_sum = 0.f, rs_sq = 0.f;
 #pragma unroll 1
             for (int hb = 0; hb < 2; ++hb) {
                 // issue all residual loads of this half first: one memory latency, not ten
@@ -362,13 +413,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         if (valid && n + j * 8 < e.N) {
                             float f[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                f[i] = __uint_as_float(v[j * 8 + i]) + brow[c * 16 + j * 8 + i];
+                            for (int i = 0; i < 8; ++i) {
+                                float acc = __uint_as_float(v[j * 8 + i]);
+                                if (e.ln_rowstats) acc = ln.y * (acc - ln.x * sBias[BN + c * 16 + j * 8 + i]);
+                                f[i] = acc + brow[c * 16 + j * 8 + i];
+                            }
+                            if (rb_global) add_bias8(rb_global, n + j * 8, f);
                             if (has_res) add_res8(res[cc * 2 + j], e.dtype, f);
+                            if (e.rowstats_out) row_stats8(f, e.dtype, rs_sum, rs_sq);
                             epi_store8(e, m, n + j * 8, f);
                         }
                     }
                 }
+            }
+            if (e.rowstats_out && valid) {
+                atomicAdd(e.rowstats_out + 2 * (size_t)m, rs_sum);
+                atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rs_sq);
             }
         }
     }
@@ -413,6 +473,14 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
         float v[8], g[8];
         sum8(nv, v);
         sum8(ng, g);
+        if (e.ln_rowstats) {
+            const float2 ln = ln_row_params(e, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = ln.y * (v[i] - ln.x * e.ln_colsum[nv + i]);
+                g[i] = ln.y * (g[i] - ln.x * e.ln_colsum[ng + i]);
+            }
+        }
         if (e.bias) {
             add_bias8(e.bias, nv, v);
             add_bias8(e.bias, ng, g);
@@ -421,6 +489,11 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
     } else {
         float acc[8];
         sum8(n, acc);
+        if (e.ln_rowstats) {
+            const float2 ln = ln_row_params(e, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = ln.y * (acc[i] - ln.x * e.ln_colsum[n + i]);
+        }
         if (e.bias) add_bias8(e.bias, n, acc);
         if (e.epi == SFB_EPI_STORE) {
             if (e.rowbias) add_bias8(e.rowbias + (size_t)(m / e.rows_per_img) * e.ld_rowbias, n, acc);
@@ -428,6 +501,12 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
                 add_res8(*reinterpret_cast<const uint4*>(
                              reinterpret_cast<const uint16_t*>(e.residual) + (size_t)m * e.ldr + n),
                          e.dtype, acc);
+        }
+        if (e.rowstats_out) {
+            float rs = 0.f, rss = 0.f;
+            row_stats8(acc, e.dtype, rs, rss);
+            atomicAdd(e.rowstats_out + 2 * (size_t)m, rs);
+            atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rss);
         }
         epi_store8(e, m, n, acc);
     }
@@ -489,8 +568,8 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     } else {
         return fail(SFB_ERR_INVALID, "sfb_gemm: a_mode");
     }
-    if (p->rowbias && (p->a_mode != SFB_A_CONV3X3 || p->box_n > GemmSmem<BN, 3>::kBiasSlots))
-        return fail(SFB_ERR_INVALID, "sfb_gemm: rowbias needs conv mode with <= 8 images per tile");
+    if (p->rowbias && p->a_mode != SFB_A_CONV3X3)
+        return fail(SFB_ERR_INVALID, "sfb_gemm: rowbias (time-embedding add) needs conv mode");
     EpiArgs& e = a.e;
     e.epi = p->epi; e.dtype = p->dtype; e.M = p->M; e.N = p->N;
     e.out = p->out; e.ldo = p->ldo; e.bias = p->bias; e.rowbias = p->rowbias;
@@ -499,6 +578,12 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     e.q = p->q; e.k = p->k; e.vt = p->vt; e.heads = p->heads; e.head_dim = p->head_dim;
     e.which_base = p->which_base; e.seq = p->seq; e.q_pitch = p->q_pitch; e.q_rows = p->q_rows;
     e.k_rows = p->k_rows; e.vt_rows = p->vt_rows; e.vt_pitch = p->vt_pitch;
+    e.rowstats_out = p->rowstats_out; e.ln_rowstats = p->ln_rowstats; e.ln_colsum = p->ln_colsum;
+    e.ln_eps = p->ln_eps; e.ln_dim = p->ln_dim;
+    if (p->ln_rowstats && (!p->ln_colsum || p->ln_dim <= 0 || p->rowbias))
+        return fail(SFB_ERR_INVALID, "sfb_gemm: LayerNorm fold needs ln_colsum / ln_dim and no rowbias");
+    if (p->rowstats_out && p->epi != SFB_EPI_STORE)
+        return fail(SFB_ERR_INVALID, "sfb_gemm: rowstats_out needs the STORE epilogue");
     if (p->epi == SFB_EPI_STORE) {
         if (!p->out || p->ldo % 8) return fail(SFB_ERR_INVALID, "sfb_gemm: out/ldo");
         if (p->residual && p->ldr % 8) return fail(SFB_ERR_INVALID, "sfb_gemm: ldr");

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearArgs
 }
 
 // ---------------------------------------------------------------------------------------
-// conv_in: NCHW (cin <= 8) -> NHWC, 3x3 pad 1.  Weights staged as [9*cin][cout] in smem.
+// conv_in: NCHW (cin <= 8) -> NHWC, 3x3 pad 1.  Weights arrive pre-transposed as
+// [9*cin][cout] (tap-major, cout contiguous) and are staged in smem with 16-byte copies.
 // thread = (pixel slot, group of 8 output channels)
 // ---------------------------------------------------------------------------------------
 struct ConvEdgeArgs {
@@ -108,17 +109,15 @@ struct ConvEdgeArgs {
     int n, h, wd, cin, cout, ld, dtype;
 };
 
-constexpr int kConvInPixelsPerBlock = 12;
+constexpr int kConvInPixelsPerBlock = 24;
 
 __global__ void __launch_bounds__(256) conv_in_kernel(const ConvEdgeArgs a) {
     extern __shared__ uint16_t wsm[];  // [9*cin][cout]
     pdl_launch_dependents();
     pdl_wait();
     const int kk = 9 * a.cin;
-    for (int i = threadIdx.x; i < kk * a.cout; i += blockDim.x) {
-        const int co = i / kk, j = i - co * kk;  // packed weight is [cout][kh][kw][cin]
-        wsm[j * a.cout + co] = a.w[i];
-    }
+    for (int i = threadIdx.x; i < (kk * a.cout) / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(wsm)[i] = reinterpret_cast<const uint4*>(a.w)[i];
     __syncthreads();
     const int ngroups = a.cout / 8;
     const int slots = blockDim.x / ngroups;

@@ -121,6 +121,129 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fused GroupNorm for tensors that fit in the machine's shared memory (the B <= 2 regime the
+// SD-1.5 bs=1 config lives in): ONE launch, x is read from HBM/L2 once.
+//   phase 1  each CTA pulls its slab of rows into shared memory and accumulates group sums
+//            (fp32, one global atomic per (CTA, group, moment));
+//   barrier  grid-wide arrive/spin on a global counter (grid <= 148 CTAs, all co-resident);
+//   phase 2  scale/shift from the finished statistics, y = act(x * scale + shift) from smem.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, unsigned* sync_counter) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    __shared__ float acc[2 * 64];
+    float* scale = reinterpret_cast<float*>(fsm);
+    float* shift = scale + a.c;
+    uint4* slab = reinterpret_cast<uint4*>(fsm + 2 * a.c * sizeof(float));
+    pdl_launch_dependents();
+    pdl_wait();
+    const int img = blockIdx.y;
+    const int by = kGnThreads / a.nvec;
+    const int tx = threadIdx.x % a.nvec;
+    const int ty = threadIdx.x / a.nvec;
+    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads) acc[i] = 0.f;
+    __syncthreads();
+    const int row0 = blockIdx.x * a.rows_per_block;
+    const int row1 = min(row0 + a.rows_per_block, a.hw);
+    if (ty < by) {
+        float s[8], ss[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+        const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
+        for (int row = row0 + ty; row < row1; row += by) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
+            slab[(row - row0) * a.nvec + tx] = v;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2(w[i], a.dtype);
+                s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
+                s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
+            }
+        }
+        int g_run = (tx * 8) / a.cpg;
+        float rs = 0.f, rss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (tx * 8 + i) / a.cpg;
+            if (g != g_run) {
+                atomicAdd(&acc[2 * g_run], rs);
+                atomicAdd(&acc[2 * g_run + 1], rss);
+                g_run = g; rs = 0.f; rss = 0.f;
+            }
+            rs += s[i]; rss += ss[i];
+        }
+        atomicAdd(&acc[2 * g_run], rs);
+        atomicAdd(&acc[2 * g_run + 1], rss);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads)
+        atomicAdd(&a.stats[(size_t)img * a.groups * 2 + i], acc[i]);
+    // ---- grid barrier
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        atomicAdd(sync_counter, 1u);
+        long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned*>(sync_counter) < total) {
+            if (clock64() - t0 > 4000000000LL) __trap();  // not co-resident: fail, do not hang
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    // ---- phase 2
+    const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
+    for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
+        const int g = ch / a.cpg;
+        const float sum = __ldcg(&a.stats[((size_t)img * a.groups + g) * 2]);
+        const float sq = __ldcg(&a.stats[((size_t)img * a.groups + g) * 2 + 1]);
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + a.eps);
+        const float sc = rstd * a.gamma[ch];
+        scale[ch] = sc;
+        shift[ch] = a.beta[ch] - mean * sc;
+    }
+    __syncthreads();
+    if (ty < by) {
+        uint16_t* yb = a.y + (size_t)img * a.hw * a.ldy + tx * 8;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc[i] = scale[tx * 8 + i]; sh[i] = shift[tx * 8 + i]; }
+        for (int row = row0 + ty; row < row1; row += by) {
+            const uint4 v = slab[(row - row0) * a.nvec + tx];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2(w[i], a.dtype);
+                float y0 = f.x * sc[2 * i] + sh[2 * i];
+                float y1 = f.y * sc[2 * i + 1] + sh[2 * i + 1];
+                if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+                o[i] = pack2(y0, y1, a.dtype);
+            }
+            *reinterpret_cast<uint4*>(yb + (size_t)row * a.ldy) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+constexpr int kGnFusedMaxSmem = 200 * 1024;
+
+// grid geometry of the fused kernel; returns false if the tensor does not fit in shared memory
+static bool gn_fused_geometry(const sfb_gn_params* p, int& blocks_per_img, int& rows_per_block,
+                              size_t& smem) {
+    if (p->n <= 0 || p->n > 148) return false;
+    blocks_per_img = 148 / p->n;
+    if (blocks_per_img > p->hw) blocks_per_img = p->hw;
+    if (blocks_per_img < 1) return false;
+    rows_per_block = (p->hw + blocks_per_img - 1) / blocks_per_img;
+    blocks_per_img = (p->hw + rows_per_block - 1) / rows_per_block;
+    smem = (size_t)rows_per_block * p->c * 2 + 2 * (size_t)p->c * sizeof(float);
+    return smem <= (size_t)kGnFusedMaxSmem;
+}
+
 struct LnArgs {
     const uint16_t* x;
     uint16_t* y;
@@ -237,6 +360,39 @@ extern "C" int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream)
                                  2 * p->c * sizeof(float), static_cast<cudaStream_t>(stream), a);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_apply: %s", cudaGetErrorString(err));
     return check_launch("sfb_group_norm_apply");
+}
+
+
+extern "C" int sfb_group_norm_fused_fits(const sfb_gn_params* p) {
+    int bpi, rpb;
+    size_t smem;
+    if (!p || p->c % 8 || p->c <= 0 || p->groups <= 0 || p->c % p->groups || p->c / 8 > kGnThreads) return 0;
+    return gn_fused_geometry(p, bpi, rpb, smem) ? 1 : 0;
+}
+
+extern "C" int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream) {
+    GnArgs a{};
+    int bpi = 1;
+    int rc = make_gn_args(p, a, bpi);
+    if (rc) return rc;
+    if (!p->y || !p->gamma || !p->beta || p->ldy % 8 || !p->sync_counter)
+        return fail(SFB_ERR_INVALID, "group_norm_fused: null/ldy/sync_counter");
+    int rpb;
+    size_t smem;
+    if (!gn_fused_geometry(p, bpi, rpb, smem))
+        return fail(SFB_ERR_INVALID, "group_norm_fused: tensor does not fit in shared memory");
+    a.rows_per_block = rpb;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kGnFusedMaxSmem);
+        if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    cudaError_t err = launch_pdl(gn_fused_kernel, dim3(bpi, p->n), dim3(kGnThreads), smem,
+                                 static_cast<cudaStream_t>(stream), a, p->sync_counter);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused: %s", cudaGetErrorString(err));
+    return check_launch("sfb_group_norm_fused");
 }
 
 extern "C" int sfb_layer_norm(const sfb_ln_params* p, sfb_stream_t stream) {

@@ -30,6 +30,8 @@ class GemmParams(C.Structure):
         ("heads", C.c_int32), ("head_dim", C.c_int32), ("which_base", C.c_int32),
         ("seq", C.c_int32), ("q_pitch", C.c_int32), ("q_rows", C.c_int32),
         ("k_rows", C.c_int32), ("vt_rows", C.c_int32), ("vt_pitch", C.c_int32),
+        ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
+        ("ln_eps", C.c_float), ("ln_dim", C.c_int32),
     ]
 
 
@@ -51,6 +53,7 @@ class GnParams(C.Structure):
         ("n", C.c_int32), ("hw", C.c_int32), ("c", C.c_int32), ("ldx", C.c_int32),
         ("ldy", C.c_int32), ("groups", C.c_int32),
         ("eps", C.c_float), ("silu", C.c_int32), ("dtype", C.c_int32),
+        ("sync_counter", C.c_void_p),
     ]
 
 
@@ -84,6 +87,8 @@ SYMBOLS = {
     "sfb_attention": (C.c_int, [C.POINTER(AttnParams), _VP]),
     "sfb_group_norm_stats": (C.c_int, [C.POINTER(GnParams), _VP]),
     "sfb_group_norm_apply": (C.c_int, [C.POINTER(GnParams), _VP]),
+    "sfb_group_norm_fused_fits": (C.c_int, [C.POINTER(GnParams)]),
+    "sfb_group_norm_fused": (C.c_int, [C.POINTER(GnParams), _VP]),
     "sfb_layer_norm": (C.c_int, [C.POINTER(LnParams), _VP]),
     "sfb_timestep_embed": (C.c_int, [_VP, _I32, _I32, _I32, _F, _VP, _I32, _I32, _VP]),
     "sfb_small_linear": (C.c_int, [C.POINTER(SmallLinearParams), _VP]),

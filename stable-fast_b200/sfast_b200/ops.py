@@ -119,7 +119,7 @@ def choose_splits(m_tiles, n_tiles, nkb):
 
 def gemm_op(name, lib, *, a_map, b_map, M, N, K, dt, out=None, ldo=0, bias=None, rowbias=None,
             rows_per_img=1, ld_rowbias=0, residual=None, ldr=0, epi=EPI_STORE, geglu_n_out=0,
-            conv=None, qkv=None, ws=None, splits=None, keep=()):
+            conv=None, qkv=None, ws=None, splits=None, keep=(), rowstats_out=None, ln=None):
     p = GemmParams()
     p.tmap_a, p.tmap_b = a_map.ptr, b_map.ptr
     p.a_mode = A_CONV3X3 if conv else A_MATRIX
@@ -160,11 +160,15 @@ def gemm_op(name, lib, *, a_map, b_map, M, N, K, dt, out=None, ldo=0, bias=None,
         for f in ("heads", "head_dim", "which_base", "seq", "q_pitch", "q_rows", "k_rows",
                   "vt_rows", "vt_pitch"):
             setattr(p, f, qkv[f])
+    p.rowstats_out = _ptr(rowstats_out)
+    if ln is not None:
+        p.ln_rowstats, p.ln_colsum = _ptr(ln["rowstats"]), _ptr(ln["colsum"])
+        p.ln_eps, p.ln_dim = ln["eps"], ln["dim"]
     esz = 2
     flops = 2 * M * N * K
     nbytes = (M * K + N * K) * esz + M * (geglu_n_out if epi == EPI_GEGLU else N) * esz
     op = Op(name, lib.sfb_gemm, (C.byref(p),), (p, a_map, b_map, out, bias, rowbias, residual, ws,
-                                               qkv, keep), flops, nbytes)
+                                               qkv, keep, rowstats_out, ln), flops, nbytes)
     return op
 
 
@@ -187,14 +191,33 @@ def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq
     return Op(name, lib.sfb_attention, (C.byref(p),), (p, tq, tk, tv, q, k, vt, out), flops, nbytes)
 
 
-def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, dt):
+def gn_fused_fits(n, hw, c, groups):
+    """Python mirror of sfb_group_norm_fused_fits (used for dry plans; the C predicate is the
+    authority on a GPU box)."""
+    if n <= 0 or n > NUM_SMS or c % 8 or c % groups or c // 8 > 512:
+        return False
+    bpi = max(1, min(NUM_SMS // n, hw))
+    rpb = (hw + bpi - 1) // bpi
+    return rpb * c * 2 + 2 * c * 4 <= 200 * 1024
+
+
+def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, dt, sync=None,
+           dry=False):
+    """GroupNorm(+SiLU): one fused launch when the tensor fits in shared memory (stats + apply
+    with a grid barrier, x read once), else the two-pass stats / apply kernels."""
     p = GnParams()
     p.x, p.y = x.ptr, y.ptr
     p.gamma, p.beta, p.stats = _ptr(gamma), _ptr(beta), _ptr(stats)
     p.n, p.hw, p.c, p.ldx, p.ldy, p.groups = x.n, x.h * x.w, x.c, x.ld, y.ld, groups
     p.eps, p.silu, p.dtype = eps, int(silu), dtype_code(dt)
-    keep = (p, x.buf, y.buf, gamma, beta, stats)
+    p.sync_counter = _ptr(sync)
+    keep = (p, x.buf, y.buf, gamma, beta, stats, sync)
     nb = x.rows * x.c * 2
+    if sync is not None:
+        fits = gn_fused_fits(p.n, p.hw, p.c, groups) if dry else bool(
+            lib.sfb_group_norm_fused_fits(C.byref(p)))
+        if fits:
+            return [Op(name + ".fused", lib.sfb_group_norm_fused, (C.byref(p),), keep, 0, 2 * nb)]
     return [Op(name + ".stats", lib.sfb_group_norm_stats, (C.byref(p),), keep, 0, nb),
             Op(name + ".apply", lib.sfb_group_norm_apply, (C.byref(p),), keep, 0, 2 * nb)]
 
@@ -249,21 +272,47 @@ def pack_conv3x3(w, dt):
     return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dt).contiguous()
 
 
-def pack_geglu(w, b, dt):
+def pack_conv_in(w, dt):
+    """[cout, cin, 3, 3] -> [(kh, kw, cin), cout] (tap-major, cout contiguous) for sfb_conv_in"""
+    return w.detach().permute(2, 3, 1, 0).reshape(-1, w.shape[0]).to(dt).contiguous()
+
+
+def pack_geglu(w, b, dt, extra=None):
     """GEGLU projection [2*inner, k] (value rows first, gate rows second; reference chunk order
     /root/reference/src/sfast/jit/passes/__init__.py:643-648) -> tile-interleaved
-    [ceil(inner/80)*160, k]: per 160-row tile, 80 value rows then the matching 80 gate rows."""
+    [ceil(inner/80)*160, k]: per 160-row tile, 80 value rows then the matching 80 gate rows.
+    `extra`: optional per-row fp32 vector permuted the same way (LayerNorm-fold column sums)."""
     inner = w.shape[0] // 2
     half = BN // 2
     tiles = (inner + half - 1) // half
     wp = torch.zeros(tiles * BN, w.shape[1], dtype=dt, device=w.device)
     bp = torch.zeros(tiles * BN, dtype=torch.float32, device=w.device)
+    ep = torch.zeros(tiles * BN, dtype=torch.float32, device=w.device) if extra is not None else None
     wv, wg = w.detach()[:inner], w.detach()[inner:]
     for t in range(tiles):
         lo, hi = t * half, min((t + 1) * half, inner)
-        wp[t * BN:t * BN + hi - lo] = wv[lo:hi].to(dt)
-        wp[t * BN + half:t * BN + half + hi - lo] = wg[lo:hi].to(dt)
+        v0, g0 = t * BN, t * BN + half
+        wp[v0:v0 + hi - lo] = wv[lo:hi].to(dt)
+        wp[g0:g0 + hi - lo] = wg[lo:hi].to(dt)
         if b is not None:
-            bp[t * BN:t * BN + hi - lo] = b.detach()[lo:hi].float()
-            bp[t * BN + half:t * BN + half + hi - lo] = b.detach()[inner + lo:inner + hi].float()
+            bp[v0:v0 + hi - lo] = b.detach()[lo:hi].float()
+            bp[g0:g0 + hi - lo] = b.detach()[inner + lo:inner + hi].float()
+        if extra is not None:
+            ep[v0:v0 + hi - lo] = extra[lo:hi].float()
+            ep[g0:g0 + hi - lo] = extra[inner + lo:inner + hi].float()
+    if extra is not None:
+        return wp, bp, inner, ep
     return wp, bp, inner
+
+
+def fold_layer_norm(w, b, gamma, beta, dt):
+    """Fold LayerNorm(gamma, beta) into the following linear layer y = LN(x) W^T + b:
+    returns (W' = W * gamma in the 16-bit type, bias' = beta W^T + b, colsum = sum_k W'[n, k]
+    taken from the ROUNDED W' so that the epilogue's mean correction matches the MMA exactly)."""
+    wf = w.detach().float()
+    wp = (wf * gamma.detach().float()[None, :]).to(dt)
+    colsum = wp.float().sum(dim=1)
+    bias = wf @ beta.detach().float()
+    if b is not None:
+        bias = bias + b.detach().float()
+    return wp, bias.contiguous(), colsum.contiguous()

@@ -83,12 +83,40 @@ class PackedWeights:
             self._cache[key] = ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)
         return self._cache[key]
 
+    def conv_in_weight(self, name):
+        key = ("cin", name)
+        if key not in self._cache:
+            self._cache[key] = ops.pack_conv_in(self._raw(name).to(self.device), self.dtype)
+        return self._cache[key]
+
     def cat_matrix(self, names):
         key = ("cat",) + tuple(names)
         if key not in self._cache:
             w = torch.cat([self._raw(n) for n in names], 0)
             w = w.to(device=self.device, dtype=self.dtype).contiguous()
             self._cache[key] = self._mat(w)
+        return self._cache[key]
+
+    def ln_matrix(self, names, ln_prefix):
+        """cat(names) with LayerNorm `ln_prefix` folded in: (Mat, bias', colsum)."""
+        key = ("lnmat", ln_prefix) + tuple(names)
+        if key not in self._cache:
+            w = torch.cat([self._raw(n) for n in names], 0).to(self.device)
+            wp, bias, colsum = ops.fold_layer_norm(
+                w, None, self._raw(ln_prefix + ".weight").to(self.device),
+                self._raw(ln_prefix + ".bias").to(self.device), self.dtype)
+            self._cache[key] = (self._mat(wp.contiguous()), bias, colsum)
+        return self._cache[key]
+
+    def ln_geglu(self, prefix, ln_prefix):
+        key = ("lngeglu", prefix, ln_prefix)
+        if key not in self._cache:
+            wp, bias, colsum = ops.fold_layer_norm(
+                self._raw(prefix + ".weight").to(self.device), self._raw(prefix + ".bias").to(self.device),
+                self._raw(ln_prefix + ".weight").to(self.device),
+                self._raw(ln_prefix + ".bias").to(self.device), self.dtype)
+            wt, bp, inner, cs = ops.pack_geglu(wp, bias, self.dtype, extra=colsum)
+            self._cache[key] = (self._mat(wt), bp, inner, cs)
         return self._cache[key]
 
     def geglu(self, prefix):
@@ -134,10 +162,35 @@ class UNetPlan:
         n_gn = sum(2 for _ in spec.all_resnets()) + 1
         for blk in spec.down + [spec.mid] + spec.up:
             n_gn += sum(1 for t in blk.attentions if t is not None)
-        self.gn_stats = self._alloc((n_gn, batch, spec.groups, 2), torch.float32)
+        # (+4 floats per slot: the fused kernel's grid-barrier counter)
+        self.gn_stats = self._alloc((n_gn, batch * spec.groups * 2 + 4), torch.float32)
+        # folded-LayerNorm row statistics: [rows, 2] fp32 per LayerNorm, zeroed once per step
+        self._ln_used = 0
+        self._ln_slots = []
+        self.ln_arena = self._alloc((max(self._ln_arena_floats(), 2),), torch.float32)
         self.ws = None
         self._ws_need = 0
         self._build()
+        assert self._ln_used <= self.ln_arena.numel(), (self._ln_used, self.ln_arena.numel())
+
+    def _ln_arena_floats(self):
+        """3 * depth LayerNorms per transformer, each [B*h*w, 2] floats at its resolution."""
+        spec, tot = self.spec, 0
+        h, w = self.H, self.W
+        for blk in spec.down:
+            tot += sum(3 * t.depth * self.B * h * w * 2 for t in blk.attentions if t is not None)
+            if blk.sampler:
+                h, w = h // 2, w // 2
+        tot += 3 * spec.mid.attentions[0].depth * self.B * h * w * 2
+        for blk in spec.up:
+            tot += sum(3 * t.depth * self.B * h * w * 2 for t in blk.attentions if t is not None)
+            if blk.sampler:
+                h, w = h * 2, w * 2
+        return tot
+
+    def _ln_view(self, slot):
+        _, off, rows = slot
+        return self.ln_arena[off:off + rows * 2]
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self, shape, dtype, zero=True):
@@ -179,11 +232,12 @@ class UNetPlan:
 
     def group_norm(self, name, x: Act, prefix, silu, eps):
         y = self.act("gn_out", x.n, x.h, x.w, x.c)
-        stats = self.gn_stats[self._gn_count]
+        slot = self.gn_stats[self._gn_count]
         self._gn_count += 1
         self._emit(ops.gn_ops(name, self.lib_or_dry(), x=x, y=y, gamma=self.w.f32(prefix + ".weight"),
-                              beta=self.w.f32(prefix + ".bias"), stats=stats,
-                              groups=self.spec.groups, eps=eps, silu=silu, dt=self.dt))
+                              beta=self.w.f32(prefix + ".bias"), stats=slot, sync=slot[-4:],
+                              groups=self.spec.groups, eps=eps, silu=silu, dt=self.dt,
+                              dry=self.dry))
         return y
 
     def conv3x3(self, name, x: Act, wname, dst: Act, stride=1, rowbias=None, residual: Act = None):
@@ -204,9 +258,10 @@ class UNetPlan:
             kw.update(residual=residual.ptr, ldr=residual.ld)
         self._emit(self._gemm(name, **kw))
 
-    def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None):
+    def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None, rowstats_out=None):
         kw = dict(a_map=self._a_matrix(x), b_map=wm.map, M=x.rows, N=wm.n, K=x.c, dt=self.dt,
-                  out=dst.ptr, ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, wm))
+                  out=dst.ptr, ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, wm),
+                  rowstats_out=rowstats_out)
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
         self._emit(self._gemm(name, **kw))
@@ -228,9 +283,11 @@ class UNetPlan:
             res = x
         self.conv3x3(p + ".conv2", a2, p + ".conv2", dst, residual=res)
 
-    def attention(self, name, hs: Act, ln: Act, blk, t, cross):
-        """attn(ln) + hs -> hs (in place).  Self-attention: fused QKV projection; cross: Q from
-        the tokens, K/V from the text embedding."""
+    def attention(self, name, hs: Act, ln_prefix, ln_stats, blk, t, cross, stats_next):
+        """attn(LayerNorm(hs)) + hs -> hs (in place).  The LayerNorm is folded into the Q(KV)
+        projection (gamma-scaled weights + epilogue mean/rstd correction from `ln_stats`, the row
+        sums the previous GEMM accumulated); `stats_next` receives the row sums of the new hs.
+        Self-attention: fused QKV projection; cross: Q from the tokens, K/V from the text."""
         B, S, C, H, D = hs.n, hs.h * hs.w, t.dim, t.heads, t.head_dim
         dv = _round_up(D + 1, 16)  # + the all-ones row that yields the softmax denominator
         q_pitch = _round_up(D, 64)
@@ -246,16 +303,15 @@ class UNetPlan:
             vt.view(B * H, dv, vt_pitch)[:, D, :] = 1.0
         qkv = dict(q=q, k=k, vt=vt, heads=H, head_dim=D, q_pitch=q_pitch, q_rows=S, k_rows=skv,
                    vt_rows=dv, vt_pitch=vt_pitch)
-        if not cross:
-            w = self.w.cat_matrix([f"{a}.to_q.weight", f"{a}.to_k.weight", f"{a}.to_v.weight"])
-            self._emit(self._gemm(a + ".qkv", a_map=self._a_matrix(ln), b_map=w.map, M=ln.rows,
-                                  N=3 * C, K=C, dt=self.dt, epi=EPI_QKV,
-                                  qkv=dict(qkv, which_base=0, seq=S), keep=(ln.buf, w)))
-        else:
-            wq = self.w.matrix(f"{a}.to_q.weight")
-            self._emit(self._gemm(a + ".q", a_map=self._a_matrix(ln), b_map=wq.map, M=ln.rows, N=C,
-                                  K=C, dt=self.dt, epi=EPI_QKV,
-                                  qkv=dict(qkv, which_base=0, seq=S), keep=(ln.buf, wq)))
+        names = [f"{a}.to_q.weight"] if cross else [f"{a}.to_q.weight", f"{a}.to_k.weight",
+                                                    f"{a}.to_v.weight"]
+        wm, bias, colsum = self.w.ln_matrix(names, ln_prefix)
+        self._emit(self._gemm(a + (".q" if cross else ".qkv"), a_map=self._a_matrix(hs), b_map=wm.map,
+                              M=hs.rows, N=wm.n, K=C, dt=self.dt, epi=EPI_QKV, bias=bias,
+                              qkv=dict(qkv, which_base=0, seq=S),
+                              ln=dict(rowstats=ln_stats, colsum=colsum, eps=1e-5, dim=C),
+                              keep=(hs.buf, wm, colsum)))
+        if cross:
             wkv = self.w.cat_matrix([f"{a}.to_k.weight", f"{a}.to_v.weight"])
             ehs = Act(self.ehs_in, B, 1, self.ctx_len, self.spec.cross_attention_dim)
             self._emit(self._gemm(a + ".kv", a_map=self._a_matrix(ehs), b_map=wkv.map, M=ehs.rows,
@@ -268,7 +324,7 @@ class UNetPlan:
                                     k_rows=skv, vt_rows=dv, q_pitch=q_pitch, vt_pitch=vt_pitch,
                                     dt=self.dt, dry=self.dry))
         self.linear(a + ".to_out", ao, self.w.matrix(f"{a}.to_out.0.weight"),
-                    self.w.f32(f"{a}.to_out.0.bias"), hs, residual=hs)
+                    self.w.f32(f"{a}.to_out.0.bias"), hs, residual=hs, rowstats_out=stats_next)
 
     def layer_norm(self, name, x: Act, prefix):
         y = self.act("ln_out", x.n, x.h, x.w, x.c)
@@ -277,27 +333,36 @@ class UNetPlan:
                              eps=1e-5, dt=self.dt))
         return y
 
+    def ln_slot(self, rows):
+        """[rows, 2] fp32 (sum, sum of squares) accumulator of one folded LayerNorm."""
+        off = self._ln_used
+        self._ln_used += rows * 2
+        self._ln_slots.append((off, rows))
+        return ("ln_slot", off, rows)
+
     def transformer(self, t, x: Act, dst: Act):
         p = t.prefix
         a1 = self.group_norm(p + ".norm", x, p + ".norm", False, 1e-6)
         hs = self.act("tf_hidden", x.n, x.h, x.w, t.dim)
+        st = self._ln_view(self.ln_slot(hs.rows))
         self.linear(p + ".proj_in", a1, self.w.matrix(p + ".proj_in.weight"),
-                    self.w.f32(p + ".proj_in.bias"), hs)
+                    self.w.f32(p + ".proj_in.bias"), hs, rowstats_out=st)
         for d in range(t.depth):
             b = f"{p}.transformer_blocks.{d}"
-            ln = self.layer_norm(b + ".norm1", hs, b + ".norm1")
-            self.attention(b + ".attn1", hs, ln, b, t, cross=False)
-            ln = self.layer_norm(b + ".norm2", hs, b + ".norm2")
-            self.attention(b + ".attn2", hs, ln, b, t, cross=True)
-            ln = self.layer_norm(b + ".norm3", hs, b + ".norm3")
-            gm, bp, inner = self.w.geglu(b + ".ff.net.0.proj")
+            st2 = self._ln_view(self.ln_slot(hs.rows))
+            self.attention(b + ".attn1", hs, b + ".norm1", st, b, t, cross=False, stats_next=st2)
+            st3 = self._ln_view(self.ln_slot(hs.rows))
+            self.attention(b + ".attn2", hs, b + ".norm2", st2, b, t, cross=True, stats_next=st3)
+            gm, bp, inner, colsum = self.w.ln_geglu(b + ".ff.net.0.proj", b + ".norm3")
             ff = self.act("ff_act", x.n, x.h, x.w, inner)
-            self._emit(self._gemm(b + ".ff.geglu", a_map=self._a_matrix(ln), b_map=gm.map, M=ln.rows,
+            self._emit(self._gemm(b + ".ff.geglu", a_map=self._a_matrix(hs), b_map=gm.map, M=hs.rows,
                                   N=gm.n, K=t.dim, dt=self.dt, out=ff.ptr, ldo=inner,
                                   bias=bp, epi=EPI_GEGLU, geglu_n_out=inner,
-                                  keep=(ln.buf, ff.buf, gm)))
+                                  ln=dict(rowstats=st3, colsum=colsum, eps=1e-5, dim=t.dim),
+                                  keep=(hs.buf, ff.buf, gm, colsum)))
+            st = self._ln_view(self.ln_slot(hs.rows)) if d + 1 < t.depth else None
             self.linear(b + ".ff.out", ff, self.w.matrix(b + ".ff.net.2.weight"),
-                        self.w.f32(b + ".ff.net.2.bias"), hs, residual=hs)
+                        self.w.f32(b + ".ff.net.2.bias"), hs, residual=hs, rowstats_out=st)
         self.linear(p + ".proj_out", hs, self.w.matrix(p + ".proj_out.weight"),
                     self.w.f32(p + ".proj_out.bias"), dst, residual=x)
 
@@ -363,6 +428,8 @@ class UNetPlan:
         self._emit(Op("gn_stats.zero", lib.sfb_memset,
                       (_ptr(self.gn_stats), 0,
                        self.gn_stats.numel() * 4), (self.gn_stats,)))
+        self._emit(Op("ln_stats.zero", lib.sfb_memset,
+                      (_ptr(self.ln_arena), 0, self.ln_arena.numel() * 4), (self.ln_arena,)))
         self.time_embedding()
 
         # ---- shape pass: where does every skip tensor live (inside its consumer's concat buffer)
@@ -391,7 +458,7 @@ class UNetPlan:
         # ---- conv_in
         c0 = spec.block_out_channels[0]
         x = skip_dst[0]
-        w_in = self.w.conv3x3_plain("conv_in.weight")
+        w_in = self.w.conv_in_weight("conv_in.weight")
         self._emit(Op("conv_in", lib.sfb_conv_in,
                       (_ptr(self.sample_in),
                        _ptr(w_in),

@@ -191,7 +191,7 @@ def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=
 
 
 def check_group_norm(n=2, c=320, h=32, w=32, silu=True, dt=torch.float16, pitch_extra=0, eps=1e-5,
-                     seed=5):
+                     seed=5, fused=True):
     lib = _lib.lib()
     torch.manual_seed(seed)
     ld = c + pitch_extra
@@ -201,9 +201,11 @@ def check_group_norm(n=2, c=320, h=32, w=32, silu=True, dt=torch.float16, pitch_
     y = Act(yb, n, h, w, c)
     gamma = torch.randn(c, device=DEV)
     beta = torch.randn(c, device=DEV)
-    stats = torch.zeros(n, 32, 2, device=DEV)
-    for op in ops.gn_ops("gn", lib, x=x, y=y, gamma=gamma, beta=beta, stats=stats, groups=32,
-                         eps=eps, silu=silu, dt=dt):
+    stats = torch.zeros(n * 32 * 2 + 4, device=DEV)
+    gops = ops.gn_ops("gn", lib, x=x, y=y, gamma=gamma, beta=beta, stats=stats, groups=32, eps=eps,
+                      silu=silu, dt=dt, sync=stats[-4:] if fused else None)
+    assert len(gops) == (1 if fused else 2), [o.name for o in gops]
+    for op in gops:
         op.launch(_stream())
     torch.cuda.synchronize()
     ref = F.group_norm(x.tensor().permute(0, 3, 1, 2).float(), 32, gamma, beta, eps)
@@ -260,7 +262,7 @@ def check_conv_in(n=2, h=64, w=64, cin=4, cout=320, dt=torch.float16, seed=8):
     x = _rand(n, cin, h, w, dt=dt, seed=seed)
     wt = _rand(cout, cin, 3, 3, dt=dt, scale=0.2)
     b = torch.randn(cout, device=DEV)
-    wp = ops.pack_conv3x3(wt, dt)
+    wp = ops.pack_conv_in(wt, dt)
     y = torch.zeros(n, h, w, cout, device=DEV, dtype=dt)
     _lib.check(lib.sfb_conv_in(x.data_ptr(), wp.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, w,
                                cin, cout, cout, ops.dtype_code(dt), _stream()))
@@ -292,6 +294,54 @@ def check_upsample(n=2, h=16, w=16, c=1280, dt=torch.float16):
     ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
     return rel_err(y, ref.permute(0, 2, 3, 1))
 
+
+
+
+def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=1, splits_c=1, seed=12):
+    """LayerNorm folded around two GEMMs: the producer accumulates per-row (sum, sum of squares)
+    in its epilogue, the consumer runs on the RAW activation with gamma-scaled weights and
+    corrects with mean / rstd in its epilogue.  Reference: F.layer_norm then the linear / GEGLU."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    a = _rand(M, C, dt=dt)
+    w0 = _rand(C, C, dt=dt, scale=1 / math.sqrt(C))
+    res = _rand(M, C, dt=dt, scale=2.0) + 0.5          # non-zero-mean rows
+    x = torch.zeros(M, C, device=DEV, dtype=dt)
+    stats = torch.zeros(M, 2, device=DEV)
+    ws = torch.empty(16 * M * max(N, C) * 2, device=DEV, dtype=torch.float32)
+    ops.gemm_op("producer", lib, a_map=ops.matrix_map(a.data_ptr(), M, C, C, 128), b_map=ops.Mat(w0).map,
+                M=M, N=C, K=C, dt=dt, out=x, ldo=C, residual=res, ldr=C, ws=ws, splits=splits_p,
+                rowstats_out=stats).launch(_stream())
+    gamma = torch.randn(C, device=DEV) * 0.5 + 1.0
+    beta = torch.randn(C, device=DEV) * 0.3
+    if mode == "geglu":
+        inner = N
+        w = _rand(2 * inner, C, dt=dt, scale=1 / math.sqrt(C))
+        b = torch.randn(2 * inner, device=DEV) * 0.1
+        wp, bias, colsum = ops.fold_layer_norm(w, b, gamma, beta, dt)
+        wt, bp, _, cs = ops.pack_geglu(wp, bias, dt, extra=colsum)
+        out = torch.zeros(M, inner, device=DEV, dtype=dt)
+        ops.gemm_op("consumer", lib, a_map=ops.matrix_map(x.data_ptr(), M, C, C, 128),
+                    b_map=ops.Mat(wt).map, M=M, N=wt.shape[0], K=C, dt=dt, out=out, ldo=inner, bias=bp,
+                    epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws, splits=splits_c,
+                    ln=dict(rowstats=stats, colsum=cs, eps=1e-5, dim=C)).launch(_stream())
+    else:
+        w = _rand(N, C, dt=dt, scale=1 / math.sqrt(C))
+        b = torch.randn(N, device=DEV) * 0.1
+        wp, bias, colsum = ops.fold_layer_norm(w, b, gamma, beta, dt)
+        out = torch.zeros(M, N, device=DEV, dtype=dt)
+        ops.gemm_op("consumer", lib, a_map=ops.matrix_map(x.data_ptr(), M, C, C, 128),
+                    b_map=ops.Mat(wp.contiguous()).map, M=M, N=N, K=C, dt=dt, out=out, ldo=N, bias=bias,
+                    ws=ws, splits=splits_c,
+                    ln=dict(rowstats=stats, colsum=colsum, eps=1e-5, dim=C)).launch(_stream())
+    torch.cuda.synchronize()
+    xr = (a.float() @ w0.float().t() + res.float())
+    e0 = rel_err(x, xr)
+    y = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.float().t() + b
+    if mode == "geglu":
+        h, g = y.chunk(2, dim=-1)
+        y = h * F.gelu(g)
+    return max(e0, rel_err(out, y))
 
 
 def diag_gemm(dt=torch.float16):
@@ -347,6 +397,11 @@ CHECKS = {
     "geglu": (lambda: check_geglu(256, 320, 1280), 2e-2),
     "geglu_ragged": (lambda: check_geglu(100, 64, 256), 2e-2),
     "geglu_splitk": (lambda: check_geglu(128, 1280, 5120, splits=4), 2e-2),
+    "ln_fold": (lambda: check_ln_fold(300, 320, 960), 5e-3),
+    "ln_fold_1280": (lambda: check_ln_fold(512, 1280, 1280), 5e-3),
+    "ln_fold_geglu": (lambda: check_ln_fold(300, 320, 1280, mode="geglu"), 2e-2),
+    "ln_fold_splitk": (lambda: check_ln_fold(256, 1280, 1280, splits_p=2, splits_c=2), 5e-3),
+    "ln_fold_geglu_splitk": (lambda: check_ln_fold(128, 1280, 5120, mode="geglu", splits_c=2), 2e-2),
     "conv_64": (lambda: check_conv(2, 64, 64, 320, 320, splits=1), 2e-3),
     "conv_32": (lambda: check_conv(2, 32, 32, 640, 640, splits=1), 2e-3),
     "conv_16_splitk": (lambda: check_conv(2, 16, 16, 1280, 1280), 2e-3),
@@ -374,6 +429,9 @@ CHECKS = {
     "group_norm_1920_pitch": (lambda: check_group_norm(2, 1920, 16, 16, True, pitch_extra=640), 1e-2),
     "group_norm_2560": (lambda: check_group_norm(3, 2560, 8, 8, True), 1e-2),
     "group_norm_64": (lambda: check_group_norm(1, 64, 32, 32, True), 1e-2),
+    "group_norm_two_pass": (lambda: check_group_norm(2, 320, 32, 32, True, fused=False), 1e-2),
+    "group_norm_two_pass_big": (lambda: check_group_norm(16, 320, 64, 64, True, fused=False), 1e-2),
+    "group_norm_fused_64x64": (lambda: check_group_norm(2, 960, 64, 64, True, pitch_extra=0), 1e-2),
     "layer_norm": (lambda: check_layer_norm(1151, 1280), 1e-2),
     "layer_norm_320": (lambda: check_layer_norm(8192, 320), 1e-2),
     "timestep_embed": (lambda: check_timestep_embed(), 2e-3),

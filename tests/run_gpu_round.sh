@@ -3,6 +3,12 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt
+if [ "$RUN_MICRO" == "1" ]; then
+  timeout 120 tests/microbench/softmax_pipes > gpurun_out/softmax_pipes.jsonl 2>&1
+  SFB_ATTN_EXP16=0 timeout 300 python tests/attn_bench.py > gpurun_out/attn_bench.jsonl 2>gpurun_out/attn_bench.err
+  SFB_ATTN_EXP16=1 timeout 300 python tests/attn_bench.py >> gpurun_out/attn_bench.jsonl 2>>gpurun_out/attn_bench.err
+  cat gpurun_out/softmax_pipes.jsonl gpurun_out/attn_bench.jsonl
+fi
 if [ "$RUN_CHECKS" == "1" ]; then
   timeout 600 python tests/kernel_checks.py > gpurun_out/kernel_checks.jsonl 2> gpurun_out/kernel_checks.err
   echo "checks rc=$?" >> gpurun_out/kernel_checks.jsonl

@@ -67,7 +67,8 @@ def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     plan = _dry_plan(uo.sd15_config(), 2, 64, 64)
     names = [op.fn.name for op in plan.ops if op.fn is not None]
     # 61 GroupNorms, 48 LayerNorms, 32 attention calls, 3 upsamples
-    assert names.count("sfb_group_norm_apply") == 61
+    # B = 2 tensors fit in shared memory: all 61 GroupNorms take the single-launch fused kernel
+    assert names.count("sfb_group_norm_fused") == 61 and names.count("sfb_group_norm_apply") == 0
     assert names.count("sfb_layer_norm") == 48
     assert names.count("sfb_attention") == 32
     assert names.count("sfb_upsample2x") == 3
@@ -156,7 +157,7 @@ def test_struct_layouts_match_the_header():
     # sizes computed by hand from include/sfb200.h with natural alignment
     assert ctypes.sizeof(_lib.AttnParams) == 4 * 8 + 10 * 4
     assert ctypes.sizeof(_lib.LnParams) == 4 * 8 + 6 * 4
-    assert ctypes.sizeof(_lib.GnParams) == 5 * 8 + 9 * 4 + 4
+    assert ctypes.sizeof(_lib.GnParams) == 5 * 8 + 9 * 4 + 4 + 8
     assert ctypes.sizeof(_lib.SmallLinearParams) == 6 * 8 + 8 * 4
 
 
