@@ -124,6 +124,12 @@ typedef struct sfb_gemm_params {
     int32_t vt_rows;         /* rows per (b, head) in V^T: (head_dim + 1) rounded up to 16; row
                               * `head_dim` must be pre-filled with ones (softmax denominator) */
     int32_t vt_pitch;        /* element pitch of a V^T row */
+    /* Thread-block cluster with TMA multicast (0/1 = off).  cluster_n (1|2) CTAs along N share one
+     * A tile: each loads 1/cluster_n of it (tmap_a box = 128/cluster_n rows; for the conv the box
+     * is split along `a_part_dim` (1 = w, 2 = h, 3 = n) into parts of `a_part_ext`) and multicasts.
+     * cluster_m (1|2|4) CTAs along M share one weight tile (tmap_b box = 160/cluster_m rows).
+     * The tile grid must be divisible by the cluster shape. */
+    int32_t cluster_n, cluster_m, a_part_dim, a_part_ext;
     /* LayerNorm folded around the GEMM (replaces sfast_triton::layer_norm,
      * /root/reference/src/sfast/triton/ops/layer_norm.py:51-133, as a separate pass):
      *   producer (SFB_EPI_STORE): rowstats_out[m] += (sum, sum of squares) of the stored row;

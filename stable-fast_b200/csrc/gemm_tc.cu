@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "host.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace sfb {
@@ -71,6 +72,11 @@ struct GemmArgs {
     float* ws;
     // conv geometry
     int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
+    // thread-block cluster (cx along N: the cx CTAs of one M-tile each load 1/cx of the A tile and
+    // multicast it; cy along M: the cy CTAs of one N-tile each load 1/cy of the weight tile)
+    int cx, cy;
+    int a_part_dim;  // conv: which box dim the A tile is split along (1 = w, 2 = h, 3 = n)
+    int a_part_ext;  // extent of one part along that dim (output pixels / rows / images)
     EpiArgs e;
 };
 
@@ -220,11 +226,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_prefetch_desc(&tma_b);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            // released by every CTA whose stage this CTA's multicasts write into
+            mbar_init(&empty_bar[i], args.cx + args.cy - 1);
         }
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
+    const bool clustered = args.cx * args.cy > 1;
+    const int cix = clustered ? (int)cluster_ctaid_x() : 0;
+    const int ciy = clustered ? (int)cluster_ctaid_y() : 0;
+    // CTAs sharing this CTA's A tile (same M-tile: all cix) / weight tile (same N-tile: all ciy)
+    const uint16_t mask_a = (uint16_t)(((1u << args.cx) - 1u) << (ciy * args.cx));
+    uint16_t mask_b = 0;
+    for (int y = 0; y < args.cy; ++y) mask_b |= (uint16_t)(1u << (y * args.cx + cix));
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
     // Everything above overlaps the previous kernel's tail (programmatic dependent launch);
     // global memory produced by it may only be touched after this point.
@@ -259,7 +273,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (clustered) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -280,19 +295,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_expect_tx(&full_bar[stage], L::kStageBytes);
                 const int kb = kb_begin + i;
+                uint8_t* dstA = sA + stage * L::kABytes + cix * (L::kABytes / args.cx);
+                uint8_t* dstB = sB + stage * L::kBBytes + ciy * (L::kBBytes / args.cy);
+                // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous BN x 64 block
+                const int b_row = (n_tile * args.nkb_total + kb) * BN + ciy * (BN / args.cy);
                 if (args.a_mode == SFB_A_MATRIX) {
-                    tma_load_2d(sA + stage * L::kABytes, &tma_a, &full_bar[stage], kb * BK,
-                                m_tile * BM);
+                    const int a_row = m_tile * BM + cix * (BM / args.cx);
+                    if (args.cx > 1) tma_load_2d_mc(dstA, &tma_a, &full_bar[stage], kb * BK, a_row, mask_a);
+                    else tma_load_2d(dstA, &tma_a, &full_bar[stage], kb * BK, a_row);
                 } else {
                     const int tap = kb / args.cpb;
                     const int cc = kb - tap * args.cpb;
                     const int kh = tap / 3, kw = tap - kh * 3;
-                    tma_load_4d(sA + stage * L::kABytes, &tma_a, &full_bar[stage], cc * BK,
-                                kw - 1, h0 * args.conv_stride + kh - 1, n0);
+                    int c1 = kw - 1, c2 = h0 * args.conv_stride + kh - 1, c3 = n0;
+                    if (args.cx > 1) {
+                        const int off = cix * args.a_part_ext;
+                        if (args.a_part_dim == 1) c1 += off * args.conv_stride;
+                        else if (args.a_part_dim == 2) c2 += off * args.conv_stride;
+                        else c3 += off;
+                        tma_load_4d_mc(dstA, &tma_a, &full_bar[stage], cc * BK, c1, c2, c3, mask_a);
+                    } else {
+                        tma_load_4d(dstA, &tma_a, &full_bar[stage], cc * BK, c1, c2, c3);
+                    }
                 }
-                // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous BN x 64 block
-                tma_load_2d(sB + stage * L::kBBytes, &tma_b, &full_bar[stage], 0,
-                            (n_tile * args.nkb_total + kb) * BN);
+                if (args.cy > 1) tma_load_2d_mc(dstB, &tma_b, &full_bar[stage], 0, b_row, mask_b);
+                else tma_load_2d(dstB, &tma_b, &full_bar[stage], 0, b_row);
             }
         }
         __syncwarp();
@@ -312,7 +339,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
                                 (i | k) != 0);
                 }
-                umma_commit(&empty_bar[stage]);
+                if (clustered) umma_commit_mc(&empty_bar[stage], (uint16_t)(mask_a | mask_b));
+                else umma_commit(&empty_bar[stage]);
             }
             umma_commit(tmem_full_bar);
         }
@@ -434,7 +462,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
+    // no CTA may exit while cluster peers can still signal its barriers
+    if (clustered) cluster_sync_all();
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
@@ -527,8 +557,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
         if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
         attr_set = true;
     }
-    cudaError_t err = launch_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(kGemmThreads), L::kTotal, stream,
-                                 ta, tb, a);
+    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(kGemmThreads),
+                                         dim3(a.cx, a.cy, 1), L::kTotal, stream, ta, tb, a);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s", cudaGetErrorString(err));
     return check_launch("sfb_gemm");
 }
@@ -599,13 +629,22 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
         return fail(SFB_ERR_INVALID, "sfb_gemm: epilogue mode");
     }
     dim3 grid((p->N + BN - 1) / BN, m_tiles, a.splits);
+    a.cx = p->cluster_n > 0 ? p->cluster_n : 1;
+    a.cy = p->cluster_m > 0 ? p->cluster_m : 1;
+    a.a_part_dim = p->a_part_dim;
+    a.a_part_ext = p->a_part_ext;
+    if ((a.cx != 1 && a.cx != 2) || (a.cy != 1 && a.cy != 2 && a.cy != 4) || grid.x % a.cx || grid.y % a.cy)
+        return fail(SFB_ERR_INVALID, "sfb_gemm: cluster %dx%d does not divide the %ux%u tile grid", a.cx, a.cy, grid.x, grid.y);
+    if (a.cx > 1 && p->a_mode == SFB_A_CONV3X3 && (a.a_part_dim < 1 || a.a_part_dim > 3 || a.a_part_ext <= 0))
+        return fail(SFB_ERR_INVALID, "sfb_gemm: conv cluster needs a_part_dim / a_part_ext");
     CUtensorMap ta, tb;
     memcpy(&ta, p->tmap_a, sizeof(CUtensorMap));
     memcpy(&tb, p->tmap_b, sizeof(CUtensorMap));
     // <= one CTA per SM anyway: take the deep 6-stage pipeline; otherwise 3 stages x 2 CTAs/SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
-    int rc = (ctas <= 148) ? launch_gemm<BN, 6>(ta, tb, a, grid, stream)
-                           : launch_gemm<BN, 3>(ta, tb, a, grid, stream);
+    static const int force_stages = [] { const char* v = getenv("SFB_GEMM_STAGES"); return v ? atoi(v) : 0; }();
+    const bool deep = force_stages ? (force_stages == 6) : (ctas <= 148);
+    int rc = deep ? launch_gemm<BN, 6>(ta, tb, a, grid, stream) : launch_gemm<BN, 3>(ta, tb, a, grid, stream);
     if (rc) return rc;
     if (a.splits > 1) {
         const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;

@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -12,7 +13,7 @@ namespace sfb {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
-int g_pdl = 1;
+int g_pdl = [] { const char* v = getenv("SFB_PDL"); return v ? atoi(v) : 1; }();
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;

@@ -16,18 +16,35 @@ extern int g_pdl;
 // Launch with (optionally) the programmatic-dependent-launch attribute.  Every kernel launched
 // through here calls pdl_wait() before touching global memory written by its predecessor.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                              cudaStream_t stream, Args... args) {
+inline cudaError_t launch_cluster_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, dim3 cluster,
+                                      size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (g_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster.x;
+        attr[n].val.clusterDim.y = cluster.y;
+        attr[n].val.clusterDim.z = cluster.z;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+    return launch_cluster_pdl(kernel, grid, block, dim3(1, 1, 1), smem, stream, args...);
 }
 }  // namespace sfb
