@@ -6,6 +6,7 @@ CUDA-graph-capturing a UNet step is a flat loop of ``op.launch(stream)`` calls.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -117,10 +118,69 @@ def choose_splits(m_tiles, n_tiles, nkb):
     return max(1, min(NUM_SMS // tiles, nkb // 8))
 
 
-def gemm_op(name, lib, *, a_map, b_map, M, N, K, dt, out=None, ldo=0, bias=None, rowbias=None,
-            rows_per_img=1, ld_rowbias=0, residual=None, ldr=0, epi=EPI_STORE, geglu_n_out=0,
-            conv=None, qkv=None, ws=None, splits=None, keep=(), rowstats_out=None, ln=None):
+ENABLE_CLUSTER = os.environ.get("SFB_CLUSTER", "1") != "0"
+
+
+def choose_cluster(m_tiles, n_tiles):
+    """(cluster_n, cluster_m): CTAs sharing an A tile (along N, <= 2) / a weight tile (along M, <= 4).
+    TMA multicast turns cluster_m (cluster_n) L2 reads of the same tile into one."""
+    if not ENABLE_CLUSTER:
+        return 1, 1
+    cn = 2 if n_tiles % 2 == 0 else 1
+    cm = 4 if m_tiles % 4 == 0 else (2 if m_tiles % 2 == 0 else 1)
+    return cn, cm
+
+
+def a_matrix(x_ptr, rows, cols, pitch):
+    return dict(kind="matrix", ptr=x_ptr, rows=rows, cols=cols, pitch=pitch)
+
+
+def a_conv(x_ptr, n, h, w, c, pitch, box_n, box_h, wo, stride):
+    return dict(kind="conv", ptr=x_ptr, n=n, h=h, w=w, c=c, pitch=pitch, box_n=box_n, box_h=box_h,
+                wo=wo, stride=stride)
+
+
+def _a_map(a, cn, dry):
+    """A-operand TMA map with a box of 1/cn of the 128-row tile; returns (map, part_dim, part_ext)."""
+    if a["kind"] == "matrix":
+        return matrix_map(a["ptr"], a["rows"], a["cols"], a["pitch"], BM // cn, dry), 0, 0
+    bn, bh, bw = a["box_n"], a["box_h"], a["wo"]
+    dim = ext = 0
+    if cn == 2:
+        if bn > 1:
+            bn //= 2
+            dim, ext = 3, bn
+        elif bh > 1:
+            bh //= 2
+            dim, ext = 2, bh
+        else:
+            bw //= 2
+            dim, ext = 1, bw
+    return nhwc_map(a["ptr"], a["n"], a["h"], a["w"], a["c"], a["pitch"], bn, bh, bw, a["stride"],
+                    dry), dim, ext
+
+
+def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, out=None, ldo=0,
+            bias=None, rowbias=None, rows_per_img=1, ld_rowbias=0, residual=None, ldr=0,
+            epi=EPI_STORE, geglu_n_out=0, conv=None, qkv=None, ws=None, splits=None, keep=(),
+            rowstats_out=None, ln=None, dry=False):
+    """Either pass ready-made maps (`a_map`, `b_map`: no cluster) or operand descriptors
+    (`a` from a_matrix()/a_conv(), `b` a Mat), in which case a thread-block cluster with TMA
+    multicast is chosen from the tile grid."""
     p = GemmParams()
+    if conv:
+        mt = conv["n"] * ((conv["h"] + conv["box_h"] - 1) // conv["box_h"]) if conv["box_n"] == 1 \
+            else (conv["n"] + conv["box_n"] - 1) // conv["box_n"]
+    else:
+        mt = (M + BM - 1) // BM
+    if a is not None:
+        cn, cm = choose_cluster(mt, (N + BN - 1) // BN)
+        if a["kind"] == "conv" and cn == 2 and a["box_n"] == 1 and a["box_h"] == 1 and a["wo"] % 2:
+            cn = 1
+        a_map, p.a_part_dim, p.a_part_ext = _a_map(a, cn, dry)
+        b_map = b.map_for(cm)
+        p.cluster_n, p.cluster_m = cn, cm
+        keep = tuple(keep) + (b,)
     p.tmap_a, p.tmap_b = a_map.ptr, b_map.ptr
     p.a_mode = A_CONV3X3 if conv else A_MATRIX
     p.M, p.N, p.K, p.dtype = M, N, K, dtype_code(dt)
@@ -249,7 +309,7 @@ class Mat:
     """A GEMM B operand: logical [n, k] weight stored TILED in HBM -- tile (n_tile, k_block) is one
     contiguous 160 x 64 block (20 KB), so each TMA box is a single contiguous DRAM stream instead
     of 160 rows strided by k -- plus its TMA map (2-D view [tiles*160, 64], box 160 rows)."""
-    __slots__ = ("data", "map", "n", "k")
+    __slots__ = ("data", "map", "n", "k", "_dry", "_rows", "_maps")
 
     def __init__(self, w, dry=False):
         n, k = w.shape
@@ -262,8 +322,19 @@ class Mat:
             wp = torch.zeros(nt * BN, k, dtype=w.dtype, device=w.device)
             wp[:n] = w
             self.data = wp.view(nt, BN, nkb, BK).permute(0, 2, 1, 3).contiguous().view(-1, BK)
-        self.map = matrix_map(_ptr(self.data), nt * nkb * BN, BK, BK, BN, dry)
-        self.map.keep = self.data  # the map alone keeps the tiled copy alive
+        self._dry = dry
+        self._rows = nt * nkb * BN
+        self._maps = {}
+        self.map = self.map_for(1)
+
+    def map_for(self, cluster_m):
+        """TMA map whose box is 1/cluster_m of a weight tile (each CTA of a cluster along M loads
+        its slice and multicasts it to the others)."""
+        if cluster_m not in self._maps:
+            m = matrix_map(_ptr(self.data), self._rows, BK, BK, BN // cluster_m, self._dry)
+            m.keep = self.data  # the map alone keeps the tiled copy alive
+            self._maps[cluster_m] = m
+        return self._maps[cluster_m]
 
 
 

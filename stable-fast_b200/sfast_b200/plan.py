@@ -221,14 +221,14 @@ class UNetPlan:
     def _gemm(self, name, **kw):
         # split-K workspace: one shared fp32 buffer, sized after all ops are known
         kw.setdefault("ws", self._ws_token)
-        op = ops.gemm_op(name, self.lib_or_dry(), **kw)
+        op = ops.gemm_op(name, self.lib_or_dry(), dry=self.dry, **kw)
         return op
 
     def lib_or_dry(self):
         return self.lib if self.lib is not None else _DryLib
 
     def _a_matrix(self, x: Act):
-        return ops.matrix_map(x.ptr, x.rows, x.c, x.ld, 128, self.dry)
+        return ops.a_matrix(x.ptr, x.rows, x.c, x.ld)
 
     def group_norm(self, name, x: Act, prefix, silu, eps):
         y = self.act("gn_out", x.n, x.h, x.w, x.c)
@@ -245,10 +245,9 @@ class UNetPlan:
         cout = wm.n
         ho, wo = x.h // stride, x.w // stride
         box_n, box_h = ops.conv_tile_box(ho, wo)
-        amap = ops.nhwc_map(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, wo,
-                            stride, self.dry)
+        adesc = ops.a_conv(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, wo, stride)
         M = x.n * ho * wo
-        kw = dict(a_map=amap, b_map=wm.map, M=M, N=cout, K=9 * x.c, dt=self.dt,
+        kw = dict(a=adesc, b=wm, M=M, N=cout, K=9 * x.c, dt=self.dt,
                   out=dst.ptr, ldo=dst.ld, bias=self.w.f32(wname + ".bias"),
                   conv=dict(n=x.n, h=ho, w=wo, cin=x.c, stride=stride, box_n=box_n, box_h=box_h),
                   keep=(x.buf, dst.buf, wm))
@@ -259,7 +258,7 @@ class UNetPlan:
         self._emit(self._gemm(name, **kw))
 
     def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None, rowstats_out=None):
-        kw = dict(a_map=self._a_matrix(x), b_map=wm.map, M=x.rows, N=wm.n, K=x.c, dt=self.dt,
+        kw = dict(a=self._a_matrix(x), b=wm, M=x.rows, N=wm.n, K=x.c, dt=self.dt,
                   out=dst.ptr, ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, wm),
                   rowstats_out=rowstats_out)
         if residual is not None:
@@ -306,7 +305,7 @@ class UNetPlan:
         names = [f"{a}.to_q.weight"] if cross else [f"{a}.to_q.weight", f"{a}.to_k.weight",
                                                     f"{a}.to_v.weight"]
         wm, bias, colsum = self.w.ln_matrix(names, ln_prefix)
-        self._emit(self._gemm(a + (".q" if cross else ".qkv"), a_map=self._a_matrix(hs), b_map=wm.map,
+        self._emit(self._gemm(a + (".q" if cross else ".qkv"), a=self._a_matrix(hs), b=wm,
                               M=hs.rows, N=wm.n, K=C, dt=self.dt, epi=EPI_QKV, bias=bias,
                               qkv=dict(qkv, which_base=0, seq=S),
                               ln=dict(rowstats=ln_stats, colsum=colsum, eps=1e-5, dim=C),
@@ -314,7 +313,7 @@ class UNetPlan:
         if cross:
             wkv = self.w.cat_matrix([f"{a}.to_k.weight", f"{a}.to_v.weight"])
             ehs = Act(self.ehs_in, B, 1, self.ctx_len, self.spec.cross_attention_dim)
-            self._emit(self._gemm(a + ".kv", a_map=self._a_matrix(ehs), b_map=wkv.map, M=ehs.rows,
+            self._emit(self._gemm(a + ".kv", a=self._a_matrix(ehs), b=wkv, M=ehs.rows,
                                   N=2 * C, K=ehs.c, dt=self.dt, epi=EPI_QKV,
                                   qkv=dict(qkv, which_base=1, seq=self.ctx_len),
                                   keep=(self.ehs_in, wkv)))
@@ -355,7 +354,7 @@ class UNetPlan:
             self.attention(b + ".attn2", hs, b + ".norm2", st2, b, t, cross=True, stats_next=st3)
             gm, bp, inner, colsum = self.w.ln_geglu(b + ".ff.net.0.proj", b + ".norm3")
             ff = self.act("ff_act", x.n, x.h, x.w, inner)
-            self._emit(self._gemm(b + ".ff.geglu", a_map=self._a_matrix(hs), b_map=gm.map, M=hs.rows,
+            self._emit(self._gemm(b + ".ff.geglu", a=self._a_matrix(hs), b=gm, M=hs.rows,
                                   N=gm.n, K=t.dim, dt=self.dt, out=ff.ptr, ldo=inner,
                                   bias=bp, epi=EPI_GEGLU, geglu_n_out=inner,
                                   ln=dict(rowstats=st3, colsum=colsum, eps=1e-5, dim=t.dim),

@@ -50,9 +50,8 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     r = _rand(M, N, dt=dt) if residual else None
     out = torch.zeros(M, N, device=DEV, dtype=dt)
     ws = torch.empty(max(splits, 1) * M * N, device=DEV, dtype=torch.float32)
-    op = ops.gemm_op("gemm", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
-                     b_map=ops.Mat(w).map, M=M, N=N, K=K, dt=dt,
-                     out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits)
+    op = ops.gemm_op("gemm", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=ops.Mat(w), M=M, N=N, K=K,
+                     dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits)
     op.launch(_stream())
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t()
@@ -72,8 +71,8 @@ def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1):
     Np = wp.shape[0]
     out = torch.zeros(M, inner, device=DEV, dtype=dt)
     ws = torch.empty(max(splits, 1) * M * Np, device=DEV, dtype=torch.float32)
-    op = ops.gemm_op("geglu", lib, a_map=ops.matrix_map(x.data_ptr(), M, K, K, 128),
-                     b_map=ops.Mat(wp).map, M=M, N=Np, K=K, dt=dt,
+    op = ops.gemm_op("geglu", lib, a=ops.a_matrix(x.data_ptr(), M, K, K), b=ops.Mat(wp), M=M, N=Np, K=K,
+                     dt=dt,
                      out=out, ldo=inner, bias=bp, epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws,
                      splits=splits)
     op.launch(_stream())
@@ -100,9 +99,9 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
     out = torch.zeros(M, cout, device=DEV, dtype=dt)
     wp = ops.pack_conv3x3(wt, dt)
     box_n, box_h = ops.conv_tile_box(ho, wo)
-    amap = ops.nhwc_map(x.ptr, n, h, w, cin, ld, box_n, box_h, wo, stride)
+    adesc = ops.a_conv(x.ptr, n, h, w, cin, ld, box_n, box_h, wo, stride)
     ws = torch.empty(64 * M * cout, device=DEV, dtype=torch.float32) if splits != 1 else None
-    op = ops.gemm_op("conv", lib, a_map=amap, b_map=ops.Mat(wp).map,
+    op = ops.gemm_op("conv", lib, a=adesc, b=ops.Mat(wp),
                      M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb,
                      rows_per_img=ho * wo, ld_rowbias=cout, residual=r, ldr=cout, ws=ws,
                      splits=splits,
@@ -165,8 +164,7 @@ def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=
     w = _rand(ncols, Kdim, dt=dt, scale=1 / math.sqrt(Kdim))
     q, k, vt, dv, q_pitch, vt_pitch = _attn_buffers(B, H, S, seq, D, dt)
     M = B * seq
-    op = ops.gemm_op("qkv", lib, a_map=ops.matrix_map(x.data_ptr(), M, Kdim, Kdim, 128),
-                     b_map=ops.Mat(w).map, M=M, N=ncols,
+    op = ops.gemm_op("qkv", lib, a=ops.a_matrix(x.data_ptr(), M, Kdim, Kdim), b=ops.Mat(w), M=M, N=ncols,
                      K=Kdim, dt=dt, epi=ops.EPI_QKV,
                      qkv=dict(q=q, k=k, vt=vt, heads=H, head_dim=D, which_base=which_base,
                               seq=seq, q_pitch=q_pitch, q_rows=S, k_rows=seq, vt_rows=dv,
@@ -309,7 +307,7 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
     x = torch.zeros(M, C, device=DEV, dtype=dt)
     stats = torch.zeros(M, 2, device=DEV)
     ws = torch.empty(16 * M * max(N, C) * 2, device=DEV, dtype=torch.float32)
-    ops.gemm_op("producer", lib, a_map=ops.matrix_map(a.data_ptr(), M, C, C, 128), b_map=ops.Mat(w0).map,
+    ops.gemm_op("producer", lib, a=ops.a_matrix(a.data_ptr(), M, C, C), b=ops.Mat(w0),
                 M=M, N=C, K=C, dt=dt, out=x, ldo=C, residual=res, ldr=C, ws=ws, splits=splits_p,
                 rowstats_out=stats).launch(_stream())
     gamma = torch.randn(C, device=DEV) * 0.5 + 1.0
@@ -321,8 +319,8 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         wp, bias, colsum = ops.fold_layer_norm(w, b, gamma, beta, dt)
         wt, bp, _, cs = ops.pack_geglu(wp, bias, dt, extra=colsum)
         out = torch.zeros(M, inner, device=DEV, dtype=dt)
-        ops.gemm_op("consumer", lib, a_map=ops.matrix_map(x.data_ptr(), M, C, C, 128),
-                    b_map=ops.Mat(wt).map, M=M, N=wt.shape[0], K=C, dt=dt, out=out, ldo=inner, bias=bp,
+        ops.gemm_op("consumer", lib, a=ops.a_matrix(x.data_ptr(), M, C, C),
+                    b=ops.Mat(wt), M=M, N=wt.shape[0], K=C, dt=dt, out=out, ldo=inner, bias=bp,
                     epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws, splits=splits_c,
                     ln=dict(rowstats=stats, colsum=cs, eps=1e-5, dim=C)).launch(_stream())
     else:
@@ -330,8 +328,8 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         b = torch.randn(N, device=DEV) * 0.1
         wp, bias, colsum = ops.fold_layer_norm(w, b, gamma, beta, dt)
         out = torch.zeros(M, N, device=DEV, dtype=dt)
-        ops.gemm_op("consumer", lib, a_map=ops.matrix_map(x.data_ptr(), M, C, C, 128),
-                    b_map=ops.Mat(wp.contiguous()).map, M=M, N=N, K=C, dt=dt, out=out, ldo=N, bias=bias,
+        ops.gemm_op("consumer", lib, a=ops.a_matrix(x.data_ptr(), M, C, C),
+                    b=ops.Mat(wp.contiguous()), M=M, N=N, K=C, dt=dt, out=out, ldo=N, bias=bias,
                     ws=ws, splits=splits_c,
                     ln=dict(rowstats=stats, colsum=colsum, eps=1e-5, dim=C)).launch(_stream())
     torch.cuda.synchronize()
@@ -393,6 +391,9 @@ CHECKS = {
     "gemm_k64": (lambda: check_gemm(128, 160, 64, bias=False, residual=False), 2e-3),
     "gemm_big": (lambda: check_gemm(8192, 1280, 1280), 2e-3),
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
+    "gemm_cluster_2x4": (lambda: check_gemm(1024, 640, 640), 2e-3),
+    "gemm_cluster_1x4_ragged": (lambda: check_gemm(500, 480, 320), 2e-3),
+    "gemm_cluster_2x2_splitk": (lambda: check_gemm(256, 640, 2560, splits=4), 2e-3),
     "gemm_bf16": (lambda: check_gemm(300, 320, 320, dt=torch.bfloat16), 1e-2),
     "geglu": (lambda: check_geglu(256, 320, 1280), 2e-2),
     "geglu_ragged": (lambda: check_geglu(100, 64, 256), 2e-2),
