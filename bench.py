@@ -285,10 +285,10 @@ def measure_roofline(plan, lib, dump_path=""):
     dominant kernel is the tcgen05 GEMM / implicit-GEMM conv; its roofline is the tensor pipe."""
     stream = torch.cuda.current_stream()
     for _ in range(2):
-        plan.run(stream.cuda_stream)
+        plan.run()
     torch.cuda.synchronize()
     evs = []
-    for op in plan.ops:
+    for op in plan.all_ops():
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         op.launch(stream.cuda_stream)

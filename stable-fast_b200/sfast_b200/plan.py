@@ -144,6 +144,12 @@ class UNetPlan:
         self.lib = None if self.dry else _lib.lib()
         self.B, self.H, self.W, self.ctx_len = batch, height, width, ctx_len
         self.ops = []
+        # Ops that depend only on the step's inputs (cross-attention K/V projections of the text
+        # embedding): issued on a forked stream so they run concurrently with the start of the
+        # main chain (a parallel branch of the captured CUDA graph).
+        self.side_ops = []
+        self._side_stream = None
+        self._joined = False
         self._bufs = {}
         self._gn_count = 0
         spec = self.spec
@@ -295,9 +301,10 @@ class UNetPlan:
         vt_pitch = _round_up(skv, 64)
         tag = f"{B}x{H}x{S}x{skv}x{D}"
         q = self.buf("attn_q_" + tag, (B * H * S, q_pitch))
-        k = self.buf("attn_k_" + tag, (B * H * skv, q_pitch))
-        new_vt = ("attn_vt_" + tag, (B * H * dv, vt_pitch), self.dt) not in self._bufs
-        vt = self.buf("attn_vt_" + tag, (B * H * dv, vt_pitch))
+        kv_tag = tag + ("@" + a if cross else "")  # hoisted cross K/V: one buffer pair per layer
+        k = self.buf("attn_k_" + kv_tag, (B * H * skv, q_pitch))
+        new_vt = ("attn_vt_" + kv_tag, (B * H * dv, vt_pitch), self.dt) not in self._bufs
+        vt = self.buf("attn_vt_" + kv_tag, (B * H * dv, vt_pitch))
         if new_vt and not self.dry:
             vt.view(B * H, dv, vt_pitch)[:, D, :] = 1.0
         qkv = dict(q=q, k=k, vt=vt, heads=H, head_dim=D, q_pitch=q_pitch, q_rows=S, k_rows=skv,
@@ -313,10 +320,13 @@ class UNetPlan:
         if cross:
             wkv = self.w.cat_matrix([f"{a}.to_k.weight", f"{a}.to_v.weight"])
             ehs = Act(self.ehs_in, B, 1, self.ctx_len, self.spec.cross_attention_dim)
-            self._emit(self._gemm(a + ".kv", a=self._a_matrix(ehs), b=wkv, M=ehs.rows,
-                                  N=2 * C, K=ehs.c, dt=self.dt, epi=EPI_QKV,
-                                  qkv=dict(qkv, which_base=1, seq=self.ctx_len),
-                                  keep=(self.ehs_in, wkv)))
+            self.side_ops.append(self._gemm(a + ".kv", a=self._a_matrix(ehs), b=wkv, M=ehs.rows,
+                                            N=2 * C, K=ehs.c, dt=self.dt, epi=EPI_QKV,
+                                            qkv=dict(qkv, which_base=1, seq=self.ctx_len),
+                                            splits=1, keep=(self.ehs_in, wkv)))
+            if not self._joined:
+                self._joined = True
+                self._emit(_JoinOp())
         ao = self.act("attn_out", hs.n, hs.h, hs.w, C)
         self._emit(ops.attention_op(a + ".core", self.lib_or_dry(), q=q, k=k, vt=vt, out=ao.buf,
                                     batch=B, heads=H, head_dim=D, seq_q=S, seq_kv=skv, q_rows=S,
@@ -530,12 +540,29 @@ class UNetPlan:
         self._ws_token.finalize(self)
 
     # ------------------------------------------------------------------ execution
-    def run(self, stream):
+    def run(self, stream=None):
+        """Launch one UNet step on torch's current stream (plus the forked side stream)."""
+        main = torch.cuda.current_stream()
+        mptr = main.cuda_stream
+        if self.side_ops:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(main)  # inputs were copied on the main stream
+            sptr = side.cuda_stream
+            for op in self.side_ops:
+                op.launch(sptr)
         for op in self.ops:
-            op.launch(stream)
+            if isinstance(op, _JoinOp):
+                main.wait_stream(self._side_stream)
+            else:
+                op.launch(mptr)
+
+    def all_ops(self):
+        return self.side_ops + [op for op in self.ops if not isinstance(op, _JoinOp)]
 
     def flops(self):
-        return sum(op.flops for op in self.ops)
+        return sum(op.flops for op in self.all_ops())
 
 
 class _WsToken:
@@ -552,17 +579,29 @@ class _WsToken:
 
     def finalize(self, plan):
         need = 0
+        gemm = plan.lib_or_dry().sfb_gemm
         for op in plan.ops:
-            if op.fn is plan.lib_or_dry().sfb_gemm:
-                p = op.keep[0]
-                if p.splits > 1:
-                    need = max(need, p.splits * p.M * p.N)
+            if op.fn is gemm and op.keep[0].splits > 1:
+                need = max(need, op.keep[0].splits * op.keep[0].M * op.keep[0].N)
         plan.ws = plan._alloc((max(need, 1),), torch.float32)
         for op in plan.ops:
-            if op.fn is plan.lib_or_dry().sfb_gemm:
-                p = op.keep[0]
-                if p.splits > 1:
-                    p.ws = _ptr(plan.ws)
+            if op.fn is gemm and op.keep[0].splits > 1:
+                op.keep[0].ws = _ptr(plan.ws)
+        # side-stream GEMMs run concurrently with the main chain: they must not share the
+        # split-K workspace, so they are never split
+        for op in plan.side_ops:
+            if op.fn is gemm and op.keep[0].splits > 1:
+                raise AssertionError("side-stream GEMM must not use split-K")
+
+
+class _JoinOp(Op):
+    """Main stream waits for the side stream (the hoisted K/V projections) here."""
+
+    def __init__(self):
+        super().__init__("join(side stream)", None, (), ())
+
+    def launch(self, stream):
+        raise RuntimeError("join marker is handled by UNetPlan.run")
 
 
 class _CopyOp(Op):

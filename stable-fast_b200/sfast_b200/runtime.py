@@ -59,20 +59,20 @@ class _GraphedPlan:
         side = torch.cuda.Stream()
         side.wait_stream(stream)
         with torch.cuda.stream(side):
-            plan.run(side.cuda_stream)
+            plan.run()
         stream.wait_stream(side)
         torch.cuda.synchronize()
         if use_graph:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                plan.run(torch.cuda.current_stream().cuda_stream)
+                plan.run()
             self.graph = g
 
     def step(self):
         if self.graph is not None:
             self.graph.replay()
         else:
-            self.plan.run(torch.cuda.current_stream().cuda_stream)
+            self.plan.run()
 
 
 class CompiledUNet:
