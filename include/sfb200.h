@@ -141,6 +141,10 @@ typedef struct sfb_gemm_params {
     const float* ln_colsum;    /* [N] fp32: sum_k W'[n, k] */
     float ln_eps;
     int32_t ln_dim;
+    /* optional profiling aid: int64 [ctas, 8] buffer receiving %globaltimer stamps per CTA
+     * (entry, setup done, first TMA issued, first data landed, MMAs issued, accumulator ready,
+     * epilogue stored, exit); NULL in production */
+    void* debug_stamps;
 } sfb_gemm_params;
 
 int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream);

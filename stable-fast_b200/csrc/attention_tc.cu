@@ -38,7 +38,6 @@ struct AttnArgs {
     int seq_q, seq_kv;
     int q_rows, k_rows, vt_rows;
     int dtype;
-    int exp16;         // 1: exponentials computed directly in the 16-bit type (MUFU.EX2.F16/BF16)
     float scale_log2;  // scale * log2(e)
 };
 
@@ -51,20 +50,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
-
-// {2^x0, 2^x1} computed and returned in the 16-bit storage type (x <= 0): the probabilities are
-// needed as fp16/bf16 MMA operands anyway, so the convert happens before the MUFU, not after.
-__device__ __forceinline__ uint32_t exp2_pack(float x0, float x1, int bf16) {
-    uint32_t r;
-    if (bf16) {
-        asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tex2.approx.ftz.bf16x2 %0, t;\n\t}"
-            : "=r"(r) : "f"(x0), "f"(x1));
-    } else {
-        asm("{\n\t.reg .b32 t;\n\tcvt.rn.f16x2.f32 t, %2, %1;\n\tex2.approx.f16x2 %0, t;\n\t}"
-            : "=r"(r) : "f"(x0), "f"(x1));
-    }
     return r;
 }
 
@@ -83,7 +68,7 @@ struct AttnSmem {
     static_assert(kVChunk % 1024 == 0, "V^T chunk must keep 1024-byte swizzle-atom alignment");
 };
 
-template <int DC, int DK, int DV, int KVS>
+template <int DC, int DK, int DV, int KVS, int BF16>
 __global__ void __launch_bounds__(kAttnThreads, (DC == 1) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
                     const __grid_constant__ CUtensorMap tma_k,
@@ -167,7 +152,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            const bool bf16 = a.dtype == SFB_BF16;
+            constexpr bool bf16 = BF16 != 0;
             const uint32_t idesc_s = umma_idesc_f16(kTileQ, kTileKV, bf16);
             const uint32_t idesc_o = umma_idesc_f16(kTileQ, DV, bf16);
             const uint32_t tS = tmem_base + kColS;
@@ -271,17 +256,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
                 uint4 pk;
-                if (a.exp16) {
-                    pk.x = exp2_pack(x[0], x[1], a.dtype);
-                    pk.y = exp2_pack(x[2], x[3], a.dtype);
-                    pk.z = exp2_pack(x[4], x[5], a.dtype);
-                    pk.w = exp2_pack(x[6], x[7], a.dtype);
-                } else {
-                    pk.x = pack2(fast_exp2(x[0]), fast_exp2(x[1]), a.dtype);
-                    pk.y = pack2(fast_exp2(x[2]), fast_exp2(x[3]), a.dtype);
-                    pk.z = pack2(fast_exp2(x[4]), fast_exp2(x[5]), a.dtype);
-                    pk.w = pack2(fast_exp2(x[6]), fast_exp2(x[7]), a.dtype);
-                }
+                pk.x = pack2(fast_exp2(x[0]), fast_exp2(x[1]), BF16);
+                pk.y = pack2(fast_exp2(x[2]), fast_exp2(x[3]), BF16);
+                pk.z = pack2(fast_exp2(x[4]), fast_exp2(x[5]), BF16);
+                pk.w = pack2(fast_exp2(x[6]), fast_exp2(x[7]), BF16);
                 const int chunk = g >> 3;  // which 64-column half
                 const int g8 = g & 7;
                 uint8_t* dst = sP + chunk * (kTileQ * 128) + r * 128 + ((g8 ^ (r & 7)) << 4);
@@ -334,10 +312,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
                 const int d = c * 16 + jv * 8;
                 if (valid && d < a.head_dim) {
                     uint4 pk;
-                    pk.x = pack2(__uint_as_float(o[jv * 8 + 0]) * inv_l, __uint_as_float(o[jv * 8 + 1]) * inv_l, a.dtype);
-                    pk.y = pack2(__uint_as_float(o[jv * 8 + 2]) * inv_l, __uint_as_float(o[jv * 8 + 3]) * inv_l, a.dtype);
-                    pk.z = pack2(__uint_as_float(o[jv * 8 + 4]) * inv_l, __uint_as_float(o[jv * 8 + 5]) * inv_l, a.dtype);
-                    pk.w = pack2(__uint_as_float(o[jv * 8 + 6]) * inv_l, __uint_as_float(o[jv * 8 + 7]) * inv_l, a.dtype);
+                    pk.x = pack2(__uint_as_float(o[jv * 8 + 0]) * inv_l, __uint_as_float(o[jv * 8 + 1]) * inv_l, BF16);
+                    pk.y = pack2(__uint_as_float(o[jv * 8 + 2]) * inv_l, __uint_as_float(o[jv * 8 + 3]) * inv_l, BF16);
+                    pk.z = pack2(__uint_as_float(o[jv * 8 + 4]) * inv_l, __uint_as_float(o[jv * 8 + 5]) * inv_l, BF16);
+                    pk.w = pack2(__uint_as_float(o[jv * 8 + 6]) * inv_l, __uint_as_float(o[jv * 8 + 7]) * inv_l, BF16);
                     *reinterpret_cast<uint4*>(orow + d) = pk;
                 }
             }
@@ -352,12 +330,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
     }
 }
 
-template <int DC, int DK, int DV, int KVS>
-static int launch_attention(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
+template <int DC, int DK, int DV, int KVS, int BF16>
+static int launch_attention_t(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
     using L = AttnSmem<DC, DK, DV, KVS>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(attention_tc_kernel<DC, DK, DV, KVS>,
+        cudaError_t err = cudaFuncSetAttribute(attention_tc_kernel<DC, DK, DV, KVS, BF16>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (err != cudaSuccess)
             return fail(SFB_ERR_CUDA, "sfb_attention: smem attribute: %s", cudaGetErrorString(err));
@@ -368,10 +346,16 @@ static int launch_attention(const sfb_attn_params* p, const AttnArgs& a, cudaStr
     memcpy(&tk, p->tmap_k, sizeof(CUtensorMap));
     memcpy(&tv, p->tmap_vt, sizeof(CUtensorMap));
     dim3 grid((p->seq_q + kTileQ - 1) / kTileQ, p->batch * p->heads);
-    cudaError_t err = launch_pdl(attention_tc_kernel<DC, DK, DV, KVS>, grid, dim3(kAttnThreads),
+    cudaError_t err = launch_pdl(attention_tc_kernel<DC, DK, DV, KVS, BF16>, grid, dim3(kAttnThreads),
                                  L::kTotal, stream, tq, tk, tv, a);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_attention: launch: %s", cudaGetErrorString(err));
     return check_launch("sfb_attention");
+}
+
+template <int DC, int DK, int DV, int KVS>
+static int launch_attention(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
+    return a.dtype == SFB_BF16 ? launch_attention_t<DC, DK, DV, KVS, 1>(p, a, stream)
+                               : launch_attention_t<DC, DK, DV, KVS, 0>(p, a, stream);
 }
 
 }  // namespace sfb
@@ -394,8 +378,6 @@ extern "C" int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream_) {
     a.seq_q = p->seq_q; a.seq_kv = p->seq_kv; a.q_rows = p->q_rows; a.k_rows = p->k_rows;
     a.vt_rows = p->vt_rows; a.dtype = p->dtype;
     a.scale_log2 = p->scale * 1.4426950408889634f;
-    static const int exp16 = [] { const char* v = getenv("SFB_ATTN_EXP16"); return v ? atoi(v) : 0; }();
-    a.exp16 = exp16;
     switch (p->head_dim) {
         case 32: return launch_attention<1, 32, 48, 2>(p, a, stream);
         case 40: return launch_attention<1, 48, 48, 2>(p, a, stream);

@@ -69,6 +69,7 @@ struct GemmArgs {
     int nkb_total;  // K / 64
     int splits;
     int pdl;        // launched with programmatic stream serialization
+    long long* dbg; // optional: per-CTA %globaltimer stamps (8 per CTA) for latency breakdowns
     float* ws;
     // conv geometry
     int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
@@ -120,10 +121,11 @@ __device__ __forceinline__ void row_stats8(const float (&acc)[8], int dtype, flo
 }
 
 // 8 consecutive output columns [n, n+8) of row m; `acc` already holds bias / row bias / residual.
+template <int BF16>
 __device__ __forceinline__ void epi_store8(const EpiArgs& e, int m, int n, const float (&acc)[8]) {
     if (e.epi == SFB_EPI_STORE) {
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)m * e.ldo + n) =
-            pack8(acc, e.dtype);
+            pack8(acc, BF16);
     } else {  // SFB_EPI_QKV
         const int C = e.heads * e.head_dim;
         const int which = n / C + e.which_base;
@@ -135,26 +137,27 @@ __device__ __forceinline__ void epi_store8(const EpiArgs& e, int m, int n, const
         const size_t bh = (size_t)b * e.heads + h;
         if (which == 0) {
             *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.q) +
-                                      (bh * e.q_rows + s) * e.q_pitch + d) = pack8(acc, e.dtype);
+                                      (bh * e.q_rows + s) * e.q_pitch + d) = pack8(acc, BF16);
         } else if (which == 1) {
             *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.k) +
-                                      (bh * e.k_rows + s) * e.q_pitch + d) = pack8(acc, e.dtype);
+                                      (bh * e.k_rows + s) * e.q_pitch + d) = pack8(acc, BF16);
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                store1(e.vt, (bh * e.vt_rows + d + i) * e.vt_pitch + s, acc[i], e.dtype);
+                store1(e.vt, (bh * e.vt_rows + d + i) * e.vt_pitch + s, acc[i], BF16);
         }
     }
 }
 
 // GEGLU: value / gate (bias already added) of 8 output columns [nout, nout+8)
+template <int BF16>
 __device__ __forceinline__ void epi_geglu8(const EpiArgs& e, int m, int nout, const float (&v)[8],
                                            const float (&g)[8]) {
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = v[i] * gelu_erf_f(g[i]);
     *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)m * e.ldo + nout) =
-        pack8(o, e.dtype);
+        pack8(o, BF16);
 }
 
 // tile-local row r (0..127) of M-tile `tile` -> global row m; false if the row is padding
@@ -196,7 +199,7 @@ struct GemmSmem {
     static_assert(STAGES > 3 || 2 * (kTotal + 1024) <= 228 * 1024, "3-stage config must fit twice per SM");
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BF16>
 __global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmArgs args) {
@@ -217,6 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int n_tile = blockIdx.x;
     const int m_tile = blockIdx.y;
     const int split = blockIdx.z;
+    long long* dbg = args.dbg ? args.dbg + 8 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = globaltimer_ns();
     const int kb_begin = (int)(((long long)args.nkb_total * split) / args.splits);
     const int kb_end = (int)(((long long)args.nkb_total * (split + 1)) / args.splits);
     const int nkb = kb_end - kb_begin;
@@ -277,6 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 0) dbg[1] = globaltimer_ns();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -320,17 +326,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 if (args.cy > 1) tma_load_2d_mc(dstB, &tma_b, &full_bar[stage], 0, b_row, mask_b);
                 else tma_load_2d(dstB, &tma_b, &full_bar[stage], 0, b_row);
+                if (dbg && i == 0) dbg[2] = globaltimer_ns();
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(BM, BN, args.e.dtype == SFB_BF16);
+            const uint32_t idesc = umma_idesc_f16(BM, BN, BF16 != 0);
             for (int i = 0; i < nkb; ++i) {
                 const int stage = i % STAGES;
                 const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
+                if (dbg && i == 0) dbg[3] = globaltimer_ns();
                 const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * L::kABytes));
                 const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::kBBytes));
 #pragma unroll
@@ -343,6 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 else umma_commit(&empty_bar[stage]);
             }
             umma_commit(tmem_full_bar);
+            if (dbg) dbg[4] = globaltimer_ns();
         }
         __syncwarp();
     } else {
@@ -353,6 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool valid = tile_row_to_m(args, m_tile, r, m);
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        if (dbg && threadIdx.x == 64) dbg[5] = globaltimer_ns();
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const EpiArgs& e = args.e;
         const int ncol0 = n_tile * BN;
@@ -398,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             fv[i] = av + sBias[cv];
                             fg[i] = ag + sBias[cg];
                         }
-                        epi_geglu8(e, m, nout + j * 8, fv, fg);
+                        epi_geglu8<BF16>(e, m, nout + j * 8, fv, fg);
                     }
                 }
             }
@@ -447,9 +457,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                 f[i] = acc + brow[c * 16 + j * 8 + i];
                             }
                             if (rb_global) add_bias8(rb_global, n + j * 8, f);
-                            if (has_res) add_res8(res[cc * 2 + j], e.dtype, f);
-                            if (e.rowstats_out) row_stats8(f, e.dtype, rs_sum, rs_sq);
-                            epi_store8(e, m, n + j * 8, f);
+                            if (has_res) add_res8(res[cc * 2 + j], BF16, f);
+                            if (e.rowstats_out) row_stats8(f, BF16, rs_sum, rs_sq);
+                            epi_store8<BF16>(e, m, n + j * 8, f);
                         }
                     }
                 }
@@ -461,6 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     }
 
+    if (dbg && threadIdx.x == 64) dbg[6] = globaltimer_ns();
     tc_fence_before();
     // no CTA may exit while cluster peers can still signal its barriers
     if (clustered) cluster_sync_all();
@@ -469,12 +480,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tc_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
+    if (dbg && threadIdx.x == 32) dbg[7] = globaltimer_ns();
 }
 
 // ---------------------------------------------------------------------------------------
 // split-K reduction + epilogue: one thread per (row, 8 output columns)
 // ---------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int BF16>
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) {
     pdl_launch_dependents();
@@ -515,7 +527,7 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
             add_bias8(e.bias, nv, v);
             add_bias8(e.bias, ng, g);
         }
-        epi_geglu8(e, m, n, v, g);
+        epi_geglu8<BF16>(e, m, n, v, g);
     } else {
         float acc[8];
         sum8(n, acc);
@@ -530,15 +542,15 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
             if (e.residual)
                 add_res8(*reinterpret_cast<const uint4*>(
                              reinterpret_cast<const uint16_t*>(e.residual) + (size_t)m * e.ldr + n),
-                         e.dtype, acc);
+                         BF16, acc);
         }
         if (e.rowstats_out) {
             float rs = 0.f, rss = 0.f;
-            row_stats8(acc, e.dtype, rs, rss);
+            row_stats8(acc, BF16, rs, rss);
             atomicAdd(e.rowstats_out + 2 * (size_t)m, rs);
             atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rss);
         }
-        epi_store8(e, m, n, acc);
+        epi_store8<BF16>(e, m, n, acc);
     }
 }
 
@@ -546,21 +558,28 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
 
 using namespace sfb;
 
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
-                       cudaStream_t stream) {
+template <int BN, int STAGES, int BF16>
+static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
+                         cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, BF16>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
         attr_set = true;
     }
-    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(kGemmThreads),
+    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<BN, STAGES, BF16>, grid, dim3(kGemmThreads),
                                          dim3(a.cx, a.cy, 1), L::kTotal, stream, ta, tb, a);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s", cudaGetErrorString(err));
     return check_launch("sfb_gemm");
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
+                       cudaStream_t stream) {
+    return a.e.dtype == SFB_BF16 ? launch_gemm_t<BN, STAGES, 1>(ta, tb, a, grid, stream)
+                                 : launch_gemm_t<BN, STAGES, 0>(ta, tb, a, grid, stream);
 }
 
 extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
@@ -575,6 +594,7 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     a.nkb_total = p->K / BK;
     a.splits = p->splits < 1 ? 1 : p->splits;
     a.pdl = g_pdl;
+    a.dbg = reinterpret_cast<long long*>(p->debug_stamps);
     if (a.splits > a.nkb_total) return fail(SFB_ERR_INVALID, "sfb_gemm: splits > K blocks");
     if (a.splits > 1 && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
     a.ws = p->ws;
@@ -650,8 +670,9 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
         const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
         const long long items = (long long)e.M * (ncols / 8);
         const int blocks = (int)((items + 255) / 256);
-        cudaError_t err = launch_pdl(splitk_finish_kernel<BN>, dim3(blocks), dim3(256), 0, stream,
-                                     (const float*)a.ws, a.splits, e);
+        cudaError_t err = (e.dtype == SFB_BF16)
+            ? launch_pdl(splitk_finish_kernel<BN, 1>, dim3(blocks), dim3(256), 0, stream, (const float*)a.ws, a.splits, e)
+            : launch_pdl(splitk_finish_kernel<BN, 0>, dim3(blocks), dim3(256), 0, stream, (const float*)a.ws, a.splits, e);
         if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: finish launch: %s", cudaGetErrorString(err));
         rc = check_launch("sfb_gemm(split-K finish)");
     }

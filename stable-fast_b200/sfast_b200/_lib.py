@@ -34,6 +34,7 @@ class GemmParams(C.Structure):
         ("a_part_ext", C.c_int32),
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_dim", C.c_int32),
+        ("debug_stamps", C.c_void_p),
     ]
 
 
