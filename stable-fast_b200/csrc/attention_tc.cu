@@ -119,7 +119,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
     pdl_launch_dependents();
-    pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -127,6 +126,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
 
     if (warp == 0) {
         if (lane == 0) {
+            // only this thread reads the predecessor's output (Q/K/V via TMA); everything the other
+            // warps do is ordered behind these loads
+            pdl_wait();
             mbar_expect_tx(q_full, L::kQBytes);
 #pragma unroll
             for (int c = 0; c < DC; ++c)

@@ -197,6 +197,7 @@ struct GemmSmem {
     static constexpr int kBiasSlots = 4;
     static constexpr int kTotal = kBiasOffset + kBiasSlots * BN * 4 + 1024;  // + alignment slack
     static_assert(STAGES > 3 || 2 * (kTotal + 1024) <= 228 * 1024, "3-stage config must fit twice per SM");
+    static_assert(BN == 160, "the epilogue's 32+32+16 TMEM load split assumes 80-column halves");
 };
 
 template <int BN, int STAGES, int BF16>
@@ -245,38 +246,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint16_t mask_b = 0;
     for (int y = 0; y < args.cy; ++y) mask_b |= (uint16_t)(1u << (y * args.cx + cix));
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
-    // Everything above overlaps the previous kernel's tail (programmatic dependent launch);
-    // global memory produced by it may only be touched after this point.
+    // Everything up to each role's pdl_wait() overlaps the previous kernel's tail (programmatic
+    // dependent launch); global memory produced by it is only touched after that wait.
     pdl_launch_dependents();
-    pdl_wait();
-    if (warp >= 2 && args.splits == 1) {
-        // stage bias (+ per-image time-embedding row bias) for this tile's columns in smem
-        const EpiArgs& e = args.e;
-        const int t = threadIdx.x - 64;
-        int img0 = 0, nslots = 1;
-        const bool rb_staged = e.rowbias && args.box_n <= L::kBiasSlots;
-        if (rb_staged) {
-            nslots = args.box_n;
-            img0 = (args.box_n == 1) ? (m_tile / args.tiles_per_img) : m_tile * args.box_n;
-        }
-        for (int i = t; i < nslots * BN; i += 128) {
-            const int slot = i / BN, c = i - slot * BN;
-            const int n = n_tile * BN + c;
-            float v = 0.f;
-            if (n < e.N) {
-                if (e.bias) v = e.bias[n];
-                if (rb_staged && img0 + slot < args.img_n)
-                    v += e.rowbias[(size_t)(img0 + slot) * e.ld_rowbias + n];
-            }
-            sBias[i] = v;
-        }
-        if (e.ln_rowstats) {  // slot 1: column sums of the gamma-scaled weight
-            for (int c = t; c < BN; c += 128) {
-                const int n = n_tile * BN + c;
-                sBias[BN + c] = (n < e.N) ? e.ln_colsum[n] : 0.f;
-            }
-        }
-    }
     tc_fence_before();
     if (clustered) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts
     else __syncthreads();
@@ -286,6 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
+            pdl_wait();
             int n0 = 0, h0 = 0;
             if (args.a_mode == SFB_A_CONV3X3) {
                 if (args.box_n == 1) {
@@ -355,6 +328,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         __syncwarp();
     } else {
+        pdl_wait();
+        if (args.splits == 1) {
+            // stage bias (+ per-image time-embedding row bias) for this tile's columns in smem;
+            // only the four epilogue warps take part (named barrier 1), the TMA / MMA warps are
+            // already streaming
+            const EpiArgs& e = args.e;
+            const int t = threadIdx.x - 64;
+            int img0 = 0, nslots = 1;
+            const bool rb_staged = e.rowbias && args.box_n <= L::kBiasSlots;
+            if (rb_staged) {
+                nslots = args.box_n;
+                img0 = (args.box_n == 1) ? (m_tile / args.tiles_per_img) : m_tile * args.box_n;
+            }
+            for (int i = t; i < nslots * BN; i += 128) {
+                const int slot = i / BN, c = i - slot * BN;
+                const int n = n_tile * BN + c;
+                float v = 0.f;
+                if (n < e.N) {
+                    if (e.bias) v = e.bias[n];
+                    if (rb_staged && img0 + slot < args.img_n)
+                        v += e.rowbias[(size_t)(img0 + slot) * e.ld_rowbias + n];
+                }
+                sBias[i] = v;
+            }
+            if (e.ln_rowstats) {  // slot 1: column sums of the gamma-scaled weight
+                for (int c = t; c < BN; c += 128) {
+                    const int n = n_tile * BN + c;
+                    sBias[BN + c] = (n < e.N) ? e.ln_colsum[n] : 0.f;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
@@ -424,43 +429,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE);
             const uint16_t* rrow = reinterpret_cast<const uint16_t*>(e.residual) +
                                    (size_t)(valid ? m : 0) * e.ldr + ncol0;
-            constexpr int kHalf = BN / 32;  // 16-column chunks per half tile
+            constexpr int kHalfCols = BN / 2;  // 80 columns per pass
             float rs_sum = 0.f, rs_sq = 0.f;
 #pragma unroll 1
             for (int hb = 0; hb < 2; ++hb) {
                 // issue all residual loads of this half first: one memory latency, not ten
-                uint4 res[2 * kHalf];
+                uint4 res[kHalfCols / 8];
                 if (has_res && valid) {
 #pragma unroll
-                    for (int i = 0; i < 2 * kHalf; ++i) {
-                        const int n = ncol0 + hb * (BN / 2) + i * 8;
+                    for (int i = 0; i < kHalfCols / 8; ++i) {
+                        const int n = ncol0 + hb * kHalfCols + i * 8;
                         res[i] = (n < e.N)
-                                     ? *reinterpret_cast<const uint4*>(rrow + hb * (BN / 2) + i * 8)
+                                     ? *reinterpret_cast<const uint4*>(rrow + hb * kHalfCols + i * 8)
                                      : make_uint4(0, 0, 0, 0);
                     }
                 }
-#pragma unroll
-                for (int cc = 0; cc < kHalf; ++cc) {
-                    const int c = hb * kHalf + cc;
-                    uint32_t v[16];
-                    tmem_ld16(trow + c * 16, v);
+                // ... and the whole half of the accumulator with ONE TMEM round trip
+                uint32_t v[kHalfCols];
+                {
+                    uint32_t t0[32], t1[32], t2[16];
+                    tmem_ld32(trow + hb * kHalfCols, t0);
+                    tmem_ld32(trow + hb * kHalfCols + 32, t1);
+                    tmem_ld16(trow + hb * kHalfCols + 64, t2);
                     tmem_wait_ld();
-                    const int n = ncol0 + c * 16;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        if (valid && n + j * 8 < e.N) {
-                            float f[8];
+                    for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float acc = __uint_as_float(v[j * 8 + i]);
-                                if (e.ln_rowstats) acc = ln.y * (acc - ln.x * sBias[BN + c * 16 + j * 8 + i]);
-                                f[i] = acc + brow[c * 16 + j * 8 + i];
-                            }
-                            if (rb_global) add_bias8(rb_global, n + j * 8, f);
-                            if (has_res) add_res8(res[cc * 2 + j], BF16, f);
-                            if (e.rowstats_out) row_stats8(f, BF16, rs_sum, rs_sq);
-                            epi_store8<BF16>(e, m, n + j * 8, f);
+                    for (int i = 0; i < 16; ++i) v[64 + i] = t2[i];
+                }
+#pragma unroll
+                for (int j = 0; j < kHalfCols / 8; ++j) {
+                    const int cl = hb * kHalfCols + j * 8;  // column inside the tile
+                    const int n = ncol0 + cl;
+                    if (valid && n < e.N) {
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float acc = __uint_as_float(v[j * 8 + i]);
+                            if (e.ln_rowstats) acc = ln.y * (acc - ln.x * sBias[BN + cl + i]);
+                            f[i] = acc + brow[cl + i];
                         }
+                        if (rb_global) add_bias8(rb_global, n, f);
+                        if (has_res) add_res8(res[j], BF16, f);
+                        if (e.rowstats_out) row_stats8(f, BF16, rs_sum, rs_sq);
+                        epi_store8<BF16>(e, m, n, f);
                     }
                 }
             }

@@ -118,7 +118,7 @@ def choose_splits(m_tiles, n_tiles, nkb):
     return max(1, min(NUM_SMS // tiles, nkb // 8))
 
 
-ENABLE_CLUSTER = os.environ.get("SFB_CLUSTER", "1") != "0"
+ENABLE_CLUSTER = os.environ.get("SFB_CLUSTER", "0") != "0"  # measured slower on B200: smem-bound, see DESIGN.md
 
 
 def choose_cluster(m_tiles, n_tiles):
