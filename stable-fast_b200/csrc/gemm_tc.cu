@@ -195,7 +195,12 @@ struct GemmSmem {
     static constexpr int kBiasOffset = kBarOffset + 256;              // fp32 [kBiasSlots][BN]
     // images per conv M-tile whose row bias is staged; 3 stages + 4 slots keeps 2 CTAs per SM
     static constexpr int kBiasSlots = 4;
-    static constexpr int kTotal = kBiasOffset + kBiasSlots * BN * 4 + 1024;  // + alignment slack
+    static constexpr int kRowMOffset = kBiasOffset + kBiasSlots * BN * 4;  // int [128]: row -> m
+    static constexpr int kTotal = kRowMOffset + BM * 4 + 1024;                // + alignment slack
+    // fp32 staging tile of the epilogue, aliased onto the (by then idle) pipeline stages; the
+    // +4 float pad makes the thread-per-row float4 writes of phase A bank-conflict free
+    static constexpr int kStagePitch = BN + 4;
+    static_assert(BM * kStagePitch * 4 <= kBarOffset, "staging tile must fit in the stage buffers");
     static_assert(STAGES > 3 || 2 * (kTotal + 1024) <= 228 * 1024, "3-stage config must fit twice per SM");
     static_assert(BN == 160, "the epilogue's 32+32+16 TMEM load split assumes 80-column halves");
 };
@@ -215,6 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     float* sBias = reinterpret_cast<float*>(smem + L::kBiasOffset);
+    int* sRowM = reinterpret_cast<int*>(smem + L::kRowMOffset);
+    float* sStage = reinterpret_cast<float*>(smem);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -360,125 +367,150 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        // ---- epilogue.  Phase A: thread = accumulator row (warp w may only touch TMEM lanes
+        // [32*(w%4), +32)): TMEM -> registers -> (+bias / LayerNorm fold) -> fp32 staging tile in the
+        // now-idle pipeline buffers.  Phase B: threads re-partition the tile so that every global
+        // access (residual load, output store) is a coalesced 16-byte slice of a row segment
+        // instead of 32 rows x 16 bytes per warp instruction.
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
+        const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
         int m;
         const bool valid = tile_row_to_m(args, m_tile, r, m);
+        sRowM[r] = valid ? m : -1;
+        const EpiArgs& e = args.e;
+        const int ncol0 = n_tile * BN;
+        const bool partial = args.splits > 1;
+        float2 ln = make_float2(0.f, 1.f);
+        if (e.ln_rowstats && valid && !partial) ln = ln_row_params(e, m);
+        const float* brow = sBias;
+        const bool rb_staged = e.rowbias && args.box_n <= L::kBiasSlots;
+        if (rb_staged) brow += (r / (args.box_h * args.img_w)) * BN;
+        // many tiny images per tile (4x4 feature maps): row bias straight from global memory
+        const float* rb_global = nullptr;
+        if (e.rowbias && !rb_staged && !partial)
+            rb_global = e.rowbias + (size_t)(m_tile * args.box_n + r / (args.box_h * args.img_w)) * e.ld_rowbias;
+
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         if (dbg && threadIdx.x == 64) dbg[5] = globaltimer_ns();
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const EpiArgs& e = args.e;
-        const int ncol0 = n_tile * BN;
-        float2 ln = make_float2(0.f, 1.f);
-        if (e.ln_rowstats && valid && args.splits == 1) ln = ln_row_params(e, m);
-        if (args.splits > 1) {
-            float* wsrow = args.ws + ((size_t)split * e.M + (valid ? m : 0)) * e.N;
+        float* srow = sStage + r * L::kStagePitch;
+        constexpr int kHalfCols = BN / 2;  // 80 columns per TMEM round trip
 #pragma unroll 1
-            for (int c = 0; c < BN / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld16(trow + c * 16, v);
+        for (int hb = 0; hb < 2; ++hb) {
+            uint32_t v[kHalfCols];
+            {
+                uint32_t t0[32], t1[32], t2[16];
+                tmem_ld32(trow + hb * kHalfCols, t0);
+                tmem_ld32(trow + hb * kHalfCols + 32, t1);
+                tmem_ld16(trow + hb * kHalfCols + 64, t2);
                 tmem_wait_ld();
-                const int n = ncol0 + c * 16;
-                if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (n + j * 4 < e.N)
-                            *reinterpret_cast<uint4*>(wsrow + n + j * 4) =
-                                make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[64 + i] = t2[i];
+            }
+#pragma unroll
+            for (int j = 0; j < kHalfCols / 8; ++j) {
+                const int cl = hb * kHalfCols + j * 8;  // column inside the tile
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float acc = __uint_as_float(v[j * 8 + i]);
+                    if (!partial) {
+                        if (e.ln_rowstats) acc = ln.y * (acc - ln.x * sBias[BN + cl + i]);
+                        acc += brow[cl + i];
                     }
+                    f[i] = acc;
+                }
+                if (rb_global && ncol0 + cl < e.N) add_bias8(rb_global, ncol0 + cl, f);
+                *reinterpret_cast<float4*>(srow + cl) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(srow + cl + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+
+        // ---- phase B
+        auto load8 = [&](int row, int col, float (&f)[8]) {
+            const float4 a = *reinterpret_cast<const float4*>(sStage + row * L::kStagePitch + col);
+            const float4 b = *reinterpret_cast<const float4*>(sStage + row * L::kStagePitch + col + 4);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        };
+        constexpr int kGroups = BN / 8;  // 16-byte output slices per row
+        if (partial) {
+#pragma unroll 4
+            for (int it = 0; it < kGroups; ++it) {
+                const int idx = et + it * 128;
+                const int row = idx / kGroups, grp = idx - row * kGroups;
+                const int mm = sRowM[row], n = ncol0 + grp * 8;
+                if (mm >= 0 && n < e.N) {
+                    float f[8];
+                    load8(row, grp * 8, f);
+                    float* dst = args.ws + ((size_t)split * e.M + mm) * e.N + n;
+                    *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
                 }
             }
         } else if (e.epi == SFB_EPI_GEGLU) {
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[16], g[16];
-                tmem_ld16(trow + c * 16, v);
-                tmem_ld16(trow + BN / 2 + c * 16, g);
-                tmem_wait_ld();
-                const int nout = n_tile * (BN / 2) + c * 16;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (valid && nout + j * 8 < e.geglu_n_out) {
-                        float fv[8], fg[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int cv = c * 16 + j * 8 + i, cg = BN / 2 + cv;
-                            float av = __uint_as_float(v[j * 8 + i]), ag = __uint_as_float(g[j * 8 + i]);
-                            if (e.ln_rowstats) {
-                                av = ln.y * (av - ln.x * sBias[BN + cv]);
-                                ag = ln.y * (ag - ln.x * sBias[BN + cg]);
-                            }
-                            fv[i] = av + sBias[cv];
-                            fg[i] = ag + sBias[cg];
-                        }
-                        epi_geglu8<BF16>(e, m, nout + j * 8, fv, fg);
-                    }
+#pragma unroll 2
+            for (int it = 0; it < kGroups / 2; ++it) {
+                const int idx = et + it * 128;
+                const int row = idx / (kGroups / 2), og = idx - row * (kGroups / 2);
+                const int mm = sRowM[row], nout = n_tile * (BN / 2) + og * 8;
+                if (mm >= 0 && nout < e.geglu_n_out) {
+                    float fv[8], fg[8];
+                    load8(row, og * 8, fv);
+                    load8(row, BN / 2 + og * 8, fg);
+                    epi_geglu8<BF16>(e, mm, nout, fv, fg);
                 }
             }
         } else {
-            // bias slot of this row (image index inside the tile for the time-embedding row bias)
-            const float* brow = sBias;
-            const bool rb_staged = e.rowbias && args.box_n <= L::kBiasSlots;
-            if (rb_staged) brow += (r / (args.box_h * args.img_w)) * BN;
-            // many tiny images per tile (4x4 feature maps): row bias straight from global memory
-            const float* rb_global = nullptr;
-            if (e.rowbias && !rb_staged)
-                rb_global = e.rowbias + (size_t)(m_tile * args.box_n + r / (args.box_h * args.img_w)) * e.ld_rowbias;
+            // V^T columns want consecutive lanes = consecutive rows (2-byte stores along seq);
+            // everything else wants consecutive lanes = consecutive 16-byte slices of a row
+            bool row_fastest = false;
+            if (e.epi == SFB_EPI_QKV) {
+                const int C = e.heads * e.head_dim;
+                const int n_last = min(ncol0 + BN, e.N) - 1;
+                row_fastest = (ncol0 / C + e.which_base == 2) && (n_last / C + e.which_base == 2);
+            }
             const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE);
-            const uint16_t* rrow = reinterpret_cast<const uint16_t*>(e.residual) +
-                                   (size_t)(valid ? m : 0) * e.ldr + ncol0;
-            constexpr int kHalfCols = BN / 2;  // 80 columns per pass
-            float rs_sum = 0.f, rs_sq = 0.f;
-#pragma unroll 1
-            for (int hb = 0; hb < 2; ++hb) {
-                // issue all residual loads of this half first: one memory latency, not ten
-                uint4 res[kHalfCols / 8];
-                if (has_res && valid) {
-#pragma unroll
-                    for (int i = 0; i < kHalfCols / 8; ++i) {
-                        const int n = ncol0 + hb * kHalfCols + i * 8;
-                        res[i] = (n < e.N)
-                                     ? *reinterpret_cast<const uint4*>(rrow + hb * kHalfCols + i * 8)
-                                     : make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+            for (int it = 0; it < kGroups; ++it) {
+                const int idx = et + it * 128;
+                int row, grp;
+                if (row_fastest) { grp = idx >> 7; row = idx & 127; }
+                else { row = idx / kGroups; grp = idx - row * kGroups; }
+                const int mm = sRowM[row], n = ncol0 + grp * 8;
+                if (mm >= 0 && n < e.N) {
+                    float f[8];
+                    load8(row, grp * 8, f);
+                    if (has_res)
+                        add_res8(*reinterpret_cast<const uint4*>(
+                                     reinterpret_cast<const uint16_t*>(e.residual) + (size_t)mm * e.ldr + n),
+                                 BF16, f);
+                    if (e.rowstats_out) {  // final values back to the tile for the row reduction
+                        float* d = sStage + row * L::kStagePitch + grp * 8;
+                        *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
+                        *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
                     }
-                }
-                // ... and the whole half of the accumulator with ONE TMEM round trip
-                uint32_t v[kHalfCols];
-                {
-                    uint32_t t0[32], t1[32], t2[16];
-                    tmem_ld32(trow + hb * kHalfCols, t0);
-                    tmem_ld32(trow + hb * kHalfCols + 32, t1);
-                    tmem_ld16(trow + hb * kHalfCols + 64, t2);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[64 + i] = t2[i];
-                }
-#pragma unroll
-                for (int j = 0; j < kHalfCols / 8; ++j) {
-                    const int cl = hb * kHalfCols + j * 8;  // column inside the tile
-                    const int n = ncol0 + cl;
-                    if (valid && n < e.N) {
-                        float f[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float acc = __uint_as_float(v[j * 8 + i]);
-                            if (e.ln_rowstats) acc = ln.y * (acc - ln.x * sBias[BN + cl + i]);
-                            f[i] = acc + brow[cl + i];
-                        }
-                        if (rb_global) add_bias8(rb_global, n, f);
-                        if (has_res) add_res8(res[j], BF16, f);
-                        if (e.rowstats_out) row_stats8(f, BF16, rs_sum, rs_sq);
-                        epi_store8<BF16>(e, m, n, f);
-                    }
+                    epi_store8<BF16>(e, mm, n, f);
                 }
             }
-            if (e.rowstats_out && valid) {
-                atomicAdd(e.rowstats_out + 2 * (size_t)m, rs_sum);
-                atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rs_sq);
+            if (e.rowstats_out) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (valid) {
+                    float rs_sum = 0.f, rs_sq = 0.f;
+                    for (int g = 0; g < kGroups; ++g) {
+                        if (ncol0 + g * 8 < e.N) {
+                            float f[8];
+                            load8(r, g * 8, f);
+                            row_stats8(f, BF16, rs_sum, rs_sq);
+                        }
+                    }
+                    atomicAdd(e.rowstats_out + 2 * (size_t)m, rs_sum);
+                    atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rs_sq);
+                }
             }
         }
     }
