@@ -229,6 +229,10 @@ int sfb_small_linear(const sfb_small_linear_params* p, sfb_stream_t stream);
  * conv_out: x NHWC [n, h, w, cin] (pitch ldx) -> y NCHW [n, cout<=8, h, w] 16-bit
  * conv_in  w: 16-bit [3, 3, cin, cout] (tap-major, cout contiguous);
  * conv_out w: 16-bit [cout, 3, 3, cin]; bias fp32. */
+/* im2col of the first convolution: x NCHW [n, cin<=7, h, w] 16-bit -> a [n*h*w, 64] 16-bit with
+ * a[p, (kh*3+kw)*cin + c] and zero padding up to 64; feeds sfb_gemm (K = 64). */
+int sfb_im2col_in(const void* x, void* a, int32_t n, int32_t h, int32_t wd, int32_t cin,
+                  sfb_stream_t stream);
 int sfb_conv_in(const void* x, const void* w, const float* bias, void* y, int32_t n, int32_t h,
                 int32_t wd, int32_t cin, int32_t cout, int32_t ldy, int32_t dtype,
                 sfb_stream_t stream);

@@ -336,19 +336,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
     } else {
         pdl_wait();
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+        int m;
+        const bool valid = tile_row_to_m(args, m_tile, r, m);
+        sRowM[r] = valid ? m : -1;
         if (args.splits == 1) {
             // stage bias (+ per-image time-embedding row bias) for this tile's columns in smem;
             // only the four epilogue warps take part (named barrier 1), the TMA / MMA warps are
             // already streaming
             const EpiArgs& e = args.e;
-            const int t = threadIdx.x - 64;
             int img0 = 0, nslots = 1;
             const bool rb_staged = e.rowbias && args.box_n <= L::kBiasSlots;
             if (rb_staged) {
                 nslots = args.box_n;
                 img0 = (args.box_n == 1) ? (m_tile / args.tiles_per_img) : m_tile * args.box_n;
             }
-            for (int i = t; i < nslots * BN; i += 128) {
+            for (int i = et; i < nslots * BN; i += 128) {
                 const int slot = i / BN, c = i - slot * BN;
                 const int n = n_tile * BN + c;
                 float v = 0.f;
@@ -360,27 +365,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 sBias[i] = v;
             }
             if (e.ln_rowstats) {  // slot 1: column sums of the gamma-scaled weight
-                for (int c = t; c < BN; c += 128) {
+                for (int c = et; c < BN; c += 128) {
                     const int n = n_tile * BN + c;
                     sBias[BN + c] = (n < e.N) ? e.ln_colsum[n] : 0.f;
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         // ---- epilogue.  Phase A: thread = accumulator row (warp w may only touch TMEM lanes
         // [32*(w%4), +32)): TMEM -> registers -> (+bias / LayerNorm fold) -> fp32 staging tile in the
         // now-idle pipeline buffers.  Phase B: threads re-partition the tile so that every global
         // access (residual load, output store) is a coalesced 16-byte slice of a row segment
         // instead of 32 rows x 16 bytes per warp instruction.
-        const int quarter = warp & 3;
-        const int r = quarter * 32 + lane;
-        const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
-        int m;
-        const bool valid = tile_row_to_m(args, m_tile, r, m);
-        sRowM[r] = valid ? m : -1;
         const EpiArgs& e = args.e;
         const int ncol0 = n_tile * BN;
         const bool partial = args.splits > 1;
+        constexpr int kGroups = BN / 8;  // 16-byte output slices per row
+        // The residual tile is fetched NOW, in the coalesced phase-B ownership (thread <-> 16-byte
+        // slice), so its 40 KB are in flight for the whole main loop instead of being a serial
+        // latency after it.
+        const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE) && !partial;
+        uint4 res[kGroups];
+        if (has_res) {
+#pragma unroll
+            for (int it = 0; it < kGroups; ++it) {
+                const int idx = et + it * 128;
+                const int row = idx / kGroups, grp = idx - row * kGroups;
+                const int mm = sRowM[row], n = ncol0 + grp * 8;
+                res[it] = (mm >= 0 && n < e.N)
+                    ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.residual) + (size_t)mm * e.ldr + n)
+                    : make_uint4(0, 0, 0, 0);
+            }
+        }
         float2 ln = make_float2(0.f, 1.f);
         if (e.ln_rowstats && valid && !partial) ln = ln_row_params(e, m);
         const float* brow = sBias;
@@ -396,24 +412,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (dbg && threadIdx.x == 64) dbg[5] = globaltimer_ns();
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float* srow = sStage + r * L::kStagePitch;
-        constexpr int kHalfCols = BN / 2;  // 80 columns per TMEM round trip
 #pragma unroll 1
-        for (int hb = 0; hb < 2; ++hb) {
-            uint32_t v[kHalfCols];
-            {
-                uint32_t t0[32], t1[32], t2[16];
-                tmem_ld32(trow + hb * kHalfCols, t0);
-                tmem_ld32(trow + hb * kHalfCols + 32, t1);
-                tmem_ld16(trow + hb * kHalfCols + 64, t2);
-                tmem_wait_ld();
+        for (int cb = 0; cb < BN / 32; ++cb) {
+            uint32_t v[32];
+            tmem_ld32(trow + cb * 32, v);
+            tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[64 + i] = t2[i];
-            }
-#pragma unroll
-            for (int j = 0; j < kHalfCols / 8; ++j) {
-                const int cl = hb * kHalfCols + j * 8;  // column inside the tile
+            for (int j = 0; j < 4; ++j) {
+                const int cl = cb * 32 + j * 8;  // column inside the tile
                 float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -437,7 +443,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const float4 b = *reinterpret_cast<const float4*>(sStage + row * L::kStagePitch + col + 4);
             f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
         };
-        constexpr int kGroups = BN / 8;  // 16-byte output slices per row
         if (partial) {
 #pragma unroll 4
             for (int it = 0; it < kGroups; ++it) {
@@ -474,8 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const int n_last = min(ncol0 + BN, e.N) - 1;
                 row_fastest = (ncol0 / C + e.which_base == 2) && (n_last / C + e.which_base == 2);
             }
-            const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE);
-#pragma unroll 4
+#pragma unroll
             for (int it = 0; it < kGroups; ++it) {
                 const int idx = et + it * 128;
                 int row, grp;
@@ -485,10 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (mm >= 0 && n < e.N) {
                     float f[8];
                     load8(row, grp * 8, f);
-                    if (has_res)
-                        add_res8(*reinterpret_cast<const uint4*>(
-                                     reinterpret_cast<const uint16_t*>(e.residual) + (size_t)mm * e.ldr + n),
-                                 BF16, f);
+                    if (has_res) add_res8(res[it], BF16, f);
                     if (e.rowstats_out) {  // final values back to the tile for the row reduction
                         float* d = sStage + row * L::kStagePitch + grp * 8;
                         *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);

@@ -169,6 +169,46 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const ConvEdgeArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// im2col for the UNet's first convolution (cin <= 7: K = 9*cin <= 63): NCHW input ->
+// A[pixels, 64] (K zero-padded to one 64-wide K block), so conv_in runs on the tcgen05 GEMM with
+// its fused bias epilogue writing NHWC straight into the first skip-concat slice.
+// One thread per output pixel; loads are coalesced along w, each thread writes one 128-byte row.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) im2col_in_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ a,
+                                                        int n, int h, int w, int cin) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n * h * w) return;
+    const int xw = p % w;
+    const int yh = (p / w) % h;
+    const int img = p / (w * h);
+    uint16_t row[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) row[i] = 0;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
+        const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
+#pragma unroll
+        for (int ci = 0; ci < 7; ++ci) {
+            if (ci < cin && ok) row[tap * cin + ci] = x[(((size_t)img * cin + ci) * h + iy) * w + ix];
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(a + (size_t)p * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint4 v;
+        v.x = row[i * 8 + 0] | ((uint32_t)row[i * 8 + 1] << 16);
+        v.y = row[i * 8 + 2] | ((uint32_t)row[i * 8 + 3] << 16);
+        v.z = row[i * 8 + 4] | ((uint32_t)row[i * 8 + 5] << 16);
+        v.w = row[i * 8 + 6] | ((uint32_t)row[i * 8 + 7] << 16);
+        dst[i] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // conv_out: NHWC (pitch ld) -> NCHW (cout <= 8), 3x3 pad 1.  One warp per output pixel; lanes
 // split the 9 * cin/8 (tap, 8-channel vector) items; weights [cout][9][cin] staged in smem.
@@ -302,6 +342,17 @@ extern "C" int sfb_conv_in(const void* x, const void* w, const float* bias, void
                                  dim3(256), smem, static_cast<cudaStream_t>(stream), a);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "conv_in: %s", cudaGetErrorString(err));
     return check_launch("sfb_conv_in");
+}
+
+extern "C" int sfb_im2col_in(const void* x, void* a, int32_t n, int32_t h, int32_t wd, int32_t cin,
+                             sfb_stream_t stream) {
+    if (!x || !a || cin <= 0 || cin > 7) return fail(SFB_ERR_INVALID, "im2col_in: cin=%d must be 1..7", cin);
+    const int total = n * h * wd;
+    cudaError_t err = launch_pdl(im2col_in_kernel, dim3((total + 127) / 128), dim3(128), 0,
+                                 static_cast<cudaStream_t>(stream), reinterpret_cast<const uint16_t*>(x),
+                                 reinterpret_cast<uint16_t*>(a), n, h, wd, cin);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "im2col_in: %s", cudaGetErrorString(err));
+    return check_launch("sfb_im2col_in");
 }
 
 extern "C" int sfb_conv_out(const void* x, const void* w, const float* bias, void* y, int32_t n,

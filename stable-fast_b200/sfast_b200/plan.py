@@ -83,6 +83,19 @@ class PackedWeights:
             self._cache[key] = ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)
         return self._cache[key]
 
+    def conv_in_matrix(self, name):
+        """First conv as a GEMM operand: [cout, (kh, kw, cin)] zero-padded along K to 64."""
+        key = ("cin_mat", name)
+        if key not in self._cache:
+            w = ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)
+            if w.device.type == "meta":
+                wp = torch.empty(w.shape[0], 64, dtype=self.dtype, device="meta")
+            else:
+                wp = torch.zeros(w.shape[0], 64, dtype=self.dtype, device=w.device)
+                wp[:, :w.shape[1]] = w
+            self._cache[key] = self._mat(wp)
+        return self._cache[key]
+
     def conv_in_weight(self, name):
         key = ("cin", name)
         if key not in self._cache:
@@ -467,14 +480,21 @@ class UNetPlan:
         # ---- conv_in
         c0 = spec.block_out_channels[0]
         x = skip_dst[0]
-        w_in = self.w.conv_in_weight("conv_in.weight")
-        self._emit(Op("conv_in", lib.sfb_conv_in,
-                      (_ptr(self.sample_in),
-                       _ptr(w_in),
-                       _ptr(self.w.f32("conv_in.bias")),
-                       x.ptr, B, H, W, spec.in_channels, c0, x.ld,
-                       ops.dtype_code(self.dt)), (self.sample_in, w_in, x.buf),
-                      2 * B * H * W * c0 * 9 * spec.in_channels))
+        if spec.in_channels <= 7:
+            # im2col (K = 9*cin padded to one 64-wide K block) + the tcgen05 GEMM with fused bias
+            a_col = self.buf("conv_in_im2col", (B * H * W, 64))
+            self._emit(Op("conv_in.im2col", lib.sfb_im2col_in,
+                          (_ptr(self.sample_in), _ptr(a_col), B, H, W, spec.in_channels),
+                          (self.sample_in, a_col), 0, B * H * W * 128))
+            self.linear("conv_in", Act(a_col, B, H, W, 64), self.w.conv_in_matrix("conv_in.weight"),
+                        self.w.f32("conv_in.bias"), x)
+            self.ops[-1].flops = 2 * B * H * W * c0 * 9 * spec.in_channels  # algorithmic, not padded
+        else:
+            w_in = self.w.conv_in_weight("conv_in.weight")
+            self._emit(Op("conv_in", lib.sfb_conv_in,
+                          (_ptr(self.sample_in), _ptr(w_in), _ptr(self.w.f32("conv_in.bias")),
+                           x.ptr, B, H, W, spec.in_channels, c0, x.ld, ops.dtype_code(self.dt)),
+                          (self.sample_in, w_in, x.buf), 2 * B * H * W * c0 * 9 * spec.in_channels))
         # ---- down path
         k = 1
         for blk in spec.down:

@@ -269,6 +269,25 @@ def check_conv_in(n=2, h=64, w=64, cin=4, cout=320, dt=torch.float16, seed=8):
     return rel_err(y, ref)
 
 
+def check_conv_in_gemm(n=2, h=64, w=64, cin=4, cout=320, dt=torch.float16, seed=13):
+    """First conv as im2col (K padded to 64) + the tcgen05 GEMM with fused bias."""
+    lib = _lib.lib()
+    x = _rand(n, cin, h, w, dt=dt, seed=seed)
+    wt = _rand(cout, cin, 3, 3, dt=dt, scale=0.2)
+    b = torch.randn(cout, device=DEV)
+    wp = torch.zeros(cout, 64, device=DEV, dtype=dt)
+    wp[:, :9 * cin] = ops.pack_conv3x3(wt, dt)
+    M = n * h * w
+    a = torch.zeros(M, 64, device=DEV, dtype=dt)
+    y = torch.zeros(M, cout, device=DEV, dtype=dt)
+    _lib.check(lib.sfb_im2col_in(x.data_ptr(), a.data_ptr(), n, h, w, cin, _stream()))
+    ops.gemm_op("conv_in", lib, a=ops.a_matrix(a.data_ptr(), M, 64, 64), b=ops.Mat(wp), M=M, N=cout, K=64,
+                dt=dt, out=y, ldo=cout, bias=b).launch(_stream())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), wt.float(), b, padding=1).permute(0, 2, 3, 1).reshape(M, cout)
+    return rel_err(y, ref)
+
+
 def check_conv_out(n=2, h=64, w=64, cin=320, cout=4, dt=torch.float16, seed=9):
     lib = _lib.lib()
     x = _rand(n, h, w, cin, dt=dt, seed=seed)
@@ -439,6 +458,8 @@ CHECKS = {
     "small_linear": (lambda: check_small_linear(), 2e-3),
     "small_linear_noact": (lambda: check_small_linear(2, 960, 1280, act_out=0), 2e-3),
     "conv_in": (lambda: check_conv_in(), 2e-3),
+    "conv_in_gemm": (lambda: check_conv_in_gemm(), 2e-3),
+    "conv_in_gemm_ragged": (lambda: check_conv_in_gemm(3, 8, 16, 4, 64), 2e-3),
     "conv_out": (lambda: check_conv_out(), 2e-3),
     "upsample": (lambda: check_upsample(), 0.0),
 }

@@ -76,9 +76,9 @@ def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     assert sum(1 for g in gemms if g.ln_rowstats is not None or g.ln_dim > 0) == 48
     assert names.count("sfb_attention") == 32
     assert names.count("sfb_upsample2x") == 3
-    # 98 convs + 184 GEMMs of the reference collapse to 208 GEMM launches (fused QKV / KV, 22
-    # time projections in one small_linear, conv_in / conv_out as edge kernels)
-    assert names.count("sfb_gemm") == 208
+    # 98 convs + 184 GEMMs of the reference collapse to 209 GEMM launches (fused QKV / KV, 22
+    # time projections in one small_linear, conv_in as im2col + GEMM, conv_out as an edge kernel)
+    assert names.count("sfb_gemm") == 209 and names.count("sfb_im2col_in") == 1
     # algorithmic FLOPs (conv/linear/attention MACs * 2), SURVEY.md section 8d: 1.607 TFLOP at B = 2
     assert abs(plan.flops() / 1e12 - 1.607) < 0.003
     # every skip concat is zero-copy: 12 concat buffers, no copy op exists
