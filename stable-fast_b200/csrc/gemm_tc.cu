@@ -70,6 +70,7 @@ struct GemmArgs {
     int splits;
     int pdl;        // launched with programmatic stream serialization
     long long* dbg; // optional: per-CTA %globaltimer stamps (8 per CTA) for latency breakdowns
+    int* split_sync; // [tiles][2] arrive / done counters of the fused split-K reduction (or null)
     float* ws;
     // conv geometry
     int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
@@ -181,6 +182,86 @@ __device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r
     const int n = n0 + dn, h = h0 + dh;
     m = (n * a.img_h + h) * a.img_w + w;
     return (n < a.img_n) && (h < a.img_h);
+}
+
+// ---------------------------------------------------------------------------------------
+// split-K reduction + epilogue
+// ---------------------------------------------------------------------------------------
+// Sum the `splits` fp32 partials of 8 output columns of row m and run the fused epilogue on them.
+// `n` is the output column (GEGLU: output column of the gated product).  Partials were written by
+// other SMs: read them through L2 (ld.global.cg).
+template <int BN, int BF16>
+__device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int splits, const EpiArgs& e,
+                                               int m, int n) {
+    auto sum8 = [&](int col, float (&acc)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int s = 0; s < splits; ++s) {
+            const float* p = ws + ((size_t)s * e.M + m) * e.N + col;
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(p + 4));
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+    };
+    if (e.epi == SFB_EPI_GEGLU) {
+        const int tile = n / (BN / 2);
+        const int nv = tile * BN + (n - tile * (BN / 2));
+        const int ng = nv + BN / 2;
+        float v[8], g[8];
+        sum8(nv, v);
+        sum8(ng, g);
+        if (e.ln_rowstats) {
+            const float2 ln = ln_row_params(e, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = ln.y * (v[i] - ln.x * e.ln_colsum[nv + i]);
+                g[i] = ln.y * (g[i] - ln.x * e.ln_colsum[ng + i]);
+            }
+        }
+        if (e.bias) {
+            add_bias8(e.bias, nv, v);
+            add_bias8(e.bias, ng, g);
+        }
+        epi_geglu8<BF16>(e, m, n, v, g);
+    } else {
+        float acc[8];
+        sum8(n, acc);
+        if (e.ln_rowstats) {
+            const float2 ln = ln_row_params(e, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = ln.y * (acc[i] - ln.x * e.ln_colsum[n + i]);
+        }
+        if (e.bias) add_bias8(e.bias, n, acc);
+        if (e.epi == SFB_EPI_STORE) {
+            if (e.rowbias) add_bias8(e.rowbias + (size_t)(m / e.rows_per_img) * e.ld_rowbias, n, acc);
+            if (e.residual)
+                add_res8(*reinterpret_cast<const uint4*>(
+                             reinterpret_cast<const uint16_t*>(e.residual) + (size_t)m * e.ldr + n),
+                         BF16, acc);
+        }
+        if (e.rowstats_out) {
+            float rs = 0.f, rss = 0.f;
+            row_stats8(acc, BF16, rs, rss);
+            atomicAdd(e.rowstats_out + 2 * (size_t)m, rs);
+            atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rss);
+        }
+        epi_store8<BF16>(e, m, n, acc);
+    }
+}
+
+// Stand-alone reduction kernel: fallback when the split CTAs of a tile cannot all be co-resident
+// (the fused in-kernel reduction needs that for its barrier).  One thread per (row, 8 columns).
+template <int BN, int BF16>
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
+    const int groups = ncols / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)e.M * groups) return;
+    splitk_reduce8<BN, BF16>(ws, splits, e, (int)(idx / groups), (int)(idx % groups) * 8);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -457,6 +538,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
                 }
             }
+            if (args.split_sync) {
+                // Fused reduction: the `splits` CTAs of this output tile (all co-resident: the host
+                // only enables this when the whole grid fits on the GPU at once) meet at a counter
+                // barrier, then each reduces + finishes its own slice of the tile's rows.
+                int* cnt = args.split_sync + 2 * (m_tile * gridDim.x + n_tile);
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    atomicAdd(cnt, 1);
+                    const long long t0 = clock64();
+                    while (*reinterpret_cast<volatile int*>(cnt) < args.splits) {
+                        if (clock64() - t0 > 4000000000LL) __trap();
+                    }
+                    __threadfence();
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int rows_per = (BM + args.splits - 1) / args.splits;
+                const int r0 = split * rows_per;
+                const int nrows = max(0, min(rows_per, BM - r0));
+                const bool geglu = e.epi == SFB_EPI_GEGLU;
+                const int gpr = geglu ? kGroups / 2 : kGroups;  // items per row
+                for (int idx = et; idx < nrows * gpr; idx += 128) {
+                    const int row = r0 + idx / gpr, grp = idx % gpr;
+                    const int mm = sRowM[row];
+                    const int n = (geglu ? n_tile * (BN / 2) : ncol0) + grp * 8;
+                    if (mm >= 0 && n < (geglu ? e.geglu_n_out : e.N))
+                        splitk_reduce8<BN, BF16>(args.ws, args.splits, e, mm, n);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    if (atomicAdd(cnt + 1, 1) == args.splits - 1) {  // last finisher re-arms the counters
+                        cnt[0] = 0;
+                        cnt[1] = 0;
+                        __threadfence();
+                    }
+                }
+            }
         } else if (e.epi == SFB_EPI_GEGLU) {
 #pragma unroll 2
             for (int it = 0; it < kGroups / 2; ++it) {
@@ -528,77 +646,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (dbg && threadIdx.x == 32) dbg[7] = globaltimer_ns();
 }
 
-// ---------------------------------------------------------------------------------------
-// split-K reduction + epilogue: one thread per (row, 8 output columns)
-// ---------------------------------------------------------------------------------------
-template <int BN, int BF16>
-__global__ void __launch_bounds__(256)
-splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
-    const int groups = ncols / 8;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)e.M * groups) return;
-    const int m = (int)(idx / groups);
-    const int n = (int)(idx % groups) * 8;
-    auto sum8 = [&](int col, float (&acc)[8]) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int s = 0; s < splits; ++s) {
-            const float* p = ws + ((size_t)s * e.M + m) * e.N + col;
-            const float4 a = *reinterpret_cast<const float4*>(p);
-            const float4 b = *reinterpret_cast<const float4*>(p + 4);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-        }
-    };
-    if (e.epi == SFB_EPI_GEGLU) {
-        const int tile = n / (BN / 2);
-        const int nv = tile * BN + (n - tile * (BN / 2));
-        const int ng = nv + BN / 2;
-        float v[8], g[8];
-        sum8(nv, v);
-        sum8(ng, g);
-        if (e.ln_rowstats) {
-            const float2 ln = ln_row_params(e, m);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                v[i] = ln.y * (v[i] - ln.x * e.ln_colsum[nv + i]);
-                g[i] = ln.y * (g[i] - ln.x * e.ln_colsum[ng + i]);
-            }
-        }
-        if (e.bias) {
-            add_bias8(e.bias, nv, v);
-            add_bias8(e.bias, ng, g);
-        }
-        epi_geglu8<BF16>(e, m, n, v, g);
-    } else {
-        float acc[8];
-        sum8(n, acc);
-        if (e.ln_rowstats) {
-            const float2 ln = ln_row_params(e, m);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = ln.y * (acc[i] - ln.x * e.ln_colsum[n + i]);
-        }
-        if (e.bias) add_bias8(e.bias, n, acc);
-        if (e.epi == SFB_EPI_STORE) {
-            if (e.rowbias) add_bias8(e.rowbias + (size_t)(m / e.rows_per_img) * e.ld_rowbias, n, acc);
-            if (e.residual)
-                add_res8(*reinterpret_cast<const uint4*>(
-                             reinterpret_cast<const uint16_t*>(e.residual) + (size_t)m * e.ldr + n),
-                         BF16, acc);
-        }
-        if (e.rowstats_out) {
-            float rs = 0.f, rss = 0.f;
-            row_stats8(acc, BF16, rs, rss);
-            atomicAdd(e.rowstats_out + 2 * (size_t)m, rs);
-            atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rss);
-        }
-        epi_store8<BF16>(e, m, n, acc);
-    }
-}
-
 }  // namespace sfb
 
 using namespace sfb;
@@ -640,6 +687,7 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     a.splits = p->splits < 1 ? 1 : p->splits;
     a.pdl = g_pdl;
     a.dbg = reinterpret_cast<long long*>(p->debug_stamps);
+    a.split_sync = nullptr;
     if (a.splits > a.nkb_total) return fail(SFB_ERR_INVALID, "sfb_gemm: splits > K blocks");
     if (a.splits > 1 && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
     a.ws = p->ws;
@@ -707,11 +755,13 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     memcpy(&tb, p->tmap_b, sizeof(CUtensorMap));
     // <= one CTA per SM anyway: take the deep 6-stage pipeline; otherwise 3 stages x 2 CTAs/SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
+    // fused split-K reduction needs every CTA of the launch resident at once (counter barrier)
+    if (a.splits > 1 && p->split_sync && ctas <= 148) a.split_sync = reinterpret_cast<int*>(p->split_sync);
     static const int force_stages = [] { const char* v = getenv("SFB_GEMM_STAGES"); return v ? atoi(v) : 0; }();
-    const bool deep = force_stages ? (force_stages == 6) : (ctas <= 148);
+    const bool deep = a.split_sync ? true : (force_stages ? (force_stages == 6) : (ctas <= 148));
     int rc = deep ? launch_gemm<BN, 6>(ta, tb, a, grid, stream) : launch_gemm<BN, 3>(ta, tb, a, grid, stream);
     if (rc) return rc;
-    if (a.splits > 1) {
+    if (a.splits > 1 && !a.split_sync) {
         const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
         const long long items = (long long)e.M * (ncols / 8);
         const int blocks = (int)((items + 255) / 256);

@@ -21,7 +21,7 @@ class GemmParams(C.Structure):
         ("dtype", C.c_int32),
         ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32), ("cin", C.c_int32),
         ("conv_stride", C.c_int32), ("box_h", C.c_int32), ("box_n", C.c_int32),
-        ("splits", C.c_int32), ("ws", C.c_void_p),
+        ("splits", C.c_int32), ("ws", C.c_void_p), ("split_sync", C.c_void_p),
         ("epi", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int32),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p),
         ("rows_per_img", C.c_int32), ("ld_rowbias", C.c_int32),

@@ -163,7 +163,7 @@ def _a_map(a, cn, dry):
 def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, out=None, ldo=0,
             bias=None, rowbias=None, rows_per_img=1, ld_rowbias=0, residual=None, ldr=0,
             epi=EPI_STORE, geglu_n_out=0, conv=None, qkv=None, ws=None, splits=None, keep=(),
-            rowstats_out=None, ln=None, dry=False):
+            rowstats_out=None, ln=None, dry=False, split_sync=None):
     """Either pass ready-made maps (`a_map`, `b_map`: no cluster) or operand descriptors
     (`a` from a_matrix()/a_conv(), `b` a Mat), in which case a thread-block cluster with TMA
     multicast is chosen from the tile grid."""
@@ -206,6 +206,7 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         if ws.numel() < need:
             raise ValueError(f"{name}: split-K workspace too small ({ws.numel()} < {need})")
         p.ws = _ptr(ws) if not hasattr(ws, "finalize") else 0
+        p.split_sync = _ptr(split_sync)
     p.epi = epi
     p.out = _ptr(out)
     p.ldo = ldo

@@ -189,6 +189,8 @@ class UNetPlan:
         self.ln_arena = self._alloc((max(self._ln_arena_floats(), 2),), torch.float32)
         self.ws = None
         self._ws_need = 0
+        # arrive/done counters of the fused split-K reduction (self re-arming: zeroed once, here)
+        self.split_sync = self._alloc((2 * 1024,), torch.int32)
         self._build()
         assert self._ln_used <= self.ln_arena.numel(), (self._ln_used, self.ln_arena.numel())
 
@@ -240,6 +242,7 @@ class UNetPlan:
     def _gemm(self, name, **kw):
         # split-K workspace: one shared fp32 buffer, sized after all ops are known
         kw.setdefault("ws", self._ws_token)
+        kw.setdefault("split_sync", self.split_sync)
         op = ops.gemm_op(name, self.lib_or_dry(), dry=self.dry, **kw)
         return op
 

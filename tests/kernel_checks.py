@@ -42,7 +42,8 @@ def _rand(*shape, dt=torch.float16, scale=1.0, seed=None):
 
 
 # ------------------------------------------------------------------------------------------
-def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, residual=True, seed=0):
+def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, residual=True, seed=0,
+               fused_reduce=True):
     lib = _lib.lib()
     a = _rand(M, K, dt=dt, seed=seed)
     w = _rand(N, K, dt=dt, scale=1 / math.sqrt(K))
@@ -50,9 +51,16 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     r = _rand(M, N, dt=dt) if residual else None
     out = torch.zeros(M, N, device=DEV, dtype=dt)
     ws = torch.empty(max(splits, 1) * M * N, device=DEV, dtype=torch.float32)
+    sync = torch.zeros(2048, device=DEV, dtype=torch.int32) if fused_reduce else None
     op = ops.gemm_op("gemm", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=ops.Mat(w), M=M, N=N, K=K,
-                     dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits)
+                     dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits,
+                     split_sync=sync)
     op.launch(_stream())
+    if fused_reduce and splits > 1:  # counters must re-arm themselves: run it twice
+        out.zero_()
+        op.launch(_stream())
+        torch.cuda.synchronize()
+        assert int(sync.abs().sum()) == 0, "split-K counters did not re-arm"
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t()
     if bias:
@@ -74,7 +82,7 @@ def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1):
     op = ops.gemm_op("geglu", lib, a=ops.a_matrix(x.data_ptr(), M, K, K), b=ops.Mat(wp), M=M, N=Np, K=K,
                      dt=dt,
                      out=out, ldo=inner, bias=bp, epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws,
-                     splits=splits)
+                     splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32))
     op.launch(_stream())
     torch.cuda.synchronize()
     # reference semantics: h * gelu(gate), hidden first (sfast passes/__init__.py:643-648)
@@ -104,7 +112,7 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
     op = ops.gemm_op("conv", lib, a=adesc, b=ops.Mat(wp),
                      M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb,
                      rows_per_img=ho * wo, ld_rowbias=cout, residual=r, ldr=cout, ws=ws,
-                     splits=splits,
+                     splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32),
                      conv=dict(n=n, h=ho, w=wo, cin=cin, stride=stride, box_n=box_n, box_h=box_h))
     op.launch(_stream())
     torch.cuda.synchronize()
@@ -326,9 +334,10 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
     x = torch.zeros(M, C, device=DEV, dtype=dt)
     stats = torch.zeros(M, 2, device=DEV)
     ws = torch.empty(16 * M * max(N, C) * 2, device=DEV, dtype=torch.float32)
+    sync = torch.zeros(2048, device=DEV, dtype=torch.int32)
     ops.gemm_op("producer", lib, a=ops.a_matrix(a.data_ptr(), M, C, C), b=ops.Mat(w0),
                 M=M, N=C, K=C, dt=dt, out=x, ldo=C, residual=res, ldr=C, ws=ws, splits=splits_p,
-                rowstats_out=stats).launch(_stream())
+                split_sync=sync, rowstats_out=stats).launch(_stream())
     gamma = torch.randn(C, device=DEV) * 0.5 + 1.0
     beta = torch.randn(C, device=DEV) * 0.3
     if mode == "geglu":
@@ -340,7 +349,7 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         out = torch.zeros(M, inner, device=DEV, dtype=dt)
         ops.gemm_op("consumer", lib, a=ops.a_matrix(x.data_ptr(), M, C, C),
                     b=ops.Mat(wt), M=M, N=wt.shape[0], K=C, dt=dt, out=out, ldo=inner, bias=bp,
-                    epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws, splits=splits_c,
+                    epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws, splits=splits_c, split_sync=sync,
                     ln=dict(rowstats=stats, colsum=cs, eps=1e-5, dim=C)).launch(_stream())
     else:
         w = _rand(N, C, dt=dt, scale=1 / math.sqrt(C))
@@ -349,7 +358,7 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         out = torch.zeros(M, N, device=DEV, dtype=dt)
         ops.gemm_op("consumer", lib, a=ops.a_matrix(x.data_ptr(), M, C, C),
                     b=ops.Mat(wp.contiguous()), M=M, N=N, K=C, dt=dt, out=out, ldo=N, bias=bias,
-                    ws=ws, splits=splits_c,
+                    ws=ws, splits=splits_c, split_sync=sync,
                     ln=dict(rowstats=stats, colsum=colsum, eps=1e-5, dim=C)).launch(_stream())
     torch.cuda.synchronize()
     xr = (a.float() @ w0.float().t() + res.float())
@@ -410,6 +419,8 @@ CHECKS = {
     "gemm_k64": (lambda: check_gemm(128, 160, 64, bias=False, residual=False), 2e-3),
     "gemm_big": (lambda: check_gemm(8192, 1280, 1280), 2e-3),
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
+    "gemm_splitk_finish_kernel": (lambda: check_gemm(256, 1280, 5120, splits=8, fused_reduce=False), 2e-3),
+    "gemm_splitk_18": (lambda: check_gemm(128, 1280, 11520, splits=18), 2e-3),
     "gemm_cluster_2x4": (lambda: check_gemm(1024, 640, 640), 2e-3),
     "gemm_cluster_1x4_ragged": (lambda: check_gemm(500, 480, 320), 2e-3),
     "gemm_cluster_2x2_splitk": (lambda: check_gemm(256, 640, 2560, splits=4), 2e-3),
