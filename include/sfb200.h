@@ -134,6 +134,10 @@ typedef struct sfb_gemm_params {
      * cluster_m (1|2|4) CTAs along M share one weight tile (tmap_b box = 160/cluster_m rows).
      * The tile grid must be divisible by the cluster shape. */
     int32_t cluster_n, cluster_m, a_part_dim, a_part_ext;
+    /* 1: CTA pairs along M run tcgen05.mma.cta_group::2 on 256 x 160 tiles (each CTA stages its own
+     * A rows and HALF of the weight tile: tmap_b box = 80 rows); needs an even number of M tiles
+     * and cluster_n = cluster_m = 0/1. */
+    int32_t cta_pair;
     /* LayerNorm folded around the GEMM (replaces sfast_triton::layer_norm,
      * /root/reference/src/sfast/triton/ops/layer_norm.py:51-133, as a separate pass):
      *   producer (SFB_EPI_STORE): rowstats_out[m] += (sum, sum of squares) of the stored row;

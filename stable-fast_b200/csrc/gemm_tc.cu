@@ -267,10 +267,14 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
 // ---------------------------------------------------------------------------------------
 // the GEMM kernel
 // ---------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster 1x2 along M) computes a 256 x BN
+// tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 A rows but only HALF of the
+// weight tile, which cuts the shared-memory traffic per MMA (the 1-CTA kernel is smem-bandwidth
+// bound: 36 KB written + 36 KB read per 320 MMA cycles at 128 B/clk).
+template <int BN, int STAGES, int CG = 1>
 struct GemmSmem {
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2 / CG;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
     static constexpr int kBiasOffset = kBarOffset + 256;              // fp32 [kBiasSlots][BN]
@@ -282,15 +286,15 @@ struct GemmSmem {
     // +4 float pad makes the thread-per-row float4 writes of phase A bank-conflict free
     static constexpr int kStagePitch = BN + 4;
     static_assert(BM * kStagePitch * 4 <= kBarOffset, "staging tile must fit in the stage buffers");
-    static_assert(STAGES > 3 || 2 * (kTotal + 1024) <= 228 * 1024, "3-stage config must fit twice per SM");
+    static_assert(STAGES > 4 || 2 * (kTotal + 1024) <= 228 * 1024, "shallow configs must fit twice per SM");
     static_assert(BN == 160, "the epilogue's 32+32+16 TMEM load split assumes 80-column halves");
 };
 
-template <int BN, int STAGES, int BF16>
-__global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
+template <int BN, int STAGES, int BF16, int CG>
+__global__ void __launch_bounds__(kGemmThreads, STAGES <= 4 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmArgs args) {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, CG>;
     constexpr uint32_t kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -320,20 +324,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_prefetch_desc(&tma_b);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            // released by every CTA whose stage this CTA's multicasts write into
-            mbar_init(&empty_bar[i], args.cx + args.cy - 1);
+            // released by every CTA whose stage this CTA's multicasts write into (pair mode: by
+            // the leader's multicast commit only)
+            mbar_init(&empty_bar[i], CG == 2 ? 1 : args.cx + args.cy - 1);
         }
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    const bool clustered = args.cx * args.cy > 1;
-    const int cix = clustered ? (int)cluster_ctaid_x() : 0;
+    const bool clustered = (CG == 2) || args.cx * args.cy > 1;
+    const int cix = (clustered && CG == 1) ? (int)cluster_ctaid_x() : 0;
     const int ciy = clustered ? (int)cluster_ctaid_y() : 0;
+    const bool leader = (CG == 1) || ciy == 0;  // pair mode: the even CTA issues every MMA
     // CTAs sharing this CTA's A tile (same M-tile: all cix) / weight tile (same N-tile: all ciy)
     const uint16_t mask_a = (uint16_t)(((1u << args.cx) - 1u) << (ciy * args.cx));
     uint16_t mask_b = 0;
     for (int y = 0; y < args.cy; ++y) mask_b |= (uint16_t)(1u << (y * args.cx + cix));
-    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_pair<kTmemCols>(tmem_slot);
+        else tmem_alloc<kTmemCols>(tmem_slot);
+    }
     // Everything up to each role's pdl_wait() overlaps the previous kernel's tail (programmatic
     // dependent launch); global memory produced by it is only touched after that wait.
     pdl_launch_dependents();
@@ -360,8 +369,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const int stage = i % STAGES;
                 const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], L::kStageBytes);
                 const int kb = kb_begin + i;
+                if (CG == 2) {
+                    // pair mode: both CTAs' bytes are counted on the LEADER's barrier
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                    uint8_t* dA = sA + stage * L::kABytes;
+                    uint8_t* dB = sB + stage * L::kBBytes;
+                    const int b_row2 = (n_tile * args.nkb_total + kb) * BN + ciy * (BN / 2);
+                    if (args.a_mode == SFB_A_MATRIX) {
+                        tma_load_2d_pair(dA, &tma_a, &full_bar[stage], kb * BK, m_tile * BM);
+                    } else {
+                        const int tap = kb / args.cpb;
+                        const int cc = kb - tap * args.cpb;
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        tma_load_4d_pair(dA, &tma_a, &full_bar[stage], cc * BK, kw - 1,
+                                         h0 * args.conv_stride + kh - 1, n0);
+                    }
+                    tma_load_2d_pair(dB, &tma_b, &full_bar[stage], 0, b_row2);
+                    continue;
+                }
+                mbar_expect_tx(&full_bar[stage], L::kStageBytes);
                 uint8_t* dstA = sA + stage * L::kABytes + cix * (L::kABytes / args.cx);
                 uint8_t* dstB = sB + stage * L::kBBytes + ciy * (L::kBBytes / args.cy);
                 // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous BN x 64 block
@@ -392,8 +419,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(BM, BN, BF16 != 0);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_f16(BM * CG, BN, BF16 != 0);
             for (int i = 0; i < nkb; ++i) {
                 const int stage = i % STAGES;
                 const uint32_t phase = (i / STAGES) & 1;
@@ -405,13 +432,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     // +32 bytes along K inside the 128-byte swizzle atom = +2 in the >>4 field
-                    umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                (i | k) != 0);
+                    if (CG == 2)
+                        umma_f16_ss_pair(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                         (i | k) != 0);
+                    else
+                        umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                    (i | k) != 0);
                 }
-                if (clustered) umma_commit_mc(&empty_bar[stage], (uint16_t)(mask_a | mask_b));
+                if (CG == 2) umma_commit_pair(&empty_bar[stage], 0b11);
+                else if (clustered) umma_commit_mc(&empty_bar[stage], (uint16_t)(mask_a | mask_b));
                 else umma_commit(&empty_bar[stage]);
             }
-            umma_commit(tmem_full_bar);
+            if (CG == 2) umma_commit_pair(tmem_full_bar, 0b11);
+            else umma_commit(tmem_full_bar);
             if (dbg) dbg[4] = globaltimer_ns();
         }
         __syncwarp();
@@ -462,21 +495,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int ncol0 = n_tile * BN;
         const bool partial = args.splits > 1;
         constexpr int kGroups = BN / 8;  // 16-byte output slices per row
-        // The residual tile is fetched NOW, in the coalesced phase-B ownership (thread <-> 16-byte
-        // slice), so its 40 KB are in flight for the whole main loop instead of being a serial
-        // latency after it.
+        // Residual in the coalesced phase-B ownership (thread <-> 16-byte slice), software-pipelined
+        // in batches of 5 slices; the first batch is issued before the accumulator is even ready.
+        // (Loops here are deliberately ROLLED: the epilogue runs once per CTA, so straight-line
+        // unrolled code is all instruction-cache misses -- measured 5 us per tile on B200.)
         const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE) && !partial;
-        uint4 res[kGroups];
+        constexpr int kBatch = 5;
+        auto item_addr = [&](int it, int& row, int& grp, int& mm, int& n) {
+            const int idx = et + it * 128;
+            row = idx / kGroups;
+            grp = idx - row * kGroups;
+            mm = sRowM[row];
+            n = ncol0 + grp * 8;
+        };
+        auto load_res = [&](int it) -> uint4 {
+            int row, grp, mm, n;
+            item_addr(it, row, grp, mm, n);
+            return (mm >= 0 && n < e.N)
+                ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.residual) + (size_t)mm * e.ldr + n)
+                : make_uint4(0, 0, 0, 0);
+        };
+        uint4 rcur[kBatch], rnxt[kBatch];
         if (has_res) {
 #pragma unroll
-            for (int it = 0; it < kGroups; ++it) {
-                const int idx = et + it * 128;
-                const int row = idx / kGroups, grp = idx - row * kGroups;
-                const int mm = sRowM[row], n = ncol0 + grp * 8;
-                res[it] = (mm >= 0 && n < e.N)
-                    ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.residual) + (size_t)mm * e.ldr + n)
-                    : make_uint4(0, 0, 0, 0);
-            }
+            for (int j = 0; j < kBatch; ++j) rcur[j] = load_res(j);
         }
         float2 ln = make_float2(0.f, 1.f);
         if (e.ln_rowstats && valid && !partial) ln = ln_row_params(e, m);
@@ -525,7 +567,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
         };
         if (partial) {
-#pragma unroll 4
+#pragma unroll 1
             for (int it = 0; it < kGroups; ++it) {
                 const int idx = et + it * 128;
                 const int row = idx / kGroups, grp = idx - row * kGroups;
@@ -576,7 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             }
         } else if (e.epi == SFB_EPI_GEGLU) {
-#pragma unroll 2
+#pragma unroll 1
             for (int it = 0; it < kGroups / 2; ++it) {
                 const int idx = et + it * 128;
                 const int row = idx / (kGroups / 2), og = idx - row * (kGroups / 2);
@@ -589,31 +631,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             }
         } else {
-            // V^T columns want consecutive lanes = consecutive rows (2-byte stores along seq);
-            // everything else wants consecutive lanes = consecutive 16-byte slices of a row
-            bool row_fastest = false;
-            if (e.epi == SFB_EPI_QKV) {
+            if (e.epi == SFB_EPI_STORE) {
+#pragma unroll 1
+                for (int b = 0; b < kGroups / kBatch; ++b) {
+                    if (has_res && b + 1 < kGroups / kBatch) {
+#pragma unroll
+                        for (int j = 0; j < kBatch; ++j) rnxt[j] = load_res((b + 1) * kBatch + j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) {
+                        int row, grp, mm, n;
+                        item_addr(b * kBatch + j, row, grp, mm, n);
+                        if (mm >= 0 && n < e.N) {
+                            float f[8];
+                            load8(row, grp * 8, f);
+                            if (has_res) add_res8(rcur[j], BF16, f);
+                            if (e.rowstats_out) {  // final values back to the tile for the row reduction
+                                float* d = sStage + row * L::kStagePitch + grp * 8;
+                                *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
+                                *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                            }
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)mm * e.ldo + n) =
+                                pack8(f, BF16);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) rcur[j] = rnxt[j];
+                }
+            } else {
+                // QKV scatter.  V^T columns want consecutive lanes = consecutive rows (2-byte stores
+                // along seq); Q / K want consecutive lanes = consecutive 16-byte slices of a row.
                 const int C = e.heads * e.head_dim;
                 const int n_last = min(ncol0 + BN, e.N) - 1;
-                row_fastest = (ncol0 / C + e.which_base == 2) && (n_last / C + e.which_base == 2);
-            }
-#pragma unroll
-            for (int it = 0; it < kGroups; ++it) {
-                const int idx = et + it * 128;
-                int row, grp;
-                if (row_fastest) { grp = idx >> 7; row = idx & 127; }
-                else { row = idx / kGroups; grp = idx - row * kGroups; }
-                const int mm = sRowM[row], n = ncol0 + grp * 8;
-                if (mm >= 0 && n < e.N) {
-                    float f[8];
-                    load8(row, grp * 8, f);
-                    if (has_res) add_res8(res[it], BF16, f);
-                    if (e.rowstats_out) {  // final values back to the tile for the row reduction
-                        float* d = sStage + row * L::kStagePitch + grp * 8;
-                        *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
-                        *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                const bool row_fastest = (ncol0 / C + e.which_base == 2) && (n_last / C + e.which_base == 2);
+#pragma unroll 1
+                for (int it = 0; it < kGroups; ++it) {
+                    const int idx = et + it * 128;
+                    int row, grp;
+                    if (row_fastest) { grp = idx >> 7; row = idx & 127; }
+                    else { row = idx / kGroups; grp = idx - row * kGroups; }
+                    const int mm = sRowM[row], n = ncol0 + grp * 8;
+                    if (mm >= 0 && n < e.N) {
+                        float f[8];
+                        load8(row, grp * 8, f);
+                        epi_store8<BF16>(e, mm, n, f);
                     }
-                    epi_store8<BF16>(e, mm, n, f);
                 }
             }
             if (e.rowstats_out) {
@@ -641,7 +703,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<kTmemCols>(tmem_base);
+        if (CG == 2) tmem_dealloc_pair<kTmemCols>(tmem_base);
+        else tmem_dealloc<kTmemCols>(tmem_base);
     }
     if (dbg && threadIdx.x == 32) dbg[7] = globaltimer_ns();
 }
@@ -650,28 +713,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
 using namespace sfb;
 
-template <int BN, int STAGES, int BF16>
+template <int BN, int STAGES, int BF16, int CG>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
                          cudaStream_t stream) {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, BF16>,
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, BF16, CG>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
         attr_set = true;
     }
-    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<BN, STAGES, BF16>, grid, dim3(kGemmThreads),
-                                         dim3(a.cx, a.cy, 1), L::kTotal, stream, ta, tb, a);
+    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<BN, STAGES, BF16, CG>, grid, dim3(kGemmThreads),
+                                         CG == 2 ? dim3(1, 2, 1) : dim3(a.cx, a.cy, 1), L::kTotal, stream,
+                                         ta, tb, a);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s", cudaGetErrorString(err));
     return check_launch("sfb_gemm");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
                        cudaStream_t stream) {
-    return a.e.dtype == SFB_BF16 ? launch_gemm_t<BN, STAGES, 1>(ta, tb, a, grid, stream)
-                                 : launch_gemm_t<BN, STAGES, 0>(ta, tb, a, grid, stream);
+    return a.e.dtype == SFB_BF16 ? launch_gemm_t<BN, STAGES, 1, CG>(ta, tb, a, grid, stream)
+                                 : launch_gemm_t<BN, STAGES, 0, CG>(ta, tb, a, grid, stream);
 }
 
 extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
@@ -759,7 +823,15 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     if (a.splits > 1 && p->split_sync && ctas <= 148) a.split_sync = reinterpret_cast<int*>(p->split_sync);
     static const int force_stages = [] { const char* v = getenv("SFB_GEMM_STAGES"); return v ? atoi(v) : 0; }();
     const bool deep = a.split_sync ? true : (force_stages ? (force_stages == 6) : (ctas <= 148));
-    int rc = deep ? launch_gemm<BN, 6>(ta, tb, a, grid, stream) : launch_gemm<BN, 3>(ta, tb, a, grid, stream);
+    int rc;
+    if (p->cta_pair) {
+        // CTA pairs along M (cluster 1x2, tcgen05.mma.cta_group::2): tmap_b box = 80 rows
+        if (grid.y % 2 || a.cx != 1 || a.cy != 1)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: cta_pair needs an even number of M tiles and no multicast cluster");
+        rc = deep ? launch_gemm<BN, 8, 2>(ta, tb, a, grid, stream) : launch_gemm<BN, 4, 2>(ta, tb, a, grid, stream);
+    } else {
+        rc = deep ? launch_gemm<BN, 6, 1>(ta, tb, a, grid, stream) : launch_gemm<BN, 3, 1>(ta, tb, a, grid, stream);
+    }
     if (rc) return rc;
     if (a.splits > 1 && !a.split_sync) {
         const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;

@@ -31,7 +31,7 @@ class GemmParams(C.Structure):
         ("seq", C.c_int32), ("q_pitch", C.c_int32), ("q_rows", C.c_int32),
         ("k_rows", C.c_int32), ("vt_rows", C.c_int32), ("vt_pitch", C.c_int32),
         ("cluster_n", C.c_int32), ("cluster_m", C.c_int32), ("a_part_dim", C.c_int32),
-        ("a_part_ext", C.c_int32),
+        ("a_part_ext", C.c_int32), ("cta_pair", C.c_int32),
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_dim", C.c_int32),
         ("debug_stamps", C.c_void_p),

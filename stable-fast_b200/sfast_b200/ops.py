@@ -121,6 +121,9 @@ def choose_splits(m_tiles, n_tiles, nkb):
 ENABLE_CLUSTER = os.environ.get("SFB_CLUSTER", "0") != "0"  # measured slower on B200: smem-bound, see DESIGN.md
 
 
+ENABLE_CTA_PAIR = os.environ.get("SFB_CTA_PAIR", "0") != "0"
+
+
 def choose_cluster(m_tiles, n_tiles):
     """(cluster_n, cluster_m): CTAs sharing an A tile (along N, <= 2) / a weight tile (along M, <= 4).
     TMA multicast turns cluster_m (cluster_n) L2 reads of the same tile into one."""
@@ -163,7 +166,7 @@ def _a_map(a, cn, dry):
 def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, out=None, ldo=0,
             bias=None, rowbias=None, rows_per_img=1, ld_rowbias=0, residual=None, ldr=0,
             epi=EPI_STORE, geglu_n_out=0, conv=None, qkv=None, ws=None, splits=None, keep=(),
-            rowstats_out=None, ln=None, dry=False, split_sync=None):
+            rowstats_out=None, ln=None, dry=False, split_sync=None, cta_pair=None):
     """Either pass ready-made maps (`a_map`, `b_map`: no cluster) or operand descriptors
     (`a` from a_matrix()/a_conv(), `b` a Mat), in which case a thread-block cluster with TMA
     multicast is chosen from the tile grid."""
@@ -173,7 +176,13 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
             else (conv["n"] + conv["box_n"] - 1) // conv["box_n"]
     else:
         mt = (M + BM - 1) // BM
-    if a is not None:
+    if a is not None and (ENABLE_CTA_PAIR if cta_pair is None else cta_pair) and mt % 2 == 0:
+        # CTA pairs along M: tcgen05.mma.cta_group::2, each CTA stages half of the weight tile
+        a_map, _, _ = _a_map(a, 1, dry)
+        b_map = b.map_for(2)
+        p.cta_pair = 1
+        keep = tuple(keep) + (b,)
+    elif a is not None:
         cn, cm = choose_cluster(mt, (N + BN - 1) // BN)
         if a["kind"] == "conv" and cn == 2 and a["box_n"] == 1 and a["box_h"] == 1 and a["wo"] % 2:
             cn = 1

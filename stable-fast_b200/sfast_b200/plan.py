@@ -13,6 +13,7 @@ Design points:
     GEGLU, one concatenated matrix for all 22 time-embedding projections).
 """
 import math
+import os
 
 import torch
 
@@ -242,7 +243,8 @@ class UNetPlan:
     def _gemm(self, name, **kw):
         # split-K workspace: one shared fp32 buffer, sized after all ops are known
         kw.setdefault("ws", self._ws_token)
-        kw.setdefault("split_sync", self.split_sync)
+        if os.environ.get("SFB_FUSED_SPLITK", "0") != "0":  # measured slower than the reduce kernel
+            kw.setdefault("split_sync", self.split_sync)
         op = ops.gemm_op(name, self.lib_or_dry(), dry=self.dry, **kw)
         return op
 

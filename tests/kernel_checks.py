@@ -43,7 +43,7 @@ def _rand(*shape, dt=torch.float16, scale=1.0, seed=None):
 
 # ------------------------------------------------------------------------------------------
 def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, residual=True, seed=0,
-               fused_reduce=True):
+               fused_reduce=True, pair=None):
     lib = _lib.lib()
     a = _rand(M, K, dt=dt, seed=seed)
     w = _rand(N, K, dt=dt, scale=1 / math.sqrt(K))
@@ -54,7 +54,7 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     sync = torch.zeros(2048, device=DEV, dtype=torch.int32) if fused_reduce else None
     op = ops.gemm_op("gemm", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=ops.Mat(w), M=M, N=N, K=K,
                      dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits,
-                     split_sync=sync)
+                     split_sync=sync, cta_pair=pair)
     op.launch(_stream())
     if fused_reduce and splits > 1:  # counters must re-arm themselves: run it twice
         out.zero_()
@@ -92,7 +92,7 @@ def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1):
 
 
 def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, splits=None,
-               rowbias=True, residual=True, pitch_extra=0, seed=2):
+               rowbias=True, residual=True, pitch_extra=0, seed=2, pair=None):
     lib = _lib.lib()
     torch.manual_seed(seed)
     ld = cin + pitch_extra
@@ -113,6 +113,7 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
                      M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb,
                      rows_per_img=ho * wo, ld_rowbias=cout, residual=r, ldr=cout, ws=ws,
                      splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32),
+                     cta_pair=pair,
                      conv=dict(n=n, h=ho, w=wo, cin=cin, stride=stride, box_n=box_n, box_h=box_h))
     op.launch(_stream())
     torch.cuda.synchronize()
@@ -421,6 +422,15 @@ CHECKS = {
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
     "gemm_splitk_finish_kernel": (lambda: check_gemm(256, 1280, 5120, splits=8, fused_reduce=False), 2e-3),
     "gemm_splitk_18": (lambda: check_gemm(128, 1280, 11520, splits=18), 2e-3),
+    "gemm_pair": (lambda: check_gemm(512, 320, 640, pair=True), 2e-3),
+    "gemm_pair_big": (lambda: check_gemm(8192, 1280, 1280, pair=True), 2e-3),
+    "gemm_pair_ragged": (lambda: check_gemm(300, 480, 320, pair=True), 2e-3),
+    "gemm_pair_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8, pair=True), 2e-3),
+    "gemm_pair_bf16": (lambda: check_gemm(512, 320, 320, dt=torch.bfloat16, pair=True), 1e-2),
+    "conv_pair_64": (lambda: check_conv(2, 64, 64, 320, 320, splits=1, pair=True), 2e-3),
+    "conv_pair_16_splitk": (lambda: check_conv(2, 16, 16, 1280, 1280, pair=True), 2e-3),
+    "conv_pair_8": (lambda: check_conv(4, 8, 8, 1280, 1280, pair=True), 2e-3),
+    "conv_pair_stride2": (lambda: check_conv(2, 64, 64, 320, 320, stride=2, residual=False, rowbias=False, pair=True), 2e-3),
     "gemm_cluster_2x4": (lambda: check_gemm(1024, 640, 640), 2e-3),
     "gemm_cluster_1x4_ragged": (lambda: check_gemm(500, 480, 320), 2e-3),
     "gemm_cluster_2x2_splitk": (lambda: check_gemm(256, 640, 2560, splits=4), 2e-3),
