@@ -310,8 +310,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x;
-    const int m_tile = blockIdx.y;
+    // pair mode: the two CTAs of a cta_group::2 pair must be neighbours along the cluster's x axis,
+    // so the M tiles run along grid.x there (grid = (m_tiles, n_tiles, splits), cluster (2,1,1))
+    const int n_tile = CG == 2 ? blockIdx.y : blockIdx.x;
+    const int m_tile = CG == 2 ? blockIdx.x : blockIdx.y;
+    const int n_tiles_grid = CG == 2 ? gridDim.y : gridDim.x;
     const int split = blockIdx.z;
     long long* dbg = args.dbg ? args.dbg + 8 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = globaltimer_ns();
@@ -333,7 +336,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     const bool clustered = (CG == 2) || args.cx * args.cy > 1;
     const int cix = (clustered && CG == 1) ? (int)cluster_ctaid_x() : 0;
-    const int ciy = clustered ? (int)cluster_ctaid_y() : 0;
+    const int ciy = clustered ? (CG == 2 ? (int)cluster_ctaid_x() : (int)cluster_ctaid_y()) : 0;
     const bool leader = (CG == 1) || ciy == 0;  // pair mode: the even CTA issues every MMA
     // CTAs sharing this CTA's A tile (same M-tile: all cix) / weight tile (same N-tile: all ciy)
     const uint16_t mask_a = (uint16_t)(((1u << args.cx) - 1u) << (ciy * args.cx));
@@ -584,7 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 // Fused reduction: the `splits` CTAs of this output tile (all co-resident: the host
                 // only enables this when the whole grid fits on the GPU at once) meet at a counter
                 // barrier, then each reduces + finishes its own slice of the tile's rows.
-                int* cnt = args.split_sync + 2 * (m_tile * gridDim.x + n_tile);
+                int* cnt = args.split_sync + 2 * (m_tile * n_tiles_grid + n_tile);
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (et == 0) {
@@ -725,9 +728,24 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
         attr_set = true;
     }
     cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<BN, STAGES, BF16, CG>, grid, dim3(kGemmThreads),
-                                         CG == 2 ? dim3(1, 2, 1) : dim3(a.cx, a.cy, 1), L::kTotal, stream,
+                                         CG == 2 ? dim3(2, 1, 1) : dim3(a.cx, a.cy, 1), L::kTotal, stream,
                                          ta, tb, a);
-    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s", cudaGetErrorString(err));
+    if (err != cudaSuccess) {
+        // diagnostics: can the requested cluster be scheduled at all?
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CG == 2 ? 2 : a.cx; at[0].val.clusterDim.y = CG == 2 ? 1 : a.cy; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int max_clusters = -1;
+        cudaError_t e2 = cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tc_kernel<BN, STAGES, BF16, CG>, &cfg);
+        cudaGetLastError();
+        return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s (%s) grid=(%u,%u,%u) cluster=(%d,%d) smem=%d stages=%d cg=%d maxActiveClusters=%d (%s)",
+                    cudaGetErrorString(err), cudaGetErrorName(err), grid.x, grid.y, grid.z,
+                    CG == 2 ? 1 : a.cx, CG == 2 ? 2 : a.cy, (int)L::kTotal, STAGES, CG, max_clusters,
+                    cudaGetErrorName(e2));
+    }
     return check_launch("sfb_gemm");
 }
 
@@ -828,7 +846,8 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
         // CTA pairs along M (cluster 1x2, tcgen05.mma.cta_group::2): tmap_b box = 80 rows
         if (grid.y % 2 || a.cx != 1 || a.cy != 1)
             return fail(SFB_ERR_INVALID, "sfb_gemm: cta_pair needs an even number of M tiles and no multicast cluster");
-        rc = deep ? launch_gemm<BN, 8, 2>(ta, tb, a, grid, stream) : launch_gemm<BN, 4, 2>(ta, tb, a, grid, stream);
+        const dim3 pgrid(grid.y, grid.x, grid.z);  // M tiles along x: pairs are x-neighbours
+        rc = deep ? launch_gemm<BN, 8, 2>(ta, tb, a, pgrid, stream) : launch_gemm<BN, 4, 2>(ta, tb, a, pgrid, stream);
     } else {
         rc = deep ? launch_gemm<BN, 6, 1>(ta, tb, a, grid, stream) : launch_gemm<BN, 3, 1>(ta, tb, a, grid, stream);
     }
