@@ -149,6 +149,14 @@ typedef struct sfb_gemm_params {
     const float* ln_colsum;    /* [N] fp32: sum_k W'[n, k] */
     float ln_eps;
     int32_t ln_dim;
+    /* GroupNorm statistics of the tensor this GEMM produces, for up to two consumers (e.g. the next
+     * resnet's norm1 and, for a skip tensor, the up-block norm over the concat buffer it lives in):
+     * gn_stats[t][img, group, 2] += (sum, sum of squares) of the stored values, with
+     * group = (gn_choff[t] + column) / gn_cpg[t], img = row / gn_rows_per_img.  SFB_EPI_STORE only;
+     * buffers are caller-zeroed.  The consumer then runs sfb_group_norm_apply alone. */
+    float* gn_stats[2];
+    int32_t gn_cpg[2], gn_choff[2];
+    int32_t gn_groups, gn_rows_per_img;
     /* optional profiling aid: int64 [ctas, 8] buffer receiving %globaltimer stamps per CTA
      * (entry, setup done, first TMA issued, first data landed, MMAs issued, accumulator ready,
      * epilogue stored, exit); NULL in production */

@@ -46,6 +46,10 @@ struct EpiArgs {
     void* k;
     void* vt;
     int heads, head_dim, which_base, seq, q_pitch, q_rows, k_rows, vt_rows, vt_pitch;
+    // GroupNorm statistics of the tensor this GEMM writes, accumulated for up to two consumers
+    float* gn_stats[2];
+    int gn_cpg[2], gn_choff[2];
+    int gn_groups, gn_rpi;
     // LayerNorm folded around the GEMM (see sfb200.h): producer side / consumer side
     float* rowstats_out;
     const float* ln_rowstats;
@@ -107,6 +111,38 @@ __device__ __forceinline__ void add_res8(uint4 r, int dtype, float (&acc)[8]) {
     f = unpack2(r.y, dtype); acc[2] += f.x; acc[3] += f.y;
     f = unpack2(r.z, dtype); acc[4] += f.x; acc[5] += f.y;
     f = unpack2(r.w, dtype); acc[6] += f.x; acc[7] += f.y;
+}
+
+template <int BF16>
+__device__ __forceinline__ float round16(float v) {
+    if (BF16) return __bfloat162float(__float2bfloat16_rn(v));
+    return __half2float(__float2half_rn(v));
+}
+
+// GroupNorm partial sums of 8 stored values (row m, columns n..n+7) straight to global memory:
+// used by the split-K reduction kernel, where a thread owns one 8-column slice.
+template <int BF16>
+__device__ __forceinline__ void gn_accumulate8(const EpiArgs& e, int m, int n, const float (&acc)[8]) {
+    const int img = m / e.gn_rpi;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        if (!e.gn_stats[t]) continue;
+        int g_run = (e.gn_choff[t] + n) / e.gn_cpg[t];
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (e.gn_choff[t] + n + i) / e.gn_cpg[t];
+            if (g != g_run) {
+                float* d = e.gn_stats[t] + ((size_t)img * e.gn_groups + g_run) * 2;
+                atomicAdd(d, s); atomicAdd(d + 1, ss);
+                g_run = g; s = 0.f; ss = 0.f;
+            }
+            const float v = round16<BF16>(acc[i]);
+            s += v; ss += v * v;
+        }
+        float* d = e.gn_stats[t] + ((size_t)img * e.gn_groups + g_run) * 2;
+        atomicAdd(d, s); atomicAdd(d + 1, ss);
+    }
 }
 
 // (sum, sum of squares) of 8 values as they will be stored (rounded to the 16-bit type)
@@ -246,6 +282,7 @@ __device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int
             atomicAdd(e.rowstats_out + 2 * (size_t)m, rs);
             atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rss);
         }
+        if (e.gn_stats[0] && e.epi == SFB_EPI_STORE) gn_accumulate8<BF16>(e, m, n, acc);
         epi_store8<BF16>(e, m, n, acc);
     }
 }
@@ -285,7 +322,8 @@ struct GemmSmem {
     // fp32 staging tile of the epilogue, aliased onto the (by then idle) pipeline stages; the
     // +4 float pad makes the thread-per-row float4 writes of phase A bank-conflict free
     static constexpr int kStagePitch = BN + 4;
-    static_assert(BM * kStagePitch * 4 <= kBarOffset, "staging tile must fit in the stage buffers");
+    static_assert(BM * kStagePitch * 4 + BM * 4 + 2 * 8 * (BN / 2 + 2) * 2 * 4 <= kBarOffset,
+                  "staging tile + GroupNorm accumulators must fit in the stage buffers");
     static_assert(STAGES > 4 || 2 * (kTotal + 1024) <= 228 * 1024, "shallow configs must fit twice per SM");
     static_assert(BN == 160, "the epilogue's 32+32+16 TMEM load split assumes 80-column halves");
 };
@@ -649,7 +687,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             float f[8];
                             load8(row, grp * 8, f);
                             if (has_res) add_res8(rcur[j], BF16, f);
-                            if (e.rowstats_out) {  // final values back to the tile for the row reduction
+                            if (e.rowstats_out || e.gn_stats[0]) {  // final values back to the tile (row / column sums)
                                 float* d = sStage + row * L::kStagePitch + grp * 8;
                                 *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
                                 *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -678,6 +716,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         float f[8];
                         load8(row, grp * 8, f);
                         epi_store8<BF16>(e, mm, n, f);
+                    }
+                }
+            }
+            if (e.gn_stats[0] && e.epi == SFB_EPI_STORE) {
+                // GroupNorm statistics of the finished tile for the consumer(s): per-column sums over
+                // the tile's rows (split at image boundaries), merged per group in shared memory, then
+                // one fire-and-forget global atomic per (consumer, image, group, moment).
+                constexpr int kMaxImg = 8, kMaxGrp = BN / 2 + 2;
+                int* sRowImg = reinterpret_cast<int*>(smem + BM * L::kStagePitch * 4);
+                float* sGn = reinterpret_cast<float*>(sRowImg + BM);  // [2][kMaxImg][kMaxGrp][2]
+                sRowImg[r] = valid ? m / e.gn_rpi : -1;
+                for (int i = et; i < 2 * kMaxImg * kMaxGrp * 2; i += 128) sGn[i] = 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int img_base = sRowImg[0];
+                int gfirst[2] = {0, 0};
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    if (e.gn_stats[t]) gfirst[t] = (e.gn_choff[t] + ncol0) / e.gn_cpg[t];
+                for (int c = et; c < BN; c += 128) {
+                    const int n = ncol0 + c;
+                    if (n >= e.N) continue;
+                    int gl[2] = {0, 0};
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+                        if (e.gn_stats[t]) gl[t] = (e.gn_choff[t] + n) / e.gn_cpg[t] - gfirst[t];
+                    float cs = 0.f, css = 0.f;
+                    int cur = -1;
+                    auto flush = [&]() {
+                        if (cur < 0) return;
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            if (!e.gn_stats[t]) continue;
+                            float* d = sGn + ((t * kMaxImg + (cur - img_base)) * kMaxGrp + gl[t]) * 2;
+                            atomicAdd(d, cs);
+                            atomicAdd(d + 1, css);
+                        }
+                    };
+#pragma unroll 4
+                    for (int row = 0; row < BM; ++row) {
+                        const int img = sRowImg[row];
+                        if (img < 0) continue;
+                        if (img != cur) { flush(); cur = img; cs = 0.f; css = 0.f; }
+                        const float v = round16<BF16>(sStage[row * L::kStagePitch + c]);
+                        cs += v;
+                        css += v * v;
+                    }
+                    flush();
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = et; i < 2 * kMaxImg * kMaxGrp; i += 128) {
+                    const int t = i / (kMaxImg * kMaxGrp);
+                    const int slot = (i / kMaxGrp) % kMaxImg, g = i % kMaxGrp;
+                    if (!e.gn_stats[t]) continue;
+                    const float a0 = sGn[i * 2], a1 = sGn[i * 2 + 1];
+                    if (a0 != 0.f || a1 != 0.f) {
+                        float* d = e.gn_stats[t] + ((size_t)(img_base + slot) * e.gn_groups + gfirst[t] + g) * 2;
+                        atomicAdd(d, a0);
+                        atomicAdd(d + 1, a1);
                     }
                 }
             }
@@ -803,6 +899,18 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     e.q = p->q; e.k = p->k; e.vt = p->vt; e.heads = p->heads; e.head_dim = p->head_dim;
     e.which_base = p->which_base; e.seq = p->seq; e.q_pitch = p->q_pitch; e.q_rows = p->q_rows;
     e.k_rows = p->k_rows; e.vt_rows = p->vt_rows; e.vt_pitch = p->vt_pitch;
+    for (int t = 0; t < 2; ++t) {
+        e.gn_stats[t] = p->gn_stats[t]; e.gn_cpg[t] = p->gn_cpg[t]; e.gn_choff[t] = p->gn_choff[t];
+    }
+    e.gn_groups = p->gn_groups; e.gn_rpi = p->gn_rows_per_img;
+    if (p->gn_stats[0]) {
+        if (p->epi != SFB_EPI_STORE || p->gn_groups <= 0 || p->gn_rows_per_img < 16 || p->gn_cpg[0] < 2 ||
+            (p->gn_stats[1] && p->gn_cpg[1] < 2) ||
+            (BM % p->gn_rows_per_img != 0 && p->gn_rows_per_img % BM != 0))
+            return fail(SFB_ERR_INVALID, "sfb_gemm: unsupported GroupNorm statistics geometry");
+    } else if (p->gn_stats[1]) {
+        return fail(SFB_ERR_INVALID, "sfb_gemm: gn_stats[1] without gn_stats[0]");
+    }
     e.rowstats_out = p->rowstats_out; e.ln_rowstats = p->ln_rowstats; e.ln_colsum = p->ln_colsum;
     e.ln_eps = p->ln_eps; e.ln_dim = p->ln_dim;
     if (p->ln_rowstats && (!p->ln_colsum || p->ln_dim <= 0 || p->rowbias))

@@ -34,6 +34,8 @@ class GemmParams(C.Structure):
         ("a_part_ext", C.c_int32), ("cta_pair", C.c_int32),
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_dim", C.c_int32),
+        ("gn_stats", C.c_void_p * 2), ("gn_cpg", C.c_int32 * 2), ("gn_choff", C.c_int32 * 2),
+        ("gn_groups", C.c_int32), ("gn_rows_per_img", C.c_int32),
         ("debug_stamps", C.c_void_p),
     ]
 

@@ -121,7 +121,7 @@ def choose_splits(m_tiles, n_tiles, nkb):
 ENABLE_CLUSTER = os.environ.get("SFB_CLUSTER", "0") != "0"  # measured slower on B200: smem-bound, see DESIGN.md
 
 
-ENABLE_CTA_PAIR = os.environ.get("SFB_CTA_PAIR", "0") != "0"
+ENABLE_CTA_PAIR = os.environ.get("SFB_CTA_PAIR", "1") != "0"
 
 
 def choose_cluster(m_tiles, n_tiles):
@@ -272,7 +272,7 @@ def gn_fused_fits(n, hw, c, groups):
 
 
 def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, dt, sync=None,
-           dry=False):
+           dry=False, stats_ready=False):
     """GroupNorm(+SiLU): one fused launch when the tensor fits in shared memory (stats + apply
     with a grid barrier, x read once), else the two-pass stats / apply kernels."""
     p = GnParams()
@@ -283,6 +283,8 @@ def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, 
     p.sync_counter = _ptr(sync)
     keep = (p, x.buf, y.buf, gamma, beta, stats, sync)
     nb = x.rows * x.c * 2
+    if stats_ready:  # the producing GEMM(s) accumulated the statistics in their epilogue
+        return [Op(name + ".apply", lib.sfb_group_norm_apply, (C.byref(p),), keep, 0, 2 * nb)]
     if sync is not None:
         fits = gn_fused_fits(p.n, p.hw, p.c, groups) if dry else bool(
             lib.sfb_group_norm_fused_fits(C.byref(p)))

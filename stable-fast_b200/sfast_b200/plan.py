@@ -162,6 +162,10 @@ class UNetPlan:
         # embedding): issued on a forked stream so they run concurrently with the start of the
         # main chain (a parallel branch of the captured CUDA graph).
         self.side_ops = []
+        # (buffer id, channel offset) -> (GemmParams, channels) of the GEMM that last wrote that slice:
+        # lets a GroupNorm ask its producer(s) to accumulate the statistics in their epilogue
+        self._producers = {}
+        self._gn_slots = {}
         self._side_stream = None
         self._joined = False
         self._bufs = {}
@@ -254,14 +258,44 @@ class UNetPlan:
     def _a_matrix(self, x: Act):
         return ops.a_matrix(x.ptr, x.rows, x.c, x.ld)
 
+    def _producer_stats(self, x: Act, stats):
+        """Ask the GEMM(s) that produced `x` to accumulate its GroupNorm statistics in their
+        epilogue.  Returns False (nothing changed) if any slice of x has no capable producer."""
+        if os.environ.get("SFB_GN_EPILOGUE", "1") == "0":
+            return False
+        groups = self.spec.groups
+        rpi, cpg = x.h * x.w, x.c // groups
+        if rpi < 16 or cpg < 2 or (128 % rpi and rpi % 128):
+            return False
+        chain, off = [], x.off
+        while off < x.off + x.c:
+            prod = self._producers.get((id(x.buf), off))
+            if prod is None:
+                return False
+            p, c = prod
+            slot = self._gn_slots.get(id(p), 0)  # consumers already registered with this producer
+            if slot > 1 or p.epi != ops.EPI_STORE or (slot and p.gn_rows_per_img != rpi):
+                return False
+            chain.append((p, slot, off - x.off))
+            off += c
+        if off != x.off + x.c:
+            return False
+        for p, slot, choff in chain:
+            self._gn_slots[id(p)] = slot + 1
+            p.gn_stats[slot] = _ptr(stats)
+            p.gn_cpg[slot], p.gn_choff[slot] = cpg, choff
+            p.gn_groups, p.gn_rows_per_img = groups, rpi
+        return True
+
     def group_norm(self, name, x: Act, prefix, silu, eps):
         y = self.act("gn_out", x.n, x.h, x.w, x.c)
         slot = self.gn_stats[self._gn_count]
         self._gn_count += 1
+        from_producer = self._producer_stats(x, slot)
         self._emit(ops.gn_ops(name, self.lib_or_dry(), x=x, y=y, gamma=self.w.f32(prefix + ".weight"),
                               beta=self.w.f32(prefix + ".bias"), stats=slot, sync=slot[-4:],
                               groups=self.spec.groups, eps=eps, silu=silu, dt=self.dt,
-                              dry=self.dry))
+                              dry=self.dry, stats_ready=from_producer))
         return y
 
     def conv3x3(self, name, x: Act, wname, dst: Act, stride=1, rowbias=None, residual: Act = None):
@@ -279,7 +313,9 @@ class UNetPlan:
             kw.update(rowbias=rowbias[0], rows_per_img=ho * wo, ld_rowbias=rowbias[1])
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
-        self._emit(self._gemm(name, **kw))
+        op = self._gemm(name, **kw)
+        self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
+        self._emit(op)
 
     def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None, rowstats_out=None):
         kw = dict(a=self._a_matrix(x), b=wm, M=x.rows, N=wm.n, K=x.c, dt=self.dt,
@@ -287,7 +323,9 @@ class UNetPlan:
                   rowstats_out=rowstats_out)
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
-        self._emit(self._gemm(name, **kw))
+        op = self._gemm(name, **kw)
+        self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
+        self._emit(op)
 
     # ------------------------------------------------------------------ sub-graphs
     def resnet(self, r, x: Act, dst: Act):

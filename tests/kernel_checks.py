@@ -371,6 +371,43 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
     return max(e0, rel_err(out, y))
 
 
+
+def check_gn_epilogue(n=2, hw=1024, c1=640, c2=320, k=320, dt=torch.float16, splits=1, seed=14):
+    """GroupNorm statistics accumulated by the PRODUCER GEMMs' epilogues (two producers writing the
+    two channel slices of one concat buffer), then the apply-only kernel; reference: F.group_norm
+    of the stored concat tensor."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    M, C = n * hw, c1 + c2
+    buf = torch.zeros(M, C, device=DEV, dtype=dt)
+    stats = torch.zeros(n * 32 * 2 + 4, device=DEV)
+    ws = torch.empty(8 * M * max(c1, c2), device=DEV, dtype=torch.float32)
+    off = 0
+    for ci in (c1, c2):
+        a = _rand(M, k, dt=dt)
+        w = _rand(ci, k, dt=dt, scale=1.5 / math.sqrt(k))
+        b = torch.randn(ci, device=DEV)
+        op = ops.gemm_op("prod", lib, a=ops.a_matrix(a.data_ptr(), M, k, k), b=ops.Mat(w), M=M, N=ci, K=k,
+                         dt=dt, out=buf.data_ptr() + off * 2, ldo=C, bias=b, ws=ws, splits=splits)
+        p = op.keep[0]
+        p.gn_stats[0] = stats.data_ptr()
+        p.gn_cpg[0], p.gn_choff[0] = C // 32, off
+        p.gn_groups, p.gn_rows_per_img = 32, hw
+        op.launch(_stream())
+        off += ci
+    x = Act(buf, n, 1, hw, C)
+    y = torch.zeros(M, C, device=DEV, dtype=dt)
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    gops = ops.gn_ops("gn", lib, x=x, y=Act(y, n, 1, hw, C), gamma=gamma, beta=beta, stats=stats, groups=32,
+                      eps=1e-5, silu=True, dt=dt, stats_ready=True)
+    assert len(gops) == 1
+    gops[0].launch(_stream())
+    torch.cuda.synchronize()
+    xin = buf.float().view(n, hw, C).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xin, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(M, C)
+    return rel_err(y, ref)
+
+
 def diag_gemm(dt=torch.float16):
     """Informational: one-hot probes that reveal row / K permutations if a descriptor or swizzle
     is wrong.  Prints the observed k -> k' and m -> m' maps for a single 128 x 160 x 64 tile."""
@@ -438,6 +475,10 @@ CHECKS = {
     "geglu": (lambda: check_geglu(256, 320, 1280), 2e-2),
     "geglu_ragged": (lambda: check_geglu(100, 64, 256), 2e-2),
     "geglu_splitk": (lambda: check_geglu(128, 1280, 5120, splits=4), 2e-2),
+    "gn_epilogue": (lambda: check_gn_epilogue(), 1e-2),
+    "gn_epilogue_8x8": (lambda: check_gn_epilogue(4, 64, 1280, 1280, 640), 1e-2),
+    "gn_epilogue_4x4": (lambda: check_gn_epilogue(8, 16, 128, 128, 64), 1e-2),
+    "gn_epilogue_splitk": (lambda: check_gn_epilogue(2, 256, 1280, 640, 1280, splits=2), 1e-2),
     "ln_fold": (lambda: check_ln_fold(300, 320, 960), 5e-3),
     "ln_fold_1280": (lambda: check_ln_fold(512, 1280, 1280), 5e-3),
     "ln_fold_geglu": (lambda: check_ln_fold(300, 320, 1280, mode="geglu"), 2e-2),

@@ -68,8 +68,9 @@ def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     names = [op.fn.name for op in plan.all_ops() if op.fn is not None]
     assert len(plan.side_ops) == 16  # cross-attention K/V projections run on the forked stream
     # 61 GroupNorms, 48 LayerNorms, 32 attention calls, 3 upsamples
-    # B = 2 tensors fit in shared memory: all 61 GroupNorms take the single-launch fused kernel
-    assert names.count("sfb_group_norm_fused") == 61 and names.count("sfb_group_norm_apply") == 0
+    # every GroupNorm's statistics come from its producer GEMM's epilogue: apply-only kernels
+    assert names.count("sfb_group_norm_apply") == 61 and names.count("sfb_group_norm_fused") == 0
+    assert names.count("sfb_group_norm_stats") == 0
     # all 48 LayerNorms are folded into the consuming GEMMs (gamma-scaled weights + epilogue)
     assert names.count("sfb_layer_norm") == 0
     gemms = [op.keep[0] for op in plan.all_ops() if op.fn is not None and op.fn.name == "sfb_gemm"]
