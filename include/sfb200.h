@@ -151,12 +151,14 @@ typedef struct sfb_gemm_params {
     int32_t ln_dim;
     /* GroupNorm statistics of the tensor this GEMM produces, for up to two consumers (e.g. the next
      * resnet's norm1 and, for a skip tensor, the up-block norm over the concat buffer it lives in):
-     * gn_stats[t][img, group, 2] += (sum, sum of squares) of the stored values, with
-     * group = (gn_choff[t] + column) / gn_cpg[t], img = row / gn_rows_per_img.  SFB_EPI_STORE only;
-     * buffers are caller-zeroed.  The consumer then runs sfb_group_norm_apply alone. */
+     * gn_stats[t][shard, img, group, 2] += (sum, sum of squares) of the stored values, with
+     * group = (gn_choff[t] + column) / gn_cpg[t], img = row / gn_rows_per_img and shard = one of 8
+     * copies `gn_shard_stride` floats apart (spreads same-address atomics; the consumer sums them).
+     * SFB_EPI_STORE only; buffers are caller-zeroed.  The consumer then runs sfb_group_norm_apply
+     * with stat_shards = 8. */
     float* gn_stats[2];
     int32_t gn_cpg[2], gn_choff[2];
-    int32_t gn_groups, gn_rows_per_img;
+    int32_t gn_groups, gn_rows_per_img, gn_shard_stride;
     /* optional profiling aid: int64 [ctas, 8] buffer receiving %globaltimer stamps per CTA
      * (entry, setup done, first TMA issued, first data landed, MMAs issued, accumulator ready,
      * epilogue stored, exit); NULL in production */
@@ -194,6 +196,9 @@ typedef struct sfb_gn_params {
     int32_t silu;    /* 1: y = silu(gn(x)) */
     int32_t dtype;
     uint32_t* sync_counter; /* sfb_group_norm_fused only: grid-barrier counter, zeroed by caller */
+    /* sfb_group_norm_apply: `stats` may arrive as `stat_shards` partial copies (0/1 = one),
+     * `stat_shard_stride` floats apart -- the layout sfb_gemm's GroupNorm accumulation writes */
+    int32_t stat_shards, stat_shard_stride;
 } sfb_gn_params;
 
 /* two-pass path (any size): `stats` must be zero before sfb_group_norm_stats */

@@ -248,24 +248,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
             m_run = m_new;
             const float neg_m = -m_new;
 
+            // all 128 exponentials first (into 64 packed registers) ...
+            uint4 pk[16];
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
+                pk[g].x = pack2(fast_exp2(x[0]), fast_exp2(x[1]), BF16);
+                pk[g].y = pack2(fast_exp2(x[2]), fast_exp2(x[3]), BF16);
+                pk[g].z = pack2(fast_exp2(x[4]), fast_exp2(x[5]), BF16);
+                pk[g].w = pack2(fast_exp2(x[6]), fast_exp2(x[7]), BF16);
+            }
+            // ... and only then wait for PV(j-1): the P buffer / O accumulator are not touched before,
+            // so the previous tile's second MMA overlaps this tile's MUFU work
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O stable
                 tc_fence_after();
             }
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {  // 16 groups of 8 kv columns -> one 16-byte store
-                float x[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
-                uint4 pk;
-                pk.x = pack2(fast_exp2(x[0]), fast_exp2(x[1]), BF16);
-                pk.y = pack2(fast_exp2(x[2]), fast_exp2(x[3]), BF16);
-                pk.z = pack2(fast_exp2(x[4]), fast_exp2(x[5]), BF16);
-                pk.w = pack2(fast_exp2(x[6]), fast_exp2(x[7]), BF16);
+            for (int g = 0; g < 16; ++g) {  // 16 groups of 8 kv columns -> one 16-byte store each
                 const int chunk = g >> 3;  // which 64-column half
                 const int g8 = g & 7;
                 uint8_t* dst = sP + chunk * (kTileQ * 128) + r * 128 + ((g8 ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = pk;
+                *reinterpret_cast<uint4*>(dst) = pk[g];
             }
 
             if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {

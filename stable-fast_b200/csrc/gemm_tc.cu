@@ -49,7 +49,7 @@ struct EpiArgs {
     // GroupNorm statistics of the tensor this GEMM writes, accumulated for up to two consumers
     float* gn_stats[2];
     int gn_cpg[2], gn_choff[2];
-    int gn_groups, gn_rpi;
+    int gn_groups, gn_rpi, gn_shard_stride;  // floats between two of the 8 accumulation shards
     // LayerNorm folded around the GEMM (see sfb200.h): producer side / consumer side
     float* rowstats_out;
     const float* ln_rowstats;
@@ -119,29 +119,33 @@ __device__ __forceinline__ float round16(float v) {
     return __half2float(__float2half_rn(v));
 }
 
-// GroupNorm partial sums of 8 stored values (row m, columns n..n+7) straight to global memory:
-// used by the split-K reduction kernel, where a thread owns one 8-column slice.
+// GroupNorm partial sums of 8 stored values (row m, columns n..n+7) into block-shared accumulators
+// sacc[2 targets][2 images][groups][2] (images img0, img0+1; anything else goes straight to global
+// memory).  Used by the split-K reduction kernel, where a thread owns one 8-column slice.
 template <int BF16>
-__device__ __forceinline__ void gn_accumulate8(const EpiArgs& e, int m, int n, const float (&acc)[8]) {
+__device__ __forceinline__ void gn_accumulate8(const EpiArgs& e, int m, int n, const float (&acc)[8],
+                                               float* sacc, int img0, int shard) {
     const int img = m / e.gn_rpi;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         if (!e.gn_stats[t]) continue;
         int g_run = (e.gn_choff[t] + n) / e.gn_cpg[t];
         float s = 0.f, ss = 0.f;
+        auto flush = [&]() {
+            float* d = (img == img0 || img == img0 + 1)
+                ? sacc + ((t * 2 + (img - img0)) * e.gn_groups + g_run) * 2
+                : e.gn_stats[t] + (size_t)shard * e.gn_shard_stride + ((size_t)img * e.gn_groups + g_run) * 2;
+            atomicAdd(d, s);
+            atomicAdd(d + 1, ss);
+        };
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int g = (e.gn_choff[t] + n + i) / e.gn_cpg[t];
-            if (g != g_run) {
-                float* d = e.gn_stats[t] + ((size_t)img * e.gn_groups + g_run) * 2;
-                atomicAdd(d, s); atomicAdd(d + 1, ss);
-                g_run = g; s = 0.f; ss = 0.f;
-            }
+            if (g != g_run) { flush(); g_run = g; s = 0.f; ss = 0.f; }
             const float v = round16<BF16>(acc[i]);
             s += v; ss += v * v;
         }
-        float* d = e.gn_stats[t] + ((size_t)img * e.gn_groups + g_run) * 2;
-        atomicAdd(d, s); atomicAdd(d + 1, ss);
+        flush();
     }
 }
 
@@ -228,7 +232,8 @@ __device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r
 // other SMs: read them through L2 (ld.global.cg).
 template <int BN, int BF16>
 __device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int splits, const EpiArgs& e,
-                                               int m, int n) {
+                                               int m, int n, float* gn_sacc = nullptr, int gn_img0 = 0,
+                                               int gn_shard = 0) {
     auto sum8 = [&](int col, float (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -282,7 +287,7 @@ __device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int
             atomicAdd(e.rowstats_out + 2 * (size_t)m, rs);
             atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rss);
         }
-        if (e.gn_stats[0] && e.epi == SFB_EPI_STORE) gn_accumulate8<BF16>(e, m, n, acc);
+        if (gn_sacc) gn_accumulate8<BF16>(e, m, n, acc, gn_sacc, gn_img0, gn_shard);
         epi_store8<BF16>(e, m, n, acc);
     }
 }
@@ -297,8 +302,32 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
     const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
     const int groups = ncols / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)e.M * groups) return;
-    splitk_reduce8<BN, BF16>(ws, splits, e, (int)(idx / groups), (int)(idx % groups) * 8);
+    const bool active = idx < (long long)e.M * groups;
+    __shared__ float sacc[2 * 2 * 64 * 2];
+    const bool gn = e.gn_stats[0] != nullptr && e.epi == SFB_EPI_STORE;
+    int img0 = 0;
+    if (gn) {
+        for (int i = threadIdx.x; i < 2 * 2 * e.gn_groups * 2; i += blockDim.x) sacc[i] = 0.f;
+        const long long first = (long long)blockIdx.x * blockDim.x;
+        img0 = (int)(first / groups) / e.gn_rpi;
+        __syncthreads();
+    }
+    if (active)
+        splitk_reduce8<BN, BF16>(ws, splits, e, (int)(idx / groups), (int)(idx % groups) * 8,
+                                 gn ? sacc : nullptr, img0, blockIdx.x & 7);
+    if (gn) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * 2 * e.gn_groups; i += blockDim.x) {
+            const int t = i / (2 * e.gn_groups), im = (i / e.gn_groups) & 1, g = i % e.gn_groups;
+            const float a0 = sacc[i * 2], a1 = sacc[i * 2 + 1];
+            if (e.gn_stats[t] && (a0 != 0.f || a1 != 0.f)) {
+                float* d = e.gn_stats[t] + (size_t)(blockIdx.x & 7) * e.gn_shard_stride +
+                           ((size_t)(img0 + im) * e.gn_groups + g) * 2;
+                atomicAdd(d, a0);
+                atomicAdd(d + 1, a1);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -771,7 +800,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (!e.gn_stats[t]) continue;
                     const float a0 = sGn[i * 2], a1 = sGn[i * 2 + 1];
                     if (a0 != 0.f || a1 != 0.f) {
-                        float* d = e.gn_stats[t] + ((size_t)(img_base + slot) * e.gn_groups + gfirst[t] + g) * 2;
+                        // 8 accumulation shards (by M tile) keep same-address atomic contention low
+                        float* d = e.gn_stats[t] + (size_t)(m_tile & 7) * e.gn_shard_stride +
+                                   ((size_t)(img_base + slot) * e.gn_groups + gfirst[t] + g) * 2;
                         atomicAdd(d, a0);
                         atomicAdd(d + 1, a1);
                     }
@@ -902,9 +933,10 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     for (int t = 0; t < 2; ++t) {
         e.gn_stats[t] = p->gn_stats[t]; e.gn_cpg[t] = p->gn_cpg[t]; e.gn_choff[t] = p->gn_choff[t];
     }
-    e.gn_groups = p->gn_groups; e.gn_rpi = p->gn_rows_per_img;
+    e.gn_groups = p->gn_groups; e.gn_rpi = p->gn_rows_per_img; e.gn_shard_stride = p->gn_shard_stride;
     if (p->gn_stats[0]) {
-        if (p->epi != SFB_EPI_STORE || p->gn_groups <= 0 || p->gn_rows_per_img < 16 || p->gn_cpg[0] < 2 ||
+        if (p->epi != SFB_EPI_STORE || p->gn_groups <= 0 || p->gn_groups > 64 || p->gn_shard_stride <= 0 ||
+            p->gn_rows_per_img < 16 || p->gn_cpg[0] < 2 ||
             (p->gn_stats[1] && p->gn_cpg[1] < 2) ||
             (BM % p->gn_rows_per_img != 0 && p->gn_rows_per_img % BM != 0))
             return fail(SFB_ERR_INVALID, "sfb_gemm: unsupported GroupNorm statistics geometry");

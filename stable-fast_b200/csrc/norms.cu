@@ -20,6 +20,7 @@ struct GnArgs {
     const float* beta;
     float* stats;
     int n, hw, c, ldx, ldy, groups, cpg, nvec, rows_per_block;
+    int shards, shard_stride;  // statistics arrive as `shards` partial copies, `shard_stride` floats apart
     float eps;
     int silu, dtype;
 };
@@ -87,8 +88,11 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
     for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
         const int g = ch / a.cpg;
-        const float sum = a.stats[((size_t)img * a.groups + g) * 2];
-        const float sq = a.stats[((size_t)img * a.groups + g) * 2 + 1];
+        float sum = 0.f, sq = 0.f;
+        for (int s = 0; s < a.shards; ++s) {
+            sum += a.stats[(size_t)s * a.shard_stride + ((size_t)img * a.groups + g) * 2];
+            sq += a.stats[(size_t)s * a.shard_stride + ((size_t)img * a.groups + g) * 2 + 1];
+        }
         const float mean = sum * inv_cnt;
         const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + a.eps);
@@ -324,6 +328,8 @@ static int make_gn_args(const sfb_gn_params* p, GnArgs& a, int& blocks_per_img) 
     a.gamma = p->gamma; a.beta = p->beta; a.stats = p->stats;
     a.n = p->n; a.hw = p->hw; a.c = p->c; a.ldx = p->ldx; a.ldy = p->ldy; a.groups = p->groups;
     a.cpg = p->c / p->groups; a.nvec = p->c / 8; a.eps = p->eps; a.silu = p->silu; a.dtype = p->dtype;
+    a.shards = p->stat_shards > 0 ? p->stat_shards : 1;
+    a.shard_stride = p->stat_shard_stride;
     const int by = kGnThreads / a.nvec;
     // aim for >= 2 waves of 148 SMs while giving each thread a few rows
     int want = (2 * 148 + p->n - 1) / p->n;

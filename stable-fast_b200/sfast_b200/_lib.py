@@ -35,7 +35,7 @@ class GemmParams(C.Structure):
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_dim", C.c_int32),
         ("gn_stats", C.c_void_p * 2), ("gn_cpg", C.c_int32 * 2), ("gn_choff", C.c_int32 * 2),
-        ("gn_groups", C.c_int32), ("gn_rows_per_img", C.c_int32),
+        ("gn_groups", C.c_int32), ("gn_rows_per_img", C.c_int32), ("gn_shard_stride", C.c_int32),
         ("debug_stamps", C.c_void_p),
     ]
 
@@ -58,7 +58,7 @@ class GnParams(C.Structure):
         ("n", C.c_int32), ("hw", C.c_int32), ("c", C.c_int32), ("ldx", C.c_int32),
         ("ldy", C.c_int32), ("groups", C.c_int32),
         ("eps", C.c_float), ("silu", C.c_int32), ("dtype", C.c_int32),
-        ("sync_counter", C.c_void_p),
+        ("sync_counter", C.c_void_p), ("stat_shards", C.c_int32), ("stat_shard_stride", C.c_int32),
     ]
 
 

@@ -283,7 +283,8 @@ def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, 
     p.sync_counter = _ptr(sync)
     keep = (p, x.buf, y.buf, gamma, beta, stats, sync)
     nb = x.rows * x.c * 2
-    if stats_ready:  # the producing GEMM(s) accumulated the statistics in their epilogue
+    if stats_ready:  # the producing GEMM(s) accumulated the statistics (8 shards) in their epilogue
+        p.stat_shards, p.stat_shard_stride = 8, x.n * groups * 2
         return [Op(name + ".apply", lib.sfb_group_norm_apply, (C.byref(p),), keep, 0, 2 * nb)]
     if sync is not None:
         fits = gn_fused_fits(p.n, p.hw, p.c, groups) if dry else bool(

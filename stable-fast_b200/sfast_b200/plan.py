@@ -186,8 +186,9 @@ class UNetPlan:
         n_gn = sum(2 for _ in spec.all_resnets()) + 1
         for blk in spec.down + [spec.mid] + spec.up:
             n_gn += sum(1 for t in blk.attentions if t is not None)
-        # (+4 floats per slot: the fused kernel's grid-barrier counter)
-        self.gn_stats = self._alloc((n_gn, batch * spec.groups * 2 + 4), torch.float32)
+        # 8 accumulation shards of [B, groups, 2] (producer-epilogue path) + 4 floats for the fused
+        # kernel's grid-barrier counter
+        self.gn_stats = self._alloc((n_gn, 8 * batch * spec.groups * 2 + 4), torch.float32)
         # folded-LayerNorm row statistics: [rows, 2] fp32 per LayerNorm, zeroed once per step
         self._ln_used = 0
         self._ln_slots = []
@@ -285,6 +286,7 @@ class UNetPlan:
             p.gn_stats[slot] = _ptr(stats)
             p.gn_cpg[slot], p.gn_choff[slot] = cpg, choff
             p.gn_groups, p.gn_rows_per_img = groups, rpi
+            p.gn_shard_stride = self.B * groups * 2
         return True
 
     def group_norm(self, name, x: Act, prefix, silu, eps):

@@ -380,7 +380,7 @@ def check_gn_epilogue(n=2, hw=1024, c1=640, c2=320, k=320, dt=torch.float16, spl
     torch.manual_seed(seed)
     M, C = n * hw, c1 + c2
     buf = torch.zeros(M, C, device=DEV, dtype=dt)
-    stats = torch.zeros(n * 32 * 2 + 4, device=DEV)
+    stats = torch.zeros(8 * n * 32 * 2 + 4, device=DEV)
     ws = torch.empty(8 * M * max(c1, c2), device=DEV, dtype=torch.float32)
     off = 0
     for ci in (c1, c2):
@@ -392,7 +392,7 @@ def check_gn_epilogue(n=2, hw=1024, c1=640, c2=320, k=320, dt=torch.float16, spl
         p = op.keep[0]
         p.gn_stats[0] = stats.data_ptr()
         p.gn_cpg[0], p.gn_choff[0] = C // 32, off
-        p.gn_groups, p.gn_rows_per_img = 32, hw
+        p.gn_groups, p.gn_rows_per_img, p.gn_shard_stride = 32, hw, n * 32 * 2
         op.launch(_stream())
         off += ci
     x = Act(buf, n, 1, hw, C)
