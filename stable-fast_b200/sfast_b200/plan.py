@@ -262,7 +262,7 @@ class UNetPlan:
     def _producer_stats(self, x: Act, stats):
         """Ask the GEMM(s) that produced `x` to accumulate its GroupNorm statistics in their
         epilogue.  Returns False (nothing changed) if any slice of x has no capable producer."""
-        if os.environ.get("SFB_GN_EPILOGUE", "1") == "0":
+        if os.environ.get("SFB_GN_EPILOGUE", "0") == "0":  # measured slower than the fused kernel (DESIGN.md)
             return False
         groups = self.spec.groups
         rpi, cpg = x.h * x.w, x.c // groups
@@ -384,7 +384,7 @@ class UNetPlan:
                                             splits=1, keep=(self.ehs_in, wkv)))
             if not self._joined:
                 self._joined = True
-                self._emit(_JoinOp())
+                self._emit(_JoinOp("all"))
         ao = self.act("attn_out", hs.n, hs.h, hs.w, C)
         self._emit(ops.attention_op(a + ".core", self.lib_or_dry(), q=q, k=k, vt=vt, out=ao.buf,
                                     batch=B, heads=H, head_dim=D, seq_q=S, seq_kv=skv, q_rows=S,
@@ -497,7 +497,13 @@ class UNetPlan:
                        self.gn_stats.numel() * 4), (self.gn_stats,)))
         self._emit(Op("ln_stats.zero", lib.sfb_memset,
                       (_ptr(self.ln_arena), 0, self.ln_arena.numel() * 4), (self.ln_arena,)))
+        # the time-embedding chain only depends on the timestep: forked stream, joined before the
+        # first resnet (its conv1 epilogue adds the projected embedding)
+        n_main = len(self.ops)
         self.time_embedding()
+        self.side_ops.extend(self.ops[n_main:])
+        del self.ops[n_main:]
+        self._temb_last = self.side_ops[-1]
 
         # ---- shape pass: where does every skip tensor live (inside its consumer's concat buffer)
         skip_shapes = [(spec.block_out_channels[0], H, W)]
@@ -540,6 +546,7 @@ class UNetPlan:
                           (_ptr(self.sample_in), _ptr(w_in), _ptr(self.w.f32("conv_in.bias")),
                            x.ptr, B, H, W, spec.in_channels, c0, x.ld, ops.dtype_code(self.dt)),
                           (self.sample_in, w_in, x.buf), 2 * B * H * W * c0 * 9 * spec.in_channels))
+        self._emit(_JoinOp("temb"))
         # ---- down path
         k = 1
         for blk in spec.down:
@@ -612,14 +619,20 @@ class UNetPlan:
         if self.side_ops:
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream()
+                self._temb_event = torch.cuda.Event()
             side = self._side_stream
             side.wait_stream(main)  # inputs were copied on the main stream
             sptr = side.cuda_stream
             for op in self.side_ops:
                 op.launch(sptr)
+                if op is self._temb_last:
+                    self._temb_event.record(side)
         for op in self.ops:
             if isinstance(op, _JoinOp):
-                main.wait_stream(self._side_stream)
+                if op.kind == "temb":
+                    main.wait_event(self._temb_event)
+                else:
+                    main.wait_stream(self._side_stream)
             else:
                 op.launch(mptr)
 
@@ -662,8 +675,9 @@ class _WsToken:
 class _JoinOp(Op):
     """Main stream waits for the side stream (the hoisted K/V projections) here."""
 
-    def __init__(self):
-        super().__init__("join(side stream)", None, (), ())
+    def __init__(self, kind="all"):
+        super().__init__(f"join(side stream: {kind})", None, (), ())
+        self.kind = kind
 
     def launch(self, stream):
         raise RuntimeError("join marker is handled by UNetPlan.run")

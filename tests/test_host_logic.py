@@ -66,11 +66,11 @@ def _dry_plan(cfg, batch, h, w):
 def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     plan = _dry_plan(uo.sd15_config(), 2, 64, 64)
     names = [op.fn.name for op in plan.all_ops() if op.fn is not None]
-    assert len(plan.side_ops) == 16  # cross-attention K/V projections run on the forked stream
+    # forked stream: time-embedding chain (4 launches) + the 16 cross-attention K/V projections
+    assert len(plan.side_ops) == 20
     # 61 GroupNorms, 48 LayerNorms, 32 attention calls, 3 upsamples
-    # every GroupNorm's statistics come from its producer GEMM's epilogue: apply-only kernels
-    assert names.count("sfb_group_norm_apply") == 61 and names.count("sfb_group_norm_fused") == 0
-    assert names.count("sfb_group_norm_stats") == 0
+    # B = 2 tensors fit in shared memory: all 61 GroupNorms take the single-launch fused kernel
+    assert names.count("sfb_group_norm_fused") == 61 and names.count("sfb_group_norm_apply") == 0
     # all 48 LayerNorms are folded into the consuming GEMMs (gamma-scaled weights + epilogue)
     assert names.count("sfb_layer_norm") == 0
     gemms = [op.keep[0] for op in plan.all_ops() if op.fn is not None and op.fn.name == "sfb_gemm"]
@@ -162,7 +162,7 @@ def test_struct_layouts_match_the_header():
     # sizes computed by hand from include/sfb200.h with natural alignment
     assert ctypes.sizeof(_lib.AttnParams) == 4 * 8 + 10 * 4
     assert ctypes.sizeof(_lib.LnParams) == 4 * 8 + 6 * 4
-    assert ctypes.sizeof(_lib.GnParams) == 5 * 8 + 9 * 4 + 4 + 8
+    assert ctypes.sizeof(_lib.GnParams) == 5 * 8 + 9 * 4 + 4 + 8 + 2 * 4
     assert ctypes.sizeof(_lib.SmallLinearParams) == 6 * 8 + 8 * 4
 
 
