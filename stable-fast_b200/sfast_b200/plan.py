@@ -692,7 +692,8 @@ class _CopyOp(Op):
 
     def launch(self, stream):
         B = self.plan.B
-        self.plan.add_in[:, self.n_text:].copy_(self.tid.view(B, -1))
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):  # may be the side stream
+            self.plan.add_in[:, self.n_text:].copy_(self.tid.view(B, -1))
 
 
 class _DryFn:
