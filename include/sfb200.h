@@ -101,6 +101,11 @@ typedef struct sfb_gemm_params {
     int32_t splits;
     float* ws;
     void* split_sync;
+    /* 1: the `splits` CTAs of one output tile form a thread-block cluster along grid.z and sum
+     * their fp32 partial tiles through distributed shared memory; CTA s finishes rows
+     * [s*128/splits, ...) of the tile.  No workspace, no second kernel.  Needs
+     * splits * (cta_pair ? 2 : 1) <= 16 (> 8 is a non-portable cluster size) and no gn_stats. */
+    int32_t cluster_k;
     /* epilogue */
     int32_t epi;
     void* out;

@@ -2,11 +2,11 @@
 //
 //   D[M, N] = A[M, K] * W[N, K]^T   (fp16/bf16 operands, fp32 accumulation in TMEM)
 //
-// One 128 x 160 output tile per CTA.  Warp roles (192 threads):
+// One 128 x 160 output tile per CTA.  Warp roles (64 + 32 * kEpiWarps threads):
 //   warp 0      TMA producer: A tile (128 rows x 64 K) + W tile (160 rows x 64 K) per stage,
 //               both landing in 128-byte-swizzled K-major shared memory;
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per stage);
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (thread = row), fuse bias / time-embedding
+//   warps 2..   epilogue: tcgen05.ld the accumulator (thread = row), fuse bias / time-embedding
 //               row bias / residual / GEGLU / QKV head scatter, store 16-byte vectors.
 // For the convolution the A tile of filter tap (kh, kw) is a *shifted NHWC box*: the tile's
 // 128 output pixels are a [box_n, box_h, W] block, so one 4-D TMA box load at
@@ -27,7 +27,19 @@ namespace sfb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
+// epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, each converting half of the
+// tile's columns -- the epilogue is latency-bound with a single warp per SM sub-partition)
+#ifndef SFB_EPI_WARPS
+#define SFB_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = SFB_EPI_WARPS;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kColSplit = kEpiWarps / 4;
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps");
+constexpr int kGemmThreads = 64 + kEpiThreads;
+__device__ __forceinline__ void epi_bar() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+}
 
 struct EpiArgs {
     int epi;
@@ -75,6 +87,9 @@ struct GemmArgs {
     int pdl;        // launched with programmatic stream serialization
     long long* dbg; // optional: per-CTA %globaltimer stamps (8 per CTA) for latency breakdowns
     int* split_sync; // [tiles][2] arrive / done counters of the fused split-K reduction (or null)
+    // cluster split-K: the `splits` CTAs of one output tile form a cluster along grid.z and sum their
+    // fp32 partial tiles through distributed shared memory (no workspace, no second kernel)
+    int cluster_k;
     float* ws;
     // conv geometry
     int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
@@ -230,21 +245,11 @@ __device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r
 // Sum the `splits` fp32 partials of 8 output columns of row m and run the fused epilogue on them.
 // `n` is the output column (GEGLU: output column of the gated product).  Partials were written by
 // other SMs: read them through L2 (ld.global.cg).
-template <int BN, int BF16>
-__device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int splits, const EpiArgs& e,
-                                               int m, int n, float* gn_sacc = nullptr, int gn_img0 = 0,
-                                               int gn_shard = 0) {
-    auto sum8 = [&](int col, float (&acc)[8]) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int s = 0; s < splits; ++s) {
-            const float* p = ws + ((size_t)s * e.M + m) * e.N + col;
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(p + 4));
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-        }
-    };
+// `sum8(col, acc)` yields the summed partials of global columns [col, col+8) of row m.
+template <int BN, int BF16, typename Sum8>
+__device__ __forceinline__ void reduce_epilogue8(Sum8&& sum8, const EpiArgs& e, int m, int n,
+                                                 float* gn_sacc = nullptr, int gn_img0 = 0,
+                                                 int gn_shard = 0) {
     if (e.epi == SFB_EPI_GEGLU) {
         const int tile = n / (BN / 2);
         const int nv = tile * BN + (n - tile * (BN / 2));
@@ -290,6 +295,24 @@ __device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int
         if (gn_sacc) gn_accumulate8<BF16>(e, m, n, acc, gn_sacc, gn_img0, gn_shard);
         epi_store8<BF16>(e, m, n, acc);
     }
+}
+
+template <int BN, int BF16>
+__device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int splits, const EpiArgs& e,
+                                               int m, int n, float* gn_sacc = nullptr, int gn_img0 = 0,
+                                               int gn_shard = 0) {
+    auto sum8 = [&](int col, float (&acc)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int s = 0; s < splits; ++s) {
+            const float* p = ws + ((size_t)s * e.M + m) * e.N + col;
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(p + 4));
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+    };
+    reduce_epilogue8<BN, BF16>(sum8, e, m, n, gn_sacc, gn_img0, gn_shard);
 }
 
 // Stand-alone reduction kernel: fallback when the split CTAs of a tile cannot all be co-resident
@@ -401,9 +424,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    const bool clustered = (CG == 2) || args.cx * args.cy > 1;
-    const int cix = (clustered && CG == 1) ? (int)cluster_ctaid_x() : 0;
-    const int ciy = clustered ? (CG == 2 ? (int)cluster_ctaid_x() : (int)cluster_ctaid_y()) : 0;
+    const bool mcast = (CG == 1) && args.cx * args.cy > 1;
+    const bool clustered = (CG == 2) || mcast || args.cluster_k;
+    // pair mode inside a larger (split-K) cluster: the pair is ranks (2j, 2j+1)
+    const uint16_t pair_mask = (uint16_t)(0b11u << (clustered ? (cluster_ctarank() & ~1u) : 0u));
+    const int cix = mcast ? (int)cluster_ctaid_x() : 0;
+    const int ciy = CG == 2 ? (int)cluster_ctaid_x() : (mcast ? (int)cluster_ctaid_y() : 0);
     const bool leader = (CG == 1) || ciy == 0;  // pair mode: the even CTA issues every MMA
     // CTAs sharing this CTA's A tile (same M-tile: all cix) / weight tile (same N-tile: all ciy)
     const uint16_t mask_a = (uint16_t)(((1u << args.cx) - 1u) << (ciy * args.cx));
@@ -509,11 +535,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
                                     (i | k) != 0);
                 }
-                if (CG == 2) umma_commit_pair(&empty_bar[stage], 0b11);
-                else if (clustered) umma_commit_mc(&empty_bar[stage], (uint16_t)(mask_a | mask_b));
+                if (CG == 2) umma_commit_pair(&empty_bar[stage], pair_mask);
+                else if (mcast) umma_commit_mc(&empty_bar[stage], (uint16_t)(mask_a | mask_b));
                 else umma_commit(&empty_bar[stage]);
             }
-            if (CG == 2) umma_commit_pair(tmem_full_bar, 0b11);
+            if (CG == 2) umma_commit_pair(tmem_full_bar, pair_mask);
             else umma_commit(tmem_full_bar);
             if (dbg) dbg[4] = globaltimer_ns();
         }
@@ -522,7 +548,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         pdl_wait();
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
-        const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 64;  // index among the epilogue threads
+        const int chalf = (warp - 2) >> 2;  // which part of the tile's columns this warp converts
         int m;
         const bool valid = tile_row_to_m(args, m_tile, r, m);
         sRowM[r] = valid ? m : -1;
@@ -537,7 +564,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 nslots = args.box_n;
                 img0 = (args.box_n == 1) ? (m_tile / args.tiles_per_img) : m_tile * args.box_n;
             }
-            for (int i = et; i < nslots * BN; i += 128) {
+            for (int i = et; i < nslots * BN; i += kEpiThreads) {
                 const int slot = i / BN, c = i - slot * BN;
                 const int n = n_tile * BN + c;
                 float v = 0.f;
@@ -549,13 +576,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 sBias[i] = v;
             }
             if (e.ln_rowstats) {  // slot 1: column sums of the gamma-scaled weight
-                for (int c = et; c < BN; c += 128) {
+                for (int c = et; c < BN; c += kEpiThreads) {
                     const int n = n_tile * BN + c;
                     sBias[BN + c] = (n < e.N) ? e.ln_colsum[n] : 0.f;
                 }
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi_bar();
         // ---- epilogue.  Phase A: thread = accumulator row (warp w may only touch TMEM lanes
         // [32*(w%4), +32)): TMEM -> registers -> (+bias / LayerNorm fold) -> fp32 staging tile in the
         // now-idle pipeline buffers.  Phase B: threads re-partition the tile so that every global
@@ -565,6 +592,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int ncol0 = n_tile * BN;
         const bool partial = args.splits > 1;
         constexpr int kGroups = BN / 8;  // 16-byte output slices per row
+        constexpr int kItems = BM * kGroups / kEpiThreads;  // slices per epilogue thread
         // Residual in the coalesced phase-B ownership (thread <-> 16-byte slice), software-pipelined
         // in batches of 5 slices; the first batch is issued before the accumulator is even ready.
         // (Loops here are deliberately ROLLED: the epilogue runs once per CTA, so straight-line
@@ -572,7 +600,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE) && !partial;
         constexpr int kBatch = 5;
         auto item_addr = [&](int it, int& row, int& grp, int& mm, int& n) {
-            const int idx = et + it * 128;
+            const int idx = et + it * kEpiThreads;
             row = idx / kGroups;
             grp = idx - row * kGroups;
             mm = sRowM[row];
@@ -605,14 +633,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (dbg && threadIdx.x == 64) dbg[5] = globaltimer_ns();
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float* srow = sStage + r * L::kStagePitch;
+        constexpr int kColsPer = BN / kColSplit;             // columns converted per thread
+        constexpr int kChunk = kColSplit == 1 ? 32 : 16;     // columns per TMEM load
 #pragma unroll 1
-        for (int cb = 0; cb < BN / 32; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(trow + cb * 32, v);
+        for (int cb = 0; cb < kColsPer / kChunk; ++cb) {
+            uint32_t v[kChunk];
+            const int c0 = chalf * kColsPer + cb * kChunk;
+            if constexpr (kChunk == 32) tmem_ld32(trow + c0, v);
+            else tmem_ld16(trow + c0, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int cl = cb * 32 + j * 8;  // column inside the tile
+            for (int j = 0; j < kChunk / 8; ++j) {
+                const int cl = c0 + j * 8;  // column inside the tile
                 float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -628,7 +660,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 *reinterpret_cast<float4*>(srow + cl + 4) = make_float4(f[4], f[5], f[6], f[7]);
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi_bar();
 
         // ---- phase B
         auto load8 = [&](int row, int col, float (&f)[8]) {
@@ -636,10 +668,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const float4 b = *reinterpret_cast<const float4*>(sStage + row * L::kStagePitch + col + 4);
             f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
         };
-        if (partial) {
+        if (partial && args.cluster_k) {
+            // the reduction happens after the cluster barrier below (all warps take part in it)
+        } else if (partial) {
 #pragma unroll 1
-            for (int it = 0; it < kGroups; ++it) {
-                const int idx = et + it * 128;
+            for (int it = 0; it < kItems; ++it) {
+                const int idx = et + it * kEpiThreads;
                 const int row = idx / kGroups, grp = idx - row * kGroups;
                 const int mm = sRowM[row], n = ncol0 + grp * 8;
                 if (mm >= 0 && n < e.N) {
@@ -656,7 +690,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 // barrier, then each reduces + finishes its own slice of the tile's rows.
                 int* cnt = args.split_sync + 2 * (m_tile * n_tiles_grid + n_tile);
                 __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                epi_bar();
                 if (et == 0) {
                     atomicAdd(cnt, 1);
                     const long long t0 = clock64();
@@ -665,20 +699,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                     __threadfence();
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                epi_bar();
                 const int rows_per = (BM + args.splits - 1) / args.splits;
                 const int r0 = split * rows_per;
                 const int nrows = max(0, min(rows_per, BM - r0));
                 const bool geglu = e.epi == SFB_EPI_GEGLU;
                 const int gpr = geglu ? kGroups / 2 : kGroups;  // items per row
-                for (int idx = et; idx < nrows * gpr; idx += 128) {
+                for (int idx = et; idx < nrows * gpr; idx += kEpiThreads) {
                     const int row = r0 + idx / gpr, grp = idx % gpr;
                     const int mm = sRowM[row];
                     const int n = (geglu ? n_tile * (BN / 2) : ncol0) + grp * 8;
                     if (mm >= 0 && n < (geglu ? e.geglu_n_out : e.N))
                         splitk_reduce8<BN, BF16>(args.ws, args.splits, e, mm, n);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                epi_bar();
                 if (et == 0) {
                     if (atomicAdd(cnt + 1, 1) == args.splits - 1) {  // last finisher re-arms the counters
                         cnt[0] = 0;
@@ -689,8 +723,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         } else if (e.epi == SFB_EPI_GEGLU) {
 #pragma unroll 1
-            for (int it = 0; it < kGroups / 2; ++it) {
-                const int idx = et + it * 128;
+            for (int it = 0; it < kItems / 2; ++it) {
+                const int idx = et + it * kEpiThreads;
                 const int row = idx / (kGroups / 2), og = idx - row * (kGroups / 2);
                 const int mm = sRowM[row], nout = n_tile * (BN / 2) + og * 8;
                 if (mm >= 0 && nout < e.geglu_n_out) {
@@ -703,8 +737,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         } else {
             if (e.epi == SFB_EPI_STORE) {
 #pragma unroll 1
-                for (int b = 0; b < kGroups / kBatch; ++b) {
-                    if (has_res && b + 1 < kGroups / kBatch) {
+                for (int b = 0; b < kItems / kBatch; ++b) {
+                    if (has_res && b + 1 < kItems / kBatch) {
 #pragma unroll
                         for (int j = 0; j < kBatch; ++j) rnxt[j] = load_res((b + 1) * kBatch + j);
                     }
@@ -735,8 +769,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const int n_last = min(ncol0 + BN, e.N) - 1;
                 const bool row_fastest = (ncol0 / C + e.which_base == 2) && (n_last / C + e.which_base == 2);
 #pragma unroll 1
-                for (int it = 0; it < kGroups; ++it) {
-                    const int idx = et + it * 128;
+                for (int it = 0; it < kItems; ++it) {
+                    const int idx = et + it * kEpiThreads;
                     int row, grp;
                     if (row_fastest) { grp = idx >> 7; row = idx & 127; }
                     else { row = idx / kGroups; grp = idx - row * kGroups; }
@@ -756,14 +790,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 int* sRowImg = reinterpret_cast<int*>(smem + BM * L::kStagePitch * 4);
                 float* sGn = reinterpret_cast<float*>(sRowImg + BM);  // [2][kMaxImg][kMaxGrp][2]
                 sRowImg[r] = valid ? m / e.gn_rpi : -1;
-                for (int i = et; i < 2 * kMaxImg * kMaxGrp * 2; i += 128) sGn[i] = 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = et; i < 2 * kMaxImg * kMaxGrp * 2; i += kEpiThreads) sGn[i] = 0.f;
+                epi_bar();
                 const int img_base = sRowImg[0];
                 int gfirst[2] = {0, 0};
 #pragma unroll
                 for (int t = 0; t < 2; ++t)
                     if (e.gn_stats[t]) gfirst[t] = (e.gn_choff[t] + ncol0) / e.gn_cpg[t];
-                for (int c = et; c < BN; c += 128) {
+                for (int c = et; c < BN; c += kEpiThreads) {
                     const int n = ncol0 + c;
                     if (n >= e.N) continue;
                     int gl[2] = {0, 0};
@@ -793,8 +827,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                     flush();
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = et; i < 2 * kMaxImg * kMaxGrp; i += 128) {
+                epi_bar();
+                for (int i = et; i < 2 * kMaxImg * kMaxGrp; i += kEpiThreads) {
                     const int t = i / (kMaxImg * kMaxGrp);
                     const int slot = (i / kMaxGrp) % kMaxImg, g = i % kMaxGrp;
                     if (!e.gn_stats[t]) continue;
@@ -809,10 +843,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             }
             if (e.rowstats_out) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                epi_bar();
                 if (valid) {
                     float rs_sum = 0.f, rs_sq = 0.f;
-                    for (int g = 0; g < kGroups; ++g) {
+                    for (int g = chalf * (kGroups / kColSplit); g < (chalf + 1) * (kGroups / kColSplit); ++g) {
                         if (ncol0 + g * 8 < e.N) {
                             float f[8];
                             load8(r, g * 8, f);
@@ -826,9 +860,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     }
 
+    if (args.cluster_k) {
+        // ---- cluster split-K: every CTA's fp32 partial tile now sits in its own shared memory.
+        // CTA `split` reduces rows [split * rows_per, +rows_per) of the tile over all peers' tiles
+        // (distributed shared memory) and runs the fused epilogue on them.
+        cluster_sync_all();
+        if (warp >= 2) {
+            const EpiArgs& e = args.e;
+            const int et = threadIdx.x - 64;
+            constexpr int kGroups = BN / 8;
+            const int rows_per = (BM + args.splits - 1) / args.splits;
+            const int r0 = split * rows_per;
+            const int nrows = max(0, min(rows_per, BM - r0));
+            const bool geglu = e.epi == SFB_EPI_GEGLU;
+            const int gpr = geglu ? kGroups / 2 : kGroups;  // items per row
+            const int ncol0 = n_tile * BN;
+            // peers: same position inside the pair (CG == 2: rank bit 0), every split
+            const uint32_t my_rank = cluster_ctarank();
+            const uint32_t rank0 = CG == 2 ? (my_rank & 1u) : 0u;
+            const uint32_t stage_u32 = smem_u32(sStage);
+#pragma unroll 1
+            for (int idx = et; idx < nrows * gpr; idx += kEpiThreads) {
+                const int row = r0 + idx / gpr, grp = idx % gpr;
+                const int mm = sRowM[row];
+                const int n = (geglu ? n_tile * (BN / 2) : ncol0) + grp * 8;
+                if (mm < 0 || n >= (geglu ? e.geglu_n_out : e.N)) continue;
+                auto sum8 = [&](int col, float (&acc)[8]) {
+                    const uint32_t off = stage_u32 + (uint32_t)(row * L::kStagePitch + (col - ncol0)) * 4u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+                    for (int s = 0; s < args.splits; ++s) {
+                        const uint32_t pa = dsmem_map(off, rank0 + (uint32_t)(s * CG));
+                        const float4 a = dsmem_ld_f4(pa);
+                        const float4 b = dsmem_ld_f4(pa + 16);
+                        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+                        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+                    }
+                };
+                reduce_epilogue8<BN, BF16>(sum8, e, mm, n);
+            }
+        }
+    }
     if (dbg && threadIdx.x == 64) dbg[6] = globaltimer_ns();
     tc_fence_before();
-    // no CTA may exit while cluster peers can still signal its barriers
+    // no CTA may exit while cluster peers can still signal its barriers / read its shared memory
     if (clustered) cluster_sync_all();
     else __syncthreads();
     if (warp == 1) {
@@ -854,8 +930,18 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
         if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
         attr_set = true;
     }
+    const int cz = a.cluster_k ? a.splits : 1;
+    if (cz * CG > 8) {
+        static bool np_set = false;
+        if (!np_set) {
+            cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, BF16, CG>,
+                                                   cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: non-portable cluster attribute: %s", cudaGetErrorString(err));
+            np_set = true;
+        }
+    }
     cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<BN, STAGES, BF16, CG>, grid, dim3(kGemmThreads),
-                                         CG == 2 ? dim3(2, 1, 1) : dim3(a.cx, a.cy, 1), L::kTotal, stream,
+                                         CG == 2 ? dim3(2, 1, cz) : dim3(a.cx, a.cy, cz), L::kTotal, stream,
                                          ta, tb, a);
     if (err != cudaSuccess) {
         // diagnostics: can the requested cluster be scheduled at all?
@@ -863,7 +949,7 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
         cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CG == 2 ? 2 : a.cx; at[0].val.clusterDim.y = CG == 2 ? 1 : a.cy; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = CG == 2 ? 2 : a.cx; at[0].val.clusterDim.y = CG == 2 ? 1 : a.cy; at[0].val.clusterDim.z = cz;
         cfg.attrs = at; cfg.numAttrs = 1;
         int max_clusters = -1;
         cudaError_t e2 = cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tc_kernel<BN, STAGES, BF16, CG>, &cfg);
@@ -898,7 +984,10 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     a.dbg = reinterpret_cast<long long*>(p->debug_stamps);
     a.split_sync = nullptr;
     if (a.splits > a.nkb_total) return fail(SFB_ERR_INVALID, "sfb_gemm: splits > K blocks");
-    if (a.splits > 1 && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
+    a.cluster_k = (p->cluster_k && a.splits > 1) ? 1 : 0;
+    if (a.cluster_k && (a.splits * (p->cta_pair ? 2 : 1) > 16 || p->gn_stats[0] || p->cluster_n > 1 || p->cluster_m > 1))
+        return fail(SFB_ERR_INVALID, "sfb_gemm: cluster_k needs splits * pair <= 16, no gn_stats, no multicast cluster");
+    if (a.splits > 1 && !a.cluster_k && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
     a.ws = p->ws;
     int m_tiles;
     if (p->a_mode == SFB_A_CONV3X3) {
@@ -978,7 +1067,7 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     // <= one CTA per SM anyway: take the deep 6-stage pipeline; otherwise 3 stages x 2 CTAs/SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     // fused split-K reduction needs every CTA of the launch resident at once (counter barrier)
-    if (a.splits > 1 && p->split_sync && ctas <= 148) a.split_sync = reinterpret_cast<int*>(p->split_sync);
+    if (a.splits > 1 && !a.cluster_k && p->split_sync && ctas <= 148) a.split_sync = reinterpret_cast<int*>(p->split_sync);
     static const int force_stages = [] { const char* v = getenv("SFB_GEMM_STAGES"); return v ? atoi(v) : 0; }();
     const bool deep = a.split_sync ? true : (force_stages ? (force_stages == 6) : (ctas <= 148));
     int rc;
@@ -992,7 +1081,7 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
         rc = deep ? launch_gemm<BN, 6, 1>(ta, tb, a, grid, stream) : launch_gemm<BN, 3, 1>(ta, tb, a, grid, stream);
     }
     if (rc) return rc;
-    if (a.splits > 1 && !a.split_sync) {
+    if (a.splits > 1 && !a.split_sync && !a.cluster_k) {
         const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
         const long long items = (long long)e.M * (ncols / 8);
         const int blocks = (int)((items + 255) / 256);

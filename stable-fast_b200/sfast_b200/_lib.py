@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsfb200.so")
+# SFB_LIB_PATH: A/B builds of the same ABI (experiments only; still no fallback)
+LIB_PATH = os.environ.get("SFB_LIB_PATH") or os.path.join(_HERE, "libsfb200.so")
 
 SFB_F16, SFB_BF16 = 0, 1
 A_MATRIX, A_CONV3X3 = 0, 1
@@ -22,6 +23,7 @@ class GemmParams(C.Structure):
         ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32), ("cin", C.c_int32),
         ("conv_stride", C.c_int32), ("box_h", C.c_int32), ("box_n", C.c_int32),
         ("splits", C.c_int32), ("ws", C.c_void_p), ("split_sync", C.c_void_p),
+        ("cluster_k", C.c_int32),
         ("epi", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int32),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p),
         ("rows_per_img", C.c_int32), ("ld_rowbias", C.c_int32),

@@ -123,6 +123,12 @@ ENABLE_CLUSTER = os.environ.get("SFB_CLUSTER", "0") != "0"  # measured slower on
 
 ENABLE_CTA_PAIR = os.environ.get("SFB_CTA_PAIR", "1") != "0"
 
+# split-K partial tiles summed through distributed shared memory inside a thread-block cluster
+# along grid.z (no fp32 workspace round trip, no reduction kernel); cluster sizes > 8 are
+# "non-portable" (one cluster of 16 per GPC on B200)
+ENABLE_CLUSTER_K = os.environ.get("SFB_CLUSTER_K", "1") != "0"
+CLUSTER_K_MAX = int(os.environ.get("SFB_CLUSTER_K_MAX", "16"))
+
 
 def choose_cluster(m_tiles, n_tiles):
     """(cluster_n, cluster_m): CTAs sharing an A tile (along N, <= 2) / a weight tile (along M, <= 4).
@@ -166,7 +172,7 @@ def _a_map(a, cn, dry):
 def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, out=None, ldo=0,
             bias=None, rowbias=None, rows_per_img=1, ld_rowbias=0, residual=None, ldr=0,
             epi=EPI_STORE, geglu_n_out=0, conv=None, qkv=None, ws=None, splits=None, keep=(),
-            rowstats_out=None, ln=None, dry=False, split_sync=None, cta_pair=None):
+            rowstats_out=None, ln=None, dry=False, split_sync=None, cta_pair=None, cluster_k=None):
     """Either pass ready-made maps (`a_map`, `b_map`: no cluster) or operand descriptors
     (`a` from a_matrix()/a_conv(), `b` a Mat), in which case a thread-block cluster with TMA
     multicast is chosen from the tile grid."""
@@ -209,8 +215,13 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         splits = choose_splits(m_tiles, n_tiles, nkb)
     if ws is None:
         splits = 1
+    if cluster_k is None:
+        cluster_k = ENABLE_CLUSTER_K
+    if splits > 1 and cluster_k and not (p.cluster_n > 1 or p.cluster_m > 1):
+        splits = min(splits, max(1, CLUSTER_K_MAX // (2 if p.cta_pair else 1)))
+        p.cluster_k = 1 if splits > 1 else 0
     p.splits = splits
-    if splits > 1:
+    if splits > 1 and not p.cluster_k:
         need = splits * M * N
         if ws.numel() < need:
             raise ValueError(f"{name}: split-K workspace too small ({ws.numel()} < {need})")

@@ -250,6 +250,8 @@ class UNetPlan:
         kw.setdefault("ws", self._ws_token)
         if os.environ.get("SFB_FUSED_SPLITK", "0") != "0":  # measured slower than the reduce kernel
             kw.setdefault("split_sync", self.split_sync)
+        if os.environ.get("SFB_GN_EPILOGUE", "0") != "0":
+            kw.setdefault("cluster_k", False)  # GroupNorm statistics live in the reduction kernel
         op = ops.gemm_op(name, self.lib_or_dry(), dry=self.dry, **kw)
         return op
 
@@ -659,16 +661,16 @@ class _WsToken:
         need = 0
         gemm = plan.lib_or_dry().sfb_gemm
         for op in plan.ops:
-            if op.fn is gemm and op.keep[0].splits > 1:
+            if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
                 need = max(need, op.keep[0].splits * op.keep[0].M * op.keep[0].N)
         plan.ws = plan._alloc((max(need, 1),), torch.float32)
         for op in plan.ops:
-            if op.fn is gemm and op.keep[0].splits > 1:
+            if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
                 op.keep[0].ws = _ptr(plan.ws)
         # side-stream GEMMs run concurrently with the main chain: they must not share the
         # split-K workspace, so they are never split
         for op in plan.side_ops:
-            if op.fn is gemm and op.keep[0].splits > 1:
+            if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
                 raise AssertionError("side-stream GEMM must not use split-K")
 
 

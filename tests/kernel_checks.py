@@ -43,7 +43,7 @@ def _rand(*shape, dt=torch.float16, scale=1.0, seed=None):
 
 # ------------------------------------------------------------------------------------------
 def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, residual=True, seed=0,
-               fused_reduce=True, pair=None):
+               fused_reduce=True, pair=None, cluster_k=False):
     lib = _lib.lib()
     a = _rand(M, K, dt=dt, seed=seed)
     w = _rand(N, K, dt=dt, scale=1 / math.sqrt(K))
@@ -54,9 +54,11 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     sync = torch.zeros(2048, device=DEV, dtype=torch.int32) if fused_reduce else None
     op = ops.gemm_op("gemm", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=ops.Mat(w), M=M, N=N, K=K,
                      dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits,
-                     split_sync=sync, cta_pair=pair)
+                     split_sync=sync, cta_pair=pair, cluster_k=cluster_k)
+    if cluster_k:
+        assert op.keep[0].cluster_k == 1 and op.keep[0].splits == splits, (op.keep[0].cluster_k, op.keep[0].splits)
     op.launch(_stream())
-    if fused_reduce and splits > 1:  # counters must re-arm themselves: run it twice
+    if fused_reduce and splits > 1 and not cluster_k:  # counters must re-arm themselves: run it twice
         out.zero_()
         op.launch(_stream())
         torch.cuda.synchronize()
@@ -70,7 +72,7 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     return rel_err(out, ref)
 
 
-def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1):
+def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1, cluster_k=False):
     lib = _lib.lib()
     x = _rand(M, K, dt=dt, seed=seed)
     w = _rand(2 * inner, K, dt=dt, scale=1 / math.sqrt(K))
@@ -82,7 +84,8 @@ def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1):
     op = ops.gemm_op("geglu", lib, a=ops.a_matrix(x.data_ptr(), M, K, K), b=ops.Mat(wp), M=M, N=Np, K=K,
                      dt=dt,
                      out=out, ldo=inner, bias=bp, epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws,
-                     splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32))
+                     splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32),
+                     cluster_k=cluster_k)
     op.launch(_stream())
     torch.cuda.synchronize()
     # reference semantics: h * gelu(gate), hidden first (sfast passes/__init__.py:643-648)
@@ -92,7 +95,7 @@ def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1):
 
 
 def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, splits=None,
-               rowbias=True, residual=True, pitch_extra=0, seed=2, pair=None):
+               rowbias=True, residual=True, pitch_extra=0, seed=2, pair=None, cluster_k=False):
     lib = _lib.lib()
     torch.manual_seed(seed)
     ld = cin + pitch_extra
@@ -113,7 +116,7 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
                      M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb,
                      rows_per_img=ho * wo, ld_rowbias=cout, residual=r, ldr=cout, ws=ws,
                      splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32),
-                     cta_pair=pair,
+                     cta_pair=pair, cluster_k=cluster_k,
                      conv=dict(n=n, h=ho, w=wo, cin=cin, stride=stride, box_n=box_n, box_h=box_h))
     op.launch(_stream())
     torch.cuda.synchronize()
@@ -323,7 +326,8 @@ def check_upsample(n=2, h=16, w=16, c=1280, dt=torch.float16):
 
 
 
-def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=1, splits_c=1, seed=12):
+def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=1, splits_c=1, seed=12,
+                  cluster_k=False):
     """LayerNorm folded around two GEMMs: the producer accumulates per-row (sum, sum of squares)
     in its epilogue, the consumer runs on the RAW activation with gamma-scaled weights and
     corrects with mean / rstd in its epilogue.  Reference: F.layer_norm then the linear / GEGLU."""
@@ -338,7 +342,7 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
     sync = torch.zeros(2048, device=DEV, dtype=torch.int32)
     ops.gemm_op("producer", lib, a=ops.a_matrix(a.data_ptr(), M, C, C), b=ops.Mat(w0),
                 M=M, N=C, K=C, dt=dt, out=x, ldo=C, residual=res, ldr=C, ws=ws, splits=splits_p,
-                split_sync=sync, rowstats_out=stats).launch(_stream())
+                split_sync=sync, rowstats_out=stats, cluster_k=cluster_k).launch(_stream())
     gamma = torch.randn(C, device=DEV) * 0.5 + 1.0
     beta = torch.randn(C, device=DEV) * 0.3
     if mode == "geglu":
@@ -351,7 +355,7 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         ops.gemm_op("consumer", lib, a=ops.a_matrix(x.data_ptr(), M, C, C),
                     b=ops.Mat(wt), M=M, N=wt.shape[0], K=C, dt=dt, out=out, ldo=inner, bias=bp,
                     epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws, splits=splits_c, split_sync=sync,
-                    ln=dict(rowstats=stats, colsum=cs, eps=1e-5, dim=C)).launch(_stream())
+                    cluster_k=cluster_k, ln=dict(rowstats=stats, colsum=cs, eps=1e-5, dim=C)).launch(_stream())
     else:
         w = _rand(N, C, dt=dt, scale=1 / math.sqrt(C))
         b = torch.randn(N, device=DEV) * 0.1
@@ -359,7 +363,7 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         out = torch.zeros(M, N, device=DEV, dtype=dt)
         ops.gemm_op("consumer", lib, a=ops.a_matrix(x.data_ptr(), M, C, C),
                     b=ops.Mat(wp.contiguous()), M=M, N=N, K=C, dt=dt, out=out, ldo=N, bias=bias,
-                    ws=ws, splits=splits_c, split_sync=sync,
+                    ws=ws, splits=splits_c, split_sync=sync, cluster_k=cluster_k,
                     ln=dict(rowstats=stats, colsum=colsum, eps=1e-5, dim=C)).launch(_stream())
     torch.cuda.synchronize()
     xr = (a.float() @ w0.float().t() + res.float())
@@ -388,7 +392,7 @@ def check_gn_epilogue(n=2, hw=1024, c1=640, c2=320, k=320, dt=torch.float16, spl
         w = _rand(ci, k, dt=dt, scale=1.5 / math.sqrt(k))
         b = torch.randn(ci, device=DEV)
         op = ops.gemm_op("prod", lib, a=ops.a_matrix(a.data_ptr(), M, k, k), b=ops.Mat(w), M=M, N=ci, K=k,
-                         dt=dt, out=buf.data_ptr() + off * 2, ldo=C, bias=b, ws=ws, splits=splits)
+                         dt=dt, out=buf.data_ptr() + off * 2, ldo=C, bias=b, ws=ws, splits=splits, cluster_k=False)
         p = op.keep[0]
         p.gn_stats[0] = stats.data_ptr()
         p.gn_cpg[0], p.gn_choff[0] = C // 32, off
@@ -459,6 +463,20 @@ CHECKS = {
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
     "gemm_splitk_finish_kernel": (lambda: check_gemm(256, 1280, 5120, splits=8, fused_reduce=False), 2e-3),
     "gemm_splitk_18": (lambda: check_gemm(128, 1280, 11520, splits=18), 2e-3),
+    "gemm_ck2_pair": (lambda: check_gemm(512, 1280, 1280, splits=2, pair=True, cluster_k=True), 2e-3),
+    "gemm_ck8": (lambda: check_gemm(256, 1280, 5120, splits=8, pair=False, cluster_k=True), 2e-3),
+    "gemm_ck4_pair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=True, cluster_k=True), 2e-3),
+    "gemm_ck3_ragged": (lambda: check_gemm(300, 480, 2560, splits=3, cluster_k=True), 2e-3),
+    "gemm_ck2_bf16": (lambda: check_gemm(512, 640, 1280, splits=2, dt=torch.bfloat16, cluster_k=True), 1e-2),
+    "gemm_ck16_nonportable": (lambda: check_gemm(128, 1280, 11520, splits=16, cluster_k=True), 2e-3),
+    "gemm_ck8_pair_nonportable": (lambda: check_gemm(256, 1280, 5120, splits=8, pair=True, cluster_k=True), 2e-3),
+    "geglu_ck4": (lambda: check_geglu(128, 1280, 5120, splits=4, cluster_k=True), 2e-2),
+    "conv_ck_16": (lambda: check_conv(2, 16, 16, 1280, 1280, cluster_k=True), 2e-3),
+    "conv_ck_8": (lambda: check_conv(2, 8, 8, 1280, 1280, cluster_k=True), 2e-3),
+    "conv_ck_stride2_16": (lambda: check_conv(2, 16, 16, 1280, 1280, stride=2, residual=False,
+                                              rowbias=False, cluster_k=True), 2e-3),
+    "ln_fold_ck": (lambda: check_ln_fold(256, 1280, 1280, splits_p=2, splits_c=2, cluster_k=True), 5e-3),
+    "ln_fold_geglu_ck": (lambda: check_ln_fold(128, 1280, 5120, mode="geglu", splits_c=2, cluster_k=True), 2e-2),
     "gemm_pair": (lambda: check_gemm(512, 320, 640, pair=True), 2e-3),
     "gemm_pair_big": (lambda: check_gemm(8192, 1280, 1280, pair=True), 2e-3),
     "gemm_pair_ragged": (lambda: check_gemm(300, 480, 320, pair=True), 2e-3),
