@@ -95,24 +95,36 @@ def load_peaks():
     return 1400.0, 6650.0, "fallback"
 
 
+def workload_name(args, batch, ctx_dim):
+    return (f"{args.model} UNet2DConditionModel forward, {batch} latent(s) 4x{args.size}x{args.size} "
+            f"per step per GPU (B=2 = the CFG pair of one {args.size * 8}^2 image), text 77x{ctx_dim}, "
+            "random-init weights")
+
+
+def cross_dim(args):
+    from sfast_b200.synthetic import CONFIGS
+    return CONFIGS[args.model]["cross_attention_dim"]
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(args, steps, warmup, budget_s):
     """The reference's CPU path for this workload = plain eager PyTorch fp32 (every sfast op falls
     back to aten on CPU: /root/reference/src/sfast/csrc/operators/cublas/cublas_gemm.cpp:705-710,
     /root/reference/src/sfast/triton/torch_ops.py:116-126), run on the oracle restatement of the
-    UNet because diffusers is not installable here.  One step = ONE latent (B = 1)."""
+    UNet because diffusers is not installable here.  One step = the same batch as the GPU arm."""
     from oracle import unet_oracle as uo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = {"sd15": uo.sd15_config, "sdxl": uo.sdxl_config, "tiny": uo.tiny_config}[args.model]()
     m = uo.build_unet(cfg, seed=0)
     g = torch.Generator().manual_seed(0)
-    s = torch.randn(1, 4, args.size, args.size, generator=g)
-    e = torch.randn(1, 77, cfg.cross_attention_dim, generator=g)
+    nb = args.batch
+    s = torch.randn(nb, 4, args.size, args.size, generator=g)
+    e = torch.randn(nb, 77, cfg.cross_attention_dim, generator=g)
     kw = {}
     if cfg.addition_embed_type == "text_time":
-        kw["added_cond_kwargs"] = {"text_embeds": torch.randn(1, 1280, generator=g),
-                                   "time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]])}
+        kw["added_cond_kwargs"] = {"text_embeds": torch.randn(nb, 1280, generator=g),
+                                   "time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * nb)}
     times = []
     with torch.no_grad():
         t0 = time.perf_counter()
@@ -126,9 +138,10 @@ def cpu_reference_run(args, steps, warmup, budget_s):
             times.append(time.perf_counter() - t0)
     times.sort()
     med = times[len(times) // 2]
-    return {"value": 1.0 / med, "ms_per_step": med * 1e3, "steps": n, "cores": cores,
-            "sample": f"{n} timed fp32 eager forward(s) of ONE {args.model} latent "
-                      f"4x{args.size}x{args.size} after 1 warm-up, {cores} threads"}
+    return {"value": nb / med, "ms_per_step": med * 1e3, "steps": n, "cores": cores,
+            "sample": f"{n} timed fp32 eager forward(s) of {nb} {args.model} latent(s) "
+                      f"4x{args.size}x{args.size} (the same batch as the GPU arm) after 1 warm-up, "
+                      f"{cores} threads, median"}
 
 
 def run_reference(args, rank):
@@ -140,8 +153,9 @@ def run_reference(args, rank):
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.model} UNet forward, 1 latent 4x{args.size}x{args.size} per "
-                               "step, fp32 CPU eager (reference CPU path = aten fallbacks)"},
+        "config": {"workload": workload_name(args, args.batch, cross_dim(args)),
+                   "global_batch": args.batch, "parallelism": "cpu",
+                   "arm": "fp32 CPU eager (the reference's CPU path = aten fallbacks) on the oracle port"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,7 +213,8 @@ def run_b200(args, rank, world, local):
     torch.cuda.synchronize()
     gp = next(iter(compiled._cached.values()))
     plan = gp.plan
-    launches_per_step = (lib.sfb_launch_count() - n0) // (2 if gp.graph is not None else 1)
+    # first call = eager warm-up pass + (graph capture | eager step): two passes over the plan
+    launches_per_step = (lib.sfb_launch_count() - n0) // 2
 
     def barrier():
         if world > 1:
@@ -260,10 +275,8 @@ def run_b200(args, rank, world, local):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {
-            "workload": f"{args.model} UNet2DConditionModel forward, {batch} latent(s) "
-                        f"4x{args.size}x{args.size} per GPU per step (CFG pair for bs=1 at "
-                        f"{args.size * 8}^2), text 77x{ctx_dim}, random-init weights, "
-                        f"CUDA graph {'on' if not args.no_graph else 'off'}",
+            "workload": workload_name(args, batch, ctx_dim),
+            "cuda_graph": not args.no_graph,
             "global_batch": total_latents, "parallelism": f"dp{world}",
             "l2": "inputs larger than L2: the 1.72 GB fp16 weight set streams from HBM every step",
             "sd15_20step_unet_ms_per_img": 20 * ms_step if (args.model == "sd15" and batch == 2) else None,
@@ -278,6 +291,26 @@ def run_b200(args, rank, world, local):
         "cpu_baseline": cpu_base,
     }
     print(json.dumps(line), flush=True)
+
+
+def ncu_traffic(prefix):
+    """DRAM bytes per launch of the kernel family, from the committed ncu launch list of this same
+    command (profiles/rNN_ncu_launch_summary.json, made by tests/summarize_ncu.py; ncu flushes the
+    caches before every kernel, so this is cold-cache traffic)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launch_summary.json")))
+    if not files:
+        return {"traffic": None}
+    d = json.load(open(files[-1]))
+    n = b = 0
+    for name, f in d.get("families", {}).items():
+        if name.startswith(prefix) and "dram_bytes_per_launch" in f:
+            n += f["launches"]
+            b += f["dram_bytes_per_launch"] * f["launches"]
+    if not n:
+        return {"traffic": None}
+    return {"traffic": b / n, "traffic_unit": "DRAM bytes per launch (read + write, ncu, cold caches)",
+            "traffic_source": os.path.relpath(files[-1], ROOT)}
 
 
 def measure_roofline(plan, lib, dump_path=""):
@@ -326,11 +359,11 @@ def measure_roofline(plan, lib, dump_path=""):
     gn = fam.get("sfb_group_norm_apply")
     if gn:
         extra["group_norm_apply_gbs"] = gn["bytes"] / (gn["ms"] / 1e3) / 1e9
-    return {"bound": "tensor", "kernel": "gemm_tc_kernel<160,3> (tcgen05 GEMM / implicit-GEMM conv)",
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM 3x3 conv, all instances)",
             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             "peak_source": f"{src} (MEASURED_PEAKS.json bf16_tflops_sustained)",
             "launches_per_step": g["n"], "avg_launch_us": g["ms"] * 1e3 / max(g["n"], 1),
-            "flop_per_step": g["flops"], "traffic": None,
+            "flop_per_step": g["flops"], **ncu_traffic("gemm_tc_kernel"),
             "eager_step_ms": total_ms, "time_share_by_entry_point": shares, **extra}
 
 

@@ -94,10 +94,10 @@ typedef struct sfb_gemm_params {
     int32_t dtype;
     /* SFB_A_CONV3X3 geometry: OUTPUT image dims and the M-tile box */
     int32_t img_n, img_h, img_w, cin, conv_stride, box_h, box_n;
-    /* split-K: >1 writes fp32 partials to `ws` ([splits, M, N]).  With `split_sync` (int32
-     * [tiles, 2], zero-initialised once, self re-arming) and a grid of <= 148 CTAs the split CTAs of
-     * a tile meet at a counter barrier and reduce + finish the tile themselves; otherwise a second
-     * kernel reduces. */
+    /* split-K: >1 writes fp32 partials to `ws` ([splits, M, N]).  With `split_sync` (int32 [tiles],
+     * zero-initialised once, self re-arming) the split CTA of a tile that arrives last adds the
+     * other partials and finishes the tile itself; otherwise (or with gn_stats) a second kernel
+     * reduces. */
     int32_t splits;
     float* ws;
     void* split_sync;

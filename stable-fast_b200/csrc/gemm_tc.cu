@@ -685,39 +685,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             }
             if (args.split_sync) {
-                // Fused reduction: the `splits` CTAs of this output tile (all co-resident: the host
-                // only enables this when the whole grid fits on the GPU at once) meet at a counter
-                // barrier, then each reduces + finishes its own slice of the tile's rows.
-                int* cnt = args.split_sync + 2 * (m_tile * n_tiles_grid + n_tile);
+                // Fused reduction, no waiting: every split CTA publishes its partial tile and bumps
+                // the tile's counter; whoever arrives LAST (its own partial is still in shared
+                // memory) adds the other partials from L2 and runs the epilogue.  No co-residency
+                // requirement, no second kernel.  The last CTA re-arms the counter.
+                int* cnt = args.split_sync + (m_tile * n_tiles_grid + n_tile);
+                int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
                 __threadfence();
                 epi_bar();
                 if (et == 0) {
-                    atomicAdd(cnt, 1);
-                    const long long t0 = clock64();
-                    while (*reinterpret_cast<volatile int*>(cnt) < args.splits) {
-                        if (clock64() - t0 > 4000000000LL) __trap();
-                    }
+                    const int old = atomicAdd(cnt, 1);
+                    const int last = old == args.splits - 1;
+                    if (last) *reinterpret_cast<volatile int*>(cnt) = 0;
+                    *s_last = last;
+                }
+                epi_bar();
+                if (*s_last) {
                     __threadfence();
-                }
-                epi_bar();
-                const int rows_per = (BM + args.splits - 1) / args.splits;
-                const int r0 = split * rows_per;
-                const int nrows = max(0, min(rows_per, BM - r0));
-                const bool geglu = e.epi == SFB_EPI_GEGLU;
-                const int gpr = geglu ? kGroups / 2 : kGroups;  // items per row
-                for (int idx = et; idx < nrows * gpr; idx += kEpiThreads) {
-                    const int row = r0 + idx / gpr, grp = idx % gpr;
-                    const int mm = sRowM[row];
-                    const int n = (geglu ? n_tile * (BN / 2) : ncol0) + grp * 8;
-                    if (mm >= 0 && n < (geglu ? e.geglu_n_out : e.N))
-                        splitk_reduce8<BN, BF16>(args.ws, args.splits, e, mm, n);
-                }
-                epi_bar();
-                if (et == 0) {
-                    if (atomicAdd(cnt + 1, 1) == args.splits - 1) {  // last finisher re-arms the counters
-                        cnt[0] = 0;
-                        cnt[1] = 0;
-                        __threadfence();
+                    for (int ps = 0; ps < args.splits; ++ps) {
+                        if (ps == split) continue;
+                        const float* wsp = args.ws + (size_t)ps * e.M * e.N;
+#pragma unroll 1
+                        for (int b = 0; b < kItems / kBatch; ++b) {
+                            float4 lo[kBatch], hi[kBatch];
+#pragma unroll
+                            for (int j = 0; j < kBatch; ++j) {
+                                int row, grp, mm, n;
+                                item_addr(b * kBatch + j, row, grp, mm, n);
+                                if (mm >= 0 && n < e.N) {
+                                    const float* src = wsp + (size_t)mm * e.N + n;
+                                    lo[j] = __ldcg(reinterpret_cast<const float4*>(src));
+                                    hi[j] = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                                } else {
+                                    lo[j] = hi[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < kBatch; ++j) {
+                                int row, grp, mm, n;
+                                item_addr(b * kBatch + j, row, grp, mm, n);
+                                float4* d = reinterpret_cast<float4*>(sStage + row * L::kStagePitch + grp * 8);
+                                float4 x = d[0], y = d[1];
+                                x.x += lo[j].x; x.y += lo[j].y; x.z += lo[j].z; x.w += lo[j].w;
+                                y.x += hi[j].x; y.y += hi[j].y; y.z += hi[j].z; y.w += hi[j].w;
+                                d[0] = x; d[1] = y;
+                            }
+                        }
+                    }
+                    epi_bar();  // the epilogue below re-partitions the tile among the threads
+                    const bool geglu = e.epi == SFB_EPI_GEGLU;
+                    const int gpr = geglu ? kGroups / 2 : kGroups;  // items per row
+#pragma unroll 1
+                    for (int idx = et; idx < BM * gpr; idx += kEpiThreads) {
+                        const int row = idx / gpr, grp = idx - row * gpr;
+                        const int mm = sRowM[row];
+                        const int n = (geglu ? n_tile * (BN / 2) : ncol0) + grp * 8;
+                        if (mm < 0 || n >= (geglu ? e.geglu_n_out : e.N)) continue;
+                        auto sum8 = [&](int col, float (&acc)[8]) {
+                            load8(row, col - ncol0, acc);
+                        };
+                        reduce_epilogue8<BN, BF16>(sum8, e, mm, n);
                     }
                 }
             }
@@ -1066,10 +1093,11 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     memcpy(&tb, p->tmap_b, sizeof(CUtensorMap));
     // <= one CTA per SM anyway: take the deep 6-stage pipeline; otherwise 3 stages x 2 CTAs/SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
-    // fused split-K reduction needs every CTA of the launch resident at once (counter barrier)
-    if (a.splits > 1 && !a.cluster_k && p->split_sync && ctas <= 148) a.split_sync = reinterpret_cast<int*>(p->split_sync);
+    // fused split-K reduction (last-arriving CTA of a tile finishes it); GroupNorm statistics only
+    // exist in the stand-alone reduction kernel
+    if (a.splits > 1 && !a.cluster_k && p->split_sync && !p->gn_stats[0]) a.split_sync = reinterpret_cast<int*>(p->split_sync);
     static const int force_stages = [] { const char* v = getenv("SFB_GEMM_STAGES"); return v ? atoi(v) : 0; }();
-    const bool deep = a.split_sync ? true : (force_stages ? (force_stages == 6) : (ctas <= 148));
+    const bool deep = force_stages ? (force_stages == 6) : (ctas <= 148);
     int rc;
     if (p->cta_pair) {
         // CTA pairs along M (cluster 1x2, tcgen05.mma.cta_group::2): tmap_b box = 80 rows

@@ -45,14 +45,25 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
         const int row0 = blockIdx.x * a.rows_per_block;
         const int row1 = min(row0 + a.rows_per_block, a.hw);
         const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
-        for (int row = row0 + ty; row < row1; row += by) {
-            const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        constexpr int kU = 8;
+        for (int rb = row0 + ty; rb < row1; rb += by * kU) {
+            uint4 v[kU];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack2(w[i], a.dtype);
-                s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
-                s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
+            for (int u = 0; u < kU; ++u) {
+                const int row = rb + u * by;
+                if (row < row1) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (rb + u * by < row1) {
+                    const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = unpack2(w[i], a.dtype);
+                        s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
+                        s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
+                    }
+                }
             }
         }
         // merge runs of equal group id among the 8 channels
@@ -106,22 +117,35 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     const int items = (row1 - row0) * a.nvec;
     const uint16_t* xb = a.x + ((size_t)img * a.hw + row0) * a.ldx;
     uint16_t* yb = a.y + ((size_t)img * a.hw + row0) * a.ldy;
-    for (int it = threadIdx.x; it < items; it += kGnThreads) {
-        const int row = it / a.nvec;
-        const int vec = it - row * a.nvec;
-        const uint4 v = *reinterpret_cast<const uint4*>(xb + (size_t)row * a.ldx + vec * 8);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t o[4];
+    constexpr int kU = 4;
+    for (int it0 = threadIdx.x; it0 < items; it0 += kGnThreads * kU) {
+        uint4 v[kU];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = unpack2(w[i], a.dtype);
-            const int ch = vec * 8 + 2 * i;
-            float y0 = f.x * scale[ch] + shift[ch];
-            float y1 = f.y * scale[ch + 1] + shift[ch + 1];
-            if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-            o[i] = pack2(y0, y1, a.dtype);
+        for (int u = 0; u < kU; ++u) {
+            const int it = it0 + u * kGnThreads;
+            if (it < items) {
+                const int row = it / a.nvec, vec = it - row * a.nvec;
+                v[u] = *reinterpret_cast<const uint4*>(xb + (size_t)row * a.ldx + vec * 8);
+            }
         }
-        *reinterpret_cast<uint4*>(yb + (size_t)row * a.ldy + vec * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int it = it0 + u * kGnThreads;
+            if (it >= items) continue;
+            const int row = it / a.nvec, vec = it - row * a.nvec;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2(w[i], a.dtype);
+                const int ch = vec * 8 + 2 * i;
+                float y0 = f.x * scale[ch] + shift[ch];
+                float y1 = f.y * scale[ch + 1] + shift[ch + 1];
+                if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+                o[i] = pack2(y0, y1, a.dtype);
+            }
+            *reinterpret_cast<uint4*>(yb + (size_t)row * a.ldy + vec * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -155,15 +179,29 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
         const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
-        for (int row = row0 + ty; row < row1; row += by) {
-            const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
-            slab[(row - row0) * a.nvec + tx] = v;
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        // all of a thread's loads of one batch are in flight together: the slab is a handful of
+        // rows per thread, so a load-use-load chain would be nothing but exposed L2 latency
+        constexpr int kU = 8;
+        for (int rb = row0 + ty; rb < row1; rb += by * kU) {
+            uint4 v[kU];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack2(w[i], a.dtype);
-                s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
-                s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
+            for (int u = 0; u < kU; ++u) {
+                const int row = rb + u * by;
+                if (row < row1) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int row = rb + u * by;
+                if (row < row1) {
+                    slab[(row - row0) * a.nvec + tx] = v[u];
+                    const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = unpack2(w[i], a.dtype);
+                        s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
+                        s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
+                    }
+                }
             }
         }
         int g_run = (tx * 8) / a.cpg;
@@ -184,6 +222,12 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads)
         atomicAdd(&a.stats[(size_t)img * a.groups * 2 + i], acc[i]);
+    // affine parameters do not depend on the statistics: fetch them (cold, from HBM) while the
+    // grid barrier is pending
+    for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
+        scale[ch] = a.gamma[ch];
+        shift[ch] = a.beta[ch];
+    }
     // ---- grid barrier
     __threadfence();
     __syncthreads();
@@ -206,9 +250,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
         const float mean = sum * inv_cnt;
         const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + a.eps);
-        const float sc = rstd * a.gamma[ch];
+        const float sc = rstd * scale[ch];
         scale[ch] = sc;
-        shift[ch] = a.beta[ch] - mean * sc;
+        shift[ch] = shift[ch] - mean * sc;
     }
     __syncthreads();
     if (ty < by) {

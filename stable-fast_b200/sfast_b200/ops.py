@@ -107,15 +107,33 @@ def conv_tile_box(ho, wo):
     return rows // ho, ho
 
 
-def choose_splits(m_tiles, n_tiles, nkb):
-    """Split-K factor.  Only the weight-bandwidth-bound low-resolution layers (few output tiles,
-    long K) are split, to put ~148 CTAs on the machine; every split keeps >= 8 K-blocks so the
-    fp32 partial round trip + reduction kernel stays small next to the main loop (measured on
-    B200: splitting K = 1280 five ways cost more in the reduction kernel than it saved)."""
+# split-K cost model (microseconds, measured on B200 inside the captured graph):
+# a single-wave GEMM launch costs ~4.5 us of prologue + epilogue + drain plus 0.34 us per 64-wide
+# K block of its longest CTA; the fused reduction (last-arriving split CTA sums the other partial
+# tiles from L2) adds ~1.5 us + 1.6 us per extra split; the stand-alone reduction kernel ~10 us
+# plus its fp32 partial traffic at ~3 TB/s.
+FUSED_SPLITK_MAX = int(os.environ.get("SFB_FUSED_SPLITK_MAX", "4"))
+_T_FIXED, _T_KB = 4.5, 0.34
+
+
+def choose_splits(m_tiles, n_tiles, nkb, M=None, N=None, fused=True):
+    """Split-K factor minimising the modelled launch time.  Only grids of at most half a wave are
+    split (the weight-bandwidth-bound low-resolution layers); all split CTAs fit in one wave."""
     tiles = m_tiles * n_tiles
     if tiles * 2 > NUM_SMS:
         return 1
-    return max(1, min(NUM_SMS // tiles, nkb // 8))
+    M = M if M is not None else m_tiles * BM
+    N = N if N is not None else n_tiles * BN
+    best, best_t = 1, _T_FIXED + _T_KB * nkb
+    for s in range(2, min(NUM_SMS // tiles, nkb) + 1):
+        t = _T_FIXED + _T_KB * -(-nkb // s)
+        if fused and s <= FUSED_SPLITK_MAX:
+            t += 1.5 + 1.6 * (s - 1)
+        else:
+            t += 10.0 + s * M * N * 4 / 3e6
+        if t < best_t - 0.5:
+            best, best_t = s, t
+    return best
 
 
 ENABLE_CLUSTER = os.environ.get("SFB_CLUSTER", "0") != "0"  # measured slower on B200: smem-bound, see DESIGN.md
@@ -126,7 +144,7 @@ ENABLE_CTA_PAIR = os.environ.get("SFB_CTA_PAIR", "1") != "0"
 # split-K partial tiles summed through distributed shared memory inside a thread-block cluster
 # along grid.z (no fp32 workspace round trip, no reduction kernel); cluster sizes > 8 are
 # "non-portable" (one cluster of 16 per GPC on B200)
-ENABLE_CLUSTER_K = os.environ.get("SFB_CLUSTER_K", "1") != "0"
+ENABLE_CLUSTER_K = os.environ.get("SFB_CLUSTER_K", "0") != "0"  # measured slower (cluster co-scheduling), DESIGN.md
 CLUSTER_K_MAX = int(os.environ.get("SFB_CLUSTER_K_MAX", "16"))
 
 
@@ -212,7 +230,7 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
     n_tiles = (N + BN - 1) // BN
     nkb = K // BK
     if splits is None:
-        splits = choose_splits(m_tiles, n_tiles, nkb)
+        splits = choose_splits(m_tiles, n_tiles, nkb, M, N, fused=split_sync is not None)
     if ws is None:
         splits = 1
     if cluster_k is None:
@@ -226,7 +244,7 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         if ws.numel() < need:
             raise ValueError(f"{name}: split-K workspace too small ({ws.numel()} < {need})")
         p.ws = _ptr(ws) if not hasattr(ws, "finalize") else 0
-        p.split_sync = _ptr(split_sync)
+        p.split_sync = _ptr(split_sync) if splits <= FUSED_SPLITK_MAX else 0
     p.epi = epi
     p.out = _ptr(out)
     p.ldo = ldo

@@ -248,8 +248,8 @@ class UNetPlan:
     def _gemm(self, name, **kw):
         # split-K workspace: one shared fp32 buffer, sized after all ops are known
         kw.setdefault("ws", self._ws_token)
-        if os.environ.get("SFB_FUSED_SPLITK", "0") != "0":  # measured slower than the reduce kernel
-            kw.setdefault("split_sync", self.split_sync)
+        if os.environ.get("SFB_FUSED_SPLITK", "1") != "0" and os.environ.get("SFB_GN_EPILOGUE", "0") == "0":
+            kw.setdefault("split_sync", self.split_sync)  # last-arriving split CTA finishes the tile
         if os.environ.get("SFB_GN_EPILOGUE", "0") != "0":
             kw.setdefault("cluster_k", False)  # GroupNorm statistics live in the reduction kernel
         op = ops.gemm_op(name, self.lib_or_dry(), dry=self.dry, **kw)

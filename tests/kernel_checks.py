@@ -463,6 +463,11 @@ CHECKS = {
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
     "gemm_splitk_finish_kernel": (lambda: check_gemm(256, 1280, 5120, splits=8, fused_reduce=False), 2e-3),
     "gemm_splitk_18": (lambda: check_gemm(128, 1280, 11520, splits=18), 2e-3),
+    "gemm_fused_s2": (lambda: check_gemm(512, 1280, 1280, splits=2), 2e-3),
+    "gemm_fused_s4_pair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=True), 2e-3),
+    "gemm_fused_s4_nopair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=False), 2e-3),
+    "gemm_fused_s3_ragged": (lambda: check_gemm(300, 480, 2560, splits=3), 2e-3),
+    "gemm_fused_s2_bf16": (lambda: check_gemm(512, 640, 1280, splits=2, dt=torch.bfloat16), 1e-2),
     "gemm_ck2_pair": (lambda: check_gemm(512, 1280, 1280, splits=2, pair=True, cluster_k=True), 2e-3),
     "gemm_ck8": (lambda: check_gemm(256, 1280, 5120, splits=8, pair=False, cluster_k=True), 2e-3),
     "gemm_ck4_pair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=True, cluster_k=True), 2e-3),

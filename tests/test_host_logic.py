@@ -100,12 +100,16 @@ def test_sdxl_plan_builds():
 
 
 def test_split_k_policy():
+    # cost model: ~4.5 us per launch + 0.34 us per K block; fused reduction cheap up to 4 splits
     assert ops.choose_splits(64, 2, 45) == 1       # 64^2 resnet conv: 128 tiles, no split
     assert ops.choose_splits(16, 4, 10) == 1       # 32^2 linear, K = 640: too short to split
     assert ops.choose_splits(16, 4, 90) == 2       # 32^2 conv: 64 tiles -> 2 splits
-    assert ops.choose_splits(4, 8, 20) == 2        # 16^2 linear K = 1280
-    assert ops.choose_splits(1, 8, 180) == 18      # 8^2 conv: weight-bandwidth-bound, fill the SMs
-    assert ops.choose_splits(1, 1, 5) == 1         # never fewer than 8 K-blocks per split
+    assert ops.choose_splits(4, 8, 20) == 1        # 16^2 linear K = 1280: a reduction costs more
+    assert ops.choose_splits(4, 8, 180) == 4       # 16^2 conv K = 11520: fused 4-way
+    s = ops.choose_splits(1, 8, 180)               # 8^2 conv: weight-bandwidth-bound, fill the SMs
+    assert 8 <= s <= 18 and 8 * s <= ops.NUM_SMS
+    assert ops.choose_splits(1, 1, 5) == 1
+    assert ops.choose_splits(4, 8, 180, fused=False) >= 2
 
 
 def test_conv_tile_box():
