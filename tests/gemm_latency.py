@@ -12,21 +12,39 @@ sys.path.insert(0, os.path.join(ROOT, "stable-fast_b200"))
 from sfast_b200 import _lib, ops  # noqa: E402
 
 
-def run(M, N, K, chain=8, residual=True):
+def run(M, N, K, chain=8, residual=True, conv=None, rowbias=False, distinct=False):
+    """conv = (n, h, w, cin): 3x3 implicit-GEMM convolution (M = n*h*w, K = 9*cin) instead of a
+    plain matrix A operand.  distinct: every launch of the chain gets its own weights / input."""
     lib = _lib.lib()
     dt = torch.float16
-    a = torch.randn(M, K, device="cuda").to(dt)
-    w = torch.randn(N, K, device="cuda").to(dt)
+    nbuf = chain if distinct else 1
+    w = [torch.randn(N, K, device="cuda").to(dt) for _ in range(nbuf)]
     r = torch.randn(M, N, device="cuda").to(dt) if residual else None
     b = torch.randn(N, device="cuda")
     out = torch.zeros(M, N, device="cuda", dtype=dt)
-    mat = ops.Mat(w)
+    mats = [ops.Mat(x) for x in w]
     mt, nt = (M + 127) // 128, (N + 159) // 160
     stamps = torch.zeros(chain, mt * nt, 8, dtype=torch.int64, device="cuda")
     oplist = []
+    if conv:
+        n, h, wd, cin = conv
+        xs = [torch.randn(n, h, wd, cin, device="cuda").to(dt) for _ in range(nbuf)]
+        box_n, box_h = ops.conv_tile_box(h, wd)
+        rb = torch.randn(n, N, device="cuda") if rowbias else None
+    else:
+        a = [torch.randn(M, K, device="cuda").to(dt) for _ in range(nbuf)]
     for i in range(chain):
-        op = ops.gemm_op("g", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=mat, M=M, N=N, K=K, dt=dt,
-                         out=out, ldo=N, bias=b, residual=r, ldr=N)
+        j = i % nbuf
+        if conv:
+            ad = ops.a_conv(xs[j].data_ptr(), n, h, wd, cin, cin, box_n, box_h, wd, 1)
+            op = ops.gemm_op("c", lib, a=ad, b=mats[j], M=M, N=N, K=K, dt=dt, out=out, ldo=N, bias=b,
+                             rowbias=rb, rows_per_img=h * wd, ld_rowbias=N, residual=r, ldr=N,
+                             conv=dict(n=n, h=h, w=wd, cin=cin, stride=1, box_n=box_n, box_h=box_h))
+            op.keep = tuple(op.keep) + (xs[j],)
+        else:
+            op = ops.gemm_op("g", lib, a=ops.a_matrix(a[j].data_ptr(), M, K, K), b=mats[j], M=M, N=N, K=K,
+                             dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N)
+            op.keep = tuple(op.keep) + (a[j],)
         op.keep[0].debug_stamps = stamps[i].data_ptr()
         oplist.append(op)
     st = torch.cuda.current_stream()
@@ -43,7 +61,7 @@ def run(M, N, K, chain=8, residual=True):
     torch.cuda.synchronize()
     t = stamps.cpu().numpy().astype("int64")
     names = ["entry", "setup", "tma0", "data0", "mma_issued", "acc_ready", "stored", "exit"]
-    res = {"M": M, "N": N, "K": K, "ctas": mt * nt}
+    res = {"M": M, "N": N, "K": K, "ctas": mt * nt, "conv": conv, "distinct": distinct}
     for i in (chain - 2, chain - 1):
         k = t[i]
         t0 = k[:, 0].min()
@@ -62,5 +80,8 @@ if __name__ == "__main__":
     run(8192, 320, 320)
     run(2048, 640, 640)
     run(512, 1280, 1280)
-    run(154, 640, 768, residual=False)
-    run(8192, 320, 2880 // 9 * 9 if False else 2880)
+    run(8192, 320, 2880)
+    run(8192, 320, 2880, distinct=True)
+    run(8192, 320, 2880, conv=(2, 64, 64, 320))
+    run(8192, 320, 2880, conv=(2, 64, 64, 320), rowbias=True, distinct=True)
+    run(2048, 640, 5760, conv=(2, 32, 32, 640), rowbias=True, distinct=True)
