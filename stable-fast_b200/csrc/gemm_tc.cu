@@ -304,12 +304,28 @@ __device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int
     auto sum8 = [&](int col, float (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int s = 0; s < splits; ++s) {
-            const float* p = ws + ((size_t)s * e.M + m) * e.N + col;
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(p + 4));
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        // batches of 6 partials with every load in flight before the first add: this kernel is
+        // one L2 round trip per batch, not per partial
+        constexpr int kU = 6;
+        const float* p0 = ws + (size_t)m * e.N + col;
+        const size_t stride = (size_t)e.M * e.N;
+        for (int s0 = 0; s0 < splits; s0 += kU) {
+            float4 a[kU], b[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (s0 + u < splits) {
+                    const float* p = p0 + (size_t)(s0 + u) * stride;
+                    a[u] = __ldcg(reinterpret_cast<const float4*>(p));
+                    b[u] = __ldcg(reinterpret_cast<const float4*>(p + 4));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (s0 + u < splits) {
+                    acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+                    acc[4] += b[u].x; acc[5] += b[u].y; acc[6] += b[u].z; acc[7] += b[u].w;
+                }
+            }
         }
     };
     reduce_epilogue8<BN, BF16>(sum8, e, m, n, gn_sacc, gn_img0, gn_shard);

@@ -322,10 +322,11 @@ class UNetPlan:
         self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
         self._emit(op)
 
-    def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None, rowstats_out=None):
+    def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None, rowstats_out=None,
+               splits=None):
         kw = dict(a=self._a_matrix(x), b=wm, M=x.rows, N=wm.n, K=x.c, dt=self.dt,
                   out=dst.ptr, ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, wm),
-                  rowstats_out=rowstats_out)
+                  rowstats_out=rowstats_out, splits=splits)
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
         op = self._gemm(name, **kw)
@@ -335,12 +336,26 @@ class UNetPlan:
     # ------------------------------------------------------------------ sub-graphs
     def resnet(self, r, x: Act, dst: Act):
         p = r.prefix
+        fork = None
+        if r.has_shortcut and os.environ.get("SFB_SIDE_SHORTCUT", "1") != "0":
+            # the 1x1 shortcut only needs the block input: parallel graph branch next to
+            # norm1 / conv1 / norm2 (most of these launches leave SMs idle at small batch)
+            sc = self.act("res_sc", x.n, x.h, x.w, r.cout)
+            n0 = len(self.ops)
+            self.linear(p + ".conv_shortcut", x, self.w.matrix(p + ".conv_shortcut.weight"),
+                        self.w.f32(p + ".conv_shortcut.bias"), sc, splits=1)
+            fork = _ForkOp(self.ops[n0:])
+            del self.ops[n0:]
+            self._emit(fork)
         a1 = self.group_norm(p + ".norm1", x, p + ".norm1", True, self.spec.eps)
         h1 = self.act("res_h1", x.n, x.h, x.w, r.cout)
         rb_ptr = _ptr(self.temb_proj) + 4 * self.w.tproj_off[p]
         self.conv3x3(p + ".conv1", a1, p + ".conv1", h1, rowbias=(rb_ptr, self.w.tproj_total))
         a2 = self.group_norm(p + ".norm2", h1, p + ".norm2", True, self.spec.eps)
-        if r.has_shortcut:
+        if fork is not None:
+            self._emit(_JoinOp(fork))
+            res = sc
+        elif r.has_shortcut:
             sc = self.act("res_sc", x.n, x.h, x.w, r.cout)
             self.linear(p + ".conv_shortcut", x, self.w.matrix(p + ".conv_shortcut.weight"),
                         self.w.f32(p + ".conv_shortcut.bias"), sc)
@@ -634,13 +649,30 @@ class UNetPlan:
             if isinstance(op, _JoinOp):
                 if op.kind == "temb":
                     main.wait_event(self._temb_event)
-                else:
+                elif op.kind == "all":
                     main.wait_stream(self._side_stream)
+                else:  # join of one forked branch
+                    main.wait_event(op.kind.ev_done)
+            elif isinstance(op, _ForkOp):
+                if op.ev_fork is None:
+                    op.ev_fork, op.ev_done = torch.cuda.Event(), torch.cuda.Event()
+                op.ev_fork.record(main)
+                side.wait_event(op.ev_fork)
+                for o in op.branch:
+                    o.launch(sptr)
+                op.ev_done.record(side)
             else:
                 op.launch(mptr)
 
     def all_ops(self):
-        return self.side_ops + [op for op in self.ops if not isinstance(op, _JoinOp)]
+        """Every kernel-launching op of one step (markers removed, forked branches expanded)."""
+        out = list(self.side_ops)
+        for op in self.ops:
+            if isinstance(op, _ForkOp):
+                out.extend(op.branch)
+            elif not isinstance(op, _JoinOp):
+                out.append(op)
+        return out
 
     def flops(self):
         return sum(op.flops for op in self.all_ops())
@@ -661,26 +693,41 @@ class _WsToken:
     def finalize(self, plan):
         need = 0
         gemm = plan.lib_or_dry().sfb_gemm
-        for op in plan.ops:
+        main_ops = [op for op in plan.ops if not isinstance(op, (_ForkOp, _JoinOp))]
+        for op in main_ops:
             if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
                 need = max(need, op.keep[0].splits * op.keep[0].M * op.keep[0].N)
         plan.ws = plan._alloc((max(need, 1),), torch.float32)
-        for op in plan.ops:
+        for op in main_ops:
             if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
                 op.keep[0].ws = _ptr(plan.ws)
         # side-stream GEMMs run concurrently with the main chain: they must not share the
         # split-K workspace, so they are never split
-        for op in plan.side_ops:
+        forked = [o for op in plan.ops if isinstance(op, _ForkOp) for o in op.branch]
+        for op in plan.side_ops + forked:
             if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
                 raise AssertionError("side-stream GEMM must not use split-K")
 
 
 class _JoinOp(Op):
-    """Main stream waits for the side stream (the hoisted K/V projections) here."""
+    """Main stream waits for the side stream here: "all" (everything issued so far), "temb" (the
+    time-embedding chain) or a _ForkOp (that branch only)."""
 
     def __init__(self, kind="all"):
-        super().__init__(f"join(side stream: {kind})", None, (), ())
+        super().__init__("join(side stream)", None, (), ())
         self.kind = kind
+
+
+class _ForkOp(Op):
+    """`branch` runs on the side stream, ordered after everything already on the main stream."""
+
+    def __init__(self, branch):
+        super().__init__("fork(side stream)", None, (), ())
+        self.branch = list(branch)
+        self.ev_fork = self.ev_done = None
+
+    def launch(self, stream):
+        raise RuntimeError("fork marker is handled by UNetPlan.run")
 
     def launch(self, stream):
         raise RuntimeError("join marker is handled by UNetPlan.run")
