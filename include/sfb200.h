@@ -106,6 +106,9 @@ typedef struct sfb_gemm_params {
      * [s*128/splits, ...) of the tile.  No workspace, no second kernel.  Needs
      * splits * (cta_pair ? 2 : 1) <= 16 (> 8 is a non-portable cluster size) and no gn_stats. */
     int32_t cluster_k;
+    /* 1 (with splits > 1, STORE epilogue, no split_sync / cluster_k): only write the partials; the
+     * consumer (sfb_group_norm_fused with part_ws) finishes the tensor */
+    int32_t defer_finish;
     /* epilogue */
     int32_t epi;
     void* out;
@@ -204,6 +207,19 @@ typedef struct sfb_gn_params {
     /* sfb_group_norm_apply: `stats` may arrive as `stat_shards` partial copies (0/1 = one),
      * `stat_shard_stride` floats apart -- the layout sfb_gemm's GroupNorm accumulation writes */
     int32_t stat_shards, stat_shard_stride;
+    /* sfb_group_norm_fused only.  part_splits > 1: channels [0, part_c) of x do not exist yet --
+     * they are the fp32 split-K partials `part_ws` ([part_splits, n*hw, part_ld]) of a sfb_gemm
+     * launched with defer_finish.  The kernel sums them, applies that GEMM's STORE epilogue
+     * (part_bias [part_c], part_rowbias [n, part_ld_rowbias] per image, part_residual with pitch
+     * part_ldr; each may be NULL), writes the finished 16-bit values into x and normalises them
+     * in the same pass: the split-K reduction kernel disappears. */
+    const float* part_ws;
+    int32_t part_splits, part_c, part_ld;
+    const float* part_bias;
+    const float* part_rowbias;
+    int32_t part_ld_rowbias;
+    const void* part_residual;
+    int32_t part_ldr;
 } sfb_gn_params;
 
 /* two-pass path (any size): `stats` must be zero before sfb_group_norm_stats */

@@ -1125,6 +1125,11 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
         rc = deep ? launch_gemm<BN, 6, 1>(ta, tb, a, grid, stream) : launch_gemm<BN, 3, 1>(ta, tb, a, grid, stream);
     }
     if (rc) return rc;
+    if (p->defer_finish && a.splits > 1) {
+        if (a.split_sync || a.cluster_k || e.epi != SFB_EPI_STORE || e.rowstats_out || e.ln_rowstats || e.gn_stats[0])
+            return fail(SFB_ERR_INVALID, "sfb_gemm: defer_finish needs a plain STORE epilogue and the workspace split-K path");
+        return rc;  // the consumer (sfb_group_norm_fused with part_ws) finishes the tensor
+    }
     if (a.splits > 1 && !a.split_sync && !a.cluster_k) {
         const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
         const long long items = (long long)e.M * (ncols / 8);

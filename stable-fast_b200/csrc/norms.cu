@@ -23,7 +23,69 @@ struct GnArgs {
     int shards, shard_stride;  // statistics arrive as `shards` partial copies, `shard_stride` floats apart
     float eps;
     int silu, dtype;
+    // deferred split-K finish of the GEMM producing channels [0, part_c) (fused kernel only)
+    const float* part_ws;
+    int part_splits, part_c, part_ld;
+    const float* part_bias;
+    const float* part_rowbias;
+    int part_ld_rowbias;
+    const uint16_t* part_residual;
+    int part_ldr;
 };
+
+// Finished 16-bit values of channels [tx*8, tx*8+8) of pixel `row` of image `img` from the
+// producer GEMM's fp32 split-K partials: sum + bias + per-image row bias + residual (the STORE
+// epilogue of gemm_tc.cu's reduction kernel), also written to x.
+__device__ __forceinline__ uint4 gn_finish_partials(const GnArgs& a, int img, int row, int tx) {
+    const int m = img * a.hw + row;
+    const int col = tx * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    constexpr int kU = 6;  // partial loads in flight per batch
+    const size_t stride = (size_t)a.n * a.hw * a.part_ld;
+    const float* p0 = a.part_ws + (size_t)m * a.part_ld + col;
+    for (int s0 = 0; s0 < a.part_splits; s0 += kU) {
+        float4 lo[kU], hi[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (s0 + u < a.part_splits) {
+                const float* p = p0 + (size_t)(s0 + u) * stride;
+                lo[u] = __ldcg(reinterpret_cast<const float4*>(p));
+                hi[u] = __ldcg(reinterpret_cast<const float4*>(p + 4));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (s0 + u < a.part_splits) {
+                acc[0] += lo[u].x; acc[1] += lo[u].y; acc[2] += lo[u].z; acc[3] += lo[u].w;
+                acc[4] += hi[u].x; acc[5] += hi[u].y; acc[6] += hi[u].z; acc[7] += hi[u].w;
+            }
+        }
+    }
+    auto add8 = [&](const float* b) {
+        const float4 b0 = *reinterpret_cast<const float4*>(b);
+        const float4 b1 = *reinterpret_cast<const float4*>(b + 4);
+        acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
+        acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
+    };
+    if (a.part_bias) add8(a.part_bias + col);
+    if (a.part_rowbias) add8(a.part_rowbias + (size_t)img * a.part_ld_rowbias + col);
+    if (a.part_residual) {
+        const uint4 r = *reinterpret_cast<const uint4*>(a.part_residual + (size_t)m * a.part_ldr + col);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack2(w[i], a.dtype);
+            acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+        }
+    }
+    uint4 v;
+    v.x = pack2(acc[0], acc[1], a.dtype); v.y = pack2(acc[2], acc[3], a.dtype);
+    v.z = pack2(acc[4], acc[5], a.dtype); v.w = pack2(acc[6], acc[7], a.dtype);
+    *reinterpret_cast<uint4*>(const_cast<uint16_t*>(a.x) + (size_t)m * a.ldx + col) = v;
+    return v;
+}
 
 // grid (blocks_per_img, n).  Thread (tx = vector column, ty = row slot) keeps per-channel
 // partial sums for its 8 channels over rows ty, ty+BY, ...; one shared-memory atomic per
@@ -158,6 +220,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
 //   barrier  grid-wide arrive/spin on a global counter (grid <= 148 CTAs, all co-resident);
 //   phase 2  scale/shift from the finished statistics, y = act(x * scale + shift) from smem.
 // ---------------------------------------------------------------------------------------
+template <bool kPart>
 __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, unsigned* sync_counter) {
     extern __shared__ __align__(16) uint8_t fsm[];
     __shared__ float acc[2 * 64];
@@ -179,27 +242,42 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
         const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
-        // all of a thread's loads of one batch are in flight together: the slab is a handful of
-        // rows per thread, so a load-use-load chain would be nothing but exposed L2 latency
-        constexpr int kU = 8;
-        for (int rb = row0 + ty; rb < row1; rb += by * kU) {
-            uint4 v[kU];
+        auto accumulate = [&](const uint4& v) {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int row = rb + u * by;
-                if (row < row1) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2(w[i], a.dtype);
+                s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
+                s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
             }
+        };
+        if constexpr (kPart) {
+            // channels [0, part_c) come from the producer GEMM's split-K partials (a few rows per
+            // thread, each with all its partial loads in flight)
+            const bool from_partials = tx * 8 < a.part_c;
+            for (int row = row0 + ty; row < row1; row += by) {
+                const uint4 v = from_partials ? gn_finish_partials(a, img, row, tx)
+                                              : *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
+                slab[(row - row0) * a.nvec + tx] = v;
+                accumulate(v);
+            }
+        } else {
+            // all of a thread's loads of one batch are in flight together: the slab is a handful of
+            // rows per thread, so a load-use-load chain would be nothing but exposed L2 latency
+            constexpr int kU = 8;
+            for (int rb = row0 + ty; rb < row1; rb += by * kU) {
+                uint4 v[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int row = rb + u * by;
-                if (row < row1) {
-                    slab[(row - row0) * a.nvec + tx] = v[u];
-                    const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                for (int u = 0; u < kU; ++u) {
+                    const int row = rb + u * by;
+                    if (row < row1) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
+                }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 f = unpack2(w[i], a.dtype);
-                        s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
-                        s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
+                for (int u = 0; u < kU; ++u) {
+                    const int row = rb + u * by;
+                    if (row < row1) {
+                        slab[(row - row0) * a.nvec + tx] = v[u];
+                        accumulate(v[u]);
                     }
                 }
             }
@@ -432,15 +510,29 @@ extern "C" int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream)
     if (!gn_fused_geometry(p, bpi, rpb, smem))
         return fail(SFB_ERR_INVALID, "group_norm_fused: tensor does not fit in shared memory");
     a.rows_per_block = rpb;
+    if (p->part_splits > 1) {
+        if (!p->part_ws || p->part_c <= 0 || p->part_c % 8 || p->part_c > p->c || p->part_ld % 4 ||
+            p->part_ld < p->part_c || (p->part_residual && p->part_ldr % 8))
+            return fail(SFB_ERR_INVALID, "group_norm_fused: bad deferred split-K description");
+        a.part_ws = p->part_ws; a.part_splits = p->part_splits; a.part_c = p->part_c; a.part_ld = p->part_ld;
+        a.part_bias = p->part_bias; a.part_rowbias = p->part_rowbias; a.part_ld_rowbias = p->part_ld_rowbias;
+        a.part_residual = reinterpret_cast<const uint16_t*>(p->part_residual); a.part_ldr = p->part_ldr;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kGnFusedMaxSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kGnFusedMaxSmem);
         if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    cudaError_t err = launch_pdl(gn_fused_kernel, dim3(bpi, p->n), dim3(kGnThreads), smem,
-                                 static_cast<cudaStream_t>(stream), a, p->sync_counter);
+    cudaError_t err = a.part_splits > 1
+        ? launch_pdl(gn_fused_kernel<true>, dim3(bpi, p->n), dim3(kGnThreads), smem,
+                     static_cast<cudaStream_t>(stream), a, p->sync_counter)
+        : launch_pdl(gn_fused_kernel<false>, dim3(bpi, p->n), dim3(kGnThreads), smem,
+                     static_cast<cudaStream_t>(stream), a, p->sync_counter);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused: %s", cudaGetErrorString(err));
     return check_launch("sfb_group_norm_fused");
 }

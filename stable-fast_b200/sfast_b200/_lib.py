@@ -23,7 +23,7 @@ class GemmParams(C.Structure):
         ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32), ("cin", C.c_int32),
         ("conv_stride", C.c_int32), ("box_h", C.c_int32), ("box_n", C.c_int32),
         ("splits", C.c_int32), ("ws", C.c_void_p), ("split_sync", C.c_void_p),
-        ("cluster_k", C.c_int32),
+        ("cluster_k", C.c_int32), ("defer_finish", C.c_int32),
         ("epi", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int32),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p),
         ("rows_per_img", C.c_int32), ("ld_rowbias", C.c_int32),
@@ -61,6 +61,9 @@ class GnParams(C.Structure):
         ("ldy", C.c_int32), ("groups", C.c_int32),
         ("eps", C.c_float), ("silu", C.c_int32), ("dtype", C.c_int32),
         ("sync_counter", C.c_void_p), ("stat_shards", C.c_int32), ("stat_shard_stride", C.c_int32),
+        ("part_ws", C.c_void_p), ("part_splits", C.c_int32), ("part_c", C.c_int32),
+        ("part_ld", C.c_int32), ("part_bias", C.c_void_p), ("part_rowbias", C.c_void_p),
+        ("part_ld_rowbias", C.c_int32), ("part_residual", C.c_void_p), ("part_ldr", C.c_int32),
     ]
 
 
