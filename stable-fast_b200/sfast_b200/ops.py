@@ -300,10 +300,22 @@ def gn_fused_fits(n, hw, c, groups):
     return rpb * c * 2 + 2 * c * 4 <= 200 * 1024
 
 
+def gn_fused_ok(lib, x: Act, groups, dt, dry):
+    """Whether GroupNorm over `x` takes the single-launch fused kernel."""
+    if dry:
+        return gn_fused_fits(x.n, x.h * x.w, x.c, groups)
+    p = GnParams()
+    p.n, p.hw, p.c, p.ldx, p.groups, p.dtype = x.n, x.h * x.w, x.c, x.ld, groups, dtype_code(dt)
+    return bool(lib.sfb_group_norm_fused_fits(C.byref(p)))
+
+
 def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, dt, sync=None,
-           dry=False, stats_ready=False):
+           dry=False, stats_ready=False, partial=None):
     """GroupNorm(+SiLU): one fused launch when the tensor fits in shared memory (stats + apply
-    with a grid barrier, x read once), else the two-pass stats / apply kernels."""
+    with a grid barrier, x read once), else the two-pass stats / apply kernels.
+    `partial`: channels [0, c) of x are still the fp32 split-K partials of their producer GEMM
+    (launched with defer_finish); the fused kernel finishes them (dict: splits, c, ld, bias,
+    rowbias, ld_rowbias, residual, ldr; the workspace pointer is patched in by the plan)."""
     p = GnParams()
     p.x, p.y = x.ptr, y.ptr
     p.gamma, p.beta, p.stats = _ptr(gamma), _ptr(beta), _ptr(stats)
@@ -319,7 +331,16 @@ def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, 
         fits = gn_fused_fits(p.n, p.hw, p.c, groups) if dry else bool(
             lib.sfb_group_norm_fused_fits(C.byref(p)))
         if fits:
+            if partial is not None:
+                p.part_splits, p.part_c, p.part_ld = partial["splits"], partial["c"], partial["ld"]
+                p.part_bias, p.part_rowbias = _ptr(partial.get("bias")), partial.get("rowbias") or 0
+                p.part_ld_rowbias = partial.get("ld_rowbias", 0)
+                p.part_residual, p.part_ldr = partial.get("residual") or 0, partial.get("ldr", 0)
+                p.part_ws = _ptr(partial.get("ws"))
+                keep = keep + (partial,)
             return [Op(name + ".fused", lib.sfb_group_norm_fused, (C.byref(p),), keep, 0, 2 * nb)]
+    if partial is not None:
+        raise ValueError(f"{name}: deferred split-K finish needs the fused GroupNorm kernel")
     return [Op(name + ".stats", lib.sfb_group_norm_stats, (C.byref(p),), keep, 0, nb),
             Op(name + ".apply", lib.sfb_group_norm_apply, (C.byref(p),), keep, 0, 2 * nb)]
 

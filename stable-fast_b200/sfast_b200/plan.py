@@ -167,6 +167,8 @@ class UNetPlan:
         self._producers = {}
         self._gn_slots = {}
         self._side_stream = None
+        self._pending = None      # conv GEMM whose split-K finish the next GroupNorm may absorb
+        self._gn_ws_patches = []  # GnParams that read the split-K workspace (pointer known late)
         self._joined = False
         self._bufs = {}
         self._gn_count = 0
@@ -240,6 +242,11 @@ class UNetPlan:
 
     # ------------------------------------------------------------------ op emitters
     def _emit(self, op):
+        # a split-K conv whose finish was tentatively left to the next GroupNorm: anything else
+        # being emitted first means that GroupNorm is not the next consumer -> finish it normally
+        if self._pending is not None:
+            self._pending["p"].defer_finish = 0
+            self._pending = None
         if isinstance(op, (list, tuple)):
             self.ops.extend(op)
         else:
@@ -297,10 +304,21 @@ class UNetPlan:
         slot = self.gn_stats[self._gn_count]
         self._gn_count += 1
         from_producer = self._producer_stats(x, slot)
-        self._emit(ops.gn_ops(name, self.lib_or_dry(), x=x, y=y, gamma=self.w.f32(prefix + ".weight"),
-                              beta=self.w.f32(prefix + ".bias"), stats=slot, sync=slot[-4:],
-                              groups=self.spec.groups, eps=eps, silu=silu, dt=self.dt,
-                              dry=self.dry, stats_ready=from_producer))
+        partial, pend = None, self._pending
+        if pend is not None:
+            d = pend["dst"]
+            if (not from_producer and d.buf is x.buf and d.off == x.off and d.c <= x.c and
+                    (d.n, d.h, d.w) == (x.n, x.h, x.w) and
+                    ops.gn_fused_ok(self.lib_or_dry(), x, self.spec.groups, self.dt, self.dry)):
+                partial = pend["info"]
+                self._pending = None  # absorbed: the GEMM keeps defer_finish = 1
+        gn = ops.gn_ops(name, self.lib_or_dry(), x=x, y=y, gamma=self.w.f32(prefix + ".weight"),
+                        beta=self.w.f32(prefix + ".bias"), stats=slot, sync=slot[-4:],
+                        groups=self.spec.groups, eps=eps, silu=silu, dt=self.dt,
+                        dry=self.dry, stats_ready=from_producer, partial=partial)
+        if partial is not None:
+            self._gn_ws_patches.append(gn[0].keep[0])
+        self._emit(gn)
         return y
 
     def conv3x3(self, name, x: Act, wname, dst: Act, stride=1, rowbias=None, residual: Act = None):
@@ -321,6 +339,17 @@ class UNetPlan:
         op = self._gemm(name, **kw)
         self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
         self._emit(op)
+        gp = op.keep[0]
+        if (gp.splits > 1 and not gp.cluster_k and not gp.split_sync and
+                os.environ.get("SFB_GN_FINISH", "1") != "0" and os.environ.get("SFB_GN_EPILOGUE", "0") == "0"):
+            # tentatively leave the split-K reduction to the GroupNorm that consumes dst next
+            gp.defer_finish = 1
+            info = dict(splits=gp.splits, c=cout, ld=cout, bias=kw["bias"])
+            if rowbias is not None:
+                info.update(rowbias=rowbias[0], ld_rowbias=rowbias[1])
+            if residual is not None:
+                info.update(residual=residual.ptr, ldr=residual.ld, res_buf=residual.buf)
+            self._pending = dict(p=gp, dst=dst, info=info)
 
     def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None, rowstats_out=None,
                splits=None):
@@ -337,6 +366,9 @@ class UNetPlan:
     def resnet(self, r, x: Act, dst: Act):
         p = r.prefix
         fork = None
+        # norm1 first: it may be the kernel that finishes x (deferred split-K reduction of the
+        # conv that produced it), so every other reader of x is ordered after it
+        a1 = self.group_norm(p + ".norm1", x, p + ".norm1", True, self.spec.eps)
         if r.has_shortcut and os.environ.get("SFB_SIDE_SHORTCUT", "1") != "0":
             # the 1x1 shortcut only needs the block input: parallel graph branch next to
             # norm1 / conv1 / norm2 (most of these launches leave SMs idle at small batch)
@@ -347,7 +379,6 @@ class UNetPlan:
             fork = _ForkOp(self.ops[n0:])
             del self.ops[n0:]
             self._emit(fork)
-        a1 = self.group_norm(p + ".norm1", x, p + ".norm1", True, self.spec.eps)
         h1 = self.act("res_h1", x.n, x.h, x.w, r.cout)
         rb_ptr = _ptr(self.temb_proj) + 4 * self.w.tproj_off[p]
         self.conv3x3(p + ".conv1", a1, p + ".conv1", h1, rowbias=(rb_ptr, self.w.tproj_total))
@@ -626,6 +657,9 @@ class UNetPlan:
                        y.ld, ops.dtype_code(self.dt)), (y.buf, w_out, self.out),
                       2 * B * H * W * c0 * 9 * spec.out_channels))
         assert self._gn_count == self.gn_stats.shape[0], (self._gn_count, self.gn_stats.shape)
+        if self._pending is not None:  # nothing consumed the last deferred reduction
+            self._pending["p"].defer_finish = 0
+            self._pending = None
         # ---- split-K workspace: allocate once at the largest requirement and patch the ops
         self._ws_token.finalize(self)
 
@@ -703,6 +737,8 @@ class _WsToken:
                 op.keep[0].ws = _ptr(plan.ws)
         # side-stream GEMMs run concurrently with the main chain: they must not share the
         # split-K workspace, so they are never split
+        for gp in plan._gn_ws_patches:
+            gp.part_ws = _ptr(plan.ws)
         forked = [o for op in plan.ops if isinstance(op, _ForkOp) for o in op.branch]
         for op in plan.side_ops + forked:
             if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:

@@ -224,6 +224,65 @@ def check_group_norm(n=2, c=320, h=32, w=32, silu=True, dt=torch.float16, pitch_
     return rel_err(yb, ref.permute(0, 2, 3, 1))
 
 
+def check_gn_finish(n=2, h=16, w=16, cin=1280, cout=1280, extra=0, splits=4, rowbias=True,
+                    residual=True, silu=True, dt=torch.float16, seed=21):
+    """Split-K conv launched with defer_finish + fused GroupNorm that sums the fp32 partials,
+    applies the conv's bias / time-embedding row bias / residual, writes the finished activation
+    and normalises it -- against conv -> (+adds) -> GroupNorm(+SiLU) in fp32.  `extra` channels of
+    the GroupNorm input come from an ordinary tensor slice (the zero-copy skip concat)."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    xin = _rand(n, h, w, cin, dt=dt)
+    wt = _rand(cout, cin, 3, 3, dt=dt, scale=1 / math.sqrt(9 * cin))
+    b = torch.randn(cout, device=DEV)
+    M = n * h * w
+    rb = torch.randn(n, cout, device=DEV) if rowbias else None
+    r = _rand(M, cout, dt=dt) if residual else None
+    C = cout + extra
+    cat = _rand(n, h, w, C, dt=dt)          # [conv output slice | skip slice]
+    skip_ref = cat[..., cout:].clone()
+    cat[..., :cout] = 7.0                     # must be overwritten by the GroupNorm kernel
+    box_n, box_h = ops.conv_tile_box(h, w)
+    adesc = ops.a_conv(xin.data_ptr(), n, h, w, cin, cin, box_n, box_h, w, 1)
+    ws = torch.empty(splits * M * cout, device=DEV, dtype=torch.float32)
+    conv = ops.gemm_op("conv", lib, a=adesc, b=ops.Mat(ops.pack_conv3x3(wt, dt)), M=M, N=cout, K=9 * cin,
+                       dt=dt, out=cat.data_ptr(), ldo=C, bias=b, rowbias=rb, rows_per_img=h * w,
+                       ld_rowbias=cout, residual=r, ldr=cout, ws=ws, splits=splits, cluster_k=False,
+                       conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=box_n, box_h=box_h))
+    assert conv.keep[0].splits == splits
+    conv.keep[0].defer_finish = 1
+    x = Act(cat, n, h, w, C)
+    yb = torch.zeros(n, h, w, C, device=DEV, dtype=dt)
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    stats = torch.zeros(n * 32 * 2 + 4, device=DEV)
+    part = dict(splits=splits, c=cout, ld=cout, bias=b, ws=ws)
+    if rowbias:
+        part.update(rowbias=rb.data_ptr(), ld_rowbias=cout)
+    if residual:
+        part.update(residual=r.data_ptr(), ldr=cout)
+    gops = ops.gn_ops("gn", lib, x=x, y=Act(yb, n, h, w, C), gamma=gamma, beta=beta, stats=stats,
+                      groups=32, eps=1e-5, silu=silu, dt=dt, sync=stats[-4:], partial=part)
+    assert len(gops) == 1
+    n0 = lib.sfb_launch_count()
+    conv.launch(_stream())
+    assert lib.sfb_launch_count() - n0 == 1, "deferred finish must not launch the reduction kernel"
+    gops[0].launch(_stream())
+    torch.cuda.synchronize()
+    ref = F.conv2d(xin.permute(0, 3, 1, 2).float(), wt.float(), b, padding=1)
+    if rowbias:
+        ref = ref + rb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1)
+    if residual:
+        ref = ref + r.float().view(n, h, w, cout)
+    e_x = rel_err(cat[..., :cout], ref)
+    assert torch.equal(cat[..., cout:], skip_ref)
+    full = torch.cat([cat[..., :cout].float(), skip_ref.float()], -1)  # what the kernel normalised
+    gref = F.group_norm(full.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)
+    if silu:
+        gref = F.silu(gref)
+    return max(e_x, rel_err(yb, gref.permute(0, 2, 3, 1)))
+
+
 def check_layer_norm(rows=1151, c=1280, dt=torch.float16, seed=6):
     lib = _lib.lib()
     x = _rand(rows, c, dt=dt, seed=seed)
@@ -463,6 +522,13 @@ CHECKS = {
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
     "gemm_splitk_finish_kernel": (lambda: check_gemm(256, 1280, 5120, splits=8, fused_reduce=False), 2e-3),
     "gemm_splitk_18": (lambda: check_gemm(128, 1280, 11520, splits=18), 2e-3),
+    "gn_finish_16": (lambda: check_gn_finish(2, 16, 16, 1280, 1280, splits=4), 3e-3),
+    "gn_finish_8_s13": (lambda: check_gn_finish(2, 8, 8, 1280, 1280, splits=13), 3e-3),
+    "gn_finish_concat": (lambda: check_gn_finish(2, 16, 16, 1280, 1280, extra=640, splits=4, rowbias=False), 3e-3),
+    "gn_finish_32_s2": (lambda: check_gn_finish(2, 32, 32, 640, 640, extra=320, splits=2, residual=False), 3e-3),
+    "gn_finish_plain": (lambda: check_gn_finish(1, 16, 16, 640, 1280, splits=3, rowbias=False, residual=False,
+                                                silu=False), 3e-3),
+    "gn_finish_bf16": (lambda: check_gn_finish(2, 16, 16, 1280, 1280, splits=4, dt=torch.bfloat16), 2e-2),
     "gemm_fused_s2": (lambda: check_gemm(512, 1280, 1280, splits=2), 2e-3),
     "gemm_fused_s4_pair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=True), 2e-3),
     "gemm_fused_s4_nopair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=False), 2e-3),

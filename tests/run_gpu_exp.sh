@@ -5,12 +5,10 @@ timeout 900 python tests/kernel_checks.py > gpurun_out/kernel_checks.jsonl 2> gp
 echo "checks rc=$?" >> gpurun_out/kernel_checks.jsonl
 grep -c '"pass": true' gpurun_out/kernel_checks.jsonl; grep -v '"pass": true' gpurun_out/kernel_checks.jsonl | cut -c1-400
 tail -5 gpurun_out/kernel_checks.err
-B="timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-roofline"
-echo "== default (side shortcut on)"; $B 2>>gpurun_out/bench.err | tee gpurun_out/bench_side1.json | cut -c1-330
-echo "== side shortcut off"; SFB_SIDE_SHORTCUT=0 $B 2>>gpurun_out/bench.err | tee gpurun_out/bench_side0.json | cut -c1-330
-echo "== B16 default"; $B --batch 16 --steps 20 2>>gpurun_out/bench.err | tee gpurun_out/bench_b16.json | cut -c1-330
-echo "== full default"; timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --dump-ops gpurun_out/ops_b2.jsonl 2>>gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-2600
-tail -5 gpurun_out/bench.err
-timeout 300 python tests/graph_breakdown.py 2 > gpurun_out/breakdown_b2.jsonl 2>gpurun_out/breakdown.err; head -40 gpurun_out/breakdown_b2.jsonl; tail -2 gpurun_out/breakdown_b2.jsonl
-timeout 300 python tests/gemm_latency.py > gpurun_out/gemm_latency_conv.jsonl 2>gpurun_out/gemm_latency.err; cut -c1-520 gpurun_out/gemm_latency_conv.jsonl; tail -3 gpurun_out/gemm_latency.err
 timeout 900 python -m pytest tests/test_unet_gpu.py -m gpu -q -x 2>&1 | tail -4
+B="timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-roofline"
+echo "== default (gn finish on)"; $B 2>>gpurun_out/bench.err | tee gpurun_out/bench_gf1.json | cut -c1-330
+echo "== gn finish off"; SFB_GN_FINISH=0 $B 2>>gpurun_out/bench.err | tee gpurun_out/bench_gf0.json | cut -c1-330
+echo "== B16 default"; $B --batch 16 --steps 20 2>>gpurun_out/bench.err | tee gpurun_out/bench_b16.json | cut -c1-330
+tail -5 gpurun_out/bench.err
+timeout 300 python tests/graph_breakdown.py 2 > gpurun_out/breakdown_b2.jsonl 2>gpurun_out/breakdown.err; head -14 gpurun_out/breakdown_b2.jsonl; tail -2 gpurun_out/breakdown_b2.jsonl

@@ -162,12 +162,29 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert b"sfb_gemm" in lib.sfb_last_error()
 
 
-def test_struct_layouts_match_the_header():
-    # sizes computed by hand from include/sfb200.h with natural alignment
-    assert ctypes.sizeof(_lib.AttnParams) == 4 * 8 + 10 * 4
-    assert ctypes.sizeof(_lib.LnParams) == 4 * 8 + 6 * 4
-    assert ctypes.sizeof(_lib.GnParams) == 5 * 8 + 9 * 4 + 4 + 8 + 2 * 4
-    assert ctypes.sizeof(_lib.SmallLinearParams) == 6 * 8 + 8 * 4
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every parameter struct as gcc lays out include/sfb200.h must equal the
+    ctypes mirror in _lib.py (field for field)."""
+    import subprocess
+    structs = {"sfb_gemm_params": _lib.GemmParams, "sfb_attn_params": _lib.AttnParams,
+               "sfb_gn_params": _lib.GnParams, "sfb_ln_params": _lib.LnParams,
+               "sfb_small_linear_params": _lib.SmallLinearParams}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sfb200.h"\nint main(void) {\n'
+                   + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = dict(line.split() for line in out.strip().splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
 
 
 def test_random_state_dict_is_seeded_and_complete():
