@@ -274,6 +274,7 @@ def run_b200(args, rank, world, local):
 
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
 
+    weight_gb = sum(int(torch.Size(sh).numel()) for sh in param_shapes(spec).values()) * 2 / 1e9
     total_latents = batch * world if not args.global_batch else args.global_batch
     value = total_latents * args.steps / (ms_dev / 1e3)
     e2e_value = total_latents * args.steps / (ms_e2e / 1e3)
@@ -282,7 +283,7 @@ def run_b200(args, rank, world, local):
 
     roofline = None
     if not args.no_roofline:
-        roofline = measure_roofline(plan, lib, args.dump_ops)
+        roofline = measure_roofline(plan, lib, args.dump_ops, f"{args.model}-b{batch}-s{args.size}")
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, steps=2, warmup=1, budget_s=25.0)
@@ -299,7 +300,7 @@ def run_b200(args, rank, world, local):
             "workload": workload_name(args, batch, ctx_dim),
             "cuda_graph": not args.no_graph,
             "global_batch": total_latents, "parallelism": f"dp{world}",
-            "l2": "inputs larger than L2: the 1.72 GB fp16 weight set streams from HBM every step",
+            "l2": f"inputs larger than L2: the {weight_gb:.2f} GB 16-bit weight set streams from HBM every step",
             "sd15_20step_unet_ms_per_img": 20 * ms_step if (args.model == "sd15" and batch == 2) else None,
             "algorithmic_tflop_per_step": plan.flops() / 1e12,
         },
@@ -314,7 +315,7 @@ def run_b200(args, rank, world, local):
     print(json.dumps(line), flush=True)
 
 
-def ncu_traffic(prefix):
+def ncu_traffic(prefix, workload=None):
     """DRAM bytes per launch of the kernel family, from the committed ncu launch list of this same
     command (profiles/rNN_ncu_launch_summary.json, made by tests/summarize_ncu.py; ncu flushes the
     caches before every kernel, so this is cold-cache traffic)."""
@@ -323,6 +324,8 @@ def ncu_traffic(prefix):
     if not files:
         return {"traffic": None}
     d = json.load(open(files[-1]))
+    if workload is not None and d.get("workload") != workload:
+        return {"traffic": None, "traffic_note": f"no ncu launch list committed for {workload}"}
     n = b = 0
     for name, f in d.get("families", {}).items():
         if name.startswith(prefix) and "dram_bytes_per_launch" in f:
@@ -334,7 +337,7 @@ def ncu_traffic(prefix):
             "traffic_source": os.path.relpath(files[-1], ROOT)}
 
 
-def measure_roofline(plan, lib, dump_path=""):
+def measure_roofline(plan, lib, dump_path="", workload=None):
     """Per-op CUDA-event timing of one eager pass over the plan (after the timed region).  The
     dominant kernel is the tcgen05 GEMM / implicit-GEMM conv; its roofline is the tensor pipe."""
     stream = torch.cuda.current_stream()
@@ -404,7 +407,7 @@ def measure_roofline(plan, lib, dump_path=""):
             "launches_per_step": g["n"], "avg_launch_us": gemm_graph_ms * 1e3 / max(g["n"], 1),
             "timing": "all sfb_gemm launches of one step replayed as a CUDA graph, CUDA events, 10 replays",
             "avg_launch_us_eager_events": g["ms"] * 1e3 / max(g["n"], 1),
-            "flop_per_step": g["flops"], **ncu_traffic("gemm_tc_kernel"),
+            "flop_per_step": g["flops"], **ncu_traffic("gemm_tc_kernel", workload),
             "eager_step_ms": total_ms, "time_share_by_entry_point": shares, **extra}
 
 

@@ -93,6 +93,8 @@ struct GemmArgs {
     float* ws;
     // conv geometry
     int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
+    int up_tiles;   // SFB_A_UPCONV2X: M tiles per output phase
+    int up_ntiles;  // ... and N tiles per phase in the phase-concatenated weight matrix
     // thread-block cluster (cx along N: the cx CTAs of one M-tile each load 1/cx of the A tile and
     // multicast it; cy along M: the cy CTAs of one N-tile each load 1/cy of the weight tile)
     int cx, cy;
@@ -222,6 +224,11 @@ __device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r
         m = tile * BM + r;
         return m < a.e.M;
     }
+    int phase = 0;
+    if (a.a_mode == SFB_A_UPCONV2X) {
+        phase = tile / a.up_tiles;
+        tile -= phase * a.up_tiles;
+    }
     int n0, h0;
     if (a.box_n == 1) {
         n0 = tile / a.tiles_per_img;
@@ -235,7 +242,10 @@ __device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r
     const int dh = t % a.box_h;
     const int dn = t / a.box_h;
     const int n = n0 + dn, h = h0 + dh;
-    m = (n * a.img_h + h) * a.img_w + w;
+    if (a.a_mode == SFB_A_UPCONV2X)  // source pixel (h, w) -> output pixel (2h + py, 2w + px)
+        m = (n * 2 * a.img_h + 2 * h + (phase >> 1)) * 2 * a.img_w + 2 * w + (phase & 1);
+    else
+        m = (n * a.img_h + h) * a.img_w + w;
     return (n < a.img_n) && (h < a.img_h);
 }
 
@@ -469,14 +479,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) {
             pdl_wait();
             int n0 = 0, h0 = 0;
-            if (args.a_mode == SFB_A_CONV3X3) {
+            // up-conv: output phase (py, px) of this M tile; its 2x2 taps sit at source offsets
+            // (py - 1 + ty, px - 1 + tx).  The weight tile comes from the phase's row block.
+            int up_py = 0, up_px = 0, b_ntile = n_tile;
+            if (args.a_mode != SFB_A_MATRIX) {
+                int mt = m_tile;
+                if (args.a_mode == SFB_A_UPCONV2X) {
+                    const int ph = m_tile / args.up_tiles;
+                    mt = m_tile - ph * args.up_tiles;
+                    up_py = ph >> 1; up_px = ph & 1;
+                    b_ntile = ph * args.up_ntiles + n_tile;
+                }
                 if (args.box_n == 1) {
-                    n0 = m_tile / args.tiles_per_img;
-                    h0 = (m_tile - n0 * args.tiles_per_img) * args.box_h;
+                    n0 = mt / args.tiles_per_img;
+                    h0 = (mt - n0 * args.tiles_per_img) * args.box_h;
                 } else {
-                    n0 = m_tile * args.box_n;
+                    n0 = mt * args.box_n;
                 }
             }
+            // conv tap of K block kb -> (w, h) source offset of the A box
+            auto tap_offset = [&](int tap, int& dw, int& dh) {
+                if (args.a_mode == SFB_A_UPCONV2X) {
+                    const int ty = tap >> 1, tx = tap & 1;
+                    dw = up_px - 1 + tx;
+                    dh = up_py - 1 + ty;
+                } else {
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    dw = kw - 1;
+                    dh = kh - 1;
+                }
+            };
             for (int i = 0; i < nkb; ++i) {
                 const int stage = i % STAGES;
                 const uint32_t phase = (i / STAGES) & 1;
@@ -487,15 +519,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
                     uint8_t* dA = sA + stage * L::kABytes;
                     uint8_t* dB = sB + stage * L::kBBytes;
-                    const int b_row2 = (n_tile * args.nkb_total + kb) * BN + ciy * (BN / 2);
+                    const int b_row2 = (b_ntile * args.nkb_total + kb) * BN + ciy * (BN / 2);
                     if (args.a_mode == SFB_A_MATRIX) {
                         tma_load_2d_pair(dA, &tma_a, &full_bar[stage], kb * BK, m_tile * BM);
                     } else {
                         const int tap = kb / args.cpb;
                         const int cc = kb - tap * args.cpb;
-                        const int kh = tap / 3, kw = tap - kh * 3;
-                        tma_load_4d_pair(dA, &tma_a, &full_bar[stage], cc * BK, kw - 1,
-                                         h0 * args.conv_stride + kh - 1, n0);
+                        int dw, dh;
+                        tap_offset(tap, dw, dh);
+                        tma_load_4d_pair(dA, &tma_a, &full_bar[stage], cc * BK, dw,
+                                         h0 * args.conv_stride + dh, n0);
                     }
                     tma_load_2d_pair(dB, &tma_b, &full_bar[stage], 0, b_row2);
                     continue;
@@ -504,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 uint8_t* dstA = sA + stage * L::kABytes + cix * (L::kABytes / args.cx);
                 uint8_t* dstB = sB + stage * L::kBBytes + ciy * (L::kBBytes / args.cy);
                 // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous BN x 64 block
-                const int b_row = (n_tile * args.nkb_total + kb) * BN + ciy * (BN / args.cy);
+                const int b_row = (b_ntile * args.nkb_total + kb) * BN + ciy * (BN / args.cy);
                 if (args.a_mode == SFB_A_MATRIX) {
                     const int a_row = m_tile * BM + cix * (BM / args.cx);
                     if (args.cx > 1) tma_load_2d_mc(dstA, &tma_a, &full_bar[stage], kb * BK, a_row, mask_a);
@@ -512,8 +545,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 } else {
                     const int tap = kb / args.cpb;
                     const int cc = kb - tap * args.cpb;
-                    const int kh = tap / 3, kw = tap - kh * 3;
-                    int c1 = kw - 1, c2 = h0 * args.conv_stride + kh - 1, c3 = n0;
+                    int dw, dh;
+                    tap_offset(tap, dw, dh);
+                    int c1 = dw, c2 = h0 * args.conv_stride + dh, c3 = n0;
                     if (args.cx > 1) {
                         const int off = cix * args.a_part_ext;
                         if (args.a_part_dim == 1) c1 += off * args.conv_stride;
@@ -1033,20 +1067,28 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     if (a.splits > 1 && !a.cluster_k && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
     a.ws = p->ws;
     int m_tiles;
-    if (p->a_mode == SFB_A_CONV3X3) {
-        if (p->cin <= 0 || p->cin % BK || p->K != 9 * p->cin)
+    const bool upconv = p->a_mode == SFB_A_UPCONV2X;
+    if (p->a_mode == SFB_A_CONV3X3 || upconv) {
+        if (p->cin <= 0 || p->cin % BK || p->K != (upconv ? 4 : 9) * p->cin)
             return fail(SFB_ERR_INVALID, "sfb_gemm: conv cin=%d K=%d", p->cin, p->K);
         if (p->box_n * p->box_h * p->img_w != BM)
             return fail(SFB_ERR_INVALID, "sfb_gemm: conv M-tile box %dx%dx%d != 128", p->box_n, p->box_h, p->img_w);
         if (p->box_n > 1 && p->box_h != p->img_h)
             return fail(SFB_ERR_INVALID, "sfb_gemm: multi-image box needs box_h == img_h");
-        if (p->M != p->img_n * p->img_h * p->img_w) return fail(SFB_ERR_INVALID, "sfb_gemm: conv M mismatch");
+        if (p->M != (upconv ? 4 : 1) * p->img_n * p->img_h * p->img_w) return fail(SFB_ERR_INVALID, "sfb_gemm: conv M mismatch");
+        if (upconv && (p->conv_stride != 1 || p->epi != SFB_EPI_STORE || p->cluster_n > 1 || p->cluster_m > 1))
+            return fail(SFB_ERR_INVALID, "sfb_gemm: up-conv needs stride 1, the STORE epilogue and no multicast cluster");
         a.img_n = p->img_n; a.img_h = p->img_h; a.img_w = p->img_w;
         a.cpb = p->cin / BK;
         a.conv_stride = p->conv_stride;
         a.box_h = p->box_h; a.box_n = p->box_n;
         a.tiles_per_img = (p->img_h + p->box_h - 1) / p->box_h;
         m_tiles = (p->box_n == 1) ? p->img_n * a.tiles_per_img : (p->img_n + p->box_n - 1) / p->box_n;
+        if (upconv) {  // 4 output phases, each its own set of M tiles and its own weight row block
+            a.up_tiles = m_tiles;
+            a.up_ntiles = (p->N + BN - 1) / BN;
+            m_tiles *= 4;
+        }
     } else if (p->a_mode == SFB_A_MATRIX) {
         m_tiles = (p->M + BM - 1) / BM;
     } else {
@@ -1117,8 +1159,8 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     int rc;
     if (p->cta_pair) {
         // CTA pairs along M (cluster 1x2, tcgen05.mma.cta_group::2): tmap_b box = 80 rows
-        if (grid.y % 2 || a.cx != 1 || a.cy != 1)
-            return fail(SFB_ERR_INVALID, "sfb_gemm: cta_pair needs an even number of M tiles and no multicast cluster");
+        if (grid.y % 2 || a.cx != 1 || a.cy != 1 || (upconv && a.up_tiles % 2))
+            return fail(SFB_ERR_INVALID, "sfb_gemm: cta_pair needs an even number of M tiles (per up-conv phase) and no multicast cluster");
         const dim3 pgrid(grid.y, grid.x, grid.z);  // M tiles along x: pairs are x-neighbours
         rc = deep ? launch_gemm<BN, 8, 2>(ta, tb, a, pgrid, stream) : launch_gemm<BN, 4, 2>(ta, tb, a, pgrid, stream);
     } else {

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SFB_LIB_PATH") or os.path.join(_HERE, "libsfb200.so")
 
 SFB_F16, SFB_BF16 = 0, 1
-A_MATRIX, A_CONV3X3 = 0, 1
+A_MATRIX, A_CONV3X3, A_UPCONV2X = 0, 1, 2
 EPI_STORE, EPI_GEGLU, EPI_QKV = 0, 1, 2
 
 

@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (A_CONV3X3, A_MATRIX, EPI_GEGLU, EPI_QKV, EPI_STORE, AttnParams, GemmParams,
+from ._lib import (A_CONV3X3, A_MATRIX, A_UPCONV2X, EPI_GEGLU, EPI_QKV, EPI_STORE, AttnParams, GemmParams,
                    GnParams, LnParams, SmallLinearParams, TensorMap, check)
 
 BM, BN, BK = 128, 160, 64
@@ -215,7 +215,7 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         p.cluster_n, p.cluster_m = cn, cm
         keep = tuple(keep) + (b,)
     p.tmap_a, p.tmap_b = a_map.ptr, b_map.ptr
-    p.a_mode = A_CONV3X3 if conv else A_MATRIX
+    p.a_mode = (A_UPCONV2X if conv.get("up") else A_CONV3X3) if conv else A_MATRIX
     p.M, p.N, p.K, p.dtype = M, N, K, dtype_code(dt)
     if conv:
         p.img_n, p.img_h, p.img_w = conv["n"], conv["h"], conv["w"]
@@ -225,6 +225,8 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
             m_tiles = p.img_n * ((p.img_h + p.box_h - 1) // p.box_h)
         else:
             m_tiles = (p.img_n + p.box_n - 1) // p.box_n
+        if conv.get("up"):
+            m_tiles *= 4  # one set of M tiles per output phase
     else:
         m_tiles = (M + BM - 1) // BM
     n_tiles = (N + BN - 1) // BN
@@ -404,6 +406,33 @@ class Mat:
 def pack_conv3x3(w, dt):
     """[cout, cin, 3, 3] -> K-major [cout, (kh, kw, cin)]"""
     return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dt).contiguous()
+
+
+# 3x3 taps of the upsampled image that read the same source pixel: S[(phase, tap)]
+_UP_TAPS = {(0, 0): (0,), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2,)}
+
+
+def pack_upconv(w, dt):
+    """Nearest-2x upsample + conv3x3 as four 2x2 convolutions on the source image (one per output
+    phase (py, px)): [cout, cin, 3, 3] -> [4 * Np, 4 * cin], Np = cout rounded up to 160, phase p =
+    2*py + px in rows [p*Np, p*Np + cout), K order (ty, tx, cin).  Tap (ty, tx) of phase (py, px)
+    reads source offset (py-1+ty, px-1+tx) and carries the SUM (in fp32) of the 3x3 weights whose
+    upsampled-image taps fall on that source pixel."""
+    cout, cin = w.shape[0], w.shape[1]
+    npad = (cout + BN - 1) // BN * BN
+    if w.device.type == "meta":
+        return torch.empty(4 * npad, 4 * cin, dtype=dt, device="meta")
+    wf = w.detach().float()
+    out = torch.zeros(4 * npad, 4 * cin, dtype=torch.float32, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            r0 = (2 * py + px) * npad
+            for ty in range(2):
+                for tx in range(2):
+                    acc = sum(wf[:, :, kh, kw] for kh in _UP_TAPS[(py, ty)] for kw in _UP_TAPS[(px, tx)])
+                    c0 = (2 * ty + tx) * cin
+                    out[r0:r0 + cout, c0:c0 + cin] = acc
+    return out.to(dt).contiguous()
 
 
 def pack_conv_in(w, dt):

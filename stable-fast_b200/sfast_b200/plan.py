@@ -78,6 +78,14 @@ class PackedWeights:
             self._cache[key] = self._mat(ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype))
         return self._cache[key]
 
+    def upconv(self, name):
+        """Upsampler conv as the 4-phase 2x2 formulation (ops.pack_upconv): (Mat, cout)."""
+        key = ("up", name)
+        if key not in self._cache:
+            w = self._raw(name)
+            self._cache[key] = (self._mat(ops.pack_upconv(w.to(self.device), self.dtype)), w.shape[0])
+        return self._cache[key]
+
     def conv3x3_plain(self, name):
         key = ("c3p", name)
         if key not in self._cache:
@@ -339,17 +347,36 @@ class UNetPlan:
         op = self._gemm(name, **kw)
         self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
         self._emit(op)
-        gp = op.keep[0]
+        self._maybe_defer_finish(op.keep[0], dst, cout, kw["bias"], rowbias, residual)
+
+    def _maybe_defer_finish(self, gp, dst, cout, bias, rowbias=None, residual=None):
+        """Tentatively leave a conv's split-K reduction to the GroupNorm that consumes dst next."""
         if (gp.splits > 1 and not gp.cluster_k and not gp.split_sync and
                 os.environ.get("SFB_GN_FINISH", "1") != "0" and os.environ.get("SFB_GN_EPILOGUE", "0") == "0"):
-            # tentatively leave the split-K reduction to the GroupNorm that consumes dst next
             gp.defer_finish = 1
-            info = dict(splits=gp.splits, c=cout, ld=cout, bias=kw["bias"])
+            info = dict(splits=gp.splits, c=cout, ld=cout, bias=bias)
             if rowbias is not None:
                 info.update(rowbias=rowbias[0], ld_rowbias=rowbias[1])
             if residual is not None:
                 info.update(residual=residual.ptr, ldr=residual.ld, res_buf=residual.buf)
             self._pending = dict(p=gp, dst=dst, info=info)
+
+    def upconv3x3(self, name, x: Act, wname, dst: Act):
+        """nearest-2x upsample + conv3x3 of `x` -> dst ([n, 2h, 2w, cout]) without materialising
+        the upsampled tensor: four 2x2 convolutions on x (one per output phase), 4/9 of the MACs."""
+        wm, cout = self.w.upconv(wname + ".weight")
+        box_n, box_h = ops.conv_tile_box(x.h, x.w)
+        adesc = ops.a_conv(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, x.w, 1)
+        M = 4 * x.n * x.h * x.w
+        bias = self.w.f32(wname + ".bias")
+        op = self._gemm(name, a=adesc, b=wm, M=M, N=cout, K=4 * x.c, dt=self.dt, out=dst.ptr,
+                        ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, wm),
+                        conv=dict(n=x.n, h=x.h, w=x.w, cin=x.c, stride=1, box_n=box_n, box_h=box_h,
+                                  up=True))
+        op.flops = 2 * M * cout * 9 * x.c  # algorithmic count of the reference formulation
+        self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
+        self._emit(op)
+        self._maybe_defer_finish(op.keep[0], dst, cout, bias)
 
     def linear(self, name, x: Act, wm, bias, dst: Act, residual: Act = None, rowstats_out=None,
                splits=None):
@@ -640,7 +667,9 @@ class UNetPlan:
                     self.resnet(r, xin, mid)
                     self.transformer(t, mid, dst)
                 x = dst
-            if blk.sampler:
+            if blk.sampler and os.environ.get("SFB_UPCONV", "1") != "0":
+                self.upconv3x3(blk.sampler, x, blk.sampler, up_in[(i + 1, 0)][1])
+            elif blk.sampler:
                 up = self.act("upsampled", x.n, 2 * x.h, 2 * x.w, x.c)
                 self._emit(Op(blk.sampler + ".nearest2x", lib.sfb_upsample2x,
                               (x.ptr, up.ptr, x.n,

@@ -130,6 +130,34 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
     return rel_err(out, ref)
 
 
+def check_upconv(n=2, h=16, w=16, cin=640, cout=640, dt=torch.float16, splits=None, pair=None,
+                 out_extra=0, seed=23):
+    """nearest-2x upsample + conv3x3 as the 4-phase 2x2 implicit GEMM on the low-res image vs
+    F.conv2d(F.interpolate(x, 2, 'nearest')) in fp32 (weights as packed: sums rounded to 16 bit)."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    xin = _rand(n, h, w, cin, dt=dt)
+    wt = _rand(cout, cin, 3, 3, dt=dt, scale=1 / math.sqrt(9 * cin))
+    b = torch.randn(cout, device=DEV)
+    M = 4 * n * h * w
+    ld = cout + out_extra
+    out = torch.zeros(n, 2 * h, 2 * w, ld, device=DEV, dtype=dt)
+    box_n, box_h = ops.conv_tile_box(h, w)
+    adesc = ops.a_conv(xin.data_ptr(), n, h, w, cin, cin, box_n, box_h, w, 1)
+    ws = torch.empty(32 * M * cout, device=DEV, dtype=torch.float32) if splits != 1 else None
+    op = ops.gemm_op("upconv", lib, a=adesc, b=ops.Mat(ops.pack_upconv(wt, dt)), M=M, N=cout, K=4 * cin,
+                     dt=dt, out=out.data_ptr(), ldo=ld, bias=b, ws=ws, splits=splits, cta_pair=pair,
+                     cluster_k=False,
+                     conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=box_n, box_h=box_h, up=True))
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    up = F.interpolate(xin.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, wt.float(), b, padding=1).permute(0, 2, 3, 1)
+    if out_extra:
+        assert float(out[..., cout:].abs().max()) == 0.0
+    return rel_err(out[..., :cout], ref)
+
+
 def _attn_buffers(B, H, S, Skv, D, dt):
     dv = (D + 1 + 15) // 16 * 16  # + the all-ones row (softmax denominator on the tensor core)
     q_pitch = (D + 63) // 64 * 64
@@ -522,6 +550,12 @@ CHECKS = {
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
     "gemm_splitk_finish_kernel": (lambda: check_gemm(256, 1280, 5120, splits=8, fused_reduce=False), 2e-3),
     "gemm_splitk_18": (lambda: check_gemm(128, 1280, 11520, splits=18), 2e-3),
+    "upconv_32": (lambda: check_upconv(2, 32, 32, 640, 640, splits=1), 3e-3),
+    "upconv_16": (lambda: check_upconv(2, 16, 16, 1280, 1280), 3e-3),
+    "upconv_8_splitk": (lambda: check_upconv(2, 8, 8, 1280, 1280), 3e-3),
+    "upconv_16_nopair_pitch": (lambda: check_upconv(1, 16, 16, 320, 320, pair=False, out_extra=320, splits=1), 3e-3),
+    "upconv_64_bf16": (lambda: check_upconv(1, 64, 64, 320, 320, dt=torch.bfloat16, splits=1), 2e-2),
+    "upconv_4_multi_image": (lambda: check_upconv(8, 4, 4, 256, 256, splits=1), 3e-3),
     "gn_finish_16": (lambda: check_gn_finish(2, 16, 16, 1280, 1280, splits=4), 3e-3),
     "gn_finish_8_s13": (lambda: check_gn_finish(2, 8, 8, 1280, 1280, splits=13), 3e-3),
     "gn_finish_concat": (lambda: check_gn_finish(2, 16, 16, 1280, 1280, extra=640, splits=4, rowbias=False), 3e-3),

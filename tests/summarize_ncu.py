@@ -1,6 +1,6 @@
 """Summarise an `ncu --csv` launch list (gpu__time_duration.sum [+ dram__bytes_*]) per kernel family.
 
-usage: python tests/summarize_ncu.py gpurun_out/launches.csv [steps_captured] > profiles/rNN_ncu_launch_summary.json
+usage: python tests/summarize_ncu.py gpurun_out/launches.csv [steps_captured [model-bB-sS]] > profiles/rNN_ncu_launch_summary.json
 The per-launch DRAM traffic of the dominant kernel feeds bench.py's roofline.traffic.
 """
 import collections
@@ -33,7 +33,8 @@ def main():
         fam = re.sub(r"\(.*", "", fam)
         per[fam][r["Metric Name"]] += to_unit(r["Metric Value"], r["Metric Unit"])
         ids[fam].add(r["ID"])
-    out = {"source": sys.argv[1], "steps_captured": steps, "families": {}}
+    out = {"source": sys.argv[1], "steps_captured": steps, "families": {},
+           "workload": sys.argv[3] if len(sys.argv) > 3 else "sd15-b2-s64"}
     total_us = sum(m["gpu__time_duration.sum"] for m in per.values())
     for fam, m in sorted(per.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
         n = len(ids[fam])

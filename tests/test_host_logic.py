@@ -76,7 +76,10 @@ def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     gemms = [op.keep[0] for op in plan.all_ops() if op.fn is not None and op.fn.name == "sfb_gemm"]
     assert sum(1 for g in gemms if g.ln_rowstats is not None or g.ln_dim > 0) == 48
     assert names.count("sfb_attention") == 32
-    assert names.count("sfb_upsample2x") == 3
+    # nearest-2x upsample + conv3x3 runs as four 2x2 convolutions on the low-res image: the
+    # upsampled tensor is never materialised
+    assert names.count("sfb_upsample2x") == 0
+    assert sum(1 for g in gemms if g.a_mode == _lib.A_UPCONV2X) == 3
     # 98 convs + 184 GEMMs of the reference collapse to 209 GEMM launches (fused QKV / KV, 22
     # time projections in one small_linear, conv_in as im2col + GEMM, conv_out as an edge kernel)
     assert names.count("sfb_gemm") == 209 and names.count("sfb_im2col_in") == 1
@@ -145,6 +148,29 @@ def test_conv_weight_packing_order():
     assert p.shape == (2, 27)
     # K index = (kh * 3 + kw) * cin + c
     assert p[1, (1 * 3 + 2) * 3 + 1] == w[1, 1, 1, 2]
+
+
+def test_upconv_weight_packing_equals_upsample_then_conv():
+    """ops.pack_upconv: the 4-phase 2x2 formulation reproduces conv3x3(nearest_upsample_2x(x))."""
+    torch.manual_seed(0)
+    cout, cin, h, w = 5, 3, 6, 7
+    wt, x = torch.randn(cout, cin, 3, 3), torch.randn(1, cin, h, w)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest"),
+                                     wt, padding=1)
+    packed = ops.pack_upconv(wt, torch.float32)
+    npad = packed.shape[0] // 4
+    assert packed.shape == (4 * 160, 4 * cin) and npad == 160
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))  # zero padding = TMA out-of-bounds fill
+    out = torch.zeros(1, cout, 2 * h, 2 * w)
+    for py in range(2):
+        for px in range(2):
+            wp = packed[(2 * py + px) * npad:(2 * py + px) * npad + cout].reshape(cout, 2, 2, cin)
+            for ty in range(2):
+                for tx in range(2):
+                    dy, dx = py - 1 + ty, px - 1 + tx
+                    src = xp[:, :, 1 + dy:1 + dy + h, 1 + dx:1 + dx + w]       # x[y + dy, x + dx]
+                    out[:, :, py::2, px::2] += torch.einsum("oc,bchw->bohw", wp[:, ty, tx], src)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
 
 
 def test_c_abi_library_exports_every_declared_symbol():
