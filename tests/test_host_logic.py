@@ -89,6 +89,45 @@ def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     assert sum(1 for k in plan._bufs if k[0].startswith("cat_")) == 12
 
 
+def _check_deferred_finishes(plan):
+    from sfast_b200.plan import _ForkOp, _JoinOp
+    main = [op for op in plan.ops if not isinstance(op, (_ForkOp, _JoinOp))]
+    n_defer = 0
+    for i, op in enumerate(main):
+        if op.fn is not None and op.fn.name == "sfb_gemm" and op.keep[0].defer_finish:
+            g, nxt = op.keep[0], main[i + 1]
+            assert nxt.fn.name == "sfb_group_norm_fused", (op.name, nxt.name)
+            gn = nxt.keep[0]
+            assert gn.part_splits == g.splits > 1 and gn.part_c == g.N and gn.part_ld == g.N
+            assert gn.x == g.out and gn.n * gn.hw == g.M and gn.c >= g.N
+            n_defer += 1
+    gn_part = sum(1 for op in main if op.fn is not None and op.fn.name == "sfb_group_norm_fused"
+                  and op.keep[0].part_splits > 1)
+    assert n_defer == gn_part
+    return n_defer
+
+
+def test_deferred_split_k_finishes_are_absorbed_by_the_next_group_norm():
+    """Every GEMM launched with defer_finish must be IMMEDIATELY followed (main stream order) by a
+    fused GroupNorm that reads its partials with the same split count and channel count; forked
+    branches are joined before the op that consumes them."""
+    from sfast_b200.plan import _ForkOp, _JoinOp
+    plan = _dry_plan(uo.sd15_config(), 2, 64, 64)
+    assert _check_deferred_finishes(plan) == 35
+    # forks: 14 resnet shortcut GEMMs, each joined exactly once, later in the list, never split
+    forks = [i for i, op in enumerate(plan.ops) if isinstance(op, _ForkOp)]
+    assert len(forks) == 14
+    for i in forks:
+        joins = [j for j, op in enumerate(plan.ops) if isinstance(op, _JoinOp) and op.kind is plan.ops[i]]
+        assert len(joins) == 1 and joins[0] > i
+        assert all(o.keep[0].splits == 1 for o in plan.ops[i].branch)
+    # other shapes keep the invariant (large batch: only the small low-resolution tensors still take
+    # the fused GroupNorm; SDXL: deeper transformers, no attention at the top level)
+    _check_deferred_finishes(_dry_plan(uo.sd15_config(), 16, 64, 64))
+    _check_deferred_finishes(_dry_plan(uo.sdxl_config(), 2, 128, 128))
+    _check_deferred_finishes(_dry_plan(uo.sd15_config(), 1, 128, 128))
+
+
 def test_plan_scales_linearly_in_batch_and_handles_128_latents():
     f1 = _dry_plan(uo.sd15_config(), 1, 64, 64).flops()
     f8 = _dry_plan(uo.sd15_config(), 8, 64, 64).flops()
