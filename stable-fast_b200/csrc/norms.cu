@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "host.h"
 
+#include <stdlib.h>
+
 namespace sfb {
 
 constexpr int kGnThreads = 512;
@@ -357,6 +359,135 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
 
 constexpr int kGnFusedMaxSmem = 200 * 1024;
 
+// ---------------------------------------------------------------------------------------
+// GroupNorm with one CTA per (image, group): the group's [hw, cpg] slab (strided 2*cpg-byte
+// segments of the NHWC rows) is pulled into shared memory once, reduced inside the CTA and
+// normalised from shared memory.  No grid barrier, no global atomics, no statistics buffer:
+// the dependent-latency chain of the barrier kernel above (atomics -> fence -> counter -> spin
+// -> statistics reload) disappears, which is what a small-batch step is made of.  Used whenever
+// hw * cpg * 2 bytes fit in shared memory (every SD-1.5 / SDXL GroupNorm at 64x64 latents
+// except the 960-channel concat at full resolution).
+// ---------------------------------------------------------------------------------------
+constexpr int kGnGroupThreads = 512;
+
+// channels (col, col+1) of pixel `px` of image `img` from the producer GEMM's split-K partials
+__device__ __forceinline__ uint32_t gn_finish_partials2(const GnArgs& a, int img, int px, int col) {
+    const int m = img * a.hw + px;
+    const size_t stride = (size_t)a.n * a.hw * a.part_ld;
+    const float* p0 = a.part_ws + (size_t)m * a.part_ld + col;
+    float ax = 0.f, ay = 0.f;
+#pragma unroll 6
+    for (int s = 0; s < a.part_splits; ++s) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(p0 + (size_t)s * stride));
+        ax += v.x; ay += v.y;
+    }
+    if (a.part_bias) { ax += a.part_bias[col]; ay += a.part_bias[col + 1]; }
+    if (a.part_rowbias) {
+        const float* rb = a.part_rowbias + (size_t)img * a.part_ld_rowbias + col;
+        ax += rb[0]; ay += rb[1];
+    }
+    if (a.part_residual) {
+        const float2 r = unpack2(*reinterpret_cast<const uint32_t*>(a.part_residual + (size_t)m * a.part_ldr + col), a.dtype);
+        ax += r.x; ay += r.y;
+    }
+    const uint32_t v = pack2(ax, ay, a.dtype);
+    *reinterpret_cast<uint32_t*>(const_cast<uint16_t*>(a.x) + (size_t)m * a.ldx + col) = v;
+    return v;
+}
+
+template <bool kPart>
+__global__ void __launch_bounds__(kGnGroupThreads) gn_group_kernel(const GnArgs a) {
+    extern __shared__ __align__(16) uint8_t gsm[];
+    uint32_t* slab = reinterpret_cast<uint32_t*>(gsm);  // [hw][cpg / 2] pairs of 16-bit values
+    __shared__ float s_gamma[128], s_beta[128];
+    __shared__ float s_red[2][kGnGroupThreads / 32];
+    __shared__ float s_stat[2];
+    const int g = blockIdx.x, img = blockIdx.y;
+    const int hp = a.cpg >> 1;
+    const int items = a.hw * hp;
+    const int ch0 = g * a.cpg;
+    pdl_launch_dependents();
+    // the affine parameters are weights: fetch them before waiting for the producer kernel
+    for (int i = threadIdx.x; i < a.cpg; i += kGnGroupThreads) {
+        s_gamma[i] = a.gamma[ch0 + i];
+        s_beta[i] = a.beta[ch0 + i];
+    }
+    pdl_wait();
+    const uint16_t* xb = a.x + (size_t)img * a.hw * a.ldx + ch0;
+    float s = 0.f, ss = 0.f;
+    constexpr int kU = kPart ? 2 : 8;  // items whose loads are in flight together
+    for (int i0 = threadIdx.x; i0 < items; i0 += kGnGroupThreads * kU) {
+        uint32_t v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int i = i0 + u * kGnGroupThreads;
+            if (i < items) {
+                const int px = i / hp, pr = i - px * hp;
+                if (kPart && ch0 + 2 * pr < a.part_c)
+                    v[u] = gn_finish_partials2(a, img, px, ch0 + 2 * pr);
+                else
+                    v[u] = *reinterpret_cast<const uint32_t*>(xb + (size_t)px * a.ldx + 2 * pr);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int i = i0 + u * kGnGroupThreads;
+            if (i < items) {
+                slab[i] = v[u];
+                const float2 f = unpack2(v[u], a.dtype);
+                s += f.x + f.y;
+                ss += f.x * f.x + f.y * f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_red[0][warp] = s; s_red[1][warp] = ss; }
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < kGnGroupThreads / 32 ? s_red[0][lane] : 0.f;
+        float tt = lane < kGnGroupThreads / 32 ? s_red[1][lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+            tt += __shfl_xor_sync(0xffffffffu, tt, o);
+        }
+        if (lane == 0) {
+            const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
+            const float mean = t * inv_cnt;
+            const float var = fmaxf(tt * inv_cnt - mean * mean, 0.f);
+            s_stat[0] = mean;
+            s_stat[1] = rsqrtf(var + a.eps);
+        }
+    }
+    __syncthreads();
+    const float mean = s_stat[0], rstd = s_stat[1];
+    uint16_t* yb = a.y + (size_t)img * a.hw * a.ldy + ch0;
+    for (int i = threadIdx.x; i < items; i += kGnGroupThreads) {
+        const int px = i / hp, pr = i - px * hp;
+        const float2 f = unpack2(slab[i], a.dtype);
+        const float sc0 = rstd * s_gamma[2 * pr], sc1 = rstd * s_gamma[2 * pr + 1];
+        float y0 = (f.x - mean) * sc0 + s_beta[2 * pr];
+        float y1 = (f.y - mean) * sc1 + s_beta[2 * pr + 1];
+        if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+        *reinterpret_cast<uint32_t*>(yb + (size_t)px * a.ldy + 2 * pr) = pack2(y0, y1, a.dtype);
+    }
+}
+
+// whether the per-(image, group) kernel applies: the group slab must fit in shared memory
+static bool gn_group_fits(const sfb_gn_params* p, size_t& smem) {
+    static const bool enabled = [] { const char* v = getenv("SFB_GN_GROUP"); return !(v && v[0] == '0'); }();
+    if (!enabled || p->groups <= 0 || p->c % p->groups || p->n <= 0) return false;
+    const int cpg = p->c / p->groups;
+    if (cpg % 2 || cpg > 128 || p->ldx % 2 || p->ldy % 2) return false;
+    smem = (size_t)p->hw * cpg * 2;
+    return smem <= (size_t)kGnFusedMaxSmem;
+}
+
 // grid geometry of the fused kernel; returns false if the tensor does not fit in shared memory
 static bool gn_fused_geometry(const sfb_gn_params* p, int& blocks_per_img, int& rows_per_block,
                               size_t& smem) {
@@ -495,6 +626,7 @@ extern "C" int sfb_group_norm_fused_fits(const sfb_gn_params* p) {
     int bpi, rpb;
     size_t smem;
     if (!p || p->c % 8 || p->c <= 0 || p->groups <= 0 || p->c % p->groups || p->c / 8 > kGnThreads) return 0;
+    if (gn_group_fits(p, smem)) return 1;
     return gn_fused_geometry(p, bpi, rpb, smem) ? 1 : 0;
 }
 
@@ -505,9 +637,10 @@ extern "C" int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream)
     if (rc) return rc;
     if (!p->y || !p->gamma || !p->beta || p->ldy % 8 || !p->sync_counter)
         return fail(SFB_ERR_INVALID, "group_norm_fused: null/ldy/sync_counter");
-    int rpb;
+    int rpb = 0;
     size_t smem;
-    if (!gn_fused_geometry(p, bpi, rpb, smem))
+    const bool per_group = gn_group_fits(p, smem);
+    if (!per_group && !gn_fused_geometry(p, bpi, rpb, smem))
         return fail(SFB_ERR_INVALID, "group_norm_fused: tensor does not fit in shared memory");
     a.rows_per_block = rpb;
     if (p->part_splits > 1) {
@@ -525,8 +658,23 @@ extern "C" int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream)
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kGnFusedMaxSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gn_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kGnFusedMaxSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gn_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kGnFusedMaxSmem);
         if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
+    }
+    if (per_group) {
+        // one CTA per (image, group): no grid barrier, no statistics buffer
+        const dim3 grid(p->groups, p->n);
+        cudaError_t err = a.part_splits > 1
+            ? launch_pdl(gn_group_kernel<true>, grid, dim3(kGnGroupThreads), smem, static_cast<cudaStream_t>(stream), a)
+            : launch_pdl(gn_group_kernel<false>, grid, dim3(kGnGroupThreads), smem, static_cast<cudaStream_t>(stream), a);
+        if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused(per group): %s", cudaGetErrorString(err));
+        return check_launch("sfb_group_norm_fused");
     }
     cudaError_t err = a.part_splits > 1
         ? launch_pdl(gn_fused_kernel<true>, dim3(bpi, p->n), dim3(kGnThreads), smem,

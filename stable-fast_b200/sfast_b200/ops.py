@@ -295,7 +295,13 @@ def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq
 def gn_fused_fits(n, hw, c, groups):
     """Python mirror of sfb_group_norm_fused_fits (used for dry plans; the C predicate is the
     authority on a GPU box)."""
-    if n <= 0 or n > NUM_SMS or c % 8 or c % groups or c // 8 > 512:
+    if n <= 0 or c % 8 or c % groups or c // 8 > 512:
+        return False
+    cpg = c // groups
+    if (os.environ.get("SFB_GN_GROUP", "1") != "0" and cpg % 2 == 0 and cpg <= 128
+            and hw * cpg * 2 <= 200 * 1024):
+        return True  # one CTA per (image, group), slab in shared memory
+    if n > NUM_SMS:
         return False
     bpi = max(1, min(NUM_SMS // n, hw))
     rpb = (hw + bpi - 1) // bpi

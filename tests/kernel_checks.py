@@ -550,6 +550,10 @@ CHECKS = {
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
     "gemm_splitk_finish_kernel": (lambda: check_gemm(256, 1280, 5120, splits=8, fused_reduce=False), 2e-3),
     "gemm_splitk_18": (lambda: check_gemm(128, 1280, 11520, splits=18), 2e-3),
+    "group_norm_960_64_barrier_kernel": (lambda: check_group_norm(2, 960, 64, 64), 1e-2),
+    "group_norm_320_64_b1": (lambda: check_group_norm(1, 320, 64, 64), 1e-2),
+    "group_norm_1280_8_b16": (lambda: check_group_norm(16, 1280, 8, 8, silu=False, eps=1e-6), 1e-2),
+    "group_norm_2560_16_pitch_bf16": (lambda: check_group_norm(2, 2560, 16, 16, dt=torch.bfloat16, pitch_extra=64), 4e-2),
     "upconv_32": (lambda: check_upconv(2, 32, 32, 640, 640, splits=1), 3e-3),
     "upconv_16": (lambda: check_upconv(2, 16, 16, 1280, 1280), 3e-3),
     "upconv_8_splitk": (lambda: check_upconv(2, 8, 8, 1280, 1280), 3e-3),
