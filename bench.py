@@ -168,7 +168,7 @@ def cpu_reference_run(args, steps, warmup, budget_s):
 def run_reference(args, rank):
     if rank != 0:
         return
-    r = cpu_reference_run(args, args.steps, args.warmup, budget_s=150.0)
+    r = cpu_reference_run(args, args.steps, args.warmup, budget_s=100.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"],

@@ -32,6 +32,9 @@ constexpr int BK = 64;
 #ifndef SFB_EPI_WARPS
 #define SFB_EPI_WARPS 8
 #endif
+#ifndef SFB_EPI_PIPELINE
+#define SFB_EPI_PIPELINE 1  // A/B switch: software-pipelined TMEM reads in the epilogue
+#endif
 constexpr int kEpiWarps = SFB_EPI_WARPS;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kColSplit = kEpiWarps / 4;
@@ -685,13 +688,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         float* srow = sStage + r * L::kStagePitch;
         constexpr int kColsPer = BN / kColSplit;             // columns converted per thread
         constexpr int kChunk = kColSplit == 1 ? 32 : 16;     // columns per TMEM load
-#pragma unroll 1
-        for (int cb = 0; cb < kColsPer / kChunk; ++cb) {
-            uint32_t v[kChunk];
-            const int c0 = chalf * kColsPer + cb * kChunk;
-            if constexpr (kChunk == 32) tmem_ld32(trow + c0, v);
-            else tmem_ld16(trow + c0, v);
-            tmem_wait_ld();
+        // accumulator chunk (already in registers) -> bias / LayerNorm fold -> fp32 staging tile
+        auto stage_chunk = [&](const uint32_t* v, int c0) {
 #pragma unroll
             for (int j = 0; j < kChunk / 8; ++j) {
                 const int cl = c0 + j * 8;  // column inside the tile
@@ -708,6 +706,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (rb_global && ncol0 + cl < e.N) add_bias8(rb_global, ncol0 + cl, f);
                 *reinterpret_cast<float4*>(srow + cl) = make_float4(f[0], f[1], f[2], f[3]);
                 *reinterpret_cast<float4*>(srow + cl + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+        };
+        constexpr int kChunks = kColsPer / kChunk;
+        if constexpr (kChunk == 16 && STAGES > 4 && SFB_EPI_PIPELINE) {
+            // one CTA per SM (deep pipeline): registers to spare -> the TMEM load of chunk i+1 is in
+            // flight while chunk i is converted (a single epilogue warp per scheduler hides nothing)
+            uint32_t va[16], vb[16];
+            tmem_ld16(trow + chalf * kColsPer, va);
+#pragma unroll 1
+            for (int cb = 0; cb < kChunks; cb += 2) {
+                const int c0 = chalf * kColsPer + cb * kChunk;
+                tmem_wait_ld16(va);
+                if (cb + 1 < kChunks) tmem_ld16(trow + c0 + kChunk, vb);
+                stage_chunk(va, c0);
+                if (cb + 1 < kChunks) {
+                    tmem_wait_ld16(vb);
+                    if (cb + 2 < kChunks) tmem_ld16(trow + c0 + 2 * kChunk, va);
+                    stage_chunk(vb, c0 + kChunk);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int cb = 0; cb < kChunks; ++cb) {
+                uint32_t v[kChunk];
+                const int c0 = chalf * kColsPer + cb * kChunk;
+                if constexpr (kChunk == 32) tmem_ld32(trow + c0, v);
+                else tmem_ld16(trow + c0, v);
+                tmem_wait_ld();
+                stage_chunk(v, c0);
             }
         }
         epi_bar();

@@ -298,7 +298,7 @@ def gn_fused_fits(n, hw, c, groups):
     if n <= 0 or c % 8 or c % groups or c // 8 > 512:
         return False
     cpg = c // groups
-    if (os.environ.get("SFB_GN_GROUP", "1") != "0" and cpg % 2 == 0 and cpg <= 128
+    if (os.environ.get("SFB_GN_GROUP", "0") == "1" and cpg % 2 == 0 and cpg <= 128
             and hw * cpg * 2 <= 200 * 1024):
         return True  # one CTA per (image, group), slab in shared memory
     if n > NUM_SMS:
