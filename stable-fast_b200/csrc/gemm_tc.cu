@@ -32,9 +32,6 @@ constexpr int BK = 64;
 #ifndef SFB_EPI_WARPS
 #define SFB_EPI_WARPS 8
 #endif
-#ifndef SFB_EPI_PIPELINE
-#define SFB_EPI_PIPELINE 1  // A/B switch: software-pipelined TMEM reads in the epilogue
-#endif
 constexpr int kEpiWarps = SFB_EPI_WARPS;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kColSplit = kEpiWarps / 4;
@@ -709,33 +706,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         };
         constexpr int kChunks = kColsPer / kChunk;
-        if constexpr (kChunk == 16 && STAGES > 4 && SFB_EPI_PIPELINE) {
-            // one CTA per SM (deep pipeline): registers to spare -> the TMEM load of chunk i+1 is in
-            // flight while chunk i is converted (a single epilogue warp per scheduler hides nothing)
-            uint32_t va[16], vb[16];
-            tmem_ld16(trow + chalf * kColsPer, va);
+        // (software-pipelining these TMEM reads -- next chunk in flight while this one is converted --
+        // was measured: no gain, 4.87 vs 4.83 ms per step)
 #pragma unroll 1
-            for (int cb = 0; cb < kChunks; cb += 2) {
-                const int c0 = chalf * kColsPer + cb * kChunk;
-                tmem_wait_ld16(va);
-                if (cb + 1 < kChunks) tmem_ld16(trow + c0 + kChunk, vb);
-                stage_chunk(va, c0);
-                if (cb + 1 < kChunks) {
-                    tmem_wait_ld16(vb);
-                    if (cb + 2 < kChunks) tmem_ld16(trow + c0 + 2 * kChunk, va);
-                    stage_chunk(vb, c0 + kChunk);
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (int cb = 0; cb < kChunks; ++cb) {
-                uint32_t v[kChunk];
-                const int c0 = chalf * kColsPer + cb * kChunk;
-                if constexpr (kChunk == 32) tmem_ld32(trow + c0, v);
-                else tmem_ld16(trow + c0, v);
-                tmem_wait_ld();
-                stage_chunk(v, c0);
-            }
+        for (int cb = 0; cb < kChunks; ++cb) {
+            uint32_t v[kChunk];
+            const int c0 = chalf * kColsPer + cb * kChunk;
+            if constexpr (kChunk == 32) tmem_ld32(trow + c0, v);
+            else tmem_ld16(trow + c0, v);
+            tmem_wait_ld();
+            stage_chunk(v, c0);
         }
         epi_bar();
 
