@@ -100,8 +100,11 @@ typedef struct sfb_gemm_params {
     int32_t a_mode;
     int32_t M, N, K;
     int32_t dtype;
-    /* SFB_A_CONV3X3 geometry: OUTPUT image dims and the M-tile box */
-    int32_t img_n, img_h, img_w, cin, conv_stride, box_h, box_n;
+    /* SFB_A_CONV3X3 geometry: OUTPUT image dims and the M-tile box: 128 pixels =
+     * [box_n images, box_h rows, box_w columns].  box_w = 0 means img_w (full-width rows; the only
+     * form that allows box_n > 1); box_w < img_w (must divide img_w) tiles the image with 2-D
+     * patches, which is how widths that do not divide 128 (96, 104, ...) are handled. */
+    int32_t img_n, img_h, img_w, cin, conv_stride, box_h, box_n, box_w;
     /* split-K: >1 writes fp32 partials to `ws` ([splits, M, N]).  With `split_sync` (int32 [tiles],
      * zero-initialised once, self re-arming) the split CTA of a tile that arrives last adds the
      * other partials and finishes the tile itself; otherwise (or with gn_stats) a second kernel

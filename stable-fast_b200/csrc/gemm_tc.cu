@@ -93,6 +93,7 @@ struct GemmArgs {
     float* ws;
     // conv geometry
     int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
+    int box_w, tiles_per_row;  // M tile = [box_n, box_h, box_w] pixels; box_w < img_w: 2-D patches
     int up_tiles;   // SFB_A_UPCONV2X: M tiles per output phase
     int up_ntiles;  // ... and N tiles per phase in the phase-concatenated weight matrix
     // thread-block cluster (cx along N: the cx CTAs of one M-tile each load 1/cx of the A tile and
@@ -218,6 +219,21 @@ __device__ __forceinline__ void epi_geglu8(const EpiArgs& e, int m, int nout, co
         pack8(o, BF16);
 }
 
+// origin (image, row, column) of conv M-tile `tile` (already reduced to one up-conv phase)
+__device__ __forceinline__ void conv_tile_origin(const GemmArgs& a, int tile, int& n0, int& h0, int& w0) {
+    if (a.box_n == 1) {
+        n0 = tile / a.tiles_per_img;
+        const int rem = tile - n0 * a.tiles_per_img;
+        const int trow = rem / a.tiles_per_row;
+        h0 = trow * a.box_h;
+        w0 = (rem - trow * a.tiles_per_row) * a.box_w;
+    } else {
+        n0 = tile * a.box_n;
+        h0 = 0;
+        w0 = 0;
+    }
+}
+
 // tile-local row r (0..127) of M-tile `tile` -> global row m; false if the row is padding
 __device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r, int& m) {
     if (a.a_mode == SFB_A_MATRIX) {
@@ -229,16 +245,10 @@ __device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r
         phase = tile / a.up_tiles;
         tile -= phase * a.up_tiles;
     }
-    int n0, h0;
-    if (a.box_n == 1) {
-        n0 = tile / a.tiles_per_img;
-        h0 = (tile - n0 * a.tiles_per_img) * a.box_h;
-    } else {
-        n0 = tile * a.box_n;
-        h0 = 0;
-    }
-    const int w = r % a.img_w;
-    const int t = r / a.img_w;
+    int n0, h0, w0;
+    conv_tile_origin(a, tile, n0, h0, w0);
+    const int w = w0 + r % a.box_w;
+    const int t = r / a.box_w;
     const int dh = t % a.box_h;
     const int dn = t / a.box_h;
     const int n = n0 + dn, h = h0 + dh;
@@ -478,7 +488,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {
             pdl_wait();
-            int n0 = 0, h0 = 0;
+            int n0 = 0, h0 = 0, w0 = 0;
             // up-conv: output phase (py, px) of this M tile; its 2x2 taps sit at source offsets
             // (py - 1 + ty, px - 1 + tx).  The weight tile comes from the phase's row block.
             int up_py = 0, up_px = 0, b_ntile = n_tile;
@@ -490,12 +500,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     up_py = ph >> 1; up_px = ph & 1;
                     b_ntile = ph * args.up_ntiles + n_tile;
                 }
-                if (args.box_n == 1) {
-                    n0 = mt / args.tiles_per_img;
-                    h0 = (mt - n0 * args.tiles_per_img) * args.box_h;
-                } else {
-                    n0 = mt * args.box_n;
-                }
+                conv_tile_origin(args, mt, n0, h0, w0);
             }
             // conv tap of K block kb -> (w, h) source offset of the A box
             auto tap_offset = [&](int tap, int& dw, int& dh) {
@@ -527,7 +532,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const int cc = kb - tap * args.cpb;
                         int dw, dh;
                         tap_offset(tap, dw, dh);
-                        tma_load_4d_pair(dA, &tma_a, &full_bar[stage], cc * BK, dw,
+                        tma_load_4d_pair(dA, &tma_a, &full_bar[stage], cc * BK, w0 * args.conv_stride + dw,
                                          h0 * args.conv_stride + dh, n0);
                     }
                     tma_load_2d_pair(dB, &tma_b, &full_bar[stage], 0, b_row2);
@@ -547,7 +552,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     const int cc = kb - tap * args.cpb;
                     int dw, dh;
                     tap_offset(tap, dw, dh);
-                    int c1 = dw, c2 = h0 * args.conv_stride + dh, c3 = n0;
+                    int c1 = w0 * args.conv_stride + dw, c2 = h0 * args.conv_stride + dh, c3 = n0;
                     if (args.cx > 1) {
                         const int off = cix * args.a_part_ext;
                         if (args.a_part_dim == 1) c1 += off * args.conv_stride;
@@ -1078,18 +1083,23 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     if (p->a_mode == SFB_A_CONV3X3 || upconv) {
         if (p->cin <= 0 || p->cin % BK || p->K != (upconv ? 4 : 9) * p->cin)
             return fail(SFB_ERR_INVALID, "sfb_gemm: conv cin=%d K=%d", p->cin, p->K);
-        if (p->box_n * p->box_h * p->img_w != BM)
-            return fail(SFB_ERR_INVALID, "sfb_gemm: conv M-tile box %dx%dx%d != 128", p->box_n, p->box_h, p->img_w);
-        if (p->box_n > 1 && p->box_h != p->img_h)
-            return fail(SFB_ERR_INVALID, "sfb_gemm: multi-image box needs box_h == img_h");
+        const int box_w = p->box_w > 0 ? p->box_w : p->img_w;
+        if (p->box_n * p->box_h * box_w != BM || box_w > p->img_w || p->img_w % box_w)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: conv M-tile box %dx%dx%d != 128 pixels / does not tile width %d",
+                        p->box_n, p->box_h, box_w, p->img_w);
+        if (p->box_n > 1 && (p->box_h != p->img_h || box_w != p->img_w))
+            return fail(SFB_ERR_INVALID, "sfb_gemm: multi-image box needs box_h == img_h and box_w == img_w");
+        if (box_w != p->img_w && (p->cluster_n > 1 || p->cluster_m > 1))
+            return fail(SFB_ERR_INVALID, "sfb_gemm: patch tiles (box_w < img_w) do not combine with multicast clusters");
         if (p->M != (upconv ? 4 : 1) * p->img_n * p->img_h * p->img_w) return fail(SFB_ERR_INVALID, "sfb_gemm: conv M mismatch");
         if (upconv && (p->conv_stride != 1 || p->epi != SFB_EPI_STORE || p->cluster_n > 1 || p->cluster_m > 1))
             return fail(SFB_ERR_INVALID, "sfb_gemm: up-conv needs stride 1, the STORE epilogue and no multicast cluster");
         a.img_n = p->img_n; a.img_h = p->img_h; a.img_w = p->img_w;
         a.cpb = p->cin / BK;
         a.conv_stride = p->conv_stride;
-        a.box_h = p->box_h; a.box_n = p->box_n;
-        a.tiles_per_img = (p->img_h + p->box_h - 1) / p->box_h;
+        a.box_h = p->box_h; a.box_n = p->box_n; a.box_w = box_w;
+        a.tiles_per_row = p->img_w / box_w;
+        a.tiles_per_img = ((p->img_h + p->box_h - 1) / p->box_h) * a.tiles_per_row;
         m_tiles = (p->box_n == 1) ? p->img_n * a.tiles_per_img : (p->img_n + p->box_n - 1) / p->box_n;
         if (upconv) {  // 4 output phases, each its own set of M tiles and its own weight row block
             a.up_tiles = m_tiles;

@@ -22,6 +22,7 @@ class GemmParams(C.Structure):
         ("dtype", C.c_int32),
         ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32), ("cin", C.c_int32),
         ("conv_stride", C.c_int32), ("box_h", C.c_int32), ("box_n", C.c_int32),
+        ("box_w", C.c_int32),
         ("splits", C.c_int32), ("ws", C.c_void_p), ("split_sync", C.c_void_p),
         ("cluster_k", C.c_int32), ("defer_finish", C.c_int32),
         ("epi", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int32),

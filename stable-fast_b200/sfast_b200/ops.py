@@ -96,15 +96,18 @@ def nhwc_map(ptr, n, h, w, c, pitch, box_n, box_h, box_w, stride=1, dry=False):
 
 
 def conv_tile_box(ho, wo):
-    """[box_n, box_h] of the 128-pixel M tile for an output image of ho x wo (full-width rows)."""
-    if wo > BM or BM % wo:
-        raise NotImplementedError(f"conv output width {wo} must divide 128")
-    rows = BM // wo
-    if rows <= ho:
-        return 1, rows
-    if rows % ho:
-        raise NotImplementedError(f"conv output {ho}x{wo}: 128 is not a multiple of h*w")
-    return rows // ho, ho
+    """[box_n, box_h, box_w] of the 128-pixel M tile for an output image of ho x wo.
+    Widths that divide 128: full-width rows (several images per tile when the image is smaller than
+    128 pixels).  Any other width: 2-D patches of box_w = gcd(wo, 128) columns x 128 / box_w rows
+    (rows past the image are zero-filled by TMA on load and masked in the epilogue)."""
+    if wo <= BM and BM % wo == 0:
+        rows = BM // wo
+        if rows <= ho:
+            return 1, rows, wo
+        if rows % ho == 0:
+            return rows // ho, ho, wo
+    box_w = math.gcd(wo, BM)
+    return 1, BM // box_w, box_w
 
 
 # split-K cost model (microseconds, measured on B200 inside the captured graph, see DESIGN.md):
@@ -162,9 +165,10 @@ def a_matrix(x_ptr, rows, cols, pitch):
     return dict(kind="matrix", ptr=x_ptr, rows=rows, cols=cols, pitch=pitch)
 
 
-def a_conv(x_ptr, n, h, w, c, pitch, box_n, box_h, wo, stride):
+def a_conv(x_ptr, n, h, w, c, pitch, box_n, box_h, box_w, stride):
+    """NHWC conv input [n, h, w, c]; the M tile covers [box_n, box_h, box_w] OUTPUT pixels."""
     return dict(kind="conv", ptr=x_ptr, n=n, h=h, w=w, c=c, pitch=pitch, box_n=box_n, box_h=box_h,
-                wo=wo, stride=stride)
+                wo=box_w, stride=stride)
 
 
 def _a_map(a, cn, dry):
@@ -196,7 +200,8 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
     multicast is chosen from the tile grid."""
     p = GemmParams()
     if conv:
-        mt = conv["n"] * ((conv["h"] + conv["box_h"] - 1) // conv["box_h"]) if conv["box_n"] == 1 \
+        mt = conv["n"] * ((conv["h"] + conv["box_h"] - 1) // conv["box_h"]) * \
+            (conv["w"] // conv.get("box_w", conv["w"])) if conv["box_n"] == 1 \
             else (conv["n"] + conv["box_n"] - 1) // conv["box_n"]
     else:
         mt = (M + BM - 1) // BM
@@ -221,8 +226,9 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         p.img_n, p.img_h, p.img_w = conv["n"], conv["h"], conv["w"]
         p.cin, p.conv_stride = conv["cin"], conv["stride"]
         p.box_n, p.box_h = conv["box_n"], conv["box_h"]
+        p.box_w = conv.get("box_w", conv["w"])
         if p.box_n == 1:
-            m_tiles = p.img_n * ((p.img_h + p.box_h - 1) // p.box_h)
+            m_tiles = p.img_n * ((p.img_h + p.box_h - 1) // p.box_h) * (p.img_w // p.box_w)
         else:
             m_tiles = (p.img_n + p.box_n - 1) // p.box_n
         if conv.get("up"):

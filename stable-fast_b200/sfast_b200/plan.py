@@ -165,6 +165,11 @@ class UNetPlan:
         self.dt, self.dev, self.dry = weights.dtype, weights.device, weights.dry
         self.lib = None if self.dry else _lib.lib()
         self.B, self.H, self.W, self.ctx_len = batch, height, width, ctx_len
+        div = 1 << (len(self.spec.block_out_channels) - 1)
+        if height % div or width % div:
+            # diffusers switches to explicit upsample sizes there (forward_upsample_size); not built
+            raise NotImplementedError(
+                f"sfast (B200 build): latent size {height}x{width} must be a multiple of {div}")
         self.ops = []
         # Ops that depend only on the step's inputs (cross-attention K/V projections of the text
         # embedding): issued on a forked stream so they run concurrently with the start of the
@@ -333,12 +338,13 @@ class UNetPlan:
         wm = self.w.conv3x3(wname + ".weight")
         cout = wm.n
         ho, wo = x.h // stride, x.w // stride
-        box_n, box_h = ops.conv_tile_box(ho, wo)
-        adesc = ops.a_conv(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, wo, stride)
+        box_n, box_h, box_w = ops.conv_tile_box(ho, wo)
+        adesc = ops.a_conv(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, box_w, stride)
         M = x.n * ho * wo
         kw = dict(a=adesc, b=wm, M=M, N=cout, K=9 * x.c, dt=self.dt,
                   out=dst.ptr, ldo=dst.ld, bias=self.w.f32(wname + ".bias"),
-                  conv=dict(n=x.n, h=ho, w=wo, cin=x.c, stride=stride, box_n=box_n, box_h=box_h),
+                  conv=dict(n=x.n, h=ho, w=wo, cin=x.c, stride=stride, box_n=box_n, box_h=box_h,
+                            box_w=box_w),
                   keep=(x.buf, dst.buf, wm))
         if rowbias is not None:
             kw.update(rowbias=rowbias[0], rows_per_img=ho * wo, ld_rowbias=rowbias[1])
@@ -365,14 +371,14 @@ class UNetPlan:
         """nearest-2x upsample + conv3x3 of `x` -> dst ([n, 2h, 2w, cout]) without materialising
         the upsampled tensor: four 2x2 convolutions on x (one per output phase), 4/9 of the MACs."""
         wm, cout = self.w.upconv(wname + ".weight")
-        box_n, box_h = ops.conv_tile_box(x.h, x.w)
-        adesc = ops.a_conv(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, x.w, 1)
+        box_n, box_h, box_w = ops.conv_tile_box(x.h, x.w)
+        adesc = ops.a_conv(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, box_w, 1)
         M = 4 * x.n * x.h * x.w
         bias = self.w.f32(wname + ".bias")
         op = self._gemm(name, a=adesc, b=wm, M=M, N=cout, K=4 * x.c, dt=self.dt, out=dst.ptr,
                         ldo=dst.ld, bias=bias, keep=(x.buf, dst.buf, wm),
                         conv=dict(n=x.n, h=x.h, w=x.w, cin=x.c, stride=1, box_n=box_n, box_h=box_h,
-                                  up=True))
+                                  box_w=box_w, up=True))
         op.flops = 2 * M * cout * 9 * x.c  # algorithmic count of the reference formulation
         self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
         self._emit(op)

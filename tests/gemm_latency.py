@@ -29,17 +29,17 @@ def run(M, N, K, chain=8, residual=True, conv=None, rowbias=False, distinct=Fals
     if conv:
         n, h, wd, cin = conv
         xs = [torch.randn(n, h, wd, cin, device="cuda").to(dt) for _ in range(nbuf)]
-        box_n, box_h = ops.conv_tile_box(h, wd)
+        box_n, box_h, box_w = ops.conv_tile_box(h, wd)
         rb = torch.randn(n, N, device="cuda") if rowbias else None
     else:
         a = [torch.randn(M, K, device="cuda").to(dt) for _ in range(nbuf)]
     for i in range(chain):
         j = i % nbuf
         if conv:
-            ad = ops.a_conv(xs[j].data_ptr(), n, h, wd, cin, cin, box_n, box_h, wd, 1)
+            ad = ops.a_conv(xs[j].data_ptr(), n, h, wd, cin, cin, box_n, box_h, box_w, 1)
             op = ops.gemm_op("c", lib, a=ad, b=mats[j], M=M, N=N, K=K, dt=dt, out=out, ldo=N, bias=b,
                              rowbias=rb, rows_per_img=h * wd, ld_rowbias=N, residual=r, ldr=N,
-                             conv=dict(n=n, h=h, w=wd, cin=cin, stride=1, box_n=box_n, box_h=box_h))
+                             conv=dict(n=n, h=h, w=wd, cin=cin, stride=1, box_n=box_n, box_h=box_h, box_w=box_w))
             op.keep = tuple(op.keep) + (xs[j],)
         else:
             op = ops.gemm_op("g", lib, a=ops.a_matrix(a[j].data_ptr(), M, K, K), b=mats[j], M=M, N=N, K=K,

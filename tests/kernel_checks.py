@@ -109,15 +109,15 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
     r = _rand(M, cout, dt=dt) if residual else None
     out = torch.zeros(M, cout, device=DEV, dtype=dt)
     wp = ops.pack_conv3x3(wt, dt)
-    box_n, box_h = ops.conv_tile_box(ho, wo)
-    adesc = ops.a_conv(x.ptr, n, h, w, cin, ld, box_n, box_h, wo, stride)
+    box_n, box_h, box_w = ops.conv_tile_box(ho, wo)
+    adesc = ops.a_conv(x.ptr, n, h, w, cin, ld, box_n, box_h, box_w, stride)
     ws = torch.empty(64 * M * cout, device=DEV, dtype=torch.float32) if splits != 1 else None
     op = ops.gemm_op("conv", lib, a=adesc, b=ops.Mat(wp),
                      M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb,
                      rows_per_img=ho * wo, ld_rowbias=cout, residual=r, ldr=cout, ws=ws,
                      splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32),
                      cta_pair=pair, cluster_k=cluster_k,
-                     conv=dict(n=n, h=ho, w=wo, cin=cin, stride=stride, box_n=box_n, box_h=box_h))
+                     conv=dict(n=n, h=ho, w=wo, cin=cin, stride=stride, box_n=box_n, box_h=box_h, box_w=box_w))
     op.launch(_stream())
     torch.cuda.synchronize()
     xin = x.tensor().permute(0, 3, 1, 2).float()
@@ -142,13 +142,13 @@ def check_upconv(n=2, h=16, w=16, cin=640, cout=640, dt=torch.float16, splits=No
     M = 4 * n * h * w
     ld = cout + out_extra
     out = torch.zeros(n, 2 * h, 2 * w, ld, device=DEV, dtype=dt)
-    box_n, box_h = ops.conv_tile_box(h, w)
-    adesc = ops.a_conv(xin.data_ptr(), n, h, w, cin, cin, box_n, box_h, w, 1)
+    box_n, box_h, box_w = ops.conv_tile_box(h, w)
+    adesc = ops.a_conv(xin.data_ptr(), n, h, w, cin, cin, box_n, box_h, box_w, 1)
     ws = torch.empty(32 * M * cout, device=DEV, dtype=torch.float32) if splits != 1 else None
     op = ops.gemm_op("upconv", lib, a=adesc, b=ops.Mat(ops.pack_upconv(wt, dt)), M=M, N=cout, K=4 * cin,
                      dt=dt, out=out.data_ptr(), ldo=ld, bias=b, ws=ws, splits=splits, cta_pair=pair,
                      cluster_k=False,
-                     conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=box_n, box_h=box_h, up=True))
+                     conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=box_n, box_h=box_h, box_w=box_w, up=True))
     op.launch(_stream())
     torch.cuda.synchronize()
     up = F.interpolate(xin.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest")
@@ -270,13 +270,13 @@ def check_gn_finish(n=2, h=16, w=16, cin=1280, cout=1280, extra=0, splits=4, row
     cat = _rand(n, h, w, C, dt=dt)          # [conv output slice | skip slice]
     skip_ref = cat[..., cout:].clone()
     cat[..., :cout] = 7.0                     # must be overwritten by the GroupNorm kernel
-    box_n, box_h = ops.conv_tile_box(h, w)
-    adesc = ops.a_conv(xin.data_ptr(), n, h, w, cin, cin, box_n, box_h, w, 1)
+    box_n, box_h, box_w = ops.conv_tile_box(h, w)
+    adesc = ops.a_conv(xin.data_ptr(), n, h, w, cin, cin, box_n, box_h, box_w, 1)
     ws = torch.empty(splits * M * cout, device=DEV, dtype=torch.float32)
     conv = ops.gemm_op("conv", lib, a=adesc, b=ops.Mat(ops.pack_conv3x3(wt, dt)), M=M, N=cout, K=9 * cin,
                        dt=dt, out=cat.data_ptr(), ldo=C, bias=b, rowbias=rb, rows_per_img=h * w,
                        ld_rowbias=cout, residual=r, ldr=cout, ws=ws, splits=splits, cluster_k=False,
-                       conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=box_n, box_h=box_h))
+                       conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=box_n, box_h=box_h, box_w=box_w))
     assert conv.keep[0].splits == splits
     conv.keep[0].defer_finish = 1
     x = Act(cat, n, h, w, C)
@@ -617,6 +617,15 @@ CHECKS = {
     "conv_8_multi_image": (lambda: check_conv(3, 8, 8, 1280, 1280), 2e-3),
     "conv_4_tiny": (lambda: check_conv(5, 4, 4, 256, 256), 2e-3),
     "conv_concat_pitch": (lambda: check_conv(2, 32, 32, 640, 320, pitch_extra=320, splits=1), 2e-3),
+    "conv_patch_96": (lambda: check_conv(1, 96, 96, 320, 320, splits=1), 2e-3),
+    "conv_patch_24_splitk": (lambda: check_conv(2, 24, 24, 640, 640), 2e-3),
+    "conv_patch_12x20": (lambda: check_conv(2, 12, 20, 1280, 640), 2e-3),
+    "conv_patch_13x19": (lambda: check_conv(1, 13, 19, 256, 320, splits=1), 2e-3),
+    "conv_patch_stride2_96": (lambda: check_conv(1, 96, 96, 320, 320, stride=2, residual=False,
+                                                 rowbias=False, splits=1), 2e-3),
+    "conv_patch_nopair_40x24": (lambda: check_conv(1, 40, 24, 320, 320, pair=False, splits=1), 2e-3),
+    "upconv_patch_48": (lambda: check_upconv(1, 48, 48, 320, 320, splits=1), 3e-3),
+    "upconv_patch_12": (lambda: check_upconv(2, 12, 12, 1280, 1280), 3e-3),
     "conv_stride2": (lambda: check_conv(2, 64, 64, 320, 320, stride=2, residual=False,
                                         rowbias=False), 2e-3),
     "conv_stride2_16": (lambda: check_conv(2, 16, 16, 1280, 1280, stride=2, residual=False,

@@ -155,12 +155,23 @@ def test_split_k_policy():
 
 
 def test_conv_tile_box():
-    assert ops.conv_tile_box(64, 64) == (1, 2)
-    assert ops.conv_tile_box(8, 8) == (2, 8)
-    assert ops.conv_tile_box(4, 4) == (8, 4)
-    assert ops.conv_tile_box(72, 128) == (1, 1)
-    with pytest.raises(NotImplementedError):
-        ops.conv_tile_box(24, 24)
+    assert ops.conv_tile_box(64, 64) == (1, 2, 64)
+    assert ops.conv_tile_box(8, 8) == (2, 8, 8)
+    assert ops.conv_tile_box(4, 4) == (8, 4, 4)
+    assert ops.conv_tile_box(72, 128) == (1, 1, 128)
+    # widths that do not divide 128: 2-D patches
+    assert ops.conv_tile_box(96, 96) == (1, 4, 32)     # 768 x 768 images
+    assert ops.conv_tile_box(152, 104) == (1, 16, 8)   # 832 x 1216 (SDXL bucket)
+    assert ops.conv_tile_box(24, 24) == (1, 16, 8)
+    assert ops.conv_tile_box(3, 12) == (1, 32, 4)
+    assert ops.conv_tile_box(5, 25) == (1, 128, 1)
+
+
+def test_plans_build_for_resolutions_that_do_not_divide_128():
+    for h, w in ((96, 96), (64, 96), (104, 152)):
+        plan = _dry_plan(uo.sd15_config(), 1, h, w)
+        assert plan.flops() > 0
+    _dry_plan(uo.sdxl_config(), 2, 104, 152)
 
 
 def test_geglu_packing_round_trip():

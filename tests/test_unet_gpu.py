@@ -101,7 +101,8 @@ def test_rectangular_and_other_resolutions():
     cfg = uo.tiny_config()
     oracle, fast = _pair(cfg, seed=3)
     fast = _compile(fast, False)
-    for h, w in ((64, 64), (32, 64), (16, 16)):
+    # (24, 24), (40, 24), (96, 48): widths that do not divide 128 -> 2-D patch tiles in the convs
+    for h, w in ((64, 64), (32, 64), (16, 16), (24, 24), (40, 24), (96, 48)):
         s, e = _inputs(cfg, 1, h, w)
         got = fast(s, torch.tensor(400), e).sample
         with torch.no_grad():
@@ -203,3 +204,12 @@ def test_sdxl_unet_full_size_bf16_and_fp16():
         assert err < tol
         del oracle, fast
         torch.cuda.empty_cache()
+
+
+def test_latent_sizes_that_need_explicit_upsample_sizes_are_refused():
+    cfg = uo.tiny_config()
+    _, fast = _pair(cfg, seed=3)
+    fast = _compile(fast, False)
+    s, e = _inputs(cfg, 1, 20, 20)   # not a multiple of 2^(levels-1)
+    with pytest.raises(NotImplementedError, match="multiple of"):
+        fast(s, torch.tensor(1), e)
