@@ -398,7 +398,9 @@ __device__ __forceinline__ void store1(void* p, size_t i, float v, int bf16) {
         reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with the approximate divide (MUFU.RCP + multiply, <= 2 ulp): the IEEE division it
+// replaces was ~20 of the ~30 instructions per element in the GroupNorm+SiLU apply loops
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float gelu_erf_f(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
