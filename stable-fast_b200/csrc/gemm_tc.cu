@@ -410,8 +410,12 @@ struct GemmSmem {
     // fp32 staging tile of the epilogue, aliased onto the (by then idle) pipeline stages; the
     // +4 float pad makes the thread-per-row float4 writes of phase A bank-conflict free
     static constexpr int kStagePitch = BN + 4;
-    static_assert(BM * kStagePitch * 4 + BM * 4 + 2 * 8 * (BN / 2 + 2) * 2 * 4 <= kBarOffset,
-                  "staging tile + GroupNorm accumulators must fit in the stage buffers");
+    // QKV scatter tables (row -> (batch, position), column slice -> (q/k/v, offset)), also aliased
+    // onto the idle stage buffers, behind the GroupNorm accumulators
+    static constexpr int kQkvRowOffset = BM * kStagePitch * 4 + BM * 4 + 2 * 8 * (BN / 2 + 2) * 2 * 4;
+    static constexpr int kQkvColOffset = kQkvRowOffset + BM * 8;
+    static_assert(kQkvColOffset + (BN / 8) * 16 <= kBarOffset,
+                  "staging tile + GroupNorm accumulators + QKV tables must fit in the stage buffers");
     static_assert(STAGES > 4 || 2 * (kTotal + 1024) <= 228 * 1024, "shallow configs must fit twice per SM");
     static_assert(BN == 160, "the epilogue's 32+32+16 TMEM load split assumes 80-column halves");
 };
@@ -686,6 +690,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         if (dbg && threadIdx.x == 64) dbg[5] = globaltimer_ns();
+        // QKV scatter: the integer divisions of the address computation once per row / per column
+        // slice (tables in the now idle stage buffers) instead of five per stored 16-byte slice
+        int2* sQkvRow = reinterpret_cast<int2*>(smem + L::kQkvRowOffset);
+        longlong2* sQkvCol = reinterpret_cast<longlong2*>(smem + L::kQkvColOffset);
+        if (args.e.epi == SFB_EPI_QKV && !partial) {
+            const EpiArgs& q = args.e;
+            if (chalf == 0) sQkvRow[r] = valid ? make_int2(m / q.seq, m % q.seq) : make_int2(0, 0);
+            if (et < BN / 8) {
+                const int n = ncol0 + et * 8;
+                const int C = q.heads * q.head_dim;
+                const int which = n / C + q.which_base;
+                const int nn = n % C;
+                const int h = nn / q.head_dim, d = nn % q.head_dim;
+                long long off;
+                if (which == 0) off = (long long)h * q.q_rows * q.q_pitch + d;
+                else if (which == 1) off = (long long)h * q.k_rows * q.q_pitch + d;
+                else off = ((long long)h * q.vt_rows + d) * q.vt_pitch;
+                sQkvCol[et] = make_longlong2(which, off);
+            }
+        }
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float* srow = sStage + r * L::kStagePitch;
         constexpr int kColsPer = BN / kColSplit;             // columns converted per thread
@@ -867,7 +891,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (mm >= 0 && n < e.N) {
                         float f[8];
                         load8(row, grp * 8, f);
-                        epi_store8<BF16>(e, mm, n, f);
+                        const int2 bs = sQkvRow[row];          // (batch, position)
+                        const longlong2 ci = sQkvCol[grp];     // (q / k / v, column offset)
+                        if (ci.x == 0) {
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.q) +
+                                ((size_t)bs.x * e.heads * e.q_rows + bs.y) * e.q_pitch + ci.y) = pack8(f, BF16);
+                        } else if (ci.x == 1) {
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.k) +
+                                ((size_t)bs.x * e.heads * e.k_rows + bs.y) * e.q_pitch + ci.y) = pack8(f, BF16);
+                        } else {
+                            const size_t base = (size_t)bs.x * e.heads * e.vt_rows * e.vt_pitch + ci.y + bs.y;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) store1(e.vt, base + (size_t)i * e.vt_pitch, f[i], BF16);
+                        }
                     }
                 }
             }
