@@ -190,7 +190,7 @@ int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream);
 
 typedef struct sfb_attn_params {
     const void* tmap_q;  /* 2-D map over Q  [bh * q_rows,  q_pitch], box 128 rows */
-    const void* tmap_k;  /* 2-D map over K  [bh * k_rows,  q_pitch], box 128 rows */
+    const void* tmap_k;  /* 2-D map over K  [bh * k_rows,  q_pitch], box 128 rows (kv_tile 64: 64) */
     const void* tmap_vt; /* 2-D map over V^T [bh * vt_rows, vt_pitch], box vt_rows rows */
     void* out;           /* [batch, seq_q, heads * head_dim] 16-bit */
     int32_t batch, heads, head_dim;
@@ -198,6 +198,9 @@ typedef struct sfb_attn_params {
     int32_t q_rows, k_rows, vt_rows;
     int32_t dtype;
     float scale; /* 1 / sqrt(head_dim) */
+    /* 0 / 128: 128-key tiles.  64 (head_dim <= 64 only): 64-key tiles with the score tile
+     * double-buffered in TMEM and the probability tile double-buffered in shared memory. */
+    int32_t kv_tile;
 } sfb_attn_params;
 
 int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream);

@@ -375,6 +375,323 @@ static int launch_attention(const sfb_attn_params* p, const AttnArgs& a, cudaStr
                                : launch_attention_t<DC, DK, DV, KVS, 0>(p, a, stream);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// v2 (head_dim <= 64): 64-key tiles with the score tile DOUBLE-BUFFERED in TMEM (S0 | S1 | O) and
+// the probability tile double-buffered in shared memory.  In v1 the four softmax warps of a CTA
+// meet the tensor core twice per tile through single buffers (S: QK^T(j+1) cannot start before all
+// of them pulled S_j; P: nobody may write P_{j+1} before PV_j has read P_j), so the slowest warp
+// paces the others and the MUFU pipe idles ~40 % of the time.  With two buffers each the MMA
+// thread runs up to two score tiles ahead and the softmax warps one probability tile ahead.
+// ---------------------------------------------------------------------------------------
+constexpr int kTileKV2 = 64;
+
+template <int DV, int KVS>
+struct AttnSmem2 {
+    static constexpr int kQBytes = kTileQ * 128;
+    static constexpr int kKStage = kTileKV2 * 128;  // 64 keys x 64 (padded) head dims
+    static constexpr int kVStage = DV * 128;        // [DV rows x 64 kv columns]
+    static constexpr int kPBytes = kTileQ * 128;    // 128 rows x 64 probabilities
+    static constexpr int kOffK = kQBytes;
+    static constexpr int kOffV = kOffK + KVS * kKStage;
+    static constexpr int kOffP = kOffV + KVS * kVStage;
+    static constexpr int kOffBar = kOffP + 2 * kPBytes;
+    static constexpr int kTotal = kOffBar + 512 + 1024;
+    static_assert(kVStage % 1024 == 0, "V^T stage must keep 1024-byte swizzle-atom alignment");
+    static_assert(2 * (kTotal + 1024) <= 228 * 1024, "two CTAs per SM");
+};
+
+template <int DK, int DV, int KVS, int BF16>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attention_v2_kernel(const __grid_constant__ CUtensorMap tma_q,
+                    const __grid_constant__ CUtensorMap tma_k,
+                    const __grid_constant__ CUtensorMap tma_vt, const AttnArgs a) {
+    using L = AttnSmem2<DV, KVS>;
+    constexpr uint32_t kTmemCols = 256;
+    constexpr uint32_t kColS = 0, kColO = 128;  // S0 = [0, 64), S1 = [64, 128), O = [128, 128 + DV)
+    static_assert(128 + DV <= 256, "TMEM budget");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + L::kOffK;
+    uint8_t* sV = smem + L::kOffV;
+    uint8_t* sP = smem + L::kOffP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + KVS;
+    uint64_t* v_full = k_empty + KVS;
+    uint64_t* v_empty = v_full + KVS;
+    uint64_t* s_full = v_empty + KVS;  // [2] score buffer b holds QK^T of its current tile
+    uint64_t* s_free = s_full + 2;     // [2] all 128 softmax threads pulled it into registers
+    uint64_t* p_full = s_free + 2;     // [2] probability buffer b written (and O rescaled)
+    uint64_t* p_free = p_full + 2;     // [2] the PV MMA that read buffer b has completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q_tile = blockIdx.x;
+    const int bh = blockIdx.y;
+    const int n_kv = (a.seq_kv + kTileKV2 - 1) / kTileKV2;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_k);
+        tma_prefetch_desc(&tma_vt);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < KVS; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 128);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&p_free[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            pdl_wait();
+            mbar_expect_tx(q_full, L::kQBytes);
+            tma_load_2d(sQ, &tma_q, q_full, 0, bh * a.q_rows + q_tile * kTileQ);
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j % KVS;
+                const uint32_t ph = (j / KVS) & 1;
+                mbar_wait(&k_empty[st], ph ^ 1);
+                mbar_expect_tx(&k_full[st], L::kKStage);
+                tma_load_2d(sK + st * L::kKStage, &tma_k, &k_full[st], 0, bh * a.k_rows + j * kTileKV2);
+                mbar_wait(&v_empty[st], ph ^ 1);
+                mbar_expect_tx(&v_full[st], L::kVStage);
+                tma_load_2d(sV + st * L::kVStage, &tma_vt, &v_full[st], j * kTileKV2, bh * a.vt_rows);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr bool bf16 = BF16 != 0;
+            const uint32_t idesc_s = umma_idesc_f16(kTileQ, kTileKV2, bf16);
+            const uint32_t idesc_o = umma_idesc_f16(kTileQ, DV, bf16);
+            const uint32_t tO = tmem_base + kColO;
+            const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
+            auto issue_qk = [&](int j) {  // S[j & 1] = Q K_j^T
+                const int st = j % KVS;
+                const uint32_t tS = tmem_base + kColS + (uint32_t)(j & 1) * kTileKV2;
+                const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + st * L::kKStage));
+#pragma unroll
+                for (int kk = 0; kk < DK / 16; ++kk)
+                    umma_f16_ss(tS, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk != 0);
+                umma_commit(&k_empty[st]);
+                umma_commit(&s_full[j & 1]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_qk(0);
+            if (n_kv > 1) {
+                mbar_wait(&k_full[1 % KVS], (1 / KVS) & 1);
+                tc_fence_after();
+                issue_qk(1);
+            }
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j % KVS, b = j & 1;
+                const uint32_t ph2 = (j >> 1) & 1;  // phase of the per-buffer barriers for tile j
+                mbar_wait(&v_full[st], (j / KVS) & 1);
+                mbar_wait(&p_full[b], ph2);  // P_j in shared memory, O rescaled if needed
+                tc_fence_after();
+                const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + b * L::kPBytes));
+                const uint64_t dv = umma_desc_k_sw128(smem_u32(sV + st * L::kVStage));
+#pragma unroll
+                for (int kk = 0; kk < kTileKV2 / 16; ++kk)
+                    umma_f16_ss(tO, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_o,
+                                (j > 0) || (kk != 0));
+                umma_commit(&v_empty[st]);
+                umma_commit(&p_free[b]);
+                if (j + 2 < n_kv) {  // score buffer b was pulled into registers long ago: refill it
+                    const int st2 = (j + 2) % KVS;
+                    mbar_wait(&k_full[st2], ((j + 2) / KVS) & 1);
+                    mbar_wait(&s_free[b], ph2);
+                    tc_fence_after();
+                    issue_qk(j + 2);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tO = tmem_base + lane_base + kColO;
+        float m_run = -INFINITY;
+        const float sl2 = a.scale_log2;
+        for (int j = 0; j < n_kv; ++j) {
+            const int b = j & 1;
+            const uint32_t ph2 = (j >> 1) & 1;
+            const uint32_t tS = tmem_base + lane_base + kColS + (uint32_t)b * kTileKV2;
+            mbar_wait(&s_full[b], ph2);
+            tc_fence_after();
+            uint32_t sraw[64];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t tmp[32];
+                tmem_ld32(tS + c * 32, tmp);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sraw[c * 32 + i] = tmp[i];
+            }
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&s_free[b]);
+
+            const int n_valid = a.seq_kv - j * kTileKV2;  // >= 1; < 64 only on the last tile
+            if (n_valid < kTileKV2) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (i >= n_valid) sraw[i] = 0xff800000u;  // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+                mx0 = fmax3(mx0, __uint_as_float(sraw[i]), __uint_as_float(sraw[i + 1]));
+                mx1 = fmax3(mx1, __uint_as_float(sraw[i + 2]), __uint_as_float(sraw[i + 3]));
+                mx2 = fmax3(mx2, __uint_as_float(sraw[i + 4]), __uint_as_float(sraw[i + 5]));
+                mx3 = fmax3(mx3, __uint_as_float(sraw[i + 6]), __uint_as_float(sraw[i + 7]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            // lazy reference maximum (see v1)
+            constexpr float kLazyLog2 = 8.0f;
+            const float m_cand = mx * sl2;
+            const bool moved = m_cand > m_run + kLazyLog2;
+            const float m_new = moved ? m_cand : m_run;
+            const float alpha = moved ? fast_exp2(m_run - m_new) : 1.0f;
+            m_run = m_new;
+            const float neg_m = -m_new;
+
+            uint4 pk[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
+                pk[g].x = pack2(fast_exp2(x[0]), fast_exp2(x[1]), BF16);
+                pk[g].y = pack2(fast_exp2(x[2]), fast_exp2(x[3]), BF16);
+                pk[g].z = pack2(fast_exp2(x[4]), fast_exp2(x[5]), BF16);
+                pk[g].w = pack2(fast_exp2(x[6]), fast_exp2(x[7]), BF16);
+            }
+            // probability buffer b was last read by PV(j-2)
+            if (j >= 2) {
+                mbar_wait(&p_free[b], ((j >> 1) - 1) & 1);
+                tc_fence_after();
+            }
+            uint8_t* prow = sP + b * L::kPBytes + r * 128;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = pk[g];
+
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+                // O must be quiescent: PV(j-1) complete (PV(j) is only issued after p_full below)
+                mbar_wait(&p_free[b ^ 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < DV / 16; ++c) {
+                    uint32_t o[16];
+                    tmem_ld16(tO + c * 16, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st16(tO + c * 16, o);
+                }
+                tmem_wait_st();
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&p_full[b]);
+        }
+        // final: O / l, with l = O[:, head_dim] (the ones row of V^T)
+        mbar_wait(&p_free[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
+        tc_fence_after();
+        const int srow = q_tile * kTileQ + r;
+        const bool valid = srow < a.seq_q;
+        const int bb = bh / a.heads, h = bh % a.heads;
+        float inv_l;
+        {
+            uint32_t o[16];
+            tmem_ld16(tO + (a.head_dim & ~15), o);
+            tmem_wait_ld();
+            float l = 1.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i == (a.head_dim & 15)) l = __uint_as_float(o[i]);
+            inv_l = 1.0f / l;
+        }
+        uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) +
+                         ((size_t)bb * a.seq_q + (valid ? srow : 0)) * (a.heads * a.head_dim) +
+                         h * a.head_dim;
+#pragma unroll 1
+        for (int c = 0; c < DV / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tO + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int jv = 0; jv < 2; ++jv) {
+                const int d = c * 16 + jv * 8;
+                if (valid && d < a.head_dim) {
+                    uint4 w;
+                    w.x = pack2(__uint_as_float(o[jv * 8 + 0]) * inv_l, __uint_as_float(o[jv * 8 + 1]) * inv_l, BF16);
+                    w.y = pack2(__uint_as_float(o[jv * 8 + 2]) * inv_l, __uint_as_float(o[jv * 8 + 3]) * inv_l, BF16);
+                    w.z = pack2(__uint_as_float(o[jv * 8 + 4]) * inv_l, __uint_as_float(o[jv * 8 + 5]) * inv_l, BF16);
+                    w.w = pack2(__uint_as_float(o[jv * 8 + 6]) * inv_l, __uint_as_float(o[jv * 8 + 7]) * inv_l, BF16);
+                    *reinterpret_cast<uint4*>(orow + d) = w;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+template <int DK, int DV, int KVS, int BF16>
+static int launch_attention_v2_t(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
+    using L = AttnSmem2<DV, KVS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(attention_v2_kernel<DK, DV, KVS, BF16>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (err != cudaSuccess)
+            return fail(SFB_ERR_CUDA, "sfb_attention(v2): smem attribute: %s", cudaGetErrorString(err));
+        attr_set = true;
+    }
+    CUtensorMap tq, tk, tv;
+    memcpy(&tq, p->tmap_q, sizeof(CUtensorMap));
+    memcpy(&tk, p->tmap_k, sizeof(CUtensorMap));
+    memcpy(&tv, p->tmap_vt, sizeof(CUtensorMap));
+    dim3 grid((p->seq_q + kTileQ - 1) / kTileQ, p->batch * p->heads);
+    cudaError_t err = launch_pdl(attention_v2_kernel<DK, DV, KVS, BF16>, grid, dim3(kAttnThreads),
+                                 L::kTotal, stream, tq, tk, tv, a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_attention(v2): launch: %s", cudaGetErrorString(err));
+    return check_launch("sfb_attention");
+}
+
+template <int DK, int DV, int KVS>
+static int launch_attention_v2(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
+    return a.dtype == SFB_BF16 ? launch_attention_v2_t<DK, DV, KVS, 1>(p, a, stream)
+                               : launch_attention_v2_t<DK, DV, KVS, 0>(p, a, stream);
+}
+
 }  // namespace sfb
 
 using namespace sfb;
@@ -395,6 +712,16 @@ extern "C" int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream_) {
     a.seq_q = p->seq_q; a.seq_kv = p->seq_kv; a.q_rows = p->q_rows; a.k_rows = p->k_rows;
     a.vt_rows = p->vt_rows; a.dtype = p->dtype;
     a.scale_log2 = p->scale * 1.4426950408889634f;
+    if (p->kv_tile == 64) {  // v2: the caller built tmap_k with a 64-row box
+        switch (p->head_dim) {
+            case 32: return launch_attention_v2<32, 48, 4>(p, a, stream);
+            case 40: return launch_attention_v2<48, 48, 4>(p, a, stream);
+            case 64: return launch_attention_v2<64, 80, 3>(p, a, stream);
+            default:
+                return fail(SFB_ERR_INVALID, "sfb_attention: kv_tile 64 supports head_dim 32 / 40 / 64, not %d", p->head_dim);
+        }
+    }
+    if (p->kv_tile != 0 && p->kv_tile != 128) return fail(SFB_ERR_INVALID, "sfb_attention: kv_tile must be 0, 64 or 128");
     switch (p->head_dim) {
         case 32: return launch_attention<1, 32, 48, 2>(p, a, stream);
         case 40: return launch_attention<1, 48, 48, 2>(p, a, stream);

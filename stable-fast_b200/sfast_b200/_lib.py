@@ -50,7 +50,7 @@ class AttnParams(C.Structure):
         ("batch", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
         ("seq_q", C.c_int32), ("seq_kv", C.c_int32),
         ("q_rows", C.c_int32), ("k_rows", C.c_int32), ("vt_rows", C.c_int32),
-        ("dtype", C.c_int32), ("scale", C.c_float),
+        ("dtype", C.c_int32), ("scale", C.c_float), ("kv_tile", C.c_int32),
     ]
 
 

@@ -279,11 +279,16 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
     return op
 
 
+ATTN_V2 = os.environ.get("SFB_ATTN_V2", "0") != "0"  # experimental until validated on the GPU
+
+
 def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq_kv, q_rows, k_rows,
                  vt_rows, q_pitch, vt_pitch, dt, dry=False):
     bh = batch * heads
+    # v2 kernel (64-key tiles, double-buffered score / probability tiles) for head_dim <= 64
+    kv_tile = 64 if (ATTN_V2 and head_dim in (32, 40, 64)) else 128
     tq = matrix_map(_ptr(q), bh * q_rows, q_pitch, q_pitch, 128, dry)
-    tk = matrix_map(_ptr(k), bh * k_rows, q_pitch, q_pitch, 128, dry)
+    tk = matrix_map(_ptr(k), bh * k_rows, q_pitch, q_pitch, kv_tile, dry)
     tv = matrix_map(_ptr(vt), bh * vt_rows, vt_pitch, vt_pitch, vt_rows, dry)
     p = AttnParams()
     p.tmap_q, p.tmap_k, p.tmap_vt = tq.ptr, tk.ptr, tv.ptr
@@ -293,6 +298,7 @@ def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq
     p.q_rows, p.k_rows, p.vt_rows = q_rows, k_rows, vt_rows
     p.dtype = dtype_code(dt)
     p.scale = 1.0 / math.sqrt(head_dim)
+    p.kv_tile = kv_tile
     flops = 4 * batch * heads * seq_q * seq_kv * head_dim
     nbytes = 2 * bh * (2 * seq_q + 2 * seq_kv) * head_dim
     return Op(name, lib.sfb_attention, (C.byref(p),), (p, tq, tk, tv, q, k, vt, out), flops, nbytes)
