@@ -279,14 +279,27 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
     return op
 
 
-ATTN_V2 = os.environ.get("SFB_ATTN_V2", "0") != "0"  # experimental until validated on the GPU
+# Attention kernel choice.  v2 (64-key tiles, score tile double-buffered in TMEM, probability tile
+# double-buffered in shared memory) exists for head_dim 32 / 40 / 64.  Measured on B200
+# (S = 4096): head_dim 64 -> 1.32x faster than v1 (576 vs 437 TFLOP/s), head_dim 40 -> 0.9x (the
+# exponentials are the bound there and the per-tile overhead doubles).  "auto" = v2 for head_dim 64.
+ATTN_V2 = os.environ.get("SFB_ATTN_V2", "auto")
+
+
+def attention_kv_tile(head_dim):
+    if ATTN_V2 == "0" or head_dim not in (32, 40, 64):
+        return 128
+    if ATTN_V2 == "auto":
+        return 64 if head_dim == 64 else 128
+    return 64  # "1" / "all": wherever the kernel exists
 
 
 def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq_kv, q_rows, k_rows,
-                 vt_rows, q_pitch, vt_pitch, dt, dry=False):
+                 vt_rows, q_pitch, vt_pitch, dt, dry=False, kv_tile=None):
     bh = batch * heads
     # v2 kernel (64-key tiles, double-buffered score / probability tiles) for head_dim <= 64
-    kv_tile = 64 if (ATTN_V2 and head_dim in (32, 40, 64)) else 128
+    if kv_tile is None:
+        kv_tile = attention_kv_tile(head_dim)
     tq = matrix_map(_ptr(q), bh * q_rows, q_pitch, q_pitch, 128, dry)
     tk = matrix_map(_ptr(k), bh * k_rows, q_pitch, q_pitch, kv_tile, dry)
     tv = matrix_map(_ptr(vt), bh * vt_rows, vt_pitch, vt_pitch, vt_rows, dry)

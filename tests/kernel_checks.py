@@ -169,7 +169,7 @@ def _attn_buffers(B, H, S, Skv, D, dt):
     return q, k, vt, dv, q_pitch, vt_pitch
 
 
-def check_attention(B=2, H=8, S=1024, Skv=None, D=40, dt=torch.float16, seed=3):
+def check_attention(B=2, H=8, S=1024, Skv=None, D=40, dt=torch.float16, seed=3, kv_tile=None):
     lib = _lib.lib()
     Skv = Skv or S
     torch.manual_seed(seed)
@@ -183,7 +183,9 @@ def check_attention(B=2, H=8, S=1024, Skv=None, D=40, dt=torch.float16, seed=3):
     out = torch.zeros(B, S, H * D, device=DEV, dtype=dt)
     op = ops.attention_op("attn", lib, q=q, k=k, vt=vt, out=out, batch=B, heads=H, head_dim=D,
                           seq_q=S, seq_kv=Skv, q_rows=S, k_rows=Skv, vt_rows=dv, q_pitch=q_pitch,
-                          vt_pitch=vt_pitch, dt=dt)
+                          vt_pitch=vt_pitch, dt=dt, kv_tile=kv_tile)
+    if kv_tile is not None:
+        assert op.keep[0].kv_tile == kv_tile
     op.launch(_stream())
     torch.cuda.synchronize()
     ref = F.scaled_dot_product_attention(qr.float(), kr.float(), vr.float())
@@ -630,6 +632,14 @@ CHECKS = {
                                         rowbias=False), 2e-3),
     "conv_stride2_16": (lambda: check_conv(2, 16, 16, 1280, 1280, stride=2, residual=False,
                                            rowbias=False), 2e-3),
+    # both attention kernels for every head_dim they exist for, whatever the default policy picks
+    "attn_v2_d40": (lambda: check_attention(2, 8, 1024, None, 40, kv_tile=64), 5e-3),
+    "attn_v2_d32": (lambda: check_attention(1, 4, 320, None, 32, kv_tile=64), 5e-3),
+    "attn_v2_d64_4096": (lambda: check_attention(1, 10, 4096, None, 64, kv_tile=64), 5e-3),
+    "attn_v2_d64_bf16_ragged": (lambda: check_attention(2, 5, 200, 333, 64, dt=torch.bfloat16, kv_tile=64), 2e-2),
+    "attn_v2_cross77": (lambda: check_attention(2, 8, 1024, 77, 40, kv_tile=64), 5e-3),
+    "attn_v2_one_tile": (lambda: check_attention(2, 8, 256, 40, 64, kv_tile=64), 5e-3),
+    "attn_v1_d64": (lambda: check_attention(2, 8, 512, None, 64, kv_tile=128), 5e-3),
     "attn_d40": (lambda: check_attention(2, 8, 1024, None, 40), 5e-3),
     "attn_d40_4096": (lambda: check_attention(1, 8, 4096, None, 40), 5e-3),
     "attn_d80": (lambda: check_attention(2, 8, 256, None, 80), 5e-3),
