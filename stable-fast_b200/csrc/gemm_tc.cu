@@ -351,8 +351,9 @@ __device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int
     reduce_epilogue8<BN, BF16>(sum8, e, m, n, gn_sacc, gn_img0, gn_shard);
 }
 
-// Stand-alone reduction kernel: fallback when the split CTAs of a tile cannot all be co-resident
-// (the fused in-kernel reduction needs that for its barrier).  One thread per (row, 8 columns).
+// Stand-alone split-K reduction kernel (the default: measured faster than the in-kernel variants,
+// DESIGN.md section 4.1).  One thread per (row, 8 columns); convs that feed a GroupNorm skip it
+// (defer_finish) and let that kernel sum the partials.
 template <int BN, int BF16>
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) {

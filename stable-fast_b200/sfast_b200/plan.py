@@ -10,7 +10,11 @@ Design points:
     of the buffer its up-block consumer reads (`torch.cat` never runs).
   * every residual / bias / time-embedding add / GEGLU / head split lives in a GEMM epilogue.
   * weights are repacked once (conv OIHW -> K-major [cout, 9*cin], fused QKV, tile-interleaved
-    GEGLU, one concatenated matrix for all 22 time-embedding projections).
+    GEGLU, one concatenated matrix for all 22 time-embedding projections, LayerNorm folded into
+    the consuming projection, upsampler convs as four pre-summed 2x2 phases).
+  * work that is off the critical path runs on a forked stream = parallel branches of the captured
+    graph: time-embedding chain, cross-attention K/V projections, resnet shortcut GEMMs.
+  * a split-K conv followed by a GroupNorm leaves its reduction to that GroupNorm kernel.
 """
 import math
 import os
