@@ -271,3 +271,91 @@ def test_random_state_dict_is_seeded_and_complete():
     assert all(torch.equal(a[k], b[k]) for k in a)
     m = uo.build_unet(uo.tiny_config())
     m.load_state_dict({k: v.float() for k, v in a.items()})
+
+
+# ---------------------------------------------------------------------------------------------
+# Host-side validation of the C ABI on CPU: every sfb_gemm / sfb_group_norm_fused / sfb_attention
+# parameter block of a (dry) plan is handed to the real library with dummy non-null pointers.  On
+# a box without a GPU the call must get PAST argument validation and fail at the CUDA launch
+# (SFB_ERR_CUDA), never with SFB_ERR_INVALID -- geometry the kernels refuse is caught here.
+# ---------------------------------------------------------------------------------------------
+_DUMMY = ctypes.create_string_buffer(256)
+_DUMMY_PTR = (ctypes.addressof(_DUMMY) + 63) & ~63
+
+
+def _clone(struct):
+    c = type(struct)()
+    ctypes.memmove(ctypes.byref(c), ctypes.byref(struct), ctypes.sizeof(struct))
+    return c
+
+
+def _nonnull(struct, fields):
+    for f in fields:
+        if not getattr(struct, f):
+            setattr(struct, f, _DUMMY_PTR)
+
+
+def _validate_plan_on_cpu(plan):
+    lib = _lib.lib()
+    n = collections_counter()
+    for op in plan.all_ops():
+        if op.fn is None:
+            continue
+        name = op.fn.name
+        if name == "sfb_gemm":
+            p = _clone(op.keep[0])
+            _nonnull(p, ["tmap_a", "tmap_b", "out"])
+            if p.splits > 1:
+                _nonnull(p, ["ws"])
+            rc = lib.sfb_gemm(ctypes.byref(p), None)
+        elif name == "sfb_group_norm_fused":
+            p = _clone(op.keep[0])
+            _nonnull(p, ["x", "y", "gamma", "beta", "stats", "sync_counter"])
+            if p.part_splits > 1:
+                _nonnull(p, ["part_ws"])
+            rc = lib.sfb_group_norm_fused(ctypes.byref(p), None)
+        elif name in ("sfb_group_norm_stats", "sfb_group_norm_apply"):
+            p = _clone(op.keep[0])
+            _nonnull(p, ["x", "y", "gamma", "beta", "stats"])
+            rc = getattr(lib, name)(ctypes.byref(p), None)
+        elif name == "sfb_attention":
+            p = _clone(op.keep[0])
+            _nonnull(p, ["tmap_q", "tmap_k", "tmap_vt", "out"])
+            rc = lib.sfb_attention(ctypes.byref(p), None)
+        else:
+            continue
+        assert rc != 0, f"{op.name}: launched without a GPU?"
+        assert rc == -2, f"{op.name} ({name}): host validation refused it: {lib.sfb_last_error().decode()}"
+        n[name] += 1
+    return n
+
+
+def collections_counter():
+    import collections
+    return collections.Counter()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box without a GPU: launches must fail")
+def test_host_validation_really_rejects_bad_geometry():
+    lib = _lib.lib()
+    plan = _dry_plan(uo.tiny_config(), 2, 32, 32)
+    g = next(op.keep[0] for op in plan.all_ops() if op.fn is not None and op.fn.name == "sfb_gemm"
+             and op.keep[0].a_mode == _lib.A_CONV3X3)
+    for field, bad in (("K", 63), ("box_h", 3), ("N", 13), ("splits", 10 ** 6)):
+        p = _clone(g)
+        _nonnull(p, ["tmap_a", "tmap_b", "out", "ws"])
+        setattr(p, field, bad)
+        assert lib.sfb_gemm(ctypes.byref(p), None) == -1, field
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box without a GPU: launches must fail")
+@pytest.mark.parametrize("cfgf,batch,h,w", [
+    (uo.sd15_config, 2, 64, 64), (uo.sd15_config, 1, 64, 64), (uo.sd15_config, 3, 64, 64),
+    (uo.sd15_config, 16, 64, 64), (uo.sd15_config, 1, 128, 128), (uo.sd15_config, 2, 96, 96),
+    (uo.sd15_config, 1, 64, 96), (uo.sdxl_config, 2, 128, 128), (uo.sdxl_config, 1, 104, 152),
+    (uo.tiny_config, 2, 32, 32), (uo.tiny_config, 1, 24, 40),
+])
+def test_every_launch_of_a_plan_passes_host_validation(cfgf, batch, h, w):
+    plan = _dry_plan(cfgf(), batch, h, w)
+    n = _validate_plan_on_cpu(plan)
+    assert n["sfb_gemm"] > 50 and n["sfb_attention"] > 0
