@@ -57,6 +57,9 @@ uint64_t sfb_launch_count(void);
  * serialization attribute and gate their first dependent global access on griddepcontrol.wait, so
  * a kernel's prologue overlaps its predecessor's tail (also inside captured CUDA graphs). */
 void sfb_set_pdl(int enable);
+/* Streaming multiprocessors of the current CUDA device (grid sizing of persistent / cooperative
+ * kernels; 148 on a full B200). */
+int sfb_sm_count(void);
 
 /* ---- TMA tensor maps (host side; `out128` receives a 128-byte, 64-byte-aligned CUtensorMap) */
 
@@ -299,6 +302,29 @@ int sfb_conv_out(const void* x, const void* w, const float* bias, void* y, int32
 /* nearest-neighbour 2x upsample, NHWC, 16-bit */
 int sfb_upsample2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
                    int32_t ldx, int32_t ldy, sfb_stream_t stream);
+
+/* ControlNet residuals (reference: compile() leaves the ControlNet eager and the traced UNet takes
+ * `down_block_additional_residuals` / `mid_block_additional_residual` as extra inputs,
+ * /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:89-90):
+ * dst[n, hw, c] (NHWC slice, channel pitch ld_dst) += src[n, c, hw] (NCHW contiguous), up to 16
+ * tensors per launch. */
+typedef struct sfb_add_nchw_item {
+    const void* src;
+    void* dst;
+    int32_t n, c, hw, ld_dst;
+} sfb_add_nchw_item;
+
+typedef struct sfb_add_nchw_params {
+    int32_t count;
+    int32_t dtype;
+    sfb_add_nchw_item items[16];
+} sfb_add_nchw_params;
+
+int sfb_add_nchw_residuals(const sfb_add_nchw_params* p, sfb_stream_t stream);
+
+/* dst[r, 0:cols] = src[r, 0:cols], 16-bit elements, row pitches in elements */
+int sfb_copy2d(const void* src, void* dst, int32_t rows, int32_t cols, int32_t ld_src,
+               int32_t ld_dst, sfb_stream_t stream);
 
 /* cudaMemsetAsync wrapper (graph capturable) */
 int sfb_memset(void* p, int32_t value, size_t bytes, sfb_stream_t stream);

@@ -396,11 +396,21 @@ class UNet2DConditionModel(nn.Module):
 
 
 def build_unet(cfg: UNetConfig, seed: int = 0, dtype=torch.float32, device="cpu",
-               weight_gain: float = 1.0):
-    """Seeded default-PyTorch-init UNet (no checkpoints exist offline)."""
+               weight_gain: float = 1.0, randomize_affine: bool = True):
+    """Seeded default-PyTorch-init UNet (no checkpoints exist offline).
+
+    `randomize_affine` (default): every GroupNorm / LayerNorm gets gamma ~ 1 + 0.3 N(0, 1) and
+    beta ~ 0.3 N(0, 1) instead of PyTorch's (1, 0), so a whole-UNet parity test sees a norm that
+    is wired to the wrong consumer, a dropped beta or a mis-permuted folded LayerNorm."""
     g = torch.random.get_rng_state()
     torch.manual_seed(seed)
     m = UNet2DConditionModel(cfg)
+    if randomize_affine:
+        with torch.no_grad():
+            for mod in m.modules():
+                if isinstance(mod, (nn.GroupNorm, nn.LayerNorm)):
+                    mod.weight.copy_(1.0 + 0.3 * torch.randn_like(mod.weight))
+                    mod.bias.copy_(0.3 * torch.randn_like(mod.bias))
     torch.random.set_rng_state(g)
     if weight_gain != 1.0:
         with torch.no_grad():

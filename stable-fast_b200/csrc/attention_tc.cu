@@ -350,7 +350,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
 template <int DC, int DK, int DV, int KVS, int BF16>
 static int launch_attention_t(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
     using L = AttnSmem<DC, DK, DV, KVS>;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
+    bool& attr_set = attr_once.flag();
     if (!attr_set) {
         cudaError_t err = cudaFuncSetAttribute(attention_tc_kernel<DC, DK, DV, KVS, BF16>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -667,7 +668,8 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tma_q,
 template <int DK, int DV, int KVS, int BF16>
 static int launch_attention_v2_t(const sfb_attn_params* p, const AttnArgs& a, cudaStream_t stream) {
     using L = AttnSmem2<DV, KVS>;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
+    bool& attr_set = attr_once.flag();
     if (!attr_set) {
         cudaError_t err = cudaFuncSetAttribute(attention_v2_kernel<DK, DV, KVS, BF16>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);

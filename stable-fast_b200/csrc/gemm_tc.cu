@@ -1049,7 +1049,8 @@ template <int BN, int STAGES, int BF16, int CG>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
                          cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES, CG>;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
+    bool& attr_set = attr_once.flag();
     if (!attr_set) {
         cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, BF16, CG>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -1058,7 +1059,8 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
     }
     const int cz = a.cluster_k ? a.splits : 1;
     if (cz * CG > 8) {
-        static bool np_set = false;
+        static PerDeviceOnce np_once;
+        bool& np_set = np_once.flag();
         if (!np_set) {
             cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, BF16, CG>,
                                                    cudaFuncAttributeNonPortableClusterSizeAllowed, 1);

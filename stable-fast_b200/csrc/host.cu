@@ -30,6 +30,20 @@ int check_launch(const char* what) {
     return SFB_OK;
 }
 
+int sm_count() {
+    static int cached[64] = {};
+    const int d = current_device();
+    if (cached[d] <= 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = 148;
+        }
+        cached[d] = n;
+    }
+    return cached[d];
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (fn) return fn;
@@ -52,6 +66,7 @@ extern "C" int sfb_abi_version(void) { return SFB_ABI_VERSION; }
 extern "C" const char* sfb_last_error(void) { return g_err; }
 extern "C" uint64_t sfb_launch_count(void) { return g_launches.load(); }
 extern "C" void sfb_set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
+extern "C" int sfb_sm_count(void) { return sm_count(); }
 
 extern "C" int sfb_tmap_2d(void* out128, const void* base, uint64_t rows, uint64_t cols,
                            uint64_t pitch_elems, uint32_t box_rows) {

@@ -10,6 +10,20 @@ namespace sfb {
 int fail(int code, const char* fmt, ...);
 // Counts one kernel launch and converts cudaGetLastError() into an sfb_status.
 int check_launch(const char* what);
+// Kernel attributes (cudaFuncSetAttribute) and SM counts are per DEVICE: a process that drives
+// several GPUs must set them once on each.  `PerDeviceOnce::flag()` is the "already done" flag of
+// the current device.
+inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    return d > 63 ? 63 : d;
+}
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool& flag() { return done[current_device()]; }
+};
+// multiProcessorCount of the current device (cached; 148 on a full B200, fewer under MIG / green contexts)
+int sm_count();
 // Whether kernels are launched with programmatic stream serialization (PDL); sfb_set_pdl().
 extern int g_pdl;
 

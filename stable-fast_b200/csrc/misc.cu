@@ -293,9 +293,100 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint16_t* __restr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// ControlNet residuals: dst[n, hw, c] (NHWC slice, channel pitch ld) += src[n, c, hw] (NCHW) for
+// up to 16 tensors in ONE launch (diffusers adds `down_block_additional_residuals` to the 12 skip
+// tensors and `mid_block_additional_residual` to the mid-block output).  32 x 32 (pixel, channel)
+// tiles transposed through shared memory: reads coalesced along hw, writes along c.
+// ---------------------------------------------------------------------------------------
+struct AddNchwArgs {
+    int count, dtype;
+    const uint16_t* src[16];
+    uint16_t* dst[16];
+    int n[16], c[16], hw[16], ld[16];
+    int tile_end[16];  // exclusive prefix of 32x32 tiles per item
+};
+
+__global__ void __launch_bounds__(256) add_nchw_kernel(const AddNchwArgs a) {
+    __shared__ float tile[32][33];
+    pdl_launch_dependents();
+    pdl_wait();
+    int it = 0;
+    while (it < a.count - 1 && (int)blockIdx.x >= a.tile_end[it]) ++it;
+    const int t = blockIdx.x - (it ? a.tile_end[it - 1] : 0);
+    const int c = a.c[it], hw = a.hw[it], ld = a.ld[it];
+    const int tc = (c + 31) / 32, tp = (hw + 31) / 32;
+    const int img = t / (tc * tp);
+    const int rem = t - img * tc * tp;
+    const int c0 = (rem / tp) * 32, p0 = (rem % tp) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const uint16_t* src = a.src[it] + (size_t)img * c * hw;
+    uint16_t* dst = a.dst[it] + (size_t)img * hw * ld;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = c0 + ty + 8 * j, px = p0 + tx;
+        tile[ty + 8 * j][tx] = (ch < c && px < hw) ? load1(src, (size_t)ch * hw + px, a.dtype) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int px = p0 + ty + 8 * j, ch = c0 + tx;
+        if (ch < c && px < hw) {
+            const size_t o = (size_t)px * ld + ch;
+            store1(dst, o, load1(dst, o, a.dtype) + tile[tx][ty + 8 * j], a.dtype);
+        }
+    }
+}
+
+// dst[r, 0:cols] = src[r, 0:cols] (16-bit, arbitrary pitches): the one strided copy a plan needs
+// (SDXL: time-id sinusoids behind text_embeds in the add-embedding input row)
+__global__ void copy2d_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int rows,
+                              int cols, int lds, int ldd) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < rows * cols) {
+        const int r = idx / cols, c = idx - r * cols;
+        dst[(size_t)r * ldd + c] = src[(size_t)r * lds + c];
+    }
+}
+
 }  // namespace sfb
 
 using namespace sfb;
+
+extern "C" int sfb_add_nchw_residuals(const sfb_add_nchw_params* p, sfb_stream_t stream) {
+    if (!p || p->count <= 0 || p->count > 16) return fail(SFB_ERR_INVALID, "add_nchw_residuals: count must be 1..16");
+    AddNchwArgs a{};
+    a.count = p->count; a.dtype = p->dtype;
+    int tiles = 0;
+    for (int i = 0; i < p->count; ++i) {
+        const sfb_add_nchw_item& it = p->items[i];
+        if (!it.src || !it.dst || it.n <= 0 || it.c <= 0 || it.hw <= 0 || it.ld_dst < it.c)
+            return fail(SFB_ERR_INVALID, "add_nchw_residuals: bad item %d", i);
+        a.src[i] = reinterpret_cast<const uint16_t*>(it.src);
+        a.dst[i] = reinterpret_cast<uint16_t*>(it.dst);
+        a.n[i] = it.n; a.c[i] = it.c; a.hw[i] = it.hw; a.ld[i] = it.ld_dst;
+        tiles += it.n * ((it.c + 31) / 32) * ((it.hw + 31) / 32);
+        a.tile_end[i] = tiles;
+    }
+    cudaError_t err = launch_pdl(add_nchw_kernel, dim3(tiles), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "add_nchw_residuals: %s", cudaGetErrorString(err));
+    return check_launch("sfb_add_nchw_residuals");
+}
+
+extern "C" int sfb_copy2d(const void* src, void* dst, int32_t rows, int32_t cols, int32_t ld_src,
+                          int32_t ld_dst, sfb_stream_t stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0 || ld_src < cols || ld_dst < cols)
+        return fail(SFB_ERR_INVALID, "copy2d: bad argument");
+    const int total = rows * cols;
+    cudaError_t err = launch_pdl(copy2d_kernel, dim3((total + 255) / 256), dim3(256), 0,
+                                 static_cast<cudaStream_t>(stream), reinterpret_cast<const uint16_t*>(src),
+                                 reinterpret_cast<uint16_t*>(dst), rows, cols, ld_src, ld_dst);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "copy2d: %s", cudaGetErrorString(err));
+    return check_launch("sfb_copy2d");
+}
 
 extern "C" int sfb_timestep_embed(const float* t, int32_t batch, int32_t dim, int32_t flip,
                                   float freq_shift, void* out, int32_t ldo, int32_t dtype,

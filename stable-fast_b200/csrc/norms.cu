@@ -653,7 +653,8 @@ extern "C" int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream)
         a.part_bias = p->part_bias; a.part_rowbias = p->part_rowbias; a.part_ld_rowbias = p->part_ld_rowbias;
         a.part_residual = reinterpret_cast<const uint16_t*>(p->part_residual); a.part_ldr = p->part_ldr;
     }
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
+    bool& attr_set = attr_once.flag();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kGnFusedMaxSmem);

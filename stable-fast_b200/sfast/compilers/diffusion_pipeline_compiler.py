@@ -13,8 +13,10 @@ Field mapping (all 11 reference fields are accepted):
   prefer_lowp_gemm, enable_xformers, enable_triton, memory_format
                          -> accepted; they select nothing: the native path always runs NHWC with
                             every fusion on (fp32 accumulation, erf-GELU)
-  preserve_parameters    -> packed weights are copies; after an in-place parameter update call
-                            ``unet.forward._compiled.rebind()``
+  preserve_parameters    -> True (default): in-place parameter updates (LoRA switch, reference
+                            README.md:228-265) are picked up by the next call -- the packed copies
+                            are refreshed in place when the parameters' version counters move;
+                            False: weights are frozen at first call (``rebind()`` refreshes)
   trace_scheduler        -> accepted, no-op (scheduler is outside the hot path)
 """
 import logging
@@ -65,7 +67,8 @@ def compile_unet(m, config):
     device = m.device if hasattr(m, 'device') else torch.device(
         'cuda' if torch.cuda.is_available() else 'cpu')
     require_b200(torch.device(device))
-    return compile_unet_module(m, enable_cuda_graph=bool(config.enable_cuda_graph))
+    return compile_unet_module(m, enable_cuda_graph=bool(config.enable_cuda_graph),
+                               preserve_parameters=bool(getattr(config, 'preserve_parameters', True)))
 
 
 def compile_vae(m, config):

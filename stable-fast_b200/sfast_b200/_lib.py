@@ -85,6 +85,15 @@ class SmallLinearParams(C.Structure):
     ]
 
 
+class AddNchwItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_int32), ("c", C.c_int32),
+                ("hw", C.c_int32), ("ld_dst", C.c_int32)]
+
+
+class AddNchwParams(C.Structure):
+    _fields_ = [("count", C.c_int32), ("dtype", C.c_int32), ("items", AddNchwItem * 16)]
+
+
 # every symbol include/sfb200.h declares: (name, restype, argtypes)
 _I32, _U32, _U64, _VP, _F = C.c_int32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_float
 SYMBOLS = {
@@ -92,6 +101,7 @@ SYMBOLS = {
     "sfb_last_error": (C.c_char_p, []),
     "sfb_launch_count": (C.c_uint64, []),
     "sfb_set_pdl": (None, [C.c_int]),
+    "sfb_sm_count": (C.c_int, []),
     "sfb_tmap_2d": (C.c_int, [_VP, _VP, _U64, _U64, _U64, _U32]),
     "sfb_tmap_nhwc": (C.c_int, [_VP, _VP, _U32, _U32, _U32, _U32, _U64, _U32, _U32, _U32, _U32]),
     "sfb_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),
@@ -107,6 +117,8 @@ SYMBOLS = {
     "sfb_conv_in": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_conv_out": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_upsample2x": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_add_nchw_residuals": (C.c_int, [C.POINTER(AddNchwParams), _VP]),
+    "sfb_copy2d": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "sfb_memset": (C.c_int, [_VP, _I32, C.c_size_t, _VP]),
 }
 

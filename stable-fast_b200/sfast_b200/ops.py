@@ -475,27 +475,28 @@ def pack_geglu(w, b, dt, extra=None):
     """GEGLU projection [2*inner, k] (value rows first, gate rows second; reference chunk order
     /root/reference/src/sfast/jit/passes/__init__.py:643-648) -> tile-interleaved
     [ceil(inner/80)*160, k]: per 160-row tile, 80 value rows then the matching 80 gate rows.
-    `extra`: optional per-row fp32 vector permuted the same way (LayerNorm-fold column sums)."""
+    `extra`: optional per-row fp32 vector permuted the same way (LayerNorm-fold column sums).
+    One gather per tensor (no per-tile loop: packing is on the first-call latency path)."""
     inner = w.shape[0] // 2
     half = BN // 2
     tiles = (inner + half - 1) // half
-    wp = torch.zeros(tiles * BN, w.shape[1], dtype=dt, device=w.device)
-    bp = torch.zeros(tiles * BN, dtype=torch.float32, device=w.device)
-    ep = torch.zeros(tiles * BN, dtype=torch.float32, device=w.device) if extra is not None else None
-    wv, wg = w.detach()[:inner], w.detach()[inner:]
-    for t in range(tiles):
-        lo, hi = t * half, min((t + 1) * half, inner)
-        v0, g0 = t * BN, t * BN + half
-        wp[v0:v0 + hi - lo] = wv[lo:hi].to(dt)
-        wp[g0:g0 + hi - lo] = wg[lo:hi].to(dt)
-        if b is not None:
-            bp[v0:v0 + hi - lo] = b.detach()[lo:hi].float()
-            bp[g0:g0 + hi - lo] = b.detach()[inner + lo:inner + hi].float()
-        if extra is not None:
-            ep[v0:v0 + hi - lo] = extra[lo:hi].float()
-            ep[g0:g0 + hi - lo] = extra[inner + lo:inner + hi].float()
+    # source row of every packed row; rows past `inner` inside the last tile point at a zero row
+    j = torch.arange(tiles * BN, device=w.device)
+    t, r = j // BN, j % BN
+    col = t * half + (r % half)                      # output column of the packed row
+    src = torch.where(r < half, col, col + inner)   # value row | gate row of that column
+    valid = col < inner
+    src = torch.where(valid, src, torch.full_like(src, 2 * inner))  # -> appended zero row
+
+    def gather(v, dtype):
+        pad = torch.zeros((1,) + tuple(v.shape[1:]), dtype=dtype, device=w.device)
+        return torch.cat([v.detach().to(dtype), pad], 0).index_select(0, src).contiguous()
+
+    wp = gather(w, dt)
+    bp = gather(b, torch.float32) if b is not None else torch.zeros(tiles * BN, dtype=torch.float32,
+                                                                     device=w.device)
     if extra is not None:
-        return wp, bp, inner, ep
+        return wp, bp, inner, gather(extra, torch.float32)
     return wp, bp, inner
 
 

@@ -33,137 +33,153 @@ def _round_up(a, b):
 class PackedWeights:
     """Device-resident, kernel-ready copy of a UNet state dict (shape independent).
 
-    The packed tensors are COPIES: an in-place update of the original parameters (LoRA switch,
-    /root/reference/README.md:228-265) needs `CompiledUNet.rebind()`.
+    The packed tensors are COPIES of the module's parameters.  The reference keeps pointer
+    aliasing with the live parameters (`preserve_parameters=True`,
+    /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:35-39,70) so that an
+    in-place update (LoRA switch, /root/reference/README.md:228-265) is seen by the next call;
+    here `refresh()` re-packs every tensor INTO THE SAME device storage, so launch plans, TMA maps
+    and captured CUDA graphs stay valid, and the runtime calls it when the parameters' version
+    counters move.
     """
 
     def __init__(self, spec: UNetSpec, state_dict, dtype, device, dry=False):
         self.spec, self.dtype, self.device, self.dry = spec, dtype, torch.device(device), dry
         self.sd = state_dict
         self._cache = {}
+        self._builders = {}
         # all per-resnet time projections as ONE [sum(cout), temb_dim] matrix
-        ws, bs, self.tproj_off = [], [], {}
+        self.tproj_off = {}
         off = 0
         for r in spec.all_resnets():
-            ws.append(self._raw(r.prefix + ".time_emb_proj.weight"))
-            bs.append(self._raw(r.prefix + ".time_emb_proj.bias"))
             self.tproj_off[r.prefix] = off
             off += r.cout
         self.tproj_total = off
-        self.tproj_w = torch.cat(ws, 0).to(device=self.device, dtype=dtype).contiguous()
-        self.tproj_b = torch.cat(bs, 0).to(device=self.device, dtype=torch.float32).contiguous()
+        self.tproj_w, self.tproj_b = self._get(("tproj",), self._build_tproj)
+
+    def _build_tproj(self):
+        ws = [self._raw(r.prefix + ".time_emb_proj.weight") for r in self.spec.all_resnets()]
+        bs = [self._raw(r.prefix + ".time_emb_proj.bias") for r in self.spec.all_resnets()]
+        return (torch.cat(ws, 0).to(device=self.device, dtype=self.dtype).contiguous(),
+                torch.cat(bs, 0).to(device=self.device, dtype=torch.float32).contiguous())
 
     def _raw(self, name):
         if name not in self.sd:
             raise KeyError(f"UNet state dict has no parameter {name!r}")
         return self.sd[name].detach()
 
-    def f32(self, name):
-        key = ("f32", name)
+    def _get(self, key, builder):
         if key not in self._cache:
-            self._cache[key] = self._raw(name).to(device=self.device, dtype=torch.float32).contiguous()
+            self._cache[key] = builder()
+            self._builders[key] = builder
         return self._cache[key]
+
+    def refresh(self, state_dict):
+        """Re-pack from `state_dict` into the existing device tensors (addresses unchanged)."""
+        self.sd = state_dict
+
+        def copy_into(old, new):
+            if isinstance(old, ops.Mat):
+                old.data.copy_(new.data)
+            elif torch.is_tensor(old):
+                old.copy_(new)
+            elif isinstance(old, (tuple, list)):
+                for o, n in zip(old, new):
+                    copy_into(o, n)
+            elif old != new:
+                raise RuntimeError("UNet architecture changed under a compiled module")
+
+        for key, builder in self._builders.items():
+            copy_into(self._cache[key], builder())
+
+    def f32(self, name):
+        return self._get(("f32", name), lambda: self._raw(name).to(
+            device=self.device, dtype=torch.float32).contiguous())
 
     def _mat(self, w):
         return ops.Mat(w, self.dry)
 
     def matrix(self, name):
         """[n, k] weight (linear or 1x1 conv) as a tiled GEMM operand."""
-        key = ("mat", name)
-        if key not in self._cache:
+        def build():
             w = self._raw(name)
-            w = w.reshape(w.shape[0], -1).to(device=self.device, dtype=self.dtype).contiguous()
-            self._cache[key] = self._mat(w)
-        return self._cache[key]
+            return self._mat(w.reshape(w.shape[0], -1).to(device=self.device, dtype=self.dtype).contiguous())
+        return self._get(("mat", name), build)
 
     def conv3x3(self, name):
-        key = ("c3", name)
-        if key not in self._cache:
-            self._cache[key] = self._mat(ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype))
-        return self._cache[key]
+        return self._get(("c3", name), lambda: self._mat(
+            ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)))
 
     def upconv(self, name):
         """Upsampler conv as the 4-phase 2x2 formulation (ops.pack_upconv): (Mat, cout)."""
-        key = ("up", name)
-        if key not in self._cache:
+        def build():
             w = self._raw(name)
-            self._cache[key] = (self._mat(ops.pack_upconv(w.to(self.device), self.dtype)), w.shape[0])
-        return self._cache[key]
+            return (self._mat(ops.pack_upconv(w.to(self.device), self.dtype)), w.shape[0])
+        return self._get(("up", name), build)
 
     def conv3x3_plain(self, name):
-        key = ("c3p", name)
-        if key not in self._cache:
-            self._cache[key] = ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)
-        return self._cache[key]
+        return self._get(("c3p", name), lambda: ops.pack_conv3x3(self._raw(name).to(self.device),
+                                                                self.dtype))
 
     def conv_in_matrix(self, name):
         """First conv as a GEMM operand: [cout, (kh, kw, cin)] zero-padded along K to 64."""
-        key = ("cin_mat", name)
-        if key not in self._cache:
+        def build():
             w = ops.pack_conv3x3(self._raw(name).to(self.device), self.dtype)
             if w.device.type == "meta":
                 wp = torch.empty(w.shape[0], 64, dtype=self.dtype, device="meta")
             else:
                 wp = torch.zeros(w.shape[0], 64, dtype=self.dtype, device=w.device)
                 wp[:, :w.shape[1]] = w
-            self._cache[key] = self._mat(wp)
-        return self._cache[key]
+            return self._mat(wp)
+        return self._get(("cin_mat", name), build)
 
     def conv_in_weight(self, name):
-        key = ("cin", name)
-        if key not in self._cache:
-            self._cache[key] = ops.pack_conv_in(self._raw(name).to(self.device), self.dtype)
-        return self._cache[key]
+        return self._get(("cin", name), lambda: ops.pack_conv_in(self._raw(name).to(self.device),
+                                                                self.dtype))
 
     def cat_matrix(self, names):
-        key = ("cat",) + tuple(names)
-        if key not in self._cache:
+        def build():
             w = torch.cat([self._raw(n) for n in names], 0)
-            w = w.to(device=self.device, dtype=self.dtype).contiguous()
-            self._cache[key] = self._mat(w)
-        return self._cache[key]
+            return self._mat(w.to(device=self.device, dtype=self.dtype).contiguous())
+        return self._get(("cat",) + tuple(names), build)
 
     def ln_matrix(self, names, ln_prefix):
         """cat(names) with LayerNorm `ln_prefix` folded in: (Mat, bias', colsum)."""
-        key = ("lnmat", ln_prefix) + tuple(names)
-        if key not in self._cache:
+        def build():
             w = torch.cat([self._raw(n) for n in names], 0).to(self.device)
             wp, bias, colsum = ops.fold_layer_norm(
                 w, None, self._raw(ln_prefix + ".weight").to(self.device),
                 self._raw(ln_prefix + ".bias").to(self.device), self.dtype)
-            self._cache[key] = (self._mat(wp.contiguous()), bias, colsum)
-        return self._cache[key]
+            return (self._mat(wp.contiguous()), bias, colsum)
+        return self._get(("lnmat", ln_prefix) + tuple(names), build)
 
     def ln_geglu(self, prefix, ln_prefix):
-        key = ("lngeglu", prefix, ln_prefix)
-        if key not in self._cache:
+        def build():
             wp, bias, colsum = ops.fold_layer_norm(
                 self._raw(prefix + ".weight").to(self.device), self._raw(prefix + ".bias").to(self.device),
                 self._raw(ln_prefix + ".weight").to(self.device),
                 self._raw(ln_prefix + ".bias").to(self.device), self.dtype)
             wt, bp, inner, cs = ops.pack_geglu(wp, bias, self.dtype, extra=colsum)
-            self._cache[key] = (self._mat(wt), bp, inner, cs)
-        return self._cache[key]
+            return (self._mat(wt), bp, inner, cs)
+        return self._get(("lngeglu", prefix, ln_prefix), build)
 
     def geglu(self, prefix):
-        key = ("geglu", prefix)
-        if key not in self._cache:
+        def build():
             wp, bp, inner = ops.pack_geglu(self._raw(prefix + ".weight").to(self.device),
                                            self._raw(prefix + ".bias").to(self.device), self.dtype)
-            self._cache[key] = (self._mat(wp), bp, inner)
-        return self._cache[key]
+            return (self._mat(wp), bp, inner)
+        return self._get(("geglu", prefix), build)
 
     def small(self, name):
-        key = ("small", name)
-        if key not in self._cache:
-            self._cache[key] = self._raw(name).to(device=self.device, dtype=self.dtype).contiguous()
-        return self._cache[key]
+        return self._get(("small", name), lambda: self._raw(name).to(
+            device=self.device, dtype=self.dtype).contiguous())
 
 
 class UNetPlan:
     """One static launch schedule for a fixed (batch, height, width)."""
 
-    def __init__(self, weights: PackedWeights, batch, height, width, ctx_len=77):
+    def __init__(self, weights: PackedWeights, batch, height, width, ctx_len=77, controlnet=False):
+        self.controlnet = controlnet
+        self.ctrl_in = []  # static NCHW inputs: 12 (SD-1.5) down-block residuals + the mid-block one
         self.w = weights
         self.spec = weights.spec
         self.dt, self.dev, self.dry = weights.dtype, weights.device, weights.dry
@@ -551,7 +567,9 @@ class UNetPlan:
                           (self.time_ids_in, tid)))
             self._add_concat = (n_text, tid)
             h2 = self.buf("add_h", (B, spec.temb_dim))
-            self._emit(_CopyOp(self, n_text, tid))
+            self._emit(Op("add_embedding.concat", lib.sfb_copy2d,
+                          (_ptr(tid), _ptr(self.add_in) + 2 * n_text, B, 6 * ad, 6 * ad, spec.add_in_dim),
+                          (tid, self.add_in)))
             self._emit(ops.small_linear_op("add_embedding.linear_1", lib, x=self.add_in,
                                            w=self.w.small("add_embedding.linear_1.weight"),
                                            bias=self.w.f32("add_embedding.linear_1.bias"), batch=B,
@@ -658,6 +676,25 @@ class UNetPlan:
         b = self.act("mid_tf_out", x.n, x.h, x.w, m.cout)
         self.transformer(m.attentions[0], a, b)
         self.resnet(m.resnets[1], b, up_in[(0, 0)][1])
+        if self.controlnet:
+            # ControlNet: skip tensor i += down_block_additional_residuals[i], mid output +=
+            # mid_block_additional_residual (diffusers adds them after the down / mid blocks; the
+            # reference passes them through its traced UNet as plain inputs,
+            # /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:89-90).  Every
+            # down-path reader of a skip slice has run by now and no up-path reader has: one
+            # multi-tensor launch adds all of them in place.
+            prm = _lib.AddNchwParams()
+            dsts = [skip_dst[i] for i in range(len(skip_shapes))] + [up_in[(0, 0)][1]]
+            prm.count, prm.dtype = len(dsts), ops.dtype_code(self.dt)
+            for i, d in enumerate(dsts):
+                src = self._alloc((B, d.c, d.h, d.w), self.dt)
+                self.ctrl_in.append(src)
+                it = prm.items[i]
+                it.src, it.dst, it.n, it.c, it.hw, it.ld_dst = _ptr(src), d.ptr, B, d.c, d.h * d.w, d.ld
+            import ctypes
+            self._emit(Op("controlnet.residuals", lib.sfb_add_nchw_residuals, (ctypes.byref(prm),),
+                          (prm, self.ctrl_in, [d.buf for d in dsts]), 0,
+                          sum(3 * t.numel() * 2 for t in self.ctrl_in)))
         # ---- up path
         for i, blk in enumerate(spec.up):
             n_res = len(blk.resnets)
@@ -806,19 +843,6 @@ class _ForkOp(Op):
 
     def launch(self, stream):
         raise RuntimeError("join marker is handled by UNetPlan.run")
-
-
-class _CopyOp(Op):
-    """SDXL: place the time-id sinusoids after text_embeds in the add-embedding input row."""
-
-    def __init__(self, plan, n_text, tid):
-        super().__init__("add_embedding.concat", None, (), (plan.add_in, tid))
-        self.plan, self.n_text, self.tid = plan, n_text, tid
-
-    def launch(self, stream):
-        B = self.plan.B
-        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):  # may be the side stream
-            self.plan.add_in[:, self.n_text:].copy_(self.tid.view(B, -1))
 
 
 class _DryFn:

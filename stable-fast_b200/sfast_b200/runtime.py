@@ -9,6 +9,7 @@ graphs.py:229-231).
 """
 import logging
 import threading
+import time
 
 import torch
 
@@ -37,7 +38,6 @@ except Exception:  # noqa: BLE001
 
 
 _UNSUPPORTED_KWARGS = ("class_labels", "timestep_cond", "attention_mask",
-                       "down_block_additional_residuals", "mid_block_additional_residual",
                        "down_intrablock_additional_residuals", "encoder_attention_mask")
 
 
@@ -46,7 +46,7 @@ def require_b200(device):
         raise RuntimeError("sfast (B200 build): the UNet hot path needs a CUDA sm_100 device; "
                            "there is no CPU / eager fallback")
     major, minor = torch.cuda.get_device_capability(device)
-    if major != 10:
+    if (major, minor) != (10, 0):  # the cubin is sm_100a: no forward compatibility to sm_103 / sm_110
         raise RuntimeError(f"sfast (B200 build): kernels are sm_100a only, device is sm_{major}{minor}")
 
 
@@ -78,28 +78,56 @@ class _GraphedPlan:
 class CompiledUNet:
     """Callable with the signature of diffusers ``UNet2DConditionModel.forward``."""
 
-    def __init__(self, config, state_dict_fn, enable_cuda_graph=True):
+    def __init__(self, config, state_dict_fn, enable_cuda_graph=True, preserve_parameters=True):
         self._config = config
         self._state_dict_fn = state_dict_fn
         self.enable_cuda_graph = enable_cuda_graph
+        # reference contract (preserve_parameters=True): an in-place parameter update is seen by
+        # the next call.  The packed weights are copies, so the parameters' version counters are
+        # compared on every call and the copies refreshed in place when they moved.
+        self.preserve_parameters = preserve_parameters
         self._weights = None
+        self._param_refs = None
+        self._param_versions = None
         self._cached = {}
         self._lock = threading.Lock()
         self.spec = spec_from_config(config)
+        self.first_call_s = None  # wall time of the first call (packing + plan + capture)
 
     # -- weights -------------------------------------------------------------------------
+    def _versions(self):
+        return [(p._version, p.data_ptr()) for p in self._param_refs]
+
     def _ensure_weights(self, dtype, device):
         if self._weights is None or self._weights.dtype != dtype or self._weights.device != device:
             logger.info("Packing UNet weights for the B200 path (%s, %s)", dtype, device)
-            self._weights = PackedWeights(self.spec, self._state_dict_fn(), dtype, device)
+            sd = self._state_dict_fn()
+            self._weights = PackedWeights(self.spec, sd, dtype, device)
+            self._param_refs = [t for t in sd.values() if torch.is_tensor(t)]
+            self._param_versions = self._versions()
             self._cached.clear()
+        elif self.preserve_parameters:
+            now = self._versions()
+            if now != self._param_versions:
+                logger.info("UNet parameters changed in place: refreshing the packed weights")
+                self._refresh_locked()
         return self._weights
 
+    def _refresh_locked(self):
+        sd = self._state_dict_fn()
+        torch.cuda.current_stream().synchronize()  # no replay may be reading the old values
+        self._weights.refresh(sd)
+        self._param_refs = [t for t in sd.values() if torch.is_tensor(t)]
+        self._param_versions = self._versions()
+
     def rebind(self):
-        """Re-pack weights after the module's parameters were changed in place (LoRA switch)."""
+        """Re-pack the weights now (same device storage: plans and CUDA graphs stay valid).
+        Only needed with preserve_parameters=False or after replacing parameter objects in a way
+        the version counters cannot see."""
         with self._lock:
-            self._weights = None
-            self._cached.clear()
+            if self._weights is not None:
+                with torch.cuda.device(self._weights.device):
+                    self._refresh_locked()
 
     # -- forward -------------------------------------------------------------------------
     def __call__(self, sample, timestep, encoder_hidden_states, class_labels=None,
@@ -109,8 +137,6 @@ class CompiledUNet:
                  encoder_attention_mask=None, return_dict=True):
         given = dict(class_labels=class_labels, timestep_cond=timestep_cond,
                      attention_mask=attention_mask,
-                     down_block_additional_residuals=down_block_additional_residuals,
-                     mid_block_additional_residual=mid_block_additional_residual,
                      down_intrablock_additional_residuals=down_intrablock_additional_residuals,
                      encoder_attention_mask=encoder_attention_mask)
         for k in _UNSUPPORTED_KWARGS:
@@ -120,20 +146,26 @@ class CompiledUNet:
             scale = cross_attention_kwargs.get("scale", 1.0)
             if set(cross_attention_kwargs) - {"scale"} or scale != 1.0:
                 raise NotImplementedError("sfast (B200 build): cross_attention_kwargs (LoRA scale) "
-                                          "is not supported; fuse LoRA weights and call rebind()")
+                                          "is not supported; fuse the LoRA weights into the parameters")
         require_b200(sample.device)
         dtype = sample.dtype
         if dtype not in (torch.float16, torch.bfloat16):
             raise NotImplementedError(f"sfast (B200 build): UNet dtype {dtype}; use fp16 or bf16")
         B, _, H, W = sample.shape
         ctx_len = encoder_hidden_states.shape[1]
-        with self._lock:
+        controlnet = down_block_additional_residuals is not None or mid_block_additional_residual is not None
+        if controlnet and (down_block_additional_residuals is None or mid_block_additional_residual is None):
+            raise NotImplementedError("sfast (B200 build): ControlNet residuals need both "
+                                      "down_block_additional_residuals and mid_block_additional_residual")
+        # everything below (allocation, TMA maps, launches, capture) targets sample's device
+        with self._lock, torch.cuda.device(sample.device):
+            t_first = time.perf_counter() if self.first_call_s is None else None
             weights = self._ensure_weights(dtype, sample.device)
-            key = (B, H, W, dtype, ctx_len, sample.device.index)
+            key = (B, H, W, dtype, ctx_len, sample.device.index, controlnet)
             gp = self._cached.get(key)
             if gp is None:
                 logger.info("Building UNet launch plan for %s", key)
-                plan = UNetPlan(weights, B, H, W, ctx_len)
+                plan = UNetPlan(weights, B, H, W, ctx_len, controlnet=controlnet)
                 gp = _GraphedPlan(plan, self.enable_cuda_graph)
                 self._cached[key] = gp
             plan = gp.plan
@@ -148,17 +180,28 @@ class CompiledUNet:
                 te = added_cond_kwargs["text_embeds"]
                 plan.add_in[:, :te.shape[1]].copy_(te)
                 plan.time_ids_in.copy_(added_cond_kwargs["time_ids"].reshape(-1).float())
+            if controlnet:
+                res = list(down_block_additional_residuals) + [mid_block_additional_residual]
+                if len(res) != len(plan.ctrl_in):
+                    raise ValueError(f"expected {len(plan.ctrl_in) - 1} down-block residuals, got {len(res) - 1}")
+                for dst, src in zip(plan.ctrl_in, res):
+                    if tuple(src.shape) != tuple(dst.shape):
+                        raise ValueError(f"ControlNet residual shape {tuple(src.shape)} != {tuple(dst.shape)}")
+                    dst.copy_(src, non_blocking=True)
             gp.step()
             out = plan.out.clone()
+            if t_first is not None:
+                torch.cuda.current_stream().synchronize()
+                self.first_call_s = time.perf_counter() - t_first
         if not return_dict:
             return (out,)
         return UNet2DConditionOutput(sample=out)
 
 
-def compile_unet_module(m, enable_cuda_graph=True):
+def compile_unet_module(m, enable_cuda_graph=True, preserve_parameters=True):
     """Replace ``m.forward`` (same module object, as the reference does at
     /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:146-149)."""
-    compiled = CompiledUNet(m.config, m.state_dict, enable_cuda_graph)
+    compiled = CompiledUNet(m.config, m.state_dict, enable_cuda_graph, preserve_parameters)
 
     def forward(*args, **kwargs):
         return compiled(*args, **kwargs)

@@ -106,6 +106,24 @@ def spec_from_config(cfg) -> UNetSpec:
         v = cfg_get(cfg, key)
         if v not in (None, False, "default", "positional"):
             raise NotImplementedError(f"UNet config {key}={v!r} is not supported by the B200 path")
+    # fields whose only supported value is the SD-1.5 / SDXL one: anything else would compile and
+    # return wrong numerics, so it is refused by name
+    required = {
+        "act_fn": ("silu", "swish"), "time_embedding_type": ("positional",),
+        "conv_in_kernel": (3,), "conv_out_kernel": (3,), "downsample_padding": (1,),
+        "mid_block_scale_factor": (1, 1.0), "resnet_out_scale_factor": (1, 1.0),
+        "resnet_skip_time_act": (False,), "mid_block_only_cross_attention": (None, False),
+        "cross_attention_norm": (None,), "attention_bias": (False,), "num_class_embeds": (None,),
+        "addition_embed_type_num_heads": (64,), "timestep_post_act": (None,),
+        "time_embedding_dim": (None,), "class_embeddings_concat": (False,),
+        "reverse_transformer_layers_per_block": (None,), "dropout": (0, 0.0),
+        "center_input_sample": (False,), "encoder_hid_dim": (None,),
+    }
+    for key, allowed in required.items():
+        v = cfg_get(cfg, key, allowed[0])
+        if v not in allowed:
+            raise NotImplementedError(f"UNet config {key}={v!r} is not supported by the B200 path "
+                                      f"(supported: {allowed})")
     mid_type = cfg_get(cfg, "mid_block_type", "UNetMidBlock2DCrossAttn")
     if mid_type not in (None, "UNetMidBlock2DCrossAttn"):
         raise NotImplementedError(f"mid block type {mid_type}")
@@ -245,14 +263,16 @@ def param_shapes(spec: UNetSpec):
 
 
 def random_state_dict(spec: UNetSpec, seed=0, dtype=torch.float16, device="cpu"):
-    """Random weights of the architecture (PyTorch-default-like uniform(-1/sqrt(fan_in), ..))."""
+    """Random weights of the architecture (PyTorch-default-like uniform(-1/sqrt(fan_in), ..);
+    norm layers: gamma ~ 1 + 0.3 N(0, 1), beta ~ 0.3 N(0, 1))."""
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
     sd = {}
     for name, shape in param_shapes(spec).items():
         is_norm = ".norm" in name or name.startswith("conv_norm_out")
         if is_norm:
-            t = torch.ones(shape) if name.endswith("weight") else torch.zeros(shape)
+            # random affine (not PyTorch's 1 / 0): a benchmark must not hide a dropped beta
+            t = torch.randn(shape, generator=g) * 0.3 + (1.0 if name.endswith("weight") else 0.0)
         else:
             wshape = shape if name.endswith("weight") else None
             if wshape is None:

@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(_ROOT, "stable-fast_b200"))
+sys.path.insert(0, _ROOT)  # oracle/ (the checker)
 
 from sfast_b200 import _lib, ops  # noqa: E402
 from sfast_b200.ops import Act  # noqa: E402
@@ -31,8 +32,16 @@ def _stream():
 
 
 def rel_err(got, ref):
+    """max of two normalised errors, both of which must be below the check's tolerance `tol`:
+      * global max-norm:  max|d| / max|ref|
+      * elementwise:      max(|d| / (|ref| + rms(ref)))   i.e. |d| <= tol * |ref| + tol * rms(ref),
+        the assert_close(rtol, atol) form of the reference's own operator tests
+        (/root/reference/tests/operators/test_cudnn_convolution.py:65) with atol scaled to the
+        tensor; a small-magnitude output that is 100 % wrong fails this one."""
     got, ref = got.float(), ref.float()
-    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+    d = (got - ref).abs()
+    rms = ref.pow(2).mean().sqrt().clamp_min(1e-6)
+    return max((d.max() / ref.abs().max().clamp_min(1e-6)).item(), (d / (ref.abs() + rms)).max().item())
 
 
 def _rand(*shape, dt=torch.float16, scale=1.0, seed=None):
@@ -231,11 +240,19 @@ def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=
 
 
 def check_group_norm(n=2, c=320, h=32, w=32, silu=True, dt=torch.float16, pitch_extra=0, eps=1e-5,
-                     seed=5, fused=True):
+                     seed=5, fused=True, adversarial=None):
+    """`adversarial`: "mean50" (every value offset by 50: |mean| >> sigma, the case a raw
+    sum-of-squares variance loses digits on), "outlier" (channel 7 scaled by 100, as real
+    checkpoints have) -- compared against oracle/ops_oracle.py (two-pass fp32 statistics)."""
     lib = _lib.lib()
     torch.manual_seed(seed)
     ld = c + pitch_extra
-    xb = _rand(n, h, w, ld, dt=dt)
+    xb = torch.randn(n, h, w, ld, device=DEV)
+    if adversarial == "mean50":
+        xb = xb + 50.0
+    elif adversarial == "outlier":
+        xb[..., 7] *= 100.0
+    xb = xb.to(dt)
     x = Act(xb, n, h, w, c, ld=ld)
     yb = torch.zeros(n, h, w, c, device=DEV, dtype=dt)
     y = Act(yb, n, h, w, c)
@@ -248,6 +265,10 @@ def check_group_norm(n=2, c=320, h=32, w=32, silu=True, dt=torch.float16, pitch_
     for op in gops:
         op.launch(_stream())
     torch.cuda.synchronize()
+    if adversarial:
+        from oracle import ops_oracle as oo
+        ref = oo.group_norm(x.tensor().permute(0, 3, 1, 2).float(), 32, gamma, beta, eps, silu)
+        return rel_err(yb, ref.permute(0, 2, 3, 1))
     ref = F.group_norm(x.tensor().permute(0, 3, 1, 2).float(), 32, gamma, beta, eps)
     if silu:
         ref = F.silu(ref)
@@ -416,7 +437,7 @@ def check_upsample(n=2, h=16, w=16, c=1280, dt=torch.float16):
 
 
 def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=1, splits_c=1, seed=12,
-                  cluster_k=False):
+                  cluster_k=False, row_offset=0.5, outlier=False):
     """LayerNorm folded around two GEMMs: the producer accumulates per-row (sum, sum of squares)
     in its epilogue, the consumer runs on the RAW activation with gamma-scaled weights and
     corrects with mean / rstd in its epilogue.  Reference: F.layer_norm then the linear / GEGLU."""
@@ -424,7 +445,10 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
     torch.manual_seed(seed)
     a = _rand(M, C, dt=dt)
     w0 = _rand(C, C, dt=dt, scale=1 / math.sqrt(C))
-    res = _rand(M, C, dt=dt, scale=2.0) + 0.5          # non-zero-mean rows
+    res = torch.randn(M, C, device=DEV) * 2.0 + row_offset   # non-zero-mean rows (row_offset >> sigma: adversarial)
+    if outlier:
+        res[:, 5] *= 40.0                                      # one outlier channel, as real checkpoints have
+    res = res.to(dt)
     x = torch.zeros(M, C, device=DEV, dtype=dt)
     stats = torch.zeros(M, 2, device=DEV)
     ws = torch.empty(16 * M * max(N, C) * 2, device=DEV, dtype=torch.float32)
@@ -457,7 +481,11 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
     torch.cuda.synchronize()
     xr = (a.float() @ w0.float().t() + res.float())
     e0 = rel_err(x, xr)
-    y = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.float().t() + b
+    if row_offset != 0.5 or outlier:
+        from oracle import ops_oracle as oo
+        y = oo.layer_norm(x.float(), gamma, beta, 1e-5) @ w.float().t() + b
+    else:
+        y = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.float().t() + b
     if mode == "geglu":
         h, g = y.chunk(2, dim=-1)
         y = h * F.gelu(g)
@@ -652,6 +680,15 @@ CHECKS = {
     "qkv_scatter": (lambda: check_qkv_scatter(2, 8, 256, 40), 2e-3),
     "qkv_scatter_d160": (lambda: check_qkv_scatter(2, 8, 64, 160), 2e-3),
     "kv_scatter_cross": (lambda: check_qkv_scatter(2, 8, 256, 40, cross_kv=77), 2e-3),
+    # adversarial statistics (vs oracle/ops_oracle.py): |mean| >> sigma, one outlier channel
+    "group_norm_mean50": (lambda: check_group_norm(2, 320, 32, 32, True, adversarial="mean50"), 1e-2),
+    "group_norm_mean50_two_pass": (lambda: check_group_norm(4, 320, 64, 64, True, fused=False, adversarial="mean50"), 1e-2),
+    "group_norm_outlier": (lambda: check_group_norm(2, 640, 16, 16, True, adversarial="outlier"), 1e-2),
+    "group_norm_outlier_two_pass": (lambda: check_group_norm(2, 640, 16, 16, False, fused=False, adversarial="outlier"), 1e-2),
+    "ln_fold_mean30": (lambda: check_ln_fold(300, 320, 960, row_offset=30.0), 1e-2),
+    "ln_fold_mean30_1280": (lambda: check_ln_fold(256, 1280, 1280, row_offset=30.0), 1e-2),
+    "ln_fold_outlier": (lambda: check_ln_fold(300, 640, 640, outlier=True), 1e-2),
+    "ln_fold_geglu_mean30": (lambda: check_ln_fold(300, 320, 1280, mode="geglu", row_offset=30.0), 2e-2),
     "group_norm_silu": (lambda: check_group_norm(2, 320, 32, 32, True), 1e-2),
     "group_norm": (lambda: check_group_norm(2, 320, 32, 32, False, eps=1e-6), 1e-2),
     "group_norm_1920_pitch": (lambda: check_group_norm(2, 1920, 16, 16, True, pitch_extra=640), 1e-2),

@@ -359,3 +359,51 @@ def test_every_launch_of_a_plan_passes_host_validation(cfgf, batch, h, w):
     plan = _dry_plan(cfgf(), batch, h, w)
     n = _validate_plan_on_cpu(plan)
     assert n["sfb_gemm"] > 50 and n["sfb_attention"] > 0
+
+
+@pytest.mark.parametrize("key,value", [("act_fn", "gelu"), ("conv_in_kernel", 5), ("num_class_embeds", 10),
+                                       ("resnet_out_scale_factor", 2.0), ("attention_bias", True),
+                                       ("cross_attention_norm", "layer_norm"), ("time_embedding_type", "fourier")])
+def test_unsupported_config_values_are_rejected_by_name(key, value):
+    from sfast_b200.synthetic import SD15
+    from sfast_b200.unet_spec import spec_from_config
+    with pytest.raises(NotImplementedError, match=key):
+        spec_from_config(dict(SD15, **{key: value}))
+
+
+def test_packed_weights_refresh_keeps_storage_and_tracks_new_values():
+    """LoRA contract (reference preserve_parameters=True): packed copies are refreshed IN PLACE."""
+    import torch
+    from sfast_b200.plan import PackedWeights
+    from sfast_b200.synthetic import TINY
+    from sfast_b200.unet_spec import random_state_dict, spec_from_config
+    spec = spec_from_config(TINY)
+    sd = random_state_dict(spec, seed=3, dtype=torch.float32)
+    pw = PackedWeights(spec, sd, torch.float16, "cpu", dry=True)  # dry: no TMA maps (no driver here)
+    name = "down_blocks.0.resnets.0.conv1.weight"
+    m = pw.conv3x3(name)
+    lm = pw.ln_matrix(["down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.weight"],
+                      "down_blocks.0.attentions.0.transformer_blocks.0.norm1")
+    ptrs = (m.data.data_ptr(), lm[0].data.data_ptr(), lm[1].data_ptr(), pw.tproj_w.data_ptr())
+    before = m.data.clone()
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2[name] = sd2[name] * 2.0
+    pw.refresh(sd2)
+    assert (m.data.data_ptr(), lm[0].data.data_ptr(), lm[1].data_ptr(), pw.tproj_w.data_ptr()) == ptrs
+    torch.testing.assert_close(m.data.float(), before.float() * 2.0, rtol=2e-3, atol=1e-6)
+
+
+def test_controlnet_plan_adds_one_launch_and_thirteen_static_inputs():
+    import torch
+    from sfast_b200.plan import PackedWeights, UNetPlan
+    from sfast_b200.synthetic import SD15
+    from sfast_b200.unet_spec import param_shapes, spec_from_config
+    spec = spec_from_config(SD15)
+    sd = {k: torch.empty(v, device="meta") for k, v in param_shapes(spec).items()}
+    w = PackedWeights(spec, sd, torch.float16, "meta", dry=True)
+    base = UNetPlan(w, 2, 64, 64)
+    ctl = UNetPlan(w, 2, 64, 64, controlnet=True)
+    assert len(ctl.all_ops()) == len(base.all_ops()) + 1
+    assert len(ctl.ctrl_in) == 13 and not base.ctrl_in
+    shapes = [tuple(t.shape) for t in ctl.ctrl_in]
+    assert shapes[0] == (2, 320, 64, 64) and shapes[-2] == (2, 1280, 8, 8) and shapes[-1] == (2, 1280, 8, 8)
