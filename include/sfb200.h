@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 1
+#define SFB_ABI_VERSION 2
 
 typedef void* sfb_stream_t; /* cudaStream_t */
 
@@ -88,6 +88,11 @@ enum sfb_gemm_a_mode {
      * 4 phases back to back, each padded to a multiple of 160 rows ([4 * Np, 4 * cin],
      * K order (ty, tx, c)); M tiles of phase p are tiles [p * T, (p + 1) * T) of the grid. */
     SFB_A_UPCONV2X = 2,
+    /* Conv3d with a (3, 1, 1) kernel, padding (1, 0, 0), over the FRAME axis of a video tensor (SVD
+     * TemporalResnetBlock): the activation is viewed as NHWC [n = videos, h = frames, w = pixels
+     * per frame, c]; K = 3 * cin in (kt, c) order; tap kt reads frame f - 1 + kt (TMA zero fill =
+     * the temporal padding).  img_* / box_* describe that view. */
+    SFB_A_CONV3X1 = 3,
 };
 
 enum sfb_epilogue {
@@ -108,20 +113,12 @@ typedef struct sfb_gemm_params {
      * form that allows box_n > 1); box_w < img_w (must divide img_w) tiles the image with 2-D
      * patches, which is how widths that do not divide 128 (96, 104, ...) are handled. */
     int32_t img_n, img_h, img_w, cin, conv_stride, box_h, box_n, box_w;
-    /* split-K: >1 writes fp32 partials to `ws` ([splits, M, N]).  With `split_sync` (int32 [tiles],
-     * zero-initialised once, self re-arming) the split CTA of a tile that arrives last adds the
-     * other partials and finishes the tile itself; otherwise (or with gn_stats) a second kernel
-     * reduces. */
+    /* split-K: >1 writes fp32 partials to `ws` ([splits, M, N]); a second kernel sums them and runs
+     * the fused epilogue (or, with defer_finish, the consuming GroupNorm does). */
     int32_t splits;
     float* ws;
-    void* split_sync;
-    /* 1: the `splits` CTAs of one output tile form a thread-block cluster along grid.z and sum
-     * their fp32 partial tiles through distributed shared memory; CTA s finishes rows
-     * [s*128/splits, ...) of the tile.  No workspace, no second kernel.  Needs
-     * splits * (cta_pair ? 2 : 1) <= 16 (> 8 is a non-portable cluster size) and no gn_stats. */
-    int32_t cluster_k;
-    /* 1 (with splits > 1, STORE epilogue, no split_sync / cluster_k): only write the partials; the
-     * consumer (sfb_group_norm_fused with part_ws) finishes the tensor */
+    /* 1 (with splits > 1 and the STORE epilogue): only write the partials; the consumer
+     * (sfb_group_norm_fused with part_ws) finishes the tensor */
     int32_t defer_finish;
     /* epilogue */
     int32_t epi;
@@ -150,16 +147,14 @@ typedef struct sfb_gemm_params {
     int32_t vt_rows;         /* rows per (b, head) in V^T: (head_dim + 1) rounded up to 16; row
                               * `head_dim` must be pre-filled with ones (softmax denominator) */
     int32_t vt_pitch;        /* element pitch of a V^T row */
-    /* Thread-block cluster with TMA multicast (0/1 = off).  cluster_n (1|2) CTAs along N share one
-     * A tile: each loads 1/cluster_n of it (tmap_a box = 128/cluster_n rows; for the conv the box
-     * is split along `a_part_dim` (1 = w, 2 = h, 3 = n) into parts of `a_part_ext`) and multicasts.
-     * cluster_m (1|2|4) CTAs along M share one weight tile (tmap_b box = 160/cluster_m rows).
-     * The tile grid must be divisible by the cluster shape. */
-    int32_t cluster_n, cluster_m, a_part_dim, a_part_ext;
     /* 1: CTA pairs along M run tcgen05.mma.cta_group::2 on 256 x 160 tiles (each CTA stages its own
-     * A rows and HALF of the weight tile: tmap_b box = 80 rows); needs an even number of M tiles
-     * and cluster_n = cluster_m = 0/1. */
+     * A rows and HALF of the weight tile: tmap_b box = 80 rows); needs an even number of M tiles. */
     int32_t cta_pair;
+    /* 1 (with cta_pair, splits == 1): PERSISTENT kernel -- one CTA pair per two SMs loops over
+     * 256 x 320 tiles (two 160-column accumulator halves share one A tile), three rotating TMEM
+     * accumulators overlap the epilogue of tile i with the main loop of tile i + 1.  For launches
+     * of more than one wave of tiles. */
+    int32_t persistent;
     /* LayerNorm folded around the GEMM (replaces sfast_triton::layer_norm,
      * /root/reference/src/sfast/triton/ops/layer_norm.py:51-133, as a separate pass):
      *   producer (SFB_EPI_STORE): rowstats_out[m] += (sum, sum of squares) of the stored row;
@@ -171,20 +166,6 @@ typedef struct sfb_gemm_params {
     const float* ln_colsum;    /* [N] fp32: sum_k W'[n, k] */
     float ln_eps;
     int32_t ln_dim;
-    /* GroupNorm statistics of the tensor this GEMM produces, for up to two consumers (e.g. the next
-     * resnet's norm1 and, for a skip tensor, the up-block norm over the concat buffer it lives in):
-     * gn_stats[t][shard, img, group, 2] += (sum, sum of squares) of the stored values, with
-     * group = (gn_choff[t] + column) / gn_cpg[t], img = row / gn_rows_per_img and shard = one of 8
-     * copies `gn_shard_stride` floats apart (spreads same-address atomics; the consumer sums them).
-     * SFB_EPI_STORE only; buffers are caller-zeroed.  The consumer then runs sfb_group_norm_apply
-     * with stat_shards = 8. */
-    float* gn_stats[2];
-    int32_t gn_cpg[2], gn_choff[2];
-    int32_t gn_groups, gn_rows_per_img, gn_shard_stride;
-    /* optional profiling aid: int64 [ctas, 8] buffer receiving %globaltimer stamps per CTA
-     * (entry, setup done, first TMA issued, first data landed, MMAs issued, accumulator ready,
-     * epilogue stored, exit); NULL in production */
-    void* debug_stamps;
 } sfb_gemm_params;
 
 int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream);
@@ -215,15 +196,14 @@ typedef struct sfb_gn_params {
     void* y;         /* [n, hw, c] 16-bit, channel pitch ldy */
     const float* gamma;
     const float* beta;
-    float* stats;    /* [n, groups, 2] fp32 (sum, sum of squares); the CALLER zeroes it per use */
+    float* stats;    /* [n, groups, 2] fp32: SHIFTED moments (sum(x - K), sum((x - K)^2)) about the
+                      * group's first stored value K = x[img, 0, g * c/groups]; the CALLER zeroes it
+                      * per use */
     int32_t n, hw, c, ldx, ldy, groups;
     float eps;
     int32_t silu;    /* 1: y = silu(gn(x)) */
     int32_t dtype;
     uint32_t* sync_counter; /* sfb_group_norm_fused only: grid-barrier counter, zeroed by caller */
-    /* sfb_group_norm_apply: `stats` may arrive as `stat_shards` partial copies (0/1 = one),
-     * `stat_shard_stride` floats apart -- the layout sfb_gemm's GroupNorm accumulation writes */
-    int32_t stat_shards, stat_shard_stride;
     /* sfb_group_norm_fused only.  part_splits > 1: channels [0, part_c) of x do not exist yet --
      * they are the fp32 split-K partials `part_ws` ([part_splits, n*hw, part_ld]) of a sfb_gemm
      * launched with defer_finish.  The kernel sums them, applies that GEMM's STORE epilogue
@@ -242,9 +222,10 @@ typedef struct sfb_gn_params {
 /* two-pass path (any size): `stats` must be zero before sfb_group_norm_stats */
 int sfb_group_norm_stats(const sfb_gn_params* p, sfb_stream_t stream);
 int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream);
-/* single-launch path for tensors that fit in the GPU's shared memory (grid <= 148 CTAs with a
- * grid-wide barrier): x is read once.  `stats` and `sync_counter` must be zero on entry.
- * sfb_group_norm_fused_fits() returns 1 when the geometry qualifies. */
+/* single-launch path for tensors that fit in the GPU's shared memory: a COOPERATIVE launch of at
+ * most one CTA per SM of the current device with a grid-wide barrier; x is read once.  `stats` and
+ * `sync_counter` must be zero on entry.  sfb_group_norm_fused_fits() returns 1 when the geometry
+ * qualifies on the current device. */
 int sfb_group_norm_fused_fits(const sfb_gn_params* p);
 int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream);
 
@@ -302,6 +283,49 @@ int sfb_conv_out(const void* x, const void* w, const float* bias, void* y, int32
 /* nearest-neighbour 2x upsample, NHWC, 16-bit */
 int sfb_upsample2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
                    int32_t ldx, int32_t ldy, sfb_stream_t stream);
+
+/* ---- SVD temporal path (UNetSpatioTemporalConditionModel; the reference traces the diffusers
+ * module and leaves these to aten, compilers/diffusion_pipeline_compiler.py:101-103) ---------- */
+
+/* Self-attention across frames: for every (video b, pixel p, head h) a sequence of `frames` <= 32
+ * tokens of head_dim 64.  qkv is the fused projection [batch * frames * seq, ld_qkv] = q | k | v in
+ * the SPATIAL row order m = (b * frames + f) * seq + p (no transposed copy of the activations);
+ * out has the same row order. */
+typedef struct sfb_temporal_attn_params {
+    const void* qkv;
+    void* out;
+    int32_t batch, frames, seq, heads, head_dim;
+    int32_t ld_qkv, ld_out, dtype;
+    float scale;
+} sfb_temporal_attn_params;
+
+int sfb_temporal_attention(const sfb_temporal_attn_params* p, sfb_stream_t stream);
+
+enum sfb_row_index_mode {
+    SFB_ROW_IDX_DIV_MOD = 0,      /* vec row = (m / div) % mod */
+    SFB_ROW_IDX_TEMPORAL_CTX = 1, /* vec row = ((b * seq + p) % batch) * frames, m = (b*frames + f)*seq + p:
+                                   * diffusers' [H*W, B]-interleaved temporal cross-attention context */
+};
+
+/* Row-wise ops on token matrices [rows, c] of 16-bit elements, one warp per row:
+ *   sfb_row_broadcast_add: y[m, :] = x[m, :] + vec[idx(m), :]   (frame position embedding; cross-
+ *                          attention over ONE context token, where softmax over a single key is 1)
+ *   sfb_alpha_blend:       y[m, :] = alpha * x[m, :] + (1 - alpha) * x2[m, :], alpha = sigmoid(*mix_factor)
+ * rowstats_out (optional): [rows, 2] fp32 (sum, sum of squares) of the STORED row, overwritten --
+ * the statistics a following folded LayerNorm consumes (sfb_gemm ln_rowstats). */
+typedef struct sfb_row_op_params {
+    const void* x;
+    const void* x2;
+    const void* vec;
+    void* y;
+    float* rowstats_out;
+    const float* mix_factor;
+    int32_t rows, c, ldx, ldx2, ldv, ldy, dtype;
+    int32_t mode, div, mod, frames, seq, batch;
+} sfb_row_op_params;
+
+int sfb_row_broadcast_add(const sfb_row_op_params* p, sfb_stream_t stream);
+int sfb_alpha_blend(const sfb_row_op_params* p, sfb_stream_t stream);
 
 /* ControlNet residuals (reference: compile() leaves the ControlNet eager and the traced UNet takes
  * `down_block_additional_residuals` / `mid_block_additional_residual` as extra inputs,

@@ -97,10 +97,10 @@ def timestep_embedding(timesteps: torch.Tensor, dim: int, flip_sin_to_cos: bool,
 
 
 class TimestepEmbedding(nn.Module):
-    def __init__(self, in_dim, dim):
+    def __init__(self, in_dim, dim, out_dim=None):
         super().__init__()
         self.linear_1 = nn.Linear(in_dim, dim)
-        self.linear_2 = nn.Linear(dim, dim)
+        self.linear_2 = nn.Linear(dim, out_dim or dim)
 
     def forward(self, x):
         return self.linear_2(F.silu(self.linear_1(x)))
@@ -364,6 +364,7 @@ class UNet2DConditionModel(nn.Module):
         return self.conv_in.weight.device
 
     def forward(self, sample, timestep, encoder_hidden_states, added_cond_kwargs=None,
+                down_block_additional_residuals=None, mid_block_additional_residual=None,
                 return_dict=True, **unused):
         cfg = self.config
         b = sample.shape[0]
@@ -386,7 +387,13 @@ class UNet2DConditionModel(nn.Module):
         for blk in self.down_blocks:
             x, outs = blk(x, emb, encoder_hidden_states)
             skips.extend(outs)
+        if down_block_additional_residuals is not None:
+            # ControlNet (diffusers UNet2DConditionModel.forward): every skip tensor gets its
+            # residual added AFTER the down path has consumed the un-modified one
+            skips = [s + r for s, r in zip(skips, down_block_additional_residuals)]
         x = self.mid_block(x, emb, encoder_hidden_states)
+        if mid_block_additional_residual is not None:
+            x = x + mid_block_additional_residual
         for blk in self.up_blocks:
             x = blk(x, skips, emb, encoder_hidden_states)
         x = self.conv_out(F.silu(self.conv_norm_out(x)))

@@ -2,15 +2,27 @@
 //
 //   D[M, N] = A[M, K] * W[N, K]^T   (fp16/bf16 operands, fp32 accumulation in TMEM)
 //
-// One 128 x 160 output tile per CTA.  Warp roles (64 + 32 * kEpiWarps threads):
-//   warp 0      TMA producer: A tile (128 rows x 64 K) + W tile (160 rows x 64 K) per stage,
-//               both landing in 128-byte-swizzled K-major shared memory;
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per stage);
+// Two kernels share one epilogue vocabulary:
+//
+//  gemm_tc_kernel       one 128 x 160 tile per CTA (CG = 1) or one 256 x 160 tile per CTA PAIR
+//                       (CG = 2, tcgen05.mma.cta_group::2).  Used for single-wave launches and for
+//                       split-K (the weight-bandwidth-bound low-resolution layers).
+//  gemm_persist_kernel  PERSISTENT CTA pairs, one pair per two SMs, looping over 256 x 320 tiles
+//                       (two 160-column accumulator halves sharing one A tile: 1.45x fewer bytes
+//                       pulled from L2 per FLOP than 256 x 160 -- the main loop is bound by what
+//                       an SM can ingest), with THREE rotating 160-column
+//                       TMEM accumulators so that the epilogue of tile i overlaps the main loop of
+//                       tile i + 1 and the prologue / teardown is paid once per SM, not per tile.
+//
+// Warp roles (64 + 32 * kEpiWarps threads):
+//   warp 0      TMA producer: A tile (128 rows x 64 K) + W tile(s) per stage, 128-byte-swizzled
+//               K-major shared memory;
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per stage and half);
 //   warps 2..   epilogue: tcgen05.ld the accumulator (thread = row), fuse bias / time-embedding
-//               row bias / residual / GEGLU / QKV head scatter, store 16-byte vectors.
+//               row bias / LayerNorm fold / residual / GEGLU / QKV head scatter, 16-byte stores.
 // For the convolution the A tile of filter tap (kh, kw) is a *shifted NHWC box*: the tile's
-// 128 output pixels are a [box_n, box_h, W] block, so one 4-D TMA box load at
-// (c, kw-1, h0*stride+kh-1, n0) is exactly the im2col slice, and TMA's out-of-bounds zero fill
+// 128 output pixels are a [box_n, box_h, box_w] block, so one 4-D TMA box load at
+// (c, w0+kw-1, h0*stride+kh-1, n0) is exactly the im2col slice, and TMA's out-of-bounds zero fill
 // is the convolution's zero padding.  No im2col buffer, no index tables.
 //
 // Replaces: cudnn_convolution_bias(_add) (/root/reference/src/sfast/csrc/operators/cudnn/
@@ -27,6 +39,7 @@ namespace sfb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int BN = 160;
 // epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, each converting half of the
 // tile's columns -- the epilogue is latency-bound with a single warp per SM sub-partition)
 #ifndef SFB_EPI_WARPS
@@ -40,6 +53,9 @@ constexpr int kGemmThreads = 64 + kEpiThreads;
 __device__ __forceinline__ void epi_bar() {
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
+
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
 
 struct EpiArgs {
     int epi;
@@ -58,10 +74,6 @@ struct EpiArgs {
     void* k;
     void* vt;
     int heads, head_dim, which_base, seq, q_pitch, q_rows, k_rows, vt_rows, vt_pitch;
-    // GroupNorm statistics of the tensor this GEMM writes, accumulated for up to two consumers
-    float* gn_stats[2];
-    int gn_cpg[2], gn_choff[2];
-    int gn_groups, gn_rpi, gn_shard_stride;  // floats between two of the 8 accumulation shards
     // LayerNorm folded around the GEMM (see sfb200.h): producer side / consumer side
     float* rowstats_out;
     const float* ln_rowstats;
@@ -84,28 +96,19 @@ struct GemmArgs {
     int a_mode;
     int nkb_total;  // K / 64
     int splits;
-    int pdl;        // launched with programmatic stream serialization
-    long long* dbg; // optional: per-CTA %globaltimer stamps (8 per CTA) for latency breakdowns
-    int* split_sync; // [tiles][2] arrive / done counters of the fused split-K reduction (or null)
-    // cluster split-K: the `splits` CTAs of one output tile form a cluster along grid.z and sum their
-    // fp32 partial tiles through distributed shared memory (no workspace, no second kernel)
-    int cluster_k;
     float* ws;
     // conv geometry
     int img_n, img_h, img_w, cpb /* cin / 64 */, conv_stride, box_h, box_n, tiles_per_img;
     int box_w, tiles_per_row;  // M tile = [box_n, box_h, box_w] pixels; box_w < img_w: 2-D patches
     int up_tiles;   // SFB_A_UPCONV2X: M tiles per output phase
     int up_ntiles;  // ... and N tiles per phase in the phase-concatenated weight matrix
-    // thread-block cluster (cx along N: the cx CTAs of one M-tile each load 1/cx of the A tile and
-    // multicast it; cy along M: the cy CTAs of one N-tile each load 1/cy of the weight tile)
-    int cx, cy;
-    int a_part_dim;  // conv: which box dim the A tile is split along (1 = w, 2 = h, 3 = n)
-    int a_part_ext;  // extent of one part along that dim (output pixels / rows / images)
+    // persistent kernel: tile grid in units of (pair of M tiles) x (pair of 160-column N tiles)
+    int m_pairs, n_tiles160, n_pairs, total_tiles;
     EpiArgs e;
 };
 
 // ---------------------------------------------------------------------------------------
-// epilogue building blocks (shared by the GEMM kernel and the split-K reduction kernel)
+// epilogue building blocks (shared by both GEMM kernels and the split-K reduction kernel)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void add_bias8(const float* __restrict__ b, int n, float (&acc)[8]) {
     const float4 b0 = *reinterpret_cast<const float4*>(b + n);
@@ -129,42 +132,6 @@ __device__ __forceinline__ void add_res8(uint4 r, int dtype, float (&acc)[8]) {
     f = unpack2(r.y, dtype); acc[2] += f.x; acc[3] += f.y;
     f = unpack2(r.z, dtype); acc[4] += f.x; acc[5] += f.y;
     f = unpack2(r.w, dtype); acc[6] += f.x; acc[7] += f.y;
-}
-
-template <int BF16>
-__device__ __forceinline__ float round16(float v) {
-    if (BF16) return __bfloat162float(__float2bfloat16_rn(v));
-    return __half2float(__float2half_rn(v));
-}
-
-// GroupNorm partial sums of 8 stored values (row m, columns n..n+7) into block-shared accumulators
-// sacc[2 targets][2 images][groups][2] (images img0, img0+1; anything else goes straight to global
-// memory).  Used by the split-K reduction kernel, where a thread owns one 8-column slice.
-template <int BF16>
-__device__ __forceinline__ void gn_accumulate8(const EpiArgs& e, int m, int n, const float (&acc)[8],
-                                               float* sacc, int img0, int shard) {
-    const int img = m / e.gn_rpi;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        if (!e.gn_stats[t]) continue;
-        int g_run = (e.gn_choff[t] + n) / e.gn_cpg[t];
-        float s = 0.f, ss = 0.f;
-        auto flush = [&]() {
-            float* d = (img == img0 || img == img0 + 1)
-                ? sacc + ((t * 2 + (img - img0)) * e.gn_groups + g_run) * 2
-                : e.gn_stats[t] + (size_t)shard * e.gn_shard_stride + ((size_t)img * e.gn_groups + g_run) * 2;
-            atomicAdd(d, s);
-            atomicAdd(d + 1, ss);
-        };
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int g = (e.gn_choff[t] + n + i) / e.gn_cpg[t];
-            if (g != g_run) { flush(); g_run = g; s = 0.f; ss = 0.f; }
-            const float v = round16<BF16>(acc[i]);
-            s += v; ss += v * v;
-        }
-        flush();
-    }
 }
 
 // (sum, sum of squares) of 8 values as they will be stored (rounded to the 16-bit type)
@@ -259,17 +226,48 @@ __device__ __forceinline__ bool tile_row_to_m(const GemmArgs& a, int tile, int r
     return (n < a.img_n) && (h < a.img_h);
 }
 
+// A-operand TMA coordinates of M-tile `m_tile`: conv tile origin, up-conv phase, weight row block
+struct ATile {
+    int n0, h0, w0, up_py, up_px, b_nbase;  // b_nbase: first 160-row weight tile of the phase
+};
+__device__ __forceinline__ ATile a_tile_coords(const GemmArgs& a, int m_tile) {
+    ATile t{0, 0, 0, 0, 0, 0};
+    if (a.a_mode != SFB_A_MATRIX) {
+        int mt = m_tile;
+        if (a.a_mode == SFB_A_UPCONV2X) {
+            const int ph = m_tile / a.up_tiles;
+            mt = m_tile - ph * a.up_tiles;
+            t.up_py = ph >> 1; t.up_px = ph & 1;
+            t.b_nbase = ph * a.up_ntiles;
+        }
+        conv_tile_origin(a, mt, t.n0, t.h0, t.w0);
+    }
+    return t;
+}
+// conv tap of K block -> (w, h) source offset of the A box
+__device__ __forceinline__ void tap_offset(const GemmArgs& a, const ATile& t, int tap, int& dw, int& dh) {
+    if (a.a_mode == SFB_A_UPCONV2X) {  // 2x2 taps of phase (py, px) sit at (py - 1 + ty, px - 1 + tx)
+        const int ty = tap >> 1, tx = tap & 1;
+        dw = t.up_px - 1 + tx;
+        dh = t.up_py - 1 + ty;
+    } else if (a.a_mode == SFB_A_CONV3X1) {  // temporal conv: taps along the frame (h) axis only
+        dw = 0;
+        dh = tap - 1;
+    } else {
+        const int kh = tap / 3, kw = tap - kh * 3;
+        dw = kw - 1;
+        dh = kh - 1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // split-K reduction + epilogue
 // ---------------------------------------------------------------------------------------
 // Sum the `splits` fp32 partials of 8 output columns of row m and run the fused epilogue on them.
 // `n` is the output column (GEGLU: output column of the gated product).  Partials were written by
 // other SMs: read them through L2 (ld.global.cg).
-// `sum8(col, acc)` yields the summed partials of global columns [col, col+8) of row m.
-template <int BN, int BF16, typename Sum8>
-__device__ __forceinline__ void reduce_epilogue8(Sum8&& sum8, const EpiArgs& e, int m, int n,
-                                                 float* gn_sacc = nullptr, int gn_img0 = 0,
-                                                 int gn_shard = 0) {
+template <int BF16, typename Sum8>
+__device__ __forceinline__ void reduce_epilogue8(Sum8&& sum8, const EpiArgs& e, int m, int n) {
     if (e.epi == SFB_EPI_GEGLU) {
         const int tile = n / (BN / 2);
         const int nv = tile * BN + (n - tile * (BN / 2));
@@ -312,15 +310,22 @@ __device__ __forceinline__ void reduce_epilogue8(Sum8&& sum8, const EpiArgs& e, 
             atomicAdd(e.rowstats_out + 2 * (size_t)m, rs);
             atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rss);
         }
-        if (gn_sacc) gn_accumulate8<BF16>(e, m, n, acc, gn_sacc, gn_img0, gn_shard);
         epi_store8<BF16>(e, m, n, acc);
     }
 }
 
-template <int BN, int BF16>
-__device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int splits, const EpiArgs& e,
-                                               int m, int n, float* gn_sacc = nullptr, int gn_img0 = 0,
-                                               int gn_shard = 0) {
+// Stand-alone split-K reduction kernel.  One thread per (row, 8 columns); convs that feed a
+// GroupNorm skip it (defer_finish) and let that kernel sum the partials.
+template <int BF16>
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
+    const int groups = ncols / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)e.M * groups) return;
+    const int m = (int)(idx / groups), n = (int)(idx % groups) * 8;
     auto sum8 = [&](int col, float (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -348,56 +353,16 @@ __device__ __forceinline__ void splitk_reduce8(const float* __restrict__ ws, int
             }
         }
     };
-    reduce_epilogue8<BN, BF16>(sum8, e, m, n, gn_sacc, gn_img0, gn_shard);
-}
-
-// Stand-alone split-K reduction kernel (the default: measured faster than the in-kernel variants,
-// DESIGN.md section 4.1).  One thread per (row, 8 columns); convs that feed a GroupNorm skip it
-// (defer_finish) and let that kernel sum the partials.
-template <int BN, int BF16>
-__global__ void __launch_bounds__(256)
-splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
-    const int groups = ncols / 8;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = idx < (long long)e.M * groups;
-    __shared__ float sacc[2 * 2 * 64 * 2];
-    const bool gn = e.gn_stats[0] != nullptr && e.epi == SFB_EPI_STORE;
-    int img0 = 0;
-    if (gn) {
-        for (int i = threadIdx.x; i < 2 * 2 * e.gn_groups * 2; i += blockDim.x) sacc[i] = 0.f;
-        const long long first = (long long)blockIdx.x * blockDim.x;
-        img0 = (int)(first / groups) / e.gn_rpi;
-        __syncthreads();
-    }
-    if (active)
-        splitk_reduce8<BN, BF16>(ws, splits, e, (int)(idx / groups), (int)(idx % groups) * 8,
-                                 gn ? sacc : nullptr, img0, blockIdx.x & 7);
-    if (gn) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 2 * 2 * e.gn_groups; i += blockDim.x) {
-            const int t = i / (2 * e.gn_groups), im = (i / e.gn_groups) & 1, g = i % e.gn_groups;
-            const float a0 = sacc[i * 2], a1 = sacc[i * 2 + 1];
-            if (e.gn_stats[t] && (a0 != 0.f || a1 != 0.f)) {
-                float* d = e.gn_stats[t] + (size_t)(blockIdx.x & 7) * e.gn_shard_stride +
-                           ((size_t)(img0 + im) * e.gn_groups + g) * 2;
-                atomicAdd(d, a0);
-                atomicAdd(d + 1, a1);
-            }
-        }
-    }
+    reduce_epilogue8<BF16>(sum8, e, m, n);
 }
 
 // ---------------------------------------------------------------------------------------
-// the GEMM kernel
+// one-tile-per-CTA kernel
 // ---------------------------------------------------------------------------------------
-// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster 1x2 along M) computes a 256 x BN
+// CG = 1: one CTA per 128 x 160 tile.  CG = 2: a CTA PAIR (cluster 2x1 along M) computes a 256 x 160
 // tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 A rows but only HALF of the
-// weight tile, which cuts the shared-memory traffic per MMA (the 1-CTA kernel is smem-bandwidth
-// bound: 36 KB written + 36 KB read per 320 MMA cycles at 128 B/clk).
-template <int BN, int STAGES, int CG = 1>
+// weight tile, which cuts the bytes each SM pulls per MMA.
+template <int STAGES, int CG = 1>
 struct GemmSmem {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2 / CG;
@@ -412,21 +377,20 @@ struct GemmSmem {
     // +4 float pad makes the thread-per-row float4 writes of phase A bank-conflict free
     static constexpr int kStagePitch = BN + 4;
     // QKV scatter tables (row -> (batch, position), column slice -> (q/k/v, offset)), also aliased
-    // onto the idle stage buffers, behind the GroupNorm accumulators
-    static constexpr int kQkvRowOffset = BM * kStagePitch * 4 + BM * 4 + 2 * 8 * (BN / 2 + 2) * 2 * 4;
+    // onto the idle stage buffers
+    static constexpr int kQkvRowOffset = BM * kStagePitch * 4;
     static constexpr int kQkvColOffset = kQkvRowOffset + BM * 8;
     static_assert(kQkvColOffset + (BN / 8) * 16 <= kBarOffset,
-                  "staging tile + GroupNorm accumulators + QKV tables must fit in the stage buffers");
+                  "staging tile + QKV tables must fit in the stage buffers");
     static_assert(STAGES > 4 || 2 * (kTotal + 1024) <= 228 * 1024, "shallow configs must fit twice per SM");
-    static_assert(BN == 160, "the epilogue's 32+32+16 TMEM load split assumes 80-column halves");
 };
 
-template <int BN, int STAGES, int BF16, int CG>
+template <int STAGES, int BF16, int CG>
 __global__ void __launch_bounds__(kGemmThreads, STAGES <= 4 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmArgs args) {
-    using L = GemmSmem<BN, STAGES, CG>;
-    constexpr uint32_t kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+    using L = GemmSmem<STAGES, CG>;
+    constexpr uint32_t kTmemCols = 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
     uint8_t* sA = smem;
@@ -445,10 +409,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // so the M tiles run along grid.x there (grid = (m_tiles, n_tiles, splits), cluster (2,1,1))
     const int n_tile = CG == 2 ? blockIdx.y : blockIdx.x;
     const int m_tile = CG == 2 ? blockIdx.x : blockIdx.y;
-    const int n_tiles_grid = CG == 2 ? gridDim.y : gridDim.x;
     const int split = blockIdx.z;
-    long long* dbg = args.dbg ? args.dbg + 8 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
-    if (dbg && threadIdx.x == 0) dbg[0] = globaltimer_ns();
     const int kb_begin = (int)(((long long)args.nkb_total * split) / args.splits);
     const int kb_end = (int)(((long long)args.nkb_total * (split + 1)) / args.splits);
     const int nkb = kb_end - kb_begin;
@@ -458,24 +419,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_prefetch_desc(&tma_b);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            // released by every CTA whose stage this CTA's multicasts write into (pair mode: by
-            // the leader's multicast commit only)
-            mbar_init(&empty_bar[i], CG == 2 ? 1 : args.cx + args.cy - 1);
+            mbar_init(&empty_bar[i], 1);
         }
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    const bool mcast = (CG == 1) && args.cx * args.cy > 1;
-    const bool clustered = (CG == 2) || mcast || args.cluster_k;
-    // pair mode inside a larger (split-K) cluster: the pair is ranks (2j, 2j+1)
-    const uint16_t pair_mask = (uint16_t)(0b11u << (clustered ? (cluster_ctarank() & ~1u) : 0u));
-    const int cix = mcast ? (int)cluster_ctaid_x() : 0;
-    const int ciy = CG == 2 ? (int)cluster_ctaid_x() : (mcast ? (int)cluster_ctaid_y() : 0);
+    const uint16_t pair_mask = 0b11;
+    const int ciy = CG == 2 ? (int)cluster_ctaid_x() : 0;
     const bool leader = (CG == 1) || ciy == 0;  // pair mode: the even CTA issues every MMA
-    // CTAs sharing this CTA's A tile (same M-tile: all cix) / weight tile (same N-tile: all ciy)
-    const uint16_t mask_a = (uint16_t)(((1u << args.cx) - 1u) << (ciy * args.cx));
-    uint16_t mask_b = 0;
-    for (int y = 0; y < args.cy; ++y) mask_b |= (uint16_t)(1u << (y * args.cx + cix));
     if (warp == 1) {
         if (CG == 2) tmem_alloc_pair<kTmemCols>(tmem_slot);
         else tmem_alloc<kTmemCols>(tmem_slot);
@@ -484,93 +435,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // dependent launch); global memory produced by it is only touched after that wait.
     pdl_launch_dependents();
     tc_fence_before();
-    if (clustered) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts
+    if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (dbg && threadIdx.x == 0) dbg[1] = globaltimer_ns();
 
     if (warp == 0) {
         if (lane == 0) {
             pdl_wait();
-            int n0 = 0, h0 = 0, w0 = 0;
-            // up-conv: output phase (py, px) of this M tile; its 2x2 taps sit at source offsets
-            // (py - 1 + ty, px - 1 + tx).  The weight tile comes from the phase's row block.
-            int up_py = 0, up_px = 0, b_ntile = n_tile;
-            if (args.a_mode != SFB_A_MATRIX) {
-                int mt = m_tile;
-                if (args.a_mode == SFB_A_UPCONV2X) {
-                    const int ph = m_tile / args.up_tiles;
-                    mt = m_tile - ph * args.up_tiles;
-                    up_py = ph >> 1; up_px = ph & 1;
-                    b_ntile = ph * args.up_ntiles + n_tile;
-                }
-                conv_tile_origin(args, mt, n0, h0, w0);
-            }
-            // conv tap of K block kb -> (w, h) source offset of the A box
-            auto tap_offset = [&](int tap, int& dw, int& dh) {
-                if (args.a_mode == SFB_A_UPCONV2X) {
-                    const int ty = tap >> 1, tx = tap & 1;
-                    dw = up_px - 1 + tx;
-                    dh = up_py - 1 + ty;
-                } else {
-                    const int kh = tap / 3, kw = tap - kh * 3;
-                    dw = kw - 1;
-                    dh = kh - 1;
-                }
-            };
+            const ATile at = a_tile_coords(args, m_tile);
+            const int b_ntile = at.b_nbase + n_tile;
             for (int i = 0; i < nkb; ++i) {
                 const int stage = i % STAGES;
                 const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 const int kb = kb_begin + i;
+                uint8_t* dA = sA + stage * L::kABytes;
+                uint8_t* dB = sB + stage * L::kBBytes;
+                // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous 160 x 64 block
+                const int b_row = (b_ntile * args.nkb_total + kb) * BN + ciy * (BN / 2);
+                int c0 = kb * BK, c1 = m_tile * BM, c2 = 0, c3 = 0;
+                if (args.a_mode != SFB_A_MATRIX) {
+                    const int tap = kb / args.cpb;
+                    int dw, dh;
+                    tap_offset(args, at, tap, dw, dh);
+                    c0 = (kb - tap * args.cpb) * BK;
+                    c1 = at.w0 * args.conv_stride + dw;
+                    c2 = at.h0 * args.conv_stride + dh;
+                    c3 = at.n0;
+                }
                 if (CG == 2) {
                     // pair mode: both CTAs' bytes are counted on the LEADER's barrier
                     if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-                    uint8_t* dA = sA + stage * L::kABytes;
-                    uint8_t* dB = sB + stage * L::kBBytes;
-                    const int b_row2 = (b_ntile * args.nkb_total + kb) * BN + ciy * (BN / 2);
-                    if (args.a_mode == SFB_A_MATRIX) {
-                        tma_load_2d_pair(dA, &tma_a, &full_bar[stage], kb * BK, m_tile * BM);
-                    } else {
-                        const int tap = kb / args.cpb;
-                        const int cc = kb - tap * args.cpb;
-                        int dw, dh;
-                        tap_offset(tap, dw, dh);
-                        tma_load_4d_pair(dA, &tma_a, &full_bar[stage], cc * BK, w0 * args.conv_stride + dw,
-                                         h0 * args.conv_stride + dh, n0);
-                    }
-                    tma_load_2d_pair(dB, &tma_b, &full_bar[stage], 0, b_row2);
-                    continue;
-                }
-                mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-                uint8_t* dstA = sA + stage * L::kABytes + cix * (L::kABytes / args.cx);
-                uint8_t* dstB = sB + stage * L::kBBytes + ciy * (L::kBBytes / args.cy);
-                // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous BN x 64 block
-                const int b_row = (b_ntile * args.nkb_total + kb) * BN + ciy * (BN / args.cy);
-                if (args.a_mode == SFB_A_MATRIX) {
-                    const int a_row = m_tile * BM + cix * (BM / args.cx);
-                    if (args.cx > 1) tma_load_2d_mc(dstA, &tma_a, &full_bar[stage], kb * BK, a_row, mask_a);
-                    else tma_load_2d(dstA, &tma_a, &full_bar[stage], kb * BK, a_row);
+                    if (args.a_mode == SFB_A_MATRIX) tma_load_2d_pair(dA, &tma_a, &full_bar[stage], c0, c1);
+                    else tma_load_4d_pair(dA, &tma_a, &full_bar[stage], c0, c1, c2, c3);
+                    tma_load_2d_pair(dB, &tma_b, &full_bar[stage], 0, b_row);
                 } else {
-                    const int tap = kb / args.cpb;
-                    const int cc = kb - tap * args.cpb;
-                    int dw, dh;
-                    tap_offset(tap, dw, dh);
-                    int c1 = w0 * args.conv_stride + dw, c2 = h0 * args.conv_stride + dh, c3 = n0;
-                    if (args.cx > 1) {
-                        const int off = cix * args.a_part_ext;
-                        if (args.a_part_dim == 1) c1 += off * args.conv_stride;
-                        else if (args.a_part_dim == 2) c2 += off * args.conv_stride;
-                        else c3 += off;
-                        tma_load_4d_mc(dstA, &tma_a, &full_bar[stage], cc * BK, c1, c2, c3, mask_a);
-                    } else {
-                        tma_load_4d(dstA, &tma_a, &full_bar[stage], cc * BK, c1, c2, c3);
-                    }
+                    mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                    if (args.a_mode == SFB_A_MATRIX) tma_load_2d(dA, &tma_a, &full_bar[stage], c0, c1);
+                    else tma_load_4d(dA, &tma_a, &full_bar[stage], c0, c1, c2, c3);
+                    tma_load_2d(dB, &tma_b, &full_bar[stage], 0, b_row);
                 }
-                if (args.cy > 1) tma_load_2d_mc(dstB, &tma_b, &full_bar[stage], 0, b_row, mask_b);
-                else tma_load_2d(dstB, &tma_b, &full_bar[stage], 0, b_row);
-                if (dbg && i == 0) dbg[2] = globaltimer_ns();
             }
         }
         __syncwarp();
@@ -582,7 +487,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                if (dbg && i == 0) dbg[3] = globaltimer_ns();
                 const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * L::kABytes));
                 const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::kBBytes));
 #pragma unroll
@@ -596,12 +500,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                     (i | k) != 0);
                 }
                 if (CG == 2) umma_commit_pair(&empty_bar[stage], pair_mask);
-                else if (mcast) umma_commit_mc(&empty_bar[stage], (uint16_t)(mask_a | mask_b));
                 else umma_commit(&empty_bar[stage]);
             }
             if (CG == 2) umma_commit_pair(tmem_full_bar, pair_mask);
             else umma_commit(tmem_full_bar);
-            if (dbg) dbg[4] = globaltimer_ns();
         }
         __syncwarp();
     } else {
@@ -615,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         sRowM[r] = valid ? m : -1;
         if (args.splits == 1) {
             // stage bias (+ per-image time-embedding row bias) for this tile's columns in smem;
-            // only the four epilogue warps take part (named barrier 1), the TMA / MMA warps are
+            // only the epilogue warps take part (named barrier 1), the TMA / MMA warps are
             // already streaming
             const EpiArgs& e = args.e;
             int img0 = 0, nslots = 1;
@@ -690,7 +592,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        if (dbg && threadIdx.x == 64) dbg[5] = globaltimer_ns();
         // QKV scatter: the integer divisions of the address computation once per row / per column
         // slice (tables in the now idle stage buffers) instead of five per stored 16-byte slice
         int2* sQkvRow = reinterpret_cast<int2*>(smem + L::kQkvRowOffset);
@@ -736,14 +637,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         };
         constexpr int kChunks = kColsPer / kChunk;
-        // (software-pipelining these TMEM reads -- next chunk in flight while this one is converted --
-        // was measured: no gain, 4.87 vs 4.83 ms per step)
 #pragma unroll 1
         for (int cb = 0; cb < kChunks; ++cb) {
             uint32_t v[kChunk];
             const int c0 = chalf * kColsPer + cb * kChunk;
-            if constexpr (kChunk == 32) tmem_ld32(trow + c0, v);
-            else tmem_ld16(trow + c0, v);
+            tmem_ld_chunk(trow + c0, v);
             tmem_wait_ld();
             stage_chunk(v, c0);
         }
@@ -755,9 +653,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const float4 b = *reinterpret_cast<const float4*>(sStage + row * L::kStagePitch + col + 4);
             f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
         };
-        if (partial && args.cluster_k) {
-            // the reduction happens after the cluster barrier below (all warps take part in it)
-        } else if (partial) {
+        if (partial) {
 #pragma unroll 1
             for (int it = 0; it < kItems; ++it) {
                 const int idx = et + it * kEpiThreads;
@@ -769,70 +665,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     float* dst = args.ws + ((size_t)split * e.M + mm) * e.N + n;
                     *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
                     *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                }
-            }
-            if (args.split_sync) {
-                // Fused reduction, no waiting: every split CTA publishes its partial tile and bumps
-                // the tile's counter; whoever arrives LAST (its own partial is still in shared
-                // memory) adds the other partials from L2 and runs the epilogue.  No co-residency
-                // requirement, no second kernel.  The last CTA re-arms the counter.
-                int* cnt = args.split_sync + (m_tile * n_tiles_grid + n_tile);
-                int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
-                __threadfence();
-                epi_bar();
-                if (et == 0) {
-                    const int old = atomicAdd(cnt, 1);
-                    const int last = old == args.splits - 1;
-                    if (last) *reinterpret_cast<volatile int*>(cnt) = 0;
-                    *s_last = last;
-                }
-                epi_bar();
-                if (*s_last) {
-                    __threadfence();
-                    for (int ps = 0; ps < args.splits; ++ps) {
-                        if (ps == split) continue;
-                        const float* wsp = args.ws + (size_t)ps * e.M * e.N;
-#pragma unroll 1
-                        for (int b = 0; b < kItems / kBatch; ++b) {
-                            float4 lo[kBatch], hi[kBatch];
-#pragma unroll
-                            for (int j = 0; j < kBatch; ++j) {
-                                int row, grp, mm, n;
-                                item_addr(b * kBatch + j, row, grp, mm, n);
-                                if (mm >= 0 && n < e.N) {
-                                    const float* src = wsp + (size_t)mm * e.N + n;
-                                    lo[j] = __ldcg(reinterpret_cast<const float4*>(src));
-                                    hi[j] = __ldcg(reinterpret_cast<const float4*>(src + 4));
-                                } else {
-                                    lo[j] = hi[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < kBatch; ++j) {
-                                int row, grp, mm, n;
-                                item_addr(b * kBatch + j, row, grp, mm, n);
-                                float4* d = reinterpret_cast<float4*>(sStage + row * L::kStagePitch + grp * 8);
-                                float4 x = d[0], y = d[1];
-                                x.x += lo[j].x; x.y += lo[j].y; x.z += lo[j].z; x.w += lo[j].w;
-                                y.x += hi[j].x; y.y += hi[j].y; y.z += hi[j].z; y.w += hi[j].w;
-                                d[0] = x; d[1] = y;
-                            }
-                        }
-                    }
-                    epi_bar();  // the epilogue below re-partitions the tile among the threads
-                    const bool geglu = e.epi == SFB_EPI_GEGLU;
-                    const int gpr = geglu ? kGroups / 2 : kGroups;  // items per row
-#pragma unroll 1
-                    for (int idx = et; idx < BM * gpr; idx += kEpiThreads) {
-                        const int row = idx / gpr, grp = idx - row * gpr;
-                        const int mm = sRowM[row];
-                        const int n = (geglu ? n_tile * (BN / 2) : ncol0) + grp * 8;
-                        if (mm < 0 || n >= (geglu ? e.geglu_n_out : e.N)) continue;
-                        auto sum8 = [&](int col, float (&acc)[8]) {
-                            load8(row, col - ncol0, acc);
-                        };
-                        reduce_epilogue8<BN, BF16>(sum8, e, mm, n);
-                    }
                 }
             }
         } else if (e.epi == SFB_EPI_GEGLU) {
@@ -864,7 +696,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             float f[8];
                             load8(row, grp * 8, f);
                             if (has_res) add_res8(rcur[j], BF16, f);
-                            if (e.rowstats_out || e.gn_stats[0]) {  // final values back to the tile (row / column sums)
+                            if (e.rowstats_out) {  // final values back to the tile (row sums below)
                                 float* d = sStage + row * L::kStagePitch + grp * 8;
                                 *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
                                 *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -908,66 +740,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
             }
-            if (e.gn_stats[0] && e.epi == SFB_EPI_STORE) {
-                // GroupNorm statistics of the finished tile for the consumer(s): per-column sums over
-                // the tile's rows (split at image boundaries), merged per group in shared memory, then
-                // one fire-and-forget global atomic per (consumer, image, group, moment).
-                constexpr int kMaxImg = 8, kMaxGrp = BN / 2 + 2;
-                int* sRowImg = reinterpret_cast<int*>(smem + BM * L::kStagePitch * 4);
-                float* sGn = reinterpret_cast<float*>(sRowImg + BM);  // [2][kMaxImg][kMaxGrp][2]
-                sRowImg[r] = valid ? m / e.gn_rpi : -1;
-                for (int i = et; i < 2 * kMaxImg * kMaxGrp * 2; i += kEpiThreads) sGn[i] = 0.f;
-                epi_bar();
-                const int img_base = sRowImg[0];
-                int gfirst[2] = {0, 0};
-#pragma unroll
-                for (int t = 0; t < 2; ++t)
-                    if (e.gn_stats[t]) gfirst[t] = (e.gn_choff[t] + ncol0) / e.gn_cpg[t];
-                for (int c = et; c < BN; c += kEpiThreads) {
-                    const int n = ncol0 + c;
-                    if (n >= e.N) continue;
-                    int gl[2] = {0, 0};
-#pragma unroll
-                    for (int t = 0; t < 2; ++t)
-                        if (e.gn_stats[t]) gl[t] = (e.gn_choff[t] + n) / e.gn_cpg[t] - gfirst[t];
-                    float cs = 0.f, css = 0.f;
-                    int cur = -1;
-                    auto flush = [&]() {
-                        if (cur < 0) return;
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            if (!e.gn_stats[t]) continue;
-                            float* d = sGn + ((t * kMaxImg + (cur - img_base)) * kMaxGrp + gl[t]) * 2;
-                            atomicAdd(d, cs);
-                            atomicAdd(d + 1, css);
-                        }
-                    };
-#pragma unroll 4
-                    for (int row = 0; row < BM; ++row) {
-                        const int img = sRowImg[row];
-                        if (img < 0) continue;
-                        if (img != cur) { flush(); cur = img; cs = 0.f; css = 0.f; }
-                        const float v = round16<BF16>(sStage[row * L::kStagePitch + c]);
-                        cs += v;
-                        css += v * v;
-                    }
-                    flush();
-                }
-                epi_bar();
-                for (int i = et; i < 2 * kMaxImg * kMaxGrp; i += kEpiThreads) {
-                    const int t = i / (kMaxImg * kMaxGrp);
-                    const int slot = (i / kMaxGrp) % kMaxImg, g = i % kMaxGrp;
-                    if (!e.gn_stats[t]) continue;
-                    const float a0 = sGn[i * 2], a1 = sGn[i * 2 + 1];
-                    if (a0 != 0.f || a1 != 0.f) {
-                        // 8 accumulation shards (by M tile) keep same-address atomic contention low
-                        float* d = e.gn_stats[t] + (size_t)(m_tile & 7) * e.gn_shard_stride +
-                                   ((size_t)(img_base + slot) * e.gn_groups + gfirst[t] + g) * 2;
-                        atomicAdd(d, a0);
-                        atomicAdd(d + 1, a1);
-                    }
-                }
-            }
             if (e.rowstats_out) {
                 epi_bar();
                 if (valid) {
@@ -986,119 +758,524 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     }
 
-    if (args.cluster_k) {
-        // ---- cluster split-K: every CTA's fp32 partial tile now sits in its own shared memory.
-        // CTA `split` reduces rows [split * rows_per, +rows_per) of the tile over all peers' tiles
-        // (distributed shared memory) and runs the fused epilogue on them.
-        cluster_sync_all();
-        if (warp >= 2) {
-            const EpiArgs& e = args.e;
-            const int et = threadIdx.x - 64;
-            constexpr int kGroups = BN / 8;
-            const int rows_per = (BM + args.splits - 1) / args.splits;
-            const int r0 = split * rows_per;
-            const int nrows = max(0, min(rows_per, BM - r0));
-            const bool geglu = e.epi == SFB_EPI_GEGLU;
-            const int gpr = geglu ? kGroups / 2 : kGroups;  // items per row
-            const int ncol0 = n_tile * BN;
-            // peers: same position inside the pair (CG == 2: rank bit 0), every split
-            const uint32_t my_rank = cluster_ctarank();
-            const uint32_t rank0 = CG == 2 ? (my_rank & 1u) : 0u;
-            const uint32_t stage_u32 = smem_u32(sStage);
-#pragma unroll 1
-            for (int idx = et; idx < nrows * gpr; idx += kEpiThreads) {
-                const int row = r0 + idx / gpr, grp = idx % gpr;
-                const int mm = sRowM[row];
-                const int n = (geglu ? n_tile * (BN / 2) : ncol0) + grp * 8;
-                if (mm < 0 || n >= (geglu ? e.geglu_n_out : e.N)) continue;
-                auto sum8 = [&](int col, float (&acc)[8]) {
-                    const uint32_t off = stage_u32 + (uint32_t)(row * L::kStagePitch + (col - ncol0)) * 4u;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 4
-                    for (int s = 0; s < args.splits; ++s) {
-                        const uint32_t pa = dsmem_map(off, rank0 + (uint32_t)(s * CG));
-                        const float4 a = dsmem_ld_f4(pa);
-                        const float4 b = dsmem_ld_f4(pa + 16);
-                        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-                        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-                    }
-                };
-                reduce_epilogue8<BN, BF16>(sum8, e, mm, n);
-            }
-        }
-    }
-    if (dbg && threadIdx.x == 64) dbg[6] = globaltimer_ns();
     tc_fence_before();
-    // no CTA may exit while cluster peers can still signal its barriers / read its shared memory
-    if (clustered) cluster_sync_all();
+    // no CTA may exit while its pair peer can still signal its barriers / read its shared memory
+    if (CG == 2) cluster_sync_all();
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_pair<kTmemCols>(tmem_base);
         else tmem_dealloc<kTmemCols>(tmem_base);
     }
-    if (dbg && threadIdx.x == 32) dbg[7] = globaltimer_ns();
+}
+
+// ---------------------------------------------------------------------------------------
+// persistent CTA-pair kernel: 256 x 320 tiles, rotating TMEM accumulators, overlapped epilogue
+// ---------------------------------------------------------------------------------------
+// Grid = 2 * P CTAs in clusters of 2 (P <= SMs / 2 pairs, one CTA per SM).  Pair p walks tiles
+// p, p + P, ... of the (m_pairs x n_pairs) grid, M fastest: the pairs running at the same time
+// share one weight tile (L2 hits) and differ in their A rows.  A tile is 256 rows (128 per CTA)
+// x two 160-column halves (the second half is absent when N has an odd number of 160-tiles):
+// per 64-wide K block each CTA pulls 16 KB of A and 10 KB of weights per half.
+//
+// TMEM: 3 accumulator slots of 160 columns.  The halves of successive tiles take slots 0,1 | 2,0 |
+// 1,2 | ...; the epilogue drains a slot (TMEM -> registers -> fp32 staging), signals tmem_empty and
+// only then does the address arithmetic and the global stores -- so the next tile's MMAs start as
+// soon as the FIRST half of the previous tile has left TMEM.
+// Shared memory: 4 stages x 36 KB + one 128 x 84 fp32 staging tile (80 accumulator columns per
+// pass) + tables.
+#ifndef SFB_PSTAGES
+#define SFB_PSTAGES 4
+#endif
+#ifndef SFB_PNH
+#define SFB_PNH 2   // 160-column accumulator halves per tile (2: 256 x 320 tiles, 1: 256 x 160)
+#endif
+constexpr int kPStages = SFB_PSTAGES;
+constexpr int kPNH = SFB_PNH;
+constexpr int kPSlots = 3;
+constexpr int kPassCols = 80;                 // accumulator columns staged per epilogue pass
+constexpr int kPStagePitch = kPassCols + 4;   // floats; +4: conflict-free float4 row writes
+struct PersistSmem {
+    static constexpr int kABytes = BM * BK * 2;          // 16 KB
+    static constexpr int kBHalf = (BN / 2) * BK * 2;     // 10 KB: this CTA's 80 rows of one 160-tile
+    static constexpr int kStageBytes = kABytes + kPNH * kBHalf;
+    static constexpr int kStagingOffset = kPStages * kStageBytes;
+    static constexpr int kStagingBytes = BM * kPStagePitch * 4;
+    static constexpr int kBarOffset = kStagingOffset + kStagingBytes;  // 8 * (2*stages + 2*slots) + tmem slot
+    static constexpr int kBiasOffset = kBarOffset + 256;               // fp32 [4 slots][BN] + colsum [BN]
+    static constexpr int kBiasSlots = 4;
+    static constexpr int kRowMOffset = kBiasOffset + (kBiasSlots + 1) * BN * 4;   // int [128]
+    static constexpr int kQkvRowOffset = kRowMOffset + BM * 4;                    // int2 [128]
+    static constexpr int kQkvColOffset = kQkvRowOffset + BM * 8;                  // longlong2 [10]
+    static constexpr int kTotal = kQkvColOffset + (kPassCols / 8) * 16 + 1024;    // + alignment slack
+    static_assert(kTotal <= 227 * 1024, "persistent GEMM shared memory");
+};
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {
+    const uint32_t remote = dsmem_map(smem_u32(bar), cta_rank);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const GemmArgs args) {
+    using L = PersistSmem;
+    static_assert(kEpiWarps == 8, "the persistent epilogue splits a pass between two warps per lane quarter");
+    constexpr uint32_t kTmemCols = 512;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    uint8_t* sA = smem;                                   // [stage][16 KB]
+    uint8_t* sB = smem + kPStages * L::kABytes;           // [stage][half][10 KB]
+    constexpr int kBStage = kPNH * L::kBHalf;
+    float* sStage = reinterpret_cast<float*>(smem + L::kStagingOffset);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + kPStages;
+    uint64_t* tmem_full = empty_bar + kPStages;           // [slot], in both CTAs
+    uint64_t* tmem_empty = tmem_full + kPSlots;           // [slot], the LEADER's copy is the one used
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kPSlots);
+    float* sBias = reinterpret_cast<float*>(smem + L::kBiasOffset);
+    float* sColsum = sBias + L::kBiasSlots * BN;
+    int* sRowM = reinterpret_cast<int*>(smem + L::kRowMOffset);
+    int2* sQkvRow = reinterpret_cast<int2*>(smem + L::kQkvRowOffset);
+    longlong2* sQkvCol = reinterpret_cast<longlong2*>(smem + L::kQkvColOffset);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ciy = (int)cluster_ctaid_x();     // 0 = leader (issues every MMA), 1 = peer
+    const bool leader = ciy == 0;
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
+    const uint32_t leader_rank = cluster_ctarank() & ~1u;
+    const uint16_t pair_mask = 0b11;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < kPStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < kPSlots; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 2);   // one arrival per CTA of the pair
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair<kTmemCols>(tmem_slot);
+    pdl_launch_dependents();
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile t -> (m pair, n pair); M fastest
+    auto tile_mn = [&](int t, int& mp, int& np_, int& nh) {
+        np_ = t / args.m_pairs;
+        mp = t - np_ * args.m_pairs;
+        nh = min(kPNH, args.n_tiles160 - kPNH * np_);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            pdl_wait();
+            uint32_t kc = 0;  // K blocks issued so far (stage ring position)
+            for (int t = pair; t < args.total_tiles; t += npairs) {
+                int mp, np_, nh;
+                tile_mn(t, mp, np_, nh);
+                const int m_tile = 2 * mp + ciy;
+                const ATile at = a_tile_coords(args, m_tile);
+                const int b_ntile = at.b_nbase + kPNH * np_;
+                const uint32_t stage_bytes = L::kABytes + nh * L::kBHalf;
+                for (int kb = 0; kb < args.nkb_total; ++kb, ++kc) {
+                    const int stage = kc % kPStages;
+                    const uint32_t phase = (kc / kPStages) & 1;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                    uint8_t* dA = sA + stage * L::kABytes;
+                    uint8_t* dB = sB + stage * kBStage;
+                    if (args.a_mode == SFB_A_MATRIX) {
+                        tma_load_2d_pair(dA, &tma_a, &full_bar[stage], kb * BK, m_tile * BM);
+                    } else {
+                        const int tap = kb / args.cpb;
+                        int dw, dh;
+                        tap_offset(args, at, tap, dw, dh);
+                        tma_load_4d_pair(dA, &tma_a, &full_bar[stage], (kb - tap * args.cpb) * BK,
+                                         at.w0 * args.conv_stride + dw, at.h0 * args.conv_stride + dh, at.n0);
+                    }
+                    for (int h = 0; h < nh; ++h) {
+                        const int b_row = ((b_ntile + h) * args.nkb_total + kb) * BN + ciy * (BN / 2);
+                        tma_load_2d_pair(dB + h * L::kBHalf, &tma_b, &full_bar[stage], 0, b_row);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_f16(2 * BM, BN, BF16 != 0);
+            uint32_t kc = 0, hc = 0;  // K blocks consumed; accumulator halves started
+            for (int t = pair; t < args.total_tiles; t += npairs) {
+                int mp, np_, nh;
+                tile_mn(t, mp, np_, nh);
+                uint32_t tacc[2] = {0, 0};
+                for (int h = 0; h < nh; ++h) {
+                    const uint32_t slot = (hc + h) % kPSlots, use = (hc + h) / kPSlots;
+                    mbar_wait(&tmem_empty[slot], (use & 1) ^ 1);  // drained by both epilogues
+                    tacc[h] = tmem_base + slot * BN;
+                }
+                tc_fence_after();
+                for (int kb = 0; kb < args.nkb_total; ++kb, ++kc) {
+                    const int stage = kc % kPStages;
+                    const uint32_t phase = (kc / kPStages) & 1;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * L::kABytes));
+                    for (int h = 0; h < nh; ++h) {
+                        const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * kBStage + h * L::kBHalf));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_ss_pair(tacc[h], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                             (kb | k) != 0);
+                    }
+                    umma_commit_pair(&empty_bar[stage], pair_mask);
+                }
+                for (int h = 0; h < nh; ++h)
+                    umma_commit_pair(&tmem_full[(hc + h) % kPSlots], pair_mask);
+                hc += nh;
+            }
+        }
+        __syncwarp();
+    } else {
+        pdl_wait();
+        const EpiArgs& e = args.e;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const int et = threadIdx.x - 64;
+        const int chalf = (warp - 2) >> 2;  // which 40 of a pass's 80 columns this warp converts
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* srow = sStage + r * kPStagePitch;
+        constexpr int kGroups = kPassCols / 8;                    // 10 16-byte slices per row and pass
+        constexpr int kItems = BM * kGroups / kEpiThreads;        // 5 per thread
+        static_assert(BM * kGroups % kEpiThreads == 0, "pass items");
+        const bool rb_staged = e.rowbias && args.box_n <= L::kBiasSlots;
+        const bool geglu = e.epi == SFB_EPI_GEGLU;
+        const bool has_res = (e.residual != nullptr) && (e.epi == SFB_EPI_STORE);
+        auto load8 = [&](int row, int col, float (&f)[8]) {
+            const float4 a = *reinterpret_cast<const float4*>(sStage + row * kPStagePitch + col);
+            const float4 b = *reinterpret_cast<const float4*>(sStage + row * kPStagePitch + col + 4);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        };
+        uint32_t hc = 0;
+        for (int t = pair; t < args.total_tiles; t += npairs) {
+            int mp, np_, nh;
+            tile_mn(t, mp, np_, nh);
+            const int m_tile = 2 * mp + ciy;
+            int m;
+            const bool valid = tile_row_to_m(args, m_tile, r, m);
+            float2 ln = make_float2(0.f, 1.f);
+            if (e.ln_rowstats && valid) ln = ln_row_params(e, m);
+            float rs_sum = 0.f, rs_sq = 0.f;  // LayerNorm statistics of the stored row (rowstats_out)
+            const float* rb_global = nullptr;
+            if (e.rowbias && !rb_staged)
+                rb_global = e.rowbias + (size_t)(m_tile * args.box_n + r / (args.box_h * args.img_w)) * e.ld_rowbias;
+            const int brow_off = rb_staged ? (r / (args.box_h * args.img_w)) * BN : 0;
+            for (int h = 0; h < nh; ++h, ++hc) {
+                const uint32_t slot = hc % kPSlots, use = hc / kPSlots;
+                const int n_tile = kPNH * np_ + h;    // 160-column tile index (inside the up-conv phase)
+                const int ncol0 = n_tile * BN;
+                // ---- per-tile / per-half tables: row -> m, bias (+ staged row bias), colsum
+                if (h == 0 && chalf == 0) {
+                    sRowM[r] = valid ? m : -1;
+                    if (e.epi == SFB_EPI_QKV) sQkvRow[r] = valid ? make_int2(m / e.seq, m % e.seq) : make_int2(0, 0);
+                }
+                {
+                    int img0 = 0, nslots = 1;
+                    if (rb_staged) {
+                        nslots = args.box_n;
+                        img0 = (args.box_n == 1) ? (m_tile / args.tiles_per_img) : m_tile * args.box_n;
+                    }
+                    for (int i = et; i < nslots * BN; i += kEpiThreads) {
+                        const int sl = i / BN, c = i - sl * BN;
+                        const int n = ncol0 + c;
+                        float v = 0.f;
+                        if (n < e.N) {
+                            if (e.bias) v = e.bias[n];
+                            if (rb_staged && img0 + sl < args.img_n)
+                                v += e.rowbias[(size_t)(img0 + sl) * e.ld_rowbias + n];
+                        }
+                        sBias[i] = v;
+                    }
+                    if (e.ln_rowstats) {
+                        for (int c = et; c < BN; c += kEpiThreads) {
+                            const int n = ncol0 + c;
+                            sColsum[c] = (n < e.N) ? e.ln_colsum[n] : 0.f;
+                        }
+                    }
+                }
+                epi_bar();
+                const float* brow = sBias + brow_off;
+                const uint32_t tacc = trow + slot * BN;
+                const int npass = geglu ? 1 : 2;
+                for (int q = 0; q < npass; ++q) {
+                    const int pc0 = q * kPassCols;  // first accumulator column of the pass (STORE / QKV)
+                    // residual of this pass in the coalesced phase-B ownership, issued before the
+                    // accumulator wait
+                    uint4 res[kItems];
+                    if (has_res) {
+#pragma unroll
+                        for (int j = 0; j < kItems; ++j) {
+                            const int idx = et + j * kEpiThreads;
+                            const int row = idx / kGroups, grp = idx - row * kGroups;
+                            const int mm = sRowM[row], n = ncol0 + pc0 + grp * 8;
+                            res[j] = (mm >= 0 && n < e.N)
+                                ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.residual) + (size_t)mm * e.ldr + n)
+                                : make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                    if (e.epi == SFB_EPI_QKV && et < kGroups) {
+                        const int n = ncol0 + pc0 + et * 8;
+                        const int C = e.heads * e.head_dim;
+                        const int which = n / C + e.which_base;
+                        const int nn = n % C;
+                        const int hh = nn / e.head_dim, d = nn % e.head_dim;
+                        long long off;
+                        if (which == 0) off = (long long)hh * e.q_rows * e.q_pitch + d;
+                        else if (which == 1) off = (long long)hh * e.k_rows * e.q_pitch + d;
+                        else off = ((long long)hh * e.vt_rows + d) * e.vt_pitch;
+                        sQkvCol[et] = make_longlong2(which, off);
+                    }
+                    if (q == 0) {
+                        mbar_wait(&tmem_full[slot], use & 1);
+                        tc_fence_after();
+                    }
+                    // ---- phase A: TMEM -> registers -> bias / LayerNorm fold (-> GEGLU) -> staging
+                    if (!geglu) {
+                        const int c0 = pc0 + chalf * 40;  // 40 columns: 32 + 8
+                        auto stage8 = [&](const uint32_t* v, int cl) {  // cl: column inside the half
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float acc = __uint_as_float(v[i]);
+                                if (e.ln_rowstats) acc = ln.y * (acc - ln.x * sColsum[cl + i]);
+                                f[i] = acc + brow[cl + i];
+                            }
+                            if (rb_global && ncol0 + cl < e.N) add_bias8(rb_global, ncol0 + cl, f);
+                            *reinterpret_cast<float4*>(srow + cl - pc0) = make_float4(f[0], f[1], f[2], f[3]);
+                            *reinterpret_cast<float4*>(srow + cl - pc0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                        };
+                        {
+                            uint32_t v[32];
+                            tmem_ld32(tacc + c0, v);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) stage8(v + 8 * j, c0 + 8 * j);
+                        }
+                        {
+                            uint32_t v[8];
+                            tmem_ld8(tacc + c0 + 32, v);
+                            tmem_wait_ld();
+                            stage8(v, c0 + 32);
+                        }
+                    } else {
+                        // value columns [chalf*40, +40), gate columns [80 + chalf*40, +40) of the half
+                        const int cv = chalf * 40;
+                        auto gate8 = [&](const uint32_t* vv, const uint32_t* vg, int cl) {
+                            float o[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float a = __uint_as_float(vv[i]), g = __uint_as_float(vg[i]);
+                                if (e.ln_rowstats) {
+                                    a = ln.y * (a - ln.x * sColsum[cl + i]);
+                                    g = ln.y * (g - ln.x * sColsum[BN / 2 + cl + i]);
+                                }
+                                a += brow[cl + i];
+                                g += brow[BN / 2 + cl + i];
+                                o[i] = a * gelu_erf_f(g);
+                            }
+                            *reinterpret_cast<float4*>(srow + cl) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(srow + cl + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                        };
+#pragma unroll 1
+                        for (int cb = 0; cb < 2; ++cb) {
+                            uint32_t vv[16], vg[16];
+                            tmem_ld16(tacc + cv + cb * 16, vv);
+                            tmem_ld16(tacc + BN / 2 + cv + cb * 16, vg);
+                            tmem_wait_ld();
+                            gate8(vv, vg, cv + cb * 16);
+                            gate8(vv + 8, vg + 8, cv + cb * 16 + 8);
+                        }
+                        {
+                            uint32_t vv[8], vg[8];
+                            tmem_ld8(tacc + cv + 32, vv);
+                            tmem_ld8(tacc + BN / 2 + cv + 32, vg);
+                            tmem_wait_ld();
+                            gate8(vv, vg, cv + 32);
+                        }
+                    }
+                    const bool last_pass = q == npass - 1;
+                    if (last_pass) tc_fence_before();  // this half has left TMEM
+                    epi_bar();
+                    if (last_pass && et == 0) {
+                        if (leader) mbar_arrive(&tmem_empty[slot]);
+                        else mbar_arrive_cluster(&tmem_empty[slot], leader_rank);
+                    }
+                    // ---- phase B: coalesced 16-byte slices
+                    if (geglu) {
+#pragma unroll 1
+                        for (int j = 0; j < kItems; ++j) {
+                            const int idx = et + j * kEpiThreads;
+                            const int row = idx / kGroups, og = idx - row * kGroups;
+                            const int mm = sRowM[row], nout = n_tile * (BN / 2) + og * 8;
+                            if (mm >= 0 && nout < e.geglu_n_out) {
+                                float f[8];
+                                load8(row, og * 8, f);
+                                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)mm * e.ldo + nout) =
+                                    pack8(f, BF16);
+                            }
+                        }
+                    } else if (e.epi == SFB_EPI_STORE) {
+#pragma unroll
+                        for (int j = 0; j < kItems; ++j) {
+                            const int idx = et + j * kEpiThreads;
+                            const int row = idx / kGroups, grp = idx - row * kGroups;
+                            const int mm = sRowM[row], n = ncol0 + pc0 + grp * 8;
+                            if (mm >= 0 && n < e.N) {
+                                float f[8];
+                                load8(row, grp * 8, f);
+                                if (has_res) add_res8(res[j], BF16, f);
+                                if (e.rowstats_out) {
+                                    float* d = sStage + row * kPStagePitch + grp * 8;
+                                    *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
+                                    *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                                }
+                                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)mm * e.ldo + n) =
+                                    pack8(f, BF16);
+                            }
+                        }
+                        if (e.rowstats_out) {
+                            epi_bar();
+                            if (valid) {
+                                for (int g = chalf * (kGroups / 2); g < (chalf + 1) * (kGroups / 2); ++g) {
+                                    if (ncol0 + pc0 + g * 8 < e.N) {
+                                        float f[8];
+                                        load8(r, g * 8, f);
+                                        row_stats8(f, BF16, rs_sum, rs_sq);
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        // QKV scatter: V^T columns want consecutive lanes = consecutive rows
+                        const int C = e.heads * e.head_dim;
+                        const int n_first = ncol0 + pc0, n_last = min(n_first + kPassCols, e.N) - 1;
+                        const bool row_fastest = (n_first / C + e.which_base == 2) && (n_last / C + e.which_base == 2);
+#pragma unroll 1
+                        for (int j = 0; j < kItems; ++j) {
+                            const int idx = et + j * kEpiThreads;
+                            int row, grp;
+                            if (row_fastest) { grp = idx >> 7; row = idx & 127; }
+                            else { row = idx / kGroups; grp = idx - row * kGroups; }
+                            const int mm = sRowM[row], n = n_first + grp * 8;
+                            if (mm >= 0 && n < e.N) {
+                                float f[8];
+                                load8(row, grp * 8, f);
+                                const int2 bs = sQkvRow[row];
+                                const longlong2 ci = sQkvCol[grp];
+                                if (ci.x == 0) {
+                                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.q) +
+                                        ((size_t)bs.x * e.heads * e.q_rows + bs.y) * e.q_pitch + ci.y) = pack8(f, BF16);
+                                } else if (ci.x == 1) {
+                                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.k) +
+                                        ((size_t)bs.x * e.heads * e.k_rows + bs.y) * e.q_pitch + ci.y) = pack8(f, BF16);
+                                } else {
+                                    const size_t base = (size_t)bs.x * e.heads * e.vt_rows * e.vt_pitch + ci.y + bs.y;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) store1(e.vt, base + (size_t)i * e.vt_pitch, f[i], BF16);
+                                }
+                            }
+                        }
+                    }
+                    epi_bar();  // the staging tile (and the QKV column table) are rewritten by the next pass
+                }
+            }
+            if (e.rowstats_out && valid) {
+                // the two warps of a lane quarter hold the two column halves of the same row
+                atomicAdd(e.rowstats_out + 2 * (size_t)m, rs_sum);
+                atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rs_sq);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer may still signal this CTA's barriers / the leader reads its smem
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair<kTmemCols>(tmem_base);
+    }
 }
 
 }  // namespace sfb
 
 using namespace sfb;
 
-template <int BN, int STAGES, int BF16, int CG>
+template <int STAGES, int BF16, int CG>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
                          cudaStream_t stream) {
-    using L = GemmSmem<BN, STAGES, CG>;
+    using L = GemmSmem<STAGES, CG>;
     static PerDeviceOnce attr_once;
     bool& attr_set = attr_once.flag();
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, BF16, CG>,
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, BF16, CG>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
         attr_set = true;
     }
-    const int cz = a.cluster_k ? a.splits : 1;
-    if (cz * CG > 8) {
-        static PerDeviceOnce np_once;
-        bool& np_set = np_once.flag();
-        if (!np_set) {
-            cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, BF16, CG>,
-                                                   cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-            if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: non-portable cluster attribute: %s", cudaGetErrorString(err));
-            np_set = true;
-        }
-    }
-    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<BN, STAGES, BF16, CG>, grid, dim3(kGemmThreads),
-                                         CG == 2 ? dim3(2, 1, cz) : dim3(a.cx, a.cy, cz), L::kTotal, stream,
-                                         ta, tb, a);
-    if (err != cudaSuccess) {
-        // diagnostics: can the requested cluster be scheduled at all?
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CG == 2 ? 2 : a.cx; at[0].val.clusterDim.y = CG == 2 ? 1 : a.cy; at[0].val.clusterDim.z = cz;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        int max_clusters = -1;
-        cudaError_t e2 = cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tc_kernel<BN, STAGES, BF16, CG>, &cfg);
-        cudaGetLastError();
-        return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s (%s) grid=(%u,%u,%u) cluster=(%d,%d) smem=%d stages=%d cg=%d maxActiveClusters=%d (%s)",
-                    cudaGetErrorString(err), cudaGetErrorName(err), grid.x, grid.y, grid.z,
-                    CG == 2 ? 1 : a.cx, CG == 2 ? 2 : a.cy, (int)L::kTotal, STAGES, CG, max_clusters,
-                    cudaGetErrorName(e2));
-    }
+    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<STAGES, BF16, CG>, grid, dim3(kGemmThreads),
+                                         CG == 2 ? dim3(2, 1, 1) : dim3(1, 1, 1), L::kTotal, stream, ta, tb, a);
+    if (err != cudaSuccess)
+        return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s (%s) grid=(%u,%u,%u) smem=%d stages=%d cg=%d",
+                    cudaGetErrorString(err), cudaGetErrorName(err), grid.x, grid.y, grid.z, (int)L::kTotal, STAGES, CG);
     return check_launch("sfb_gemm");
 }
 
-template <int BN, int STAGES, int CG>
+template <int STAGES, int CG>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
                        cudaStream_t stream) {
-    return a.e.dtype == SFB_BF16 ? launch_gemm_t<BN, STAGES, 1, CG>(ta, tb, a, grid, stream)
-                                 : launch_gemm_t<BN, STAGES, 0, CG>(ta, tb, a, grid, stream);
+    return a.e.dtype == SFB_BF16 ? launch_gemm_t<STAGES, 1, CG>(ta, tb, a, grid, stream)
+                                 : launch_gemm_t<STAGES, 0, CG>(ta, tb, a, grid, stream);
+}
+
+template <int BF16>
+static int launch_persist_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+    static PerDeviceOnce attr_once;
+    bool& attr_set = attr_once.flag();
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(gemm_persist_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               PersistSmem::kTotal);
+        if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm(persistent): smem attribute: %s", cudaGetErrorString(err));
+        attr_set = true;
+    }
+    int pairs = sm_count() / 2;
+    if (pairs > a.total_tiles) pairs = a.total_tiles;
+    if (pairs < 1) return fail(SFB_ERR_INVALID, "sfb_gemm(persistent): no SM pair available");
+    cudaError_t err = launch_cluster_pdl(gemm_persist_kernel<BF16>, dim3(2 * pairs), dim3(kGemmThreads), dim3(2, 1, 1),
+                                         PersistSmem::kTotal, stream, ta, tb, a);
+    if (err != cudaSuccess)
+        return fail(SFB_ERR_CUDA, "sfb_gemm(persistent): launch: %s (%s) pairs=%d smem=%d", cudaGetErrorString(err),
+                    cudaGetErrorName(err), pairs, (int)PersistSmem::kTotal);
+    return check_launch("sfb_gemm");
 }
 
 extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
-    constexpr int BN = 160;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!p || !p->tmap_a || !p->tmap_b) return fail(SFB_ERR_INVALID, "sfb_gemm: null argument");
     if (p->K <= 0 || p->K % BK) return fail(SFB_ERR_INVALID, "sfb_gemm: K=%d must be a multiple of 64", p->K);
@@ -1108,19 +1285,14 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     a.a_mode = p->a_mode;
     a.nkb_total = p->K / BK;
     a.splits = p->splits < 1 ? 1 : p->splits;
-    a.pdl = g_pdl;
-    a.dbg = reinterpret_cast<long long*>(p->debug_stamps);
-    a.split_sync = nullptr;
     if (a.splits > a.nkb_total) return fail(SFB_ERR_INVALID, "sfb_gemm: splits > K blocks");
-    a.cluster_k = (p->cluster_k && a.splits > 1) ? 1 : 0;
-    if (a.cluster_k && (a.splits * (p->cta_pair ? 2 : 1) > 16 || p->gn_stats[0] || p->cluster_n > 1 || p->cluster_m > 1))
-        return fail(SFB_ERR_INVALID, "sfb_gemm: cluster_k needs splits * pair <= 16, no gn_stats, no multicast cluster");
-    if (a.splits > 1 && !a.cluster_k && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
+    if (a.splits > 1 && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
     a.ws = p->ws;
     int m_tiles;
     const bool upconv = p->a_mode == SFB_A_UPCONV2X;
-    if (p->a_mode == SFB_A_CONV3X3 || upconv) {
-        if (p->cin <= 0 || p->cin % BK || p->K != (upconv ? 4 : 9) * p->cin)
+    const bool tconv = p->a_mode == SFB_A_CONV3X1;
+    if (p->a_mode == SFB_A_CONV3X3 || upconv || tconv) {
+        if (p->cin <= 0 || p->cin % BK || p->K != (upconv ? 4 : (tconv ? 3 : 9)) * p->cin)
             return fail(SFB_ERR_INVALID, "sfb_gemm: conv cin=%d K=%d", p->cin, p->K);
         const int box_w = p->box_w > 0 ? p->box_w : p->img_w;
         if (p->box_n * p->box_h * box_w != BM || box_w > p->img_w || p->img_w % box_w)
@@ -1128,11 +1300,9 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
                         p->box_n, p->box_h, box_w, p->img_w);
         if (p->box_n > 1 && (p->box_h != p->img_h || box_w != p->img_w))
             return fail(SFB_ERR_INVALID, "sfb_gemm: multi-image box needs box_h == img_h and box_w == img_w");
-        if (box_w != p->img_w && (p->cluster_n > 1 || p->cluster_m > 1))
-            return fail(SFB_ERR_INVALID, "sfb_gemm: patch tiles (box_w < img_w) do not combine with multicast clusters");
         if (p->M != (upconv ? 4 : 1) * p->img_n * p->img_h * p->img_w) return fail(SFB_ERR_INVALID, "sfb_gemm: conv M mismatch");
-        if (upconv && (p->conv_stride != 1 || p->epi != SFB_EPI_STORE || p->cluster_n > 1 || p->cluster_m > 1))
-            return fail(SFB_ERR_INVALID, "sfb_gemm: up-conv needs stride 1, the STORE epilogue and no multicast cluster");
+        if (upconv && (p->conv_stride != 1 || p->epi != SFB_EPI_STORE))
+            return fail(SFB_ERR_INVALID, "sfb_gemm: up-conv needs stride 1 and the STORE epilogue");
         a.img_n = p->img_n; a.img_h = p->img_h; a.img_w = p->img_w;
         a.cpb = p->cin / BK;
         a.conv_stride = p->conv_stride;
@@ -1150,8 +1320,9 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     } else {
         return fail(SFB_ERR_INVALID, "sfb_gemm: a_mode");
     }
-    if (p->rowbias && p->a_mode != SFB_A_CONV3X3)
+    if (p->rowbias && p->a_mode != SFB_A_CONV3X3 && !tconv)
         return fail(SFB_ERR_INVALID, "sfb_gemm: rowbias (time-embedding add) needs conv mode");
+    if (tconv && p->conv_stride != 1) return fail(SFB_ERR_INVALID, "sfb_gemm: temporal conv needs stride 1");
     EpiArgs& e = a.e;
     e.epi = p->epi; e.dtype = p->dtype; e.M = p->M; e.N = p->N;
     e.out = p->out; e.ldo = p->ldo; e.bias = p->bias; e.rowbias = p->rowbias;
@@ -1160,19 +1331,6 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     e.q = p->q; e.k = p->k; e.vt = p->vt; e.heads = p->heads; e.head_dim = p->head_dim;
     e.which_base = p->which_base; e.seq = p->seq; e.q_pitch = p->q_pitch; e.q_rows = p->q_rows;
     e.k_rows = p->k_rows; e.vt_rows = p->vt_rows; e.vt_pitch = p->vt_pitch;
-    for (int t = 0; t < 2; ++t) {
-        e.gn_stats[t] = p->gn_stats[t]; e.gn_cpg[t] = p->gn_cpg[t]; e.gn_choff[t] = p->gn_choff[t];
-    }
-    e.gn_groups = p->gn_groups; e.gn_rpi = p->gn_rows_per_img; e.gn_shard_stride = p->gn_shard_stride;
-    if (p->gn_stats[0]) {
-        if (p->epi != SFB_EPI_STORE || p->gn_groups <= 0 || p->gn_groups > 64 || p->gn_shard_stride <= 0 ||
-            p->gn_rows_per_img < 16 || p->gn_cpg[0] < 2 ||
-            (p->gn_stats[1] && p->gn_cpg[1] < 2) ||
-            (BM % p->gn_rows_per_img != 0 && p->gn_rows_per_img % BM != 0))
-            return fail(SFB_ERR_INVALID, "sfb_gemm: unsupported GroupNorm statistics geometry");
-    } else if (p->gn_stats[1]) {
-        return fail(SFB_ERR_INVALID, "sfb_gemm: gn_stats[1] without gn_stats[0]");
-    }
     e.rowstats_out = p->rowstats_out; e.ln_rowstats = p->ln_rowstats; e.ln_colsum = p->ln_colsum;
     e.ln_eps = p->ln_eps; e.ln_dim = p->ln_dim;
     if (p->ln_rowstats && (!p->ln_colsum || p->ln_dim <= 0 || p->rowbias))
@@ -1193,48 +1351,48 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     } else {
         return fail(SFB_ERR_INVALID, "sfb_gemm: epilogue mode");
     }
-    dim3 grid((p->N + BN - 1) / BN, m_tiles, a.splits);
-    a.cx = p->cluster_n > 0 ? p->cluster_n : 1;
-    a.cy = p->cluster_m > 0 ? p->cluster_m : 1;
-    a.a_part_dim = p->a_part_dim;
-    a.a_part_ext = p->a_part_ext;
-    if ((a.cx != 1 && a.cx != 2) || (a.cy != 1 && a.cy != 2 && a.cy != 4) || grid.x % a.cx || grid.y % a.cy)
-        return fail(SFB_ERR_INVALID, "sfb_gemm: cluster %dx%d does not divide the %ux%u tile grid", a.cx, a.cy, grid.x, grid.y);
-    if (a.cx > 1 && p->a_mode == SFB_A_CONV3X3 && (a.a_part_dim < 1 || a.a_part_dim > 3 || a.a_part_ext <= 0))
-        return fail(SFB_ERR_INVALID, "sfb_gemm: conv cluster needs a_part_dim / a_part_ext");
+    const int n_tiles = (p->N + BN - 1) / BN;
     CUtensorMap ta, tb;
     memcpy(&ta, p->tmap_a, sizeof(CUtensorMap));
     memcpy(&tb, p->tmap_b, sizeof(CUtensorMap));
-    // <= one CTA per SM anyway: take the deep 6-stage pipeline; otherwise 3 stages x 2 CTAs/SM
+    if (p->persistent) {
+        // persistent CTA pairs over 256 x 320 tiles (tmap_b box = 80 rows, as for cta_pair)
+        if (!p->cta_pair || a.splits != 1 || m_tiles % 2 || (upconv && a.up_tiles % 2) || p->defer_finish)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: persistent needs cta_pair, no split-K and an even number of M tiles (per up-conv phase)");
+        a.m_pairs = m_tiles / 2;
+        a.n_tiles160 = n_tiles;
+        a.n_pairs = (n_tiles + kPNH - 1) / kPNH;
+        a.total_tiles = a.m_pairs * a.n_pairs;
+        return e.dtype == SFB_BF16 ? launch_persist_t<1>(ta, tb, a, stream) : launch_persist_t<0>(ta, tb, a, stream);
+    }
+    dim3 grid(n_tiles, m_tiles, a.splits);
+    // <= one CTA per SM anyway: take the deep pipeline; otherwise the shallow one x 2 CTAs/SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
-    // fused split-K reduction (last-arriving CTA of a tile finishes it); GroupNorm statistics only
-    // exist in the stand-alone reduction kernel
-    if (a.splits > 1 && !a.cluster_k && p->split_sync && !p->gn_stats[0]) a.split_sync = reinterpret_cast<int*>(p->split_sync);
     static const int force_stages = [] { const char* v = getenv("SFB_GEMM_STAGES"); return v ? atoi(v) : 0; }();
-    const bool deep = force_stages ? (force_stages == 6) : (ctas <= 148);
+    const bool deep = force_stages ? (force_stages == 6) : (ctas <= sm_count());
     int rc;
     if (p->cta_pair) {
-        // CTA pairs along M (cluster 1x2, tcgen05.mma.cta_group::2): tmap_b box = 80 rows
-        if (grid.y % 2 || a.cx != 1 || a.cy != 1 || (upconv && a.up_tiles % 2))
-            return fail(SFB_ERR_INVALID, "sfb_gemm: cta_pair needs an even number of M tiles (per up-conv phase) and no multicast cluster");
+        // CTA pairs along M (cluster 2x1, tcgen05.mma.cta_group::2): tmap_b box = 80 rows
+        if (grid.y % 2 || (upconv && a.up_tiles % 2))
+            return fail(SFB_ERR_INVALID, "sfb_gemm: cta_pair needs an even number of M tiles (per up-conv phase)");
         const dim3 pgrid(grid.y, grid.x, grid.z);  // M tiles along x: pairs are x-neighbours
-        rc = deep ? launch_gemm<BN, 8, 2>(ta, tb, a, pgrid, stream) : launch_gemm<BN, 4, 2>(ta, tb, a, pgrid, stream);
+        rc = deep ? launch_gemm<8, 2>(ta, tb, a, pgrid, stream) : launch_gemm<4, 2>(ta, tb, a, pgrid, stream);
     } else {
-        rc = deep ? launch_gemm<BN, 6, 1>(ta, tb, a, grid, stream) : launch_gemm<BN, 3, 1>(ta, tb, a, grid, stream);
+        rc = deep ? launch_gemm<6, 1>(ta, tb, a, grid, stream) : launch_gemm<3, 1>(ta, tb, a, grid, stream);
     }
     if (rc) return rc;
     if (p->defer_finish && a.splits > 1) {
-        if (a.split_sync || a.cluster_k || e.epi != SFB_EPI_STORE || e.rowstats_out || e.ln_rowstats || e.gn_stats[0])
-            return fail(SFB_ERR_INVALID, "sfb_gemm: defer_finish needs a plain STORE epilogue and the workspace split-K path");
+        if (e.epi != SFB_EPI_STORE || e.rowstats_out || e.ln_rowstats)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: defer_finish needs a plain STORE epilogue");
         return rc;  // the consumer (sfb_group_norm_fused with part_ws) finishes the tensor
     }
-    if (a.splits > 1 && !a.split_sync && !a.cluster_k) {
+    if (a.splits > 1) {
         const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
         const long long items = (long long)e.M * (ncols / 8);
         const int blocks = (int)((items + 255) / 256);
         cudaError_t err = (e.dtype == SFB_BF16)
-            ? launch_pdl(splitk_finish_kernel<BN, 1>, dim3(blocks), dim3(256), 0, stream, (const float*)a.ws, a.splits, e)
-            : launch_pdl(splitk_finish_kernel<BN, 0>, dim3(blocks), dim3(256), 0, stream, (const float*)a.ws, a.splits, e);
+            ? launch_pdl(splitk_finish_kernel<1>, dim3(blocks), dim3(256), 0, stream, (const float*)a.ws, a.splits, e)
+            : launch_pdl(splitk_finish_kernel<0>, dim3(blocks), dim3(256), 0, stream, (const float*)a.ws, a.splits, e);
         if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: finish launch: %s", cudaGetErrorString(err));
         rc = check_launch("sfb_gemm(split-K finish)");
     }

@@ -3,7 +3,14 @@
 // GroupNorm is two passes, like the reference's NHWC path (/root/reference/src/sfast/triton/ops/
 // group_norm.py:126-165 stats, :272-320 apply) but with the statistics kept in fp32 end to end
 // (the reference round-trips mean/rstd through the input dtype, group_norm.py:405-416) and with
-// the stats grid sized to fill 148 SMs instead of groups*batch CTAs.
+// the stats grid sized to fill the SMs instead of groups*batch CTAs.
+//
+// Variance: the reference merges Welford partials (triton/ops/utils.py:5-15).  Here every
+// (image, group) accumulates the SHIFTED moments  S1 = sum(x - K), S2 = sum((x - K)^2)  with
+// K = the group's first stored value x[img, pixel 0, first channel of the group] (identical for
+// every CTA of the image), and  mean = K + S1/n,  var = S2/n - (S1/n)^2.  With K inside the data
+// range the subtraction no longer cancels the leading digits when |mean| >> sigma (outlier
+// channels of real checkpoints), which the raw sum-of-squares form E[x^2] - mean^2 does.
 // LayerNorm is one warp per row, row held in registers, two-pass mean/variance in fp32
 // (reference: triton/ops/layer_norm.py:51-133).
 #include "common.cuh"
@@ -22,7 +29,6 @@ struct GnArgs {
     const float* beta;
     float* stats;
     int n, hw, c, ldx, ldy, groups, cpg, nvec, rows_per_block;
-    int shards, shard_stride;  // statistics arrive as `shards` partial copies, `shard_stride` floats apart
     float eps;
     int silu, dtype;
     // deferred split-K finish of the GEMM producing channels [0, part_c) (fused kernel only)
@@ -89,11 +95,97 @@ __device__ __forceinline__ uint4 gn_finish_partials(const GnArgs& a, int img, in
     return v;
 }
 
+// One finished 16-bit value (as float) of channel `ch` of pixel `row`: the same arithmetic, in the
+// same order, as gn_finish_partials -- so every CTA derives the identical shift K from it.
+__device__ __forceinline__ float gn_finish_partial1(const GnArgs& a, int img, int row, int ch) {
+    const int m = img * a.hw + row;
+    const size_t stride = (size_t)a.n * a.hw * a.part_ld;
+    const float* p0 = a.part_ws + (size_t)m * a.part_ld + ch;
+    float acc = 0.f;
+    constexpr int kU = 6;
+    for (int s0 = 0; s0 < a.part_splits; s0 += kU) {
+        float v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (s0 + u < a.part_splits) v[u] = __ldcg(p0 + (size_t)(s0 + u) * stride);
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (s0 + u < a.part_splits) acc += v[u];
+    }
+    if (a.part_bias) acc += a.part_bias[ch];
+    if (a.part_rowbias) acc += a.part_rowbias[(size_t)img * a.part_ld_rowbias + ch];
+    if (a.part_residual) acc += load1(a.part_residual, (size_t)m * a.part_ldr + ch, a.dtype);
+    const uint32_t r = pack2(acc, 0.f, a.dtype);
+    return unpack2(r, a.dtype).x;
+}
+
+// Shift K of every group of image `img` into shared memory: the first stored value of the group
+// (pixel 0, first channel).  kPart: channels below part_c do not exist in x yet.
+template <bool kPart>
+__device__ __forceinline__ void gn_load_shifts(const GnArgs& a, int img, float* sK) {
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+        const int ch = g * a.cpg;
+        float k;
+        if (kPart && ch < a.part_c) k = gn_finish_partial1(a, img, 0, ch);
+        else k = load1(a.x, (size_t)img * a.hw * a.ldx + ch, a.dtype);
+        sK[g] = k;
+    }
+}
+
+// (S1, S2) of the 8 channels of `v` about their groups' shifts
+struct GnAcc8 {
+    float s[8], ss[8];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+    }
+    __device__ __forceinline__ void add(const uint4& v, const float (&k)[8], int dtype) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack2(w[i], dtype);
+            const float d0 = f.x - k[2 * i], d1 = f.y - k[2 * i + 1];
+            s[2 * i] += d0; ss[2 * i] += d0 * d0;
+            s[2 * i + 1] += d1; ss[2 * i + 1] += d1 * d1;
+        }
+    }
+    // merge runs of equal group id among the 8 channels into acc[2 * groups] (shared memory)
+    __device__ __forceinline__ void flush(float* acc, int ch0, int cpg) const {
+        int g_run = ch0 / cpg;
+        float rs = 0.f, rss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (ch0 + i) / cpg;
+            if (g != g_run) {
+                atomicAdd(&acc[2 * g_run], rs);
+                atomicAdd(&acc[2 * g_run + 1], rss);
+                g_run = g; rs = 0.f; rss = 0.f;
+            }
+            rs += s[i]; rss += ss[i];
+        }
+        atomicAdd(&acc[2 * g_run], rs);
+        atomicAdd(&acc[2 * g_run + 1], rss);
+    }
+};
+
+// per-channel scale / shift from the finished shifted moments
+__device__ __forceinline__ void gn_scale_shift(const GnArgs& a, int img, const float* sK, float inv_cnt,
+                                               int ch, float gamma, float beta, float& sc, float& sh) {
+    const int g = ch / a.cpg;
+    const float s1 = __ldcg(&a.stats[((size_t)img * a.groups + g) * 2]) * inv_cnt;
+    const float s2 = __ldcg(&a.stats[((size_t)img * a.groups + g) * 2 + 1]) * inv_cnt;
+    const float mean = sK[g] + s1;
+    const float var = fmaxf(s2 - s1 * s1, 0.f);
+    sc = rsqrtf(var + a.eps) * gamma;
+    sh = beta - mean * sc;
+}
+
 // grid (blocks_per_img, n).  Thread (tx = vector column, ty = row slot) keeps per-channel
 // partial sums for its 8 channels over rows ty, ty+BY, ...; one shared-memory atomic per
 // (thread, group run) at the end, then one global atomic per (block, group, moment).
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
     __shared__ float acc[2 * 64];
+    __shared__ float sK[64];
     pdl_launch_dependents();
     pdl_wait();
     const int img = blockIdx.y;
@@ -101,11 +193,14 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
     const int tx = threadIdx.x % a.nvec;
     const int ty = threadIdx.x / a.nvec;
     for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads) acc[i] = 0.f;
+    gn_load_shifts<false>(a, img, sK);
     __syncthreads();
     if (ty < by) {
-        float s[8], ss[8];
+        float k[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+        for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
+        GnAcc8 st;
+        st.zero();
         const int row0 = blockIdx.x * a.rows_per_block;
         const int row1 = min(row0 + a.rows_per_block, a.hw);
         const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
@@ -118,33 +213,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
                 if (row < row1) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
             }
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                if (rb + u * by < row1) {
-                    const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 f = unpack2(w[i], a.dtype);
-                        s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
-                        s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
-                    }
-                }
-            }
+            for (int u = 0; u < kU; ++u)
+                if (rb + u * by < row1) st.add(v[u], k, a.dtype);
         }
-        // merge runs of equal group id among the 8 channels
-        int g_run = (tx * 8) / a.cpg;
-        float rs = 0.f, rss = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int g = (tx * 8 + i) / a.cpg;
-            if (g != g_run) {
-                atomicAdd(&acc[2 * g_run], rs);
-                atomicAdd(&acc[2 * g_run + 1], rss);
-                g_run = g; rs = 0.f; rss = 0.f;
-            }
-            rs += s[i]; rss += ss[i];
-        }
-        atomicAdd(&acc[2 * g_run], rs);
-        atomicAdd(&acc[2 * g_run + 1], rss);
+        st.flush(acc, tx * 8, a.cpg);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads)
@@ -155,26 +227,17 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
 // a streaming y = act(x * scale + shift) over the block's rows with 16-byte accesses.
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     extern __shared__ float sm[];
+    __shared__ float sK[64];
     pdl_launch_dependents();
     pdl_wait();
     float* scale = sm;
     float* shift = sm + a.c;
     const int img = blockIdx.y;
     const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
-    for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
-        const int g = ch / a.cpg;
-        float sum = 0.f, sq = 0.f;
-        for (int s = 0; s < a.shards; ++s) {
-            sum += a.stats[(size_t)s * a.shard_stride + ((size_t)img * a.groups + g) * 2];
-            sq += a.stats[(size_t)s * a.shard_stride + ((size_t)img * a.groups + g) * 2 + 1];
-        }
-        const float mean = sum * inv_cnt;
-        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + a.eps);
-        const float sc = rstd * a.gamma[ch];
-        scale[ch] = sc;
-        shift[ch] = a.beta[ch] - mean * sc;
-    }
+    gn_load_shifts<false>(a, img, sK);
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads)
+        gn_scale_shift(a, img, sK, inv_cnt, ch, a.gamma[ch], a.beta[ch], scale[ch], shift[ch]);
     __syncthreads();
     const int row0 = blockIdx.x * a.rows_per_block;
     const int row1 = min(row0 + a.rows_per_block, a.hw);
@@ -226,6 +289,7 @@ template <bool kPart>
 __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, unsigned* sync_counter) {
     extern __shared__ __align__(16) uint8_t fsm[];
     __shared__ float acc[2 * 64];
+    __shared__ float sK[64];
     float* scale = reinterpret_cast<float*>(fsm);
     float* shift = scale + a.c;
     uint4* slab = reinterpret_cast<uint4*>(fsm + 2 * a.c * sizeof(float));
@@ -236,33 +300,19 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
     const int tx = threadIdx.x % a.nvec;
     const int ty = threadIdx.x / a.nvec;
     for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads) acc[i] = 0.f;
-    __syncthreads();
+    gn_load_shifts<kPart>(a, img, sK);  // in flight together with the slab loads below
     const int row0 = blockIdx.x * a.rows_per_block;
     const int row1 = min(row0 + a.rows_per_block, a.hw);
+    const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
     if (ty < by) {
-        float s[8], ss[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
-        const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
-        auto accumulate = [&](const uint4& v) {
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack2(w[i], a.dtype);
-                s[2 * i] += f.x; ss[2 * i] += f.x * f.x;
-                s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
-            }
-        };
         if constexpr (kPart) {
             // channels [0, part_c) come from the producer GEMM's split-K partials (a few rows per
             // thread, each with all its partial loads in flight)
             const bool from_partials = tx * 8 < a.part_c;
-            for (int row = row0 + ty; row < row1; row += by) {
-                const uint4 v = from_partials ? gn_finish_partials(a, img, row, tx)
-                                              : *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
-                slab[(row - row0) * a.nvec + tx] = v;
-                accumulate(v);
-            }
+            for (int row = row0 + ty; row < row1; row += by)
+                slab[(row - row0) * a.nvec + tx] = from_partials
+                    ? gn_finish_partials(a, img, row, tx)
+                    : *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
         } else {
             // all of a thread's loads of one batch are in flight together: the slab is a handful of
             // rows per thread, so a load-use-load chain would be nothing but exposed L2 latency
@@ -277,27 +327,20 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
 #pragma unroll
                 for (int u = 0; u < kU; ++u) {
                     const int row = rb + u * by;
-                    if (row < row1) {
-                        slab[(row - row0) * a.nvec + tx] = v[u];
-                        accumulate(v[u]);
-                    }
+                    if (row < row1) slab[(row - row0) * a.nvec + tx] = v[u];
                 }
             }
         }
-        int g_run = (tx * 8) / a.cpg;
-        float rs = 0.f, rss = 0.f;
+    }
+    __syncthreads();  // shifts and accumulators visible; each thread re-reads only its own slab rows
+    if (ty < by) {
+        float k[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int g = (tx * 8 + i) / a.cpg;
-            if (g != g_run) {
-                atomicAdd(&acc[2 * g_run], rs);
-                atomicAdd(&acc[2 * g_run + 1], rss);
-                g_run = g; rs = 0.f; rss = 0.f;
-            }
-            rs += s[i]; rss += ss[i];
-        }
-        atomicAdd(&acc[2 * g_run], rs);
-        atomicAdd(&acc[2 * g_run + 1], rss);
+        for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
+        GnAcc8 st;
+        st.zero();
+        for (int row = row0 + ty; row < row1; row += by) st.add(slab[(row - row0) * a.nvec + tx], k, a.dtype);
+        st.flush(acc, tx * 8, a.cpg);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads)
@@ -308,15 +351,16 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
         scale[ch] = a.gamma[ch];
         shift[ch] = a.beta[ch];
     }
-    // ---- grid barrier
+    // ---- grid barrier.  The launch is COOPERATIVE (cudaLaunchAttributeCooperative): the driver
+    // only starts the grid when every CTA can be resident, so the arrive / spin below cannot
+    // wait for an unscheduled CTA -- not with other streams' kernels on the GPU, not on a MIG or
+    // green-context slice (the grid is sized from the occupancy query, see sfb_group_norm_fused).
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned total = gridDim.x * gridDim.y;
         atomicAdd(sync_counter, 1u);
-        long long t0 = clock64();
         while (*reinterpret_cast<volatile unsigned*>(sync_counter) < total) {
-            if (clock64() - t0 > 4000000000LL) __trap();  // not co-resident: fail, do not hang
         }
         __threadfence();
     }
@@ -324,15 +368,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
     // ---- phase 2
     const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
     for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
-        const int g = ch / a.cpg;
-        const float sum = __ldcg(&a.stats[((size_t)img * a.groups + g) * 2]);
-        const float sq = __ldcg(&a.stats[((size_t)img * a.groups + g) * 2 + 1]);
-        const float mean = sum * inv_cnt;
-        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + a.eps);
-        const float sc = rstd * scale[ch];
+        float sc, sh;
+        gn_scale_shift(a, img, sK, inv_cnt, ch, scale[ch], shift[ch], sc, sh);
         scale[ch] = sc;
-        shift[ch] = shift[ch] - mean * sc;
+        shift[ch] = sh;
     }
     __syncthreads();
     if (ty < by) {
@@ -359,142 +398,12 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
 
 constexpr int kGnFusedMaxSmem = 200 * 1024;
 
-// ---------------------------------------------------------------------------------------
-// GroupNorm with one CTA per (image, group): the group's [hw, cpg] slab (strided 2*cpg-byte
-// segments of the NHWC rows) is pulled into shared memory once, reduced inside the CTA and
-// normalised from shared memory.  No grid barrier, no global atomics, no statistics buffer:
-// the dependent-latency chain of the barrier kernel above (atomics -> fence -> counter -> spin
-// -> statistics reload) disappears, which is what a small-batch step is made of.  Used whenever
-// hw * cpg * 2 bytes fit in shared memory (every SD-1.5 / SDXL GroupNorm at 64x64 latents
-// except the 960-channel concat at full resolution).
-// ---------------------------------------------------------------------------------------
-constexpr int kGnGroupThreads = 512;
-
-// channels (col, col+1) of pixel `px` of image `img` from the producer GEMM's split-K partials
-__device__ __forceinline__ uint32_t gn_finish_partials2(const GnArgs& a, int img, int px, int col) {
-    const int m = img * a.hw + px;
-    const size_t stride = (size_t)a.n * a.hw * a.part_ld;
-    const float* p0 = a.part_ws + (size_t)m * a.part_ld + col;
-    float ax = 0.f, ay = 0.f;
-#pragma unroll 6
-    for (int s = 0; s < a.part_splits; ++s) {
-        const float2 v = __ldcg(reinterpret_cast<const float2*>(p0 + (size_t)s * stride));
-        ax += v.x; ay += v.y;
-    }
-    if (a.part_bias) { ax += a.part_bias[col]; ay += a.part_bias[col + 1]; }
-    if (a.part_rowbias) {
-        const float* rb = a.part_rowbias + (size_t)img * a.part_ld_rowbias + col;
-        ax += rb[0]; ay += rb[1];
-    }
-    if (a.part_residual) {
-        const float2 r = unpack2(*reinterpret_cast<const uint32_t*>(a.part_residual + (size_t)m * a.part_ldr + col), a.dtype);
-        ax += r.x; ay += r.y;
-    }
-    const uint32_t v = pack2(ax, ay, a.dtype);
-    *reinterpret_cast<uint32_t*>(const_cast<uint16_t*>(a.x) + (size_t)m * a.ldx + col) = v;
-    return v;
-}
-
-template <bool kPart>
-__global__ void __launch_bounds__(kGnGroupThreads) gn_group_kernel(const GnArgs a) {
-    extern __shared__ __align__(16) uint8_t gsm[];
-    uint32_t* slab = reinterpret_cast<uint32_t*>(gsm);  // [hw][cpg / 2] pairs of 16-bit values
-    __shared__ float s_gamma[128], s_beta[128];
-    __shared__ float s_red[2][kGnGroupThreads / 32];
-    __shared__ float s_stat[2];
-    const int g = blockIdx.x, img = blockIdx.y;
-    const int hp = a.cpg >> 1;
-    const int items = a.hw * hp;
-    const int ch0 = g * a.cpg;
-    pdl_launch_dependents();
-    // the affine parameters are weights: fetch them before waiting for the producer kernel
-    for (int i = threadIdx.x; i < a.cpg; i += kGnGroupThreads) {
-        s_gamma[i] = a.gamma[ch0 + i];
-        s_beta[i] = a.beta[ch0 + i];
-    }
-    pdl_wait();
-    const uint16_t* xb = a.x + (size_t)img * a.hw * a.ldx + ch0;
-    float s = 0.f, ss = 0.f;
-    constexpr int kU = kPart ? 2 : 8;  // items whose loads are in flight together
-    for (int i0 = threadIdx.x; i0 < items; i0 += kGnGroupThreads * kU) {
-        uint32_t v[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const int i = i0 + u * kGnGroupThreads;
-            if (i < items) {
-                const int px = i / hp, pr = i - px * hp;
-                if (kPart && ch0 + 2 * pr < a.part_c)
-                    v[u] = gn_finish_partials2(a, img, px, ch0 + 2 * pr);
-                else
-                    v[u] = *reinterpret_cast<const uint32_t*>(xb + (size_t)px * a.ldx + 2 * pr);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const int i = i0 + u * kGnGroupThreads;
-            if (i < items) {
-                slab[i] = v[u];
-                const float2 f = unpack2(v[u], a.dtype);
-                s += f.x + f.y;
-                ss += f.x * f.x + f.y * f.y;
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { s_red[0][warp] = s; s_red[1][warp] = ss; }
-    __syncthreads();
-    if (warp == 0) {
-        float t = lane < kGnGroupThreads / 32 ? s_red[0][lane] : 0.f;
-        float tt = lane < kGnGroupThreads / 32 ? s_red[1][lane] : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            t += __shfl_xor_sync(0xffffffffu, t, o);
-            tt += __shfl_xor_sync(0xffffffffu, tt, o);
-        }
-        if (lane == 0) {
-            const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
-            const float mean = t * inv_cnt;
-            const float var = fmaxf(tt * inv_cnt - mean * mean, 0.f);
-            s_stat[0] = mean;
-            s_stat[1] = rsqrtf(var + a.eps);
-        }
-    }
-    __syncthreads();
-    const float mean = s_stat[0], rstd = s_stat[1];
-    uint16_t* yb = a.y + (size_t)img * a.hw * a.ldy + ch0;
-    for (int i = threadIdx.x; i < items; i += kGnGroupThreads) {
-        const int px = i / hp, pr = i - px * hp;
-        const float2 f = unpack2(slab[i], a.dtype);
-        const float sc0 = rstd * s_gamma[2 * pr], sc1 = rstd * s_gamma[2 * pr + 1];
-        float y0 = (f.x - mean) * sc0 + s_beta[2 * pr];
-        float y1 = (f.y - mean) * sc1 + s_beta[2 * pr + 1];
-        if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-        *reinterpret_cast<uint32_t*>(yb + (size_t)px * a.ldy + 2 * pr) = pack2(y0, y1, a.dtype);
-    }
-}
-
-// whether the per-(image, group) kernel applies: the group slab must fit in shared memory
-static bool gn_group_fits(const sfb_gn_params* p, size_t& smem) {
-    // measured on B200: 4-byte strided accesses from only n * groups CTAs cost more than the grid
-    // barrier they avoid (5.60 vs 4.88 ms per step at B = 2), so this kernel is opt-in
-    static const bool enabled = [] { const char* v = getenv("SFB_GN_GROUP"); return v && v[0] == '1'; }();
-    if (!enabled || p->groups <= 0 || p->c % p->groups || p->n <= 0) return false;
-    const int cpg = p->c / p->groups;
-    if (cpg % 2 || cpg > 128 || p->ldx % 2 || p->ldy % 2) return false;
-    smem = (size_t)p->hw * cpg * 2;
-    return smem <= (size_t)kGnFusedMaxSmem;
-}
-
 // grid geometry of the fused kernel; returns false if the tensor does not fit in shared memory
 static bool gn_fused_geometry(const sfb_gn_params* p, int& blocks_per_img, int& rows_per_block,
                               size_t& smem) {
-    if (p->n <= 0 || p->n > 148) return false;
-    blocks_per_img = 148 / p->n;
+    const int sms = sm_count();
+    if (p->n <= 0 || p->n > sms) return false;
+    blocks_per_img = sms / p->n;
     if (blocks_per_img > p->hw) blocks_per_img = p->hw;
     if (blocks_per_img < 1) return false;
     rows_per_block = (p->hw + blocks_per_img - 1) / blocks_per_img;
@@ -583,11 +492,9 @@ static int make_gn_args(const sfb_gn_params* p, GnArgs& a, int& blocks_per_img) 
     a.gamma = p->gamma; a.beta = p->beta; a.stats = p->stats;
     a.n = p->n; a.hw = p->hw; a.c = p->c; a.ldx = p->ldx; a.ldy = p->ldy; a.groups = p->groups;
     a.cpg = p->c / p->groups; a.nvec = p->c / 8; a.eps = p->eps; a.silu = p->silu; a.dtype = p->dtype;
-    a.shards = p->stat_shards > 0 ? p->stat_shards : 1;
-    a.shard_stride = p->stat_shard_stride;
     const int by = kGnThreads / a.nvec;
-    // aim for >= 2 waves of 148 SMs while giving each thread a few rows
-    int want = (2 * 148 + p->n - 1) / p->n;
+    // aim for >= 2 waves of the SMs while giving each thread a few rows
+    int want = (2 * sm_count() + p->n - 1) / p->n;
     int max_blocks = (p->hw + by - 1) / by;
     blocks_per_img = want < max_blocks ? want : max_blocks;
     if (blocks_per_img < 1) blocks_per_img = 1;
@@ -628,8 +535,46 @@ extern "C" int sfb_group_norm_fused_fits(const sfb_gn_params* p) {
     int bpi, rpb;
     size_t smem;
     if (!p || p->c % 8 || p->c <= 0 || p->groups <= 0 || p->c % p->groups || p->c / 8 > kGnThreads) return 0;
-    if (gn_group_fits(p, smem)) return 1;
     return gn_fused_geometry(p, bpi, rpb, smem) ? 1 : 0;
+}
+
+// Cooperative launch of the fused kernel (the grid barrier needs every CTA resident).  The
+// programmatic-dependent-launch attribute is added when the driver accepts the combination
+// (probed once per device on the first launch, outside any graph capture: the runtime's warm-up
+// pass precedes capture).
+template <bool kPart>
+static cudaError_t launch_gn_fused(dim3 grid, size_t smem, cudaStream_t stream, const GnArgs& a, unsigned* sync) {
+    static int pdl_ok[64];  // 0 unknown, 1 yes, -1 no
+    const int dev = current_device();
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool with_pdl = g_pdl && pdl_ok[dev] >= 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kGnThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        int n = 0;
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
+        if (with_pdl) {
+            attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[n].val.programmaticStreamSerializationAllowed = 1;
+            ++n;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = n;
+        const cudaError_t err = cudaLaunchKernelEx(&cfg, gn_fused_kernel<kPart>, a, sync);
+        if (err == cudaSuccess) {
+            if (with_pdl) pdl_ok[dev] = 1;
+            return err;
+        }
+        if (!with_pdl || pdl_ok[dev] == 1) return err;
+        cudaGetLastError();
+        pdl_ok[dev] = -1;  // cooperative + PDL refused: cooperative alone from now on
+    }
+    return cudaErrorUnknown;
 }
 
 extern "C" int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream) {
@@ -641,8 +586,7 @@ extern "C" int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream)
         return fail(SFB_ERR_INVALID, "group_norm_fused: null/ldy/sync_counter");
     int rpb = 0;
     size_t smem;
-    const bool per_group = gn_group_fits(p, smem);
-    if (!per_group && !gn_fused_geometry(p, bpi, rpb, smem))
+    if (!gn_fused_geometry(p, bpi, rpb, smem))
         return fail(SFB_ERR_INVALID, "group_norm_fused: tensor does not fit in shared memory");
     a.rows_per_block = rpb;
     if (p->part_splits > 1) {
@@ -661,29 +605,21 @@ extern "C" int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream)
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kGnFusedMaxSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(gn_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kGnFusedMaxSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(gn_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kGnFusedMaxSmem);
         if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    if (per_group) {
-        // one CTA per (image, group): no grid barrier, no statistics buffer
-        const dim3 grid(p->groups, p->n);
-        cudaError_t err = a.part_splits > 1
-            ? launch_pdl(gn_group_kernel<true>, grid, dim3(kGnGroupThreads), smem, static_cast<cudaStream_t>(stream), a)
-            : launch_pdl(gn_group_kernel<false>, grid, dim3(kGnGroupThreads), smem, static_cast<cudaStream_t>(stream), a);
-        if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused(per group): %s", cudaGetErrorString(err));
-        return check_launch("sfb_group_norm_fused");
-    }
+    // the whole grid must be co-resident: check against the occupancy of this kernel on this device
+    int per_sm = 0;
+    cudaError_t oe = a.part_splits > 1
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<true>, kGnThreads, smem)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<false>, kGnThreads, smem);
+    if (oe != cudaSuccess || (long long)per_sm * sm_count() < (long long)bpi * p->n)
+        return fail(SFB_ERR_INVALID, "group_norm_fused: grid of %d CTAs cannot be co-resident (%d per SM x %d SMs)",
+                    bpi * p->n, per_sm, sm_count());
+    const dim3 grid(bpi, p->n);
     cudaError_t err = a.part_splits > 1
-        ? launch_pdl(gn_fused_kernel<true>, dim3(bpi, p->n), dim3(kGnThreads), smem,
-                     static_cast<cudaStream_t>(stream), a, p->sync_counter)
-        : launch_pdl(gn_fused_kernel<false>, dim3(bpi, p->n), dim3(kGnThreads), smem,
-                     static_cast<cudaStream_t>(stream), a, p->sync_counter);
+        ? launch_gn_fused<true>(grid, smem, static_cast<cudaStream_t>(stream), a, p->sync_counter)
+        : launch_gn_fused<false>(grid, smem, static_cast<cudaStream_t>(stream), a, p->sync_counter);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_fused: %s", cudaGetErrorString(err));
     return check_launch("sfb_group_norm_fused");
 }

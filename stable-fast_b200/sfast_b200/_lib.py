@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SFB_LIB_PATH") or os.path.join(_HERE, "libsfb200.so")
 
 SFB_F16, SFB_BF16 = 0, 1
-A_MATRIX, A_CONV3X3, A_UPCONV2X = 0, 1, 2
+A_MATRIX, A_CONV3X3, A_UPCONV2X, A_CONV3X1 = 0, 1, 2, 3
+ROW_IDX_DIV_MOD, ROW_IDX_TEMPORAL_CTX = 0, 1
 EPI_STORE, EPI_GEGLU, EPI_QKV = 0, 1, 2
 
 
@@ -23,8 +24,7 @@ class GemmParams(C.Structure):
         ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32), ("cin", C.c_int32),
         ("conv_stride", C.c_int32), ("box_h", C.c_int32), ("box_n", C.c_int32),
         ("box_w", C.c_int32),
-        ("splits", C.c_int32), ("ws", C.c_void_p), ("split_sync", C.c_void_p),
-        ("cluster_k", C.c_int32), ("defer_finish", C.c_int32),
+        ("splits", C.c_int32), ("ws", C.c_void_p), ("defer_finish", C.c_int32),
         ("epi", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int32),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p),
         ("rows_per_img", C.c_int32), ("ld_rowbias", C.c_int32),
@@ -33,13 +33,9 @@ class GemmParams(C.Structure):
         ("heads", C.c_int32), ("head_dim", C.c_int32), ("which_base", C.c_int32),
         ("seq", C.c_int32), ("q_pitch", C.c_int32), ("q_rows", C.c_int32),
         ("k_rows", C.c_int32), ("vt_rows", C.c_int32), ("vt_pitch", C.c_int32),
-        ("cluster_n", C.c_int32), ("cluster_m", C.c_int32), ("a_part_dim", C.c_int32),
-        ("a_part_ext", C.c_int32), ("cta_pair", C.c_int32),
+        ("cta_pair", C.c_int32), ("persistent", C.c_int32),
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_dim", C.c_int32),
-        ("gn_stats", C.c_void_p * 2), ("gn_cpg", C.c_int32 * 2), ("gn_choff", C.c_int32 * 2),
-        ("gn_groups", C.c_int32), ("gn_rows_per_img", C.c_int32), ("gn_shard_stride", C.c_int32),
-        ("debug_stamps", C.c_void_p),
     ]
 
 
@@ -61,7 +57,7 @@ class GnParams(C.Structure):
         ("n", C.c_int32), ("hw", C.c_int32), ("c", C.c_int32), ("ldx", C.c_int32),
         ("ldy", C.c_int32), ("groups", C.c_int32),
         ("eps", C.c_float), ("silu", C.c_int32), ("dtype", C.c_int32),
-        ("sync_counter", C.c_void_p), ("stat_shards", C.c_int32), ("stat_shard_stride", C.c_int32),
+        ("sync_counter", C.c_void_p),
         ("part_ws", C.c_void_p), ("part_splits", C.c_int32), ("part_c", C.c_int32),
         ("part_ld", C.c_int32), ("part_bias", C.c_void_p), ("part_rowbias", C.c_void_p),
         ("part_ld_rowbias", C.c_int32), ("part_residual", C.c_void_p), ("part_ldr", C.c_int32),
@@ -83,6 +79,22 @@ class SmallLinearParams(C.Structure):
         ("batch", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("ldx", C.c_int32),
         ("ldy", C.c_int32), ("act_in", C.c_int32), ("act_out", C.c_int32), ("dtype", C.c_int32),
     ]
+
+
+class TemporalAttnParams(C.Structure):
+    _fields_ = [("qkv", C.c_void_p), ("out", C.c_void_p),
+                ("batch", C.c_int32), ("frames", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32),
+                ("head_dim", C.c_int32), ("ld_qkv", C.c_int32), ("ld_out", C.c_int32), ("dtype", C.c_int32),
+                ("scale", C.c_float)]
+
+
+class RowOpParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x2", C.c_void_p), ("vec", C.c_void_p), ("y", C.c_void_p),
+                ("rowstats_out", C.c_void_p), ("mix_factor", C.c_void_p),
+                ("rows", C.c_int32), ("c", C.c_int32), ("ldx", C.c_int32), ("ldx2", C.c_int32),
+                ("ldv", C.c_int32), ("ldy", C.c_int32), ("dtype", C.c_int32),
+                ("mode", C.c_int32), ("div", C.c_int32), ("mod", C.c_int32), ("frames", C.c_int32),
+                ("seq", C.c_int32), ("batch", C.c_int32)]
 
 
 class AddNchwItem(C.Structure):
@@ -117,6 +129,9 @@ SYMBOLS = {
     "sfb_conv_in": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_conv_out": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_upsample2x": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_temporal_attention": (C.c_int, [C.POINTER(TemporalAttnParams), _VP]),
+    "sfb_row_broadcast_add": (C.c_int, [C.POINTER(RowOpParams), _VP]),
+    "sfb_alpha_blend": (C.c_int, [C.POINTER(RowOpParams), _VP]),
     "sfb_add_nchw_residuals": (C.c_int, [C.POINTER(AddNchwParams), _VP]),
     "sfb_copy2d": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "sfb_memset": (C.c_int, [_VP, _I32, C.c_size_t, _VP]),
@@ -143,7 +158,7 @@ def lib():
             fn = getattr(h, name)
             fn.restype = res
             fn.argtypes = args
-        if h.sfb_abi_version() != 1:
+        if h.sfb_abi_version() != 2:
             raise SfbError("libsfb200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -11,11 +11,23 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (A_CONV3X3, A_MATRIX, A_UPCONV2X, EPI_GEGLU, EPI_QKV, EPI_STORE, AttnParams, GemmParams,
+from ._lib import (A_CONV3X1, A_CONV3X3, A_MATRIX, A_UPCONV2X, EPI_GEGLU, EPI_QKV, EPI_STORE, AttnParams, GemmParams,
                    GnParams, LnParams, SmallLinearParams, TensorMap, check)
 
 BM, BN, BK = 128, 160, 64
-NUM_SMS = 148
+_NUM_SMS = None
+
+
+def num_sms():
+    """SMs of the current CUDA device (the C library's count: 148 on a full B200, fewer under MIG
+    or a green context); 148 when planning without a GPU (dry plans in CPU tests)."""
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        if torch.cuda.is_available():
+            _NUM_SMS = int(_lib.lib().sfb_sm_count())
+        else:
+            return 148
+    return _NUM_SMS
 
 
 def dtype_code(dt):
@@ -112,53 +124,36 @@ def conv_tile_box(ho, wo):
 
 # split-K cost model (microseconds, measured on B200 inside the captured graph):
 # a single-wave GEMM launch costs ~4.5 us of prologue + epilogue + drain plus 0.34 us per 64-wide
-# K block of its longest CTA; the fused reduction (last-arriving split CTA sums the other partial
-# tiles from L2) adds ~1.5 us + 1.6 us per extra split; the stand-alone reduction kernel ~10 us
-# plus its fp32 partial traffic at ~3 TB/s.
-FUSED_SPLITK_MAX = int(os.environ.get("SFB_FUSED_SPLITK_MAX", "4"))
+# K block of its longest CTA; the stand-alone reduction kernel ~10 us plus its fp32 partial
+# traffic at ~3 TB/s (a conv followed by a GroupNorm leaves the reduction to that kernel).
 _T_FIXED, _T_KB = 4.5, 0.34
 
 
-def choose_splits(m_tiles, n_tiles, nkb, M=None, N=None, fused=True):
+def choose_splits(m_tiles, n_tiles, nkb, M=None, N=None):
     """Split-K factor minimising the modelled launch time.  Only grids of at most half a wave are
     split (the weight-bandwidth-bound low-resolution layers); all split CTAs fit in one wave."""
     tiles = m_tiles * n_tiles
-    if tiles * 2 > NUM_SMS:
+    sms = num_sms()
+    if tiles * 2 > sms:
         return 1
     M = M if M is not None else m_tiles * BM
     N = N if N is not None else n_tiles * BN
     best, best_t = 1, _T_FIXED + _T_KB * nkb
-    for s in range(2, min(NUM_SMS // tiles, nkb) + 1):
-        t = _T_FIXED + _T_KB * -(-nkb // s)
-        if fused and s <= FUSED_SPLITK_MAX:
-            t += 1.5 + 1.6 * (s - 1)
-        else:
-            t += 10.0 + s * M * N * 4 / 3e6
+    for s in range(2, min(sms // tiles, nkb) + 1):
+        t = _T_FIXED + _T_KB * -(-nkb // s) + 10.0 + s * M * N * 4 / 3e6
         if t < best_t - 0.5:
             best, best_t = s, t
     return best
 
 
-ENABLE_CLUSTER = os.environ.get("SFB_CLUSTER", "0") != "0"  # measured slower on B200: smem-bound, see DESIGN.md
-
-
 ENABLE_CTA_PAIR = os.environ.get("SFB_CTA_PAIR", "1") != "0"
 
-# split-K partial tiles summed through distributed shared memory inside a thread-block cluster
-# along grid.z (no fp32 workspace round trip, no reduction kernel); cluster sizes > 8 are
-# "non-portable" (one cluster of 16 per GPC on B200)
-ENABLE_CLUSTER_K = os.environ.get("SFB_CLUSTER_K", "0") != "0"  # measured slower (cluster co-scheduling), DESIGN.md
-CLUSTER_K_MAX = int(os.environ.get("SFB_CLUSTER_K_MAX", "16"))
-
-
-def choose_cluster(m_tiles, n_tiles):
-    """(cluster_n, cluster_m): CTAs sharing an A tile (along N, <= 2) / a weight tile (along M, <= 4).
-    TMA multicast turns cluster_m (cluster_n) L2 reads of the same tile into one."""
-    if not ENABLE_CLUSTER:
-        return 1, 1
-    cn = 2 if n_tiles % 2 == 0 else 1
-    cm = 4 if m_tiles % 4 == 0 else (2 if m_tiles % 2 == 0 else 1)
-    return cn, cm
+# Persistent 256 x 320 pair kernel: "auto" = launches whose one-tile-per-CTA grid (128/256 x 160
+# tiles) would be larger than SFB_PERSIST_MIN_CTAS CTAs, i.e. more than ~1.4 waves of 148 SMs --
+# below that the one-tile kernel already has every SM busy for one tile and the persistent
+# kernel's larger tile would leave SMs idle.  "0" / "1": never / whenever eligible.
+PERSIST = os.environ.get("SFB_PERSIST", "0")
+PERSIST_MIN_CTAS = int(os.environ.get("SFB_PERSIST_MIN_CTAS", "200"))
 
 
 def a_matrix(x_ptr, rows, cols, pitch):
@@ -171,88 +166,64 @@ def a_conv(x_ptr, n, h, w, c, pitch, box_n, box_h, box_w, stride):
                 wo=box_w, stride=stride)
 
 
-def _a_map(a, cn, dry):
-    """A-operand TMA map with a box of 1/cn of the 128-row tile; returns (map, part_dim, part_ext)."""
+def _a_map(a, dry):
+    """A-operand TMA map with a box of one 128-row tile."""
     if a["kind"] == "matrix":
-        return matrix_map(a["ptr"], a["rows"], a["cols"], a["pitch"], BM // cn, dry), 0, 0
-    bn, bh, bw = a["box_n"], a["box_h"], a["wo"]
-    dim = ext = 0
-    if cn == 2:
-        if bn > 1:
-            bn //= 2
-            dim, ext = 3, bn
-        elif bh > 1:
-            bh //= 2
-            dim, ext = 2, bh
-        else:
-            bw //= 2
-            dim, ext = 1, bw
-    return nhwc_map(a["ptr"], a["n"], a["h"], a["w"], a["c"], a["pitch"], bn, bh, bw, a["stride"],
-                    dry), dim, ext
+        return matrix_map(a["ptr"], a["rows"], a["cols"], a["pitch"], BM, dry)
+    return nhwc_map(a["ptr"], a["n"], a["h"], a["w"], a["c"], a["pitch"], a["box_n"], a["box_h"],
+                    a["wo"], a["stride"], dry)
 
 
 def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, out=None, ldo=0,
             bias=None, rowbias=None, rows_per_img=1, ld_rowbias=0, residual=None, ldr=0,
             epi=EPI_STORE, geglu_n_out=0, conv=None, qkv=None, ws=None, splits=None, keep=(),
-            rowstats_out=None, ln=None, dry=False, split_sync=None, cta_pair=None, cluster_k=None):
-    """Either pass ready-made maps (`a_map`, `b_map`: no cluster) or operand descriptors
-    (`a` from a_matrix()/a_conv(), `b` a Mat), in which case a thread-block cluster with TMA
-    multicast is chosen from the tile grid."""
+            rowstats_out=None, ln=None, dry=False, cta_pair=None, persistent=None):
+    """Either pass ready-made maps (`a_map`, `b_map`) or operand descriptors (`a` from
+    a_matrix()/a_conv(), `b` a Mat), in which case CTA pairs (cta_group::2) are used whenever the
+    number of M tiles is even, and the persistent 256 x 320 kernel when the launch is large enough
+    (PERSIST policy above; `persistent=True/False` forces it)."""
     p = GemmParams()
+    up = bool(conv and conv.get("up"))
     if conv:
-        mt = conv["n"] * ((conv["h"] + conv["box_h"] - 1) // conv["box_h"]) * \
-            (conv["w"] // conv.get("box_w", conv["w"])) if conv["box_n"] == 1 \
-            else (conv["n"] + conv["box_n"] - 1) // conv["box_n"]
+        if conv["box_n"] == 1:
+            m_tiles = conv["n"] * ((conv["h"] + conv["box_h"] - 1) // conv["box_h"]) * \
+                (conv["w"] // conv.get("box_w", conv["w"]))
+        else:
+            m_tiles = (conv["n"] + conv["box_n"] - 1) // conv["box_n"]
+        phase_tiles = m_tiles
+        if up:
+            m_tiles *= 4  # one set of M tiles per output phase
     else:
-        mt = (M + BM - 1) // BM
-    if a is not None and (ENABLE_CTA_PAIR if cta_pair is None else cta_pair) and mt % 2 == 0:
-        # CTA pairs along M: tcgen05.mma.cta_group::2, each CTA stages half of the weight tile
-        a_map, _, _ = _a_map(a, 1, dry)
-        b_map = b.map_for(2)
-        p.cta_pair = 1
-        keep = tuple(keep) + (b,)
-    elif a is not None:
-        cn, cm = choose_cluster(mt, (N + BN - 1) // BN)
-        if a["kind"] == "conv" and cn == 2 and a["box_n"] == 1 and a["box_h"] == 1 and a["wo"] % 2:
-            cn = 1
-        a_map, p.a_part_dim, p.a_part_ext = _a_map(a, cn, dry)
-        b_map = b.map_for(cm)
-        p.cluster_n, p.cluster_m = cn, cm
+        m_tiles = phase_tiles = (M + BM - 1) // BM
+    n_tiles = (N + BN - 1) // BN
+    nkb = K // BK
+    if a is not None:
+        pair = (ENABLE_CTA_PAIR if cta_pair is None else cta_pair) and phase_tiles % 2 == 0
+        a_map = _a_map(a, dry)
+        b_map = b.map_for(2 if pair else 1)
+        p.cta_pair = 1 if pair else 0
         keep = tuple(keep) + (b,)
     p.tmap_a, p.tmap_b = a_map.ptr, b_map.ptr
-    p.a_mode = (A_UPCONV2X if conv.get("up") else A_CONV3X3) if conv else A_MATRIX
+    p.a_mode = (A_UPCONV2X if up else (A_CONV3X1 if conv.get("temporal") else A_CONV3X3)) if conv else A_MATRIX
     p.M, p.N, p.K, p.dtype = M, N, K, dtype_code(dt)
     if conv:
         p.img_n, p.img_h, p.img_w = conv["n"], conv["h"], conv["w"]
         p.cin, p.conv_stride = conv["cin"], conv["stride"]
         p.box_n, p.box_h = conv["box_n"], conv["box_h"]
         p.box_w = conv.get("box_w", conv["w"])
-        if p.box_n == 1:
-            m_tiles = p.img_n * ((p.img_h + p.box_h - 1) // p.box_h) * (p.img_w // p.box_w)
-        else:
-            m_tiles = (p.img_n + p.box_n - 1) // p.box_n
-        if conv.get("up"):
-            m_tiles *= 4  # one set of M tiles per output phase
-    else:
-        m_tiles = (M + BM - 1) // BM
-    n_tiles = (N + BN - 1) // BN
-    nkb = K // BK
     if splits is None:
-        splits = choose_splits(m_tiles, n_tiles, nkb, M, N, fused=split_sync is not None)
+        splits = choose_splits(m_tiles, n_tiles, nkb, M, N)
     if ws is None:
         splits = 1
-    if cluster_k is None:
-        cluster_k = ENABLE_CLUSTER_K
-    if splits > 1 and cluster_k and not (p.cluster_n > 1 or p.cluster_m > 1):
-        splits = min(splits, max(1, CLUSTER_K_MAX // (2 if p.cta_pair else 1)))
-        p.cluster_k = 1 if splits > 1 else 0
     p.splits = splits
-    if splits > 1 and not p.cluster_k:
+    if splits > 1:
         need = splits * M * N
         if ws.numel() < need:
             raise ValueError(f"{name}: split-K workspace too small ({ws.numel()} < {need})")
         p.ws = _ptr(ws) if not hasattr(ws, "finalize") else 0
-        p.split_sync = _ptr(split_sync) if splits <= FUSED_SPLITK_MAX else 0
+    if persistent is None:
+        persistent = PERSIST == "1" or (PERSIST == "auto" and m_tiles * n_tiles >= PERSIST_MIN_CTAS)
+    p.persistent = 1 if (persistent and p.cta_pair and splits == 1) else 0
     p.epi = epi
     p.out = _ptr(out)
     p.ldo = ldo
@@ -322,13 +293,9 @@ def gn_fused_fits(n, hw, c, groups):
     authority on a GPU box)."""
     if n <= 0 or c % 8 or c % groups or c // 8 > 512:
         return False
-    cpg = c // groups
-    if (os.environ.get("SFB_GN_GROUP", "0") == "1" and cpg % 2 == 0 and cpg <= 128
-            and hw * cpg * 2 <= 200 * 1024):
-        return True  # one CTA per (image, group), slab in shared memory
-    if n > NUM_SMS:
+    if n > num_sms():
         return False
-    bpi = max(1, min(NUM_SMS // n, hw))
+    bpi = max(1, min(num_sms() // n, hw))
     rpb = (hw + bpi - 1) // bpi
     return rpb * c * 2 + 2 * c * 4 <= 200 * 1024
 
@@ -343,7 +310,7 @@ def gn_fused_ok(lib, x: Act, groups, dt, dry):
 
 
 def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, dt, sync=None,
-           dry=False, stats_ready=False, partial=None):
+           dry=False, partial=None):
     """GroupNorm(+SiLU): one fused launch when the tensor fits in shared memory (stats + apply
     with a grid barrier, x read once), else the two-pass stats / apply kernels.
     `partial`: channels [0, c) of x are still the fp32 split-K partials of their producer GEMM
@@ -357,9 +324,6 @@ def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, 
     p.sync_counter = _ptr(sync)
     keep = (p, x.buf, y.buf, gamma, beta, stats, sync)
     nb = x.rows * x.c * 2
-    if stats_ready:  # the producing GEMM(s) accumulated the statistics (8 shards) in their epilogue
-        p.stat_shards, p.stat_shard_stride = 8, x.n * groups * 2
-        return [Op(name + ".apply", lib.sfb_group_norm_apply, (C.byref(p),), keep, 0, 2 * nb)]
     if sync is not None:
         fits = gn_fused_fits(p.n, p.hw, p.c, groups) if dry else bool(
             lib.sfb_group_norm_fused_fits(C.byref(p)))

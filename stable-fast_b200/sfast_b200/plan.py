@@ -169,6 +169,25 @@ class PackedWeights:
             return (self._mat(wp), bp, inner)
         return self._get(("geglu", prefix), build)
 
+    def conv3x1_t(self, name, one_minus_alpha_of=None):
+        """Temporal conv weight [cout, cin, 3, 1, 1] -> K-major [cout, (kt, cin)] as a GEMM operand;
+        `one_minus_alpha_of`: name of an AlphaBlender mix_factor -- the weight is pre-scaled by
+        (1 - sigmoid(mix_factor)) so that the blend  alpha * x_s + (1 - alpha) * (x_s + conv(..))
+        = x_s + (1 - alpha) * conv(..)  is a plain residual epilogue."""
+        def build():
+            w = self._raw(name).to(self.device).float()
+            w = w[:, :, :, 0, 0].permute(0, 2, 1).reshape(w.shape[0], -1)
+            if one_minus_alpha_of is not None:
+                w = w * (1.0 - torch.sigmoid(self._raw(one_minus_alpha_of).to(self.device).float()))
+            return self._mat(w.to(self.dtype).contiguous())
+        return self._get(("c3t", name, one_minus_alpha_of), build)
+
+    def f32_scaled(self, name, one_minus_alpha_of):
+        def build():
+            v = self._raw(name).to(device=self.device, dtype=torch.float32)
+            return (v * (1.0 - torch.sigmoid(self._raw(one_minus_alpha_of).to(self.device).float()))).contiguous()
+        return self._get(("f32s", name, one_minus_alpha_of), build)
+
     def small(self, name):
         return self._get(("small", name), lambda: self._raw(name).to(
             device=self.device, dtype=self.dtype).contiguous())
@@ -195,10 +214,6 @@ class UNetPlan:
         # embedding): issued on a forked stream so they run concurrently with the start of the
         # main chain (a parallel branch of the captured CUDA graph).
         self.side_ops = []
-        # (buffer id, channel offset) -> (GemmParams, channels) of the GEMM that last wrote that slice:
-        # lets a GroupNorm ask its producer(s) to accumulate the statistics in their epilogue
-        self._producers = {}
-        self._gn_slots = {}
         self._side_stream = None
         self._pending = None      # conv GEMM whose split-K finish the next GroupNorm may absorb
         self._gn_ws_patches = []  # GnParams that read the split-K workspace (pointer known late)
@@ -221,17 +236,14 @@ class UNetPlan:
         n_gn = sum(2 for _ in spec.all_resnets()) + 1
         for blk in spec.down + [spec.mid] + spec.up:
             n_gn += sum(1 for t in blk.attentions if t is not None)
-        # 8 accumulation shards of [B, groups, 2] (producer-epilogue path) + 4 floats for the fused
-        # kernel's grid-barrier counter
-        self.gn_stats = self._alloc((n_gn, 8 * batch * spec.groups * 2 + 4), torch.float32)
+        # [B, groups, 2] statistics + 4 floats for the fused kernel's grid-barrier counter
+        self.gn_stats = self._alloc((n_gn, batch * spec.groups * 2 + 4), torch.float32)
         # folded-LayerNorm row statistics: [rows, 2] fp32 per LayerNorm, zeroed once per step
         self._ln_used = 0
         self._ln_slots = []
         self.ln_arena = self._alloc((max(self._ln_arena_floats(), 2),), torch.float32)
         self.ws = None
         self._ws_need = 0
-        # arrive/done counters of the fused split-K reduction (self re-arming: zeroed once, here)
-        self.split_sync = self._alloc((2 * 1024,), torch.int32)
         self._build()
         assert self._ln_used <= self.ln_arena.numel(), (self._ln_used, self.ln_arena.numel())
 
@@ -288,13 +300,7 @@ class UNetPlan:
     def _gemm(self, name, **kw):
         # split-K workspace: one shared fp32 buffer, sized after all ops are known
         kw.setdefault("ws", self._ws_token)
-        # last-arriving split CTA finishes the tile: measured slower than the reduction kernel
-        if os.environ.get("SFB_FUSED_SPLITK", "0") != "0" and os.environ.get("SFB_GN_EPILOGUE", "0") == "0":
-            kw.setdefault("split_sync", self.split_sync)
-        if os.environ.get("SFB_GN_EPILOGUE", "0") != "0":
-            kw.setdefault("cluster_k", False)  # GroupNorm statistics live in the reduction kernel
-        op = ops.gemm_op(name, self.lib_or_dry(), dry=self.dry, **kw)
-        return op
+        return ops.gemm_op(name, self.lib_or_dry(), dry=self.dry, **kw)
 
     def lib_or_dry(self):
         return self.lib if self.lib is not None else _DryLib
@@ -302,45 +308,14 @@ class UNetPlan:
     def _a_matrix(self, x: Act):
         return ops.a_matrix(x.ptr, x.rows, x.c, x.ld)
 
-    def _producer_stats(self, x: Act, stats):
-        """Ask the GEMM(s) that produced `x` to accumulate its GroupNorm statistics in their
-        epilogue.  Returns False (nothing changed) if any slice of x has no capable producer."""
-        if os.environ.get("SFB_GN_EPILOGUE", "0") == "0":  # measured slower than the fused kernel (DESIGN.md)
-            return False
-        groups = self.spec.groups
-        rpi, cpg = x.h * x.w, x.c // groups
-        if rpi < 16 or cpg < 2 or (128 % rpi and rpi % 128):
-            return False
-        chain, off = [], x.off
-        while off < x.off + x.c:
-            prod = self._producers.get((id(x.buf), off))
-            if prod is None:
-                return False
-            p, c = prod
-            slot = self._gn_slots.get(id(p), 0)  # consumers already registered with this producer
-            if slot > 1 or p.epi != ops.EPI_STORE or (slot and p.gn_rows_per_img != rpi):
-                return False
-            chain.append((p, slot, off - x.off))
-            off += c
-        if off != x.off + x.c:
-            return False
-        for p, slot, choff in chain:
-            self._gn_slots[id(p)] = slot + 1
-            p.gn_stats[slot] = _ptr(stats)
-            p.gn_cpg[slot], p.gn_choff[slot] = cpg, choff
-            p.gn_groups, p.gn_rows_per_img = groups, rpi
-            p.gn_shard_stride = self.B * groups * 2
-        return True
-
     def group_norm(self, name, x: Act, prefix, silu, eps):
         y = self.act("gn_out", x.n, x.h, x.w, x.c)
         slot = self.gn_stats[self._gn_count]
         self._gn_count += 1
-        from_producer = self._producer_stats(x, slot)
         partial, pend = None, self._pending
         if pend is not None:
             d = pend["dst"]
-            if (not from_producer and d.buf is x.buf and d.off == x.off and d.c <= x.c and
+            if (d.buf is x.buf and d.off == x.off and d.c <= x.c and
                     (d.n, d.h, d.w) == (x.n, x.h, x.w) and
                     ops.gn_fused_ok(self.lib_or_dry(), x, self.spec.groups, self.dt, self.dry)):
                 partial = pend["info"]
@@ -348,7 +323,7 @@ class UNetPlan:
         gn = ops.gn_ops(name, self.lib_or_dry(), x=x, y=y, gamma=self.w.f32(prefix + ".weight"),
                         beta=self.w.f32(prefix + ".bias"), stats=slot, sync=slot[-4:],
                         groups=self.spec.groups, eps=eps, silu=silu, dt=self.dt,
-                        dry=self.dry, stats_ready=from_producer, partial=partial)
+                        dry=self.dry, partial=partial)
         if partial is not None:
             self._gn_ws_patches.append(gn[0].keep[0])
         self._emit(gn)
@@ -371,14 +346,12 @@ class UNetPlan:
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
         op = self._gemm(name, **kw)
-        self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
         self._emit(op)
         self._maybe_defer_finish(op.keep[0], dst, cout, kw["bias"], rowbias, residual)
 
     def _maybe_defer_finish(self, gp, dst, cout, bias, rowbias=None, residual=None):
         """Tentatively leave a conv's split-K reduction to the GroupNorm that consumes dst next."""
-        if (gp.splits > 1 and not gp.cluster_k and not gp.split_sync and
-                os.environ.get("SFB_GN_FINISH", "1") != "0" and os.environ.get("SFB_GN_EPILOGUE", "0") == "0"):
+        if gp.splits > 1 and os.environ.get("SFB_GN_FINISH", "1") != "0":
             gp.defer_finish = 1
             info = dict(splits=gp.splits, c=cout, ld=cout, bias=bias)
             if rowbias is not None:
@@ -400,7 +373,6 @@ class UNetPlan:
                         conv=dict(n=x.n, h=x.h, w=x.w, cin=x.c, stride=1, box_n=box_n, box_h=box_h,
                                   box_w=box_w, up=True))
         op.flops = 2 * M * cout * 9 * x.c  # algorithmic count of the reference formulation
-        self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
         self._emit(op)
         self._maybe_defer_finish(op.keep[0], dst, cout, bias)
 
@@ -412,7 +384,6 @@ class UNetPlan:
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
         op = self._gemm(name, **kw)
-        self._producers[(id(dst.buf), dst.off)] = (op.keep[0], dst.c)
         self._emit(op)
 
     # ------------------------------------------------------------------ sub-graphs
@@ -421,7 +392,8 @@ class UNetPlan:
         fork = None
         # norm1 first: it may be the kernel that finishes x (deferred split-K reduction of the
         # conv that produced it), so every other reader of x is ordered after it
-        a1 = self.group_norm(p + ".norm1", x, p + ".norm1", True, self.spec.eps)
+        eps = r.eps if r.eps is not None else self.spec.eps
+        a1 = self.group_norm(p + ".norm1", x, p + ".norm1", True, eps)
         if r.has_shortcut and os.environ.get("SFB_SIDE_SHORTCUT", "1") != "0":
             # the 1x1 shortcut only needs the block input: parallel graph branch next to
             # norm1 / conv1 / norm2 (most of these launches leave SMs idle at small batch)
@@ -435,7 +407,7 @@ class UNetPlan:
         h1 = self.act("res_h1", x.n, x.h, x.w, r.cout)
         rb_ptr = _ptr(self.temb_proj) + 4 * self.w.tproj_off[p]
         self.conv3x3(p + ".conv1", a1, p + ".conv1", h1, rowbias=(rb_ptr, self.w.tproj_total))
-        a2 = self.group_norm(p + ".norm2", h1, p + ".norm2", True, self.spec.eps)
+        a2 = self.group_norm(p + ".norm2", h1, p + ".norm2", True, eps)
         if fork is not None:
             self._emit(_JoinOp(fork))
             res = sc
@@ -805,11 +777,11 @@ class _WsToken:
         gemm = plan.lib_or_dry().sfb_gemm
         main_ops = [op for op in plan.ops if not isinstance(op, (_ForkOp, _JoinOp))]
         for op in main_ops:
-            if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
+            if op.fn is gemm and op.keep[0].splits > 1:
                 need = max(need, op.keep[0].splits * op.keep[0].M * op.keep[0].N)
         plan.ws = plan._alloc((max(need, 1),), torch.float32)
         for op in main_ops:
-            if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
+            if op.fn is gemm and op.keep[0].splits > 1:
                 op.keep[0].ws = _ptr(plan.ws)
         # side-stream GEMMs run concurrently with the main chain: they must not share the
         # split-K workspace, so they are never split
@@ -817,7 +789,7 @@ class _WsToken:
             gp.part_ws = _ptr(plan.ws)
         forked = [o for op in plan.ops if isinstance(op, _ForkOp) for o in op.branch]
         for op in plan.side_ops + forked:
-            if op.fn is gemm and op.keep[0].splits > 1 and not op.keep[0].cluster_k:
+            if op.fn is gemm and op.keep[0].splits > 1:
                 raise AssertionError("side-stream GEMM must not use split-K")
 
 

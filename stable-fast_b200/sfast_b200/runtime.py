@@ -14,6 +14,7 @@ import time
 import torch
 
 from .plan import PackedWeights, UNetPlan
+from .svd_plan import SVDPlan
 from .unet_spec import spec_from_config
 
 logger = logging.getLogger(__name__)
@@ -130,7 +131,51 @@ class CompiledUNet:
                     self._refresh_locked()
 
     # -- forward -------------------------------------------------------------------------
-    def __call__(self, sample, timestep, encoder_hidden_states, class_labels=None,
+    def _call_svd(self, sample, timestep, encoder_hidden_states, added_time_ids, return_dict=True):
+        """diffusers UNetSpatioTemporalConditionModel.forward(sample [B, F, C, H, W], timestep,
+        encoder_hidden_states [B, 1, ctx], added_time_ids [B, 3])."""
+        require_b200(sample.device)
+        dtype = sample.dtype
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise NotImplementedError(f"sfast (B200 build): UNet dtype {dtype}; use fp16 or bf16")
+        B, F_, _, H, W = sample.shape
+        if F_ != self.spec.num_frames:
+            raise NotImplementedError(f"sfast (B200 build): {F_} frames, the UNet was configured for "
+                                      f"{self.spec.num_frames}")
+        if encoder_hidden_states.shape[1] != 1:
+            raise NotImplementedError("sfast (B200 build): SVD path needs a single-token encoder_hidden_states")
+        with self._lock, torch.cuda.device(sample.device):
+            t_first = time.perf_counter() if self.first_call_s is None else None
+            weights = self._ensure_weights(dtype, sample.device)
+            key = ("svd", B, H, W, dtype, sample.device.index)
+            gp = self._cached.get(key)
+            if gp is None:
+                logger.info("Building SVD UNet launch plan for %s", key)
+                gp = _GraphedPlan(SVDPlan(weights, B, H, W), self.enable_cuda_graph)
+                self._cached[key] = gp
+            plan = gp.plan
+            plan.sample_in.copy_(sample.reshape(B * F_, -1, H, W), non_blocking=True)
+            plan.ehs_in.copy_(encoder_hidden_states.repeat_interleave(F_, dim=0), non_blocking=True)
+            t = timestep if torch.is_tensor(timestep) else torch.tensor(float(timestep))
+            t = t.reshape(-1).to(device=sample.device, dtype=torch.float32, non_blocking=True)
+            plan.t_in.copy_((t.expand(B) if t.numel() == 1 else t).repeat_interleave(F_))
+            plan.time_ids_in.copy_(added_time_ids.to(device=sample.device, dtype=torch.float32)
+                                   .repeat_interleave(F_, dim=0).reshape(-1))
+            gp.step()
+            out = plan.out.clone().reshape(B, F_, -1, H, W)
+            if t_first is not None:
+                torch.cuda.current_stream().synchronize()
+                self.first_call_s = time.perf_counter() - t_first
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(sample=out)
+
+    def __call__(self, sample, timestep, encoder_hidden_states, *args, **kwargs):
+        if self.spec.temporal:
+            return self._call_svd(sample, timestep, encoder_hidden_states, *args, **kwargs)
+        return self._call_2d(sample, timestep, encoder_hidden_states, *args, **kwargs)
+
+    def _call_2d(self, sample, timestep, encoder_hidden_states, class_labels=None,
                  timestep_cond=None, attention_mask=None, cross_attention_kwargs=None,
                  added_cond_kwargs=None, down_block_additional_residuals=None,
                  mid_block_additional_residual=None, down_intrablock_additional_residuals=None,

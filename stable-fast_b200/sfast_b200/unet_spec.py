@@ -31,6 +31,11 @@ class ResnetSpec:
     prefix: str
     cin: int
     cout: int
+    eps: Optional[float] = None          # GroupNorm eps (None: the UNet's norm_eps)
+    # SVD SpatioTemporalResBlock: `prefix` is the spatial ResnetBlock2D; the temporal
+    # TemporalResnetBlock ((3,1,1) convolutions over the frame axis) and the AlphaBlender follow
+    temporal_prefix: Optional[str] = None
+    mixer: Optional[str] = None          # name of the AlphaBlender's mix_factor parameter
 
     @property
     def has_shortcut(self):
@@ -45,6 +50,7 @@ class TransformerSpec:
     depth: int
     ctx_dim: int
     linear_proj: bool
+    temporal: bool = False  # SVD TransformerSpatioTemporalModel (temporal blocks + time_pos_embed + mixer)
 
     @property
     def head_dim(self):
@@ -77,11 +83,20 @@ class UNetSpec:
     down: List[BlockSpec] = field(default_factory=list)
     mid: Optional[BlockSpec] = None
     up: List[BlockSpec] = field(default_factory=list)
+    num_frames: int = 0     # > 0: UNetSpatioTemporalConditionModel (SVD)
+
+    @property
+    def temporal(self):
+        return self.num_frames > 0
 
     def all_resnets(self):
+        """Every block that owns a `time_emb_proj` (SVD: spatial and temporal halves)."""
         out = []
         for b in self.down + [self.mid] + self.up:
-            out.extend(b.resnets)
+            for r in b.resnets:
+                out.append(r)
+                if r.temporal_prefix:
+                    out.append(ResnetSpec(r.temporal_prefix, r.cout, r.cout, r.eps))
         return out
 
 
@@ -90,6 +105,8 @@ _SUPPORTED_UP = ("CrossAttnUpBlock2D", "UpBlock2D")
 
 
 def spec_from_config(cfg) -> UNetSpec:
+    if is_svd_config(cfg):
+        return svd_spec_from_config(cfg)
     boc = tuple(cfg_get(cfg, "block_out_channels"))
     nb = len(boc)
     down_types = tuple(cfg_get(cfg, "down_block_types"))
@@ -189,6 +206,85 @@ def spec_from_config(cfg) -> UNetSpec:
     return spec
 
 
+_SVD_DOWN = ("CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal")
+_SVD_UP = ("CrossAttnUpBlockSpatioTemporal", "UpBlockSpatioTemporal")
+
+
+def is_svd_config(cfg):
+    return any("SpatioTemporal" in t for t in (cfg_get(cfg, "down_block_types") or ()))
+
+
+def svd_spec_from_config(cfg) -> UNetSpec:
+    """diffusers UNetSpatioTemporalConditionModel (Stable Video Diffusion)."""
+    boc = tuple(cfg_get(cfg, "block_out_channels"))
+    nb = len(boc)
+    down_types, up_types = tuple(cfg_get(cfg, "down_block_types")), tuple(cfg_get(cfg, "up_block_types"))
+    for t in down_types:
+        if t not in _SVD_DOWN:
+            raise NotImplementedError(f"down block type {t} is not supported by the B200 path")
+    for t in up_types:
+        if t not in _SVD_UP:
+            raise NotImplementedError(f"up block type {t} is not supported by the B200 path")
+    layers = cfg_get(cfg, "layers_per_block", 2)
+    if isinstance(layers, (list, tuple)):
+        if len(set(layers)) != 1:
+            raise NotImplementedError("per-block layers_per_block")
+        layers = layers[0]
+    heads = _tuple(cfg_get(cfg, "num_attention_heads"), nb)
+    depth = _tuple(cfg_get(cfg, "transformer_layers_per_block", 1), nb)
+    ctx = cfg_get(cfg, "cross_attention_dim")
+    if isinstance(ctx, (list, tuple)):
+        ctx = ctx[0]
+    frames = int(cfg_get(cfg, "num_frames", 25))
+    if frames > 32:
+        raise NotImplementedError("temporal attention kernel handles at most 32 frames")
+    for i in range(nb):
+        if boc[i] % heads[i] or boc[i] // heads[i] != 64:
+            raise NotImplementedError("SVD path needs attention head_dim 64")
+    spec = UNetSpec(
+        in_channels=cfg_get(cfg, "in_channels", 8), out_channels=cfg_get(cfg, "out_channels", 4),
+        block_out_channels=boc, temb_dim=boc[0] * 4, groups=cfg_get(cfg, "norm_num_groups", 32) or 32,
+        eps=1e-5, flip_sin_to_cos=True, freq_shift=0.0, cross_attention_dim=ctx,
+        addition_embed_type="time_ids",
+        addition_time_embed_dim=cfg_get(cfg, "addition_time_embed_dim", 256),
+        add_in_dim=cfg_get(cfg, "projection_class_embeddings_input_dim", 768), num_frames=frames)
+
+    def res(p, cin, cout, eps):
+        return ResnetSpec(p + ".spatial_res_block", cin, cout, eps, p + ".temporal_res_block",
+                          p + ".time_mixer.mix_factor")
+
+    def tf(prefix, dim, i):
+        return TransformerSpec(prefix, dim, heads[i], depth[i], ctx, True, temporal=True)
+
+    cout = boc[0]
+    for i, t in enumerate(down_types):
+        cin, cout = cout, boc[i]
+        p = f"down_blocks.{i}"
+        attn = t.startswith("CrossAttn")
+        eps = 1e-6 if attn else 1e-5
+        rs = [res(f"{p}.resnets.{j}", cin if j == 0 else cout, cout, eps) for j in range(layers)]
+        att = [tf(f"{p}.attentions.{j}", cout, i) if attn else None for j in range(layers)]
+        spec.down.append(BlockSpec(p, rs, att, f"{p}.downsamplers.0.conv" if i != nb - 1 else None, cout))
+    c = boc[-1]
+    spec.mid = BlockSpec("mid_block", [res("mid_block.resnets.0", c, c, 1e-5), res("mid_block.resnets.1", c, c, 1e-5)],
+                         [tf("mid_block.attentions.0", c, nb - 1)], None, c)
+    rboc = list(reversed(boc))
+    cout = rboc[0]
+    for i, t in enumerate(up_types):
+        cprev, cout = cout, rboc[i]
+        cin = rboc[min(i + 1, nb - 1)]
+        p = f"up_blocks.{i}"
+        rs = []
+        for j in range(layers + 1):
+            skip = cin if j == layers else cout
+            rin = cprev if j == 0 else cout
+            rs.append(res(f"{p}.resnets.{j}", rin + skip, cout, 1e-6))
+        att = [tf(f"{p}.attentions.{j}", cout, nb - 1 - i) if t.startswith("CrossAttn") else None
+               for j in range(layers + 1)]
+        spec.up.append(BlockSpec(p, rs, att, f"{p}.upsamplers.0.conv" if i != nb - 1 else None, cout))
+    return spec
+
+
 def param_shapes(spec: UNetSpec):
     """Ordered {diffusers parameter name: shape} of the architecture."""
     out = {}
@@ -214,8 +310,47 @@ def param_shapes(spec: UNetSpec):
         conv(r.prefix + ".conv2", r.cout, r.cout, 3)
         if r.has_shortcut:
             conv(r.prefix + ".conv_shortcut", r.cout, r.cin, 1)
+        if r.temporal_prefix:
+            t = r.temporal_prefix
+            norm(t + ".norm1", r.cout)
+            out[t + ".conv1.weight"] = (r.cout, r.cout, 3, 1, 1)
+            out[t + ".conv1.bias"] = (r.cout,)
+            lin(t + ".time_emb_proj", r.cout, spec.temb_dim)
+            norm(t + ".norm2", r.cout)
+            out[t + ".conv2.weight"] = (r.cout, r.cout, 3, 1, 1)
+            out[t + ".conv2.bias"] = (r.cout,)
+            out[r.mixer] = (1,)
+
+    def tblock(b, dim, ctx_dim, temporal):
+        if temporal:
+            norm(b + ".norm_in", dim)
+            lin(b + ".ff_in.net.0.proj", dim * 8, dim)
+            lin(b + ".ff_in.net.2", dim, dim * 4)
+        norm(b + ".norm1", dim)
+        for a, kd in (("attn1", dim), ("attn2", ctx_dim)):
+            lin(f"{b}.{a}.to_q", dim, dim, False)
+            lin(f"{b}.{a}.to_k", dim, kd, False)
+            lin(f"{b}.{a}.to_v", dim, kd, False)
+            lin(f"{b}.{a}.to_out.0", dim, dim)
+            if a == "attn1":
+                norm(b + ".norm2", dim)
+        norm(b + ".norm3", dim)
+        lin(b + ".ff.net.0.proj", dim * 8, dim)
+        lin(b + ".ff.net.2", dim, dim * 4)
 
     def transformer(t):
+        if t.temporal:
+            norm(t.prefix + ".norm", t.dim)
+            lin(t.prefix + ".proj_in", t.dim, t.dim)
+            for d in range(t.depth):
+                tblock(f"{t.prefix}.transformer_blocks.{d}", t.dim, t.ctx_dim, False)
+            for d in range(t.depth):
+                tblock(f"{t.prefix}.temporal_transformer_blocks.{d}", t.dim, t.ctx_dim, True)
+            lin(t.prefix + ".time_pos_embed.linear_1", t.dim * 4, t.dim)
+            lin(t.prefix + ".time_pos_embed.linear_2", t.dim, t.dim * 4)
+            out[t.prefix + ".time_mixer.mix_factor"] = (1,)
+            lin(t.prefix + ".proj_out", t.dim, t.dim)
+            return
         norm(t.prefix + ".norm", t.dim)
         if t.linear_proj:
             lin(t.prefix + ".proj_in", t.dim, t.dim)
@@ -242,7 +377,7 @@ def param_shapes(spec: UNetSpec):
     conv("conv_in", spec.block_out_channels[0], spec.in_channels, 3)
     lin("time_embedding.linear_1", spec.temb_dim, spec.block_out_channels[0])
     lin("time_embedding.linear_2", spec.temb_dim, spec.temb_dim)
-    if spec.addition_embed_type == "text_time":
+    if spec.addition_embed_type in ("text_time", "time_ids"):
         lin("add_embedding.linear_1", spec.temb_dim, spec.add_in_dim)
         lin("add_embedding.linear_2", spec.temb_dim, spec.temb_dim)
     for blk in spec.down + [spec.mid] + spec.up:
@@ -270,7 +405,9 @@ def random_state_dict(spec: UNetSpec, seed=0, dtype=torch.float16, device="cpu")
     sd = {}
     for name, shape in param_shapes(spec).items():
         is_norm = ".norm" in name or name.startswith("conv_norm_out")
-        if is_norm:
+        if name.endswith("mix_factor"):
+            t = torch.randn(shape, generator=g) * 1.5
+        elif is_norm:
             # random affine (not PyTorch's 1 / 0): a benchmark must not hide a dropped beta
             t = torch.randn(shape, generator=g) * 0.3 + (1.0 if name.endswith("weight") else 0.0)
         else:

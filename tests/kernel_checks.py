@@ -52,7 +52,7 @@ def _rand(*shape, dt=torch.float16, scale=1.0, seed=None):
 
 # ------------------------------------------------------------------------------------------
 def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, residual=True, seed=0,
-               fused_reduce=True, pair=None, cluster_k=False):
+               pair=None, persistent=False):
     lib = _lib.lib()
     a = _rand(M, K, dt=dt, seed=seed)
     w = _rand(N, K, dt=dt, scale=1 / math.sqrt(K))
@@ -60,18 +60,11 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     r = _rand(M, N, dt=dt) if residual else None
     out = torch.zeros(M, N, device=DEV, dtype=dt)
     ws = torch.empty(max(splits, 1) * M * N, device=DEV, dtype=torch.float32)
-    sync = torch.zeros(2048, device=DEV, dtype=torch.int32) if fused_reduce else None
     op = ops.gemm_op("gemm", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=ops.Mat(w), M=M, N=N, K=K,
                      dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits,
-                     split_sync=sync, cta_pair=pair, cluster_k=cluster_k)
-    if cluster_k:
-        assert op.keep[0].cluster_k == 1 and op.keep[0].splits == splits, (op.keep[0].cluster_k, op.keep[0].splits)
+                     cta_pair=pair, persistent=persistent)
+    assert op.keep[0].persistent == int(bool(persistent)), "persistent kernel was not selected"
     op.launch(_stream())
-    if fused_reduce and splits > 1 and not cluster_k:  # counters must re-arm themselves: run it twice
-        out.zero_()
-        op.launch(_stream())
-        torch.cuda.synchronize()
-        assert int(sync.abs().sum()) == 0, "split-K counters did not re-arm"
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t()
     if bias:
@@ -81,7 +74,7 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     return rel_err(out, ref)
 
 
-def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1, cluster_k=False):
+def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1, persistent=False):
     lib = _lib.lib()
     x = _rand(M, K, dt=dt, seed=seed)
     w = _rand(2 * inner, K, dt=dt, scale=1 / math.sqrt(K))
@@ -93,8 +86,8 @@ def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1, cl
     op = ops.gemm_op("geglu", lib, a=ops.a_matrix(x.data_ptr(), M, K, K), b=ops.Mat(wp), M=M, N=Np, K=K,
                      dt=dt,
                      out=out, ldo=inner, bias=bp, epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws,
-                     splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32),
-                     cluster_k=cluster_k)
+                     splits=splits, persistent=persistent)
+    assert op.keep[0].persistent == int(bool(persistent))
     op.launch(_stream())
     torch.cuda.synchronize()
     # reference semantics: h * gelu(gate), hidden first (sfast passes/__init__.py:643-648)
@@ -104,7 +97,7 @@ def check_geglu(M=256, K=320, inner=1280, dt=torch.float16, splits=1, seed=1, cl
 
 
 def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, splits=None,
-               rowbias=True, residual=True, pitch_extra=0, seed=2, pair=None, cluster_k=False):
+               rowbias=True, residual=True, pitch_extra=0, seed=2, pair=None, persistent=False):
     lib = _lib.lib()
     torch.manual_seed(seed)
     ld = cin + pitch_extra
@@ -124,9 +117,9 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
     op = ops.gemm_op("conv", lib, a=adesc, b=ops.Mat(wp),
                      M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb,
                      rows_per_img=ho * wo, ld_rowbias=cout, residual=r, ldr=cout, ws=ws,
-                     splits=splits, split_sync=torch.zeros(2048, device=DEV, dtype=torch.int32),
-                     cta_pair=pair, cluster_k=cluster_k,
+                     splits=splits, cta_pair=pair, persistent=persistent,
                      conv=dict(n=n, h=ho, w=wo, cin=cin, stride=stride, box_n=box_n, box_h=box_h, box_w=box_w))
+    assert op.keep[0].persistent == int(bool(persistent))
     op.launch(_stream())
     torch.cuda.synchronize()
     xin = x.tensor().permute(0, 3, 1, 2).float()
@@ -140,7 +133,7 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
 
 
 def check_upconv(n=2, h=16, w=16, cin=640, cout=640, dt=torch.float16, splits=None, pair=None,
-                 out_extra=0, seed=23):
+                 out_extra=0, seed=23, persistent=False):
     """nearest-2x upsample + conv3x3 as the 4-phase 2x2 implicit GEMM on the low-res image vs
     F.conv2d(F.interpolate(x, 2, 'nearest')) in fp32 (weights as packed: sums rounded to 16 bit)."""
     lib = _lib.lib()
@@ -156,7 +149,7 @@ def check_upconv(n=2, h=16, w=16, cin=640, cout=640, dt=torch.float16, splits=No
     ws = torch.empty(32 * M * cout, device=DEV, dtype=torch.float32) if splits != 1 else None
     op = ops.gemm_op("upconv", lib, a=adesc, b=ops.Mat(ops.pack_upconv(wt, dt)), M=M, N=cout, K=4 * cin,
                      dt=dt, out=out.data_ptr(), ldo=ld, bias=b, ws=ws, splits=splits, cta_pair=pair,
-                     cluster_k=False,
+                     persistent=persistent,
                      conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=box_n, box_h=box_h, box_w=box_w, up=True))
     op.launch(_stream())
     torch.cuda.synchronize()
@@ -202,7 +195,7 @@ def check_attention(B=2, H=8, S=1024, Skv=None, D=40, dt=torch.float16, seed=3, 
     return rel_err(out, ref)
 
 
-def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=4):
+def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=4, persistent=False):
     """QKV projection GEMM whose epilogue writes the attention layouts directly."""
     lib = _lib.lib()
     C = H * D
@@ -219,7 +212,8 @@ def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=
                      K=Kdim, dt=dt, epi=ops.EPI_QKV,
                      qkv=dict(q=q, k=k, vt=vt, heads=H, head_dim=D, which_base=which_base,
                               seq=seq, q_pitch=q_pitch, q_rows=S, k_rows=seq, vt_rows=dv,
-                              vt_pitch=vt_pitch))
+                              vt_pitch=vt_pitch), persistent=persistent)
+    assert op.keep[0].persistent == int(bool(persistent))
     op.launch(_stream())
     torch.cuda.synchronize()
     y = (x.float() @ w.float().t()).view(B, seq, -1, H, D)  # [B, seq, which, H, D]
@@ -298,7 +292,7 @@ def check_gn_finish(n=2, h=16, w=16, cin=1280, cout=1280, extra=0, splits=4, row
     ws = torch.empty(splits * M * cout, device=DEV, dtype=torch.float32)
     conv = ops.gemm_op("conv", lib, a=adesc, b=ops.Mat(ops.pack_conv3x3(wt, dt)), M=M, N=cout, K=9 * cin,
                        dt=dt, out=cat.data_ptr(), ldo=C, bias=b, rowbias=rb, rows_per_img=h * w,
-                       ld_rowbias=cout, residual=r, ldr=cout, ws=ws, splits=splits, cluster_k=False,
+                       ld_rowbias=cout, residual=r, ldr=cout, ws=ws, splits=splits, persistent=False,
                        conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=box_n, box_h=box_h, box_w=box_w))
     assert conv.keep[0].splits == splits
     conv.keep[0].defer_finish = 1
@@ -437,7 +431,7 @@ def check_upsample(n=2, h=16, w=16, c=1280, dt=torch.float16):
 
 
 def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=1, splits_c=1, seed=12,
-                  cluster_k=False, row_offset=0.5, outlier=False):
+                  persistent=False, row_offset=0.5, outlier=False):
     """LayerNorm folded around two GEMMs: the producer accumulates per-row (sum, sum of squares)
     in its epilogue, the consumer runs on the RAW activation with gamma-scaled weights and
     corrects with mean / rstd in its epilogue.  Reference: F.layer_norm then the linear / GEGLU."""
@@ -452,10 +446,9 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
     x = torch.zeros(M, C, device=DEV, dtype=dt)
     stats = torch.zeros(M, 2, device=DEV)
     ws = torch.empty(16 * M * max(N, C) * 2, device=DEV, dtype=torch.float32)
-    sync = torch.zeros(2048, device=DEV, dtype=torch.int32)
     ops.gemm_op("producer", lib, a=ops.a_matrix(a.data_ptr(), M, C, C), b=ops.Mat(w0),
                 M=M, N=C, K=C, dt=dt, out=x, ldo=C, residual=res, ldr=C, ws=ws, splits=splits_p,
-                split_sync=sync, rowstats_out=stats, cluster_k=cluster_k).launch(_stream())
+                rowstats_out=stats, persistent=persistent).launch(_stream())
     gamma = torch.randn(C, device=DEV) * 0.5 + 1.0
     beta = torch.randn(C, device=DEV) * 0.3
     if mode == "geglu":
@@ -467,8 +460,8 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         out = torch.zeros(M, inner, device=DEV, dtype=dt)
         ops.gemm_op("consumer", lib, a=ops.a_matrix(x.data_ptr(), M, C, C),
                     b=ops.Mat(wt), M=M, N=wt.shape[0], K=C, dt=dt, out=out, ldo=inner, bias=bp,
-                    epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws, splits=splits_c, split_sync=sync,
-                    cluster_k=cluster_k, ln=dict(rowstats=stats, colsum=cs, eps=1e-5, dim=C)).launch(_stream())
+                    epi=ops.EPI_GEGLU, geglu_n_out=inner, ws=ws, splits=splits_c, persistent=persistent,
+                    ln=dict(rowstats=stats, colsum=cs, eps=1e-5, dim=C)).launch(_stream())
     else:
         w = _rand(N, C, dt=dt, scale=1 / math.sqrt(C))
         b = torch.randn(N, device=DEV) * 0.1
@@ -476,7 +469,7 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         out = torch.zeros(M, N, device=DEV, dtype=dt)
         ops.gemm_op("consumer", lib, a=ops.a_matrix(x.data_ptr(), M, C, C),
                     b=ops.Mat(wp.contiguous()), M=M, N=N, K=C, dt=dt, out=out, ldo=N, bias=bias,
-                    ws=ws, splits=splits_c, split_sync=sync, cluster_k=cluster_k,
+                    ws=ws, splits=splits_c, persistent=persistent,
                     ln=dict(rowstats=stats, colsum=colsum, eps=1e-5, dim=C)).launch(_stream())
     torch.cuda.synchronize()
     xr = (a.float() @ w0.float().t() + res.float())
@@ -493,92 +486,114 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
 
 
 
-def check_gn_epilogue(n=2, hw=1024, c1=640, c2=320, k=320, dt=torch.float16, splits=1, seed=14):
-    """GroupNorm statistics accumulated by the PRODUCER GEMMs' epilogues (two producers writing the
-    two channel slices of one concat buffer), then the apply-only kernel; reference: F.group_norm
-    of the stored concat tensor."""
+
+# ------------------------------------------------------------------------------------------
+# SVD temporal path
+def check_temporal_attention(B=2, F_=25, S=64, H=5, dt=torch.float16, seed=31):
+    """Self-attention across frames on the fused QKV projection in the SPATIAL row order, against
+    diffusers' formulation: reshape to [B*S, F, C], scaled_dot_product_attention, reshape back."""
+    lib = _lib.lib()
+    D, C_ = 64, H * 64
+    torch.manual_seed(seed)
+    rows = B * F_ * S
+    qkv = _rand(rows, 3 * C_, dt=dt)
+    out = torch.zeros(rows, C_, device=DEV, dtype=dt)
+    p = _lib.TemporalAttnParams()
+    p.qkv, p.out = qkv.data_ptr(), out.data_ptr()
+    p.batch, p.frames, p.seq, p.heads, p.head_dim = B, F_, S, H, D
+    p.ld_qkv, p.ld_out, p.dtype, p.scale = 3 * C_, C_, ops.dtype_code(dt), D ** -0.5
+    import ctypes
+    _lib.check(lib.sfb_temporal_attention(ctypes.byref(p), _stream()))
+    torch.cuda.synchronize()
+    x = qkv.float().view(B, F_, S, 3, H, D).permute(3, 0, 2, 4, 1, 5)  # [3, B, S, H, F, D]
+    ref = F.scaled_dot_product_attention(x[0], x[1], x[2])             # [B, S, H, F, D]
+    ref = ref.permute(0, 3, 1, 2, 4).reshape(rows, C_)
+    return rel_err(out, ref)
+
+
+def check_row_ops(B=2, F_=6, S=48, c=320, dt=torch.float16, seed=32):
+    """sfb_row_broadcast_add (both index modes) and sfb_alpha_blend, with their row statistics."""
+    import ctypes
     lib = _lib.lib()
     torch.manual_seed(seed)
-    M, C = n * hw, c1 + c2
-    buf = torch.zeros(M, C, device=DEV, dtype=dt)
-    stats = torch.zeros(8 * n * 32 * 2 + 4, device=DEV)
-    ws = torch.empty(8 * M * max(c1, c2), device=DEV, dtype=torch.float32)
-    off = 0
-    for ci in (c1, c2):
-        a = _rand(M, k, dt=dt)
-        w = _rand(ci, k, dt=dt, scale=1.5 / math.sqrt(k))
-        b = torch.randn(ci, device=DEV)
-        op = ops.gemm_op("prod", lib, a=ops.a_matrix(a.data_ptr(), M, k, k), b=ops.Mat(w), M=M, N=ci, K=k,
-                         dt=dt, out=buf.data_ptr() + off * 2, ldo=C, bias=b, ws=ws, splits=splits, cluster_k=False)
-        p = op.keep[0]
-        p.gn_stats[0] = stats.data_ptr()
-        p.gn_cpg[0], p.gn_choff[0] = C // 32, off
-        p.gn_groups, p.gn_rows_per_img, p.gn_shard_stride = 32, hw, n * 32 * 2
-        op.launch(_stream())
-        off += ci
-    x = Act(buf, n, 1, hw, C)
-    y = torch.zeros(M, C, device=DEV, dtype=dt)
-    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
-    gops = ops.gn_ops("gn", lib, x=x, y=Act(y, n, 1, hw, C), gamma=gamma, beta=beta, stats=stats, groups=32,
-                      eps=1e-5, silu=True, dt=dt, stats_ready=True)
-    assert len(gops) == 1
-    gops[0].launch(_stream())
-    torch.cuda.synchronize()
-    xin = buf.float().view(n, hw, C).permute(0, 2, 1)
-    ref = F.silu(F.group_norm(xin, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(M, C)
-    return rel_err(y, ref)
+    rows = B * F_ * S
+    x = _rand(rows, c, dt=dt)
+    errs = []
 
-
-def diag_gemm(dt=torch.float16):
-    """Informational: one-hot probes that reveal row / K permutations if a descriptor or swizzle
-    is wrong.  Prints the observed k -> k' and m -> m' maps for a single 128 x 160 x 64 tile."""
-    lib = _lib.lib()
-    M, N, K = 128, 160, 64
-    torch.manual_seed(11)
-    w = _rand(N, K, dt=dt)
-    info = {}
-    kmap = {}
-    for k0 in (0, 1, 7, 8, 15, 16, 31, 32, 48, 63):
-        a = torch.zeros(M, K, device=DEV, dtype=dt)
-        a[:, k0] = 1
-        out = torch.zeros(M, N, device=DEV, dtype=dt)
-        ops.gemm_op("diag", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
-                    b_map=ops.Mat(w).map, M=M, N=N, K=K, dt=dt,
-                    out=out, ldo=N).launch(_stream())
+    def run(fn, **kw):
+        p = _lib.RowOpParams()
+        y = torch.zeros(rows, c, device=DEV, dtype=dt)
+        st = torch.full((rows, 2), 7.0, device=DEV)
+        p.x, p.y, p.rowstats_out = x.data_ptr(), y.data_ptr(), st.data_ptr()
+        p.rows, p.c, p.ldx, p.ldy, p.dtype = rows, c, c, c, ops.dtype_code(dt)
+        p.frames, p.seq, p.batch = F_, S, B
+        for k, v in kw.items():
+            setattr(p, k, v)
+        _lib.check(fn(ctypes.byref(p), _stream()))
         torch.cuda.synchronize()
-        d = (out[0].float()[:, None] - w.float()).abs().sum(0)  # [K]
-        kmap[k0] = (int(d.argmin()), round(float(d.min()), 3))
-    info["k_map(row0)"] = kmap
-    # row map: A[m, :] = onehot(m % 64) * (1 + m // 64) -> out[m, n] = W[n, m % 64] * (1 + m//64)
-    a = torch.zeros(M, K, device=DEV, dtype=dt)
-    for m in range(M):
-        a[m, m % 64] = 1 + m // 64
-    out = torch.zeros(M, N, device=DEV, dtype=dt)
-    ops.gemm_op("diag", lib, a_map=ops.matrix_map(a.data_ptr(), M, K, K, 128),
-                b_map=ops.Mat(w).map, M=M, N=N, K=K, dt=dt,
-                out=out, ldo=N).launch(_stream())
+        return y, st
+
+    m = torch.arange(rows, device=DEV)
+    # frame position embedding: vec[(m / S) % F]
+    vec = _rand(F_, c, dt=dt)
+    y, st = run(lib.sfb_row_broadcast_add, vec=vec.data_ptr(), ldv=c, mode=_lib.ROW_IDX_DIV_MOD, div=S, mod=F_)
+    ref = x.float() + vec.float()[(m // S) % F_]
+    errs.append(rel_err(y, ref))
+    errs.append(rel_err(st[:, 0], y.float().sum(-1)) + rel_err(st[:, 1], (y.float() ** 2).sum(-1)))
+    # per image: vec[(m / S) % (B * F)]
+    vec = _rand(B * F_, c, dt=dt)
+    y, _ = run(lib.sfb_row_broadcast_add, vec=vec.data_ptr(), ldv=c, mode=_lib.ROW_IDX_DIV_MOD, div=S, mod=B * F_)
+    errs.append(rel_err(y, x.float() + vec.float()[m // S]))
+    # temporal context (diffusers layout quirk): sequence j = b * S + p reads video j % B, first frame
+    y, _ = run(lib.sfb_row_broadcast_add, vec=vec.data_ptr(), ldv=c, mode=_lib.ROW_IDX_TEMPORAL_CTX)
+    b_, p_ = m // (F_ * S), m % S
+    errs.append(rel_err(y, x.float() + vec.float()[((b_ * S + p_) % B) * F_]))
+    # AlphaBlender
+    x2 = _rand(rows, c, dt=dt)
+    mix = torch.tensor([0.37], device=DEV)
+    y, st = run(lib.sfb_alpha_blend, x2=x2.data_ptr(), ldx2=c, mix_factor=mix.data_ptr())
+    al = torch.sigmoid(mix)
+    errs.append(rel_err(y, al * x.float() + (1 - al) * x2.float()))
+    errs.append(rel_err(st[:, 0], y.float().sum(-1)))
+    return max(errs)
+
+
+def check_conv_t(B=2, F_=25, h=8, w=16, cin=320, cout=320, dt=torch.float16, rowbias=True, residual=True,
+                 persistent=False, seed=33):
+    """Conv3d (3,1,1) over the frame axis as the SFB_A_CONV3X1 implicit GEMM vs F.conv3d."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    S = h * w
+    x = _rand(B * F_, h, w, cin, dt=dt)
+    wt = _rand(cout, cin, 3, 1, 1, dt=dt, scale=1 / math.sqrt(3 * cin))
+    b = torch.randn(cout, device=DEV)
+    M = B * F_ * S
+    rb = torch.randn(B, cout, device=DEV) if rowbias else None
+    r = _rand(M, cout, dt=dt) if residual else None
+    out = torch.zeros(M, cout, device=DEV, dtype=dt)
+    wp = wt[:, :, :, 0, 0].permute(0, 2, 1).reshape(cout, 3 * cin).contiguous()
+    bn, bh, bw = ops.conv_tile_box(F_, S)
+    op = ops.gemm_op("conv_t", lib, a=ops.a_conv(x.data_ptr(), B, F_, S, cin, cin, bn, bh, bw, 1), b=ops.Mat(wp),
+                     M=M, N=cout, K=3 * cin, dt=dt, out=out, ldo=cout, bias=b, rowbias=rb, rows_per_img=F_ * S,
+                     ld_rowbias=cout, residual=r, ldr=cout, splits=1, persistent=persistent,
+                     conv=dict(n=B, h=F_, w=S, cin=cin, stride=1, box_n=bn, box_h=bh, box_w=bw, temporal=True))
+    op.launch(_stream())
     torch.cuda.synchronize()
-    ref = (a.float() @ w.float().t())
-    bad_rows = ((out.float() - ref).abs().max(1).values > 1e-2).nonzero().flatten().tolist()
-    bad_cols = ((out.float() - ref).abs().max(0).values > 1e-2).nonzero().flatten().tolist()
-    info["bad_rows"] = bad_rows[:40]
-    info["n_bad_rows"] = len(bad_rows)
-    info["bad_cols"] = bad_cols[:40]
-    info["n_bad_cols"] = len(bad_cols)
-    info["out00"] = [round(float(v), 3) for v in out[0, :6]]
-    info["ref00"] = [round(float(v), 3) for v in ref[0, :6]]
-    print(json.dumps({"diag_gemm": info}), flush=True)
-    return 0.0
+    xin = x.float().view(B, F_, h, w, cin).permute(0, 4, 1, 2, 3)  # [B, C, F, H, W]
+    ref = F.conv3d(xin, wt.float(), b, padding=(1, 0, 0))
+    if rowbias:
+        ref = ref + rb[:, :, None, None, None]
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(M, cout)
+    if residual:
+        ref = ref + r.float()
+    return rel_err(out, ref)
 
 
-# name -> (callable, tolerance)
 CHECKS = {
-    "diag_gemm": (diag_gemm, 1.0),
     "gemm_small": (lambda: check_gemm(300, 320, 320), 2e-3),
     "gemm_k64": (lambda: check_gemm(128, 160, 64, bias=False, residual=False), 2e-3),
     "gemm_big": (lambda: check_gemm(8192, 1280, 1280), 2e-3),
     "gemm_splitk": (lambda: check_gemm(256, 1280, 5120, splits=8), 2e-3),
-    "gemm_splitk_finish_kernel": (lambda: check_gemm(256, 1280, 5120, splits=8, fused_reduce=False), 2e-3),
     "gemm_splitk_18": (lambda: check_gemm(128, 1280, 11520, splits=18), 2e-3),
     "group_norm_960_64_barrier_kernel": (lambda: check_group_norm(2, 960, 64, 64), 1e-2),
     "group_norm_320_64_b1": (lambda: check_group_norm(1, 320, 64, 64), 1e-2),
@@ -597,25 +612,51 @@ CHECKS = {
     "gn_finish_plain": (lambda: check_gn_finish(1, 16, 16, 640, 1280, splits=3, rowbias=False, residual=False,
                                                 silu=False), 3e-3),
     "gn_finish_bf16": (lambda: check_gn_finish(2, 16, 16, 1280, 1280, splits=4, dt=torch.bfloat16), 2e-2),
-    "gemm_fused_s2": (lambda: check_gemm(512, 1280, 1280, splits=2), 2e-3),
-    "gemm_fused_s4_pair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=True), 2e-3),
-    "gemm_fused_s4_nopair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=False), 2e-3),
-    "gemm_fused_s3_ragged": (lambda: check_gemm(300, 480, 2560, splits=3), 2e-3),
-    "gemm_fused_s2_bf16": (lambda: check_gemm(512, 640, 1280, splits=2, dt=torch.bfloat16), 1e-2),
-    "gemm_ck2_pair": (lambda: check_gemm(512, 1280, 1280, splits=2, pair=True, cluster_k=True), 2e-3),
-    "gemm_ck8": (lambda: check_gemm(256, 1280, 5120, splits=8, pair=False, cluster_k=True), 2e-3),
-    "gemm_ck4_pair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=True, cluster_k=True), 2e-3),
-    "gemm_ck3_ragged": (lambda: check_gemm(300, 480, 2560, splits=3, cluster_k=True), 2e-3),
-    "gemm_ck2_bf16": (lambda: check_gemm(512, 640, 1280, splits=2, dt=torch.bfloat16, cluster_k=True), 1e-2),
-    "gemm_ck16_nonportable": (lambda: check_gemm(128, 1280, 11520, splits=16, cluster_k=True), 2e-3),
-    "gemm_ck8_pair_nonportable": (lambda: check_gemm(256, 1280, 5120, splits=8, pair=True, cluster_k=True), 2e-3),
-    "geglu_ck4": (lambda: check_geglu(128, 1280, 5120, splits=4, cluster_k=True), 2e-2),
-    "conv_ck_16": (lambda: check_conv(2, 16, 16, 1280, 1280, cluster_k=True), 2e-3),
-    "conv_ck_8": (lambda: check_conv(2, 8, 8, 1280, 1280, cluster_k=True), 2e-3),
-    "conv_ck_stride2_16": (lambda: check_conv(2, 16, 16, 1280, 1280, stride=2, residual=False,
-                                              rowbias=False, cluster_k=True), 2e-3),
-    "ln_fold_ck": (lambda: check_ln_fold(256, 1280, 1280, splits_p=2, splits_c=2, cluster_k=True), 5e-3),
-    "ln_fold_geglu_ck": (lambda: check_ln_fold(128, 1280, 5120, mode="geglu", splits_c=2, cluster_k=True), 2e-2),
+    "gemm_s2": (lambda: check_gemm(512, 1280, 1280, splits=2), 2e-3),
+    "gemm_s4_pair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=True), 2e-3),
+    "gemm_s4_nopair": (lambda: check_gemm(256, 1280, 5120, splits=4, pair=False), 2e-3),
+    "gemm_s3_ragged": (lambda: check_gemm(300, 480, 2560, splits=3), 2e-3),
+    "gemm_s2_bf16": (lambda: check_gemm(512, 640, 1280, splits=2, dt=torch.bfloat16), 1e-2),
+    # persistent 256 x 320 pair kernel (forced, whatever the size policy would pick): more tiles than
+    # SM pairs (several tiles per CTA: accumulator rotation, phase bits), ragged M / N, odd number of
+    # 160-column tiles (single-half tiles), every epilogue and A mode
+    "persist_gemm_big": (lambda: check_gemm(8192, 1280, 1280, persistent=True), 2e-3),
+    "persist_gemm_many_tiles": (lambda: check_gemm(16384 + 256, 1920, 320, persistent=True), 2e-3),
+    "persist_gemm_one_half": (lambda: check_gemm(4096, 160, 640, persistent=True), 2e-3),
+    "persist_gemm_odd_halves": (lambda: check_gemm(2048, 480, 320, persistent=True), 2e-3),
+    "persist_gemm_ragged": (lambda: check_gemm(400, 488, 320, persistent=True), 2e-3),
+    "persist_gemm_k64_nobias": (lambda: check_gemm(8192, 320, 64, bias=False, residual=False, persistent=True), 2e-3),
+    "persist_gemm_bf16": (lambda: check_gemm(4096, 640, 640, dt=torch.bfloat16, persistent=True), 1e-2),
+    "persist_geglu": (lambda: check_geglu(8192, 320, 1280, persistent=True), 2e-2),
+    "persist_geglu_ragged": (lambda: check_geglu(500, 64, 280, persistent=True), 2e-2),
+    "persist_geglu_bf16": (lambda: check_geglu(2048, 640, 2560, dt=torch.bfloat16, persistent=True), 2e-2),
+    "persist_conv_64": (lambda: check_conv(4, 64, 64, 320, 320, splits=1, persistent=True), 2e-3),
+    "persist_conv_32_b8": (lambda: check_conv(8, 32, 32, 640, 640, splits=1, persistent=True), 2e-3),
+    "persist_conv_8_multi_image": (lambda: check_conv(16, 8, 8, 1280, 1280, splits=1, persistent=True), 2e-3),
+    "persist_conv_4_tiny": (lambda: check_conv(64, 4, 4, 256, 256, splits=1, persistent=True), 2e-3),
+    "persist_conv_concat_pitch": (lambda: check_conv(2, 32, 32, 640, 320, pitch_extra=320, splits=1, persistent=True), 2e-3),
+    "persist_conv_patch_96": (lambda: check_conv(2, 96, 96, 320, 320, splits=1, persistent=True), 2e-3),
+    "persist_conv_stride2": (lambda: check_conv(2, 64, 64, 320, 320, stride=2, residual=False, rowbias=False,
+                                                splits=1, persistent=True), 2e-3),
+    "persist_upconv_32": (lambda: check_upconv(2, 32, 32, 640, 640, splits=1, persistent=True), 3e-3),
+    "persist_upconv_16_pitch": (lambda: check_upconv(2, 16, 16, 320, 320, out_extra=320, splits=1, persistent=True), 3e-3),
+    "persist_qkv_scatter": (lambda: check_qkv_scatter(2, 8, 1024, 40, persistent=True), 2e-3),
+    "persist_qkv_scatter_d80": (lambda: check_qkv_scatter(2, 8, 512, 80, persistent=True), 2e-3),
+    "persist_kv_scatter_cross": (lambda: check_qkv_scatter(6, 8, 256, 40, cross_kv=77, persistent=True), 2e-3),
+    "persist_ln_fold": (lambda: check_ln_fold(2048, 320, 960, persistent=True), 5e-3),
+    "persist_ln_fold_1280": (lambda: check_ln_fold(1024, 1280, 1280, persistent=True), 5e-3),
+    "persist_ln_fold_geglu": (lambda: check_ln_fold(1024, 640, 2560, mode="geglu", persistent=True), 2e-2),
+    # SVD temporal path
+    "temporal_attn_25": (lambda: check_temporal_attention(2, 25, 64, 5), 5e-3),
+    "temporal_attn_6_d64x4": (lambda: check_temporal_attention(1, 6, 37, 4), 5e-3),
+    "temporal_attn_32_bf16": (lambda: check_temporal_attention(2, 32, 16, 10, dt=torch.bfloat16), 2e-2),
+    "row_ops": (lambda: check_row_ops(), 2e-3),
+    "row_ops_1280_bf16": (lambda: check_row_ops(3, 5, 20, 1280, dt=torch.bfloat16), 1e-2),
+    "conv_t_25": (lambda: check_conv_t(2, 25, 8, 16, 320, 320), 2e-3),
+    "conv_t_small_frames": (lambda: check_conv_t(2, 6, 4, 4, 256, 256), 2e-3),
+    "conv_t_patch_9x16": (lambda: check_conv_t(1, 25, 9, 16, 1280, 1280, rowbias=False), 2e-3),
+    "conv_t_big": (lambda: check_conv_t(2, 25, 36, 64, 640, 640), 2e-3),
+    "conv_t_persistent": (lambda: check_conv_t(2, 25, 16, 32, 320, 320, persistent=True), 2e-3),
     "gemm_pair": (lambda: check_gemm(512, 320, 640, pair=True), 2e-3),
     "gemm_pair_big": (lambda: check_gemm(8192, 1280, 1280, pair=True), 2e-3),
     "gemm_pair_ragged": (lambda: check_gemm(300, 480, 320, pair=True), 2e-3),
@@ -625,17 +666,13 @@ CHECKS = {
     "conv_pair_16_splitk": (lambda: check_conv(2, 16, 16, 1280, 1280, pair=True), 2e-3),
     "conv_pair_8": (lambda: check_conv(4, 8, 8, 1280, 1280, pair=True), 2e-3),
     "conv_pair_stride2": (lambda: check_conv(2, 64, 64, 320, 320, stride=2, residual=False, rowbias=False, pair=True), 2e-3),
-    "gemm_cluster_2x4": (lambda: check_gemm(1024, 640, 640), 2e-3),
-    "gemm_cluster_1x4_ragged": (lambda: check_gemm(500, 480, 320), 2e-3),
-    "gemm_cluster_2x2_splitk": (lambda: check_gemm(256, 640, 2560, splits=4), 2e-3),
+    "gemm_1024_640": (lambda: check_gemm(1024, 640, 640), 2e-3),
+    "gemm_500_480": (lambda: check_gemm(500, 480, 320), 2e-3),
+    "gemm_256_640_splitk": (lambda: check_gemm(256, 640, 2560, splits=4), 2e-3),
     "gemm_bf16": (lambda: check_gemm(300, 320, 320, dt=torch.bfloat16), 1e-2),
     "geglu": (lambda: check_geglu(256, 320, 1280), 2e-2),
     "geglu_ragged": (lambda: check_geglu(100, 64, 256), 2e-2),
     "geglu_splitk": (lambda: check_geglu(128, 1280, 5120, splits=4), 2e-2),
-    "gn_epilogue": (lambda: check_gn_epilogue(), 1e-2),
-    "gn_epilogue_8x8": (lambda: check_gn_epilogue(4, 64, 1280, 1280, 640), 1e-2),
-    "gn_epilogue_4x4": (lambda: check_gn_epilogue(8, 16, 128, 128, 64), 1e-2),
-    "gn_epilogue_splitk": (lambda: check_gn_epilogue(2, 256, 1280, 640, 1280, splits=2), 1e-2),
     "ln_fold": (lambda: check_ln_fold(300, 320, 960), 5e-3),
     "ln_fold_1280": (lambda: check_ln_fold(512, 1280, 1280), 5e-3),
     "ln_fold_geglu": (lambda: check_ln_fold(300, 320, 1280, mode="geglu"), 2e-2),

@@ -142,16 +142,15 @@ def test_sdxl_plan_builds():
 
 
 def test_split_k_policy():
-    # cost model: ~4.5 us per launch + 0.34 us per K block; fused reduction cheap up to 4 splits
+    # cost model: ~4.5 us per launch + 0.34 us per K block + a ~10 us reduction pass
     assert ops.choose_splits(64, 2, 45) == 1       # 64^2 resnet conv: 128 tiles, no split
     assert ops.choose_splits(16, 4, 10) == 1       # 32^2 linear, K = 640: too short to split
     assert ops.choose_splits(16, 4, 90) == 2       # 32^2 conv: 64 tiles -> 2 splits
     assert ops.choose_splits(4, 8, 20) == 1        # 16^2 linear K = 1280: a reduction costs more
-    assert ops.choose_splits(4, 8, 180) == 4       # 16^2 conv K = 11520: fused 4-way
+    assert ops.choose_splits(4, 8, 180) == 4       # 16^2 conv K = 11520: 4-way
     s = ops.choose_splits(1, 8, 180)               # 8^2 conv: weight-bandwidth-bound, fill the SMs
-    assert 8 <= s <= 18 and 8 * s <= ops.NUM_SMS
+    assert 8 <= s <= 18 and 8 * s <= ops.num_sms()
     assert ops.choose_splits(1, 1, 5) == 1
-    assert ops.choose_splits(4, 8, 180, fused=False) >= 2
 
 
 def test_conv_tile_box():
@@ -231,7 +230,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(h, name), name
     lib = _lib.lib()
-    assert lib.sfb_abi_version() == 1
+    assert lib.sfb_abi_version() == 2
     # argument validation works without a GPU and never falls back silently
     p = _lib.GemmParams()
     assert lib.sfb_gemm(ctypes.byref(p), None) < 0
@@ -322,6 +321,16 @@ def _validate_plan_on_cpu(plan):
             p = _clone(op.keep[0])
             _nonnull(p, ["tmap_q", "tmap_k", "tmap_vt", "out"])
             rc = lib.sfb_attention(ctypes.byref(p), None)
+        elif name == "sfb_temporal_attention":
+            p = _clone(op.keep[0])
+            _nonnull(p, ["qkv", "out"])
+            rc = lib.sfb_temporal_attention(ctypes.byref(p), None)
+        elif name in ("sfb_row_broadcast_add", "sfb_alpha_blend"):
+            p = _clone(op.keep[0])
+            _nonnull(p, ["x", "y", "vec" if name == "sfb_row_broadcast_add" else "x2"])
+            if name == "sfb_alpha_blend":
+                _nonnull(p, ["mix_factor"])
+            rc = getattr(lib, name)(ctypes.byref(p), None)
         else:
             continue
         assert rc != 0, f"{op.name}: launched without a GPU?"
@@ -407,3 +416,43 @@ def test_controlnet_plan_adds_one_launch_and_thirteen_static_inputs():
     assert len(ctl.ctrl_in) == 13 and not base.ctrl_in
     shapes = [tuple(t.shape) for t in ctl.ctrl_in]
     assert shapes[0] == (2, 320, 64, 64) and shapes[-2] == (2, 1280, 8, 8) and shapes[-1] == (2, 1280, 8, 8)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box without a GPU: launches must fail")
+@pytest.mark.parametrize("tiny,videos,h,w", [(True, 2, 16, 16), (True, 3, 24, 40), (False, 2, 72, 128), (False, 1, 40, 64)])
+def test_every_launch_of_an_svd_plan_passes_host_validation(tiny, videos, h, w):
+    from oracle import svd_oracle as so
+    from sfast_b200.svd_plan import SVDPlan
+    from sfast_b200.plan import PackedWeights
+    from sfast_b200.unet_spec import param_shapes, spec_from_config
+    spec = spec_from_config(so.svd_tiny_config() if tiny else so.svd_xt_config())
+    sd = {k: torch.empty(v, dtype=torch.float16, device="meta") for k, v in param_shapes(spec).items()}
+    plan = SVDPlan(PackedWeights(spec, sd, torch.float16, "meta", dry=True), videos, h, w)
+    n = _validate_plan_on_cpu(plan)
+    assert n["sfb_gemm"] > 100 and n["sfb_temporal_attention"] == 16 and n["sfb_row_broadcast_add"] == 48
+
+
+def test_svd_plan_builds_and_counts_its_temporal_ops():
+    import torch
+    from oracle import svd_oracle as so
+    from sfast_b200.svd_plan import SVDPlan
+    from sfast_b200.plan import PackedWeights
+    from sfast_b200.unet_spec import param_shapes, spec_from_config
+    cfg = so.svd_xt_config()
+    spec = spec_from_config(cfg)
+    assert spec.temporal and spec.num_frames == 25
+    shapes = param_shapes(spec)
+    assert sum(int(torch.Size(s).numel()) for s in shapes.values()) == 1_524_623_082
+    sd = {k: torch.empty(v, dtype=torch.float16, device="meta") for k, v in shapes.items()}
+    pw = PackedWeights(spec, sd, torch.float16, "meta", dry=True)
+    plan = SVDPlan(pw, 2, 72, 128)
+    names = [op.fn.name for op in plan.all_ops() if op.fn is not None]
+    # 16 spatio-temporal transformers: one temporal attention, 3 broadcast adds (spatial ctx, frame
+    # position, temporal ctx) and one AlphaBlender each; 22 res blocks: 2 temporal convs each
+    assert names.count("sfb_temporal_attention") == 16
+    assert names.count("sfb_row_broadcast_add") == 48 and names.count("sfb_alpha_blend") == 16
+    gemms = [op.keep[0] for op in plan.all_ops() if op.fn is not None and op.fn.name == "sfb_gemm"]
+    assert sum(1 for g in gemms if g.a_mode == _lib.A_CONV3X1) == 44
+    assert names.count("sfb_attention") == 16          # spatial self-attention only: cross-attention is an add
+    assert plan.flops() / 1e12 > 50                    # ~10^2 TFLOP per denoising step of a 2 x 25-frame clip
+    print("SVD-XT 2x25x72x128: %.1f TFLOP / step, %d launches" % (plan.flops() / 1e12, len(names)))
