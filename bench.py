@@ -337,6 +337,8 @@ def run_b200(args, rank, world, local):
     del unet, compiled, plan, gp
     if not args.no_extras and args.model == "sd15" and world == 1 and not args.global_batch:
         extras["config2_sdxl"] = sdxl_bench(dev)
+        extras["config3_svd"] = svd_bench(dev)
+        extras["vae_decode"] = vae_bench(dev)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, steps=2, warmup=1, budget_s=25.0)
@@ -481,6 +483,84 @@ def sdxl_bench(dev, steps=5, warmup=3):
     del unet, compiled, plan
     torch.cuda.empty_cache()
     return out
+
+
+def svd_bench(dev, steps=3, warmup=2):
+    """BASELINE configs[3]: StableVideoDiffusion-XT UNet (UNetSpatioTemporalConditionModel), 576 x 1024,
+    25 frames, CFG pair of videos (B = 2), fp16, CUDA graph; s/clip = 25 denoising steps of the UNet."""
+    from sfast.compilers.diffusion_pipeline_compiler import CompilationConfig, compile_unet
+    from sfast_b200.synthetic import CONFIGS, SyntheticUNet
+    try:
+        torch.cuda.empty_cache()
+        dtype, B, F_ = torch.float16, 2, 25
+        unet = SyntheticUNet(CONFIGS["svd"], seed=0, dtype=dtype, device=dev)
+        cc = CompilationConfig.Default()
+        cc.enable_cuda_graph = True
+        unet = compile_unet(unet, cc)
+        g = torch.Generator().manual_seed(6)
+        s = torch.randn(B, F_, 8, 72, 128, generator=g).to(dev, dtype)
+        e = torch.randn(B, 1, 1024, generator=g).to(dev, dtype)
+        tid = torch.tensor([[6.0, 127.0, 0.02]] * B, device=dev, dtype=dtype)
+        ts = [torch.tensor(1.6 - 0.06 * i, device=dev) for i in range(max(steps, warmup))]
+        for i in range(warmup):
+            unet(s, ts[i], e, tid)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(dev.index or 0)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            unet(s, ts[i], e, tid)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1) / steps
+        compiled = unet.forward._compiled
+        plan = next(iter(compiled._cached.values())).plan
+        out = {"what": "BASELINE configs[3]: SVD-XT UNet forward, 2 videos (CFG pair) x 25 frames of 8x72x128 "
+                       "latents (576x1024), fp16, CUDA graph, 1 GPU, random-init weights",
+               "ms_per_step": ms, "svd_xt_25step_unet_s_per_clip": 25 * ms / 1e3, "steps": steps, "warmup": warmup,
+               "first_call_s": compiled.first_call_s, "kernel_launches_per_step": len(plan.all_ops()),
+               "algorithmic_tflop_per_step": plan.flops() / 1e12, "step_tflops": plan.flops() / (ms / 1e3) / 1e12,
+               "clocks": clocks, **family_rates(plan)}
+        del unet, compiled, plan
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:  # noqa: BLE001
+        torch.cuda.empty_cache()
+        return {"unavailable": repr(exc)[:300]}
+
+
+def vae_bench(dev, steps=10, warmup=3):
+    """SD VAE decode (compile_vae): 4x64x64 latent -> 3x512x512 image, fp16, CUDA graph."""
+    from sfast.compilers.diffusion_pipeline_compiler import CompilationConfig, compile_vae
+    from sfast_b200.synthetic import SyntheticVAE
+    try:
+        vae = SyntheticVAE(seed=0, dtype=torch.float16, device=dev)
+        cc = CompilationConfig.Default()
+        cc.enable_cuda_graph = True
+        vae = compile_vae(vae, cc)
+        z = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(2)).to(dev, torch.float16)
+        for _ in range(warmup):
+            vae.decode(z)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            vae.decode(z)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        plan = next(iter(vae.decode._compiled._cached.values())).plan
+        out = {"what": "SD-1.5 VAE decode, 1 latent 4x64x64 -> 3x512x512, fp16, CUDA graph", "ms_per_image": ms,
+               "algorithmic_tflop": plan.flops() / 1e12, "tflops": plan.flops() / (ms / 1e3) / 1e12,
+               "steps": steps, "warmup": warmup}
+        del vae, plan
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:  # noqa: BLE001
+        torch.cuda.empty_cache()
+        return {"unavailable": repr(exc)[:300]}
 
 
 def gpu_library_baseline(args, sd, batch, dtype, dev, dev_s, dev_e, tsteps):

@@ -104,7 +104,8 @@ enum sfb_epilogue {
 typedef struct sfb_gemm_params {
     const void* tmap_a; /* host pointer to a 128-byte tensor map */
     const void* tmap_b; /* weights, TILED: block (n_tile, k_block) = contiguous [160, 64]; 2-D map
-                         * over [n_tiles * K/64 * 160, 64], box rows = 160 */
+                         * over [n_tiles * K/64 * 160, 64], box rows = 160 (80 with cta_pair).  With
+                         * b_plain: a plain row-major [N, K] matrix (sfb_tmap_2d, same box rows) */
     int32_t a_mode;
     int32_t M, N, K;
     int32_t dtype;
@@ -155,6 +156,9 @@ typedef struct sfb_gemm_params {
      * accumulators overlap the epilogue of tile i with the main loop of tile i + 1.  For launches
      * of more than one wave of tiles. */
     int32_t persistent;
+    /* 1: the B operand is a plain row-major [N, K] 16-bit matrix -- an ACTIVATION (activation x
+     * activation products: Q K^T and P V of the VAE's single-head attention), not a pre-tiled weight */
+    int32_t b_plain;
     /* LayerNorm folded around the GEMM (replaces sfast_triton::layer_norm,
      * /root/reference/src/sfast/triton/ops/layer_norm.py:51-133, as a separate pass):
      *   producer (SFB_EPI_STORE): rowstats_out[m] += (sum, sum of squares) of the stored row;
@@ -349,6 +353,15 @@ int sfb_add_nchw_residuals(const sfb_add_nchw_params* p, sfb_stream_t stream);
 /* dst[r, 0:cols] = src[r, 0:cols], 16-bit elements, row pitches in elements */
 int sfb_copy2d(const void* src, void* dst, int32_t rows, int32_t cols, int32_t ld_src,
                int32_t ld_dst, sfb_stream_t stream);
+
+/* In-place softmax over the rows of a [rows, cols] 16-bit matrix (row pitch ld elements), fp32
+ * arithmetic: the softmax of an attention computed as GEMMs (VAE decoder, head_dim 512). */
+int sfb_row_softmax(void* x, int32_t rows, int32_t cols, int32_t ld, int32_t dtype, sfb_stream_t stream);
+
+/* 1x1 convolution with tiny channel counts on NCHW tensors (the VAE's post_quant_conv, 4 -> 4):
+ * y[n, co, p] = bias[co] + sum_ci w[co, ci] x[n, ci, p]; cin, cout <= 8; w 16-bit [cout, cin]. */
+int sfb_pointwise_nchw(const void* x, const void* w, const float* bias, void* y, int32_t n, int32_t hw,
+                       int32_t cin, int32_t cout, int32_t dtype, sfb_stream_t stream);
 
 /* cudaMemsetAsync wrapper (graph capturable) */
 int sfb_memset(void* p, int32_t value, size_t bytes, sfb_stream_t stream);

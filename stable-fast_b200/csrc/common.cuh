@@ -402,8 +402,24 @@ __device__ __forceinline__ void store1(void* p, size_t i, float v, int bf16) {
 // replaces was ~20 of the ~30 instructions per element in the GroupNorm+SiLU apply loops
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// erf-GELU (diffusers GEGLU; the reference's CUTLASS kernel switches to the tanh form under torch's
+// default flags, cutlass_dual_linear_kernel.cu:509-514).  erf by Abramowitz & Stegun 7.1.26:
+// |error| <= 1.5e-7 absolute -- below fp32 round-off of the product -- with one MUFU.RCP, one
+// MUFU.EX2 and nine FMAs instead of libm erff's ~40 branchy instructions: the GEGLU epilogue of a
+// K = 320 projection is bound by this function, not by the MMAs in front of it.
+__device__ __forceinline__ float erf_as_f(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-ax * ax);
+    return copysignf(e, x);
+}
+
 __device__ __forceinline__ float gelu_erf_f(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752440f));
 }
 
 }  // namespace sfb

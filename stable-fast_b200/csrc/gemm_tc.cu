@@ -102,6 +102,7 @@ struct GemmArgs {
     int box_w, tiles_per_row;  // M tile = [box_n, box_h, box_w] pixels; box_w < img_w: 2-D patches
     int up_tiles;   // SFB_A_UPCONV2X: M tiles per output phase
     int up_ntiles;  // ... and N tiles per phase in the phase-concatenated weight matrix
+    int b_plain;    // B is a plain row-major [N, K] matrix (an activation), not a pre-tiled weight
     // persistent kernel: tile grid in units of (pair of M tiles) x (pair of 160-column N tiles)
     int m_pairs, n_tiles160, n_pairs, total_tiles;
     EpiArgs e;
@@ -453,7 +454,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 uint8_t* dA = sA + stage * L::kABytes;
                 uint8_t* dB = sB + stage * L::kBBytes;
                 // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous 160 x 64 block
-                const int b_row = (b_ntile * args.nkb_total + kb) * BN + ciy * (BN / 2);
+                int b_col = 0, b_row = (b_ntile * args.nkb_total + kb) * BN + ciy * (BN / 2);
+                if (args.b_plain) { b_col = kb * BK; b_row = b_ntile * BN + ciy * (BN / 2); }
                 int c0 = kb * BK, c1 = m_tile * BM, c2 = 0, c3 = 0;
                 if (args.a_mode != SFB_A_MATRIX) {
                     const int tap = kb / args.cpb;
@@ -469,12 +471,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
                     if (args.a_mode == SFB_A_MATRIX) tma_load_2d_pair(dA, &tma_a, &full_bar[stage], c0, c1);
                     else tma_load_4d_pair(dA, &tma_a, &full_bar[stage], c0, c1, c2, c3);
-                    tma_load_2d_pair(dB, &tma_b, &full_bar[stage], 0, b_row);
+                    tma_load_2d_pair(dB, &tma_b, &full_bar[stage], b_col, b_row);
                 } else {
                     mbar_expect_tx(&full_bar[stage], L::kStageBytes);
                     if (args.a_mode == SFB_A_MATRIX) tma_load_2d(dA, &tma_a, &full_bar[stage], c0, c1);
                     else tma_load_4d(dA, &tma_a, &full_bar[stage], c0, c1, c2, c3);
-                    tma_load_2d(dB, &tma_b, &full_bar[stage], 0, b_row);
+                    tma_load_2d(dB, &tma_b, &full_bar[stage], b_col, b_row);
                 }
             }
         }
@@ -912,8 +914,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                          at.w0 * args.conv_stride + dw, at.h0 * args.conv_stride + dh, at.n0);
                     }
                     for (int h = 0; h < nh; ++h) {
-                        const int b_row = ((b_ntile + h) * args.nkb_total + kb) * BN + ciy * (BN / 2);
-                        tma_load_2d_pair(dB + h * L::kBHalf, &tma_b, &full_bar[stage], 0, b_row);
+                        int b_col = 0, b_row = ((b_ntile + h) * args.nkb_total + kb) * BN + ciy * (BN / 2);
+                        if (args.b_plain) { b_col = kb * BK; b_row = (b_ntile + h) * BN + ciy * (BN / 2); }
+                        tma_load_2d_pair(dB + h * L::kBHalf, &tma_b, &full_bar[stage], b_col, b_row);
                     }
                 }
             }
@@ -1288,6 +1291,8 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     if (a.splits > a.nkb_total) return fail(SFB_ERR_INVALID, "sfb_gemm: splits > K blocks");
     if (a.splits > 1 && !p->ws) return fail(SFB_ERR_INVALID, "sfb_gemm: split-K needs a workspace");
     a.ws = p->ws;
+    a.b_plain = p->b_plain ? 1 : 0;
+    if (a.b_plain && p->a_mode == SFB_A_UPCONV2X) return fail(SFB_ERR_INVALID, "sfb_gemm: b_plain with up-conv");
     int m_tiles;
     const bool upconv = p->a_mode == SFB_A_UPCONV2X;
     const bool tconv = p->a_mode == SFB_A_CONV3X1;

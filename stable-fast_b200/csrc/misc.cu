@@ -352,9 +352,113 @@ __global__ void copy2d_kernel(const uint16_t* __restrict__ src, uint16_t* __rest
     }
 }
 
+// in-place row softmax: one CTA per row, the row (<= 16384 columns) held in registers
+__global__ void __launch_bounds__(256) row_softmax_kernel(uint16_t* x, int rows, int cols, int ld, int dtype) {
+    __shared__ float red[8];
+    pdl_launch_dependents();
+    pdl_wait();
+    uint16_t* xr = x + (size_t)blockIdx.x * ld;
+    const int nvec = cols / 8;
+    constexpr int kMaxVec = 8;  // 8 vectors x 8 values x 256 threads = 16384 columns
+    float v[kMaxVec][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+        const int vec = threadIdx.x + j * 256;
+        if (vec < nvec) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + vec * 8);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2(w[i], dtype);
+                v[j][2 * i] = f.x; v[j][2 * i + 1] = f.y;
+                mx = fmaxf(mx, fmaxf(f.x, f.y));
+            }
+        }
+    }
+    auto block_reduce = [&](float val, bool is_max) -> float {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, val, o);
+            val = is_max ? fmaxf(val, other) : val + other;
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = val;
+        __syncthreads();
+        float r = red[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+        return r;
+    };
+    mx = block_reduce(mx, true);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+        if (threadIdx.x + j * 256 < nvec) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[j][i] = __expf(v[j][i] - mx);
+                sum += v[j][i];
+            }
+        }
+    }
+    const float inv = 1.0f / block_reduce(sum, false);
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+        const int vec = threadIdx.x + j * 256;
+        if (vec < nvec) {
+            uint4 o;
+            o.x = pack2(v[j][0] * inv, v[j][1] * inv, dtype);
+            o.y = pack2(v[j][2] * inv, v[j][3] * inv, dtype);
+            o.z = pack2(v[j][4] * inv, v[j][5] * inv, dtype);
+            o.w = pack2(v[j][6] * inv, v[j][7] * inv, dtype);
+            *reinterpret_cast<uint4*>(xr + vec * 8) = o;
+        }
+    }
+}
+
+__global__ void pointwise_nchw_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
+                                      const float* __restrict__ bias, uint16_t* __restrict__ y, int n, int hw,
+                                      int cin, int cout, int dtype) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * hw) return;
+    const int img = (int)(idx / hw), p = (int)(idx % hw);
+    float xin[8];
+    for (int ci = 0; ci < cin; ++ci) xin[ci] = load1(x, ((size_t)img * cin + ci) * hw + p, dtype);
+    for (int co = 0; co < cout; ++co) {
+        float acc = bias ? bias[co] : 0.f;
+        for (int ci = 0; ci < cin; ++ci) acc += load1(w, (size_t)co * cin + ci, dtype) * xin[ci];
+        store1(y, ((size_t)img * cout + co) * hw + p, acc, dtype);
+    }
+}
+
 }  // namespace sfb
 
 using namespace sfb;
+
+extern "C" int sfb_row_softmax(void* x, int32_t rows, int32_t cols, int32_t ld, int32_t dtype, sfb_stream_t stream) {
+    if (!x || rows <= 0 || cols <= 0 || cols % 8 || ld % 8 || cols > 16384 || ld < cols)
+        return fail(SFB_ERR_INVALID, "row_softmax: cols=%d must be a multiple of 8 and <= 16384", cols);
+    cudaError_t err = launch_pdl(row_softmax_kernel, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                 reinterpret_cast<uint16_t*>(x), rows, cols, ld, dtype);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "row_softmax: %s", cudaGetErrorString(err));
+    return check_launch("sfb_row_softmax");
+}
+
+extern "C" int sfb_pointwise_nchw(const void* x, const void* w, const float* bias, void* y, int32_t n, int32_t hw,
+                                  int32_t cin, int32_t cout, int32_t dtype, sfb_stream_t stream) {
+    if (!x || !w || !y || n <= 0 || hw <= 0 || cin <= 0 || cin > 8 || cout <= 0 || cout > 8)
+        return fail(SFB_ERR_INVALID, "pointwise_nchw: cin / cout must be 1..8");
+    const long long total = (long long)n * hw;
+    cudaError_t err = launch_pdl(pointwise_nchw_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
+                                 static_cast<cudaStream_t>(stream), reinterpret_cast<const uint16_t*>(x),
+                                 reinterpret_cast<const uint16_t*>(w), bias, reinterpret_cast<uint16_t*>(y), n, hw,
+                                 cin, cout, dtype);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "pointwise_nchw: %s", cudaGetErrorString(err));
+    return check_launch("sfb_pointwise_nchw");
+}
 
 extern "C" int sfb_add_nchw_residuals(const sfb_add_nchw_params* p, sfb_stream_t stream) {
     if (!p || p->count <= 0 || p->count > 16) return fail(SFB_ERR_INVALID, "add_nchw_residuals: count must be 1..16");

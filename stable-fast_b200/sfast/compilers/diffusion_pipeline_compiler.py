@@ -72,5 +72,15 @@ def compile_unet(m, config):
 
 
 def compile_vae(m, config):
-    """VAE decode is outside this build's hot path: returned as is."""
-    return m
+    """Replace ``m.decode`` with the B200-native VAE decoder (reference `compile_vae`, :154-190, which
+    wraps the sub-modules in auto-trace hooks); `encode` stays eager.  A VAE without a `decode`
+    method, or one on a non-sm_100 device, is returned unchanged with a warning (the reference, too,
+    only hooks what it can trace)."""
+    from sfast_b200.runtime import compile_vae_module, require_b200
+    if not hasattr(m, 'decode') or not hasattr(m, 'config'):
+        logger.warning('sfast (B200 build): VAE without decode()/config is left on its eager path')
+        return m
+    device = m.device if hasattr(m, 'device') else torch.device(
+        'cuda' if torch.cuda.is_available() else 'cpu')
+    require_b200(torch.device(device))
+    return compile_vae_module(m, enable_cuda_graph=bool(config.enable_cuda_graph))

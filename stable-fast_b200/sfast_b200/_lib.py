@@ -33,7 +33,7 @@ class GemmParams(C.Structure):
         ("heads", C.c_int32), ("head_dim", C.c_int32), ("which_base", C.c_int32),
         ("seq", C.c_int32), ("q_pitch", C.c_int32), ("q_rows", C.c_int32),
         ("k_rows", C.c_int32), ("vt_rows", C.c_int32), ("vt_pitch", C.c_int32),
-        ("cta_pair", C.c_int32), ("persistent", C.c_int32),
+        ("cta_pair", C.c_int32), ("persistent", C.c_int32), ("b_plain", C.c_int32),
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_dim", C.c_int32),
     ]
@@ -134,6 +134,8 @@ SYMBOLS = {
     "sfb_alpha_blend": (C.c_int, [C.POINTER(RowOpParams), _VP]),
     "sfb_add_nchw_residuals": (C.c_int, [C.POINTER(AddNchwParams), _VP]),
     "sfb_copy2d": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_row_softmax": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_pointwise_nchw": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_memset": (C.c_int, [_VP, _I32, C.c_size_t, _VP]),
 }
 

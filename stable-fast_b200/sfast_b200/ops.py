@@ -202,6 +202,7 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         a_map = _a_map(a, dry)
         b_map = b.map_for(2 if pair else 1)
         p.cta_pair = 1 if pair else 0
+        p.b_plain = 1 if isinstance(b, PlainB) else 0
         keep = tuple(keep) + (b,)
     p.tmap_a, p.tmap_b = a_map.ptr, b_map.ptr
     p.a_mode = (A_UPCONV2X if up else (A_CONV3X1 if conv.get("temporal") else A_CONV3X3)) if conv else A_MATRIX
@@ -396,6 +397,21 @@ class Mat:
             self._maps[cluster_m] = m
         return self._maps[cluster_m]
 
+
+
+class PlainB:
+    """A GEMM B operand that is a plain row-major [n, k] 16-bit matrix in device memory (an
+    activation: Q K^T, P V), addressed by a 2-D TMA map instead of the tiled weight layout."""
+    __slots__ = ("ptr", "n", "k", "pitch", "_dry", "_maps")
+
+    def __init__(self, ptr, n, k, pitch, dry=False):
+        assert k % BK == 0, f"K={k} must be a multiple of {BK}"
+        self.ptr, self.n, self.k, self.pitch, self._dry, self._maps = ptr, n, k, pitch, dry, {}
+
+    def map_for(self, cluster_m):
+        if cluster_m not in self._maps:
+            self._maps[cluster_m] = matrix_map(self.ptr, self.n, self.k, self.pitch, BN // cluster_m, self._dry)
+        return self._maps[cluster_m]
 
 
 def pack_conv3x3(w, dt):

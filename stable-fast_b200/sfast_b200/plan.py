@@ -54,7 +54,8 @@ class PackedWeights:
             self.tproj_off[r.prefix] = off
             off += r.cout
         self.tproj_total = off
-        self.tproj_w, self.tproj_b = self._get(("tproj",), self._build_tproj)
+        if off:  # (the VAE decoder has no time embedding)
+            self.tproj_w, self.tproj_b = self._get(("tproj",), self._build_tproj)
 
     def _build_tproj(self):
         ws = [self._raw(r.prefix + ".time_emb_proj.weight") for r in self.spec.all_resnets()]
@@ -187,6 +188,14 @@ class PackedWeights:
             v = self._raw(name).to(device=self.device, dtype=torch.float32)
             return (v * (1.0 - torch.sigmoid(self._raw(one_minus_alpha_of).to(self.device).float()))).contiguous()
         return self._get(("f32s", name, one_minus_alpha_of), build)
+
+    def scaled_linear(self, prefix, scale):
+        """(Mat of scale * W, fp32 scale * b): a linear layer with a constant folded in."""
+        def build():
+            w = (self._raw(prefix + ".weight").to(self.device).float() * scale).to(self.dtype).contiguous()
+            b = (self._raw(prefix + ".bias").to(self.device).float() * scale).contiguous()
+            return (self._mat(w), b)
+        return self._get(("slin", prefix, scale), build)
 
     def small(self, name):
         return self._get(("small", name), lambda: self._raw(name).to(

@@ -97,7 +97,7 @@ class CompiledUNet:
 
     # -- weights -------------------------------------------------------------------------
     def _versions(self):
-        return [(p._version, p.data_ptr()) for p in self._param_refs]
+        return [p._version for p in self._param_refs]
 
     def _ensure_weights(self, dtype, device):
         if self._weights is None or self._weights.dtype != dtype or self._weights.device != device:
@@ -241,6 +241,86 @@ class CompiledUNet:
         if not return_dict:
             return (out,)
         return UNet2DConditionOutput(sample=out)
+
+
+class DecoderOutput(dict):
+    """Stand-in for diffusers' DecoderOutput (attribute, key and index access)."""
+
+    def __init__(self, sample):
+        super().__init__(sample=sample)
+        self.sample = sample
+
+    def __getitem__(self, k):
+        return tuple(self.values())[k] if isinstance(k, int) else super().__getitem__(k)
+
+
+class CompiledVAEDecoder:
+    """`AutoencoderKL.decode(z, return_dict=True, generator=None)` on the native path."""
+
+    def __init__(self, config, state_dict_fn, eager_decode, enable_cuda_graph=True):
+        from .vae_plan import vae_spec_from_config
+        self.spec = vae_spec_from_config(config)
+        self._state_dict_fn, self._eager = state_dict_fn, eager_decode
+        self.enable_cuda_graph = enable_cuda_graph
+        self._weights, self._param_refs, self._param_versions = None, None, None
+        self._cached = {}
+        self._lock = threading.Lock()
+        self._warned = False
+
+    def __call__(self, z, return_dict=True, generator=None):
+        from .vae_plan import VAEDecodePlan
+        if z.dtype not in (torch.float16, torch.bfloat16):
+            # e.g. SDXL's force_upcast fp32 VAE: the whole module stays on its own eager path
+            if not self._warned:
+                logger.warning("sfast (B200 build): VAE decode in %s is left on the module's eager path "
+                               "(the native decoder computes in fp16 / bf16)", z.dtype)
+                self._warned = True
+            return self._eager(z, return_dict=return_dict, generator=generator)
+        require_b200(z.device)
+        B, _, H, W = z.shape
+        with self._lock, torch.cuda.device(z.device):
+            if self._weights is None or self._weights.dtype != z.dtype or self._weights.device != z.device:
+                sd = self._state_dict_fn()
+                self._weights = PackedWeights(self.spec, sd, z.dtype, z.device)
+                self._param_refs = [t for t in sd.values() if torch.is_tensor(t)]
+                self._param_versions = [t._version for t in self._param_refs]
+                self._cached.clear()
+            elif [t._version for t in self._param_refs] != self._param_versions:
+                sd = self._state_dict_fn()
+                torch.cuda.current_stream().synchronize()
+                self._weights.refresh(sd)
+                self._param_refs = [t for t in sd.values() if torch.is_tensor(t)]
+                self._param_versions = [t._version for t in self._param_refs]
+            key = (B, H, W, z.dtype, z.device.index)
+            gp = self._cached.get(key)
+            if gp is None:
+                gp = _GraphedPlan(VAEDecodePlan(self._weights, B, H, W), self.enable_cuda_graph)
+                self._cached[key] = gp
+            gp.plan.z_in.copy_(z, non_blocking=True)
+            gp.step()
+            out = gp.plan.out.clone()
+        if not return_dict:
+            return (out,)
+        try:
+            from diffusers.models.autoencoders.vae import DecoderOutput as DO  # type: ignore
+            return DO(sample=out)
+        except Exception:  # noqa: BLE001
+            return DecoderOutput(sample=out)
+
+
+def compile_vae_module(m, enable_cuda_graph=True):
+    """Replace ``m.decode`` of an AutoencoderKL (same module object; `encode` is left alone)."""
+    eager = m.decode
+    compiled = CompiledVAEDecoder(m.config, m.state_dict, eager, enable_cuda_graph)
+
+    def decode(z, return_dict=True, generator=None):
+        return compiled(z, return_dict=return_dict, generator=generator)
+
+    decode.__self__ = m
+    decode._cached = compiled._cached
+    decode._compiled = compiled
+    m.decode = decode
+    return m
 
 
 def compile_unet_module(m, enable_cuda_graph=True, preserve_parameters=True):

@@ -26,7 +26,44 @@ SDXL = dict(
 TINY = dict(SD15, block_out_channels=(64, 128, 256, 256), attention_head_dim=(2, 2, 4, 4),
             cross_attention_dim=128, sample_size=32)
 
-CONFIGS = {"sd15": SD15, "sdxl": SDXL, "tiny": TINY}
+SVD = dict(
+    in_channels=8, out_channels=4, block_out_channels=(320, 640, 1280, 1280),
+    down_block_types=("CrossAttnDownBlockSpatioTemporal",) * 3 + ("DownBlockSpatioTemporal",),
+    up_block_types=("UpBlockSpatioTemporal",) + ("CrossAttnUpBlockSpatioTemporal",) * 3,
+    layers_per_block=2, num_attention_heads=(5, 10, 20, 20), cross_attention_dim=1024,
+    transformer_layers_per_block=1, addition_time_embed_dim=256,
+    projection_class_embeddings_input_dim=768, num_frames=25, sample_size=96)
+
+SD_VAE = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
+              layers_per_block=2, norm_num_groups=32, act_fn="silu", scaling_factor=0.18215, sample_size=512)
+
+CONFIGS = {"sd15": SD15, "sdxl": SDXL, "tiny": TINY, "svd": SVD}
+
+
+class SyntheticVAE:
+    """Random-weight stand-in for a diffusers AutoencoderKL (decoder side) for `compile_vae`."""
+
+    def __init__(self, config=None, seed=0, dtype=torch.float16, device="cuda"):
+        import math
+        from .vae_plan import vae_decoder_param_shapes, vae_spec_from_config
+        self.config = dict(config or SD_VAE)
+        self.dtype, self.device = dtype, torch.device(device)
+        g = torch.Generator().manual_seed(seed)
+        sd = {}
+        for name, shape in vae_decoder_param_shapes(vae_spec_from_config(self.config)).items():
+            if "norm" in name:
+                t = torch.randn(shape, generator=g) * 0.3 + (1.0 if name.endswith("weight") else 0.0)
+            else:
+                fan = math.prod(shape[1:]) if len(shape) > 1 else shape[0]
+                t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(max(fan, 1))
+            sd[name] = t.to(dtype=dtype, device=self.device)
+        self._sd = sd
+
+    def state_dict(self):
+        return self._sd
+
+    def decode(self, *a, **k):
+        raise RuntimeError("SyntheticVAE has no eager decode; compile it first")
 
 
 class SyntheticUNet:

@@ -589,6 +589,52 @@ def check_conv_t(B=2, F_=25, h=8, w=16, cin=320, cout=320, dt=torch.float16, row
     return rel_err(out, ref)
 
 
+
+# ------------------------------------------------------------------------------------------
+# VAE decoder pieces
+def check_gemm_plain_b(M=512, N=4096, K=512, dt=torch.float16, bias=False, persistent=False, seed=41):
+    """Activation x activation GEMM: B is a plain row-major [N, K] matrix (Q K^T, P V, V^T = W X^T)."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    a = _rand(M, K, dt=dt)
+    bm = _rand(N, K, dt=dt, scale=1 / math.sqrt(K))
+    b = torch.randn(N, device=DEV) if bias else None
+    out = torch.zeros(M, N, device=DEV, dtype=dt)
+    op = ops.gemm_op("plain_b", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=ops.PlainB(bm.data_ptr(), N, K, K),
+                     M=M, N=N, K=K, dt=dt, out=out, ldo=N, bias=b, splits=1, persistent=persistent)
+    assert op.keep[0].b_plain == 1
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    ref = a.float() @ bm.float().t()
+    if bias:
+        ref = ref + b
+    return rel_err(out, ref)
+
+
+def check_row_softmax(rows=300, cols=4096, dt=torch.float16, seed=42):
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    x = _rand(rows, cols, dt=dt, scale=3.0)
+    ref = torch.softmax(x.float(), dim=-1)
+    _lib.check(lib.sfb_row_softmax(x.data_ptr(), rows, cols, cols, ops.dtype_code(dt), _stream()))
+    torch.cuda.synchronize()
+    return rel_err(x, ref)
+
+
+def check_pointwise(n=2, hw=4096, cin=4, cout=4, dt=torch.float16, seed=43):
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    x = _rand(n, cin, hw, dt=dt)
+    w = _rand(cout, cin, dt=dt)
+    b = torch.randn(cout, device=DEV)
+    y = torch.zeros(n, cout, hw, device=DEV, dtype=dt)
+    _lib.check(lib.sfb_pointwise_nchw(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, hw, cin, cout,
+                                      ops.dtype_code(dt), _stream()))
+    torch.cuda.synchronize()
+    ref = torch.einsum("oc,ncp->nop", w.float(), x.float()) + b[None, :, None]
+    return rel_err(y, ref)
+
+
 CHECKS = {
     "gemm_small": (lambda: check_gemm(300, 320, 320), 2e-3),
     "gemm_k64": (lambda: check_gemm(128, 160, 64, bias=False, residual=False), 2e-3),
@@ -646,6 +692,15 @@ CHECKS = {
     "persist_ln_fold": (lambda: check_ln_fold(2048, 320, 960, persistent=True), 5e-3),
     "persist_ln_fold_1280": (lambda: check_ln_fold(1024, 1280, 1280, persistent=True), 5e-3),
     "persist_ln_fold_geglu": (lambda: check_ln_fold(1024, 640, 2560, mode="geglu", persistent=True), 2e-2),
+    # VAE decoder pieces
+    "gemm_plain_b_vt": (lambda: check_gemm_plain_b(512, 4096, 512), 2e-3),
+    "gemm_plain_b_scores": (lambda: check_gemm_plain_b(4096, 4096, 512), 2e-3),
+    "gemm_plain_b_pv": (lambda: check_gemm_plain_b(4096, 512, 4096, bias=True), 2e-3),
+    "gemm_plain_b_ragged": (lambda: check_gemm_plain_b(256, 1024, 128), 2e-3),
+    "gemm_plain_b_bf16_persistent": (lambda: check_gemm_plain_b(4096, 4096, 512, dt=torch.bfloat16, persistent=True), 1e-2),
+    "row_softmax": (lambda: check_row_softmax(), 2e-3),
+    "row_softmax_1024_bf16": (lambda: check_row_softmax(64, 1024, dt=torch.bfloat16), 1e-2),
+    "pointwise_nchw": (lambda: check_pointwise(), 2e-3),
     # SVD temporal path
     "temporal_attn_25": (lambda: check_temporal_attention(2, 25, 64, 5), 5e-3),
     "temporal_attn_6_d64x4": (lambda: check_temporal_attention(1, 6, 37, 4), 5e-3),

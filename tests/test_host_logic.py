@@ -456,3 +456,26 @@ def test_svd_plan_builds_and_counts_its_temporal_ops():
     assert names.count("sfb_attention") == 16          # spatial self-attention only: cross-attention is an add
     assert plan.flops() / 1e12 > 50                    # ~10^2 TFLOP per denoising step of a 2 x 25-frame clip
     print("SVD-XT 2x25x72x128: %.1f TFLOP / step, %d launches" % (plan.flops() / 1e12, len(names)))
+
+
+def test_vae_decoder_plan_builds_and_passes_host_validation():
+    import torch
+    from oracle import vae_oracle as vo
+    from sfast_b200.plan import PackedWeights
+    from sfast_b200.vae_plan import VAEDecodePlan, vae_decoder_param_shapes, vae_spec_from_config
+    spec = vae_spec_from_config(vo.sd_vae_config())
+    shapes = vae_decoder_param_shapes(spec)
+    assert sum(int(torch.Size(s).numel()) for s in shapes.values()) == 49_490_199  # decoder + post_quant_conv
+    with torch.device("meta"):
+        m = vo.AutoencoderKLDecoder(vo.sd_vae_config())
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v) for k, v in shapes.items()}
+    sd = {k: torch.empty(v, dtype=torch.float16, device="meta") for k, v in shapes.items()}
+    plan = VAEDecodePlan(PackedWeights(spec, sd, torch.float16, "meta", dry=True), 1, 64, 64)
+    names = [op.fn.name for op in plan.all_ops() if op.fn is not None]
+    assert names.count("sfb_row_softmax") == 1 and names.count("sfb_pointwise_nchw") == 1
+    gemms = [op.keep[0] for op in plan.all_ops() if op.fn is not None and op.fn.name == "sfb_gemm"]
+    assert sum(1 for g in gemms if g.b_plain) == 3 and sum(1 for g in gemms if g.a_mode == _lib.A_UPCONV2X) == 3
+    print("VAE decode 64x64 -> 512x512: %.2f TFLOP, %d launches" % (plan.flops() / 1e12, len(names)))
+    if not torch.cuda.is_available():
+        n = _validate_plan_on_cpu(plan)
+        assert n["sfb_gemm"] >= 35
