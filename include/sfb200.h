@@ -99,6 +99,9 @@ enum sfb_epilogue {
     SFB_EPI_STORE = 0, /* out[m, n] = acc + bias[n] + rowbias[img(m), n] + residual[m, n] */
     SFB_EPI_GEGLU = 1, /* out[m, j] = (acc_v + b_v) * gelu(acc_g + b_g); weights tile-interleaved */
     SFB_EPI_QKV = 2,   /* scatter columns into per-head Q / K ([bh, s, dp]) and V^T ([bh, d, sp]) */
+    /* out is fp32 [M, ldo floats]: acc + bias, unrounded (attention scores of the VAE's single-head
+     * attention: 16-bit scores lose ~2 % on the probabilities).  One-tile kernel only, no split-K. */
+    SFB_EPI_STORE_F32 = 3,
 };
 
 typedef struct sfb_gemm_params {
@@ -354,9 +357,12 @@ int sfb_add_nchw_residuals(const sfb_add_nchw_params* p, sfb_stream_t stream);
 int sfb_copy2d(const void* src, void* dst, int32_t rows, int32_t cols, int32_t ld_src,
                int32_t ld_dst, sfb_stream_t stream);
 
-/* In-place softmax over the rows of a [rows, cols] 16-bit matrix (row pitch ld elements), fp32
- * arithmetic: the softmax of an attention computed as GEMMs (VAE decoder, head_dim 512). */
-int sfb_row_softmax(void* x, int32_t rows, int32_t cols, int32_t ld, int32_t dtype, sfb_stream_t stream);
+/* Softmax over the rows of x [rows, cols] (fp32 when x_is_f32, else 16-bit; row pitch ldx elements of
+ * its type) -> y 16-bit [rows, cols] (row pitch ldy elements), fp32 arithmetic.  y may alias x (each
+ * row is read completely before it is written): the softmax of an attention computed as GEMMs (VAE
+ * decoder, head_dim 512). */
+int sfb_row_softmax(const void* x, void* y, int32_t rows, int32_t cols, int32_t ldx, int32_t ldy,
+                    int32_t x_is_f32, int32_t dtype, sfb_stream_t stream);
 
 /* 1x1 convolution with tiny channel counts on NCHW tensors (the VAE's post_quant_conv, 4 -> 4):
  * y[n, co, p] = bias[co] + sum_ci w[co, ci] x[n, ci, p]; cin, cout <= 8; w 16-bit [cout, cin]. */

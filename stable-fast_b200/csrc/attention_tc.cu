@@ -47,6 +47,33 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// 2^x on the FMA / ALU pipes instead of the MUFU (special-function) pipe: Cody-Waite split
+// x = n + f, f in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (max relative error 1.0e-4,
+// below the half-ulp of the 16-bit probability it is rounded to), 2^n by an integer add into the
+// exponent.  The softmax of these kernels is bound by MUFU.EX2 (16 lanes / clk / SM against 128 for
+// FMA): one exponential per score with head_dim 40 / 64 means one MUFU op per 160 / 256 tensor FLOPs.
+// Sending a fixed fraction of every row's exponentials through this routine (kPolyMask: which of each
+// 8 consecutive scores) trades 8 extra issue slots per element for a free MUFU slot; the balance
+// point of the two pipes is ~30 %.  x <= ~8 here (lazy reference maximum).
+__device__ __forceinline__ float poly_exp2(float x) {
+    x = fmaxf(x, -125.0f);                       // 2^-125: a zero probability after rounding
+    const float t = x + 12582912.0f;             // 1.5 * 2^23: round(x) lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);       // [-0.5, 0.5]
+    float p = fmaf(f, 0.05500893f, 0.24221096f);
+    p = fmaf(p, f, 0.69328293f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef SFB_EXP_POLY_MASK
+#define SFB_EXP_POLY_MASK 0x88   // elements 3 and 7 of every 8: 25 % of the exponentials
+#endif
+constexpr unsigned kPolyMask = SFB_EXP_POLY_MASK;
+template <int I>
+__device__ __forceinline__ float softmax_exp2(float x) {
+    if constexpr ((kPolyMask >> (I & 7)) & 1u) return poly_exp2(x);
+    else return fast_exp2(x);
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -264,10 +291,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
-                pk[g].x = pack2(fast_exp2(x[0]), fast_exp2(x[1]), BF16);
-                pk[g].y = pack2(fast_exp2(x[2]), fast_exp2(x[3]), BF16);
-                pk[g].z = pack2(fast_exp2(x[4]), fast_exp2(x[5]), BF16);
-                pk[g].w = pack2(fast_exp2(x[6]), fast_exp2(x[7]), BF16);
+                pk[g].x = pack2(softmax_exp2<0>(x[0]), softmax_exp2<1>(x[1]), BF16);
+                pk[g].y = pack2(softmax_exp2<2>(x[2]), softmax_exp2<3>(x[3]), BF16);
+                pk[g].z = pack2(softmax_exp2<4>(x[4]), softmax_exp2<5>(x[5]), BF16);
+                pk[g].w = pack2(softmax_exp2<6>(x[6]), softmax_exp2<7>(x[7]), BF16);
             }
             // ... and only then wait for PV(j-1): the P buffer / O accumulator are not touched before,
             // so the previous tile's second MMA overlaps this tile's MUFU work
@@ -583,10 +610,10 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tma_q,
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
-                pk[g].x = pack2(fast_exp2(x[0]), fast_exp2(x[1]), BF16);
-                pk[g].y = pack2(fast_exp2(x[2]), fast_exp2(x[3]), BF16);
-                pk[g].z = pack2(fast_exp2(x[4]), fast_exp2(x[5]), BF16);
-                pk[g].w = pack2(fast_exp2(x[6]), fast_exp2(x[7]), BF16);
+                pk[g].x = pack2(softmax_exp2<0>(x[0]), softmax_exp2<1>(x[1]), BF16);
+                pk[g].y = pack2(softmax_exp2<2>(x[2]), softmax_exp2<3>(x[3]), BF16);
+                pk[g].z = pack2(softmax_exp2<4>(x[4]), softmax_exp2<5>(x[5]), BF16);
+                pk[g].w = pack2(softmax_exp2<6>(x[6]), softmax_exp2<7>(x[7]), BF16);
             }
             // probability buffer b was last read by PV(j-2)
             if (j >= 2) {

@@ -669,6 +669,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
                 }
             }
+        } else if (e.epi == SFB_EPI_STORE_F32) {
+#pragma unroll 1
+            for (int it = 0; it < kItems; ++it) {
+                const int idx = et + it * kEpiThreads;
+                const int row = idx / kGroups, grp = idx - row * kGroups;
+                const int mm = sRowM[row], n = ncol0 + grp * 8;
+                if (mm >= 0 && n < e.N) {
+                    float f[8];
+                    load8(row, grp * 8, f);
+                    float* dst = reinterpret_cast<float*>(e.out) + (size_t)mm * e.ldo + n;
+                    *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                }
+            }
         } else if (e.epi == SFB_EPI_GEGLU) {
 #pragma unroll 1
             for (int it = 0; it < kItems / 2; ++it) {
@@ -1353,6 +1367,9 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     } else if (p->epi == SFB_EPI_QKV) {
         if (p->head_dim % 8 || p->heads <= 0 || p->seq <= 0 || p->N % (p->heads * p->head_dim))
             return fail(SFB_ERR_INVALID, "sfb_gemm: qkv geometry");
+    } else if (p->epi == SFB_EPI_STORE_F32) {
+        if (!p->out || p->ldo % 4 || p->residual || p->rowstats_out || p->ln_rowstats || a.splits != 1 || p->persistent)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: the fp32 store epilogue takes bias only, no split-K, one-tile kernel");
     } else {
         return fail(SFB_ERR_INVALID, "sfb_gemm: epilogue mode");
     }

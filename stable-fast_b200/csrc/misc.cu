@@ -352,12 +352,13 @@ __global__ void copy2d_kernel(const uint16_t* __restrict__ src, uint16_t* __rest
     }
 }
 
-// in-place row softmax: one CTA per row, the row (<= 16384 columns) held in registers
-__global__ void __launch_bounds__(256) row_softmax_kernel(uint16_t* x, int rows, int cols, int ld, int dtype) {
+// row softmax: one CTA per row, the row (<= 16384 columns) held in registers; y may alias x
+template <bool kF32>
+__global__ void __launch_bounds__(256) row_softmax_kernel(const void* x, uint16_t* y, int rows, int cols, int ldx,
+                                                          int ldy, int dtype) {
     __shared__ float red[8];
     pdl_launch_dependents();
     pdl_wait();
-    uint16_t* xr = x + (size_t)blockIdx.x * ld;
     const int nvec = cols / 8;
     constexpr int kMaxVec = 8;  // 8 vectors x 8 values x 256 threads = 16384 columns
     float v[kMaxVec][8];
@@ -366,14 +367,23 @@ __global__ void __launch_bounds__(256) row_softmax_kernel(uint16_t* x, int rows,
     for (int j = 0; j < kMaxVec; ++j) {
         const int vec = threadIdx.x + j * 256;
         if (vec < nvec) {
-            const uint4 u = *reinterpret_cast<const uint4*>(xr + vec * 8);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            if (kF32) {
+                const float* xr = reinterpret_cast<const float*>(x) + (size_t)blockIdx.x * ldx + vec * 8;
+                const float4 a = *reinterpret_cast<const float4*>(xr), b = *reinterpret_cast<const float4*>(xr + 4);
+                v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
+                v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+            } else {
+                const uint16_t* xr = reinterpret_cast<const uint16_t*>(x) + (size_t)blockIdx.x * ldx + vec * 8;
+                const uint4 u = *reinterpret_cast<const uint4*>(xr);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack2(w[i], dtype);
-                v[j][2 * i] = f.x; v[j][2 * i + 1] = f.y;
-                mx = fmaxf(mx, fmaxf(f.x, f.y));
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack2(w[i], dtype);
+                    v[j][2 * i] = f.x; v[j][2 * i + 1] = f.y;
+                }
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[j][i]);
         }
     }
     auto block_reduce = [&](float val, bool is_max) -> float {
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(256) row_softmax_kernel(uint16_t* x, int rows,
         for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
         return r;
     };
-    mx = block_reduce(mx, true);
+    mx = block_reduce(mx, true);  // (its barriers also order every read of the row before any write)
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) {
@@ -403,6 +413,7 @@ __global__ void __launch_bounds__(256) row_softmax_kernel(uint16_t* x, int rows,
         }
     }
     const float inv = 1.0f / block_reduce(sum, false);
+    uint16_t* yr = y + (size_t)blockIdx.x * ldy;
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) {
         const int vec = threadIdx.x + j * 256;
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(256) row_softmax_kernel(uint16_t* x, int rows,
             o.y = pack2(v[j][2] * inv, v[j][3] * inv, dtype);
             o.z = pack2(v[j][4] * inv, v[j][5] * inv, dtype);
             o.w = pack2(v[j][6] * inv, v[j][7] * inv, dtype);
-            *reinterpret_cast<uint4*>(xr + vec * 8) = o;
+            *reinterpret_cast<uint4*>(yr + vec * 8) = o;
         }
     }
 }
@@ -438,11 +449,15 @@ __global__ void pointwise_nchw_kernel(const uint16_t* __restrict__ x, const uint
 
 using namespace sfb;
 
-extern "C" int sfb_row_softmax(void* x, int32_t rows, int32_t cols, int32_t ld, int32_t dtype, sfb_stream_t stream) {
-    if (!x || rows <= 0 || cols <= 0 || cols % 8 || ld % 8 || cols > 16384 || ld < cols)
+extern "C" int sfb_row_softmax(const void* x, void* y, int32_t rows, int32_t cols, int32_t ldx, int32_t ldy,
+                               int32_t x_is_f32, int32_t dtype, sfb_stream_t stream) {
+    if (!x || !y || rows <= 0 || cols <= 0 || cols % 8 || ldx % 8 || ldy % 8 || cols > 16384 || ldx < cols || ldy < cols)
         return fail(SFB_ERR_INVALID, "row_softmax: cols=%d must be a multiple of 8 and <= 16384", cols);
-    cudaError_t err = launch_pdl(row_softmax_kernel, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                                 reinterpret_cast<uint16_t*>(x), rows, cols, ld, dtype);
+    cudaError_t err = x_is_f32
+        ? launch_pdl(row_softmax_kernel<true>, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream), x,
+                     reinterpret_cast<uint16_t*>(y), rows, cols, ldx, ldy, dtype)
+        : launch_pdl(row_softmax_kernel<false>, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream), x,
+                     reinterpret_cast<uint16_t*>(y), rows, cols, ldx, ldy, dtype);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "row_softmax: %s", cudaGetErrorString(err));
     return check_launch("sfb_row_softmax");
 }

@@ -300,20 +300,53 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
     const int tx = threadIdx.x % a.nvec;
     const int ty = threadIdx.x / a.nvec;
     for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads) acc[i] = 0.f;
-    gn_load_shifts<kPart>(a, img, sK);  // in flight together with the slab loads below
     const int row0 = blockIdx.x * a.rows_per_block;
     const int row1 = min(row0 + a.rows_per_block, a.hw);
     const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
-    if (ty < by) {
-        if constexpr (kPart) {
-            // channels [0, part_c) come from the producer GEMM's split-K partials (a few rows per
-            // thread, each with all its partial loads in flight)
+    if constexpr (kPart) {
+        // channels [0, part_c) come from the producer GEMM's split-K partials (a few rows per thread,
+        // each with all its partial loads in flight); the shifts need a finished value -> shared memory
+        gn_load_shifts<true>(a, img, sK);
+        if (ty < by) {
             const bool from_partials = tx * 8 < a.part_c;
             for (int row = row0 + ty; row < row1; row += by)
                 slab[(row - row0) * a.nvec + tx] = from_partials
                     ? gn_finish_partials(a, img, row, tx)
                     : *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
-        } else {
+        }
+        __syncthreads();  // shifts and accumulators visible; each thread re-reads only its own slab rows
+        if (ty < by) {
+            float k[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
+            GnAcc8 st;
+            st.zero();
+            for (int row = row0 + ty; row < row1; row += by) st.add(slab[(row - row0) * a.nvec + tx], k, a.dtype);
+            st.flush(acc, tx * 8, a.cpg);
+        }
+    } else {
+        __syncthreads();  // acc zeroed
+        if (ty < by) {
+            // every thread fetches the shifts of its own 8 channels itself (a group's shift is one
+            // 2-byte load of a line all threads of the group share): they are in flight together with
+            // the slab loads, and the sums accumulate straight from the registers the loads land in
+            float k[8];
+            {
+                int g_prev = -1;
+                float kv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int g = (tx * 8 + i) / a.cpg;
+                    if (g != g_prev) {
+                        kv = load1(a.x, (size_t)img * a.hw * a.ldx + g * a.cpg, a.dtype);
+                        g_prev = g;
+                        if (ty == 0 && g * a.cpg >= tx * 8) sK[g] = kv;  // the group's first channel is this thread's
+                    }
+                    k[i] = kv;
+                }
+            }
+            GnAcc8 st;
+            st.zero();
             // all of a thread's loads of one batch are in flight together: the slab is a handful of
             // rows per thread, so a load-use-load chain would be nothing but exposed L2 latency
             constexpr int kU = 8;
@@ -327,20 +360,14 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
 #pragma unroll
                 for (int u = 0; u < kU; ++u) {
                     const int row = rb + u * by;
-                    if (row < row1) slab[(row - row0) * a.nvec + tx] = v[u];
+                    if (row < row1) {
+                        slab[(row - row0) * a.nvec + tx] = v[u];
+                        st.add(v[u], k, a.dtype);
+                    }
                 }
             }
+            st.flush(acc, tx * 8, a.cpg);
         }
-    }
-    __syncthreads();  // shifts and accumulators visible; each thread re-reads only its own slab rows
-    if (ty < by) {
-        float k[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
-        GnAcc8 st;
-        st.zero();
-        for (int row = row0 + ty; row < row1; row += by) st.add(slab[(row - row0) * a.nvec + tx], k, a.dtype);
-        st.flush(acc, tx * 8, a.cpg);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads)
@@ -546,6 +573,9 @@ template <bool kPart>
 static cudaError_t launch_gn_fused(dim3 grid, size_t smem, cudaStream_t stream, const GnArgs& a, unsigned* sync) {
     static int pdl_ok[64];  // 0 unknown, 1 yes, -1 no
     const int dev = current_device();
+    // measurement switch only: SFB_GN_COOP=0 launches the kernel WITHOUT the co-residency guarantee
+    static const bool coop = [] { const char* v = getenv("SFB_GN_COOP"); return !(v && v[0] == '0'); }();
+    if (!coop) return launch_pdl(gn_fused_kernel<kPart>, grid, dim3(kGnThreads), smem, stream, a, sync);
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool with_pdl = g_pdl && pdl_ok[dev] >= 0;
         cudaLaunchConfig_t cfg{};

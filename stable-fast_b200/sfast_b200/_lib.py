@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SFB_LIB_PATH") or os.path.join(_HERE, "libsfb200.so")
 SFB_F16, SFB_BF16 = 0, 1
 A_MATRIX, A_CONV3X3, A_UPCONV2X, A_CONV3X1 = 0, 1, 2, 3
 ROW_IDX_DIV_MOD, ROW_IDX_TEMPORAL_CTX = 0, 1
-EPI_STORE, EPI_GEGLU, EPI_QKV = 0, 1, 2
+EPI_STORE, EPI_GEGLU, EPI_QKV, EPI_STORE_F32 = 0, 1, 2, 3
 
 
 class GemmParams(C.Structure):
@@ -134,7 +134,7 @@ SYMBOLS = {
     "sfb_alpha_blend": (C.c_int, [C.POINTER(RowOpParams), _VP]),
     "sfb_add_nchw_residuals": (C.c_int, [C.POINTER(AddNchwParams), _VP]),
     "sfb_copy2d": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP]),
-    "sfb_row_softmax": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_row_softmax": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_pointwise_nchw": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_memset": (C.c_int, [_VP, _I32, C.c_size_t, _VP]),
 }

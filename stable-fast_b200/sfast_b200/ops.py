@@ -224,7 +224,7 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         p.ws = _ptr(ws) if not hasattr(ws, "finalize") else 0
     if persistent is None:
         persistent = PERSIST == "1" or (PERSIST == "auto" and m_tiles * n_tiles >= PERSIST_MIN_CTAS)
-    p.persistent = 1 if (persistent and p.cta_pair and splits == 1) else 0
+    p.persistent = 1 if (persistent and p.cta_pair and splits == 1 and epi != _lib.EPI_STORE_F32) else 0
     p.epi = epi
     p.out = _ptr(out)
     p.ldo = ldo

@@ -149,7 +149,9 @@ class VAEDecodePlan(UNetPlan):
         self.linear(p + ".to_q", hn, wq, bq, q)
         self.linear(p + ".to_k", hn, self.w.matrix(p + ".to_k.weight"), self.w.f32(p + ".to_k.bias"), k)
         vt = self.buf("vae_vt", (B, c, S))        # V^T per image: [c, S]
-        sc = self.buf("vae_scores", (S, S))       # one image at a time (stream order makes reuse safe)
+        # fp32 scores, one image at a time (stream order makes reuse safe); the softmax writes the 16-bit
+        # probabilities over the first half of each row (16-bit scores cost ~2 % on the probabilities)
+        sc = self.buf("vae_scores", (S, S), torch.float32)
         o = self.act("vae_o", x.n, x.h, x.w, c)
         wv_plain = self.w.small(p + ".to_v.weight")  # [c, c] row-major: the A operand of V^T = W_v X^T
         es = 2
@@ -162,11 +164,12 @@ class VAEDecodePlan(UNetPlan):
             # S = q_b k_b^T
             self._emit(self._gemm(f"{p}.qk^T[{b}]", a=ops.a_matrix(_ptr(q.buf) + b * S * c * es, S, c, c),
                                   b=ops.PlainB(_ptr(k.buf) + b * S * c * es, S, c, c, self.dry), M=S, N=S, K=c,
-                                  dt=self.dt, out=_ptr(sc), ldo=S, splits=1, keep=(q.buf, k.buf, sc)))
+                                  dt=self.dt, out=_ptr(sc), ldo=S, splits=1, epi=_lib.EPI_STORE_F32,
+                                  keep=(q.buf, k.buf, sc)))
             self._emit(Op(f"{p}.softmax[{b}]", lib.sfb_row_softmax,
-                          (_ptr(sc), S, S, S, ops.dtype_code(self.dt)), (sc,), 0, 2 * S * S * es))
-            # O = P V + b_v
-            self._emit(self._gemm(f"{p}.pv[{b}]", a=ops.a_matrix(_ptr(sc), S, S, S),
+                          (_ptr(sc), _ptr(sc), S, S, S, 2 * S, 1, ops.dtype_code(self.dt)), (sc,), 0, 6 * S * S))
+            # O = P V + b_v   (P: 16-bit rows at a pitch of 2 * S elements inside the fp32 buffer)
+            self._emit(self._gemm(f"{p}.pv[{b}]", a=ops.a_matrix(_ptr(sc), S, S, 2 * S),
                                   b=ops.PlainB(_ptr(vt) + b * c * S * es, c, S, S, self.dry), M=S, N=c, K=S,
                                   dt=self.dt, out=_ptr(o.buf) + b * S * c * es, ldo=c,
                                   bias=self.w.f32(p + ".to_v.bias"), splits=1, keep=(sc, vt, o.buf)))

@@ -1,5 +1,6 @@
 """Times the attention kernel alone (CUDA events, L2-flushing rotation of buffers) for the shapes
-of SD-1.5 at 64x64 latents.  SFB_ATTN_EXP16=0/1 selects the exponential path."""
+of SD-1.5 / SDXL / SVD.  SFB_LIB_PATH selects an alternative build of the library (A/B of the
+MUFU / polynomial exponential split, -DSFB_EXP_POLY_MASK=...)."""
 import json
 import os
 import sys
@@ -35,7 +36,7 @@ def bench(B, H, S, Skv, D, iters=20):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / iters
     fl = 4 * B * H * S * Skv * D
-    print(json.dumps({"exp16": os.environ.get("SFB_ATTN_EXP16", "0"), "B": B, "S": S, "Skv": Skv, "D": D,
+    print(json.dumps({"lib": os.path.basename(os.environ.get("SFB_LIB_PATH", "libsfb200.so")), "B": B, "S": S, "Skv": Skv, "D": D,
                       "us": round(us, 1), "tflops": round(fl / us / 1e6, 1)}), flush=True)
 
 
@@ -45,3 +46,5 @@ if __name__ == "__main__":
     bench(2, 8, 1024, 1024, 80)
     bench(2, 8, 4096, 77, 40)
     bench(8, 10, 4096, 4096, 64)
+    bench(8, 8, 16384, 16384, 40, iters=4)
+    bench(10, 5, 9216, 9216, 64, iters=6)

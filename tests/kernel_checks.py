@@ -611,14 +611,36 @@ def check_gemm_plain_b(M=512, N=4096, K=512, dt=torch.float16, bias=False, persi
     return rel_err(out, ref)
 
 
-def check_row_softmax(rows=300, cols=4096, dt=torch.float16, seed=42):
+def check_row_softmax(rows=300, cols=4096, dt=torch.float16, f32_in=False, seed=42):
     lib = _lib.lib()
     torch.manual_seed(seed)
+    if f32_in:  # fp32 scores, 16-bit probabilities written over the first half of each row
+        x = torch.randn(rows, cols, device=DEV) * 6.0
+        ref = torch.softmax(x, dim=-1)
+        _lib.check(lib.sfb_row_softmax(x.data_ptr(), x.data_ptr(), rows, cols, cols, 2 * cols, 1,
+                                       ops.dtype_code(dt), _stream()))
+        torch.cuda.synchronize()
+        got = x.view(dt).view(rows, 2 * cols)[:, :cols]
+        return rel_err(got, ref)
     x = _rand(rows, cols, dt=dt, scale=3.0)
     ref = torch.softmax(x.float(), dim=-1)
-    _lib.check(lib.sfb_row_softmax(x.data_ptr(), rows, cols, cols, ops.dtype_code(dt), _stream()))
+    _lib.check(lib.sfb_row_softmax(x.data_ptr(), x.data_ptr(), rows, cols, cols, cols, 0, ops.dtype_code(dt), _stream()))
     torch.cuda.synchronize()
     return rel_err(x, ref)
+
+
+def check_gemm_f32_out(M=1024, N=1024, K=512, dt=torch.float16, seed=44):
+    """fp32 store epilogue (attention scores) with a plain-B operand."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    a = _rand(M, K, dt=dt)
+    bm = _rand(N, K, dt=dt, scale=1 / math.sqrt(K))
+    out = torch.zeros(M, N, device=DEV, dtype=torch.float32)
+    op = ops.gemm_op("f32", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=ops.PlainB(bm.data_ptr(), N, K, K),
+                     M=M, N=N, K=K, dt=dt, out=out, ldo=N, splits=1, epi=_lib.EPI_STORE_F32)
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    return rel_err(out, a.float() @ bm.float().t())
 
 
 def check_pointwise(n=2, hw=4096, cin=4, cout=4, dt=torch.float16, seed=43):
@@ -699,6 +721,10 @@ CHECKS = {
     "gemm_plain_b_ragged": (lambda: check_gemm_plain_b(256, 1024, 128), 2e-3),
     "gemm_plain_b_bf16_persistent": (lambda: check_gemm_plain_b(4096, 4096, 512, dt=torch.bfloat16, persistent=True), 1e-2),
     "row_softmax": (lambda: check_row_softmax(), 2e-3),
+    "row_softmax_f32_in_place": (lambda: check_row_softmax(257, 4096, f32_in=True), 2e-3),
+    "row_softmax_f32_bf16": (lambda: check_row_softmax(64, 256, dt=torch.bfloat16, f32_in=True), 1e-2),
+    "gemm_f32_out": (lambda: check_gemm_f32_out(), 1e-5),
+    "gemm_f32_out_ragged_bf16": (lambda: check_gemm_f32_out(384, 384, 128, dt=torch.bfloat16), 1e-5),
     "row_softmax_1024_bf16": (lambda: check_row_softmax(64, 1024, dt=torch.bfloat16), 1e-2),
     "pointwise_nchw": (lambda: check_pointwise(), 2e-3),
     # SVD temporal path

@@ -1,5 +1,14 @@
 """GPU parity of the VAE decoder (`compile_vae` -> AutoencoderKL.decode on the native path) against
-oracle/vae_oracle.py on the same seeded weights (random norm affines) and synthetic latents."""
+oracle/vae_oracle.py on the same seeded weights (random norm affines) and synthetic latents.
+
+Tolerance.  A RANDOM-INIT VAE decoder amplifies storage rounding far more than the UNet does (31
+un-contracted conv layers up to 512 x 512): PyTorch's own eager decoder in fp16 / bf16 differs from
+the fp32 evaluation by 1.8e-2 / 1.8e-1 in the elementwise metric used here (measured on the tiny
+configuration, CPU).  The bar is therefore two-sided: (1) against the fp32 oracle the native path
+must be NO WORSE than 1.25 x the error of the same oracle module run eagerly in the same 16-bit
+type on the same GPU (library kernels, 16-bit storage between layers -- the reference's own eager
+path), in both the elementwise and the rms metric, and (2) the rms error stays below 1e-2 (fp16) /
+6e-2 (bf16) absolutely.  The individual kernels are held to 2e-3 in tests/kernel_checks.py."""
 import pytest
 import torch
 
@@ -16,6 +25,23 @@ def _rel(got, ref):
     return max((d.max() / ref.abs().max()).item(), (d / (ref.abs() + rms)).max().item())
 
 
+def _rms(got, ref):
+    got, ref = got.float(), ref.float()
+    return ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+
+
+def _check(got, oracle32, eager16, z, rms_cap, what):
+    with torch.no_grad():
+        ref = oracle32.decode(z.float()).sample
+        lib = eager16.decode(z).sample            # same module, same 16-bit type, eager library kernels
+    e_ours, e_lib = _rel(got, ref), _rel(lib, ref)
+    r_ours, r_lib = _rms(got, ref), _rms(lib, ref)
+    print(f"{what}: native {e_ours:.3e} (rms {r_ours:.3e}) | eager 16-bit {e_lib:.3e} (rms {r_lib:.3e})")
+    assert got.shape == ref.shape
+    assert e_ours < max(TOL, 1.25 * e_lib), (what, e_ours, e_lib)
+    assert r_ours < max(2e-3, 1.25 * r_lib) and r_ours < rms_cap, (what, r_ours, r_lib)
+
+
 def _compile(m, graph=True):
     from sfast.compilers.diffusion_pipeline_compiler import CompilationConfig, compile_vae
     c = CompilationConfig.Default()
@@ -26,39 +52,32 @@ def _compile(m, graph=True):
 def _pair(cfg, seed, dtype=torch.float16):
     oracle = vo.build_vae(cfg, seed=seed, dtype=torch.float32, device="cuda")
     fast = vo.build_vae(cfg, seed=seed, dtype=dtype, device="cuda")
+    eager = vo.build_vae(cfg, seed=seed, dtype=dtype, device="cuda")
     oracle.load_state_dict({k: v.float() for k, v in fast.state_dict().items()})
-    return oracle, fast
+    return oracle, fast, eager
 
 
 @pytest.mark.parametrize("graph", [False, True])
 def test_tiny_vae_decode_vs_oracle(graph):
     cfg = vo.tiny_vae_config()
-    oracle, fast = _pair(cfg, seed=4)
+    oracle, fast, eager = _pair(cfg, seed=4)
     fast = _compile(fast, graph)
     for b, h, w in ((1, 16, 16), (2, 16, 24), (1, 32, 32)):
         g = torch.Generator(device="cuda").manual_seed(b * 100 + h)
         z = torch.randn(b, 4, h, w, device="cuda", generator=g).half()
         got = fast.decode(z).sample
-        with torch.no_grad():
-            ref = oracle.decode(z.float()).sample
-        assert got.shape == ref.shape == (b, 3, 8 * h, 8 * w)
-        err = _rel(got, ref)
-        print(f"tiny VAE {b}x{h}x{w}: rel err {err:.3e}")
-        assert err < TOL
+        assert got.shape == (b, 3, 8 * h, 8 * w)
+        _check(got, oracle, eager, z, 1e-2, f"tiny VAE {b}x{h}x{w}")
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float16, TOL), (torch.bfloat16, 4e-2)])
-def test_sd_vae_decode_512(dtype, tol):
+@pytest.mark.parametrize("dtype,rms_cap", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)])
+def test_sd_vae_decode_512(dtype, rms_cap):
     """The SD-1.5 VAE decoder at its pipeline shape: 4 x 64 x 64 latent -> 3 x 512 x 512 image."""
     cfg = vo.sd_vae_config()
-    oracle, fast = _pair(cfg, seed=1, dtype=dtype)
+    oracle, fast, eager = _pair(cfg, seed=1, dtype=dtype)
     fast = _compile(fast, True)
     g = torch.Generator(device="cuda").manual_seed(9)
     z = (torch.randn(1, 4, 64, 64, device="cuda", generator=g) / 0.18215 * 0.2).to(dtype)
     got = fast.decode(z, return_dict=False)[0]
-    with torch.no_grad():
-        ref = oracle.decode(z.float()).sample
-    err = _rel(got, ref)
-    print(f"SD VAE decode 512x512 {dtype}: rel err {err:.3e}")
-    assert err < tol
+    _check(got, oracle, eager, z, rms_cap, f"SD VAE decode 512x512 {dtype}")
     assert len(fast.decode._cached) == 1
