@@ -705,8 +705,25 @@ def measure_roofline(plan, lib, dump_path="", workload=None):
     g = fam.get("sfb_gemm", {"ms": 1e-9, "flops": 0, "n": 1, "bytes": 0})
     achieved = g["flops"] / (gemm_graph_ms / 1e3) / 1e12
     shares = {k: round(v["ms"] / total_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    # every GEMM launch against ITS OWN roofline: max(FLOPs / tensor peak, operand bytes / HBM peak) --
+    # the family mixes tensor-bound convolutions with projections whose arithmetic intensity is below
+    # the ridge (K <= 640: ~100 FLOP/B) and weight-bandwidth-bound low-resolution layers
+    by = {"tensor": [0, 0.0, 0.0], "hbm": [0, 0.0, 0.0]}
+    for op, a, b in evs:
+        if getattr(op.fn, "__name__", "") != "sfb_gemm":
+            continue
+        t_t, t_m = op.flops / (peak_tf * 1e12) * 1e6, op.bytes / (peak_bw * 1e9) * 1e6
+        k = "tensor" if t_t >= t_m else "hbm"
+        by[k][0] += 1
+        by[k][1] += max(t_t, t_m)
+        by[k][2] += a.elapsed_time(b) * 1e3
+    by_launch = {k: {"launches": v[0], "roofline_us": round(v[1], 1), "measured_us_eager_events": round(v[2], 1),
+                     "frac": round(v[1] / v[2], 4) if v[2] else None} for k, v in by.items()}
+    tot_b, tot_m = sum(v[1] for v in by.values()), sum(v[2] for v in by.values())
+    by_launch["all"] = {"roofline_us": round(tot_b, 1), "measured_us_eager_events": round(tot_m, 1),
+                        "frac": round(tot_b / tot_m, 4) if tot_m else None}
     att = fam.get("sfb_attention")
-    extra = {}
+    extra = {"by_launch_own_roofline": by_launch}
     if att:
         extra["attention_tflops"] = att["flops"] / (att["ms"] / 1e3) / 1e12
     gn = fam.get("sfb_group_norm_apply")

@@ -54,7 +54,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // FMA): one exponential per score with head_dim 40 / 64 means one MUFU op per 160 / 256 tensor FLOPs.
 // Sending a fixed fraction of every row's exponentials through this routine (kPolyMask: which of each
 // 8 consecutive scores) trades 8 extra issue slots per element for a free MUFU slot; the balance
-// point of the two pipes is ~30 %.  x <= ~8 here (lazy reference maximum).
+// point of the two pipes was estimated at ~30 %, measured lower (below).  x <= ~8 here (lazy maximum).
 __device__ __forceinline__ float poly_exp2(float x) {
     x = fmaxf(x, -125.0f);                       // 2^-125: a zero probability after rounding
     const float t = x + 12582912.0f;             // 1.5 * 2^23: round(x) lands in the low mantissa bits
@@ -64,13 +64,19 @@ __device__ __forceinline__ float poly_exp2(float x) {
     p = fmaf(p, f, 1.0f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// Measured on B200 (profiles/r02_attention_poly_exp_split.jsonl, S = 4096): the 128-key-tile kernel
+// (head_dim 40 / 80 / 160) gains 8.8 % with 1 of every 8 exponentials on the FMA pipe (119.4 -> 108.9 us
+// at head_dim 40, B = 2; 25 %: 112.1, 37.5 %: 113.5 -- the extra issue slots then cost more than the
+// freed MUFU slots); the 64-key-tile kernel (head_dim 64) LOSES with any split (596 -> 618 / 646 / 670 us):
+// with two score tiles in flight it is bound by issue slots, not by MUFU.  Hence per-kernel masks.
 #ifndef SFB_EXP_POLY_MASK
-#define SFB_EXP_POLY_MASK 0x88   // elements 3 and 7 of every 8: 25 % of the exponentials
+#define SFB_EXP_POLY_MASK 0x08   // element 3 of every 8 scores: 12.5 % of the exponentials
 #endif
-constexpr unsigned kPolyMask = SFB_EXP_POLY_MASK;
-template <int I>
+constexpr unsigned kPolyMaskV1 = SFB_EXP_POLY_MASK;  // attention_tc_kernel
+constexpr unsigned kPolyMaskV2 = 0x00;               // attention_v2_kernel
+template <int I, unsigned MASK>
 __device__ __forceinline__ float softmax_exp2(float x) {
-    if constexpr ((kPolyMask >> (I & 7)) & 1u) return poly_exp2(x);
+    if constexpr ((MASK >> (I & 7)) & 1u) return poly_exp2(x);
     else return fast_exp2(x);
 }
 
@@ -291,10 +297,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q,
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
-                pk[g].x = pack2(softmax_exp2<0>(x[0]), softmax_exp2<1>(x[1]), BF16);
-                pk[g].y = pack2(softmax_exp2<2>(x[2]), softmax_exp2<3>(x[3]), BF16);
-                pk[g].z = pack2(softmax_exp2<4>(x[4]), softmax_exp2<5>(x[5]), BF16);
-                pk[g].w = pack2(softmax_exp2<6>(x[6]), softmax_exp2<7>(x[7]), BF16);
+                pk[g].x = pack2(softmax_exp2<0, kPolyMaskV1>(x[0]), softmax_exp2<1, kPolyMaskV1>(x[1]), BF16);
+                pk[g].y = pack2(softmax_exp2<2, kPolyMaskV1>(x[2]), softmax_exp2<3, kPolyMaskV1>(x[3]), BF16);
+                pk[g].z = pack2(softmax_exp2<4, kPolyMaskV1>(x[4]), softmax_exp2<5, kPolyMaskV1>(x[5]), BF16);
+                pk[g].w = pack2(softmax_exp2<6, kPolyMaskV1>(x[6]), softmax_exp2<7, kPolyMaskV1>(x[7]), BF16);
             }
             // ... and only then wait for PV(j-1): the P buffer / O accumulator are not touched before,
             // so the previous tile's second MMA overlaps this tile's MUFU work
@@ -610,10 +616,10 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tma_q,
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sraw[g * 8 + i]), sl2, neg_m);
-                pk[g].x = pack2(softmax_exp2<0>(x[0]), softmax_exp2<1>(x[1]), BF16);
-                pk[g].y = pack2(softmax_exp2<2>(x[2]), softmax_exp2<3>(x[3]), BF16);
-                pk[g].z = pack2(softmax_exp2<4>(x[4]), softmax_exp2<5>(x[5]), BF16);
-                pk[g].w = pack2(softmax_exp2<6>(x[6]), softmax_exp2<7>(x[7]), BF16);
+                pk[g].x = pack2(softmax_exp2<0, kPolyMaskV2>(x[0]), softmax_exp2<1, kPolyMaskV2>(x[1]), BF16);
+                pk[g].y = pack2(softmax_exp2<2, kPolyMaskV2>(x[2]), softmax_exp2<3, kPolyMaskV2>(x[3]), BF16);
+                pk[g].z = pack2(softmax_exp2<4, kPolyMaskV2>(x[4]), softmax_exp2<5, kPolyMaskV2>(x[5]), BF16);
+                pk[g].w = pack2(softmax_exp2<6, kPolyMaskV2>(x[6]), softmax_exp2<7, kPolyMaskV2>(x[7]), BF16);
             }
             // probability buffer b was last read by PV(j-2)
             if (j >= 2) {
