@@ -196,6 +196,15 @@ __device__ __forceinline__ float4 dsmem_ld_f4(uint32_t addr) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
+// Split form without the release fence: orders nothing but the barrier itself.  For "the peer may
+// retire / TMEM may be freed" hand-shakes whose data hazards are already closed (tcgen05.wait::ld +
+// tcgen05 fences); a .release arrive would first drain every outstanding global store of the CTA.
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -54,8 +54,25 @@ __device__ __forceinline__ void epi_bar() {
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[80]) {
+    tmem_ld32(taddr, *reinterpret_cast<uint32_t (*)[32]>(&v[0]));
+    tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t (*)[32]>(&v[32]));
+    tmem_ld16(taddr + 64, *reinterpret_cast<uint32_t (*)[16]>(&v[64]));
+}
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[40]) {
+    tmem_ld32(taddr, *reinterpret_cast<uint32_t (*)[32]>(&v[0]));
+    tmem_ld8(taddr + 32, *reinterpret_cast<uint32_t (*)[8]>(&v[32]));
+}
 
 struct EpiArgs {
     int epi;
@@ -106,7 +123,26 @@ struct GemmArgs {
     // persistent kernel: tile grid in units of (pair of M tiles) x (pair of 160-column N tiles)
     int m_pairs, n_tiles160, n_pairs, total_tiles;
     EpiArgs e;
+#ifdef SFB_TRACE
+    unsigned long long* trace;  // [ctas][16] %globaltimer stamps (latency anatomy builds only)
+#endif
 };
+
+// Latency-anatomy instrumentation: compiled only into the -DSFB_TRACE measurement build
+// (tests/gemm_latency.py); the product library carries none of it.
+#ifdef SFB_TRACE
+__device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
+    if (a.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        a.trace[(size_t)cta * 16 + slot] = t;
+    }
+}
+#define SFB_STAMP(slot) trace_stamp(args, slot)
+#else
+#define SFB_STAMP(slot) ((void)0)
+#endif
 
 // ---------------------------------------------------------------------------------------
 // epilogue building blocks (shared by both GEMM kernels and the split-K reduction kernel)
@@ -416,6 +452,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int nkb = kb_end - kb_begin;
 
     if (threadIdx.x == 0) {
+        SFB_STAMP(0);
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int i = 0; i < STAGES; ++i) {
@@ -440,22 +477,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) SFB_STAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {
-            pdl_wait();
             const ATile at = a_tile_coords(args, m_tile);
             const int b_ntile = at.b_nbase + n_tile;
-            for (int i = 0; i < nkb; ++i) {
+            auto load_b = [&](int i) {
                 const int stage = i % STAGES;
-                const uint32_t phase = (i / STAGES) & 1;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
                 const int kb = kb_begin + i;
-                uint8_t* dA = sA + stage * L::kABytes;
                 uint8_t* dB = sB + stage * L::kBBytes;
                 // weights are pre-tiled in HBM: tile (n_tile, kb) is one contiguous 160 x 64 block
                 int b_col = 0, b_row = (b_ntile * args.nkb_total + kb) * BN + ciy * (BN / 2);
                 if (args.b_plain) { b_col = kb * BK; b_row = b_ntile * BN + ciy * (BN / 2); }
+                if (CG == 2) {
+                    // pair mode: both CTAs' bytes are counted on the LEADER's barrier
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                    tma_load_2d_pair(dB, &tma_b, &full_bar[stage], b_col, b_row);
+                } else {
+                    mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                    tma_load_2d(dB, &tma_b, &full_bar[stage], b_col, b_row);
+                }
+            };
+            // Pre-tiled weights never depend on the predecessor kernel: the first pipeline fill of
+            // W tiles is in flight before the programmatic-dependent-launch wait releases the
+            // activation loads.  (b_plain: B is an activation -> nothing is loaded early.)
+            const int npre = args.b_plain ? 0 : min(nkb, STAGES);
+            for (int i = 0; i < npre; ++i) load_b(i);
+            pdl_wait();
+            SFB_STAMP(2);
+            for (int i = 0; i < nkb; ++i) {
+                const int stage = i % STAGES;
+                const uint32_t phase = (i / STAGES) & 1;
+                if (i >= npre) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    load_b(i);
+                }
+                const int kb = kb_begin + i;
+                uint8_t* dA = sA + stage * L::kABytes;
                 int c0 = kb * BK, c1 = m_tile * BM, c2 = 0, c3 = 0;
                 if (args.a_mode != SFB_A_MATRIX) {
                     const int tap = kb / args.cpb;
@@ -467,20 +526,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     c3 = at.n0;
                 }
                 if (CG == 2) {
-                    // pair mode: both CTAs' bytes are counted on the LEADER's barrier
-                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
                     if (args.a_mode == SFB_A_MATRIX) tma_load_2d_pair(dA, &tma_a, &full_bar[stage], c0, c1);
                     else tma_load_4d_pair(dA, &tma_a, &full_bar[stage], c0, c1, c2, c3);
-                    tma_load_2d_pair(dB, &tma_b, &full_bar[stage], b_col, b_row);
                 } else {
-                    mbar_expect_tx(&full_bar[stage], L::kStageBytes);
                     if (args.a_mode == SFB_A_MATRIX) tma_load_2d(dA, &tma_a, &full_bar[stage], c0, c1);
                     else tma_load_4d(dA, &tma_a, &full_bar[stage], c0, c1, c2, c3);
-                    tma_load_2d(dB, &tma_b, &full_bar[stage], b_col, b_row);
                 }
             }
         }
         __syncwarp();
+        if (CG == 2) cluster_arrive_relaxed();
     } else if (warp == 1) {
         if (lane == 0 && leader) {
             const uint32_t idesc = umma_idesc_f16(BM * CG, BN, BF16 != 0);
@@ -489,6 +544,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
+                if (i == 0) SFB_STAMP(3);
                 const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * L::kABytes));
                 const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::kBBytes));
 #pragma unroll
@@ -506,8 +562,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             if (CG == 2) umma_commit_pair(tmem_full_bar, pair_mask);
             else umma_commit(tmem_full_bar);
+            SFB_STAMP(4);
         }
         __syncwarp();
+        if (CG == 2) cluster_arrive_relaxed();
     } else {
         pdl_wait();
         const int quarter = warp & 3;
@@ -577,11 +635,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.residual) + (size_t)mm * e.ldr + n)
                 : make_uint4(0, 0, 0, 0);
         };
+        // LEAN path (plain STORE, the common case): phase B gives every thread ONE 4-column slice
+        // (fixed n, fixed output / residual column pointers) and walks it down the rows -- no
+        // per-item divisions, conflict-free 16-byte staging reads, 8-byte global accesses that
+        // still cover whole 32-byte sectors per warp.
+        const bool rb_staged0 = e.rowbias && args.box_n <= L::kBiasSlots;
+        const bool lean = (e.epi == SFB_EPI_STORE) && !partial && !e.rowstats_out && !(e.rowbias && !rb_staged0);
+        constexpr int kLSlices = BN / 4;                       // 16-byte fp32 slices per tile row
+        constexpr int kLRows = kEpiThreads / kLSlices;         // rows covered per pass (6)
+        constexpr int kLItems = (BM + kLRows - 1) / kLRows;    // 22
+        // residual slices in flight per thread: ALL of them (issued before the accumulator is
+        // ready) where one CTA owns the SM's registers, batches of 8 under the 2-CTAs/SM cap
+        constexpr int kLBatch = STAGES > 4 ? kLItems : 8;
+        constexpr int kLSub = STAGES > 4 ? 6 : 4;              // staging rows fetched ahead per step
+        constexpr int kLBatches = (kLItems + kLBatch - 1) / kLBatch;
+        const int lgrp = et % kLSlices, lrow0 = et / kLSlices;
+        const int ln_col = ncol0 + lgrp * 4;
+        const bool lactive = lean && lrow0 < kLRows && ln_col < e.N;
+        const uint16_t* lres = reinterpret_cast<const uint16_t*>(e.residual) + ln_col;
+        uint2 lcur[kLBatch], lnxt[kLBatch];
+        auto lean_load = [&](int b, uint2 (&dst)[kLBatch]) {
+#pragma unroll
+            for (int j = 0; j < kLBatch; ++j) {
+                const int row = lrow0 + (b * kLBatch + j) * kLRows;
+                const int mm = row < BM ? sRowM[row] : -1;
+                dst[j] = mm >= 0 ? *reinterpret_cast<const uint2*>(lres + (size_t)mm * e.ldr) : make_uint2(0, 0);
+            }
+        };
         uint4 rcur[kBatch], rnxt[kBatch];
-        if (has_res) {
+        if (has_res && !lean) {
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) rcur[j] = load_res(j);
         }
+        if (has_res && lactive) lean_load(0, lcur);
         float2 ln = make_float2(0.f, 1.f);
         if (e.ln_rowstats && valid && !partial) ln = ln_row_params(e, m);
         const float* brow = sBias;
@@ -594,6 +680,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        if (et == 0) SFB_STAMP(5);
         // QKV scatter: the integer divisions of the address computation once per row / per column
         // slice (tables in the now idle stage buffers) instead of five per stored 16-byte slice
         int2* sQkvRow = reinterpret_cast<int2*>(smem + L::kQkvRowOffset);
@@ -617,7 +704,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float* srow = sStage + r * L::kStagePitch;
         constexpr int kColsPer = BN / kColSplit;             // columns converted per thread
-        constexpr int kChunk = kColSplit == 1 ? 32 : 16;     // columns per TMEM load
+        // columns per TMEM load + wait: the one-CTA-per-SM configurations have the registers to
+        // pull a thread's whole 80-column share in one go
+        constexpr int kChunk = kColSplit == 1 ? 32 : (STAGES > 4 ? 80 : 40);
+        const bool has_ln = e.ln_rowstats != nullptr;
         // accumulator chunk (already in registers) -> bias / LayerNorm fold -> fp32 staging tile
         auto stage_chunk = [&](const uint32_t* v, int c0) {
 #pragma unroll
@@ -625,13 +715,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const int cl = c0 + j * 8;  // column inside the tile
                 float f[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float acc = __uint_as_float(v[j * 8 + i]);
-                    if (!partial) {
-                        if (e.ln_rowstats) acc = ln.y * (acc - ln.x * sBias[BN + cl + i]);
-                        acc += brow[cl + i];
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
+                if (!partial) {
+                    if (has_ln) {
+                        const float4 s0 = *reinterpret_cast<const float4*>(sBias + BN + cl);
+                        const float4 s1 = *reinterpret_cast<const float4*>(sBias + BN + cl + 4);
+                        f[0] = ln.y * (f[0] - ln.x * s0.x); f[1] = ln.y * (f[1] - ln.x * s0.y);
+                        f[2] = ln.y * (f[2] - ln.x * s0.z); f[3] = ln.y * (f[3] - ln.x * s0.w);
+                        f[4] = ln.y * (f[4] - ln.x * s1.x); f[5] = ln.y * (f[5] - ln.x * s1.y);
+                        f[6] = ln.y * (f[6] - ln.x * s1.z); f[7] = ln.y * (f[7] - ln.x * s1.w);
                     }
-                    f[i] = acc;
+                    add_bias8(brow, cl, f);
                 }
                 if (rb_global && ncol0 + cl < e.N) add_bias8(rb_global, ncol0 + cl, f);
                 *reinterpret_cast<float4*>(srow + cl) = make_float4(f[0], f[1], f[2], f[3]);
@@ -639,6 +733,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         };
         constexpr int kChunks = kColsPer / kChunk;
+        static_assert(kChunks * kChunk == kColsPer, "TMEM chunking must cover the thread's columns");
 #pragma unroll 1
         for (int cb = 0; cb < kChunks; ++cb) {
             uint32_t v[kChunk];
@@ -647,7 +742,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tmem_wait_ld();
             stage_chunk(v, c0);
         }
+        // this thread is done with TMEM: its half of the end-of-kernel pair hand-shake (below)
+        tc_fence_before();
+        if (CG == 2) cluster_arrive_relaxed();
         epi_bar();
+        if (et == 0) SFB_STAMP(6);
 
         // ---- phase B
         auto load8 = [&](int row, int col, float (&f)[8]) {
@@ -655,7 +754,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const float4 b = *reinterpret_cast<const float4*>(sStage + row * L::kStagePitch + col + 4);
             f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
         };
-        if (partial) {
+        if (lean) {
+            if (lactive) {
+                uint16_t* lout = reinterpret_cast<uint16_t*>(e.out) + ln_col;
+                const float* lst = sStage + lgrp * 4;
+#pragma unroll 1
+                for (int b = 0; b < kLBatches; ++b) {
+                    if (has_res && b + 1 < kLBatches) lean_load(b + 1, lnxt);
+#pragma unroll
+                    for (int j0 = 0; j0 < kLBatch; j0 += kLSub) {
+                        // loads of kLSub rows first (row -> m, staged fp32 slice), then the math /
+                        // stores: two epilogue warps per scheduler cannot hide a dependent
+                        // LDS -> LDS -> STG chain per row
+                        int mmv[kLSub];
+                        float4 fv[kLSub];
+#pragma unroll
+                        for (int u = 0; u < kLSub; ++u) {
+                            if (j0 + u < kLBatch) {
+                                const int row = lrow0 + (b * kLBatch + j0 + u) * kLRows;
+                                const int rr = min(row, BM - 1);
+                                mmv[u] = row < BM ? sRowM[rr] : -1;
+                                fv[u] = *reinterpret_cast<const float4*>(lst + rr * L::kStagePitch);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kLSub; ++u) {
+                            if (j0 + u < kLBatch) {
+                                if (mmv[u] >= 0) {
+                                    float4 f = fv[u];
+                                    if (has_res) {
+                                        const float2 r0 = unpack2(lcur[j0 + u].x, BF16), r1 = unpack2(lcur[j0 + u].y, BF16);
+                                        f.x += r0.x; f.y += r0.y; f.z += r1.x; f.w += r1.y;
+                                    }
+                                    *reinterpret_cast<uint2*>(lout + (size_t)mmv[u] * e.ldo) =
+                                        make_uint2(pack2(f.x, f.y, BF16), pack2(f.z, f.w, BF16));
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kLBatch; ++j) lcur[j] = lnxt[j];
+                }
+            }
+        } else if (partial) {
 #pragma unroll 1
             for (int it = 0; it < kItems; ++it) {
                 const int idx = et + it * kEpiThreads;
@@ -774,14 +915,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     }
 
+    if (threadIdx.x == 64) SFB_STAMP(7);   // first epilogue thread: its stores are issued
+    if (threadIdx.x == kGemmThreads - 1) SFB_STAMP(10);  // last epilogue thread
     tc_fence_before();
-    // no CTA may exit while its pair peer can still signal its barriers / read its shared memory
-    if (CG == 2) cluster_sync_all();
+    // No CTA may exit (and TMEM may not be freed) while its pair peer can still signal its barriers,
+    // read its shared memory or read the pair's accumulator.  Every thread ARRIVED at this cluster
+    // barrier when its own part of that was over (TMA / MMA warps after their loops, epilogue
+    // threads after their last tcgen05.ld), with a relaxed arrive: a releasing one would first
+    // drain this CTA's output stores (0.7 us per launch, profiles/r02_gemm_latency_anatomy.jsonl).
+    if (CG == 2) cluster_wait();
     else __syncthreads();
+    if (threadIdx.x == 0) SFB_STAMP(8);
     if (warp == 1) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_pair<kTmemCols>(tmem_base);
         else tmem_dealloc<kTmemCols>(tmem_base);
+        if (lane == 0) SFB_STAMP(9);
     }
 }
 
@@ -801,7 +950,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // Shared memory: 4 stages x 36 KB + one 128 x 84 fp32 staging tile (80 accumulator columns per
 // pass) + tables.
 #ifndef SFB_PSTAGES
-#define SFB_PSTAGES 4
+#define SFB_PSTAGES 3   // (3 and 4 stages time the same; 3 leaves room for two epilogue staging tiles)
 #endif
 #ifndef SFB_PNH
 #define SFB_PNH 2   // 160-column accumulator halves per tile (2: 256 x 320 tiles, 1: 256 x 160)
@@ -809,6 +958,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 constexpr int kPStages = SFB_PSTAGES;
 constexpr int kPNH = SFB_PNH;
 constexpr int kPSlots = 3;
+constexpr int kPGroups = 2;                               // epilogue warp groups (one per accumulator half)
+constexpr int kPersistThreads = 64 + kPGroups * kEpiThreads;
 constexpr int kPassCols = 80;                 // accumulator columns staged per epilogue pass
 constexpr int kPStagePitch = kPassCols + 4;   // floats; +4: conflict-free float4 row writes
 struct PersistSmem {
@@ -816,14 +967,15 @@ struct PersistSmem {
     static constexpr int kBHalf = (BN / 2) * BK * 2;     // 10 KB: this CTA's 80 rows of one 160-tile
     static constexpr int kStageBytes = kABytes + kPNH * kBHalf;
     static constexpr int kStagingOffset = kPStages * kStageBytes;
-    static constexpr int kStagingBytes = BM * kPStagePitch * 4;
-    static constexpr int kBarOffset = kStagingOffset + kStagingBytes;  // 8 * (2*stages + 2*slots) + tmem slot
-    static constexpr int kBiasOffset = kBarOffset + 256;               // fp32 [4 slots][BN] + colsum [BN]
+    static constexpr int kStagingBytes = BM * kPStagePitch * 4;         // per epilogue group
+    static constexpr int kBarOffset = kStagingOffset + kPGroups * kStagingBytes;  // mbarriers + tmem slot
+    static constexpr int kBiasOffset = kBarOffset + 256;
     static constexpr int kBiasSlots = 4;
-    static constexpr int kRowMOffset = kBiasOffset + (kBiasSlots + 1) * BN * 4;   // int [128]
-    static constexpr int kQkvRowOffset = kRowMOffset + BM * 4;                    // int2 [128]
-    static constexpr int kQkvColOffset = kQkvRowOffset + BM * 8;                  // longlong2 [10]
-    static constexpr int kTotal = kQkvColOffset + (kPassCols / 8) * 16 + 1024;    // + alignment slack
+    // per epilogue group: bias [4 slots][BN] + colsum [BN] (fp32), row -> m [128] (int), QKV row table
+    // [128] (int2), QKV column table [10] (longlong2)
+    static constexpr int kTableBytes = (kBiasSlots + 1) * BN * 4 + BM * 4 + BM * 8 + (kPassCols / 8) * 16;
+    static constexpr int kTotal = kBiasOffset + kPGroups * kTableBytes + 1024;    // + alignment slack
+    static_assert(kTableBytes % 16 == 0, "table alignment");
     static_assert(kTotal <= 227 * 1024, "persistent GEMM shared memory");
 };
 
@@ -832,37 +984,23 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-        : "r"(taddr)
-        : "memory");
-}
-
 template <int BF16>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const GemmArgs args) {
     using L = PersistSmem;
-    static_assert(kEpiWarps == 8, "the persistent epilogue splits a pass between two warps per lane quarter");
+    static_assert(kEpiWarps == 8 && kPNH == kPGroups, "one 8-warp epilogue group per accumulator half");
     constexpr uint32_t kTmemCols = 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
     uint8_t* sA = smem;                                   // [stage][16 KB]
     uint8_t* sB = smem + kPStages * L::kABytes;           // [stage][half][10 KB]
     constexpr int kBStage = kPNH * L::kBHalf;
-    float* sStage = reinterpret_cast<float*>(smem + L::kStagingOffset);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
     uint64_t* empty_bar = full_bar + kPStages;
     uint64_t* tmem_full = empty_bar + kPStages;           // [slot], in both CTAs
     uint64_t* tmem_empty = tmem_full + kPSlots;           // [slot], the LEADER's copy is the one used
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kPSlots);
-    float* sBias = reinterpret_cast<float*>(smem + L::kBiasOffset);
-    float* sColsum = sBias + L::kBiasSlots * BN;
-    int* sRowM = reinterpret_cast<int*>(smem + L::kRowMOffset);
-    int2* sQkvRow = reinterpret_cast<int2*>(smem + L::kQkvRowOffset);
-    longlong2* sQkvCol = reinterpret_cast<longlong2*>(smem + L::kQkvColOffset);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -974,11 +1112,23 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     } else {
         pdl_wait();
         const EpiArgs& e = args.e;
-        const int quarter = warp & 3;
+        // Two epilogue groups of 8 warps: group g drains accumulator half g of every tile (its own
+        // staging tile, tables and named barrier), so the two halves of a tile are converted and
+        // stored concurrently -- for K <= 1280 the epilogue, not the MMA loop, bounds a tile.
+        const int grp = (warp - 2) >> 3;
+        const int gw = (warp - 2) & 7;      // warp inside the group
+        const int quarter = warp & 3;       // TMEM lane quarter this warp may touch (warp id % 4)
         const int r = quarter * 32 + lane;
-        const int et = threadIdx.x - 64;
-        const int chalf = (warp - 2) >> 2;  // which 40 of a pass's 80 columns this warp converts
+        const int et = gw * 32 + lane;      // thread index inside the group
+        const int chalf = gw >> 2;          // which 40 of a pass's 80 columns this warp converts
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* sStage = reinterpret_cast<float*>(smem + L::kStagingOffset + grp * L::kStagingBytes);
+        float* sBias = reinterpret_cast<float*>(smem + L::kBiasOffset + grp * L::kTableBytes);
+        float* sColsum = sBias + L::kBiasSlots * BN;
+        int* sRowM = reinterpret_cast<int*>(sColsum + BN);
+        int2* sQkvRow = reinterpret_cast<int2*>(sRowM + BM);
+        longlong2* sQkvCol = reinterpret_cast<longlong2*>(sQkvRow + BM);
+        auto epi_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kEpiThreads) : "memory"); };
         float* srow = sStage + r * kPStagePitch;
         constexpr int kGroups = kPassCols / 8;                    // 10 16-byte slices per row and pass
         constexpr int kItems = BM * kGroups / kEpiThreads;        // 5 per thread
@@ -1005,12 +1155,15 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             if (e.rowbias && !rb_staged)
                 rb_global = e.rowbias + (size_t)(m_tile * args.box_n + r / (args.box_h * args.img_w)) * e.ld_rowbias;
             const int brow_off = rb_staged ? (r / (args.box_h * args.img_w)) * BN : 0;
-            for (int h = 0; h < nh; ++h, ++hc) {
-                const uint32_t slot = hc % kPSlots, use = hc / kPSlots;
+            const uint32_t hc_tile = hc;
+            hc += nh;
+            if (grp < nh) {
+                const int h = grp;
+                const uint32_t slot = (hc_tile + h) % kPSlots, use = (hc_tile + h) / kPSlots;
                 const int n_tile = kPNH * np_ + h;    // 160-column tile index (inside the up-conv phase)
                 const int ncol0 = n_tile * BN;
                 // ---- per-tile / per-half tables: row -> m, bias (+ staged row bias), colsum
-                if (h == 0 && chalf == 0) {
+                if (chalf == 0) {
                     sRowM[r] = valid ? m : -1;
                     if (e.epi == SFB_EPI_QKV) sQkvRow[r] = valid ? make_int2(m / e.seq, m % e.seq) : make_int2(0, 0);
                 }
@@ -1284,13 +1437,19 @@ static int launch_persist_t(const CUtensorMap& ta, const CUtensorMap& tb, const 
     int pairs = sm_count() / 2;
     if (pairs > a.total_tiles) pairs = a.total_tiles;
     if (pairs < 1) return fail(SFB_ERR_INVALID, "sfb_gemm(persistent): no SM pair available");
-    cudaError_t err = launch_cluster_pdl(gemm_persist_kernel<BF16>, dim3(2 * pairs), dim3(kGemmThreads), dim3(2, 1, 1),
+    cudaError_t err = launch_cluster_pdl(gemm_persist_kernel<BF16>, dim3(2 * pairs), dim3(kPersistThreads), dim3(2, 1, 1),
                                          PersistSmem::kTotal, stream, ta, tb, a);
     if (err != cudaSuccess)
         return fail(SFB_ERR_CUDA, "sfb_gemm(persistent): launch: %s (%s) pairs=%d smem=%d", cudaGetErrorString(err),
                     cudaGetErrorName(err), pairs, (int)PersistSmem::kTotal);
     return check_launch("sfb_gemm");
 }
+
+#ifdef SFB_TRACE
+static thread_local unsigned long long* g_trace_next = nullptr;
+// measurement build only: the NEXT sfb_gemm call writes its per-CTA stamps to `buf` ([ctas][16] u64)
+extern "C" void sfb_trace_next_gemm(void* buf) { g_trace_next = static_cast<unsigned long long*>(buf); }
+#endif
 
 extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1373,6 +1532,10 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     } else {
         return fail(SFB_ERR_INVALID, "sfb_gemm: epilogue mode");
     }
+#ifdef SFB_TRACE
+    a.trace = g_trace_next;
+    g_trace_next = nullptr;
+#endif
     const int n_tiles = (p->N + BN - 1) / BN;
     CUtensorMap ta, tb;
     memcpy(&ta, p->tmap_a, sizeof(CUtensorMap));
@@ -1391,7 +1554,11 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     // <= one CTA per SM anyway: take the deep pipeline; otherwise the shallow one x 2 CTAs/SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     static const int force_stages = [] { const char* v = getenv("SFB_GEMM_STAGES"); return v ? atoi(v) : 0; }();
-    const bool deep = force_stages ? (force_stages == 6) : (ctas <= sm_count());
+    // The shallow configuration also lets the NEXT kernel's CTAs become resident beside this one's
+    // (programmatic dependent launch): their set-up and first weight tiles overlap this epilogue.
+    static const int deep_min_kb = [] { const char* v = getenv("SFB_GEMM_DEEP_MIN_KB"); return v ? atoi(v) : 0; }();
+    const int kb_per_cta = a.nkb_total / a.splits;
+    const bool deep = force_stages ? (force_stages == 6) : (ctas <= sm_count() && kb_per_cta >= deep_min_kb);
     int rc;
     if (p->cta_pair) {
         // CTA pairs along M (cluster 2x1, tcgen05.mma.cta_group::2): tmap_b box = 80 rows

@@ -1,6 +1,11 @@
 """Latency anatomy of one small tcgen05 GEMM launch: %globaltimer stamps from inside the kernel
-(entry / setup / first TMA / first data / MMAs issued / accumulator ready / stored / exit), taken
-on the last launch of a back-to-back chain inside a CUDA graph."""
+(entry / setup / PDL wait passed / first data / MMAs issued / accumulator ready / staged / stored /
+synced / exit), taken on the last launches of a back-to-back chain inside a CUDA graph.
+
+Needs the measurement build of the library (the product build carries no instrumentation):
+    cd stable-fast_b200/csrc && make trace        # -> sfast_b200/libsfb200_trace.so
+    SFB_LIB_PATH=stable-fast_b200/sfast_b200/libsfb200_trace.so python tests/gemm_latency.py"""
+import ctypes
 import json
 import os
 import sys
@@ -24,7 +29,10 @@ def run(M, N, K, chain=8, residual=True, conv=None, rowbias=False, distinct=Fals
     out = torch.zeros(M, N, device="cuda", dtype=dt)
     mats = [ops.Mat(x) for x in w]
     mt, nt = (M + 127) // 128, (N + 159) // 160
-    stamps = torch.zeros(chain, mt * nt, 8, dtype=torch.int64, device="cuda")
+    stamps = torch.zeros(chain, mt * nt, 16, dtype=torch.int64, device="cuda")
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    raw.sfb_trace_next_gemm.argtypes = [ctypes.c_void_p]
+    raw.sfb_trace_next_gemm.restype = None
     oplist = []
     if conv:
         n, h, wd, cin = conv
@@ -45,7 +53,6 @@ def run(M, N, K, chain=8, residual=True, conv=None, rowbias=False, distinct=Fals
             op = ops.gemm_op("g", lib, a=ops.a_matrix(a[j].data_ptr(), M, K, K), b=mats[j], M=M, N=N, K=K,
                              dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N)
             op.keep = tuple(op.keep) + (a[j],)
-        op.keep[0].debug_stamps = stamps[i].data_ptr()
         oplist.append(op)
     st = torch.cuda.current_stream()
     for op in oplist:
@@ -54,30 +61,37 @@ def run(M, N, K, chain=8, residual=True, conv=None, rowbias=False, distinct=Fals
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         s = torch.cuda.current_stream().cuda_stream
-        for op in oplist:
+        for i, op in enumerate(oplist):
+            raw.sfb_trace_next_gemm(stamps[i].data_ptr())
             op.launch(s)
     for _ in range(3):
         g.replay()
     torch.cuda.synchronize()
     t = stamps.cpu().numpy().astype("int64")
-    names = ["entry", "setup", "tma0", "data0", "mma_issued", "acc_ready", "stored", "exit"]
-    res = {"M": M, "N": N, "K": K, "ctas": mt * nt, "conv": conv, "distinct": distinct}
+    names = ["entry", "setup", "pdl_released", "data0", "mma_issued", "acc_ready", "staged", "stored_first_thread",
+             "synced", "exit", "stored_last_thread"]
+    res = {"M": M, "N": N, "K": K, "ctas": mt * nt, "conv": conv, "distinct": distinct, "residual": residual}
     for i in (chain - 2, chain - 1):
         k = t[i]
-        t0 = k[:, 0].min()
-        prev_end = t[i - 1][:, 7].max()
-        row = {"gap_prev_exit_to_first_entry_ns": int(t0 - prev_end),
-               "last_entry_ns": int(k[:, 0].max() - t0)}
-        for j, nm in enumerate(names[1:], 1):
+        k = k[k[:, 0] > 0]                      # (pair grids: every CTA stamps)
+        prev = t[i - 1]
+        prev = prev[prev[:, 0] > 0]
+        # all times relative to the PREVIOUS launch's last exit = the moment this launch's inputs exist
+        prev_end = prev[:, 9].max()
+        row = {"first_entry_vs_prev_exit_ns": int(k[:, 0].min() - prev_end)}
+        for j, nm in enumerate(names):
             v = k[:, j]
-            row[nm + "_med"] = int(sorted(v - k[:, 0])[len(v) // 2])
-        row["total_first_entry_to_last_exit_ns"] = int(k[:, 7].max() - t0)
+            v = v[v > 0]
+            if len(v):
+                row[nm + "_med"] = int(sorted(v - prev_end)[len(v) // 2])
+        row["last_exit_ns"] = int(k[:, 9].max() - prev_end)
         res[f"launch{i}"] = row
     print(json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":
     run(8192, 320, 320)
+    run(8192, 320, 320, residual=False)
     run(2048, 640, 640)
     run(512, 1280, 1280)
     run(8192, 320, 2880)

@@ -97,7 +97,10 @@ def time_op(op, reps=20, iters=5):
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else os.environ.get("SFB_LIB_PATH", "default")
+    only = os.environ.get("SFB_SHAPES")  # substring filter (profiling one shape under ncu)
     for name, kind, a in SHAPES:
+        if only and only not in name:
+            continue
         row = {"lib": os.path.basename(tag), "shape": name}
         for label, persistent in (("legacy", False), ("persistent", True)):
             try:

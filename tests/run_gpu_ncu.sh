@@ -18,4 +18,7 @@ full gn_fused gn_fused 0 1 python tests/kernel_checks.py group_norm_fused_64x64
 full gn_two_pass 'gn_stats|gn_apply' 0 2 python tests/kernel_checks.py group_norm_two_pass_big
 full temporal_attn temporal_attention 0 1 python tests/kernel_checks.py temporal_attn_25
 full geglu gemm_tc 0 1 python tests/kernel_checks.py geglu
+SFB_SHAPES="linear M32768 N320 K320" full shortk_legacy gemm_tc 0 1 python tests/gemm_shapes_bench.py
+SFB_SHAPES="geglu M32768 K320" full geglu320_legacy gemm_tc 0 1 python tests/gemm_shapes_bench.py
+SFB_SHAPES="geglu M32768 K320" full geglu320_persist gemm_persist 0 1 python tests/gemm_shapes_bench.py
 ls -la gpurun_out/*.ncu-rep | head -20

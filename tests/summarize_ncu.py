@@ -1,6 +1,7 @@
 """Summarise an `ncu --csv` launch list (gpu__time_duration.sum [+ dram__bytes_*]) per kernel family.
 
-usage: python tests/summarize_ncu.py gpurun_out/launches.csv [steps_captured [model-bB-sS]] > profiles/rNN_ncu_launch_summary.json
+usage: python tests/summarize_ncu.py gpurun_out/launches.csv [steps_captured [model-bB-sS [launches_per_step]]] > profiles/rNN_ncu_launch_summary.json
+With launches_per_step the first (cold) pass is skipped and the next `steps_captured` complete passes are kept.
 The per-launch DRAM traffic of the dominant kernel feeds bench.py's roofline.traffic.
 """
 import collections
@@ -26,6 +27,12 @@ def to_unit(v, unit):
 def main():
     rows = load(sys.argv[1])
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    if len(sys.argv) > 4:
+        lps = int(sys.argv[4])
+        order = sorted({int(r["ID"]) for r in rows})
+        keep = set(order[lps:lps * (1 + steps)])
+        assert len(keep) == lps * steps, (len(order), lps, steps)
+        rows = [r for r in rows if int(r["ID"]) in keep]
     per = collections.defaultdict(lambda: collections.defaultdict(float))
     ids = collections.defaultdict(set)
     for r in rows:
