@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 2
+#define SFB_ABI_VERSION 3
 
 typedef void* sfb_stream_t; /* cudaStream_t */
 
@@ -103,6 +103,8 @@ enum sfb_epilogue {
      * attention: 16-bit scores lose ~2 % on the probabilities).  One-tile kernel only, no split-K. */
     SFB_EPI_STORE_F32 = 3,
 };
+
+enum { SFB_ACT_NONE = 0, SFB_ACT_QUICK_GELU = 1 /* x * sigmoid(1.702 x) */, SFB_ACT_GELU = 2 /* erf form */ };
 
 typedef struct sfb_gemm_params {
     const void* tmap_a; /* host pointer to a 128-byte tensor map */
@@ -173,6 +175,10 @@ typedef struct sfb_gemm_params {
     const float* ln_colsum;    /* [N] fp32: sum_k W'[n, k] */
     float ln_eps;
     int32_t ln_dim;
+    /* element-wise activation of the SFB_EPI_STORE epilogue, applied after bias / LayerNorm fold and
+     * before the residual add (the CLIP text encoders' MLP: fc1 + quick_gelu / gelu, encoders traced by
+     * /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:93-103).  Needs splits == 1. */
+    int32_t act; /* SFB_ACT_* */
 } sfb_gemm_params;
 
 int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream);
@@ -192,6 +198,9 @@ typedef struct sfb_attn_params {
     /* 0 / 128: 128-key tiles.  64 (head_dim <= 64 only): 64-key tiles with the score tile
      * double-buffered in TMEM and the probability tile double-buffered in shared memory. */
     int32_t kv_tile;
+    /* 1: causal mask (key j attends to query i only if j <= i; seq_q == seq_kv, kv_tile 64): the text
+     * encoders' self-attention */
+    int32_t causal;
 } sfb_attn_params;
 
 int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream);
@@ -371,6 +380,22 @@ int sfb_pointwise_nchw(const void* x, const void* w, const float* bias, void* y,
 
 /* cudaMemsetAsync wrapper (graph capturable) */
 int sfb_memset(void* p, int32_t value, size_t bytes, sfb_stream_t stream);
+
+/* ---- CLIP text encoder edges (reference: text_encoder / text_encoder_2 traced + graphed by
+ * /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:93-112) ---------------- */
+
+/* out[b * seq + s, :] = tok_emb[ids[b, s], :] + pos_emb[s, :]   (16-bit tables and output, row pitch ld_out);
+ * rowstats (optional, [rows, 2] fp32): (sum, sum of squares) of each stored row, WRITTEN (not accumulated) --
+ * the statistics the first folded LayerNorm consumes.  ids: int64 [batch, seq]; ids outside [0, vocab) are an
+ * error the kernel reports by writing zeros for that row. */
+int sfb_embed_tokens(const int64_t* ids, const void* tok_emb, const void* pos_emb, void* out, float* rowstats,
+                     int32_t batch, int32_t seq, int32_t dim, int32_t vocab, int32_t ld_out, int32_t dtype,
+                     sfb_stream_t stream);
+
+/* pooled[b, :] = x[b * seq + p_b, :], p_b = first position whose id equals eos_id, or (eos_id == 2, the
+ * legacy CLIP config) the position of the largest id -- transformers' CLIPTextTransformer pooling rule. */
+int sfb_clip_pool(const int64_t* ids, const void* x, void* pooled, int32_t batch, int32_t seq, int32_t dim,
+                  int32_t ld_x, int32_t eos_id, sfb_stream_t stream);
 
 #ifdef __cplusplus
 }

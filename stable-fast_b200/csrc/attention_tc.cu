@@ -39,6 +39,7 @@ struct AttnArgs {
     int q_rows, k_rows, vt_rows;
     int dtype;
     float scale_log2;  // scale * log2(e)
+    int causal;        // v2 only: key j is visible to query i iff j <= i
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -586,7 +587,11 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tma_q,
             tc_fence_before();
             mbar_arrive(&s_free[b]);
 
-            const int n_valid = a.seq_kv - j * kTileKV2;  // >= 1; < 64 only on the last tile
+            int n_valid = a.seq_kv - j * kTileKV2;  // >= 1; < 64 only on the last tile
+            // causal (text encoders): this row sees keys 0 .. its own position.  Key 0 is visible to
+            // every row, so tile 0 always moves the running maximum off -inf; a later tile that is
+            // entirely masked for a row leaves exp2(-inf) = 0 everywhere.
+            if (a.causal) n_valid = min(n_valid, q_tile * kTileQ + r - j * kTileKV2 + 1);
             if (n_valid < kTileKV2) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
@@ -747,6 +752,9 @@ extern "C" int sfb_attention(const sfb_attn_params* p, sfb_stream_t stream_) {
     a.seq_q = p->seq_q; a.seq_kv = p->seq_kv; a.q_rows = p->q_rows; a.k_rows = p->k_rows;
     a.vt_rows = p->vt_rows; a.dtype = p->dtype;
     a.scale_log2 = p->scale * 1.4426950408889634f;
+    a.causal = p->causal ? 1 : 0;
+    if (a.causal && (p->kv_tile != 64 || p->seq_q != p->seq_kv))
+        return fail(SFB_ERR_INVALID, "sfb_attention: causal needs kv_tile 64 (head_dim <= 64) and seq_q == seq_kv");
     if (p->kv_tile == 64) {  // v2: the caller built tmap_k with a 64-row box
         switch (p->head_dim) {
             case 32: return launch_attention_v2<32, 48, 4>(p, a, stream);

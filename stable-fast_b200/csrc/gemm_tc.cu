@@ -97,7 +97,14 @@ struct EpiArgs {
     const float* ln_colsum;
     float ln_eps;
     int ln_dim;
+    int act;  // SFB_ACT_*: STORE epilogue only
 };
+
+// quick_gelu (x * sigmoid(1.702 x)) / erf gelu of the CLIP text encoders' MLP
+__device__ __forceinline__ float epi_act(float x, int act) {
+    if (act == SFB_ACT_QUICK_GELU) return __fdividef(x, 1.0f + __expf(-1.702f * x));
+    return gelu_erf_f(x);
+}
 
 // LayerNorm(x) W^T == rstd * (x W'^T - mean * colsum(W')) + (beta W^T + b), W' = W * gamma.
 // (mean, rstd) of row m from the (sum, sum of squares) its producer GEMMs accumulated.
@@ -728,6 +735,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     add_bias8(brow, cl, f);
                 }
                 if (rb_global && ncol0 + cl < e.N) add_bias8(rb_global, ncol0 + cl, f);
+                if (e.act) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = epi_act(f[i], e.act);
+                }
                 *reinterpret_cast<float4*>(srow + cl) = make_float4(f[0], f[1], f[2], f[3]);
                 *reinterpret_cast<float4*>(srow + cl + 4) = make_float4(f[4], f[5], f[6], f[7]);
             }
@@ -1511,6 +1522,11 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     e.k_rows = p->k_rows; e.vt_rows = p->vt_rows; e.vt_pitch = p->vt_pitch;
     e.rowstats_out = p->rowstats_out; e.ln_rowstats = p->ln_rowstats; e.ln_colsum = p->ln_colsum;
     e.ln_eps = p->ln_eps; e.ln_dim = p->ln_dim;
+    e.act = p->act;
+    if (p->act < SFB_ACT_NONE || p->act > SFB_ACT_GELU)
+        return fail(SFB_ERR_INVALID, "sfb_gemm: unknown activation %d", p->act);
+    if (p->act && (p->epi != SFB_EPI_STORE || p->splits > 1 || p->persistent || p->rowbias))
+        return fail(SFB_ERR_INVALID, "sfb_gemm: act needs the STORE epilogue of the one-tile kernel without split-K / row bias");
     if (p->ln_rowstats && (!p->ln_colsum || p->ln_dim <= 0 || p->rowbias))
         return fail(SFB_ERR_INVALID, "sfb_gemm: LayerNorm fold needs ln_colsum / ln_dim and no rowbias");
     if (p->rowstats_out && p->epi != SFB_EPI_STORE)

@@ -595,3 +595,107 @@ extern "C" int sfb_upsample2x(const void* x, void* y, int32_t n, int32_t h, int3
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "upsample2x: %s", cudaGetErrorString(err));
     return check_launch("sfb_upsample2x");
 }
+
+// ---------------------------------------------------------------------------------------
+// CLIP text encoder edges: token + position embedding gather (with the row statistics of the first
+// folded LayerNorm), end-of-text pooling
+// ---------------------------------------------------------------------------------------
+namespace sfb {
+
+// one warp per token row
+__global__ void __launch_bounds__(256) embed_tokens_kernel(const long long* __restrict__ ids,
+                                                           const uint16_t* __restrict__ tok,
+                                                           const uint16_t* __restrict__ pos, uint16_t* __restrict__ out,
+                                                           float* __restrict__ rowstats, int rows, int seq, int nvec,
+                                                           int vocab, int ld_out, int dtype) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const long long id = ids[row];
+    const bool ok = id >= 0 && id < vocab;
+    const int s = row % seq;
+    const uint4* t = reinterpret_cast<const uint4*>(tok + (size_t)(ok ? id : 0) * nvec * 8);
+    const uint4* p = reinterpret_cast<const uint4*>(pos + (size_t)s * nvec * 8);
+    float sum = 0.f, sq = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+        const uint4 a = t[v], b = p[v];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 fa = unpack2(aw[i], dtype), fb = unpack2(bw[i], dtype);
+            o[i] = ok ? pack2(fa.x + fb.x, fa.y + fb.y, dtype) : 0u;
+            const float2 r = unpack2(o[i], dtype);  // statistics of the values as stored
+            sum += r.x + r.y;
+            sq += r.x * r.x + r.y * r.y;
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)row * ld_out + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (rowstats) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            sq += __shfl_xor_sync(0xffffffffu, sq, d);
+        }
+        if (lane == 0) {
+            rowstats[2 * (size_t)row] = sum;
+            rowstats[2 * (size_t)row + 1] = sq;
+        }
+    }
+}
+
+// one warp per batch row: position of the first end-of-text token (or of the first maximal id), then
+// the row copy
+__global__ void __launch_bounds__(32) clip_pool_kernel(const long long* __restrict__ ids,
+                                                       const uint16_t* __restrict__ x, uint16_t* __restrict__ pooled,
+                                                       int seq, int nvec, int ld_x, int eos_id) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x, lane = threadIdx.x;
+    long long best = -1;
+    int best_pos = 0x7fffffff;
+    for (int s = lane; s < seq; s += 32) {
+        const long long id = ids[(size_t)b * seq + s];
+        const long long key = (eos_id == 2) ? id : (long long)(id == eos_id);
+        if (key > best) { best = key; best_pos = s; }  // ascending s: the first maximum of this lane
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const long long ob = __shfl_xor_sync(0xffffffffu, best, d);
+        const int op = __shfl_xor_sync(0xffffffffu, best_pos, d);
+        if (ob > best || (ob == best && op < best_pos)) { best = ob; best_pos = op; }
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * seq + best_pos) * ld_x);
+    uint4* dst = reinterpret_cast<uint4*>(pooled + (size_t)b * nvec * 8);
+    for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
+}
+
+}  // namespace sfb
+
+extern "C" int sfb_embed_tokens(const int64_t* ids, const void* tok_emb, const void* pos_emb, void* out,
+                                float* rowstats, int32_t batch, int32_t seq, int32_t dim, int32_t vocab,
+                                int32_t ld_out, int32_t dtype, sfb_stream_t stream) {
+    if (!ids || !tok_emb || !pos_emb || !out || batch <= 0 || seq <= 0 || dim <= 0 || dim % 8 || ld_out % 8 ||
+        ld_out < dim || vocab <= 0)
+        return fail(SFB_ERR_INVALID, "embed_tokens: bad argument (dim=%d ld_out=%d)", dim, ld_out);
+    const int rows = batch * seq;
+    cudaError_t err = launch_pdl(sfb::embed_tokens_kernel, dim3((rows + 7) / 8), dim3(256), 0,
+                                 static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(ids),
+                                 reinterpret_cast<const uint16_t*>(tok_emb), reinterpret_cast<const uint16_t*>(pos_emb),
+                                 reinterpret_cast<uint16_t*>(out), rowstats, rows, seq, dim / 8, vocab, ld_out, dtype);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "embed_tokens: %s", cudaGetErrorString(err));
+    return check_launch("sfb_embed_tokens");
+}
+
+extern "C" int sfb_clip_pool(const int64_t* ids, const void* x, void* pooled, int32_t batch, int32_t seq, int32_t dim,
+                             int32_t ld_x, int32_t eos_id, sfb_stream_t stream) {
+    if (!ids || !x || !pooled || batch <= 0 || seq <= 0 || dim <= 0 || dim % 8 || ld_x % 8 || ld_x < dim)
+        return fail(SFB_ERR_INVALID, "clip_pool: bad argument (dim=%d ld_x=%d)", dim, ld_x);
+    cudaError_t err = launch_pdl(sfb::clip_pool_kernel, dim3(batch), dim3(32), 0, static_cast<cudaStream_t>(stream),
+                                 reinterpret_cast<const long long*>(ids), reinterpret_cast<const uint16_t*>(x),
+                                 reinterpret_cast<uint16_t*>(pooled), seq, dim / 8, ld_x, eos_id);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "clip_pool: %s", cudaGetErrorString(err));
+    return check_launch("sfb_clip_pool");
+}

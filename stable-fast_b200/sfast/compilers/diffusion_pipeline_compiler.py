@@ -56,7 +56,31 @@ def compile(m, config):
                        '(outside the UNet hot path, see DESIGN.md)')
     if getattr(m, 'vae', None) is not None:
         m.vae = compile_vae(m.vae, config)
+    # text encoders (reference :93-112: lazy trace + CUDA graph of text_encoder / text_encoder_2)
+    for attr in ('text_encoder', 'text_encoder_2'):
+        if getattr(m, attr, None) is not None:
+            setattr(m, attr, compile_text_encoder(getattr(m, attr), config))
+    if getattr(m, 'image_encoder', None) is not None:
+        logger.warning('sfast (B200 build): image_encoder (SVD CLIP vision tower, one call per clip) '
+                       'is left on its eager path')
+    if getattr(config, 'trace_scheduler', False):
+        logger.warning('sfast (B200 build): trace_scheduler is ignored (scheduler.step stays eager)')
     return m
+
+
+def compile_text_encoder(m, config):
+    """Replace ``m.forward`` of a transformers CLIPTextModel / CLIPTextModelWithProjection with the
+    B200-native encoder (reference :93-112).  Any other encoder class, or one on a non-sm_100
+    device, is returned unchanged with a warning."""
+    from sfast_b200.runtime import compile_text_encoder_module, require_b200
+    cfg = getattr(m, 'config', None)
+    if cfg is None or not hasattr(m, 'text_model') or getattr(cfg, 'model_type', 'clip_text_model') != 'clip_text_model':
+        logger.warning('sfast (B200 build): %s is not a CLIP text model; left on its eager path', type(m).__name__)
+        return m
+    device = m.device if hasattr(m, 'device') else torch.device(
+        'cuda' if torch.cuda.is_available() else 'cpu')
+    require_b200(torch.device(device))
+    return compile_text_encoder_module(m, enable_cuda_graph=bool(config.enable_cuda_graph))
 
 
 def compile_unet(m, config):

@@ -14,6 +14,7 @@ SFB_F16, SFB_BF16 = 0, 1
 A_MATRIX, A_CONV3X3, A_UPCONV2X, A_CONV3X1 = 0, 1, 2, 3
 ROW_IDX_DIV_MOD, ROW_IDX_TEMPORAL_CTX = 0, 1
 EPI_STORE, EPI_GEGLU, EPI_QKV, EPI_STORE_F32 = 0, 1, 2, 3
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU = 0, 1, 2
 
 
 class GemmParams(C.Structure):
@@ -35,7 +36,7 @@ class GemmParams(C.Structure):
         ("k_rows", C.c_int32), ("vt_rows", C.c_int32), ("vt_pitch", C.c_int32),
         ("cta_pair", C.c_int32), ("persistent", C.c_int32), ("b_plain", C.c_int32),
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
-        ("ln_eps", C.c_float), ("ln_dim", C.c_int32),
+        ("ln_eps", C.c_float), ("ln_dim", C.c_int32), ("act", C.c_int32),
     ]
 
 
@@ -46,7 +47,7 @@ class AttnParams(C.Structure):
         ("batch", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
         ("seq_q", C.c_int32), ("seq_kv", C.c_int32),
         ("q_rows", C.c_int32), ("k_rows", C.c_int32), ("vt_rows", C.c_int32),
-        ("dtype", C.c_int32), ("scale", C.c_float), ("kv_tile", C.c_int32),
+        ("dtype", C.c_int32), ("scale", C.c_float), ("kv_tile", C.c_int32), ("causal", C.c_int32),
     ]
 
 
@@ -137,6 +138,8 @@ SYMBOLS = {
     "sfb_row_softmax": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_pointwise_nchw": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_memset": (C.c_int, [_VP, _I32, C.c_size_t, _VP]),
+    "sfb_embed_tokens": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_clip_pool": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
 }
 
 _lib = None
@@ -160,7 +163,7 @@ def lib():
             fn = getattr(h, name)
             fn.restype = res
             fn.argtypes = args
-        if h.sfb_abi_version() != 2:
+        if h.sfb_abi_version() != 3:
             raise SfbError("libsfb200.so ABI version mismatch")
         _lib = h
     return _lib

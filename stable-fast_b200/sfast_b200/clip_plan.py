@@ -1,0 +1,210 @@
+"""Launch schedule of the CLIP text encoders (transformers ``CLIPTextModel`` /
+``CLIPTextModelWithProjection``), the modules the reference traces and graphs around the UNet
+(/root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:93-112: ``text_encoder`` of SD-1.5,
+``text_encoder`` + ``text_encoder_2`` of SDXL).
+
+Same kernel families as the UNet's transformer blocks, on 77-token rows:
+
+  ids -> token + position embedding (one gather kernel, which also writes the row statistics of the
+         first LayerNorm)
+  per layer:  LayerNorm1 folded into the fused QKV projection (tcgen05 GEMM, QKV-scatter epilogue)
+              -> causal flash attention (64-key tiles) -> out_proj + residual (+ row statistics)
+              -> LayerNorm2 folded into fc1 + quick_gelu / gelu (GEMM epilogue activation)
+              -> fc2 + residual (+ row statistics)
+  final LayerNorm (stand-alone kernel), end-of-text pooling (gather kernel), text projection.
+
+Every layer's output lives in its own buffer: ``output_hidden_states=True`` (SDXL reads the penultimate
+layer, clip_skip reads others) returns views of them at no extra cost.
+"""
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, ops
+from .ops import Act, EPI_QKV, Op, _ptr
+from .plan import UNetPlan, _WsToken, _round_up
+from .unet_spec import cfg_get
+
+_ACTS = {"quick_gelu": _lib.ACT_QUICK_GELU, "gelu": _lib.ACT_GELU}
+
+
+@dataclass
+class ClipTextSpec:
+    vocab_size: int
+    hidden: int
+    intermediate: int
+    layers: int
+    heads: int
+    max_positions: int
+    act: str
+    eps: float
+    eos_token_id: int
+    projection_dim: int = 0  # > 0: CLIPTextModelWithProjection (text_projection, no bias)
+    groups: int = 32         # (unused: lets the UNet plan's helpers be shared)
+
+    @property
+    def temporal(self):
+        return False
+
+    @property
+    def head_dim(self):
+        return self.hidden // self.heads
+
+    def all_resnets(self):
+        return []
+
+
+def clip_text_spec_from_config(cfg, with_projection=False) -> ClipTextSpec:
+    act = cfg_get(cfg, "hidden_act", "quick_gelu")
+    if act not in _ACTS:
+        raise NotImplementedError(f"CLIP text encoder hidden_act={act!r} is not supported by the B200 path")
+    hidden, heads = cfg_get(cfg, "hidden_size"), cfg_get(cfg, "num_attention_heads")
+    if hidden % heads or hidden // heads not in (32, 64):
+        raise NotImplementedError(f"CLIP text encoder head_dim {hidden / heads} (causal attention kernel: 32 / 64)")
+    if hidden % 64 or cfg_get(cfg, "intermediate_size") % 64:
+        raise NotImplementedError("CLIP text encoder widths must be multiples of 64")
+    return ClipTextSpec(vocab_size=cfg_get(cfg, "vocab_size"), hidden=hidden,
+                        intermediate=cfg_get(cfg, "intermediate_size"), layers=cfg_get(cfg, "num_hidden_layers"),
+                        heads=heads, max_positions=cfg_get(cfg, "max_position_embeddings", 77), act=act,
+                        eps=float(cfg_get(cfg, "layer_norm_eps", 1e-5)), eos_token_id=cfg_get(cfg, "eos_token_id", 2),
+                        projection_dim=cfg_get(cfg, "projection_dim", 0) if with_projection else 0)
+
+
+def clip_text_param_shapes(spec: ClipTextSpec):
+    """{transformers parameter name: shape} of CLIPTextModel(WithProjection)."""
+    out, c, i = {}, spec.hidden, spec.intermediate
+    out["text_model.embeddings.token_embedding.weight"] = (spec.vocab_size, c)
+    out["text_model.embeddings.position_embedding.weight"] = (spec.max_positions, c)
+    for l in range(spec.layers):
+        p = f"text_model.encoder.layers.{l}"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            out[f"{p}.self_attn.{n}.weight"], out[f"{p}.self_attn.{n}.bias"] = (c, c), (c,)
+        for n in ("layer_norm1", "layer_norm2"):
+            out[f"{p}.{n}.weight"], out[f"{p}.{n}.bias"] = (c,), (c,)
+        out[f"{p}.mlp.fc1.weight"], out[f"{p}.mlp.fc1.bias"] = (i, c), (i,)
+        out[f"{p}.mlp.fc2.weight"], out[f"{p}.mlp.fc2.bias"] = (c, i), (c,)
+    out["text_model.final_layer_norm.weight"] = out["text_model.final_layer_norm.bias"] = (c,)
+    if spec.projection_dim:
+        out["text_projection.weight"] = (spec.projection_dim, c)
+    return out
+
+
+def random_clip_state_dict(spec: ClipTextSpec, dtype, device, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    for name, shape in clip_text_param_shapes(spec).items():
+        if "layer_norm" in name:
+            v = (1.0 + 0.2 * torch.randn(shape, generator=g)) if name.endswith(".weight") else 0.2 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            v = 0.05 * torch.randn(shape, generator=g)
+        elif "embedding" in name:
+            v = 0.05 * torch.randn(shape, generator=g)
+        else:
+            v = torch.randn(shape, generator=g) / (shape[-1] ** 0.5)
+        sd[name] = v.to(device=device, dtype=dtype)
+    return sd
+
+
+class ClipTextPlan(UNetPlan):
+    """Static launch schedule of one text-encoder forward for a fixed (batch, sequence length)."""
+
+    def __init__(self, weights, batch, seq):  # noqa: super().__init__ is UNet-specific
+        self.controlnet, self.ctrl_in = False, []
+        self.w, self.spec = weights, weights.spec
+        self.dt, self.dev, self.dry = weights.dtype, weights.device, weights.dry
+        self.lib = None if self.dry else _lib.lib()
+        self.B, self.S, self.H, self.W, self.ctx_len = batch, seq, 1, seq, 0
+        if seq > self.spec.max_positions:
+            raise ValueError(f"sequence length {seq} exceeds max_position_embeddings {self.spec.max_positions}")
+        self.ops, self.side_ops = [], []
+        self._side_stream, self._pending, self._gn_ws_patches, self._joined = None, None, [], True
+        self._bufs, self._gn_count = {}, 0
+        spec, rows = self.spec, batch * seq
+        self.ids_in = self._alloc((batch, seq), torch.int64)
+        self.gn_stats = self._alloc((1, 4), torch.float32)
+        # row statistics of every folded LayerNorm: 2 per layer + the embedding's
+        self.ln_arena = self._alloc(((2 * spec.layers + 1) * rows * 2,), torch.float32)
+        self._ln_used, self._ln_slots = 0, []
+        self.ws, self._ws_need = None, 0
+        self.hidden = []       # [layers + 1] activations: embedding output, then every layer's output
+        self.last_hidden_state = None
+        self.pooled = None
+        self.text_embeds = None
+        self._build()
+        assert self._ln_used <= self.ln_arena.numel()
+
+    def _build(self):
+        spec, B, S, lib = self.spec, self.B, self.S, self.lib_or_dry()
+        C, H, D, I = spec.hidden, spec.heads, spec.head_dim, spec.intermediate
+        rows = B * S
+        self._ws_token = _WsToken()
+        self._emit(Op("ln_stats.zero", lib.sfb_memset, (_ptr(self.ln_arena), 0, self.ln_arena.numel() * 4),
+                      (self.ln_arena,)))
+        hs = self.act("clip_h0", B, 1, S, C)
+        st = self._ln_view(self.ln_slot(rows))
+        tok = self.w.small("text_model.embeddings.token_embedding.weight")
+        pos = self.w.small("text_model.embeddings.position_embedding.weight")
+        self._emit(Op("embeddings", lib.sfb_embed_tokens,
+                      (_ptr(self.ids_in), _ptr(tok), _ptr(pos), hs.ptr, _ptr(st), B, S, C, spec.vocab_size, hs.ld,
+                       ops.dtype_code(self.dt)), (self.ids_in, tok, pos, hs.buf, st), 0, 4 * rows * C))
+        self.hidden.append(hs)
+        dv = _round_up(D + 1, 16)
+        q_pitch, vt_pitch = _round_up(D, 64), _round_up(S, 64)
+        q = self.buf("clip_q", (B * H * S, q_pitch))
+        k = self.buf("clip_k", (B * H * S, q_pitch))
+        vt = self.buf("clip_vt", (B * H * dv, vt_pitch))
+        if not self.dry:
+            vt.view(B * H, dv, vt_pitch)[:, D, :] = 1.0  # the ones row: softmax denominators on the tensor core
+        qkv = dict(q=q, k=k, vt=vt, heads=H, head_dim=D, q_pitch=q_pitch, q_rows=S, k_rows=S, vt_rows=dv,
+                   vt_pitch=vt_pitch, which_base=0, seq=S)
+        for l in range(spec.layers):
+            p = f"text_model.encoder.layers.{l}"
+            a = p + ".self_attn"
+            wm, bias, colsum = self.w.ln_matrix(
+                [f"{a}.q_proj.weight", f"{a}.k_proj.weight", f"{a}.v_proj.weight"], p + ".layer_norm1",
+                bias_names=[f"{a}.q_proj.bias", f"{a}.k_proj.bias", f"{a}.v_proj.bias"])
+            self._emit(self._gemm(a + ".qkv", a=self._a_matrix(hs), b=wm, M=rows, N=wm.n, K=C, dt=self.dt,
+                                  epi=EPI_QKV, bias=bias, qkv=qkv, splits=1,
+                                  ln=dict(rowstats=st, colsum=colsum, eps=spec.eps, dim=C),
+                                  keep=(hs.buf, wm, colsum)))
+            ao = self.act("clip_attn_out", B, 1, S, C)
+            self._emit(ops.attention_op(a + ".core", lib, q=q, k=k, vt=vt, out=ao.buf, batch=B, heads=H,
+                                        head_dim=D, seq_q=S, seq_kv=S, q_rows=S, k_rows=S, vt_rows=dv,
+                                        q_pitch=q_pitch, vt_pitch=vt_pitch, dt=self.dt, dry=self.dry, kv_tile=64,
+                                        causal=True))
+            mid = self.act("clip_mid", B, 1, S, C)
+            st2 = self._ln_view(self.ln_slot(rows))
+            self.linear(a + ".out_proj", ao, self.w.matrix(f"{a}.out_proj.weight"), self.w.f32(f"{a}.out_proj.bias"),
+                        mid, residual=hs, rowstats_out=st2, splits=1)
+            w1, b1, cs1 = self.w.ln_matrix([p + ".mlp.fc1.weight"], p + ".layer_norm2",
+                                           bias_names=[p + ".mlp.fc1.bias"])
+            ff = self.act("clip_ff", B, 1, S, I)
+            self._emit(self._gemm(p + ".mlp.fc1", a=self._a_matrix(mid), b=w1, M=rows, N=I, K=C, dt=self.dt,
+                                  out=ff.ptr, ldo=ff.ld, bias=b1, splits=1, act=_ACTS[spec.act],
+                                  ln=dict(rowstats=st2, colsum=cs1, eps=spec.eps, dim=C),
+                                  keep=(mid.buf, ff.buf, w1, cs1)))
+            nxt = self.act(f"clip_h{l + 1}", B, 1, S, C)
+            st = self._ln_view(self.ln_slot(rows)) if l + 1 < spec.layers else None
+            self.linear(p + ".mlp.fc2", ff, self.w.matrix(p + ".mlp.fc2.weight"), self.w.f32(p + ".mlp.fc2.bias"),
+                        nxt, residual=mid, rowstats_out=st, splits=1)
+            hs = nxt
+            self.hidden.append(hs)
+        out = self.act("clip_last", B, 1, S, C)
+        self._emit(ops.ln_op("final_layer_norm", lib, x=hs.buf, y=out.buf, rows=rows, c=C,
+                             gamma=self.w.f32("text_model.final_layer_norm.weight"),
+                             beta=self.w.f32("text_model.final_layer_norm.bias"), eps=spec.eps, dt=self.dt))
+        self.last_hidden_state = out.buf.view(B, S, C) if not self.dry else out.buf
+        self.pooled = self.buf("clip_pooled", (B, C))
+        self._emit(Op("pool(eos)", lib.sfb_clip_pool,
+                      (_ptr(self.ids_in), out.ptr, _ptr(self.pooled), B, S, C, out.ld, spec.eos_token_id),
+                      (self.ids_in, out.buf, self.pooled)))
+        if spec.projection_dim:
+            self.text_embeds = self.buf("clip_text_embeds", (B, spec.projection_dim))
+            self._emit(ops.small_linear_op("text_projection", lib, x=self.pooled,
+                                           w=self.w.small("text_projection.weight"), bias=None, batch=B,
+                                           n=spec.projection_dim, k=C, dt=self.dt, y16=self.text_embeds))
+        self._ws_token.finalize(self)
+
+    def hidden_states(self):
+        """Tuple of [B, S, C] views: embedding output, then each encoder layer's output."""
+        return tuple(h.buf.view(self.B, self.S, self.spec.hidden) for h in self.hidden)

@@ -177,7 +177,7 @@ def _a_map(a, dry):
 def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, out=None, ldo=0,
             bias=None, rowbias=None, rows_per_img=1, ld_rowbias=0, residual=None, ldr=0,
             epi=EPI_STORE, geglu_n_out=0, conv=None, qkv=None, ws=None, splits=None, keep=(),
-            rowstats_out=None, ln=None, dry=False, cta_pair=None, persistent=None):
+            rowstats_out=None, ln=None, dry=False, cta_pair=None, persistent=None, act=0):
     """Either pass ready-made maps (`a_map`, `b_map`) or operand descriptors (`a` from
     a_matrix()/a_conv(), `b` a Mat), in which case CTA pairs (cta_group::2) are used whenever the
     number of M tiles is even, and the persistent 256 x 320 kernel when the launch is large enough
@@ -224,7 +224,8 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         p.ws = _ptr(ws) if not hasattr(ws, "finalize") else 0
     if persistent is None:
         persistent = PERSIST == "1" or (PERSIST == "auto" and m_tiles * n_tiles >= PERSIST_MIN_CTAS)
-    p.persistent = 1 if (persistent and p.cta_pair and splits == 1 and epi != _lib.EPI_STORE_F32) else 0
+    p.persistent = 1 if (persistent and p.cta_pair and splits == 1 and epi != _lib.EPI_STORE_F32 and not act) else 0
+    p.act = act
     p.epi = epi
     p.out = _ptr(out)
     p.ldo = ldo
@@ -267,7 +268,7 @@ def attention_kv_tile(head_dim):
 
 
 def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq_kv, q_rows, k_rows,
-                 vt_rows, q_pitch, vt_pitch, dt, dry=False, kv_tile=None):
+                 vt_rows, q_pitch, vt_pitch, dt, dry=False, kv_tile=None, causal=False):
     bh = batch * heads
     # v2 kernel (64-key tiles, double-buffered score / probability tiles) for head_dim <= 64
     if kv_tile is None:
@@ -284,6 +285,7 @@ def attention_op(name, lib, *, q, k, vt, out, batch, heads, head_dim, seq_q, seq
     p.dtype = dtype_code(dt)
     p.scale = 1.0 / math.sqrt(head_dim)
     p.kv_tile = kv_tile
+    p.causal = 1 if causal else 0
     flops = 4 * batch * heads * seq_q * seq_kv * head_dim
     nbytes = 2 * bh * (2 * seq_q + 2 * seq_kv) * head_dim
     return Op(name, lib.sfb_attention, (C.byref(p),), (p, tq, tk, tv, q, k, vt, out), flops, nbytes)

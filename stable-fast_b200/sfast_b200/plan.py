@@ -143,15 +143,24 @@ class PackedWeights:
             return self._mat(w.to(device=self.device, dtype=self.dtype).contiguous())
         return self._get(("cat",) + tuple(names), build)
 
-    def ln_matrix(self, names, ln_prefix):
-        """cat(names) with LayerNorm `ln_prefix` folded in: (Mat, bias', colsum)."""
+    def ln_matrix(self, names, ln_prefix, bias_names=None, row_scale=None):
+        """cat(names) with LayerNorm `ln_prefix` folded in: (Mat, bias', colsum).  `bias_names`: the
+        linear layers' own biases (CLIP projections have them, the UNet's attention projections do
+        not); `row_scale`: per-matrix constants folded into weight and bias (CLIP scales q by
+        head_dim ** -0.5 before the scores)."""
         def build():
-            w = torch.cat([self._raw(n) for n in names], 0).to(self.device)
+            ws = [self._raw(n).to(self.device).float() for n in names]
+            bs = None if bias_names is None else [self._raw(n).to(self.device).float() for n in bias_names]
+            if row_scale is not None:
+                ws = [w * s for w, s in zip(ws, row_scale)]
+                if bs is not None:
+                    bs = [b * s for b, s in zip(bs, row_scale)]
             wp, bias, colsum = ops.fold_layer_norm(
-                w, None, self._raw(ln_prefix + ".weight").to(self.device),
+                torch.cat(ws, 0), None if bs is None else torch.cat(bs, 0),
+                self._raw(ln_prefix + ".weight").to(self.device),
                 self._raw(ln_prefix + ".bias").to(self.device), self.dtype)
             return (self._mat(wp.contiguous()), bias, colsum)
-        return self._get(("lnmat", ln_prefix) + tuple(names), build)
+        return self._get(("lnmat", ln_prefix, tuple(bias_names or ()), tuple(row_scale or ())) + tuple(names), build)
 
     def ln_geglu(self, prefix, ln_prefix):
         def build():

@@ -15,7 +15,7 @@ import torch
 
 from .plan import PackedWeights, UNetPlan
 from .svd_plan import SVDPlan
-from .unet_spec import spec_from_config
+from .unet_spec import cfg_get, spec_from_config
 
 logger = logging.getLogger(__name__)
 
@@ -320,6 +320,129 @@ def compile_vae_module(m, enable_cuda_graph=True):
     decode._cached = compiled._cached
     decode._compiled = compiled
     m.decode = decode
+    return m
+
+
+class CompiledTextEncoder:
+    """transformers ``CLIPTextModel`` / ``CLIPTextModelWithProjection`` forward on the native path: the
+    text encoders the reference traces and graphs
+    (/root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:93-112).  One plan + CUDA graph
+    per (batch, sequence length); outputs are fresh tensors."""
+
+    def __init__(self, config, state_dict_fn, eager_forward, with_projection, enable_cuda_graph=True):
+        from .clip_plan import clip_text_spec_from_config
+        self.spec = clip_text_spec_from_config(config, with_projection)
+        self._state_dict_fn, self._eager = state_dict_fn, eager_forward
+        self.with_projection = with_projection
+        self.enable_cuda_graph = enable_cuda_graph
+        self._weights, self._param_refs, self._param_versions = None, None, None
+        self._cached = {}
+        self._lock = threading.Lock()
+        self._warned = False
+        rd = cfg_get(config, "return_dict", None)
+        self._return_dict_default = True if rd is None else bool(rd)
+
+    def _route_eager(self, why, args, kwargs):
+        if not self._warned:
+            logger.warning("sfast (B200 build): text encoder call left on the module's eager path (%s)", why)
+            self._warned = True
+        return self._eager(*args, **kwargs)
+
+    def __call__(self, input_ids=None, attention_mask=None, position_ids=None, output_attentions=None,
+                 output_hidden_states=None, return_dict=None, **kwargs):
+        from .clip_plan import ClipTextPlan
+        call = dict(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                    output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+                    return_dict=return_dict, **kwargs)
+        call = {k: v for k, v in call.items() if v is not None}
+        if input_ids is None:
+            raise ValueError("You have to specify input_ids")
+        if attention_mask is not None or position_ids is not None or output_attentions or kwargs:
+            return self._route_eager("attention_mask / position_ids / output_attentions / extra kwargs", (), call)
+        sd = None
+        if self._weights is None:
+            sd = self._state_dict_fn()
+            wdt = sd["text_model.embeddings.token_embedding.weight"].dtype
+            if wdt not in (torch.float16, torch.bfloat16):
+                return self._route_eager(f"{wdt} weights: the native encoder computes in fp16 / bf16", (), call)
+        ids = input_ids.view(-1, input_ids.shape[-1])
+        require_b200(ids.device)
+        B, S = ids.shape
+        with self._lock, torch.cuda.device(ids.device):
+            if self._weights is None:
+                wdt = sd["text_model.embeddings.token_embedding.weight"].dtype
+                self._weights = PackedWeights(self.spec, sd, wdt, ids.device)
+                self._param_refs = [t for t in sd.values() if torch.is_tensor(t)]
+                self._param_versions = [t._version for t in self._param_refs]
+            elif [t._version for t in self._param_refs] != self._param_versions:
+                sd = self._state_dict_fn()
+                torch.cuda.current_stream().synchronize()
+                self._weights.refresh(sd)
+                self._param_refs = [t for t in sd.values() if torch.is_tensor(t)]
+                self._param_versions = [t._version for t in self._param_refs]
+            key = (B, S, ids.device.index)
+            gp = self._cached.get(key)
+            if gp is None:
+                gp = _GraphedPlan(ClipTextPlan(self._weights, B, S), self.enable_cuda_graph)
+                self._cached[key] = gp
+            plan = gp.plan
+            plan.ids_in.copy_(ids, non_blocking=True)
+            gp.step()
+            last = plan.last_hidden_state.clone()
+            pooled = plan.pooled.clone()
+            embeds = plan.text_embeds.clone() if self.with_projection else None
+            hidden = tuple(h.clone() for h in plan.hidden_states()) if output_hidden_states else None
+        if return_dict is None:
+            return_dict = self._return_dict_default
+        if self.with_projection:
+            if not return_dict:
+                return tuple(v for v in (embeds, last, hidden) if v is not None)
+            return _clip_output("CLIPTextModelOutput", text_embeds=embeds, last_hidden_state=last,
+                                hidden_states=hidden)
+        if not return_dict:
+            return tuple(v for v in (last, pooled, hidden) if v is not None)
+        return _clip_output("BaseModelOutputWithPooling", last_hidden_state=last, pooler_output=pooled,
+                            hidden_states=hidden)
+
+
+class _PlainOutput(dict):
+    """Stand-in for transformers' ModelOutput when transformers is not importable: attribute, key and
+    integer access over the non-None fields, like the real class."""
+
+    def __init__(self, **kw):
+        super().__init__({k: v for k, v in kw.items() if v is not None})
+        self.__dict__.update(kw)
+
+    def __getitem__(self, k):
+        return tuple(self.values())[k] if isinstance(k, (int, slice)) else super().__getitem__(k)
+
+
+def _clip_output(kind, **fields):
+    try:
+        if kind == "CLIPTextModelOutput":
+            from transformers.models.clip.modeling_clip import CLIPTextModelOutput as cls
+        else:
+            from transformers.modeling_outputs import BaseModelOutputWithPooling as cls
+        return cls(**fields)
+    except Exception:  # noqa: BLE001
+        return _PlainOutput(**fields)
+
+
+def compile_text_encoder_module(m, enable_cuda_graph=True):
+    """Replace ``m.forward`` of a CLIPTextModel / CLIPTextModelWithProjection (same module object)."""
+    with_projection = hasattr(m, "text_projection")
+    eager = m.forward
+    compiled = CompiledTextEncoder(m.config, m.state_dict, eager, with_projection, enable_cuda_graph)
+
+    def forward(*args, **kwargs):
+        if args:
+            kwargs = dict(zip(("input_ids", "attention_mask", "position_ids"), args), **kwargs)
+        return compiled(**kwargs)
+
+    forward.__self__ = m
+    forward._cached = compiled._cached
+    forward._compiled = compiled
+    m.forward = forward
     return m
 
 

@@ -52,7 +52,7 @@ def _rand(*shape, dt=torch.float16, scale=1.0, seed=None):
 
 # ------------------------------------------------------------------------------------------
 def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, residual=True, seed=0,
-               pair=None, persistent=False):
+               pair=None, persistent=False, act=0):
     lib = _lib.lib()
     a = _rand(M, K, dt=dt, seed=seed)
     w = _rand(N, K, dt=dt, scale=1 / math.sqrt(K))
@@ -62,13 +62,17 @@ def check_gemm(M=300, N=320, K=320, dt=torch.float16, splits=1, bias=True, resid
     ws = torch.empty(max(splits, 1) * M * N, device=DEV, dtype=torch.float32)
     op = ops.gemm_op("gemm", lib, a=ops.a_matrix(a.data_ptr(), M, K, K), b=ops.Mat(w), M=M, N=N, K=K,
                      dt=dt, out=out, ldo=N, bias=b, residual=r, ldr=N, ws=ws, splits=splits,
-                     cta_pair=pair, persistent=persistent)
+                     cta_pair=pair, persistent=persistent, act=act)
     assert op.keep[0].persistent == int(bool(persistent)), "persistent kernel was not selected"
     op.launch(_stream())
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t()
     if bias:
         ref = ref + b
+    if act == _lib.ACT_QUICK_GELU:   # CLIP: x * sigmoid(1.702 x), before the residual
+        ref = ref * torch.sigmoid(1.702 * ref)
+    elif act == _lib.ACT_GELU:
+        ref = F.gelu(ref)
     if residual:
         ref = ref + r.float()
     return rel_err(out, ref)
@@ -171,7 +175,7 @@ def _attn_buffers(B, H, S, Skv, D, dt):
     return q, k, vt, dv, q_pitch, vt_pitch
 
 
-def check_attention(B=2, H=8, S=1024, Skv=None, D=40, dt=torch.float16, seed=3, kv_tile=None):
+def check_attention(B=2, H=8, S=1024, Skv=None, D=40, dt=torch.float16, seed=3, kv_tile=None, causal=False):
     lib = _lib.lib()
     Skv = Skv or S
     torch.manual_seed(seed)
@@ -185,14 +189,57 @@ def check_attention(B=2, H=8, S=1024, Skv=None, D=40, dt=torch.float16, seed=3, 
     out = torch.zeros(B, S, H * D, device=DEV, dtype=dt)
     op = ops.attention_op("attn", lib, q=q, k=k, vt=vt, out=out, batch=B, heads=H, head_dim=D,
                           seq_q=S, seq_kv=Skv, q_rows=S, k_rows=Skv, vt_rows=dv, q_pitch=q_pitch,
-                          vt_pitch=vt_pitch, dt=dt, kv_tile=kv_tile)
+                          vt_pitch=vt_pitch, dt=dt, kv_tile=kv_tile, causal=causal)
     if kv_tile is not None:
         assert op.keep[0].kv_tile == kv_tile
     op.launch(_stream())
     torch.cuda.synchronize()
-    ref = F.scaled_dot_product_attention(qr.float(), kr.float(), vr.float())
+    ref = F.scaled_dot_product_attention(qr.float(), kr.float(), vr.float(), is_causal=causal)
     ref = ref.transpose(1, 2).reshape(B, S, H * D)
     return rel_err(out, ref)
+
+
+
+def check_embed_tokens(B=3, S=77, C=768, V=1000, dt=torch.float16, seed=11):
+    """Token + position embedding gather and the row statistics it hands to the first folded LayerNorm."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    tok, pos = _rand(V, C, dt=dt), _rand(S, C, dt=dt)
+    ids = torch.randint(0, V, (B, S), device=DEV)
+    out = torch.zeros(B * S, C, device=DEV, dtype=dt)
+    stats = torch.full((B * S, 2), 7.0, device=DEV)  # written, not accumulated
+    _lib.check(lib.sfb_embed_tokens(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), out.data_ptr(), stats.data_ptr(),
+                                    B, S, C, V, C, ops.dtype_code(dt), _stream()), "embed")
+    torch.cuda.synchronize()
+    ref = (tok[ids].float() + pos[None].float()).reshape(B * S, C)
+    e = rel_err(out, ref)
+    o = out.float()
+    e_s = float((stats[:, 0] - o.sum(1)).abs().max() / o.sum(1).abs().max())
+    e_q = float((stats[:, 1] - (o * o).sum(1)).abs().max() / (o * o).sum(1).abs().max())
+    return max(e, e_s, e_q)
+
+
+def check_clip_pool(eos_id, B=5, S=77, C=768, dt=torch.float16, seed=12):
+    """End-of-text pooling: first eos position (or, eos_id == 2, the first maximal id) per row."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    x = _rand(B * S, C, dt=dt)
+    ids = torch.randint(3, 1000, (B, S), device=DEV)
+    eos_tok = 49407 if eos_id == 2 else eos_id
+    for b in range(B):   # eos somewhere, then padded with eos (SD pads with the eos token)
+        p = 5 + 13 * b
+        ids[b, p:] = eos_tok
+    if eos_id != 2:
+        ids[B - 1] = 7   # a row without any eos: transformers' argmax of all-False is position 0
+    pooled = torch.zeros(B, C, device=DEV, dtype=dt)
+    _lib.check(lib.sfb_clip_pool(ids.data_ptr(), x.data_ptr(), pooled.data_ptr(), B, S, C, C, eos_id, _stream()), "pool")
+    torch.cuda.synchronize()
+    if eos_id == 2:
+        pos = ids.to(torch.int).argmax(dim=-1)
+    else:
+        pos = (ids.to(torch.int) == eos_id).int().argmax(dim=-1)
+    ref = x.view(B, S, C)[torch.arange(B, device=DEV), pos]
+    return float((pooled.float() - ref.float()).abs().max())
 
 
 def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=4, persistent=False):
@@ -785,6 +832,18 @@ CHECKS = {
     "attn_v2_d64_bf16_ragged": (lambda: check_attention(2, 5, 200, 333, 64, dt=torch.bfloat16, kv_tile=64), 2e-2),
     "attn_v2_cross77": (lambda: check_attention(2, 8, 1024, 77, 40, kv_tile=64), 5e-3),
     "attn_v2_one_tile": (lambda: check_attention(2, 8, 256, 40, 64, kv_tile=64), 5e-3),
+    # causal self-attention of the CLIP text encoders (77 tokens; and several query / key tiles)
+    "attn_v2_causal_77": (lambda: check_attention(2, 12, 77, None, 64, kv_tile=64, causal=True), 5e-3),
+    "attn_v2_causal_77_bf16": (lambda: check_attention(1, 20, 77, None, 64, dt=torch.bfloat16, kv_tile=64, causal=True), 2e-2),
+    "attn_v2_causal_300": (lambda: check_attention(2, 4, 300, None, 64, kv_tile=64, causal=True), 5e-3),
+    "attn_v2_causal_d32": (lambda: check_attention(2, 4, 200, None, 32, kv_tile=64, causal=True), 5e-3),
+    "gemm_act_quick_gelu": (lambda: check_gemm(154, 3072, 768, residual=False, act=_lib.ACT_QUICK_GELU), 2e-3),
+    "gemm_act_gelu_bf16": (lambda: check_gemm(77, 5120, 1280, dt=torch.bfloat16, residual=False, act=_lib.ACT_GELU), 1e-2),
+    "gemm_act_gelu_pair_residual": (lambda: check_gemm(512, 640, 320, pair=True, act=_lib.ACT_GELU), 2e-3),
+    "embed_tokens": (lambda: check_embed_tokens(), 2e-3),
+    "embed_tokens_bf16": (lambda: check_embed_tokens(2, 50, 1280, 5000, dt=torch.bfloat16), 1e-2),
+    "clip_pool_legacy_argmax": (lambda: check_clip_pool(2), 0.0),
+    "clip_pool_eos": (lambda: check_clip_pool(49407), 0.0),
     "attn_v1_d64": (lambda: check_attention(2, 8, 512, None, 64, kv_tile=128), 5e-3),
     "attn_d40": (lambda: check_attention(2, 8, 1024, None, 40), 5e-3),
     "attn_d40_4096": (lambda: check_attention(1, 8, 4096, None, 40), 5e-3),

@@ -230,7 +230,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(h, name), name
     lib = _lib.lib()
-    assert lib.sfb_abi_version() == 2
+    assert lib.sfb_abi_version() == 3
     # argument validation works without a GPU and never falls back silently
     p = _lib.GemmParams()
     assert lib.sfb_gemm(ctypes.byref(p), None) < 0
@@ -479,3 +479,34 @@ def test_vae_decoder_plan_builds_and_passes_host_validation():
     if not torch.cuda.is_available():
         n = _validate_plan_on_cpu(plan)
         assert n["sfb_gemm"] >= 35
+
+
+# ---------------------------------------------------------------------------------------------
+# CLIP text encoder schedule (row f4): dry plans on CPU
+# ---------------------------------------------------------------------------------------------
+def test_clip_text_plan_dry_launch_list_and_parameter_totals():
+    from collections import Counter
+    from sfast_b200 import clip_plan as cp
+    from sfast_b200.plan import PackedWeights
+    cfg = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+               num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu", eos_token_id=2,
+               projection_dim=768, layer_norm_eps=1e-5)
+    spec = cp.clip_text_spec_from_config(cfg)
+    shapes = cp.clip_text_param_shapes(spec)
+    assert sum(torch.Size(s).numel() for s in shapes.values()) == 123_060_480      # CLIP ViT-L/14 text model
+    sd = {k: torch.empty(v, device="meta", dtype=torch.float16) for k, v in shapes.items()}
+    plan = cp.ClipTextPlan(PackedWeights(spec, sd, torch.float16, "meta", dry=True), 2, 77)
+    names = Counter(op.name.rsplit(".", 1)[-1] for op in plan.all_ops())
+    # 5 launches per layer (LayerNorms folded, activation and residuals in epilogues) + 4 edge kernels
+    assert names["qkv"] == names["core"] == names["out_proj"] == names["fc1"] == names["fc2"] == 12
+    assert len(plan.all_ops()) == 5 * 12 + 4
+    assert len(plan.hidden) == 13
+    # SDXL text_encoder_2 (OpenCLIP bigG text tower): 694,659,840 parameters with the projection
+    big = cp.clip_text_spec_from_config(dict(cfg, hidden_size=1280, intermediate_size=5120, num_hidden_layers=32,
+                                             num_attention_heads=20, hidden_act="gelu", projection_dim=1280),
+                                        with_projection=True)
+    assert sum(torch.Size(s).numel() for s in cp.clip_text_param_shapes(big).values()) == 694_659_840
+    with pytest.raises(NotImplementedError):
+        cp.clip_text_spec_from_config(dict(cfg, hidden_act="relu"))
+    with pytest.raises(NotImplementedError):
+        cp.clip_text_spec_from_config(dict(cfg, num_attention_heads=16))      # head_dim 48
