@@ -339,6 +339,7 @@ def run_b200(args, rank, world, local):
         extras["config2_sdxl"] = sdxl_bench(dev)
         extras["config3_svd"] = svd_bench(dev)
         extras["vae_decode"] = vae_bench(dev)
+        extras["text_encoder"] = text_encoder_bench(dev)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, steps=2, warmup=1, budget_s=25.0)
@@ -556,6 +557,54 @@ def vae_bench(dev, steps=10, warmup=3):
                "algorithmic_tflop": plan.flops() / 1e12, "tflops": plan.flops() / (ms / 1e3) / 1e12,
                "steps": steps, "warmup": warmup}
         del vae, plan
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:  # noqa: BLE001
+        torch.cuda.empty_cache()
+        return {"unavailable": repr(exc)[:300]}
+
+
+def text_encoder_bench(dev, steps=20, warmup=3):
+    """CLIP ViT-L/14 text encoder (the SD-1.5 / SDXL `text_encoder`): 2 prompts x 77 tokens, fp16, through
+    `compile_text_encoder` on transformers' own CLIPTextModel (random init) -- and the same module run
+    eagerly (library kernels) on the same GPU beside it.  Host ids -> device copy inside the timed call."""
+    try:
+        import copy
+        import transformers
+        from sfast.compilers.diffusion_pipeline_compiler import CompilationConfig, compile_text_encoder
+        cfg = transformers.CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072,
+                                          num_hidden_layers=12, num_attention_heads=12, max_position_embeddings=77,
+                                          hidden_act="quick_gelu", eos_token_id=2, projection_dim=768)
+        torch.manual_seed(0)
+        eager = transformers.CLIPTextModel(cfg).eval().to(dev, torch.float16)
+        fast = copy.deepcopy(eager)
+        cc = CompilationConfig.Default()
+        cc.enable_cuda_graph = True
+        fast = compile_text_encoder(fast, cc)
+        ids = torch.randint(0, 49407, (2, 77), generator=torch.Generator().manual_seed(1)).pin_memory()
+
+        def timed(m):
+            with torch.no_grad():
+                for _ in range(warmup):
+                    m(ids.to(dev, non_blocking=True))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    out = m(ids.to(dev, non_blocking=True))[0]
+                e1.record()
+                torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps, out
+
+        ms_fast, o_fast = timed(fast)
+        ms_eager, o_eager = timed(eager)
+        plan = next(iter(fast.forward._cached.values())).plan
+        out = {"what": "CLIP ViT-L/14 text encoder, 2 x 77 tokens, fp16, CUDA graph (transformers CLIPTextModel, random init)",
+               "ms_per_call": ms_fast, "eager_library_ms_per_call": ms_eager, "speedup_vs_eager": ms_eager / ms_fast,
+               "kernel_launches": len(plan.all_ops()), "algorithmic_gflop": plan.flops() / 1e9,
+               "max_abs_diff_vs_eager_fp16": float((o_fast.float() - o_eager.float()).abs().max()),
+               "steps": steps, "warmup": warmup}
+        del fast, eager, plan
         torch.cuda.empty_cache()
         return out
     except Exception as exc:  # noqa: BLE001

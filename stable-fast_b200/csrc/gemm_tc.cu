@@ -683,7 +683,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // many tiny images per tile (4x4 feature maps): row bias straight from global memory
         const float* rb_global = nullptr;
         if (e.rowbias && !rb_staged && !partial)
-            rb_global = e.rowbias + (size_t)(m_tile * args.box_n + r / (args.box_h * args.img_w)) * e.ld_rowbias;
+            rb_global = e.rowbias + (size_t)min(m_tile * args.box_n + r / (args.box_h * args.img_w), args.img_n - 1) * e.ld_rowbias;  // (padding rows of the last tile: clamped, never stored)
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
@@ -735,10 +735,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     add_bias8(brow, cl, f);
                 }
                 if (rb_global && ncol0 + cl < e.N) add_bias8(rb_global, ncol0 + cl, f);
-                if (e.act) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = epi_act(f[i], e.act);
-                }
+
                 *reinterpret_cast<float4*>(srow + cl) = make_float4(f[0], f[1], f[2], f[3]);
                 *reinterpret_cast<float4*>(srow + cl + 4) = make_float4(f[4], f[5], f[6], f[7]);
             }
@@ -756,6 +753,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // this thread is done with TMEM: its half of the end-of-kernel pair hand-shake (below)
         tc_fence_before();
         if (CG == 2) cluster_arrive_relaxed();
+        if (e.act) {
+            // activation (CLIP MLP): a ROLLED second pass over this thread's own staged values -- kept
+            // out of the unrolled conversion above, whose straight-line code every launch pays for
+            // in instruction fetch whether it has an activation or not
+#pragma unroll 1
+            for (int c = 0; c < kColsPer; c += 4) {
+                float4 v = *reinterpret_cast<float4*>(srow + chalf * kColsPer + c);
+                v.x = epi_act(v.x, e.act); v.y = epi_act(v.y, e.act);
+                v.z = epi_act(v.z, e.act); v.w = epi_act(v.w, e.act);
+                *reinterpret_cast<float4*>(srow + chalf * kColsPer + c) = v;
+            }
+        }
         epi_bar();
         if (et == 0) SFB_STAMP(6);
 
@@ -1164,7 +1173,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             float rs_sum = 0.f, rs_sq = 0.f;  // LayerNorm statistics of the stored row (rowstats_out)
             const float* rb_global = nullptr;
             if (e.rowbias && !rb_staged)
-                rb_global = e.rowbias + (size_t)(m_tile * args.box_n + r / (args.box_h * args.img_w)) * e.ld_rowbias;
+                rb_global = e.rowbias + (size_t)min(m_tile * args.box_n + r / (args.box_h * args.img_w), args.img_n - 1) * e.ld_rowbias;  // (padding rows of the last tile: clamped, never stored)
             const int brow_off = rb_staged ? (r / (args.box_h * args.img_w)) * BN : 0;
             const uint32_t hc_tile = hc;
             hc += nh;
