@@ -397,6 +397,12 @@ int sfb_embed_tokens(const int64_t* ids, const void* tok_emb, const void* pos_em
 int sfb_clip_pool(const int64_t* ids, const void* x, void* pooled, int32_t batch, int32_t seq, int32_t dim,
                   int32_t ld_x, int32_t eos_id, sfb_stream_t stream);
 
+/* CLIP vision tower (SVD image_encoder, reference :100-103): non-overlapping patch x patch blocks of an NCHW
+ * 16-bit image as rows of a GEMM A operand: a[(b, py, px), (c, i, j)] = x[b, c, py*patch + i, px*patch + j],
+ * row pitch kpad (a multiple of 64 for the GEMM), columns beyond chans * patch^2 zeroed. */
+int sfb_patchify(const void* x, void* a, int32_t batch, int32_t chans, int32_t h, int32_t w, int32_t patch,
+                 int32_t kpad, sfb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

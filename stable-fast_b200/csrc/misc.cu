@@ -699,3 +699,53 @@ extern "C" int sfb_clip_pool(const int64_t* ids, const void* x, void* pooled, in
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "clip_pool: %s", cudaGetErrorString(err));
     return check_launch("sfb_clip_pool");
 }
+
+// ---------------------------------------------------------------------------------------
+// CLIP vision tower edge: non-overlapping P x P patches of an NCHW image as GEMM rows
+// ---------------------------------------------------------------------------------------
+namespace sfb {
+
+// a[(b, py, px), (c, i, j)] = x[b, c, py*P + i, px*P + j]; columns [C*P*P, kpad) are zero.  One thread
+// per 8 output columns (one 16-byte store).
+__global__ void __launch_bounds__(256) patchify_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ a,
+                                                       int batch, int chans, int h, int w, int patch, int kpad) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int gw = w / patch, gh = h / patch, kv = kpad / 8, k_real = chans * patch * patch;
+    const long long total = (long long)batch * gh * gw * kv;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % kv);
+        const long long row = idx / kv;
+        const int px = (int)(row % gw), py = (int)((row / gw) % gh), b = (int)(row / ((long long)gw * gh));
+        uint16_t o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = v * 8 + e;
+            uint16_t val = 0;
+            if (k < k_real) {
+                const int c = k / (patch * patch), ij = k - c * patch * patch, i = ij / patch, j = ij - i * patch;
+                val = x[(((size_t)b * chans + c) * h + py * patch + i) * w + px * patch + j];
+            }
+            o[e] = val;
+        }
+        *reinterpret_cast<uint4*>(a + (size_t)row * kpad + v * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+}  // namespace sfb
+
+extern "C" int sfb_patchify(const void* x, void* a, int32_t batch, int32_t chans, int32_t h, int32_t w, int32_t patch,
+                            int32_t kpad, sfb_stream_t stream) {
+    if (!x || !a || batch <= 0 || chans <= 0 || patch <= 0 || h % patch || w % patch || kpad % 8 ||
+        kpad < chans * patch * patch)
+        return fail(SFB_ERR_INVALID, "patchify: bad geometry (h=%d w=%d patch=%d kpad=%d)", h, w, patch, kpad);
+    const long long total = (long long)batch * (h / patch) * (w / patch) * (kpad / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cudaError_t err = launch_pdl(sfb::patchify_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                 reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(a), batch, chans, h,
+                                 w, patch, kpad);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "patchify: %s", cudaGetErrorString(err));
+    return check_launch("sfb_patchify");
+}

@@ -60,12 +60,27 @@ def compile(m, config):
     for attr in ('text_encoder', 'text_encoder_2'):
         if getattr(m, attr, None) is not None:
             setattr(m, attr, compile_text_encoder(getattr(m, attr), config))
+    # SVD's CLIP vision tower (reference :100-103)
     if getattr(m, 'image_encoder', None) is not None:
-        logger.warning('sfast (B200 build): image_encoder (SVD CLIP vision tower, one call per clip) '
-                       'is left on its eager path')
+        m.image_encoder = compile_image_encoder(m.image_encoder, config)
     if getattr(config, 'trace_scheduler', False):
         logger.warning('sfast (B200 build): trace_scheduler is ignored (scheduler.step stays eager)')
     return m
+
+
+def compile_image_encoder(m, config):
+    """Replace ``m.forward`` of a transformers CLIPVisionModel / CLIPVisionModelWithProjection (the SVD
+    pipeline's image_encoder, reference :100-103) with the B200-native tower; anything else is returned
+    unchanged with a warning."""
+    from sfast_b200.runtime import compile_image_encoder_module, require_b200
+    cfg = getattr(m, 'config', None)
+    if cfg is None or not hasattr(m, 'vision_model') or getattr(cfg, 'model_type', 'clip_vision_model') != 'clip_vision_model':
+        logger.warning('sfast (B200 build): %s is not a CLIP vision model; left on its eager path', type(m).__name__)
+        return m
+    device = m.device if hasattr(m, 'device') else torch.device(
+        'cuda' if torch.cuda.is_available() else 'cpu')
+    require_b200(torch.device(device))
+    return compile_image_encoder_module(m, enable_cuda_graph=bool(config.enable_cuda_graph))
 
 
 def compile_text_encoder(m, config):

@@ -140,6 +140,7 @@ SYMBOLS = {
     "sfb_memset": (C.c_int, [_VP, _I32, C.c_size_t, _VP]),
     "sfb_embed_tokens": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_clip_pool": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_patchify": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
 }
 
 _lib = None

@@ -405,6 +405,107 @@ class CompiledTextEncoder:
                             hidden_states=hidden)
 
 
+class CompiledVisionEncoder:
+    """transformers ``CLIPVisionModel`` / ``CLIPVisionModelWithProjection`` forward on the native path (the
+    SVD pipeline's image_encoder, reference :100-103).  One plan + CUDA graph per batch size."""
+
+    def __init__(self, config, state_dict_fn, eager_forward, with_projection, enable_cuda_graph=True):
+        from .clip_plan import clip_vision_spec_from_config
+        self.spec = clip_vision_spec_from_config(config, with_projection)
+        self._state_dict_fn, self._eager = state_dict_fn, eager_forward
+        self.with_projection = with_projection
+        self.enable_cuda_graph = enable_cuda_graph
+        self._weights, self._param_refs, self._param_versions = None, None, None
+        self._cached = {}
+        self._lock = threading.Lock()
+        self._warned = False
+        rd = cfg_get(config, "return_dict", None)
+        self._return_dict_default = True if rd is None else bool(rd)
+
+    def _route_eager(self, why, call):
+        if not self._warned:
+            logger.warning("sfast (B200 build): image encoder call left on the module's eager path (%s)", why)
+            self._warned = True
+        return self._eager(**call)
+
+    def __call__(self, pixel_values=None, interpolate_pos_encoding=False, output_attentions=None,
+                 output_hidden_states=None, return_dict=None, **kwargs):
+        from .clip_plan import ClipVisionPlan
+        call = dict(pixel_values=pixel_values, interpolate_pos_encoding=interpolate_pos_encoding,
+                    output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+                    return_dict=return_dict, **kwargs)
+        call = {k: v for k, v in call.items() if v is not None}
+        if pixel_values is None:
+            raise ValueError("You have to specify pixel_values")
+        spec = self.spec
+        if interpolate_pos_encoding or output_attentions or kwargs:
+            return self._route_eager("interpolate_pos_encoding / output_attentions / extra kwargs", call)
+        if tuple(pixel_values.shape[1:]) != (spec.channels, spec.image_size, spec.image_size):
+            raise ValueError(f"Input image size {tuple(pixel_values.shape[2:])} doesn't match model "
+                             f"({spec.image_size}*{spec.image_size}).")
+        sd = None
+        if self._weights is None:
+            sd = self._state_dict_fn()
+            wdt = sd["vision_model.embeddings.patch_embedding.weight"].dtype
+            if wdt not in (torch.float16, torch.bfloat16):
+                return self._route_eager(f"{wdt} weights: the native encoder computes in fp16 / bf16", call)
+        require_b200(pixel_values.device)
+        B = pixel_values.shape[0]
+        with self._lock, torch.cuda.device(pixel_values.device):
+            if self._weights is None:
+                wdt = sd["vision_model.embeddings.patch_embedding.weight"].dtype
+                self._weights = PackedWeights(self.spec, sd, wdt, pixel_values.device)
+                self._param_refs = [t for t in sd.values() if torch.is_tensor(t)]
+                self._param_versions = [t._version for t in self._param_refs]
+            elif [t._version for t in self._param_refs] != self._param_versions:
+                sd = self._state_dict_fn()
+                torch.cuda.current_stream().synchronize()
+                self._weights.refresh(sd)
+                self._param_refs = [t for t in sd.values() if torch.is_tensor(t)]
+                self._param_versions = [t._version for t in self._param_refs]
+            key = (B, pixel_values.device.index)
+            gp = self._cached.get(key)
+            if gp is None:
+                gp = _GraphedPlan(ClipVisionPlan(self._weights, B), self.enable_cuda_graph)
+                self._cached[key] = gp
+            plan = gp.plan
+            plan.pixels_in.copy_(pixel_values, non_blocking=True)   # (casts to the module's dtype, as the module does)
+            gp.step()
+            last = plan.last_hidden_state.clone()
+            pooled = plan.pooled.clone()
+            embeds = plan.image_embeds.clone() if self.with_projection else None
+            hidden = tuple(h.clone() for h in plan.hidden_states()) if output_hidden_states else None
+        if return_dict is None:
+            return_dict = self._return_dict_default
+        if self.with_projection:
+            if not return_dict:
+                return tuple(v for v in (embeds, last, hidden) if v is not None)
+            return _clip_output("CLIPVisionModelOutput", image_embeds=embeds, last_hidden_state=last,
+                                hidden_states=hidden)
+        if not return_dict:
+            return tuple(v for v in (last, pooled, hidden) if v is not None)
+        return _clip_output("BaseModelOutputWithPooling", last_hidden_state=last, pooler_output=pooled,
+                            hidden_states=hidden)
+
+
+def compile_image_encoder_module(m, enable_cuda_graph=True):
+    """Replace ``m.forward`` of a CLIPVisionModel / CLIPVisionModelWithProjection (same module object)."""
+    with_projection = hasattr(m, "visual_projection")
+    eager = m.forward
+    compiled = CompiledVisionEncoder(m.config, m.state_dict, eager, with_projection, enable_cuda_graph)
+
+    def forward(*args, **kwargs):
+        if args:
+            kwargs = dict(zip(("pixel_values",), args), **kwargs)
+        return compiled(**kwargs)
+
+    forward.__self__ = m
+    forward._cached = compiled._cached
+    forward._compiled = compiled
+    m.forward = forward
+    return m
+
+
 class _PlainOutput(dict):
     """Stand-in for transformers' ModelOutput when transformers is not importable: attribute, key and
     integer access over the non-None fields, like the real class."""
@@ -421,6 +522,8 @@ def _clip_output(kind, **fields):
     try:
         if kind == "CLIPTextModelOutput":
             from transformers.models.clip.modeling_clip import CLIPTextModelOutput as cls
+        elif kind == "CLIPVisionModelOutput":
+            from transformers.models.clip.modeling_clip import CLIPVisionModelOutput as cls
         else:
             from transformers.modeling_outputs import BaseModelOutputWithPooling as cls
         return cls(**fields)

@@ -242,6 +242,19 @@ def check_clip_pool(eos_id, B=5, S=77, C=768, dt=torch.float16, seed=12):
     return float((pooled.float() - ref.float()).abs().max())
 
 
+
+def check_patchify(B=2, C=3, H=56, P=14, kpad=640, dt=torch.float16, seed=13):
+    """Non-overlapping patches as GEMM rows == unfold; padding columns zero."""
+    lib = _lib.lib()
+    x = _rand(B, C, H, H, dt=dt, seed=seed)
+    g = H // P
+    a = torch.full((B * g * g, kpad), 3.0, device=DEV, dtype=dt)
+    _lib.check(lib.sfb_patchify(x.data_ptr(), a.data_ptr(), B, C, H, H, P, kpad, _stream()), "patchify")
+    torch.cuda.synchronize()
+    ref = F.unfold(x.float(), kernel_size=P, stride=P).transpose(1, 2).reshape(B * g * g, C * P * P)
+    return float((a[:, :C * P * P].float() - ref).abs().max()) + float(a[:, C * P * P:].float().abs().max())
+
+
 def check_qkv_scatter(B=2, H=8, S=256, D=40, dt=torch.float16, cross_kv=0, seed=4, persistent=False):
     """QKV projection GEMM whose epilogue writes the attention layouts directly."""
     lib = _lib.lib()
@@ -844,6 +857,9 @@ CHECKS = {
     "embed_tokens_bf16": (lambda: check_embed_tokens(2, 50, 1280, 5000, dt=torch.bfloat16), 1e-2),
     "clip_pool_legacy_argmax": (lambda: check_clip_pool(2), 0.0),
     "clip_pool_eos": (lambda: check_clip_pool(49407), 0.0),
+    "patchify_14": (lambda: check_patchify(), 0.0),
+    "patchify_224_bf16": (lambda: check_patchify(1, 3, 224, 14, 640, dt=torch.bfloat16), 0.0),
+    "patchify_16": (lambda: check_patchify(3, 3, 64, 16, 768), 0.0),
     "attn_v1_d64": (lambda: check_attention(2, 8, 512, None, 64, kv_tile=128), 5e-3),
     "attn_d40": (lambda: check_attention(2, 8, 1024, None, 40), 5e-3),
     "attn_d40_4096": (lambda: check_attention(1, 8, 4096, None, 40), 5e-3),

@@ -186,3 +186,82 @@ def test_unsupported_calls_stay_on_the_modules_own_path():
         want = ref(ids, attention_mask=mask)
     assert _rel(got.last_hidden_state, want.last_hidden_state) < 1e-2
     assert len(fast.forward._cached) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# CLIP vision tower (SVD image_encoder)
+# ---------------------------------------------------------------------------------------------
+def _vision(hidden, heads, layers, inter, act, image, proj, dtype, seed, with_projection=True):
+    cfg = transformers.CLIPVisionConfig(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers,
+                                        num_attention_heads=heads, image_size=image, patch_size=14,
+                                        projection_dim=proj, hidden_act=act)
+    torch.manual_seed(seed)
+    cls = transformers.CLIPVisionModelWithProjection if with_projection else transformers.CLIPVisionModel
+    m = cls(cfg).eval()
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if "norm" in name:
+                p.copy_(1.0 + 0.3 * torch.randn_like(p) if name.endswith("weight") else 0.3 * torch.randn_like(p))
+            elif name.endswith(".bias"):
+                p.copy_(0.1 * torch.randn_like(p))
+            elif "class_embedding" in name or "position_embedding" in name:
+                p.copy_(0.5 * torch.randn_like(p))
+    ref = copy.deepcopy(m).to("cuda", torch.float32)
+    return cfg, m.to("cuda", dtype), ref
+
+
+def _compile_vision(m):
+    from sfast.compilers.diffusion_pipeline_compiler import CompilationConfig, compile_image_encoder
+    c = CompilationConfig.Default()
+    c.enable_cuda_graph = True
+    return compile_image_encoder(m, c)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 4e-2)])
+def test_tiny_vision_tower_all_outputs(dtype, tol):
+    cfg, fast, ref = _vision(128, 2, 2, 256, "quick_gelu", 56, 64, dtype, seed=21)
+    eager16 = copy.deepcopy(fast)
+    fast = _compile_vision(fast)
+    x = torch.randn(3, 3, 56, 56, generator=torch.Generator().manual_seed(22)).to("cuda", dtype)
+    with torch.no_grad():
+        got = fast(x, output_hidden_states=True)
+        want = ref(x.float(), output_hidden_states=True)
+        lib = eager16(x)
+    assert type(got).__name__ == "CLIPVisionModelOutput"
+    e = _rel(got.image_embeds, want.image_embeds)
+    print(f"tiny CLIP vision {dtype}: native {e:.3e} | eager 16-bit {_rel(lib.image_embeds, want.image_embeds):.3e}")
+    assert e < tol
+    assert _rel(got.last_hidden_state, want.last_hidden_state) < tol
+    assert len(got.hidden_states) == len(want.hidden_states) == 3
+    for g, w in zip(got.hidden_states, want.hidden_states):
+        assert _rel(g, w) < tol
+    x2 = torch.randn(3, 3, 56, 56, generator=torch.Generator().manual_seed(23)).to("cuda", dtype)
+    with torch.no_grad():
+        assert _rel(fast(x2).image_embeds, ref(x2.float()).image_embeds) < tol      # replay with new pixels
+    assert len(fast.forward._cached) == 1
+
+
+def test_vision_tower_without_projection_and_wrong_size():
+    cfg, fast, ref = _vision(128, 2, 2, 256, "gelu", 56, 64, torch.float16, seed=24, with_projection=False)
+    fast = _compile_vision(fast)
+    x = torch.randn(2, 3, 56, 56, generator=torch.Generator().manual_seed(25)).to("cuda", torch.float16)
+    with torch.no_grad():
+        got, want = fast(x), ref(x.float())
+    assert _rel(got.pooler_output, want.pooler_output) < 1e-2
+    assert _rel(got[0], want[0]) < 1e-2
+    with pytest.raises(ValueError):
+        fast(torch.zeros(1, 3, 42, 42, device="cuda", dtype=torch.float16))
+
+
+def test_svd_image_encoder_shape_vit_h14():
+    """OpenCLIP ViT-H/14 vision tower as the SVD image_encoder: 1280 wide, 16 heads (head_dim 80), gelu,
+    224^2 images -> 257 tokens, projection to 1024; 6 of its 32 layers keep the fp32 reference quick."""
+    cfg, fast, ref = _vision(1280, 16, 6, 5120, "gelu", 224, 1024, torch.float16, seed=26)
+    fast = _compile_vision(fast)
+    x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(27)).to("cuda", torch.float16)
+    with torch.no_grad():
+        got, want = fast(x), ref(x.float())
+    e = _rel(got.image_embeds, want.image_embeds)
+    print(f"ViT-H/14 vision (6 layers) fp16: image_embeds {e:.3e}, last_hidden_state {_rel(got.last_hidden_state, want.last_hidden_state):.3e}")
+    assert got.image_embeds.shape == (1, 1024) and e < 1e-2
+    assert _rel(got.last_hidden_state, want.last_hidden_state) < 1e-2

@@ -510,3 +510,18 @@ def test_clip_text_plan_dry_launch_list_and_parameter_totals():
         cp.clip_text_spec_from_config(dict(cfg, hidden_act="relu"))
     with pytest.raises(NotImplementedError):
         cp.clip_text_spec_from_config(dict(cfg, num_attention_heads=16))      # head_dim 48
+
+
+def test_clip_vision_plan_dry_launch_list_and_parameter_totals():
+    from sfast_b200 import clip_plan as cp
+    from sfast_b200.plan import PackedWeights
+    cfg = dict(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=16,
+               image_size=224, patch_size=14, hidden_act="gelu", projection_dim=1024)
+    spec = cp.clip_vision_spec_from_config(cfg, with_projection=True)
+    shapes = cp.clip_vision_param_shapes(spec)
+    assert sum(torch.Size(s).numel() for s in shapes.values()) == 632_076_800   # OpenCLIP ViT-H/14 vision + projection
+    sd = {k: torch.empty(v, device="meta", dtype=torch.float16) for k, v in shapes.items()}
+    plan = cp.ClipVisionPlan(PackedWeights(spec, sd, torch.float16, "meta", dry=True), 1)
+    assert spec.tokens == 257 and len(plan.hidden) == 33
+    # 5 launches per layer + layer 0's stand-alone LayerNorm + 8 edge kernels at batch 1
+    assert len(plan.all_ops()) == 5 * 32 + 1 + 8
