@@ -166,12 +166,16 @@ typedef struct sfb_gemm_params {
     int32_t b_plain;
     /* LayerNorm folded around the GEMM (replaces sfast_triton::layer_norm,
      * /root/reference/src/sfast/triton/ops/layer_norm.py:51-133, as a separate pass):
-     *   producer (SFB_EPI_STORE): rowstats_out[m] += (sum, sum of squares) of the stored row;
+     *   producer (SFB_EPI_STORE): rowstats_out[m][slot] = (sum, sum of squares) over the columns that slot
+     *     covers of the stored row -- slot = the 160-column tile (one-tile kernel) or the warp segment of the
+     *     row (split-K reduction); every slot is WRITTEN once, nothing is accumulated atomically;
      *   consumer: A is the RAW activation, the weight is pre-scaled by gamma (W' = W * gamma),
      *     out = rstd_m * (acc - mean_m * ln_colsum[n]) + bias[n],  bias = beta W^T + b,
-     *     (mean_m, rstd_m) from ln_rowstats[m] over ln_dim columns.  Buffers are caller-zeroed. */
-    float* rowstats_out;       /* [M, 2] fp32 or NULL */
-    const float* ln_rowstats;  /* [M, 2] fp32 or NULL */
+     *     (mean_m, rstd_m) from the ln_slots slots of ln_rowstats[m] added in index order, over ln_dim columns.
+     *   Slots no producer wrote must be zero: the caller clears the buffer (once per step).  Results are
+     *   bit-identical from run to run.  sfb_rowstats_slots(N) = slots a producer of N columns may write. */
+    float* rowstats_out;       /* [M, rowstats_out_slots, 2] fp32 or NULL */
+    const float* ln_rowstats;  /* [M, ln_slots, 2] fp32 or NULL */
     const float* ln_colsum;    /* [N] fp32: sum_k W'[n, k] */
     float ln_eps;
     int32_t ln_dim;
@@ -179,7 +183,12 @@ typedef struct sfb_gemm_params {
      * before the residual add (the CLIP text encoders' MLP: fc1 + quick_gelu / gelu, encoders traced by
      * /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:93-103).  Needs splits == 1. */
     int32_t act; /* SFB_ACT_* */
+    int32_t rowstats_out_slots; /* slots per row of rowstats_out (>= sfb_rowstats_slots(N)) */
+    int32_t ln_slots;           /* slots per row of ln_rowstats */
 } sfb_gemm_params;
+
+/* slots per row a rowstats_out producer with N output columns needs (any split-K factor) */
+int sfb_rowstats_slots(int32_t n_cols);
 
 int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream);
 
@@ -212,9 +221,11 @@ typedef struct sfb_gn_params {
     void* y;         /* [n, hw, c] 16-bit, channel pitch ldy */
     const float* gamma;
     const float* beta;
-    float* stats;    /* [n, groups, 2] fp32: SHIFTED moments (sum(x - K), sum((x - K)^2)) about the
-                      * group's first stored value K = x[img, 0, g * c/groups]; the CALLER zeroes it
-                      * per use */
+    float* stats;    /* statistics WORKSPACE, sfb_group_norm_ws_floats(n, groups) floats, no initialisation
+                      * needed: one slot of [groups][2] SHIFTED moments (sum(x - K), sum((x - K)^2) about the
+                      * group's first stored value K = x[img, 0, g * c/groups]) per CTA of the statistics
+                      * pass, summed by the apply pass in a fixed order -- no floating-point atomics, so
+                      * results are bit-identical from run to run.  stats -> apply must use the same params. */
     int32_t n, hw, c, ldx, ldy, groups;
     float eps;
     int32_t silu;    /* 1: y = silu(gn(x)) */
@@ -242,6 +253,8 @@ int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream);
  * most one CTA per SM of the current device with a grid-wide barrier; x is read once.  `stats` and
  * `sync_counter` must be zero on entry.  sfb_group_norm_fused_fits() returns 1 when the geometry
  * qualifies on the current device. */
+/* floats the `stats` workspace of one GroupNorm over n images must hold on this device */
+int sfb_group_norm_ws_floats(int32_t n, int32_t groups);
 int sfb_group_norm_fused_fits(const sfb_gn_params* p);
 int sfb_group_norm_fused(const sfb_gn_params* p, sfb_stream_t stream);
 
@@ -327,8 +340,9 @@ enum sfb_row_index_mode {
  *   sfb_row_broadcast_add: y[m, :] = x[m, :] + vec[idx(m), :]   (frame position embedding; cross-
  *                          attention over ONE context token, where softmax over a single key is 1)
  *   sfb_alpha_blend:       y[m, :] = alpha * x[m, :] + (1 - alpha) * x2[m, :], alpha = sigmoid(*mix_factor)
- * rowstats_out (optional): [rows, 2] fp32 (sum, sum of squares) of the STORED row, overwritten --
- * the statistics a following folded LayerNorm consumes (sfb_gemm ln_rowstats). */
+ * rowstats_out (optional): [rows, rowstats_slots, 2] fp32; slot 0 receives (sum, sum of squares) of the STORED
+ * row (written, not accumulated; the other slots stay as the caller cleared them) -- the statistics a
+ * following folded LayerNorm consumes (sfb_gemm ln_rowstats / ln_slots). */
 typedef struct sfb_row_op_params {
     const void* x;
     const void* x2;
@@ -338,6 +352,7 @@ typedef struct sfb_row_op_params {
     const float* mix_factor;
     int32_t rows, c, ldx, ldx2, ldv, ldy, dtype;
     int32_t mode, div, mod, frames, seq, batch;
+    int32_t rowstats_slots; /* slots per row of rowstats_out (0 = 1) */
 } sfb_row_op_params;
 
 int sfb_row_broadcast_add(const sfb_row_op_params* p, sfb_stream_t stream);
@@ -385,12 +400,12 @@ int sfb_memset(void* p, int32_t value, size_t bytes, sfb_stream_t stream);
  * /root/reference/src/sfast/compilers/diffusion_pipeline_compiler.py:93-112) ---------------- */
 
 /* out[b * seq + s, :] = tok_emb[ids[b, s], :] + pos_emb[s, :]   (16-bit tables and output, row pitch ld_out);
- * rowstats (optional, [rows, 2] fp32): (sum, sum of squares) of each stored row, WRITTEN (not accumulated) --
- * the statistics the first folded LayerNorm consumes.  ids: int64 [batch, seq]; ids outside [0, vocab) are an
+ * rowstats (optional, [rows, rowstats_slots, 2] fp32): slot 0 = (sum, sum of squares) of each stored row, WRITTEN
+ * (not accumulated) -- the statistics the first folded LayerNorm consumes.  ids: int64 [batch, seq]; ids outside [0, vocab) are an
  * error the kernel reports by writing zeros for that row. */
 int sfb_embed_tokens(const int64_t* ids, const void* tok_emb, const void* pos_emb, void* out, float* rowstats,
-                     int32_t batch, int32_t seq, int32_t dim, int32_t vocab, int32_t ld_out, int32_t dtype,
-                     sfb_stream_t stream);
+                     int32_t rowstats_slots, int32_t batch, int32_t seq, int32_t dim, int32_t vocab, int32_t ld_out,
+                     int32_t dtype, sfb_stream_t stream);
 
 /* pooled[b, :] = x[b * seq + p_b, :], p_b = first position whose id equals eos_id, or (eos_id == 2, the
  * legacy CLIP config) the position of the largest id -- transformers' CLIPTextTransformer pooling rule. */

@@ -98,6 +98,12 @@ struct EpiArgs {
     float ln_eps;
     int ln_dim;
     int act;  // SFB_ACT_*: STORE epilogue only
+    // Row statistics live in SLOTS: [M][slots] x (sum, sum of squares).  Every producer writes each of
+    // its slots exactly once (GEMM epilogue: slot = its 160-column tile; split-K reduction: slot = warp
+    // segment of the row), nothing is accumulated atomically, and the consumer adds the slots in index
+    // order -- bit-identical from run to run.  Unwritten slots are zero (the caller clears the buffer).
+    int rs_slots;  // slots per row of rowstats_out
+    int ln_slots;  // slots per row of ln_rowstats
 };
 
 // quick_gelu (x * sigmoid(1.702 x)) / erf gelu of the CLIP text encoders' MLP
@@ -109,7 +115,12 @@ __device__ __forceinline__ float epi_act(float x, int act) {
 // LayerNorm(x) W^T == rstd * (x W'^T - mean * colsum(W')) + (beta W^T + b), W' = W * gamma.
 // (mean, rstd) of row m from the (sum, sum of squares) its producer GEMMs accumulated.
 __device__ __forceinline__ float2 ln_row_params(const EpiArgs& e, int m) {
-    const float2 st = __ldcg(reinterpret_cast<const float2*>(e.ln_rowstats) + m);
+    const float2* sp = reinterpret_cast<const float2*>(e.ln_rowstats) + (size_t)m * e.ln_slots;
+    float2 st = __ldcg(sp);
+    for (int i = 1; i < e.ln_slots; ++i) {
+        const float2 t = __ldcg(sp + i);
+        st.x += t.x; st.y += t.y;
+    }
     const float inv = 1.0f / (float)e.ln_dim;
     const float mean = st.x * inv;
     const float var = fmaxf(st.y * inv - mean * mean, 0.f);
@@ -311,7 +322,7 @@ __device__ __forceinline__ void tap_offset(const GemmArgs& a, const ATile& t, in
 // `n` is the output column (GEGLU: output column of the gated product).  Partials were written by
 // other SMs: read them through L2 (ld.global.cg).
 template <int BF16, typename Sum8>
-__device__ __forceinline__ void reduce_epilogue8(Sum8&& sum8, const EpiArgs& e, int m, int n) {
+__device__ __forceinline__ void reduce_epilogue8(Sum8&& sum8, const EpiArgs& e, int m, int n, float& rs, float& rss) {
     if (e.epi == SFB_EPI_GEGLU) {
         const int tile = n / (BN / 2);
         const int nv = tile * BN + (n - tile * (BN / 2));
@@ -348,12 +359,7 @@ __device__ __forceinline__ void reduce_epilogue8(Sum8&& sum8, const EpiArgs& e, 
                              reinterpret_cast<const uint16_t*>(e.residual) + (size_t)m * e.ldr + n),
                          BF16, acc);
         }
-        if (e.rowstats_out) {
-            float rs = 0.f, rss = 0.f;
-            row_stats8(acc, BF16, rs, rss);
-            atomicAdd(e.rowstats_out + 2 * (size_t)m, rs);
-            atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rss);
-        }
+        if (e.rowstats_out) row_stats8(acc, BF16, rs, rss);
         epi_store8<BF16>(e, m, n, acc);
     }
 }
@@ -368,8 +374,11 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
     const int ncols = (e.epi == SFB_EPI_GEGLU) ? e.geglu_n_out : e.N;
     const int groups = ncols / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)e.M * groups) return;
-    const int m = (int)(idx / groups), n = (int)(idx % groups) * 8;
+    const bool live = idx < (long long)e.M * groups;
+    if (!live && !e.rowstats_out) return;
+    const int m = live ? (int)(idx / groups) : -1, n = live ? (int)(idx % groups) * 8 : 0;
+    float rs = 0.f, rss = 0.f;  // (sum, sum of squares) of this thread's 8 stored values (rowstats_out)
+    if (live) {
     auto sum8 = [&](int col, float (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -397,7 +406,27 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
             }
         }
     };
-    reduce_epilogue8<BF16>(sum8, e, m, n);
+    reduce_epilogue8<BF16>(sum8, e, m, n, rs, rss);
+    }
+    if (e.rowstats_out) {
+        // (the whole warp gets here: out-of-range threads carry m = -1)  Segmented sum over the lanes that
+        // hold the same row, fixed shuffle tree; the segment's first lane writes slot = how many warp
+        // boundaries lie between the row's first column group and this segment.
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float o1 = __shfl_down_sync(0xffffffffu, rs, d), o2 = __shfl_down_sync(0xffffffffu, rss, d);
+            const int om = __shfl_down_sync(0xffffffffu, m, d);
+            if ((int)(threadIdx.x & 31) + d < 32 && om == m) { rs += o1; rss += o2; }
+        }
+        const int pm = __shfl_up_sync(0xffffffffu, m, 1);
+        const bool head = live && ((threadIdx.x & 31) == 0 || pm != m);
+        if (head) {
+            const long long row_start = (long long)m * groups;
+            const int seg = (int)((idx - row_start + 31) / 32);
+            float* d = e.rowstats_out + ((size_t)m * e.rs_slots + seg) * 2;
+            d[0] = rs; d[1] = rss;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -919,6 +948,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             if (e.rowstats_out) {
                 epi_bar();
+                float2 rs_keep = make_float2(0.f, 0.f);
                 if (valid) {
                     float rs_sum = 0.f, rs_sq = 0.f;
                     for (int g = chalf * (kGroups / kColSplit); g < (chalf + 1) * (kGroups / kColSplit); ++g) {
@@ -928,8 +958,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             row_stats8(f, BF16, rs_sum, rs_sq);
                         }
                     }
-                    atomicAdd(e.rowstats_out + 2 * (size_t)m, rs_sum);
-                    atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rs_sq);
+                    // the other column half of the same row sits in the partner warp: hand it over
+                    // through shared memory (the bias slots are idle by now) and add in a fixed order
+                    if (chalf == 1) *reinterpret_cast<float2*>(sBias + 2 * r) = make_float2(rs_sum, rs_sq);
+                    rs_keep = make_float2(rs_sum, rs_sq);
+                }
+                epi_bar();
+                if (valid && chalf == 0) {
+                    float2 o = make_float2(0.f, 0.f);
+                    if (kColSplit == 2) o = *reinterpret_cast<const float2*>(sBias + 2 * r);
+                    float* d = e.rowstats_out + ((size_t)m * e.rs_slots + n_tile) * 2;
+                    d[0] = rs_keep.x + o.x;
+                    d[1] = rs_keep.y + o.y;
                 }
             }
         }
@@ -1170,7 +1210,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const bool valid = tile_row_to_m(args, m_tile, r, m);
             float2 ln = make_float2(0.f, 1.f);
             if (e.ln_rowstats && valid) ln = ln_row_params(e, m);
-            float rs_sum = 0.f, rs_sq = 0.f;  // LayerNorm statistics of the stored row (rowstats_out)
             const float* rb_global = nullptr;
             if (e.rowbias && !rb_staged)
                 rb_global = e.rowbias + (size_t)min(m_tile * args.box_n + r / (args.box_h * args.img_w), args.img_n - 1) * e.ld_rowbias;  // (padding rows of the last tile: clamped, never stored)
@@ -1342,25 +1381,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                 float f[8];
                                 load8(row, grp * 8, f);
                                 if (has_res) add_res8(res[j], BF16, f);
-                                if (e.rowstats_out) {
-                                    float* d = sStage + row * kPStagePitch + grp * 8;
-                                    *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
-                                    *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                                }
                                 *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + (size_t)mm * e.ldo + n) =
                                     pack8(f, BF16);
-                            }
-                        }
-                        if (e.rowstats_out) {
-                            epi_bar();
-                            if (valid) {
-                                for (int g = chalf * (kGroups / 2); g < (chalf + 1) * (kGroups / 2); ++g) {
-                                    if (ncol0 + pc0 + g * 8 < e.N) {
-                                        float f[8];
-                                        load8(r, g * 8, f);
-                                        row_stats8(f, BF16, rs_sum, rs_sq);
-                                    }
-                                }
                             }
                         }
                     } else {
@@ -1396,11 +1418,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     }
                     epi_bar();  // the staging tile (and the QKV column table) are rewritten by the next pass
                 }
-            }
-            if (e.rowstats_out && valid) {
-                // the two warps of a lane quarter hold the two column halves of the same row
-                atomicAdd(e.rowstats_out + 2 * (size_t)m, rs_sum);
-                atomicAdd(e.rowstats_out + 2 * (size_t)m + 1, rs_sq);
             }
         }
     }
@@ -1471,6 +1488,12 @@ static thread_local unsigned long long* g_trace_next = nullptr;
 extern "C" void sfb_trace_next_gemm(void* buf) { g_trace_next = static_cast<unsigned long long*>(buf); }
 #endif
 
+extern "C" int sfb_rowstats_slots(int32_t n_cols) {
+    const int tiles = (n_cols + BN - 1) / BN;                 // one-tile kernel: a slot per 160-column tile
+    const int segs = (n_cols / 8 - 1 + 31) / 32 + 1;          // split-K reduction: a slot per warp segment
+    return tiles > segs ? tiles : segs;
+}
+
 extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!p || !p->tmap_a || !p->tmap_b) return fail(SFB_ERR_INVALID, "sfb_gemm: null argument");
@@ -1532,6 +1555,17 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     e.rowstats_out = p->rowstats_out; e.ln_rowstats = p->ln_rowstats; e.ln_colsum = p->ln_colsum;
     e.ln_eps = p->ln_eps; e.ln_dim = p->ln_dim;
     e.act = p->act;
+    e.rs_slots = p->rowstats_out_slots; e.ln_slots = p->ln_slots;
+    if (p->rowstats_out) {
+        // slots a producer may write: its 160-column tiles, or (split-K reduction kernel, one thread per 8
+        // columns) the warp segments of a row
+        int need = (p->N + BN - 1) / BN;
+        if (p->splits > 1) need = (p->N / 8 - 1 + 31) / 32 + 1;
+        if (p->rowstats_out_slots < need || p->persistent)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: rowstats_out needs rowstats_out_slots >= %d (got %d) and the one-tile kernel",
+                        need, p->rowstats_out_slots);
+    }
+    if (p->ln_rowstats && p->ln_slots < 1) return fail(SFB_ERR_INVALID, "sfb_gemm: ln_rowstats needs ln_slots >= 1");
     if (p->act < SFB_ACT_NONE || p->act > SFB_ACT_GELU)
         return fail(SFB_ERR_INVALID, "sfb_gemm: unknown activation %d", p->act);
     if (p->act && (p->epi != SFB_EPI_STORE || p->splits > 1 || p->persistent || p->rowbias))

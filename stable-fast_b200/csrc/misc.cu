@@ -606,8 +606,8 @@ namespace sfb {
 __global__ void __launch_bounds__(256) embed_tokens_kernel(const long long* __restrict__ ids,
                                                            const uint16_t* __restrict__ tok,
                                                            const uint16_t* __restrict__ pos, uint16_t* __restrict__ out,
-                                                           float* __restrict__ rowstats, int rows, int seq, int nvec,
-                                                           int vocab, int ld_out, int dtype) {
+                                                           float* __restrict__ rowstats, int rs_slots, int rows, int seq,
+                                                           int nvec, int vocab, int ld_out, int dtype) {
     pdl_launch_dependents();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -640,8 +640,8 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(const long long* __re
             sq += __shfl_xor_sync(0xffffffffu, sq, d);
         }
         if (lane == 0) {
-            rowstats[2 * (size_t)row] = sum;
-            rowstats[2 * (size_t)row + 1] = sq;
+            rowstats[2 * (size_t)row * rs_slots] = sum;
+            rowstats[2 * (size_t)row * rs_slots + 1] = sq;
         }
     }
 }
@@ -675,8 +675,8 @@ __global__ void __launch_bounds__(32) clip_pool_kernel(const long long* __restri
 }  // namespace sfb
 
 extern "C" int sfb_embed_tokens(const int64_t* ids, const void* tok_emb, const void* pos_emb, void* out,
-                                float* rowstats, int32_t batch, int32_t seq, int32_t dim, int32_t vocab,
-                                int32_t ld_out, int32_t dtype, sfb_stream_t stream) {
+                                float* rowstats, int32_t rowstats_slots, int32_t batch, int32_t seq, int32_t dim,
+                                int32_t vocab, int32_t ld_out, int32_t dtype, sfb_stream_t stream) {
     if (!ids || !tok_emb || !pos_emb || !out || batch <= 0 || seq <= 0 || dim <= 0 || dim % 8 || ld_out % 8 ||
         ld_out < dim || vocab <= 0)
         return fail(SFB_ERR_INVALID, "embed_tokens: bad argument (dim=%d ld_out=%d)", dim, ld_out);
@@ -684,7 +684,8 @@ extern "C" int sfb_embed_tokens(const int64_t* ids, const void* tok_emb, const v
     cudaError_t err = launch_pdl(sfb::embed_tokens_kernel, dim3((rows + 7) / 8), dim3(256), 0,
                                  static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(ids),
                                  reinterpret_cast<const uint16_t*>(tok_emb), reinterpret_cast<const uint16_t*>(pos_emb),
-                                 reinterpret_cast<uint16_t*>(out), rowstats, rows, seq, dim / 8, vocab, ld_out, dtype);
+                                 reinterpret_cast<uint16_t*>(out), rowstats, rowstats_slots > 0 ? rowstats_slots : 1, rows,
+                                 seq, dim / 8, vocab, ld_out, dtype);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "embed_tokens: %s", cudaGetErrorString(err));
     return check_launch("sfb_embed_tokens");
 }

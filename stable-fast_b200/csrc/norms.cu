@@ -149,31 +149,106 @@ struct GnAcc8 {
             s[2 * i + 1] += d1; ss[2 * i + 1] += d1 * d1;
         }
     }
-    // merge runs of equal group id among the 8 channels into acc[2 * groups] (shared memory)
-    __device__ __forceinline__ void flush(float* acc, int ch0, int cpg) const {
-        int g_run = ch0 / cpg;
-        float rs = 0.f, rss = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int g = (ch0 + i) / cpg;
-            if (g != g_run) {
-                atomicAdd(&acc[2 * g_run], rs);
-                atomicAdd(&acc[2 * g_run + 1], rss);
-                g_run = g; rs = 0.f; rss = 0.f;
-            }
-            rs += s[i]; rss += ss[i];
-        }
-        atomicAdd(&acc[2 * g_run], rs);
-        atomicAdd(&acc[2 * g_run + 1], rss);
-    }
 };
 
+// ---- deterministic reductions (no floating-point atomics anywhere: replays are bit-identical) --------
+// kGnThreads x 16 floats of scratch: per-thread moments, then per-channel totals, then slot partials
+constexpr int kGnRedFloats = kGnThreads * 16;
+
+// CTA level: the (S1, S2) of thread (tx, ty)'s 8 channels -> acc[2 * groups] in shared memory, every
+// addition in a fixed order: (1) row slots ty = 0, 1, ... per channel, (2) channels in order per group.
+// All threads of the CTA call it (it synchronises); `active` = the thread holds data.
+__device__ __forceinline__ void gn_block_reduce(const GnAcc8& st, bool active, int tx, int ty, int by,
+                                                const GnArgs& a, float* red, float* acc) {
+    float4* red4 = reinterpret_cast<float4*>(red);
+    if (active && ty > 0) {
+        const int t = ty * a.nvec + tx;
+        red4[0 * kGnThreads + t] = make_float4(st.s[0], st.s[1], st.s[2], st.s[3]);
+        red4[1 * kGnThreads + t] = make_float4(st.s[4], st.s[5], st.s[6], st.s[7]);
+        red4[2 * kGnThreads + t] = make_float4(st.ss[0], st.ss[1], st.ss[2], st.ss[3]);
+        red4[3 * kGnThreads + t] = make_float4(st.ss[4], st.ss[5], st.ss[6], st.ss[7]);
+    }
+    __syncthreads();
+    float s[8], ss[8];
+    const bool owner = active && ty == 0;
+    if (owner) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] = st.s[i]; ss[i] = st.ss[i]; }
+        for (int r = 1; r < by; ++r) {
+            const int t = r * a.nvec + tx;
+            const float4 a0 = red4[0 * kGnThreads + t], a1 = red4[1 * kGnThreads + t];
+            const float4 b0 = red4[2 * kGnThreads + t], b1 = red4[3 * kGnThreads + t];
+            s[0] += a0.x; s[1] += a0.y; s[2] += a0.z; s[3] += a0.w;
+            s[4] += a1.x; s[5] += a1.y; s[6] += a1.z; s[7] += a1.w;
+            ss[0] += b0.x; ss[1] += b0.y; ss[2] += b0.z; ss[3] += b0.w;
+            ss[4] += b1.x; ss[5] += b1.y; ss[6] += b1.z; ss[7] += b1.w;
+        }
+    }
+    __syncthreads();  // the per-thread partials are consumed: the scratch becomes [2][c] channel totals
+    if (owner) {
+        float4* ch = reinterpret_cast<float4*>(red + tx * 8);
+        ch[0] = make_float4(s[0], s[1], s[2], s[3]);
+        ch[1] = make_float4(s[4], s[5], s[6], s[7]);
+        float4* ch2 = reinterpret_cast<float4*>(red + a.c + tx * 8);
+        ch2[0] = make_float4(ss[0], ss[1], ss[2], ss[3]);
+        ch2[1] = make_float4(ss[4], ss[5], ss[6], ss[7]);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < a.groups) {
+        const int c0 = threadIdx.x * a.cpg;
+        float g1 = 0.f, g2 = 0.f;
+        for (int c = c0; c < c0 + a.cpg; ++c) { g1 += red[c]; g2 += red[a.c + c]; }
+        acc[2 * threadIdx.x] = g1;
+        acc[2 * threadIdx.x + 1] = g2;
+    }
+    __syncthreads();
+}
+
+// this CTA's group moments -> its own slot of the statistics workspace [n][blocks_per_img][2 * groups]
+__device__ __forceinline__ void gn_store_slot(const GnArgs& a, int img, const float* acc) {
+    float* slot = a.stats + ((size_t)img * gridDim.x + blockIdx.x) * 2 * a.groups;
+    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads) slot[i] = acc[i];
+}
+
+// grid level: the slots of image `img` summed in a fixed order (identical in every CTA and every replay):
+// kGnThreads / (2 * groups) interleaved chains over the slots, then the chains in order.  -> acc (shared)
+__device__ __forceinline__ void gn_sum_slots(const GnArgs& a, int img, float* red, float* acc) {
+    const int pairs = 2 * a.groups;
+    const int chains = kGnThreads / pairs;  // >= 4 (groups <= 64)
+    const int pair = threadIdx.x % pairs, q = threadIdx.x / pairs;
+    const int bpi = gridDim.x;
+    if (q < chains) {
+        const float* base = a.stats + (size_t)img * bpi * pairs + pair;
+        float part = 0.f;
+        constexpr int kU = 8;
+        for (int b0 = q; b0 < bpi; b0 += chains * kU) {
+            float v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int b = b0 + u * chains;
+                if (b < bpi) v[u] = __ldcg(base + (size_t)b * pairs);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (b0 + u * chains < bpi) part += v[u];
+        }
+        red[q * pairs + pair] = part;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < pairs) {
+        float t = 0.f;
+        for (int c = 0; c < chains; ++c) t += red[c * pairs + threadIdx.x];
+        acc[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
 // per-channel scale / shift from the finished shifted moments
-__device__ __forceinline__ void gn_scale_shift(const GnArgs& a, int img, const float* sK, float inv_cnt,
+__device__ __forceinline__ void gn_scale_shift(const GnArgs& a, const float* acc, const float* sK, float inv_cnt,
                                                int ch, float gamma, float beta, float& sc, float& sh) {
     const int g = ch / a.cpg;
-    const float s1 = __ldcg(&a.stats[((size_t)img * a.groups + g) * 2]) * inv_cnt;
-    const float s2 = __ldcg(&a.stats[((size_t)img * a.groups + g) * 2 + 1]) * inv_cnt;
+    const float s1 = acc[2 * g] * inv_cnt;
+    const float s2 = acc[2 * g + 1] * inv_cnt;
     const float mean = sK[g] + s1;
     const float var = fmaxf(s2 - s1 * s1, 0.f);
     sc = rsqrtf(var + a.eps) * gamma;
@@ -186,21 +261,21 @@ __device__ __forceinline__ void gn_scale_shift(const GnArgs& a, int img, const f
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
     __shared__ float acc[2 * 64];
     __shared__ float sK[64];
+    __shared__ __align__(16) float red[kGnRedFloats];
     pdl_launch_dependents();
     pdl_wait();
     const int img = blockIdx.y;
     const int by = kGnThreads / a.nvec;
     const int tx = threadIdx.x % a.nvec;
     const int ty = threadIdx.x / a.nvec;
-    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads) acc[i] = 0.f;
     gn_load_shifts<false>(a, img, sK);
     __syncthreads();
+    GnAcc8 st;
+    st.zero();
     if (ty < by) {
         float k[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
-        GnAcc8 st;
-        st.zero();
         const int row0 = blockIdx.x * a.rows_per_block;
         const int row1 = min(row0 + a.rows_per_block, a.hw);
         const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
@@ -216,11 +291,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
             for (int u = 0; u < kU; ++u)
                 if (rb + u * by < row1) st.add(v[u], k, a.dtype);
         }
-        st.flush(acc, tx * 8, a.cpg);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads)
-        atomicAdd(&a.stats[(size_t)img * a.groups * 2 + i], acc[i]);
+    gn_block_reduce(st, ty < by, tx, ty, by, a, red, acc);
+    gn_store_slot(a, img, acc);
 }
 
 // grid (blocks_per_img, n): per-channel scale/shift for this image staged in shared memory, then
@@ -228,6 +301,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     extern __shared__ float sm[];
     __shared__ float sK[64];
+    __shared__ float acc[2 * 64];
+    __shared__ float red[kGnThreads];
     pdl_launch_dependents();
     pdl_wait();
     float* scale = sm;
@@ -235,9 +310,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     const int img = blockIdx.y;
     const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
     gn_load_shifts<false>(a, img, sK);
-    __syncthreads();
+    gn_sum_slots(a, img, red, acc);  // (the statistics kernel ran with the same grid: one slot per CTA of it)
     for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads)
-        gn_scale_shift(a, img, sK, inv_cnt, ch, a.gamma[ch], a.beta[ch], scale[ch], shift[ch]);
+        gn_scale_shift(a, acc, sK, inv_cnt, ch, a.gamma[ch], a.beta[ch], scale[ch], shift[ch]);
     __syncthreads();
     const int row0 = blockIdx.x * a.rows_per_block;
     const int row1 = min(row0 + a.rows_per_block, a.hw);
@@ -290,6 +365,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
     extern __shared__ __align__(16) uint8_t fsm[];
     __shared__ float acc[2 * 64];
     __shared__ float sK[64];
+    __shared__ __align__(16) float red[kGnRedFloats];
     float* scale = reinterpret_cast<float*>(fsm);
     float* shift = scale + a.c;
     uint4* slab = reinterpret_cast<uint4*>(fsm + 2 * a.c * sizeof(float));
@@ -299,10 +375,11 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
     const int by = kGnThreads / a.nvec;
     const int tx = threadIdx.x % a.nvec;
     const int ty = threadIdx.x / a.nvec;
-    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads) acc[i] = 0.f;
     const int row0 = blockIdx.x * a.rows_per_block;
     const int row1 = min(row0 + a.rows_per_block, a.hw);
     const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
+    GnAcc8 st;
+    st.zero();
     if constexpr (kPart) {
         // channels [0, part_c) come from the producer GEMM's split-K partials (a few rows per thread,
         // each with all its partial loads in flight); the shifts need a finished value -> shared memory
@@ -314,18 +391,14 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
                     ? gn_finish_partials(a, img, row, tx)
                     : *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
         }
-        __syncthreads();  // shifts and accumulators visible; each thread re-reads only its own slab rows
+        __syncthreads();  // shifts visible; each thread re-reads only its own slab rows
         if (ty < by) {
             float k[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
-            GnAcc8 st;
-            st.zero();
             for (int row = row0 + ty; row < row1; row += by) st.add(slab[(row - row0) * a.nvec + tx], k, a.dtype);
-            st.flush(acc, tx * 8, a.cpg);
         }
     } else {
-        __syncthreads();  // acc zeroed
         if (ty < by) {
             // every thread fetches the shifts of its own 8 channels itself (a group's shift is one
             // 2-byte load of a line all threads of the group share): they are in flight together with
@@ -345,8 +418,6 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
                     k[i] = kv;
                 }
             }
-            GnAcc8 st;
-            st.zero();
             // all of a thread's loads of one batch are in flight together: the slab is a handful of
             // rows per thread, so a load-use-load chain would be nothing but exposed L2 latency
             constexpr int kU = 8;
@@ -366,12 +437,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
                     }
                 }
             }
-            st.flush(acc, tx * 8, a.cpg);
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * a.groups; i += kGnThreads)
-        atomicAdd(&a.stats[(size_t)img * a.groups * 2 + i], acc[i]);
+    gn_block_reduce(st, ty < by, tx, ty, by, a, red, acc);
+    gn_store_slot(a, img, acc);
     // affine parameters do not depend on the statistics: fetch them (cold, from HBM) while the
     // grid barrier is pending
     for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
@@ -392,11 +461,12 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
         __threadfence();
     }
     __syncthreads();
-    // ---- phase 2
+    // ---- phase 2: every CTA of the image sums the image's slots in the same fixed order
+    gn_sum_slots(a, img, red, acc);
     const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
     for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
         float sc, sh;
-        gn_scale_shift(a, img, sK, inv_cnt, ch, scale[ch], shift[ch], sc, sh);
+        gn_scale_shift(a, acc, sK, inv_cnt, ch, scale[ch], shift[ch], sc, sh);
         scale[ch] = sc;
         shift[ch] = sh;
     }
@@ -423,7 +493,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const GnArgs a, un
     }
 }
 
-constexpr int kGnFusedMaxSmem = 200 * 1024;
+constexpr int kGnFusedMaxSmem = 190 * 1024;  // + 33 KB of static scratch for the ordered reductions
 
 // grid geometry of the fused kernel; returns false if the tensor does not fit in shared memory
 static bool gn_fused_geometry(const sfb_gn_params* p, int& blocks_per_img, int& rows_per_block,
@@ -557,6 +627,11 @@ extern "C" int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream)
     return check_launch("sfb_group_norm_apply");
 }
 
+
+extern "C" int sfb_group_norm_ws_floats(int32_t n, int32_t groups) {
+    // two-pass grid: n * ceil(2 * SMs / n) <= 2 * SMs + n CTAs; fused grid: <= SMs CTAs
+    return (2 * sm_count() + (n > 0 ? n : 1)) * 2 * (groups > 0 ? groups : 1);
+}
 
 extern "C" int sfb_group_norm_fused_fits(const sfb_gn_params* p) {
     int bpi, rpb;

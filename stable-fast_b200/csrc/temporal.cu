@@ -154,7 +154,8 @@ struct RowOpArgs {
     const uint16_t* x2;  // blend: the temporal stream [rows, ldx2]; else unused
     const uint16_t* vec; // broadcast add: [nvec, ldv] 16-bit
     uint16_t* y;         // [rows, ldy]
-    float* rowstats;     // [rows, 2] fp32 (sum, sum of squares of the stored row), OVERWRITTEN; or null
+    float* rowstats;     // [rows, rs_slots, 2] fp32: slot 0 = (sum, sum of squares) of the stored row, WRITTEN; or null
+    int rs_slots;
     const float* mix;    // blend: pointer to mix_factor (alpha = sigmoid(*mix))
     int rows, c, ldx, ldx2, ldv, ldy, dtype;
     int mode, div, mod, frames, seq, batch;  // index mode (sfb_row_index_mode) and its parameters
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) row_op_kernel(const RowOpArgs a) {
             s += __shfl_xor_sync(0xffffffffu, s, o);
             ss += __shfl_xor_sync(0xffffffffu, ss, o);
         }
-        if (lane == 0) *reinterpret_cast<float2*>(a.rowstats + 2 * (size_t)m) = make_float2(s, ss);
+        if (lane == 0) *reinterpret_cast<float2*>(a.rowstats + 2 * (size_t)m * a.rs_slots) = make_float2(s, ss);
     }
 }
 
@@ -245,6 +246,7 @@ static int make_row_args(const sfb_row_op_params* p, RowOpArgs& a, bool blend) {
     a.x = reinterpret_cast<const uint16_t*>(p->x); a.x2 = reinterpret_cast<const uint16_t*>(p->x2);
     a.vec = reinterpret_cast<const uint16_t*>(p->vec); a.y = reinterpret_cast<uint16_t*>(p->y);
     a.rowstats = p->rowstats_out; a.mix = p->mix_factor;
+    a.rs_slots = p->rowstats_slots > 0 ? p->rowstats_slots : 1;
     a.rows = p->rows; a.c = p->c; a.ldx = p->ldx; a.ldx2 = p->ldx2; a.ldv = p->ldv; a.ldy = p->ldy;
     a.dtype = p->dtype; a.mode = p->mode; a.div = p->div; a.mod = p->mod;
     a.frames = p->frames; a.seq = p->seq; a.batch = p->batch;

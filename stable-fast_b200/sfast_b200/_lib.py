@@ -37,6 +37,7 @@ class GemmParams(C.Structure):
         ("cta_pair", C.c_int32), ("persistent", C.c_int32), ("b_plain", C.c_int32),
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_dim", C.c_int32), ("act", C.c_int32),
+        ("rowstats_out_slots", C.c_int32), ("ln_slots", C.c_int32),
     ]
 
 
@@ -95,7 +96,7 @@ class RowOpParams(C.Structure):
                 ("rows", C.c_int32), ("c", C.c_int32), ("ldx", C.c_int32), ("ldx2", C.c_int32),
                 ("ldv", C.c_int32), ("ldy", C.c_int32), ("dtype", C.c_int32),
                 ("mode", C.c_int32), ("div", C.c_int32), ("mod", C.c_int32), ("frames", C.c_int32),
-                ("seq", C.c_int32), ("batch", C.c_int32)]
+                ("seq", C.c_int32), ("batch", C.c_int32), ("rowstats_slots", C.c_int32)]
 
 
 class AddNchwItem(C.Structure):
@@ -122,6 +123,7 @@ SYMBOLS = {
     "sfb_group_norm_stats": (C.c_int, [C.POINTER(GnParams), _VP]),
     "sfb_group_norm_apply": (C.c_int, [C.POINTER(GnParams), _VP]),
     "sfb_group_norm_fused_fits": (C.c_int, [C.POINTER(GnParams)]),
+    "sfb_group_norm_ws_floats": (C.c_int, [_I32, _I32]),
     "sfb_group_norm_fused": (C.c_int, [C.POINTER(GnParams), _VP]),
     "sfb_layer_norm": (C.c_int, [C.POINTER(LnParams), _VP]),
     "sfb_timestep_embed": (C.c_int, [_VP, _I32, _I32, _I32, _F, _VP, _I32, _I32, _VP]),
@@ -138,7 +140,8 @@ SYMBOLS = {
     "sfb_row_softmax": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_pointwise_nchw": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_memset": (C.c_int, [_VP, _I32, C.c_size_t, _VP]),
-    "sfb_embed_tokens": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_embed_tokens": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "sfb_rowstats_slots": (C.c_int, [_I32]),
     "sfb_clip_pool": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "sfb_patchify": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
 }

@@ -122,8 +122,9 @@ class ClipTextPlan(UNetPlan):
         spec, rows = self.spec, batch * seq
         self.ids_in = self._alloc((batch, seq), torch.int64)
         self.gn_stats = self._alloc((1, 4), torch.float32)
+        self.gn_sync = self._alloc((1, 4), torch.int32)
         # row statistics of every folded LayerNorm: 2 per layer + the embedding's
-        self.ln_arena = self._alloc(((2 * spec.layers + 1) * rows * 2,), torch.float32)
+        self.ln_arena = self._alloc(((2 * spec.layers + 1) * rows * 2 * ops.rowstats_slots(spec.hidden),), torch.float32)
         self._ln_used, self._ln_slots = 0, []
         self.ws, self._ws_need = None, 0
         self.hidden = []       # [layers + 1] activations: embedding output, then every layer's output
@@ -141,11 +142,11 @@ class ClipTextPlan(UNetPlan):
         self._emit(Op("ln_stats.zero", lib.sfb_memset, (_ptr(self.ln_arena), 0, self.ln_arena.numel() * 4),
                       (self.ln_arena,)))
         hs = self.act("clip_h0", B, 1, S, C)
-        st = self._ln_view(self.ln_slot(rows))
+        st = self._ln_view(self.ln_slot(rows, C))
         tok = self.w.small("text_model.embeddings.token_embedding.weight")
         pos = self.w.small("text_model.embeddings.position_embedding.weight")
         self._emit(Op("embeddings", lib.sfb_embed_tokens,
-                      (_ptr(self.ids_in), _ptr(tok), _ptr(pos), hs.ptr, _ptr(st), B, S, C, spec.vocab_size, hs.ld,
+                      (_ptr(self.ids_in), _ptr(tok), _ptr(pos), hs.ptr, _ptr(st), st.slots, B, S, C, spec.vocab_size, hs.ld,
                        ops.dtype_code(self.dt)), (self.ids_in, tok, pos, hs.buf, st), 0, 4 * rows * C))
         self.hidden.append(hs)
         dv = _round_up(D + 1, 16)
@@ -173,7 +174,7 @@ class ClipTextPlan(UNetPlan):
                                         q_pitch=q_pitch, vt_pitch=vt_pitch, dt=self.dt, dry=self.dry, kv_tile=64,
                                         causal=True))
             mid = self.act("clip_mid", B, 1, S, C)
-            st2 = self._ln_view(self.ln_slot(rows))
+            st2 = self._ln_view(self.ln_slot(rows, C))
             self.linear(a + ".out_proj", ao, self.w.matrix(f"{a}.out_proj.weight"), self.w.f32(f"{a}.out_proj.bias"),
                         mid, residual=hs, rowstats_out=st2, splits=1)
             w1, b1, cs1 = self.w.ln_matrix([p + ".mlp.fc1.weight"], p + ".layer_norm2",
@@ -184,7 +185,7 @@ class ClipTextPlan(UNetPlan):
                                   ln=dict(rowstats=st2, colsum=cs1, eps=spec.eps, dim=C),
                                   keep=(mid.buf, ff.buf, w1, cs1)))
             nxt = self.act(f"clip_h{l + 1}", B, 1, S, C)
-            st = self._ln_view(self.ln_slot(rows)) if l + 1 < spec.layers else None
+            st = self._ln_view(self.ln_slot(rows, C)) if l + 1 < spec.layers else None
             self.linear(p + ".mlp.fc2", ff, self.w.matrix(p + ".mlp.fc2.weight"), self.w.f32(p + ".mlp.fc2.bias"),
                         nxt, residual=mid, rowstats_out=st, splits=1)
             hs = nxt
@@ -305,7 +306,8 @@ class ClipVisionPlan(UNetPlan):
         rows = batch * spec.tokens
         self.pixels_in = self._alloc((batch, spec.channels, spec.image_size, spec.image_size), self.dt)
         self.gn_stats = self._alloc((1, 4), torch.float32)
-        self.ln_arena = self._alloc((2 * spec.layers * rows * 2,), torch.float32)
+        self.gn_sync = self._alloc((1, 4), torch.int32)
+        self.ln_arena = self._alloc((2 * spec.layers * rows * 2 * ops.rowstats_slots(spec.hidden),), torch.float32)
         self._ln_used, self._ln_slots = 0, []
         self.ws, self._ws_need = None, 0
         self.hidden = []
@@ -411,7 +413,7 @@ class ClipVisionPlan(UNetPlan):
                                         head_dim=D, seq_q=S, seq_kv=S, q_rows=S, k_rows=S, vt_rows=dv,
                                         q_pitch=q_pitch, vt_pitch=vt_pitch, dt=self.dt, dry=self.dry))
             mid = self.act("clipv_mid", B, 1, S, C)
-            st2 = self._ln_view(self.ln_slot(rows))
+            st2 = self._ln_view(self.ln_slot(rows, C))
             self.linear(a + ".out_proj", ao, self.w.matrix(f"{a}.out_proj.weight"), self.w.f32(f"{a}.out_proj.bias"),
                         mid, residual=hs, rowstats_out=st2, splits=1)
             w1, b1, cs1 = self.w.ln_matrix([p + ".mlp.fc1.weight"], p + ".layer_norm2",
@@ -422,7 +424,7 @@ class ClipVisionPlan(UNetPlan):
                                   ln=dict(rowstats=st2, colsum=cs1, eps=spec.eps, dim=C),
                                   keep=(mid.buf, ff.buf, w1, cs1)))
             nxt = self.act(f"clipv_h{l + 1}", B, 1, S, C)
-            st = self._ln_view(self.ln_slot(rows)) if l + 1 < spec.layers else None
+            st = self._ln_view(self.ln_slot(rows, C)) if l + 1 < spec.layers else None
             self.linear(p + ".mlp.fc2", ff, self.w.matrix(p + ".mlp.fc2.weight"), self.w.f32(p + ".mlp.fc2.bias"),
                         nxt, residual=mid, rowstats_out=st, splits=1)
             hs = nxt

@@ -224,7 +224,8 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         p.ws = _ptr(ws) if not hasattr(ws, "finalize") else 0
     if persistent is None:
         persistent = PERSIST == "1" or (PERSIST == "auto" and m_tiles * n_tiles >= PERSIST_MIN_CTAS)
-    p.persistent = 1 if (persistent and p.cta_pair and splits == 1 and epi != _lib.EPI_STORE_F32 and not act) else 0
+    p.persistent = 1 if (persistent and p.cta_pair and splits == 1 and epi != _lib.EPI_STORE_F32 and not act
+                         and rowstats_out is None) else 0
     p.act = act
     p.epi = epi
     p.out = _ptr(out)
@@ -241,9 +242,11 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
                   "vt_rows", "vt_pitch"):
             setattr(p, f, qkv[f])
     p.rowstats_out = _ptr(rowstats_out)
+    p.rowstats_out_slots = getattr(rowstats_out, "slots", rowstats_slots(N)) if rowstats_out is not None else 0
     if ln is not None:
         p.ln_rowstats, p.ln_colsum = _ptr(ln["rowstats"]), _ptr(ln["colsum"])
         p.ln_eps, p.ln_dim = ln["eps"], ln["dim"]
+        p.ln_slots = getattr(ln["rowstats"], "slots", 1)
     esz = 2
     flops = 2 * M * N * K
     nbytes = (M * K + N * K) * esz + M * (geglu_n_out if epi == EPI_GEGLU else N) * esz
@@ -300,7 +303,35 @@ def gn_fused_fits(n, hw, c, groups):
         return False
     bpi = max(1, min(num_sms() // n, hw))
     rpb = (hw + bpi - 1) // bpi
-    return rpb * c * 2 + 2 * c * 4 <= 200 * 1024
+    return rpb * c * 2 + 2 * c * 4 <= 190 * 1024
+
+
+def rowstats_slots(n_cols):
+    """Slots per row of a folded LayerNorm's statistics buffer whose producer has n_cols output columns
+    (mirror of sfb_rowstats_slots): one per 160-column GEMM tile, or per warp segment of the split-K
+    reduction kernel, whichever is more."""
+    return max((n_cols + BN - 1) // BN, (n_cols // 8 - 1 + 31) // 32 + 1)
+
+
+class RowStats:
+    """[rows, slots, 2] fp32 view of a statistics arena; quacks like a tensor for _ptr()."""
+    __slots__ = ("t", "slots")
+
+    def __init__(self, t, slots):
+        self.t, self.slots = t, slots
+
+    @property
+    def device(self):
+        return self.t.device
+
+    def data_ptr(self):
+        return self.t.data_ptr()
+
+
+def gn_ws_floats(n, groups):
+    """Floats of the statistics workspace of one GroupNorm over n images (mirror of
+    sfb_group_norm_ws_floats): one [groups][2] slot per CTA of the statistics pass."""
+    return (2 * num_sms() + max(n, 1)) * 2 * groups
 
 
 def gn_fused_ok(lib, x: Act, groups, dt, dry):

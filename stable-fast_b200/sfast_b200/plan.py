@@ -250,12 +250,10 @@ class UNetPlan:
         if spec.addition_embed_type == "text_time":
             self.add_in = self._alloc((batch, spec.add_in_dim), self.dt)
             self.time_ids_in = self._alloc((batch * 6,), torch.float32)
-        # group-norm statistics arena: one [B, groups, 2] slot per GroupNorm, zeroed once per step
         n_gn = sum(2 for _ in spec.all_resnets()) + 1
         for blk in spec.down + [spec.mid] + spec.up:
             n_gn += sum(1 for t in blk.attentions if t is not None)
-        # [B, groups, 2] statistics + 4 floats for the fused kernel's grid-barrier counter
-        self.gn_stats = self._alloc((n_gn, batch * spec.groups * 2 + 4), torch.float32)
+        self._alloc_gn(n_gn, batch)
         # folded-LayerNorm row statistics: [rows, 2] fp32 per LayerNorm, zeroed once per step
         self._ln_used = 0
         self._ln_slots = []
@@ -265,24 +263,35 @@ class UNetPlan:
         self._build()
         assert self._ln_used <= self.ln_arena.numel(), (self._ln_used, self.ln_arena.numel())
 
+    def _alloc_gn(self, n_gn, max_images):
+        """Per-GroupNorm statistics workspace (one [groups][2] slot per CTA of the statistics pass, summed
+        in a fixed order by the apply pass: no initialisation needed) and the fused kernel's grid-barrier
+        counters (zeroed once per step)."""
+        self.gn_stats = self._alloc((n_gn, ops.gn_ws_floats(max_images, self.spec.groups)), torch.float32)
+        self.gn_sync = self._alloc((n_gn, 4), torch.int32)
+
     def _ln_arena_floats(self):
-        """3 * depth LayerNorms per transformer, each [B*h*w, 2] floats at its resolution."""
+        """3 * depth LayerNorms per transformer, each [B*h*w, slots(dim), 2] floats at its resolution."""
         spec, tot = self.spec, 0
         h, w = self.H, self.W
+
+        def need(blk):
+            return sum(3 * t.depth * self.B * h * w * 2 * ops.rowstats_slots(t.dim)
+                       for t in blk.attentions if t is not None)
         for blk in spec.down:
-            tot += sum(3 * t.depth * self.B * h * w * 2 for t in blk.attentions if t is not None)
+            tot += need(blk)
             if blk.sampler:
                 h, w = h // 2, w // 2
-        tot += 3 * spec.mid.attentions[0].depth * self.B * h * w * 2
+        tot += need(spec.mid)
         for blk in spec.up:
-            tot += sum(3 * t.depth * self.B * h * w * 2 for t in blk.attentions if t is not None)
+            tot += need(blk)
             if blk.sampler:
                 h, w = h * 2, w * 2
         return tot
 
     def _ln_view(self, slot):
-        _, off, rows = slot
-        return self.ln_arena[off:off + rows * 2]
+        _, off, rows, slots = slot
+        return ops.RowStats(self.ln_arena[off:off + rows * slots * 2], slots)
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self, shape, dtype, zero=True):
@@ -328,7 +337,7 @@ class UNetPlan:
 
     def group_norm(self, name, x: Act, prefix, silu, eps):
         y = self.act("gn_out", x.n, x.h, x.w, x.c)
-        slot = self.gn_stats[self._gn_count]
+        slot, sync = self.gn_stats[self._gn_count], self.gn_sync[self._gn_count]
         self._gn_count += 1
         partial, pend = None, self._pending
         if pend is not None:
@@ -339,7 +348,7 @@ class UNetPlan:
                 partial = pend["info"]
                 self._pending = None  # absorbed: the GEMM keeps defer_finish = 1
         gn = ops.gn_ops(name, self.lib_or_dry(), x=x, y=y, gamma=self.w.f32(prefix + ".weight"),
-                        beta=self.w.f32(prefix + ".bias"), stats=slot, sync=slot[-4:],
+                        beta=self.w.f32(prefix + ".bias"), stats=slot, sync=sync,
                         groups=self.spec.groups, eps=eps, silu=silu, dt=self.dt,
                         dry=self.dry, partial=partial)
         if partial is not None:
@@ -492,25 +501,27 @@ class UNetPlan:
                              eps=1e-5, dt=self.dt))
         return y
 
-    def ln_slot(self, rows):
-        """[rows, 2] fp32 (sum, sum of squares) accumulator of one folded LayerNorm."""
+    def ln_slot(self, rows, dim):
+        """[rows, slots, 2] fp32 (sum, sum of squares) statistics of one folded LayerNorm over `dim`
+        columns: every producer writes its own slots, the consumer adds them in order."""
+        slots = ops.rowstats_slots(dim)
         off = self._ln_used
-        self._ln_used += rows * 2
+        self._ln_used += rows * slots * 2
         self._ln_slots.append((off, rows))
-        return ("ln_slot", off, rows)
+        return ("ln_slot", off, rows, slots)
 
     def transformer(self, t, x: Act, dst: Act):
         p = t.prefix
         a1 = self.group_norm(p + ".norm", x, p + ".norm", False, 1e-6)
         hs = self.act("tf_hidden", x.n, x.h, x.w, t.dim)
-        st = self._ln_view(self.ln_slot(hs.rows))
+        st = self._ln_view(self.ln_slot(hs.rows, t.dim))
         self.linear(p + ".proj_in", a1, self.w.matrix(p + ".proj_in.weight"),
                     self.w.f32(p + ".proj_in.bias"), hs, rowstats_out=st)
         for d in range(t.depth):
             b = f"{p}.transformer_blocks.{d}"
-            st2 = self._ln_view(self.ln_slot(hs.rows))
+            st2 = self._ln_view(self.ln_slot(hs.rows, t.dim))
             self.attention(b + ".attn1", hs, b + ".norm1", st, b, t, cross=False, stats_next=st2)
-            st3 = self._ln_view(self.ln_slot(hs.rows))
+            st3 = self._ln_view(self.ln_slot(hs.rows, t.dim))
             self.attention(b + ".attn2", hs, b + ".norm2", st2, b, t, cross=True, stats_next=st3)
             gm, bp, inner, colsum = self.w.ln_geglu(b + ".ff.net.0.proj", b + ".norm3")
             ff = self.act("ff_act", x.n, x.h, x.w, inner)
@@ -519,7 +530,7 @@ class UNetPlan:
                                   bias=bp, epi=EPI_GEGLU, geglu_n_out=inner,
                                   ln=dict(rowstats=st3, colsum=colsum, eps=1e-5, dim=t.dim),
                                   keep=(hs.buf, ff.buf, gm, colsum)))
-            st = self._ln_view(self.ln_slot(hs.rows)) if d + 1 < t.depth else None
+            st = self._ln_view(self.ln_slot(hs.rows, t.dim)) if d + 1 < t.depth else None
             self.linear(b + ".ff.out", ff, self.w.matrix(b + ".ff.net.2.weight"),
                         self.w.f32(b + ".ff.net.2.bias"), hs, residual=hs, rowstats_out=st)
         self.linear(p + ".proj_out", hs, self.w.matrix(p + ".proj_out.weight"),
@@ -586,9 +597,9 @@ class UNetPlan:
     def _build(self):
         spec, B, H, W, lib = self.spec, self.B, self.H, self.W, self.lib_or_dry()
         self._ws_token = _WsToken()
-        self._emit(Op("gn_stats.zero", lib.sfb_memset,
-                      (_ptr(self.gn_stats), 0,
-                       self.gn_stats.numel() * 4), (self.gn_stats,)))
+        self._emit(Op("gn_sync.zero", lib.sfb_memset,
+                      (_ptr(self.gn_sync), 0,
+                       self.gn_sync.numel() * 4), (self.gn_sync,)))
         self._emit(Op("ln_stats.zero", lib.sfb_memset,
                       (_ptr(self.ln_arena), 0, self.ln_arena.numel() * 4), (self.ln_arena,)))
         # the time-embedding chain only depends on the timestep: forked stream, joined before the

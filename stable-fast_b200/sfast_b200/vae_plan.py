@@ -120,7 +120,7 @@ class VAEDecodePlan(UNetPlan):
         up = 1 << (len(spec.block_out_channels) - 1)
         self.out = self._alloc((batch, spec.out_channels, height * up, width * up), self.dt)
         n_gn = 2 * (2 + len(spec.block_out_channels) * (spec.layers_per_block + 1)) + 2
-        self.gn_stats = self._alloc((n_gn, batch * spec.groups * 2 + 4), torch.float32)
+        self._alloc_gn(n_gn, batch)
         self.ln_arena = self._alloc((2,), torch.float32)
         self._ln_used, self._ln_slots = 0, []
         self.ws, self._ws_need = None, 0
@@ -179,8 +179,8 @@ class VAEDecodePlan(UNetPlan):
     def _build(self):
         spec, B, H, W, lib = self.spec, self.B, self.H, self.W, self.lib_or_dry()
         self._ws_token = _WsToken()
-        self._emit(Op("gn_stats.zero", lib.sfb_memset, (_ptr(self.gn_stats), 0, self.gn_stats.numel() * 4),
-                      (self.gn_stats,)))
+        self._emit(Op("gn_sync.zero", lib.sfb_memset, (_ptr(self.gn_sync), 0, self.gn_sync.numel() * 4),
+                      (self.gn_sync,)))
         lc, boc = spec.latent_channels, spec.block_out_channels
         c = boc[-1]
         # post_quant_conv (1x1, NCHW -> NCHW) then conv_in (NCHW -> NHWC)

@@ -209,7 +209,7 @@ def check_embed_tokens(B=3, S=77, C=768, V=1000, dt=torch.float16, seed=11):
     out = torch.zeros(B * S, C, device=DEV, dtype=dt)
     stats = torch.full((B * S, 2), 7.0, device=DEV)  # written, not accumulated
     _lib.check(lib.sfb_embed_tokens(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), out.data_ptr(), stats.data_ptr(),
-                                    B, S, C, V, C, ops.dtype_code(dt), _stream()), "embed")
+                                    1, B, S, C, V, C, ops.dtype_code(dt), _stream()), "embed")
     torch.cuda.synchronize()
     ref = (tok[ids].float() + pos[None].float()).reshape(B * S, C)
     e = rel_err(out, ref)
@@ -313,9 +313,10 @@ def check_group_norm(n=2, c=320, h=32, w=32, silu=True, dt=torch.float16, pitch_
     y = Act(yb, n, h, w, c)
     gamma = torch.randn(c, device=DEV)
     beta = torch.randn(c, device=DEV)
-    stats = torch.zeros(n * 32 * 2 + 4, device=DEV)
+    stats = torch.full((ops.gn_ws_floats(n, 32),), float("nan"), device=DEV)  # workspace: never needs zeroing
+    sync = torch.zeros(4, device=DEV, dtype=torch.int32)
     gops = ops.gn_ops("gn", lib, x=x, y=y, gamma=gamma, beta=beta, stats=stats, groups=32, eps=eps,
-                      silu=silu, dt=dt, sync=stats[-4:] if fused else None)
+                      silu=silu, dt=dt, sync=sync if fused else None)
     assert len(gops) == (1 if fused else 2), [o.name for o in gops]
     for op in gops:
         op.launch(_stream())
@@ -328,6 +329,28 @@ def check_group_norm(n=2, c=320, h=32, w=32, silu=True, dt=torch.float16, pitch_
     if silu:
         ref = F.silu(ref)
     return rel_err(yb, ref.permute(0, 2, 3, 1))
+
+
+def check_group_norm_bitwise_replay(n=2, c=960, h=64, w=64, fused=True, dt=torch.float16):
+    """Two launches over the same input give bit-identical outputs (ordered reductions, no fp atomics)."""
+    lib = _lib.lib()
+    torch.manual_seed(5)
+    xb = (torch.randn(n, h, w, c, device=DEV) * 3 + 1).to(dt)
+    x = Act(xb, n, h, w, c)
+    gamma, beta = torch.randn(c, device=DEV), torch.randn(c, device=DEV)
+    outs = []
+    for rep in range(3):
+        yb = torch.zeros(n, h, w, c, device=DEV, dtype=dt)
+        stats = torch.full((ops.gn_ws_floats(n, 32),), float(rep), device=DEV)  # stale garbage must not matter
+        sync = torch.zeros(4, device=DEV, dtype=torch.int32)
+        gops = ops.gn_ops("gn", lib, x=x, y=Act(yb, n, h, w, c), gamma=gamma, beta=beta, stats=stats, groups=32,
+                          eps=1e-5, silu=True, dt=dt, sync=sync if fused else None)
+        assert len(gops) == (1 if fused else 2)
+        for op in gops:
+            op.launch(_stream())
+        torch.cuda.synchronize()
+        outs.append(yb)
+    return 0.0 if (torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])) else 1.0
 
 
 def check_gn_finish(n=2, h=16, w=16, cin=1280, cout=1280, extra=0, splits=4, rowbias=True,
@@ -360,14 +383,15 @@ def check_gn_finish(n=2, h=16, w=16, cin=1280, cout=1280, extra=0, splits=4, row
     x = Act(cat, n, h, w, C)
     yb = torch.zeros(n, h, w, C, device=DEV, dtype=dt)
     gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
-    stats = torch.zeros(n * 32 * 2 + 4, device=DEV)
+    stats = torch.full((ops.gn_ws_floats(n, 32),), float("nan"), device=DEV)
+    sync = torch.zeros(4, device=DEV, dtype=torch.int32)
     part = dict(splits=splits, c=cout, ld=cout, bias=b, ws=ws)
     if rowbias:
         part.update(rowbias=rb.data_ptr(), ld_rowbias=cout)
     if residual:
         part.update(residual=r.data_ptr(), ldr=cout)
     gops = ops.gn_ops("gn", lib, x=x, y=Act(yb, n, h, w, C), gamma=gamma, beta=beta, stats=stats,
-                      groups=32, eps=1e-5, silu=silu, dt=dt, sync=stats[-4:], partial=part)
+                      groups=32, eps=1e-5, silu=silu, dt=dt, sync=sync, partial=part)
     assert len(gops) == 1
     n0 = lib.sfb_launch_count()
     conv.launch(_stream())
@@ -505,7 +529,8 @@ def check_ln_fold(M=300, C=320, N=960, dt=torch.float16, mode="store", splits_p=
         res[:, 5] *= 40.0                                      # one outlier channel, as real checkpoints have
     res = res.to(dt)
     x = torch.zeros(M, C, device=DEV, dtype=dt)
-    stats = torch.zeros(M, 2, device=DEV)
+    slots = ops.rowstats_slots(C)
+    stats = ops.RowStats(torch.zeros(M, slots, 2, device=DEV), slots)   # cleared by the caller, slots written once
     ws = torch.empty(16 * M * max(N, C) * 2, device=DEV, dtype=torch.float32)
     ops.gemm_op("producer", lib, a=ops.a_matrix(a.data_ptr(), M, C, C), b=ops.Mat(w0),
                 M=M, N=C, K=C, dt=dt, out=x, ldo=C, residual=res, ldr=C, ws=ws, splits=splits_p,
@@ -883,6 +908,8 @@ CHECKS = {
     "ln_fold_mean30_1280": (lambda: check_ln_fold(256, 1280, 1280, row_offset=30.0), 1e-2),
     "ln_fold_outlier": (lambda: check_ln_fold(300, 640, 640, outlier=True), 1e-2),
     "ln_fold_geglu_mean30": (lambda: check_ln_fold(300, 320, 1280, mode="geglu", row_offset=30.0), 2e-2),
+    "group_norm_bitwise_replay_fused": (lambda: check_group_norm_bitwise_replay(), 0.0),
+    "group_norm_bitwise_replay_two_pass": (lambda: check_group_norm_bitwise_replay(16, 320, 64, 64, fused=False), 0.0),
     "group_norm_silu": (lambda: check_group_norm(2, 320, 32, 32, True), 1e-2),
     "group_norm": (lambda: check_group_norm(2, 320, 32, 32, False, eps=1e-6), 1e-2),
     "group_norm_1920_pitch": (lambda: check_group_norm(2, 1920, 16, 16, True, pitch_extra=640), 1e-2),

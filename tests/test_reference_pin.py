@@ -110,11 +110,12 @@ def test_cuda_group_norm_matches_reference_triton_outputs(silu, fused):
         n, c, h, w = x.shape
         xb = x.permute(0, 2, 3, 1).contiguous()                      # the path's NHWC layout
         yb = torch.zeros_like(xb)
-        stats = torch.zeros(n * case["groups"] * 2 + 4, device="cuda")
+        stats = torch.empty(ops.gn_ws_floats(n, case["groups"]), device="cuda")
+        sync = torch.zeros(4, device="cuda", dtype=torch.int32)
         gops = ops.gn_ops("gn", lib, x=Act(xb, n, h, w, c), y=Act(yb, n, h, w, c),
                           gamma=case["weight"].cuda().float(), beta=case["bias"].cuda().float(),
                           stats=stats, groups=case["groups"], eps=case["eps"], silu=silu,
-                          dt=torch.float16, sync=stats[-4:] if fused else None)
+                          dt=torch.float16, sync=sync if fused else None)
         assert len(gops) == (1 if fused else 2)
         for op in gops:
             op.launch(torch.cuda.current_stream().cuda_stream)

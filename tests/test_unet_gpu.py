@@ -83,11 +83,10 @@ def test_graph_replay_tracks_new_inputs_and_returns_fresh_tensors():
     b = fast(s2, torch.tensor([700, 300], device="cuda"), e2, return_dict=False)[0]
     a2 = fast(s1, 10, e1).sample
     assert a.data_ptr() != b.data_ptr()
-    # GroupNorm / LayerNorm statistics are accumulated with fp32 atomics, so two replays differ in
-    # the last fp32 bits of those sums; through ~60 fp16-stored layers that is the same noise floor
-    # as the error against the fp32 oracle (measured 4.5e-3 in this elementwise metric): the bound is
-    # the parity tolerance itself, not bitwise equality (the reference's replay IS bitwise)
-    assert _rel(a2, a) < TOL
+    # every reduction (GroupNorm / LayerNorm statistics, split-K) runs in a fixed order without
+    # floating-point atomics: a replay on the same inputs is BIT-identical, like the reference's
+    # (/root/reference/tests/cuda/test_graphs.py:8-39)
+    assert torch.equal(a2, a)
     with torch.no_grad():
         ref = oracle(s2.float(), torch.tensor([700, 300], device="cuda"), e2.float()).sample
     assert _rel(b, ref) < TOL
@@ -263,7 +262,7 @@ def test_in_place_parameter_update_is_picked_up_like_the_reference_lora_contract
             if name.endswith("resnets.0.conv1.weight"):
                 p.mul_(1.25)
     f1 = frozen(s, t, e).sample
-    assert _rel(f1, f0) < TOL
+    assert torch.equal(f1, f0)      # frozen weights: same graph, same inputs -> same bits
     frozen.forward._compiled.rebind()
     f2 = frozen(s, t, e).sample
     assert _rel(f2, f0) > 2 * TOL
