@@ -3,7 +3,7 @@
 # full-section captures of each kernel family, on kernel-check invocations that launch exactly that kernel.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-KREGEX='regex:gemm_tc|gemm_persist|attention_|gn_|layer_norm|small_linear|conv_in|conv_out|upsample2x|timestep_embed|splitk|im2col|temporal_|row_op|row_softmax|pointwise|add_nchw|copy2d'
+KREGEX='regex:gemm_tc|gemm_persist|attention_|gn_|layer_norm|small_linear|conv_in|conv_out|upsample2x|timestep_embed|splitk|im2col|temporal_|row_op|row_softmax|pointwise|add_nchw|copy2d|embed_tokens|clip_pool|patchify'
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$KREGEX" -c 1400 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline --no-extras > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log
 full() {  # name  kernel-regex  skip  count  command...
   local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
