@@ -3,8 +3,5 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?"; cut -c1-1200 gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 --global-batch 16 --no-cpu-baseline > gpurun_out/bench_n2_strong.json 2>> gpurun_out/bench_n2.err; echo "rc=$?"; cut -c1-400 gpurun_out/bench_n2_strong.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2>> gpurun_out/bench_n2.err; echo "rc=$?"; cut -c1-600 gpurun_out/bench_ref_n2.json
-timeout 300 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_n1_full.json 2>> gpurun_out/bench_n2.err; cut -c1-2500 gpurun_out/bench_n1_full.json
-tail -3 gpurun_out/bench_n2.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?"; cut -c1-700 gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2>> gpurun_out/bench_n2.err; echo "rc=$?"; cut -c1-500 gpurun_out/bench_ref_n2.json
