@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 3
+#define SFB_ABI_VERSION 4
 
 typedef void* sfb_stream_t; /* cudaStream_t */
 
@@ -93,6 +93,20 @@ enum sfb_gemm_a_mode {
      * per frame, c]; K = 3 * cin in (kt, c) order; tap kt reads frame f - 1 + kt (TMA zero fill =
      * the temporal padding).  img_* / box_* describe that view. */
     SFB_A_CONV3X1 = 3,
+    /* GroupNorm(+SiLU) FOLDED INTO the 3x3 convolution's A-operand path (stride 1, padding 1): A is the
+     * RAW (un-normalised) NHWC activation and gn_scale_shift holds, per (image, channel), the pair
+     * (scale, shift) = (rstd * gamma, beta - mean * rstd * gamma) written by sfb_group_norm_scale_shift.
+     * The M tile is a 16 x 8 pixel patch (box_n = 1, box_h = 16, box_w = 8; img_w % 8 == 0; rows past
+     * the image are masked).  Per 64-channel block the kernel pulls ONE [18 x 10]-pixel halo tile of
+     * the patch through TMA (tmap_a: sfb_tmap_nhwc with box_n = 1, box_h = 18, box_w = 10), applies
+     * y = act(x * scale + shift) to each halo element once, in shared memory (padding pixels forced back
+     * to zero), and all nine filter taps multiply shifted views of that tile: the normalised activation
+     * never exists in HBM and the conv reads its input through L2 once instead of nine times.  Needs
+     * cta_pair, splits == 1, the STORE epilogue (bias / rowbias / residual as for SFB_A_CONV3X3).
+     * Replaces the separate group_norm_silu launch of the reference
+     * (/root/reference/src/sfast/jit/passes/triton_passes.py:68-88,
+     *  src/sfast/triton/ops/group_norm.py:272-320) in front of cudnn_convolution_bias(_add). */
+    SFB_A_CONV3X3_GN = 4,
 };
 
 enum sfb_epilogue {
@@ -185,6 +199,9 @@ typedef struct sfb_gemm_params {
     int32_t act; /* SFB_ACT_* */
     int32_t rowstats_out_slots; /* slots per row of rowstats_out (>= sfb_rowstats_slots(N)) */
     int32_t ln_slots;           /* slots per row of ln_rowstats */
+    /* SFB_A_CONV3X3_GN */
+    const float* gn_scale_shift; /* [img_n, cin, 2] fp32: (scale, shift) per image and input channel */
+    int32_t gn_silu;             /* 1: SiLU after the affine */
 } sfb_gemm_params;
 
 /* slots per row a rowstats_out producer with N output columns needs (any split-K factor) */
@@ -246,9 +263,16 @@ typedef struct sfb_gn_params {
     int32_t part_ldr;
 } sfb_gn_params;
 
-/* two-pass path (any size): `stats` must be zero before sfb_group_norm_stats */
+/* two-pass path (any size) */
 int sfb_group_norm_stats(const sfb_gn_params* p, sfb_stream_t stream);
 int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream);
+/* Statistics pass that ends in the per-(image, channel) affine a consumer applies itself -- the conv with
+ * SFB_A_CONV3X3_GN: scale_shift[img][ch] = (rstd * gamma[ch], beta[ch] - mean * rstd * gamma[ch]), fp32
+ * [n, c, 2].  One launch: every CTA writes its slot of `stats`, the LAST CTA of an image to finish (an
+ * integer ticket in p->sync_counter[img]; n counters, zero before the first launch, reset by the kernel)
+ * adds the image's slots in the fixed order of the other paths and writes the pairs -- bit-identical from
+ * run to run.  p->y / ldy / silu are unused. */
+int sfb_group_norm_scale_shift(const sfb_gn_params* p, float* scale_shift, sfb_stream_t stream);
 /* single-launch path for tensors that fit in the GPU's shared memory: a COOPERATIVE launch of at
  * most one CTA per SM of the current device with a grid-wide barrier; x is read once.  `stats` and
  * `sync_counter` must be zero on entry.  sfb_group_norm_fused_fits() returns 1 when the geometry

@@ -140,6 +140,9 @@ struct GemmArgs {
     int b_plain;    // B is a plain row-major [N, K] matrix (an activation), not a pre-tiled weight
     // persistent kernel: tile grid in units of (pair of M tiles) x (pair of 160-column N tiles)
     int m_pairs, n_tiles160, n_pairs, total_tiles;
+    // SFB_A_CONV3X3_GN: per-(image, channel) GroupNorm (scale, shift) pairs [img_n][cin][2], SiLU flag
+    const float* gn_ab;
+    int gn_silu;
     EpiArgs e;
 #ifdef SFB_TRACE
     unsigned long long* trace;  // [ctas][16] %globaltimer stamps (latency anatomy builds only)
@@ -435,15 +438,28 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, const EpiArgs e) 
 // CG = 1: one CTA per 128 x 160 tile.  CG = 2: a CTA PAIR (cluster 2x1 along M) computes a 256 x 160
 // tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 A rows but only HALF of the
 // weight tile, which cuts the bytes each SM pulls per MMA.
-template <int STAGES, int CG = 1>
+// HALO = 1 (SFB_A_CONV3X3_GN): the A operand is not staged tap by tap.  Per 64-channel block ONE
+// raw [18 x 10] pixel halo tile of the 16 x 8 pixel output patch lands by TMA; the (otherwise idle)
+// epilogue warps apply GroupNorm scale / shift + SiLU to every halo element ONCE and write it into
+// three column-shifted copies (dx = 0, 1, 2), each [18 halo rows][8 columns] x 128 B in the
+// 128-byte-swizzled K-major layout: one halo row = one 8-row swizzle atom (1024 B), so the A tile
+// of tap (dy, dx) is simply copy dx advanced by dy atoms -- every UMMA descriptor stays 1024-byte
+// aligned.  The nine taps of a channel block re-read that copy from shared memory instead of
+// pulling nine shifted boxes through L2.
+template <int STAGES, int CG = 1, int HALO = 0>
 struct GemmSmem {
-    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kABytes = HALO ? 0 : BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2 / CG;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kHaloRows = 18, kHaloCols = 10;
+    static constexpr int kHaloABuf = kHaloRows * 1024;                    // one shifted copy
+    static constexpr int kHaloRawBytes = kHaloRows * kHaloCols * 128;     // the TMA box
+    static constexpr int kHaloRawAlloc = (kHaloRawBytes + 1023) / 1024 * 1024;
+    static constexpr int kHaloBytes = HALO ? 3 * kHaloABuf + kHaloRawAlloc : 0;
+    static constexpr int kBarOffset = kHaloBytes + STAGES * kStageBytes;
     static constexpr int kBiasOffset = kBarOffset + 256;              // fp32 [kBiasSlots][BN]
     // images per conv M-tile whose row bias is staged; 3 stages + 4 slots keeps 2 CTAs per SM
-    static constexpr int kBiasSlots = 4;
+    static constexpr int kBiasSlots = HALO ? 2 : 4;
     static constexpr int kRowMOffset = kBiasOffset + kBiasSlots * BN * 4;  // int [128]: row -> m
     static constexpr int kTotal = kRowMOffset + BM * 4 + 1024;                // + alignment slack
     // fp32 staging tile of the epilogue, aliased onto the (by then idle) pipeline stages; the
@@ -458,20 +474,45 @@ struct GemmSmem {
     static_assert(STAGES > 4 || 2 * (kTotal + 1024) <= 228 * 1024, "shallow configs must fit twice per SM");
 };
 
-template <int STAGES, int BF16, int CG>
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2, on a pair of 16-bit values: one MUFU.TANH per TWO elements
+// (the halo transform runs once per conv input element per launch; the fp32 exp + rcp form is 4x the MUFU work)
+template <int BF16>
+__device__ __forceinline__ uint32_t silu_pair16(uint32_t x) {
+    uint32_t h, t, o;
+    if (BF16) {
+        asm("mul.bf16x2 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(0x3F003F00u));
+        asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(h));
+        asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
+    } else {
+        asm("mul.f16x2 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(0x38003800u));
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
+    }
+    return o;
+}
+
+template <int STAGES, int BF16, int CG, int HALO = 0>
 __global__ void __launch_bounds__(kGemmThreads, STAGES <= 4 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmArgs args) {
-    using L = GemmSmem<STAGES, CG>;
+    using L = GemmSmem<STAGES, CG, HALO>;
+    static_assert(!HALO || (STAGES <= 4 && kEpiWarps == 8), "halo conv: shallow weight ring, 8 transform warps");
     constexpr uint32_t kTmemCols = 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * L::kABytes;
+    uint8_t* sA = smem;                                   // HALO: the three shifted copies
+    uint8_t* sRaw = smem + 3 * L::kHaloABuf;              // HALO: raw halo tile (TMA destination)
+    uint8_t* sB = smem + L::kHaloBytes + STAGES * L::kABytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    // HALO: raw tile landed / consumed (CTA-local); transformed copies ready (counted on the pair
+    // LEADER: every transform warp of both CTAs arrives there) / free again (MMA commit, both CTAs)
+    uint64_t* raw_full = tmem_full_bar + 2;
+    uint64_t* raw_empty = tmem_full_bar + 3;
+    uint64_t* a_full = tmem_full_bar + 4;
+    uint64_t* a_empty = tmem_full_bar + 5;
     float* sBias = reinterpret_cast<float*>(smem + L::kBiasOffset);
     int* sRowM = reinterpret_cast<int*>(smem + L::kRowMOffset);
     float* sStage = reinterpret_cast<float*>(smem);
@@ -496,6 +537,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(tmem_full_bar, 1);
+        if (HALO) {
+            mbar_init(raw_full, 1);
+            mbar_init(raw_empty, kEpiWarps);
+            mbar_init(a_full, kEpiWarps * CG);
+            mbar_init(a_empty, 1);
+        }
         fence_barrier_init();
     }
     const uint16_t pair_mask = 0b11;
@@ -516,6 +563,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (threadIdx.x == 0) SFB_STAMP(1);
 
     if (warp == 0) {
+        if (HALO) {
+            if (lane == 0) {
+                // ---- halo conv producer: per 64-channel block cb ONE raw halo tile, and the nine weight
+                // tiles (tap, cb) of the block through the STAGES-deep ring
+                const ATile at = a_tile_coords(args, m_tile);
+                const int ncb = args.cpb, total = ncb * 9;
+                auto load_w = [&](int i) {
+                    const int cb = i / 9, tap = i - cb * 9;
+                    const int kb = tap * ncb + cb;  // weight K order is (kh, kw, cin)
+                    const int stage = i % STAGES;
+                    uint8_t* dB = sB + stage * L::kBBytes;
+                    const int b_row = (n_tile * args.nkb_total + kb) * BN + ciy * (BN / 2);
+                    if (CG == 2) {
+                        if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kBBytes);
+                        tma_load_2d_pair(dB, &tma_b, &full_bar[stage], 0, b_row);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], L::kBBytes);
+                        tma_load_2d(dB, &tma_b, &full_bar[stage], 0, b_row);
+                    }
+                };
+                auto load_raw = [&](int cb) {
+                    mbar_expect_tx(raw_full, L::kHaloRawBytes);
+                    // box [64 ch][10 w][18 h][1 n] at the patch origin minus the one-pixel border:
+                    // out-of-image pixels arrive as zeros (and are re-zeroed after the transform)
+                    tma_load_4d(sRaw, &tma_a, raw_full, cb * BK, at.w0 - 1, at.h0 - 1, at.n0);
+                };
+                const int npre = min(total, STAGES);
+                for (int i = 0; i < npre; ++i) load_w(i);  // weights never depend on the predecessor
+                pdl_wait();
+                SFB_STAMP(2);
+                load_raw(0);
+                for (int i = 0; i < total; ++i) {
+                    const int cb = i / 9, tap = i - cb * 9;
+                    if (tap == 3 && cb + 1 < ncb) {
+                        // the transform of block cb has read the raw tile (it ran before this block's
+                        // first MMA): fetch the next one while the taps of this block are multiplied
+                        mbar_wait(raw_empty, cb & 1);
+                        load_raw(cb + 1);
+                    }
+                    if (i >= npre) {
+                        mbar_wait(&empty_bar[i % STAGES], ((i / STAGES) & 1) ^ 1);
+                        load_w(i);
+                    }
+                }
+            }
+        } else
         if (lane == 0) {
             const ATile at = a_tile_coords(args, m_tile);
             const int b_ntile = at.b_nbase + n_tile;
@@ -573,6 +666,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
         if (CG == 2) cluster_arrive_relaxed();
     } else if (warp == 1) {
+        if (HALO) {
+            if (lane == 0 && leader) {
+                const uint32_t idesc = umma_idesc_f16(BM * CG, BN, BF16 != 0);
+                int i = 0;
+                for (int cb = 0; cb < args.cpb; ++cb) {
+                    mbar_wait_cluster(a_full, cb & 1);  // both CTAs' transformed copies of block cb
+                    tc_fence_after();
+                    for (int tap = 0; tap < 9; ++tap, ++i) {
+                        const int stage = i % STAGES;
+                        mbar_wait(&full_bar[stage], (i / STAGES) & 1);
+                        tc_fence_after();
+                        if (i == 0) SFB_STAMP(3);
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        // tap (dy, dx): copy dx, advanced by dy halo rows (one 1024-byte atom each)
+                        const uint64_t da = umma_desc_k_sw128(smem_u32(sA + dx * L::kHaloABuf + dy * 1024));
+                        const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::kBBytes));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            if (CG == 2)
+                                umma_f16_ss_pair(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                                 (i | k) != 0);
+                            else
+                                umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                            (i | k) != 0);
+                        }
+                        if (CG == 2) umma_commit_pair(&empty_bar[stage], pair_mask);
+                        else umma_commit(&empty_bar[stage]);
+                    }
+                    // the copies may be overwritten once these 36 MMAs have read them
+                    if (CG == 2) umma_commit_pair(a_empty, pair_mask);
+                    else umma_commit(a_empty);
+                }
+                if (CG == 2) umma_commit_pair(tmem_full_bar, pair_mask);
+                else umma_commit(tmem_full_bar);
+                SFB_STAMP(4);
+            }
+        } else
         if (lane == 0 && leader) {
             const uint32_t idesc = umma_idesc_f16(BM * CG, BN, BF16 != 0);
             for (int i = 0; i < nkb; ++i) {
@@ -641,6 +771,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
         epi_bar();
+        if (HALO) {
+            // ---- GroupNorm(+SiLU) transform of the conv's A operand (these warps are idle until the
+            // accumulator is complete).  Thread = (16-byte channel chunk c, halo pixels p0 + 32 i):
+            // a warp reads / writes four consecutive 128-byte rows per instruction -- conflict-free.
+            const int c = et & 7;
+            const int p0 = et >> 3;
+            const ATile at = a_tile_coords(args, m_tile);
+            const int cin = args.cpb * BK;
+            constexpr int kPix = (L::kHaloRows * L::kHaloCols + 31) / 32;  // 6 halo pixels per thread
+            uint32_t roff[kPix], dbase[kPix], meta[kPix];
+#pragma unroll
+            for (int i = 0; i < kPix; ++i) {
+                const int p = p0 + 32 * i;
+                const bool live = p < L::kHaloRows * L::kHaloCols;
+                const int hy = p / L::kHaloCols, hx = p - hy * L::kHaloCols;
+                const int gy = at.h0 - 1 + hy, gx = at.w0 - 1 + hx;
+                const bool inside = live && gy >= 0 && gy < args.img_h && gx >= 0 && gx < args.img_w;
+                roff[i] = (uint32_t)(p * 128 + ((c ^ (p & 7)) << 4));   // TMA's 128-byte swizzle
+                dbase[i] = (uint32_t)(hy * 1024);
+                meta[i] = (uint32_t)hx | (inside ? 16u : 0u) | (live ? 32u : 0u);
+            }
+            float sc[8], sh[8];
+            auto load_ab = [&](int cb) {
+                const float4* q = reinterpret_cast<const float4*>(
+                    args.gn_ab + 2 * ((size_t)at.n0 * cin + cb * BK + c * 8));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = q[j];
+                    sc[2 * j] = t.x; sh[2 * j] = t.y; sc[2 * j + 1] = t.z; sh[2 * j + 1] = t.w;
+                }
+            };
+            load_ab(0);
+            for (int cb = 0; cb < args.cpb; ++cb) {
+                mbar_wait(raw_full, cb & 1);
+                uint4 v[kPix];
+#pragma unroll
+                for (int i = 0; i < kPix; ++i)
+                    if (meta[i] & 32u) v[i] = *reinterpret_cast<const uint4*>(sRaw + roff[i]);
+#pragma unroll
+                for (int i = 0; i < kPix; ++i) {
+                    uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack2(w[j], BF16);
+                        const uint32_t y = pack2(fmaf(f.x, sc[2 * j], sh[2 * j]), fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]), BF16);
+                        w[j] = args.gn_silu ? silu_pair16<BF16>(y) : y;
+                    }
+                    // padding pixels must be zero AFTER the transform: silu(0 * scale + shift) != 0
+                    v[i] = (meta[i] & 16u) ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0, 0, 0, 0);
+                }
+                // the raw tile is consumed (its values sit in registers): release it for the next block
+                __syncwarp();
+                if (lane == 0) mbar_arrive(raw_empty);
+                if (cb + 1 < args.cpb) load_ab(cb + 1);
+                if (cb > 0) {
+                    mbar_wait(a_empty, (cb - 1) & 1);  // the previous block's MMAs have read the copies
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int i = 0; i < kPix; ++i) {
+                    if (meta[i] & 32u) {
+                        const int hx = meta[i] & 15;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int x = hx - dx;  // column inside the shifted copy
+                            if (x >= 0 && x < 8)
+                                *reinterpret_cast<uint4*>(sA + dx * L::kHaloABuf + dbase[i] + x * 128 + ((c ^ x) << 4)) = v[i];
+                        }
+                    }
+                }
+                fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(a_full, 0);  // counted on the pair leader
+                    else mbar_arrive(a_full);
+                }
+            }
+        }
         // ---- epilogue.  Phase A: thread = accumulator row (warp w may only touch TMEM lanes
         // [32*(w%4), +32)): TMEM -> registers -> (+bias / LayerNorm fold) -> fp32 staging tile in the
         // now-idle pipeline buffers.  Phase B: threads re-partition the tile so that every global
@@ -1039,11 +1247,6 @@ struct PersistSmem {
     static_assert(kTotal <= 227 * 1024, "persistent GEMM shared memory");
 };
 
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {
-    const uint32_t remote = dsmem_map(smem_u32(bar), cta_rank);
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-
 template <int BF16>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -1434,19 +1637,19 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
 using namespace sfb;
 
-template <int STAGES, int BF16, int CG>
+template <int STAGES, int BF16, int CG, int HALO = 0>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, dim3 grid,
                          cudaStream_t stream) {
-    using L = GemmSmem<STAGES, CG>;
+    using L = GemmSmem<STAGES, CG, HALO>;
     static PerDeviceOnce attr_once;
     bool& attr_set = attr_once.flag();
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, BF16, CG>,
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, BF16, CG, HALO>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "sfb_gemm: smem attribute: %s", cudaGetErrorString(err));
         attr_set = true;
     }
-    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<STAGES, BF16, CG>, grid, dim3(kGemmThreads),
+    cudaError_t err = launch_cluster_pdl(gemm_tc_kernel<STAGES, BF16, CG, HALO>, grid, dim3(kGemmThreads),
                                          CG == 2 ? dim3(2, 1, 1) : dim3(1, 1, 1), L::kTotal, stream, ta, tb, a);
     if (err != cudaSuccess)
         return fail(SFB_ERR_CUDA, "sfb_gemm: launch: %s (%s) grid=(%u,%u,%u) smem=%d stages=%d cg=%d",
@@ -1512,7 +1715,18 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     int m_tiles;
     const bool upconv = p->a_mode == SFB_A_UPCONV2X;
     const bool tconv = p->a_mode == SFB_A_CONV3X1;
-    if (p->a_mode == SFB_A_CONV3X3 || upconv || tconv) {
+    const bool gnconv = p->a_mode == SFB_A_CONV3X3_GN;
+    if (gnconv) {
+        // 16 x 8 pixel patches, halo tile transformed in shared memory (tmap_a box = [64, 10, 18, 1])
+        if (!p->gn_scale_shift) return fail(SFB_ERR_INVALID, "sfb_gemm: SFB_A_CONV3X3_GN needs gn_scale_shift");
+        if (p->box_n != 1 || p->box_h != 16 || p->box_w != 8 || p->conv_stride != 1 || !p->cta_pair ||
+            a.splits != 1 || p->persistent || p->epi != SFB_EPI_STORE || p->b_plain)
+            return fail(SFB_ERR_INVALID, "sfb_gemm: SFB_A_CONV3X3_GN needs the 1x16x8 box, stride 1, cta_pair, "
+                                         "no split-K, the one-tile kernel and the STORE epilogue");
+        a.gn_ab = p->gn_scale_shift;
+        a.gn_silu = p->gn_silu ? 1 : 0;
+    }
+    if (p->a_mode == SFB_A_CONV3X3 || upconv || tconv || gnconv) {
         if (p->cin <= 0 || p->cin % BK || p->K != (upconv ? 4 : (tconv ? 3 : 9)) * p->cin)
             return fail(SFB_ERR_INVALID, "sfb_gemm: conv cin=%d K=%d", p->cin, p->K);
         const int box_w = p->box_w > 0 ? p->box_w : p->img_w;
@@ -1541,7 +1755,7 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
     } else {
         return fail(SFB_ERR_INVALID, "sfb_gemm: a_mode");
     }
-    if (p->rowbias && p->a_mode != SFB_A_CONV3X3 && !tconv)
+    if (p->rowbias && p->a_mode != SFB_A_CONV3X3 && !tconv && !gnconv)
         return fail(SFB_ERR_INVALID, "sfb_gemm: rowbias (time-embedding add) needs conv mode");
     if (tconv && p->conv_stride != 1) return fail(SFB_ERR_INVALID, "sfb_gemm: temporal conv needs stride 1");
     EpiArgs& e = a.e;
@@ -1624,6 +1838,10 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
         if (grid.y % 2 || (upconv && a.up_tiles % 2))
             return fail(SFB_ERR_INVALID, "sfb_gemm: cta_pair needs an even number of M tiles (per up-conv phase)");
         const dim3 pgrid(grid.y, grid.x, grid.z);  // M tiles along x: pairs are x-neighbours
+        if (gnconv)
+            rc = e.dtype == SFB_BF16 ? launch_gemm_t<3, 1, 2, 1>(ta, tb, a, pgrid, stream)
+                                     : launch_gemm_t<3, 0, 2, 1>(ta, tb, a, pgrid, stream);
+        else
         rc = deep ? launch_gemm<8, 2>(ta, tb, a, pgrid, stream) : launch_gemm<4, 2>(ta, tb, a, pgrid, stream);
     } else {
         rc = deep ? launch_gemm<6, 1>(ta, tb, a, grid, stream) : launch_gemm<3, 1>(ta, tb, a, grid, stream);

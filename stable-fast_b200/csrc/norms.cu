@@ -296,6 +296,62 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
     gn_store_slot(a, img, acc);
 }
 
+// gn_stats_kernel + the finish: the last CTA of an image to arrive (integer ticket) sums the image's slots
+// in the fixed order and writes the per-channel (scale, shift) pairs the halo convolution applies.
+__global__ void __launch_bounds__(kGnThreads) gn_stats_ab_kernel(const GnArgs a, float* __restrict__ ab,
+                                                                  unsigned* counters) {
+    __shared__ float acc[2 * 64];
+    __shared__ float sK[64];
+    __shared__ __align__(16) float red[kGnRedFloats];
+    __shared__ int s_last;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int img = blockIdx.y;
+    const int by = kGnThreads / a.nvec;
+    const int tx = threadIdx.x % a.nvec;
+    const int ty = threadIdx.x / a.nvec;
+    gn_load_shifts<false>(a, img, sK);
+    __syncthreads();
+    GnAcc8 st;
+    st.zero();
+    if (ty < by) {
+        float k[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
+        const int row0 = blockIdx.x * a.rows_per_block;
+        const int row1 = min(row0 + a.rows_per_block, a.hw);
+        const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
+        constexpr int kU = 8;
+        for (int rb = row0 + ty; rb < row1; rb += by * kU) {
+            uint4 v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int row = rb + u * by;
+                if (row < row1) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (rb + u * by < row1) st.add(v[u], k, a.dtype);
+        }
+    }
+    gn_block_reduce(st, ty < by, tx, ty, by, a, red, acc);
+    gn_store_slot(a, img, acc);
+    __threadfence();   // this CTA's slot is visible device-wide before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[img], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    gn_sum_slots(a, img, red, acc);
+    const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
+    for (int ch = threadIdx.x; ch < a.c; ch += kGnThreads) {
+        float sc, sh;
+        gn_scale_shift(a, acc, sK, inv_cnt, ch, a.gamma[ch], a.beta[ch], sc, sh);
+        *reinterpret_cast<float2*>(ab + ((size_t)img * a.c + ch) * 2) = make_float2(sc, sh);
+    }
+    if (threadIdx.x == 0) counters[img] = 0;  // every CTA of the image has arrived: ready for the next launch
+}
+
 // grid (blocks_per_img, n): per-channel scale/shift for this image staged in shared memory, then
 // a streaming y = act(x * scale + shift) over the block's rows with 16-byte accesses.
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
@@ -613,6 +669,19 @@ extern "C" int sfb_group_norm_stats(const sfb_gn_params* p, sfb_stream_t stream)
                                  static_cast<cudaStream_t>(stream), a);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_stats: %s", cudaGetErrorString(err));
     return check_launch("sfb_group_norm_stats");
+}
+
+extern "C" int sfb_group_norm_scale_shift(const sfb_gn_params* p, float* scale_shift, sfb_stream_t stream) {
+    GnArgs a{};
+    int bpi = 1;
+    int rc = make_gn_args(p, a, bpi);
+    if (rc) return rc;
+    if (!scale_shift || !p->gamma || !p->beta || !p->sync_counter)
+        return fail(SFB_ERR_INVALID, "group_norm_scale_shift: null scale_shift / gamma / beta / sync_counter");
+    cudaError_t err = launch_pdl(gn_stats_ab_kernel, dim3(bpi, p->n), dim3(kGnThreads), 0,
+                                 static_cast<cudaStream_t>(stream), a, scale_shift, p->sync_counter);
+    if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_scale_shift: %s", cudaGetErrorString(err));
+    return check_launch("sfb_group_norm_scale_shift");
 }
 
 extern "C" int sfb_group_norm_apply(const sfb_gn_params* p, sfb_stream_t stream) {

@@ -10,8 +10,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SFB_LIB_PATH: A/B builds of the same ABI (experiments only; still no fallback)
 LIB_PATH = os.environ.get("SFB_LIB_PATH") or os.path.join(_HERE, "libsfb200.so")
 
+ABI_VERSION = 4  # SFB_ABI_VERSION of include/sfb200.h
 SFB_F16, SFB_BF16 = 0, 1
-A_MATRIX, A_CONV3X3, A_UPCONV2X, A_CONV3X1 = 0, 1, 2, 3
+A_MATRIX, A_CONV3X3, A_UPCONV2X, A_CONV3X1, A_CONV3X3_GN = 0, 1, 2, 3, 4
 ROW_IDX_DIV_MOD, ROW_IDX_TEMPORAL_CTX = 0, 1
 EPI_STORE, EPI_GEGLU, EPI_QKV, EPI_STORE_F32 = 0, 1, 2, 3
 ACT_NONE, ACT_QUICK_GELU, ACT_GELU = 0, 1, 2
@@ -38,6 +39,7 @@ class GemmParams(C.Structure):
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_dim", C.c_int32), ("act", C.c_int32),
         ("rowstats_out_slots", C.c_int32), ("ln_slots", C.c_int32),
+        ("gn_scale_shift", C.c_void_p), ("gn_silu", C.c_int32),
     ]
 
 
@@ -122,6 +124,7 @@ SYMBOLS = {
     "sfb_attention": (C.c_int, [C.POINTER(AttnParams), _VP]),
     "sfb_group_norm_stats": (C.c_int, [C.POINTER(GnParams), _VP]),
     "sfb_group_norm_apply": (C.c_int, [C.POINTER(GnParams), _VP]),
+    "sfb_group_norm_scale_shift": (C.c_int, [C.POINTER(GnParams), _VP, _VP]),
     "sfb_group_norm_fused_fits": (C.c_int, [C.POINTER(GnParams)]),
     "sfb_group_norm_ws_floats": (C.c_int, [_I32, _I32]),
     "sfb_group_norm_fused": (C.c_int, [C.POINTER(GnParams), _VP]),
@@ -167,7 +170,7 @@ def lib():
             fn = getattr(h, name)
             fn.restype = res
             fn.argtypes = args
-        if h.sfb_abi_version() != 3:
+        if h.sfb_abi_version() != ABI_VERSION:
             raise SfbError("libsfb200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (A_CONV3X1, A_CONV3X3, A_MATRIX, A_UPCONV2X, EPI_GEGLU, EPI_QKV, EPI_STORE, AttnParams, GemmParams,
+from ._lib import (A_CONV3X1, A_CONV3X3, A_CONV3X3_GN, A_MATRIX, A_UPCONV2X, EPI_GEGLU, EPI_QKV, EPI_STORE, AttnParams, GemmParams,
                    GnParams, LnParams, SmallLinearParams, TensorMap, check)
 
 BM, BN, BK = 128, 160, 64
@@ -166,10 +166,33 @@ def a_conv(x_ptr, n, h, w, c, pitch, box_n, box_h, box_w, stride):
                 wo=box_w, stride=stride)
 
 
+# GroupNorm folded into the conv (SFB_A_CONV3X3_GN): 16 x 8 pixel output patches, [18 x 10] halo tiles
+HALO_BOX_H, HALO_BOX_W = 16, 8
+CONV_GN = os.environ.get("SFB_CONV_GN", "auto")
+
+
+def a_conv_halo(x_ptr, n, h, w, c, pitch):
+    """RAW NHWC conv input whose GroupNorm(+SiLU) the conv applies itself: TMA box = the halo tile of
+    a 16 x 8 output patch."""
+    return dict(kind="conv_halo", ptr=x_ptr, n=n, h=h, w=w, c=c, pitch=pitch)
+
+
+def conv_gn_tiles(n, h, w):
+    """M tiles of the halo conv over n images of h x w pixels, or 0 if the geometry is not eligible
+    (width a multiple of 8, an even number of tiles for the CTA pairs)."""
+    if w % HALO_BOX_W or h < 1:
+        return 0
+    tiles = n * ((h + HALO_BOX_H - 1) // HALO_BOX_H) * (w // HALO_BOX_W)
+    return tiles if tiles % 2 == 0 else 0
+
+
 def _a_map(a, dry):
     """A-operand TMA map with a box of one 128-row tile."""
     if a["kind"] == "matrix":
         return matrix_map(a["ptr"], a["rows"], a["cols"], a["pitch"], BM, dry)
+    if a["kind"] == "conv_halo":
+        return nhwc_map(a["ptr"], a["n"], a["h"], a["w"], a["c"], a["pitch"], 1, HALO_BOX_H + 2,
+                        HALO_BOX_W + 2, 1, dry)
     return nhwc_map(a["ptr"], a["n"], a["h"], a["w"], a["c"], a["pitch"], a["box_n"], a["box_h"],
                     a["wo"], a["stride"], dry)
 
@@ -177,13 +200,20 @@ def _a_map(a, dry):
 def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, out=None, ldo=0,
             bias=None, rowbias=None, rows_per_img=1, ld_rowbias=0, residual=None, ldr=0,
             epi=EPI_STORE, geglu_n_out=0, conv=None, qkv=None, ws=None, splits=None, keep=(),
-            rowstats_out=None, ln=None, dry=False, cta_pair=None, persistent=None, act=0):
+            rowstats_out=None, ln=None, dry=False, cta_pair=None, persistent=None, act=0, gn=None):
     """Either pass ready-made maps (`a_map`, `b_map`) or operand descriptors (`a` from
     a_matrix()/a_conv(), `b` a Mat), in which case CTA pairs (cta_group::2) are used whenever the
     number of M tiles is even, and the persistent 256 x 320 kernel when the launch is large enough
     (PERSIST policy above; `persistent=True/False` forces it)."""
     p = GemmParams()
     up = bool(conv and conv.get("up"))
+    if gn is not None:
+        # GroupNorm folded into the conv: `gn` = dict(scale_shift=[n, cin, 2] fp32 tensor, silu=bool)
+        assert conv and a is not None and a["kind"] == "conv_halo" and not up
+        assert (conv["box_n"], conv["box_h"], conv["box_w"]) == (1, HALO_BOX_H, HALO_BOX_W)
+        splits, persistent, cta_pair = 1, False, True
+        p.gn_scale_shift, p.gn_silu = _ptr(gn["scale_shift"]), int(bool(gn.get("silu", True)))
+        keep = tuple(keep) + (gn["scale_shift"],)
     if conv:
         if conv["box_n"] == 1:
             m_tiles = conv["n"] * ((conv["h"] + conv["box_h"] - 1) // conv["box_h"]) * \
@@ -206,6 +236,9 @@ def gemm_op(name, lib, *, M, N, K, dt, a_map=None, b_map=None, a=None, b=None, o
         keep = tuple(keep) + (b,)
     p.tmap_a, p.tmap_b = a_map.ptr, b_map.ptr
     p.a_mode = (A_UPCONV2X if up else (A_CONV3X1 if conv.get("temporal") else A_CONV3X3)) if conv else A_MATRIX
+    if gn is not None:
+        assert p.cta_pair == 1, "halo conv needs an even number of M tiles"
+        p.a_mode = A_CONV3X3_GN
     p.M, p.N, p.K, p.dtype = M, N, K, dtype_code(dt)
     if conv:
         p.img_n, p.img_h, p.img_w = conv["n"], conv["h"], conv["w"]
@@ -374,6 +407,19 @@ def gn_ops(name, lib, *, x: Act, y: Act, gamma, beta, stats, groups, eps, silu, 
         raise ValueError(f"{name}: deferred split-K finish needs the fused GroupNorm kernel")
     return [Op(name + ".stats", lib.sfb_group_norm_stats, (C.byref(p),), keep, 0, nb),
             Op(name + ".apply", lib.sfb_group_norm_apply, (C.byref(p),), keep, 0, 2 * nb)]
+
+
+def gn_scale_shift_op(name, lib, *, x: Act, gamma, beta, stats, counters, scale_shift, groups, eps, dt):
+    """GroupNorm statistics of x ending in per-(image, channel) (scale, shift) pairs -- the producer side of
+    the halo conv (`gemm_op(..., gn=...)`).  `counters`: x.n int32 tickets, zero before the first launch."""
+    p = GnParams()
+    p.x = x.ptr
+    p.gamma, p.beta, p.stats = _ptr(gamma), _ptr(beta), _ptr(stats)
+    p.n, p.hw, p.c, p.ldx, p.ldy, p.groups = x.n, x.h * x.w, x.c, x.ld, x.ld, groups
+    p.eps, p.silu, p.dtype = eps, 0, dtype_code(dt)
+    p.sync_counter = _ptr(counters)
+    return Op(name + ".scale_shift", lib.sfb_group_norm_scale_shift, (C.byref(p), _ptr(scale_shift)),
+              (p, x.buf, gamma, beta, stats, counters, scale_shift), 0, x.rows * x.c * 2)
 
 
 def ln_op(name, lib, *, x, y, rows, c, gamma, beta, eps, dt, ldx=None, ldy=None):

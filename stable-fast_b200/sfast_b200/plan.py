@@ -269,6 +269,8 @@ class UNetPlan:
         counters (zeroed once per step)."""
         self.gn_stats = self._alloc((n_gn, ops.gn_ws_floats(max_images, self.spec.groups)), torch.float32)
         self.gn_sync = self._alloc((n_gn, 4), torch.int32)
+        # GroupNorm folded into the conv: per-image tickets of the statistics kernel (self-resetting)
+        self.gn_tickets = self._alloc((n_gn, max(max_images, 4)), torch.int32)
 
     def _ln_arena_floats(self):
         """3 * depth LayerNorms per transformer, each [B*h*w, slots(dim), 2] floats at its resolution."""
@@ -356,12 +358,50 @@ class UNetPlan:
         self._emit(gn)
         return y
 
-    def conv3x3(self, name, x: Act, wname, dst: Act, stride=1, rowbias=None, residual: Act = None):
+    def _conv_gn_ok(self, x: Act, cout):
+        """Whether GroupNorm+SiLU over `x` is folded into the 3x3 conv that consumes it (halo conv,
+        SFB_A_CONV3X3_GN) instead of running as its own kernel.  SFB_CONV_GN = 0: never; 1: wherever the
+        geometry allows; auto: where, additionally, the conv is a full launch (no split-K -- the
+        weight-bandwidth-bound low-resolution layers keep the fused GroupNorm that also finishes
+        their producer's split-K partials)."""
+        mode = ops.CONV_GN
+        if mode == "0" or x.c % ops.BK:
+            return False
+        tiles = ops.conv_gn_tiles(x.n, x.h, x.w)
+        if not tiles:
+            return False
+        if mode == "1":
+            return True
+        if self._pending is not None:
+            return False
+        return ops.choose_splits(tiles, -(-cout // ops.BN), 9 * x.c // ops.BK, x.rows, cout) == 1
+
+    def norm_for_conv(self, name, x: Act, prefix, eps, cout):
+        """GroupNorm + SiLU in front of a 3x3 conv with `cout` outputs.  Returns (conv input, gn):
+        gn is None when the normalised activation was materialised by a GroupNorm kernel, else the
+        descriptor the conv needs to normalise its raw input itself."""
+        if not self._conv_gn_ok(x, cout):
+            return self.group_norm(name, x, prefix, True, eps), None
+        idx = self._gn_count
+        self._gn_count += 1
+        ab = self.buf(f"gn_scale_shift.{idx}", (x.n, x.c, 2), torch.float32)
+        self._emit(ops.gn_scale_shift_op(name, self.lib_or_dry(), x=x, gamma=self.w.f32(prefix + ".weight"),
+                                         beta=self.w.f32(prefix + ".bias"), stats=self.gn_stats[idx],
+                                         counters=self.gn_tickets[idx], scale_shift=ab,
+                                         groups=self.spec.groups, eps=eps, dt=self.dt))
+        return x, dict(scale_shift=ab, silu=True)
+
+    def conv3x3(self, name, x: Act, wname, dst: Act, stride=1, rowbias=None, residual: Act = None, gn=None):
         wm = self.w.conv3x3(wname + ".weight")
         cout = wm.n
         ho, wo = x.h // stride, x.w // stride
-        box_n, box_h, box_w = ops.conv_tile_box(ho, wo)
-        adesc = ops.a_conv(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, box_w, stride)
+        if gn is not None:  # raw input, GroupNorm applied on the conv's operand path
+            assert stride == 1
+            box_n, box_h, box_w = 1, ops.HALO_BOX_H, ops.HALO_BOX_W
+            adesc = ops.a_conv_halo(x.ptr, x.n, x.h, x.w, x.c, x.ld)
+        else:
+            box_n, box_h, box_w = ops.conv_tile_box(ho, wo)
+            adesc = ops.a_conv(x.ptr, x.n, x.h, x.w, x.c, x.ld, box_n, box_h, box_w, stride)
         M = x.n * ho * wo
         kw = dict(a=adesc, b=wm, M=M, N=cout, K=9 * x.c, dt=self.dt,
                   out=dst.ptr, ldo=dst.ld, bias=self.w.f32(wname + ".bias"),
@@ -372,6 +412,8 @@ class UNetPlan:
             kw.update(rowbias=rowbias[0], rows_per_img=ho * wo, ld_rowbias=rowbias[1])
         if residual is not None:
             kw.update(residual=residual.ptr, ldr=residual.ld)
+        if gn is not None:
+            kw.update(gn=gn)
         op = self._gemm(name, **kw)
         self._emit(op)
         self._maybe_defer_finish(op.keep[0], dst, cout, kw["bias"], rowbias, residual)
@@ -420,7 +462,7 @@ class UNetPlan:
         # norm1 first: it may be the kernel that finishes x (deferred split-K reduction of the
         # conv that produced it), so every other reader of x is ordered after it
         eps = r.eps if r.eps is not None else self.spec.eps
-        a1 = self.group_norm(p + ".norm1", x, p + ".norm1", True, eps)
+        a1, gn1 = self.norm_for_conv(p + ".norm1", x, p + ".norm1", eps, r.cout)
         if r.has_shortcut and os.environ.get("SFB_SIDE_SHORTCUT", "1") != "0":
             # the 1x1 shortcut only needs the block input: parallel graph branch next to
             # norm1 / conv1 / norm2 (most of these launches leave SMs idle at small batch)
@@ -433,8 +475,8 @@ class UNetPlan:
             self._emit(fork)
         h1 = self.act("res_h1", x.n, x.h, x.w, r.cout)
         rb_ptr = _ptr(self.temb_proj) + 4 * self.w.tproj_off[p]
-        self.conv3x3(p + ".conv1", a1, p + ".conv1", h1, rowbias=(rb_ptr, self.w.tproj_total))
-        a2 = self.group_norm(p + ".norm2", h1, p + ".norm2", True, eps)
+        self.conv3x3(p + ".conv1", a1, p + ".conv1", h1, rowbias=(rb_ptr, self.w.tproj_total), gn=gn1)
+        a2, gn2 = self.norm_for_conv(p + ".norm2", h1, p + ".norm2", eps, r.cout)
         if fork is not None:
             self._emit(_JoinOp(fork))
             res = sc
@@ -445,7 +487,7 @@ class UNetPlan:
             res = sc
         else:
             res = x
-        self.conv3x3(p + ".conv2", a2, p + ".conv2", dst, residual=res)
+        self.conv3x3(p + ".conv2", a2, p + ".conv2", dst, residual=res, gn=gn2)
 
     def attention(self, name, hs: Act, ln_prefix, ln_stats, blk, t, cross, stats_next):
         """attn(LayerNorm(hs)) + hs -> hs (in place).  The LayerNorm is folded into the Q(KV)

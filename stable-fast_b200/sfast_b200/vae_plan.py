@@ -128,16 +128,16 @@ class VAEDecodePlan(UNetPlan):
 
     def vae_resnet(self, p, x: Act, dst: Act, cin, cout):
         eps = self.spec.eps
-        a1 = self.group_norm(p + ".norm1", x, p + ".norm1", True, eps)
+        a1, gn1 = self.norm_for_conv(p + ".norm1", x, p + ".norm1", eps, cout)
         h1 = self.act("res_h1", x.n, x.h, x.w, cout)
-        self.conv3x3(p + ".conv1", a1, p + ".conv1", h1)
-        a2 = self.group_norm(p + ".norm2", h1, p + ".norm2", True, eps)
+        self.conv3x3(p + ".conv1", a1, p + ".conv1", h1, gn=gn1)
+        a2, gn2 = self.norm_for_conv(p + ".norm2", h1, p + ".norm2", eps, cout)
         res = x
         if cin != cout:
             res = self.act("res_sc", x.n, x.h, x.w, cout)
             self.linear(p + ".conv_shortcut", x, self.w.matrix(p + ".conv_shortcut.weight"),
                         self.w.f32(p + ".conv_shortcut.bias"), res)
-        self.conv3x3(p + ".conv2", a2, p + ".conv2", dst, residual=res)
+        self.conv3x3(p + ".conv2", a2, p + ".conv2", dst, residual=res, gn=gn2)
 
     def vae_attention(self, p, x: Act, dst: Act):
         """dst = x + to_out(softmax(q k^T / sqrt(c)) v) over the h*w tokens of each image, one head."""

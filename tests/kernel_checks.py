@@ -136,6 +136,71 @@ def check_conv(n=2, h=64, w=64, cin=320, cout=320, stride=1, dt=torch.float16, s
     return rel_err(out, ref)
 
 
+def check_conv_gn(n=2, h=64, w=64, cin=320, cout=320, dt=torch.float16, groups=32, silu=True, rowbias=True,
+                  residual=True, pitch_extra=0, out_extra=0, mean=0.0, seed=51, eps=1e-5, replay=False):
+    """GroupNorm(+SiLU) folded into the 3x3 conv's A-operand path (SFB_A_CONV3X3_GN: statistics ->
+    per-channel (scale, shift) -> halo tile transformed in shared memory) vs fp32
+    conv2d(silu(group_norm(x))) + bias + per-image row bias + residual."""
+    lib = _lib.lib()
+    torch.manual_seed(seed)
+    ld = cin + pitch_extra
+    xbuf = (torch.randn(n, h, w, ld, device=DEV) * (1.0 + torch.rand(ld, device=DEV)) + mean
+            + torch.randn(ld, device=DEV) * (0.5 if mean == 0.0 else 2.0)).to(dt)
+    x = Act(xbuf, n, h, w, cin, ld=ld)
+    gamma = 1.0 + 0.5 * torch.randn(cin, device=DEV)
+    beta = 0.3 * torch.randn(cin, device=DEV)
+    wt = _rand(cout, cin, 3, 3, dt=dt, scale=1 / math.sqrt(9 * cin))
+    b = torch.randn(cout, device=DEV)
+    M = n * h * w
+    rb = torch.randn(n, cout, device=DEV) if rowbias else None
+    r = _rand(M, cout, dt=dt) if residual else None
+    ldo = cout + out_extra
+    out = torch.zeros(M, ldo, device=DEV, dtype=dt)
+    stats = torch.zeros(ops.gn_ws_floats(n, groups), device=DEV)
+    counters = torch.zeros(max(n, 4), device=DEV, dtype=torch.int32)
+    ab = torch.zeros(n, cin, 2, device=DEV)
+    assert ops.conv_gn_tiles(n, h, w) > 0, "geometry not eligible for the halo conv"
+    st = ops.gn_scale_shift_op("gn", lib, x=x, gamma=gamma, beta=beta, stats=stats, counters=counters,
+                               scale_shift=ab, groups=groups, eps=eps, dt=dt)
+    op = ops.gemm_op("conv_gn", lib, a=ops.a_conv_halo(x.ptr, n, h, w, cin, ld), b=ops.Mat(ops.pack_conv3x3(wt, dt)),
+                     M=M, N=cout, K=9 * cin, dt=dt, out=out, ldo=ldo, bias=b, rowbias=rb, rows_per_img=h * w,
+                     ld_rowbias=cout, residual=r, ldr=cout,
+                     conv=dict(n=n, h=h, w=w, cin=cin, stride=1, box_n=1, box_h=ops.HALO_BOX_H, box_w=ops.HALO_BOX_W),
+                     gn=dict(scale_shift=ab, silu=silu))
+    assert op.keep[0].a_mode == _lib.A_CONV3X3_GN
+    st.launch(_stream())
+    op.launch(_stream())
+    torch.cuda.synchronize()
+    xin = x.tensor().permute(0, 3, 1, 2).float()
+    y = F.group_norm(xin, groups, gamma, beta, eps)
+    # (scale, shift) against the fp32 statistics
+    mean_ = xin.view(n, groups, -1).mean(-1)
+    var_ = xin.view(n, groups, -1).var(-1, unbiased=False)
+    sc_ref = (gamma.view(1, groups, -1) * torch.rsqrt(var_ + eps)[:, :, None]).reshape(n, cin)
+    sh_ref = beta[None] - (mean_[:, :, None] * sc_ref.view(n, groups, -1)).reshape(n, cin)
+    e_ab = max(rel_err(ab[..., 0], sc_ref), rel_err(ab[..., 1], sh_ref))
+    if silu:
+        y = F.silu(y)
+    ref = F.conv2d(y, wt.float(), b, padding=1)
+    if rowbias:
+        ref = ref + rb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(M, cout)
+    if residual:
+        ref = ref + r.float()
+    err = max(rel_err(out[:, :cout], ref), e_ab)
+    if out_extra and float(out[:, cout:].abs().max()) != 0.0:
+        return float("inf")  # wrote outside its channel slice
+    if replay:  # a second pass (self-resetting tickets, ordered reductions) must be bit-identical
+        first, ab1 = out.clone(), ab.clone()
+        out.zero_()
+        st.launch(_stream())
+        op.launch(_stream())
+        torch.cuda.synchronize()
+        if not (torch.equal(first, out) and torch.equal(ab1, ab)):
+            return float("inf")
+    return err
+
+
 def check_upconv(n=2, h=16, w=16, cin=640, cout=640, dt=torch.float16, splits=None, pair=None,
                  out_extra=0, seed=23, persistent=False):
     """nearest-2x upsample + conv3x3 as the 4-phase 2x2 implicit GEMM on the low-res image vs
@@ -845,6 +910,16 @@ CHECKS = {
     "ln_fold_geglu": (lambda: check_ln_fold(300, 320, 1280, mode="geglu"), 2e-2),
     "ln_fold_splitk": (lambda: check_ln_fold(256, 1280, 1280, splits_p=2, splits_c=2), 5e-3),
     "ln_fold_geglu_splitk": (lambda: check_ln_fold(128, 1280, 5120, mode="geglu", splits_c=2), 2e-2),
+    "conv_gn_64": (lambda: check_conv_gn(2, 64, 64, 320, 320, replay=True), 4e-3),
+    "conv_gn_32_640": (lambda: check_conv_gn(2, 32, 32, 640, 640), 4e-3),
+    "conv_gn_16_one_block": (lambda: check_conv_gn(2, 16, 16, 64, 160, groups=8, rowbias=False, residual=False), 4e-3),
+    "conv_gn_concat_pitch": (lambda: check_conv_gn(2, 32, 32, 960, 320, pitch_extra=320, out_extra=160), 4e-3),
+    "conv_gn_24_ragged_rows": (lambda: check_conv_gn(2, 24, 24, 640, 320), 4e-3),
+    "conv_gn_40x24_ragged_n": (lambda: check_conv_gn(2, 40, 24, 320, 488), 4e-3),
+    "conv_gn_mean50": (lambda: check_conv_gn(2, 32, 32, 320, 320, mean=50.0), 1e-2),
+    "conv_gn_nosilu": (lambda: check_conv_gn(2, 32, 32, 320, 320, silu=False), 4e-3),
+    "conv_gn_b8": (lambda: check_conv_gn(8, 64, 64, 320, 320), 4e-3),
+    "conv_gn_bf16": (lambda: check_conv_gn(2, 32, 32, 640, 640, dt=torch.bfloat16), 3e-2),
     "conv_64": (lambda: check_conv(2, 64, 64, 320, 320, splits=1), 2e-3),
     "conv_32": (lambda: check_conv(2, 32, 32, 640, 640, splits=1), 2e-3),
     "conv_16_splitk": (lambda: check_conv(2, 16, 16, 1280, 1280), 2e-3),

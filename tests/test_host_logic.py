@@ -69,11 +69,20 @@ def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     # forked stream: time-embedding chain (4 launches) + the 16 cross-attention K/V projections
     assert len(plan.side_ops) == 20
     # 61 GroupNorms, 48 LayerNorms, 32 attention calls, 3 upsamples
-    # B = 2 tensors fit in shared memory: all 61 GroupNorms take the single-launch fused kernel
-    assert names.count("sfb_group_norm_fused") == 61 and names.count("sfb_group_norm_apply") == 0
+    # B = 2 tensors fit in shared memory: every GroupNorm that is its own kernel takes the single-launch
+    # fused one; the others are FOLDED INTO the 3x3 conv that consumes them (statistics -> (scale, shift),
+    # applied on the conv's operand path): the full-launch convs of the 64^2 level and the first 32^2 one
+    n_folded = names.count("sfb_group_norm_scale_shift")
+    assert names.count("sfb_group_norm_fused") + n_folded == 61 and names.count("sfb_group_norm_apply") == 0
+    assert n_folded == (0 if ops.CONV_GN == "0" else 11)
     # all 48 LayerNorms are folded into the consuming GEMMs (gamma-scaled weights + epilogue)
     assert names.count("sfb_layer_norm") == 0
     gemms = [op.keep[0] for op in plan.all_ops() if op.fn is not None and op.fn.name == "sfb_gemm"]
+    assert sum(1 for g in gemms if g.a_mode == _lib.A_CONV3X3_GN) == n_folded
+    for g in gemms:
+        if g.a_mode == _lib.A_CONV3X3_GN:  # what sfb_gemm demands of the halo conv
+            assert (g.box_n, g.box_h, g.box_w, g.splits, g.cta_pair, g.persistent) == (1, 16, 8, 1, 1, 0)
+            assert g.img_w % 8 == 0 and g.cin % 64 == 0 and g.conv_stride == 1 and g.epi == _lib.EPI_STORE
     assert sum(1 for g in gemms if g.ln_rowstats is not None or g.ln_dim > 0) == 48
     assert names.count("sfb_attention") == 32
     # nearest-2x upsample + conv3x3 runs as four 2x2 convolutions on the low-res image: the
@@ -230,7 +239,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(h, name), name
     lib = _lib.lib()
-    assert lib.sfb_abi_version() == 3
+    assert lib.sfb_abi_version() == _lib.ABI_VERSION == 4
     # argument validation works without a GPU and never falls back silently
     p = _lib.GemmParams()
     assert lib.sfb_gemm(ctypes.byref(p), None) < 0
@@ -306,7 +315,13 @@ def _validate_plan_on_cpu(plan):
             _nonnull(p, ["tmap_a", "tmap_b", "out"])
             if p.splits > 1:
                 _nonnull(p, ["ws"])
+            if p.a_mode == _lib.A_CONV3X3_GN:
+                _nonnull(p, ["gn_scale_shift"])
             rc = lib.sfb_gemm(ctypes.byref(p), None)
+        elif name == "sfb_group_norm_scale_shift":
+            p = _clone(op.keep[0])
+            _nonnull(p, ["x", "gamma", "beta", "stats", "sync_counter"])
+            rc = lib.sfb_group_norm_scale_shift(ctypes.byref(p), _DUMMY_PTR, None)
         elif name == "sfb_group_norm_fused":
             p = _clone(op.keep[0])
             _nonnull(p, ["x", "y", "gamma", "beta", "stats", "sync_counter"])
