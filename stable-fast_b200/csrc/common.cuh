@@ -85,42 +85,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// Arrive on the barrier at the same shared-memory offset in CTA `cta_rank` of the cluster, releasing
-// this thread's prior writes at cluster scope (consumer: mbar_wait_cluster in that CTA).
+// Arrive on the barrier at the same shared-memory offset in CTA `cta_rank` of the cluster.  Default
+// semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): a .release.cluster
+// arrive compiles to MEMBAR.ALL.GPU + ERRBAR in front of the SYNCS.ARRIVE -- a device-wide drain of
+// the thread's memory operations, on the critical path of every hand-off.  What the waiter consumes
+// is shared memory of THIS CTA, read by its own tensor core through the async proxy: the writers
+// order it with fence.proxy.async before arriving.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {
     asm volatile(
         "{\n\t"
         ".reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
         "}\n"
         ::"r"(smem_u32(bar)), "r"(cta_rank)
         : "memory");
-}
-
-// mbar_wait with cluster-scope acquire: the arrivals come from other CTAs of the cluster
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    uint32_t spins = 0;
-    long long t0 = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) break;
-        if ((++spins & 0x3FF) == 0) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();
-        }
-    }
 }
 
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization

@@ -511,8 +511,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // LEADER: every transform warp of both CTAs arrives there) / free again (MMA commit, both CTAs)
     uint64_t* raw_full = tmem_full_bar + 2;
     uint64_t* raw_empty = tmem_full_bar + 3;
-    uint64_t* a_full = tmem_full_bar + 4;
-    uint64_t* a_empty = tmem_full_bar + 5;
+    uint64_t* a_full = tmem_full_bar + 4;    // [3]: one per shifted copy
+    uint64_t* a_empty = tmem_full_bar + 7;   // [3]
     float* sBias = reinterpret_cast<float*>(smem + L::kBiasOffset);
     int* sRowM = reinterpret_cast<int*>(smem + L::kRowMOffset);
     float* sStage = reinterpret_cast<float*>(smem);
@@ -540,8 +540,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (HALO) {
             mbar_init(raw_full, 1);
             mbar_init(raw_empty, kEpiWarps);
-            mbar_init(a_full, kEpiWarps * CG);
-            mbar_init(a_empty, 1);
+            for (int i = 0; i < 3; ++i) {
+                mbar_init(&a_full[i], kEpiWarps * CG);
+                mbar_init(&a_empty[i], 1);
+            }
         }
         fence_barrier_init();
     }
@@ -570,8 +572,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const ATile at = a_tile_coords(args, m_tile);
                 const int ncb = args.cpb, total = ncb * 9;
                 auto load_w = [&](int i) {
-                    const int cb = i / 9, tap = i - cb * 9;
-                    const int kb = tap * ncb + cb;  // weight K order is (kh, kw, cin)
+                    // taps run copy-major (dx, dy): the three taps of one shifted copy are consecutive
+                    const int cb = i / 9, t = i - cb * 9;
+                    const int dx = t / 3, dy = t - dx * 3;
+                    const int kb = (dy * 3 + dx) * ncb + cb;  // weight K order is (kh, kw, cin)
                     const int stage = i % STAGES;
                     uint8_t* dB = sB + stage * L::kBBytes;
                     const int b_row = (n_tile * args.nkb_total + kb) * BN + ciy * (BN / 2);
@@ -671,32 +675,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const uint32_t idesc = umma_idesc_f16(BM * CG, BN, BF16 != 0);
                 int i = 0;
                 for (int cb = 0; cb < args.cpb; ++cb) {
-                    mbar_wait_cluster(a_full, cb & 1);  // both CTAs' transformed copies of block cb
-                    tc_fence_after();
-                    for (int tap = 0; tap < 9; ++tap, ++i) {
-                        const int stage = i % STAGES;
-                        mbar_wait(&full_bar[stage], (i / STAGES) & 1);
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(&a_full[dx], cb & 1);  // both CTAs' copy dx of block cb
                         tc_fence_after();
-                        if (i == 0) SFB_STAMP(3);
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        // tap (dy, dx): copy dx, advanced by dy halo rows (one 1024-byte atom each)
-                        const uint64_t da = umma_desc_k_sw128(smem_u32(sA + dx * L::kHaloABuf + dy * 1024));
-                        const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::kBBytes));
+                        for (int dy = 0; dy < 3; ++dy, ++i) {
+                            const int stage = i % STAGES;
+                            mbar_wait(&full_bar[stage], (i / STAGES) & 1);
+                            tc_fence_after();
+                            if (i == 0) SFB_STAMP(3);
+                            // tap (dy, dx): copy dx, advanced by dy halo rows (one 1024-byte atom each)
+                            const uint64_t da = umma_desc_k_sw128(smem_u32(sA + dx * L::kHaloABuf + dy * 1024));
+                            const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::kBBytes));
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            if (CG == 2)
-                                umma_f16_ss_pair(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                                 (i | k) != 0);
-                            else
-                                umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                            (i | k) != 0);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                if (CG == 2)
+                                    umma_f16_ss_pair(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                                     (i | k) != 0);
+                                else
+                                    umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                                (i | k) != 0);
+                            }
+                            if (CG == 2) umma_commit_pair(&empty_bar[stage], pair_mask);
+                            else umma_commit(&empty_bar[stage]);
                         }
-                        if (CG == 2) umma_commit_pair(&empty_bar[stage], pair_mask);
-                        else umma_commit(&empty_bar[stage]);
+                        // copy dx may be overwritten (with the next channel block) once these 12 MMAs have
+                        // read it -- while the other two copies of this block are still being multiplied
+                        if (CG == 2) umma_commit_pair(&a_empty[dx], pair_mask);
+                        else umma_commit(&a_empty[dx]);
                     }
-                    // the copies may be overwritten once these 36 MMAs have read them
-                    if (CG == 2) umma_commit_pair(a_empty, pair_mask);
-                    else umma_commit(a_empty);
                 }
                 if (CG == 2) umma_commit_pair(tmem_full_bar, pair_mask);
                 else umma_commit(tmem_full_bar);
@@ -824,29 +830,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 // the raw tile is consumed (its values sit in registers): release it for the next block
                 __syncwarp();
                 if (lane == 0) mbar_arrive(raw_empty);
-                if (cb + 1 < args.cpb) load_ab(cb + 1);
-                if (cb > 0) {
-                    mbar_wait(a_empty, (cb - 1) & 1);  // the previous block's MMAs have read the copies
-                    tc_fence_after();
-                }
+                // Copy by copy: copy dx of the PREVIOUS block is free as soon as its three taps are done,
+                // so these stores run under the MMAs of the other copies and the tensor pipe never waits
+                // for a whole-block hand-off.
 #pragma unroll
-                for (int i = 0; i < kPix; ++i) {
-                    if (meta[i] & 32u) {
-                        const int hx = meta[i] & 15;
+                for (int dx = 0; dx < 3; ++dx) {
+                    if (cb > 0) {
+                        mbar_wait(&a_empty[dx], (cb - 1) & 1);
+                        tc_fence_after();
+                    }
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const int x = hx - dx;  // column inside the shifted copy
-                            if (x >= 0 && x < 8)
-                                *reinterpret_cast<uint4*>(sA + dx * L::kHaloABuf + dbase[i] + x * 128 + ((c ^ x) << 4)) = v[i];
-                        }
+                    for (int i = 0; i < kPix; ++i) {
+                        const int x = (int)(meta[i] & 15) - dx;  // column inside the shifted copy
+                        if ((meta[i] & 32u) && x >= 0 && x < 8)
+                            *reinterpret_cast<uint4*>(sA + dx * L::kHaloABuf + dbase[i] + x * 128 + ((c ^ x) << 4)) = v[i];
+                    }
+                    fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_cluster(&a_full[dx], 0);  // counted on the pair leader
+                        else mbar_arrive(&a_full[dx]);
                     }
                 }
-                fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's reads
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) mbar_arrive_cluster(a_full, 0);  // counted on the pair leader
-                    else mbar_arrive(a_full);
-                }
+                // next block's (scale, shift): in flight during this block's MMAs (issued after the
+                // proxy fences above, which would otherwise wait for these loads)
+                if (cb + 1 < args.cpb) load_ab(cb + 1);
             }
         }
         // ---- epilogue.  Phase A: thread = accumulator row (warp w may only touch TMEM lanes

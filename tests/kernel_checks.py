@@ -171,7 +171,7 @@ def check_conv_gn(n=2, h=64, w=64, cin=320, cout=320, dt=torch.float16, groups=3
     st.launch(_stream())
     op.launch(_stream())
     torch.cuda.synchronize()
-    xin = x.tensor().permute(0, 3, 1, 2).float()
+    xin = x.tensor().permute(0, 3, 1, 2).float().contiguous()
     y = F.group_norm(xin, groups, gamma, beta, eps)
     # (scale, shift) against the fp32 statistics
     mean_ = xin.view(n, groups, -1).mean(-1)
