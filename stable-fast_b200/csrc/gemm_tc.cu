@@ -474,20 +474,30 @@ struct GemmSmem {
     static_assert(STAGES > 4 || 2 * (kTotal + 1024) <= 228 * 1024, "shallow configs must fit twice per SM");
 };
 
-// x * sigmoid(x) = h + h * tanh(h), h = x / 2, on a pair of 16-bit values: one MUFU.TANH per TWO elements
-// (the halo transform runs once per conv input element per launch; the fp32 exp + rcp form is 4x the MUFU work)
+// GroupNorm affine + SiLU of two conv-input elements -> one packed 16-bit pair.
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE MUFU per element (the exp + rcp form is two).
+// fp16: the SiLU runs on the packed pair (HMUL2 / 2 x MUFU.TANH.F16 / HFMA2, error ~2^-11 like the
+// storage type).  bf16: three more 8-bit roundings in front of the conv would show (SDXL 128^2:
+// 4.1e-2 vs 3.7e-2 whole-UNet error), so the SiLU stays in fp32 and is rounded once.
 template <int BF16>
-__device__ __forceinline__ uint32_t silu_pair16(uint32_t x) {
-    uint32_t h, t, o;
+__device__ __forceinline__ uint32_t gn_act_pair(float y0, float y1, int silu) {
     if (BF16) {
-        asm("mul.bf16x2 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(0x3F003F00u));
-        asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(h));
-        asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
-    } else {
-        asm("mul.f16x2 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(0x38003800u));
-        asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
-        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
+        if (silu) {
+            float t0, t1;
+            const float h0 = 0.5f * y0, h1 = 0.5f * y1;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+            y0 = fmaf(h0, t0, h0);
+            y1 = fmaf(h1, t1, h1);
+        }
+        return pack2(y0, y1, 1);
     }
+    const uint32_t x = pack2(y0, y1, 0);
+    if (!silu) return x;
+    uint32_t h, t, o;
+    asm("mul.f16x2 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(0x38003800u));
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+    asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
     return o;
 }
 
@@ -821,8 +831,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float2 f = unpack2(w[j], BF16);
-                        const uint32_t y = pack2(fmaf(f.x, sc[2 * j], sh[2 * j]), fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]), BF16);
-                        w[j] = args.gn_silu ? silu_pair16<BF16>(y) : y;
+                        w[j] = gn_act_pair<BF16>(fmaf(f.x, sc[2 * j], sh[2 * j]), fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]),
+                                                 args.gn_silu);
                     }
                     // padding pixels must be zero AFTER the transform: silu(0 * scale + shift) != 0
                     v[i] = (meta[i] & 16u) ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0, 0, 0, 0);

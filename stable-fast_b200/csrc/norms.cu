@@ -263,19 +263,38 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
     __shared__ float sK[64];
     __shared__ __align__(16) float red[kGnRedFloats];
     pdl_launch_dependents();
+    // the finishing CTA reads gamma / beta at the very end of a dependent chain: pull them into L2 now
+    // (parameters: not produced by the predecessor kernel, so before the dependency wait)
+    if (blockIdx.x == 0 && (int)threadIdx.x * 32 < a.c) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.gamma + threadIdx.x * 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.beta + threadIdx.x * 32));
+    }
     pdl_wait();
     const int img = blockIdx.y;
     const int by = kGnThreads / a.nvec;
     const int tx = threadIdx.x % a.nvec;
     const int ty = threadIdx.x / a.nvec;
-    gn_load_shifts<false>(a, img, sK);
-    __syncthreads();
     GnAcc8 st;
     st.zero();
     if (ty < by) {
+        // every thread fetches the shifts of its own 8 channels itself (one 2-byte load per group run, of a
+        // line the whole group shares): in flight together with the first batch of rows instead of a
+        // load -> barrier -> load chain
         float k[8];
+        {
+            int g_prev = -1;
+            float kv = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
+            for (int i = 0; i < 8; ++i) {
+                const int g = (tx * 8 + i) / a.cpg;
+                if (g != g_prev) {
+                    kv = load1(a.x, (size_t)img * a.hw * a.ldx + g * a.cpg, a.dtype);
+                    g_prev = g;
+                    if (ty == 0 && g * a.cpg >= tx * 8) sK[g] = kv;  // the group's first channel is this thread's
+                }
+                k[i] = kv;
+            }
+        }
         const int row0 = blockIdx.x * a.rows_per_block;
         const int row1 = min(row0 + a.rows_per_block, a.hw);
         const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
@@ -305,19 +324,38 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_ab_kernel(const GnArgs a,
     __shared__ __align__(16) float red[kGnRedFloats];
     __shared__ int s_last;
     pdl_launch_dependents();
+    // the finishing CTA reads gamma / beta at the very end of a dependent chain: pull them into L2 now
+    // (parameters: not produced by the predecessor kernel, so before the dependency wait)
+    if (blockIdx.x == 0 && (int)threadIdx.x * 32 < a.c) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.gamma + threadIdx.x * 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.beta + threadIdx.x * 32));
+    }
     pdl_wait();
     const int img = blockIdx.y;
     const int by = kGnThreads / a.nvec;
     const int tx = threadIdx.x % a.nvec;
     const int ty = threadIdx.x / a.nvec;
-    gn_load_shifts<false>(a, img, sK);
-    __syncthreads();
     GnAcc8 st;
     st.zero();
     if (ty < by) {
+        // every thread fetches the shifts of its own 8 channels itself (one 2-byte load per group run, of a
+        // line the whole group shares): in flight together with the first batch of rows instead of a
+        // load -> barrier -> load chain
         float k[8];
+        {
+            int g_prev = -1;
+            float kv = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) k[i] = sK[(tx * 8 + i) / a.cpg];
+            for (int i = 0; i < 8; ++i) {
+                const int g = (tx * 8 + i) / a.cpg;
+                if (g != g_prev) {
+                    kv = load1(a.x, (size_t)img * a.hw * a.ldx + g * a.cpg, a.dtype);
+                    g_prev = g;
+                    if (ty == 0 && g * a.cpg >= tx * 8) sK[g] = kv;  // the group's first channel is this thread's
+                }
+                k[i] = kv;
+            }
+        }
         const int row0 = blockIdx.x * a.rows_per_block;
         const int row1 = min(row0 + a.rows_per_block, a.hw);
         const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;

@@ -374,6 +374,10 @@ class UNetPlan:
             return True
         if self._pending is not None:
             return False
+        if x.c < 640 and x.rows < 16384:
+            # few channel blocks in a single-wave launch: the halo kernel's longer pipeline fill costs
+            # more than the GroupNorm write + read it saves (measured: 2 x 64^2 x 320 -> +2 us per pair)
+            return False
         return ops.choose_splits(tiles, -(-cout // ops.BN), 9 * x.c // ops.BK, x.rows, cout) == 1
 
     def norm_for_conv(self, name, x: Act, prefix, eps, cout):

@@ -71,10 +71,10 @@ def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     # 61 GroupNorms, 48 LayerNorms, 32 attention calls, 3 upsamples
     # B = 2 tensors fit in shared memory: every GroupNorm that is its own kernel takes the single-launch
     # fused one; the others are FOLDED INTO the 3x3 conv that consumes them (statistics -> (scale, shift),
-    # applied on the conv's operand path): the full-launch convs of the 64^2 level and the first 32^2 one
+    # applied on the conv's operand path): at B = 2 the three wide (960 / 640-channel) full-launch convs of the last up block
     n_folded = names.count("sfb_group_norm_scale_shift")
     assert names.count("sfb_group_norm_fused") + n_folded == 61 and names.count("sfb_group_norm_apply") == 0
-    assert n_folded == (0 if ops.CONV_GN == "0" else 11)
+    assert n_folded == (0 if ops.CONV_GN == "0" else 3)
     # all 48 LayerNorms are folded into the consuming GEMMs (gamma-scaled weights + epilogue)
     assert names.count("sfb_layer_norm") == 0
     gemms = [op.keep[0] for op in plan.all_ops() if op.fn is not None and op.fn.name == "sfb_gemm"]
