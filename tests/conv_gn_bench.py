@@ -101,6 +101,8 @@ def main():
             continue
         row = {"shape": name}
         for label, folded in (("separate", False), ("folded", True)):
+            if os.environ.get("SFB_ONLY") and os.environ["SFB_ONLY"] != label:   # one variant (ncu captures)
+                continue
             try:
                 o1, o2, keep, sync = build(a, folded)
                 us = time_pair(o1, o2, sync)
