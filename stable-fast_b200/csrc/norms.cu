@@ -151,6 +151,34 @@ struct GnAcc8 {
     }
 };
 
+// Compile-time dtype form of GnAcc8::add for the streaming statistics kernel, which is INSTRUCTION-bound
+// with the generic one (ncu: 85 warp instructions per 16-byte load, 41 % issue utilisation at 2 TB/s -- a
+// uniform dtype branch per row, FMUL + FADD where an FFMA does, a 64-bit multiply per address).  fp16: the
+// shift subtraction rides on the half -> float conversion (HADD2.F32 takes two half operands; K is a
+// stored 16-bit value, so x - K is exact in fp32 either way).
+template <int BF16>
+__device__ __forceinline__ void gn_add8_t(GnAcc8& st, const uint4& v, const uint32_t (&kp)[4], const float (&k)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float d0, d1;
+        if (BF16) {
+            const float2 f = unpack2(w[i], 1);
+            d0 = f.x - k[2 * i];
+            d1 = f.y - k[2 * i + 1];
+        } else {
+            const __half2 x = *reinterpret_cast<const __half2*>(&w[i]);
+            const __half2 kk = *reinterpret_cast<const __half2*>(&kp[i]);
+            d0 = __half2float(__low2half(x)) - __half2float(__low2half(kk));
+            d1 = __half2float(__high2half(x)) - __half2float(__high2half(kk));
+        }
+        st.s[2 * i] += d0;
+        st.ss[2 * i] = fmaf(d0, d0, st.ss[2 * i]);
+        st.s[2 * i + 1] += d1;
+        st.ss[2 * i + 1] = fmaf(d1, d1, st.ss[2 * i + 1]);
+    }
+}
+
 // ---- deterministic reductions (no floating-point atomics anywhere: replays are bit-identical) --------
 // kGnThreads x 16 floats of scratch: per-thread moments, then per-channel totals, then slot partials
 constexpr int kGnRedFloats = kGnThreads * 16;
@@ -258,17 +286,12 @@ __device__ __forceinline__ void gn_scale_shift(const GnArgs& a, const float* acc
 // grid (blocks_per_img, n).  Thread (tx = vector column, ty = row slot) keeps per-channel
 // partial sums for its 8 channels over rows ty, ty+BY, ...; one shared-memory atomic per
 // (thread, group run) at the end, then one global atomic per (block, group, moment).
+template <int BF16>
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
     __shared__ float acc[2 * 64];
     __shared__ float sK[64];
     __shared__ __align__(16) float red[kGnRedFloats];
     pdl_launch_dependents();
-    // the finishing CTA reads gamma / beta at the very end of a dependent chain: pull them into L2 now
-    // (parameters: not produced by the predecessor kernel, so before the dependency wait)
-    if (blockIdx.x == 0 && (int)threadIdx.x * 32 < a.c) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.gamma + threadIdx.x * 32));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.beta + threadIdx.x * 32));
-    }
     pdl_wait();
     const int img = blockIdx.y;
     const int by = kGnThreads / a.nvec;
@@ -295,20 +318,23 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
                 k[i] = kv;
             }
         }
+        uint32_t kp[4];  // the shifts again as packed 16-bit pairs (exact: they ARE stored values)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kp[i] = pack2(k[2 * i], k[2 * i + 1], BF16);
         const int row0 = blockIdx.x * a.rows_per_block;
         const int row1 = min(row0 + a.rows_per_block, a.hw);
-        const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
+        // one pointer walked down the rows (no 64-bit multiply per load)
+        const uint16_t* ptr = a.x + ((size_t)img * a.hw + row0 + ty) * a.ldx + tx * 8;
+        const size_t step = (size_t)by * a.ldx;
         constexpr int kU = 8;
-        for (int rb = row0 + ty; rb < row1; rb += by * kU) {
+        for (int rb = row0 + ty; rb < row1; rb += by * kU, ptr += kU * step) {
             uint4 v[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int row = rb + u * by;
-                if (row < row1) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
-            }
+            for (int u = 0; u < kU; ++u)
+                if (rb + u * by < row1) v[u] = *reinterpret_cast<const uint4*>(ptr + u * step);
 #pragma unroll
             for (int u = 0; u < kU; ++u)
-                if (rb + u * by < row1) st.add(v[u], k, a.dtype);
+                if (rb + u * by < row1) gn_add8_t<BF16>(st, v[u], kp, k);
         }
     }
     gn_block_reduce(st, ty < by, tx, ty, by, a, red, acc);
@@ -317,6 +343,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
 
 // gn_stats_kernel + the finish: the last CTA of an image to arrive (integer ticket) sums the image's slots
 // in the fixed order and writes the per-channel (scale, shift) pairs the halo convolution applies.
+template <int BF16>
 __global__ void __launch_bounds__(kGnThreads) gn_stats_ab_kernel(const GnArgs a, float* __restrict__ ab,
                                                                   unsigned* counters) {
     __shared__ float acc[2 * 64];
@@ -356,20 +383,23 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_ab_kernel(const GnArgs a,
                 k[i] = kv;
             }
         }
+        uint32_t kp[4];  // the shifts again as packed 16-bit pairs (exact: they ARE stored values)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kp[i] = pack2(k[2 * i], k[2 * i + 1], BF16);
         const int row0 = blockIdx.x * a.rows_per_block;
         const int row1 = min(row0 + a.rows_per_block, a.hw);
-        const uint16_t* base = a.x + (size_t)img * a.hw * a.ldx + tx * 8;
+        // one pointer walked down the rows (no 64-bit multiply per load)
+        const uint16_t* ptr = a.x + ((size_t)img * a.hw + row0 + ty) * a.ldx + tx * 8;
+        const size_t step = (size_t)by * a.ldx;
         constexpr int kU = 8;
-        for (int rb = row0 + ty; rb < row1; rb += by * kU) {
+        for (int rb = row0 + ty; rb < row1; rb += by * kU, ptr += kU * step) {
             uint4 v[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int row = rb + u * by;
-                if (row < row1) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)row * a.ldx);
-            }
+            for (int u = 0; u < kU; ++u)
+                if (rb + u * by < row1) v[u] = *reinterpret_cast<const uint4*>(ptr + u * step);
 #pragma unroll
             for (int u = 0; u < kU; ++u)
-                if (rb + u * by < row1) st.add(v[u], k, a.dtype);
+                if (rb + u * by < row1) gn_add8_t<BF16>(st, v[u], kp, k);
         }
     }
     gn_block_reduce(st, ty < by, tx, ty, by, a, red, acc);
@@ -703,8 +733,9 @@ extern "C" int sfb_group_norm_stats(const sfb_gn_params* p, sfb_stream_t stream)
     int bpi = 1;
     int rc = make_gn_args(p, a, bpi);
     if (rc) return rc;
-    cudaError_t err = launch_pdl(gn_stats_kernel, dim3(bpi, p->n), dim3(kGnThreads), 0,
-                                 static_cast<cudaStream_t>(stream), a);
+    cudaError_t err = p->dtype == SFB_BF16
+        ? launch_pdl(gn_stats_kernel<1>, dim3(bpi, p->n), dim3(kGnThreads), 0, static_cast<cudaStream_t>(stream), a)
+        : launch_pdl(gn_stats_kernel<0>, dim3(bpi, p->n), dim3(kGnThreads), 0, static_cast<cudaStream_t>(stream), a);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_stats: %s", cudaGetErrorString(err));
     return check_launch("sfb_group_norm_stats");
 }
@@ -716,8 +747,11 @@ extern "C" int sfb_group_norm_scale_shift(const sfb_gn_params* p, float* scale_s
     if (rc) return rc;
     if (!scale_shift || !p->gamma || !p->beta || !p->sync_counter)
         return fail(SFB_ERR_INVALID, "group_norm_scale_shift: null scale_shift / gamma / beta / sync_counter");
-    cudaError_t err = launch_pdl(gn_stats_ab_kernel, dim3(bpi, p->n), dim3(kGnThreads), 0,
-                                 static_cast<cudaStream_t>(stream), a, scale_shift, p->sync_counter);
+    cudaError_t err = p->dtype == SFB_BF16
+        ? launch_pdl(gn_stats_ab_kernel<1>, dim3(bpi, p->n), dim3(kGnThreads), 0, static_cast<cudaStream_t>(stream), a,
+                     scale_shift, p->sync_counter)
+        : launch_pdl(gn_stats_ab_kernel<0>, dim3(bpi, p->n), dim3(kGnThreads), 0, static_cast<cudaStream_t>(stream), a,
+                     scale_shift, p->sync_counter);
     if (err != cudaSuccess) return fail(SFB_ERR_CUDA, "group_norm_scale_shift: %s", cudaGetErrorString(err));
     return check_launch("sfb_group_norm_scale_shift");
 }
