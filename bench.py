@@ -680,12 +680,19 @@ def ncu_traffic(prefix, workload=None):
     command (profiles/rNN_ncu_launch_summary.json, made by tests/summarize_ncu.py; ncu flushes the
     caches before every kernel, so this is cold-cache traffic)."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launch_summary.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launch_summary*.json")))
     if not files:
         return {"traffic": None}
-    d = json.load(open(files[-1]))
-    if workload is not None and d.get("workload") != workload:
+    # the newest committed launch list of THIS workload (one file per workload: ..._summary[_b8].json)
+    d, src = None, None
+    for f in reversed(files):
+        cand = json.load(open(f))
+        if workload is None or cand.get("workload") == workload:
+            d, src = cand, f
+            break
+    if d is None:
         return {"traffic": None, "traffic_note": f"no ncu launch list committed for {workload}"}
+    files = [src]
     n = b = 0
     for name, f in d.get("families", {}).items():
         if name.startswith(prefix) and "dram_bytes_per_launch" in f:
