@@ -98,6 +98,40 @@ def test_sd15_plan_matches_survey_kernel_counts_and_flops():
     assert sum(1 for k in plan._bufs if k[0].startswith("cat_")) == 12
 
 
+@pytest.mark.parametrize("cfg_name,batch,size", [("sd15_config", 2, 64), ("sd15_config", 8, 64),
+                                                 ("sd15_config", 8, 128), ("sdxl_config", 8, 128)])
+def test_folded_group_norms_feed_exactly_the_conv_that_applies_them(cfg_name, batch, size):
+    """Every GroupNorm folded into a conv is a (statistics -> scale/shift) launch whose buffer is consumed by
+    the very next SFB_A_CONV3X3_GN conv of the main stream, over the same raw tensor; buffers are not shared
+    between GroupNorm sites; the conv is never a split-K launch (its producer's partials would have nobody to
+    finish them) and nothing is left pending in front of it."""
+    from sfast_b200.plan import _ForkOp, _JoinOp
+    plan = _dry_plan(getattr(uo, cfg_name)(), batch, size, size)
+    main = [op for op in plan.ops if not isinstance(op, (_ForkOp, _JoinOp))]
+    seen, n = set(), 0
+    for i, op in enumerate(main):
+        if op.fn is None or op.fn.name != "sfb_group_norm_scale_shift":
+            continue
+        n += 1
+        gp, ab = op.keep[0], op.keep[-1]
+        assert id(ab) not in seen and tuple(ab.shape) == (gp.n, gp.c, 2)
+        seen.add(id(ab))
+        nxt = next(o for o in main[i + 1:] if o.fn is not None and o.fn.name == "sfb_gemm")
+        g = nxt.keep[0]
+        assert g.a_mode == _lib.A_CONV3X3_GN and any(k is ab for k in nxt.keep[-3]), (op.name, nxt.name)
+        assert (g.img_n, g.img_h * g.img_w, g.cin) == (gp.n, gp.hw, gp.c) and g.gn_silu == 1
+        assert g.splits == 1 and g.defer_finish == 0 and g.cta_pair == 1
+        assert (g.img_n * -(-g.img_h // 16) * (g.img_w // 8)) % 2 == 0
+    n_conv = sum(1 for o in main if o.fn is not None and o.fn.name == "sfb_gemm"
+                 and o.keep[0].a_mode == _lib.A_CONV3X3_GN)
+    assert n == n_conv and (n > 0 or ops.CONV_GN == "0")
+    # the kernels that were replaced are gone, not duplicated: one GroupNorm launch set per site
+    spec_gn = sum(2 for _ in plan.spec.all_resnets()) + 1 + sum(
+        1 for blk in plan.spec.down + [plan.spec.mid] + plan.spec.up for t in blk.attentions if t is not None)
+    names = [o.fn.name for o in plan.all_ops() if o.fn is not None]
+    assert n + names.count("sfb_group_norm_fused") + names.count("sfb_group_norm_stats") == spec_gn
+
+
 def _check_deferred_finishes(plan):
     from sfast_b200.plan import _ForkOp, _JoinOp
     main = [op for op in plan.ops if not isinstance(op, (_ForkOp, _JoinOp))]
