@@ -388,6 +388,7 @@ class UNetPlan:
             return self.group_norm(name, x, prefix, True, eps), None
         idx = self._gn_count
         self._gn_count += 1
+        assert x.n <= self.gn_tickets.shape[1], "one ticket per image of the GroupNorm"
         ab = self.buf(f"gn_scale_shift.{idx}", (x.n, x.c, 2), torch.float32)
         self._emit(ops.gn_scale_shift_op(name, self.lib_or_dry(), x=x, gamma=self.w.f32(prefix + ".weight"),
                                          beta=self.w.f32(prefix + ".bias"), stats=self.gn_stats[idx],

@@ -132,6 +132,45 @@ def test_folded_group_norms_feed_exactly_the_conv_that_applies_them(cfg_name, ba
     assert n + names.count("sfb_group_norm_fused") + names.count("sfb_group_norm_stats") == spec_gn
 
 
+def test_halo_conv_shared_memory_index_algebra():
+    """The address algebra of the folded-GroupNorm conv (gemm_tc.cu, HALO branch), emulated: TMA's
+    128-byte swizzle of the raw [18 x 10]-pixel halo tile, the transform threads' read addresses, their
+    writes into the three column-shifted copies, and the UMMA K-major SWIZZLE_128B read of tap (dy, dx) as
+    "copy dx advanced by dy 1024-byte atoms" must deliver halo pixel (y + dy, x + dx) as row m = 8 y + x of
+    the A tile, for every tap, row and 16-byte channel chunk."""
+    HR, HC, ABUF = 18, 10, 18 * 1024
+
+    def swz(addr):  # chunk bits [4:7) ^= row bits [7:10): what TMA writes and the tensor core reads
+        return addr ^ (((addr >> 7) & 7) << 4)
+
+    raw = {swz((hy * HC + hx) * 128 + c * 16): (hy, hx, c) for hy in range(HR) for hx in range(HC) for c in range(8)}
+    copies = {}
+    for et in range(256):           # the 8 epilogue warps
+        c, p0 = et & 7, et >> 3
+        for i in range(6):
+            p = p0 + 32 * i
+            if p >= HR * HC:
+                continue
+            hy, hx = divmod(p, HC)
+            assert raw[p * 128 + ((c ^ (p & 7)) << 4)] == (hy, hx, c)        # roff[i]
+            for dx in range(3):
+                x = hx - dx
+                if 0 <= x < 8:
+                    addr = dx * ABUF + hy * 1024 + x * 128 + ((c ^ x) << 4)  # the STS address
+                    assert addr not in copies
+                    copies[addr] = (hy, hx, c)
+    assert len(copies) == 3 * HR * 8 * 8                                     # every slot written exactly once
+    for dy in range(3):
+        for dx in range(3):
+            start = dx * ABUF + dy * 1024                                    # descriptor start, SBO = 1024
+            assert start % 1024 == 0
+            for m in range(128):
+                y, x = divmod(m, 8)
+                for k in range(8):
+                    got = copies[swz(start + (m // 8) * 1024 + (m % 8) * 128 + k * 16)]
+                    assert got == (y + dy, x + dx, k), (dy, dx, m, k, got)
+
+
 def _check_deferred_finishes(plan):
     from sfast_b200.plan import _ForkOp, _JoinOp
     main = [op for op in plan.ops if not isinstance(op, (_ForkOp, _JoinOp))]
