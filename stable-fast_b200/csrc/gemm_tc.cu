@@ -622,8 +622,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
             }
-        } else
-        if (lane == 0) {
+        } else if (lane == 0) {
             const ATile at = a_tile_coords(args, m_tile);
             const int b_ntile = at.b_nbase + n_tile;
             auto load_b = [&](int i) {
@@ -718,8 +717,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 else umma_commit(tmem_full_bar);
                 SFB_STAMP(4);
             }
-        } else
-        if (lane == 0 && leader) {
+        } else if (lane == 0 && leader) {
             const uint32_t idesc = umma_idesc_f16(BM * CG, BN, BF16 != 0);
             for (int i = 0; i < nkb; ++i) {
                 const int stage = i % STAGES;
@@ -1860,7 +1858,7 @@ extern "C" int sfb_gemm(const sfb_gemm_params* p, sfb_stream_t stream_) {
             rc = e.dtype == SFB_BF16 ? launch_gemm_t<3, 1, 2, 1>(ta, tb, a, pgrid, stream)
                                      : launch_gemm_t<3, 0, 2, 1>(ta, tb, a, pgrid, stream);
         else
-        rc = deep ? launch_gemm<8, 2>(ta, tb, a, pgrid, stream) : launch_gemm<4, 2>(ta, tb, a, pgrid, stream);
+            rc = deep ? launch_gemm<8, 2>(ta, tb, a, pgrid, stream) : launch_gemm<4, 2>(ta, tb, a, pgrid, stream);
     } else {
         rc = deep ? launch_gemm<6, 1>(ta, tb, a, grid, stream) : launch_gemm<3, 1>(ta, tb, a, grid, stream);
     }
