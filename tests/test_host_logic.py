@@ -451,6 +451,7 @@ def test_host_validation_really_rejects_bad_geometry():
     (uo.sd15_config, 16, 64, 64), (uo.sd15_config, 1, 128, 128), (uo.sd15_config, 2, 96, 96),
     (uo.sd15_config, 1, 64, 96), (uo.sdxl_config, 2, 128, 128), (uo.sdxl_config, 1, 104, 152),
     (uo.tiny_config, 2, 32, 32), (uo.tiny_config, 1, 24, 40),
+    (uo.sd15_config, 8, 64, 64), (uo.sd15_config, 8, 128, 128), (uo.sdxl_config, 8, 128, 128),  # the bench shapes
 ])
 def test_every_launch_of_a_plan_passes_host_validation(cfgf, batch, h, w):
     plan = _dry_plan(cfgf(), batch, h, w)
