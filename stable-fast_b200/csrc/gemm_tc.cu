@@ -25,6 +25,13 @@
 // (c, w0+kw-1, h0*stride+kh-1, n0) is exactly the im2col slice, and TMA's out-of-bounds zero fill
 // is the convolution's zero padding.  No im2col buffer, no index tables.
 //
+// SFB_A_CONV3X3_GN (template parameter HALO) folds the GroupNorm(+SiLU) in front of a 3x3 conv into this
+// kernel's operand path: ONE raw halo tile per 64-channel block by TMA, normalised + activated once per
+// element by the epilogue warps (idle during the main loop) into three column-shifted swizzled copies,
+// nine taps = shifted views of those copies (see GemmSmem and DESIGN.md section 4.2).  It replaces the
+// reference's separate sfast_triton::group_norm_silu launch (/root/reference/src/sfast/jit/passes/
+// triton_passes.py:68-88, src/sfast/triton/ops/group_norm.py:272-320) in front of the conv.
+//
 // Replaces: cudnn_convolution_bias(_add) (/root/reference/src/sfast/csrc/operators/cudnn/
 // cudnn_convolution_impl.cc:890-987), cublas_lowp_linear(_add) (csrc/operators/cublas/
 // cublas_gemm.cpp:798-853,900-948) and cutlass_linear_geglu (csrc/operators/cutlass/
